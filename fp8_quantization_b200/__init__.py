@@ -1,0 +1,15 @@
+"""fp8_quantization_b200 -- B200-native FP8 fake-quantisation engine.
+
+Drop-in for the hot path of Qualcomm-AI-research/FP8-quantization: ``FPQuantizer`` and the range
+estimators, wired through the reference's ``QuantizationManager`` / hijacker module API.  All
+arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in ``include/fp8fq.h``
+(``libfp8fq.so``); there is no CPU or eager-PyTorch fallback.
+"""
+from ._lib import Fp8fqError, LIB_PATH, lib  # noqa: F401
+from . import ops  # noqa: F401
+from .quantizers import FPQuantizer, QuantizerBase, QuantizerNotInitializedError  # noqa: F401
+from .range_estimators import (AllMinMaxEstimator, CurrentMinMaxEstimator, FP_MSE_Estimator,  # noqa: F401
+                               RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator)
+from .quantization_manager import QMethods, Qstates, QuantizationManager  # noqa: F401
+
+__version__ = "0.1.0"

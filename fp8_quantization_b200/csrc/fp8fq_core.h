@@ -1,0 +1,275 @@
+// fp8fq_core.h -- the arithmetic of the FP8 fake-quantiser, shared by the CUDA kernels and by a
+// host build used for CPU-side logic tests (tests/host_emul).  Everything here is a pure function.
+//
+// Reference being reproduced: quantize_to_fp8_ste_MM, quantization/quantizers/fp8_quantizer.py:91-133
+//
+//   M    = clamp(round(mantissa_bits), 1, n_bits - sign_bits)                        (:105)
+//   E    = n_bits - sign_bits - M                                                    (:106)
+//   bias = 2^E - log2(maxval) + log2(2 - 2^-M) - 1                                   (:110)
+//   xc   = min(max(x, minval), maxval),  minval = -maxval | 0                        (:112-113)
+//   e    = clamp_min(floor(log2|xc| + bias), 1)                                      (:128)
+//   s    = 2^(e - M - bias)                                                          (:130)
+//   y    = round_half_even(xc / s) * s                                               (:132)
+//
+// Design: e and s depend on x only through which of K = max(1, 2^E - 1) intervals |xc| falls in.
+// A prologue ("prepare") evaluates, with the SAME fp32 operations and the same libm entry points the
+// reference's ATen kernels call (log2f, powf; no FMA contraction across the reference's op
+// boundaries), the bias, the K scales and the K-1 switching points of (:128), found by bisection on
+// the float ordering.  The streaming kernel then needs per element: two NaN-propagating min/max, a
+// table lookup, one multiply by the pre-computed reciprocal with an exactness guard that falls back
+// to IEEE division near rounding ties, one round-to-nearest-even and one multiply.  No log2, no pow,
+// no division on the fast path -- and bit-identical results to evaluating (:128)-(:132) directly.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define FQ_HD __host__ __device__ __forceinline__
+#else
+#define FQ_HD inline
+#endif
+
+namespace fp8fq {
+
+constexpr int kHdr = 8;          // header floats per channel
+constexpr int kMaxE = 7;         // at most 127 exponent codes
+constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
+constexpr int kMaxK = (1 << kMaxE) - 1;
+
+enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6 };
+enum : int { FLAG_IRREGULAR = 1 };
+
+FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
+FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
+FQ_HD int table_stride(int K) { return kHdr + k_pad(K) + 2 * (K + 1); }
+FQ_HD int off_thr(int) { return kHdr; }
+FQ_HD int off_sr(int K) { return kHdr + k_pad(K); }
+
+FQ_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+FQ_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// ---- fp32 primitives with pinned rounding (never fused) ------------------------------------
+FQ_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+FQ_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+FQ_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+FQ_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  volatile float r = a / b; return r;
+#endif
+}
+FQ_HD float rcp_rn(float a) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(a);
+#else
+  volatile float r = 1.0f / a; return r;
+#endif
+}
+// torch.max / torch.min semantics: NaN in either operand propagates.
+FQ_HD float max_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+#else
+  if (a != a) return a; if (b != b) return b; return a > b ? a : b;
+#endif
+}
+FQ_HD float min_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+#else
+  if (a != a) return a; if (b != b) return b; return a < b ? a : b;
+#endif
+}
+FQ_HD bool is_normal_pos(float f) {
+  uint32_t u = f2u(f);
+  return u >= 0x00800000u && u < 0x7f800000u;
+}
+
+// ---- format split (:105-106); host side --------------------------------------------------------
+inline int format_split(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
+  if (!(mantissa_bits == mantissa_bits)) return -1;
+  float r = nearbyintf(mantissa_bits);  // torch.round: half to even
+  float hi = (float)(n_bits - sign_bits);
+  if (hi < 1.0f) return -1;             // torch.clamp with min > max returns max; not a valid format
+  if (r < 1.0f) r = 1.0f;
+  if (r > hi) r = hi;
+  int m = (int)r, e = n_bits - sign_bits - m;
+  if (e > kMaxE || m > kMaxM) return -2;
+  *M = m; *E = e; *K = k_codes(e);
+  return 0;
+}
+
+// ---- prologue pieces ---------------------------------------------------------------------------
+// bias (:110), evaluated left to right like the Python expression.
+FQ_HD float ref_bias(float maxval, int M, int E) {
+  float p2E = powf(2.0f, (float)E);           // 2**E      (E is a float tensor in the reference)
+  float t = sub_rn(p2E, log2f(maxval));       // - log2(maxval)
+  float p2nM = powf(2.0f, -(float)M);         // 2 ** (-M)
+  float l2 = log2f(sub_rn(2.0f, p2nM));       // log2(2 - 2**-M)
+  t = add_rn(t, l2);
+  return sub_rn(t, 1.0f);
+}
+// scale of exponent code e (:130): 2.0 ** ((e - M) - bias)
+FQ_HD float ref_scale(int e, int M, float bias) {
+  float y = sub_rn(sub_rn((float)e, (float)M), bias);
+  return powf(2.0f, y);
+}
+// the reference's exponent code before the clamp (:128) reaches k?
+FQ_HD bool ref_code_ge(float a, float bias, float k) {
+  float v = floorf(add_rn(log2f(a), bias));
+  return v >= k;  // NaN -> false
+}
+// Smallest positive float a with ref_code_ge(a, bias, k), by bisection on the float ordering
+// (positive floats order like their bit patterns).  +inf if there is none.
+FQ_HD float find_threshold(float bias, int k) {
+  const float kf = (float)k;
+  uint32_t lo = 0u;            // invariant: code(lo) < k   (a = +0 -> log2 = -inf)
+  uint32_t hi = 0x7f800000u;   // invariant: code(hi) >= k, or hi == +inf
+  if (!ref_code_ge(u2f(hi), bias, kf)) return u2f(0x7f800000u);
+  if (ref_code_ge(u2f(1u), bias, kf)) return u2f(1u);
+  lo = 1u;
+  // narrow bracket around the analytic switching point 2^(k - bias) first
+  float g = exp2f(sub_rn(kf, bias));
+  if (is_normal_pos(g)) {
+    uint32_t gi = f2u(g);
+    uint32_t span = 1u << 12;
+    uint32_t l2 = gi > span + 1u ? gi - span : 1u;
+    uint32_t h2 = gi + span < 0x7f800000u ? gi + span : 0x7f800000u;
+    if (!ref_code_ge(u2f(l2), bias, kf) && l2 > lo) lo = l2;
+    if (ref_code_ge(u2f(h2), bias, kf) && h2 < hi) hi = h2;
+  }
+  while (hi - lo > 1u) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (ref_code_ge(u2f(mid), bias, kf)) hi = mid; else lo = mid;
+  }
+  // guard against a locally non-monotone log2f: take the lowest switching point within 4 ulps
+  for (uint32_t t = 1; t <= 4u && hi > t; ++t)
+    if (ref_code_ge(u2f(hi - t), bias, kf)) { hi -= t; t = 0; }
+  return u2f(hi);
+}
+
+// Writes header + thr/sr entries of one channel given bias and the already computed thresholds
+// T[k] (k = 2..K, T[k] stored at thr_in[k]) -- used by the host build; the device does the same
+// work spread over a CTA (see prepare kernel).
+FQ_HD float tie_guard(int M) {
+  // |xc/s| <= 2^(M+1)(1+eps); multiplying by RN(1/s) instead of dividing by s perturbs the quotient
+  // by < 1.6 * 2^-23 relative.  If the fast quotient is further than this from a .5 tie, rounding
+  // it gives the same integer as rounding the IEEE quotient.  2^(M-20) >= 2.6x that bound.
+  return 0.5f - ldexpf(1.0f, M - 20);
+}
+
+// One channel's table is built in three steps so that a CTA can spread step 2 over its threads
+// while the host emulation (tests/host_emul) runs the very same code serially.
+// step 1 (one thread): header
+FQ_HD float prep_header(float* tab, float mv, int M, int E, int K, int sign_bits) {
+  const float bias = ref_bias(mv, M, E);
+  float* thr = tab + kHdr;
+  tab[H_HI] = mv;
+  tab[H_LO] = sign_bits ? -mv : 0.0f;  // (:112) -maxval or zeros_like(maxval)
+  tab[H_BIAS] = bias;
+  tab[H_K] = u2f((uint32_t)K);
+  tab[H_GUARD] = tie_guard(M);
+  tab[7] = 0.0f;
+  thr[0] = u2f(0x7f800000u);
+  for (int j = K; j < k_pad(K); ++j) thr[j] = u2f(0x7f800000u);
+  return bias;
+}
+// step 2 (any thread, k = 1..K): scale pair of code k and the threshold at which code k starts
+FQ_HD void prep_entry(float* tab, int k, int M, int K, float bias) {
+  float* thr = tab + kHdr;
+  float* sr = tab + off_sr(K);
+  const float s = ref_scale(k, M, bias);
+  float rs = rcp_rn(s);
+  if (!(is_normal_pos(s) && is_normal_pos(rs))) rs = u2f(0x7fc00000u);  // forces the exact-division path
+  sr[2 * k] = s;
+  sr[2 * k + 1] = rs;
+  if (k == 1) { sr[0] = s; sr[1] = rs; }
+  if (k >= 2) thr[k - 1] = find_threshold(bias, k);
+}
+// step 3 (one thread, after all entries are visible): bucket base + regularity check
+FQ_HD void prep_finish(float* tab, int K, float mv) {
+  const float* thr = tab + kHdr;
+  int flags = 0;
+  uint32_t base = 0x00800000u;
+  if (K >= 2) {
+    const float t2 = thr[1];
+    const uint32_t t2i = f2u(t2);
+    if (is_normal_pos(t2) && t2i > 0x00C00000u + 0x00800000u) {
+      base = t2i - 0x00C00000u;  // 1.5 binades below T_2 on the float bit-pattern axis
+      for (int k = 2; k <= K; ++k) {
+        const uint32_t ti = f2u(thr[k - 1]);
+        if (!is_normal_pos(thr[k - 1]) || ti < base || (int)((ti - base) >> 23) != k - 1) flags |= FLAG_IRREGULAR;
+      }
+      // the largest clamped input must not index past entry K
+      const float hi = fabsf(mv);
+      if (is_normal_pos(hi) && f2u(hi) >= base && (int)((f2u(hi) - base) >> 23) > K) flags |= FLAG_IRREGULAR;
+    } else {
+      flags |= FLAG_IRREGULAR;
+    }
+  }
+  tab[H_BASE] = u2f(base);
+  tab[H_FLAGS] = u2f((uint32_t)flags);
+}
+
+// ---- element path ------------------------------------------------------------------------------
+// Generic lookup of e' (index into the (scale, rcp) pairs) for a = |xc|, from a channel table.
+template <typename Ld>
+FQ_HD int lookup_code(float a, const float* tab, int K, uint32_t base, bool irregular, Ld ld) {
+  const float* thr = tab + kHdr;
+  if (!irregular) {
+    // bucket j = binade of |xc| relative to `base` (a float 1.5 binades below T_2); bucket j
+    // (1 <= j <= K-1) contains exactly the threshold T_{j+1}.
+    float ac = fmaxf(a, u2f(base));              // non-NaN max: NaN -> base, j = 0
+    int j = (int)((f2u(ac) - base) >> 23);
+    j = j < K ? j : K;
+    return j + (a >= ld(thr + j) ? 1 : 0);
+  }
+  int e = 1;
+  for (int k = 2; k <= K; ++k) e += (a >= ld(thr + (k - 1)) ? 1 : 0);
+  return e;
+}
+
+// Quantise xc (already clamped) with the selected (s, rs).  Returns y; *q_out = round(xc / s).
+FQ_HD float quant_core(float xc, float s, float rs, float guard, float* q_out) {
+  float r = mul_rn(xc, rs);
+  float q = nearbyintf(r);
+  float d = r - q;
+  if (!(fabsf(d) < guard)) q = nearbyintf(div_rn(xc, s));  // near a tie, or rs unusable (NaN)
+  *q_out = q;
+  return mul_rn(q, s);
+}
+
+}  // namespace fp8fq

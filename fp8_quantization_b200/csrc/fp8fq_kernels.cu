@@ -1,0 +1,1005 @@
+// fp8fq_kernels.cu -- sm_100a kernels + C ABI of libfp8fq.so (see include/fp8fq.h).
+//
+// Kernel families (DESIGN.md has the roofline of each):
+//   prepare_kernel        per-channel prologue of quantize_to_fp8_ste_MM (fp8_quantizer.py:105-113,128,130)
+//   fq_stream_kernel      K1: streaming fake-quant, optionally fused with BN+act or residual-add+act
+//                         (fp8_quantizer.py:113-132; quantized_folded_bn.py:39-55; resnet_quantized.py:43-46)
+//   fq_rows_kernel        K1 per-channel (weights, channel = dim 0)
+//   minmax_*_kernel       K2a: NaN-propagating min/max + estimator update (+ fused prologue)
+//                         (range_estimators.py:61-125)
+//   mse_grid_kernel       K2b: FP_MSE_Estimator's candidate loop (range_estimators.py:337-347)
+//
+// All HBM-bound kernels use 128-bit coalesced global accesses, UNROLL independent loads in flight per
+// thread, tables staged in shared memory / registers, and persistent grids sized to SMs x occupancy.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/fp8fq.h"
+#include "fp8fq_core.h"
+
+using namespace fp8fq;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+struct DevInfo {
+  int sms = 0;
+  bool ok = false;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!g_dev[dev].ok) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_dev[dev].sms = n;
+    g_dev[dev].ok = true;
+  }
+  return g_dev[dev].sms;
+}
+
+inline int launch_status() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? FP8FQ_OK : (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector access helpers
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+struct Pack;
+template <>
+struct Pack<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Pack<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldcs(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+template <int VEC>
+struct IPack;
+template <>
+struct IPack<4> {
+  int32_t v[4];
+  __device__ __forceinline__ void store(int32_t* p) const {
+    *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct IPack<1> {
+  int32_t v[1];
+  __device__ __forceinline__ void store(int32_t* p) const { *p = v[0]; }
+};
+
+// exact unsigned division by a runtime-constant divisor (n < 2^32): q = (umulhi(n, m) + n) >> s
+struct FastDiv {
+  uint32_t m, s, d;
+};
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d == 1) { f.m = 0; f.s = 0; return f; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;  // ceil(log2 d)
+  uint64_t m = ((1ull << 32) * ((1ull << l) - d)) / d + 1;
+  f.m = (uint32_t)m;
+  f.s = l;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  uint64_t t = (uint64_t)__umulhi(n, f.m) + n;
+  return (uint32_t)(t >> f.s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue: one CTA builds the table of one channel
+// ------------------------------------------------------------------------------------------------
+__device__ void prepare_channel(float mv, int M, int E, int K, int sign_bits, float* tab) {
+  __shared__ float s_bias;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bias = prep_header(tab, mv, M, E, K, sign_bits);
+  __syncthreads();
+  const float bias = s_bias;
+  for (int k = tid + 1; k <= K; k += blockDim.x) prep_entry(tab, k, M, K, bias);
+  __syncthreads();
+  if (tid == 0) prep_finish(tab, K, mv);
+  __syncthreads();
+}
+
+// set_quant_range (fp8_quantizer.py:236-237): maxval = | max(|x_min|, x_max) |
+__device__ __forceinline__ float range_to_maxval(float xmin, float xmax) {
+  return fabsf(max_nan(fabsf(xmin), xmax));
+}
+
+__global__ void prepare_kernel(const float* __restrict__ maxval, const float* __restrict__ xmin,
+                               const float* __restrict__ xmax, float* __restrict__ maxval_out, int64_t C,
+                               int M, int E, int K, int sign_bits, float* __restrict__ table) {
+  const int stride = table_stride(K);
+  for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
+    float mv;
+    if (xmin != nullptr) {
+      mv = range_to_maxval(xmin[c], xmax[c]);
+      if (maxval_out != nullptr && threadIdx.x == 0) maxval_out[c] = mv;
+    } else {
+      mv = maxval[c];
+    }
+    prepare_channel(mv, M, E, K, sign_bits, table + c * stride);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: streaming fake-quant
+// ------------------------------------------------------------------------------------------------
+enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2 };
+
+struct StreamArgs {
+  const float* x;
+  const float* x2;      // PRE_ADD: second addend
+  float* y;
+  int32_t* codes;
+  const float* table;   // per-tensor table
+  int64_t n;
+  int K;
+  int act;
+  const float* bn_scale;
+  const float* bn_shift;
+  FastDiv hw_div;       // PRE_AFFINE: row = idx / hw
+  FastDiv c_div;        //             c   = row % Cbn
+  int bn_mode;
+};
+
+struct RegTab {  // K <= 3: everything in registers
+  float t2, t3, s1, s2, s3, r1, r2, r3;
+};
+
+template <int KMODE>
+struct ElemCtx {
+  float hi, lo, guard;
+  RegTab rt;            // KMODE 0
+  const float* stab;    // KMODE 1: table in shared memory
+  int K;
+  uint32_t base;
+  bool irregular;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  // torch.relu / relu6 propagate NaN (clamp semantics)
+  if (act == FP8FQ_ACT_RELU) return max_nan(v, 0.0f);
+  if (act == FP8FQ_ACT_RELU6) return min_nan(max_nan(v, 0.0f), 6.0f);
+  return v;
+}
+
+template <int KMODE, bool CODES>
+__device__ __forceinline__ float quant_elem(float v, const ElemCtx<KMODE>& c, int32_t* code) {
+  const float xc = min_nan(max_nan(v, c.lo), c.hi);
+  const float a = fabsf(xc);
+  float s, rs;
+  int e;
+  if (KMODE == 0) {
+    const bool p2 = a >= c.rt.t2, p3 = a >= c.rt.t3;
+    s = p3 ? c.rt.s3 : (p2 ? c.rt.s2 : c.rt.s1);
+    rs = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
+    e = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+  } else {
+    e = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
+    const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * e);
+    s = p.x;
+    rs = p.y;
+    e = e < 1 ? 1 : e;
+  }
+  float q;
+  const float y = quant_core(xc, s, rs, c.guard, &q);
+  if (CODES) {
+    if (y != y) *code = 0x7fffffff;
+    else *code = (int32_t)((f2u(y) & 0x80000000u) | ((uint32_t)e << 16) | (uint32_t)fabsf(q));
+  }
+  return y;
+}
+
+template <int KMODE>
+__device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, int K, float* smem) {
+  const int stride = table_stride(K);
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) smem[i] = gtab[i];
+  __syncthreads();
+  c.hi = smem[H_HI];
+  c.lo = smem[H_LO];
+  c.guard = smem[H_GUARD];
+  c.K = K;
+  c.base = f2u(smem[H_BASE]);
+  c.irregular = (f2u(smem[H_FLAGS]) & FLAG_IRREGULAR) != 0;
+  c.stab = smem;
+  if (KMODE == 0) {
+    const float inf = __int_as_float(0x7f800000);
+    const float* thr = smem + kHdr;
+    const float* sr = smem + off_sr(K);
+    c.rt.t2 = K >= 2 ? thr[1] : inf;
+    c.rt.t3 = K >= 3 ? thr[2] : inf;
+    c.rt.s1 = sr[2]; c.rt.r1 = sr[3];
+    c.rt.s2 = K >= 2 ? sr[4] : sr[2]; c.rt.r2 = K >= 2 ? sr[5] : sr[3];
+    c.rt.s3 = K >= 3 ? sr[6] : c.rt.s2; c.rt.r3 = K >= 3 ? sr[7] : c.rt.r2;
+  }
+}
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+template <int KMODE, int PRE, int VEC, bool CODES>
+__global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a) {
+  __shared__ __align__(16) float s_tab[kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1)];
+  ElemCtx<KMODE> ctx;
+  load_ctx<KMODE>(ctx, a.table, a.K, s_tab);
+
+  constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
+  const int64_t nvec_elems = a.n - (a.n % VEC);
+  const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * kTile + (int64_t)threadIdx.x * VEC;
+    Pack<VEC> in[kUnroll], in2[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads * VEC;
+      ok[u] = i < nvec_elems;
+      if (ok[u]) {
+        in[u].load(a.x + i);
+        if (PRE == PRE_ADD) in2[u].load(a.x2 + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = base + (int64_t)u * kThreads * VEC;
+      float sc = 1.0f, sh = 0.0f;
+      if (PRE == PRE_AFFINE) {
+        // all VEC lanes of a vector share a row because hw % VEC == 0 (checked by the launcher)
+        const uint32_t row = fdiv((uint32_t)i, a.hw_div);
+        const uint32_t ch = row - fdiv(row, a.c_div) * a.c_div.d;
+        sc = __ldg(a.bn_scale + ch);
+        sh = __ldg(a.bn_shift + ch);
+      }
+      Pack<VEC> out;
+      IPack<VEC> cd;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float v = in[u].v[k];
+        if (PRE == PRE_AFFINE) {
+          v = a.bn_mode == 0 ? fmaf(v, sc, sh) : add_rn(mul_rn(v, sc), sh);
+          v = apply_act(v, a.act);
+        } else if (PRE == PRE_ADD) {
+          v = apply_act(add_rn(v, in2[u].v[k]), a.act);
+        }
+        out.v[k] = quant_elem<KMODE, CODES>(v, ctx, &cd.v[k]);
+      }
+      out.store(a.y + i);
+      if (CODES) cd.store(a.codes + i);
+    }
+  }
+  // scalar tail (n % VEC elements), VEC == 4 only
+  if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {
+    const int64_t i = nvec_elems + threadIdx.x;
+    float v = a.x[i];
+    if (PRE == PRE_AFFINE) {
+      const uint32_t row = fdiv((uint32_t)i, a.hw_div);
+      const uint32_t ch = row - fdiv(row, a.c_div) * a.c_div.d;
+      const float sc = a.bn_scale[ch], sh = a.bn_shift[ch];
+      v = a.bn_mode == 0 ? fmaf(v, sc, sh) : add_rn(mul_rn(v, sc), sh);
+      v = apply_act(v, a.act);
+    } else if (PRE == PRE_ADD) {
+      v = apply_act(add_rn(v, a.x2[i]), a.act);
+    }
+    int32_t cd;
+    a.y[i] = quant_elem<KMODE, CODES>(v, ctx, &cd);
+    if (CODES) a.codes[i] = cd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 per-channel: x is [C, inner]; one CTA per (row, chunk) work item, row table staged in smem
+// ------------------------------------------------------------------------------------------------
+struct RowsArgs {
+  const float* x;
+  float* y;
+  int32_t* codes;
+  const float* table;
+  int64_t C, inner;
+  int64_t chunks_per_row;   // ceil(inner / chunk)
+  int64_t chunk;            // elements per work item (multiple of 4)
+  int K;
+  int vec_ok;               // inner % 4 == 0 and pointers 16B aligned
+};
+
+template <int KMODE, bool CODES>
+__global__ void __launch_bounds__(128) fq_rows_kernel(const RowsArgs a) {
+  __shared__ __align__(16) float s_tab[kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1)];
+  const int stride = table_stride(a.K);
+  const int64_t nwork = a.C * a.chunks_per_row;
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t row = w / a.chunks_per_row;
+    const int64_t ck = w - row * a.chunks_per_row;
+    __syncthreads();  // previous iteration done with s_tab
+    ElemCtx<KMODE> ctx;
+    load_ctx<KMODE>(ctx, a.table + row * stride, a.K, s_tab);
+    const int64_t beg = ck * a.chunk;
+    const int64_t end = (beg + a.chunk < a.inner) ? beg + a.chunk : a.inner;
+    const float* xr = a.x + row * a.inner;
+    float* yr = a.y + row * a.inner;
+    int32_t* cr = CODES ? a.codes + row * a.inner : nullptr;
+    if (a.vec_ok) {
+      for (int64_t i = beg + (int64_t)threadIdx.x * 4; i < end; i += (int64_t)blockDim.x * 4) {
+        Pack<4> in, out;
+        IPack<4> cd;
+        in.load(xr + i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out.v[k] = quant_elem<KMODE, CODES>(in.v[k], ctx, &cd.v[k]);
+        out.store(yr + i);
+        if (CODES) cd.store(cr + i);
+      }
+    } else {
+      for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        int32_t cd;
+        yr[i] = quant_elem<KMODE, CODES>(xr[i], ctx, &cd);
+        if (CODES) cr[i] = cd;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: min/max
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_minmax(float& mn, float& mx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+}
+// result valid in thread 0 (all threads must call)
+__device__ __forceinline__ void block_minmax(float& mn, float& mx) {
+  __shared__ float s_mn[32], s_mx[32];
+  warp_minmax(mn, mx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) { s_mn[wid] = mn; s_mx[wid] = mx; }
+  __syncthreads();
+  if (wid == 0) {
+    mn = lane < nw ? s_mn[lane] : __int_as_float(0x7f800000);
+    mx = lane < nw ? s_mx[lane] : __int_as_float(0xff800000);
+    warp_minmax(mn, mx);
+  }
+}
+
+struct EstArgs {
+  float* cur_min;
+  float* cur_max;
+  int est_mode;
+  int initialized;
+  float w_new;   // (float)(1 - momentum), the Python double expression rounded to fp32
+  float w_old;   // (float)momentum
+  // optional fused set_quant_range + prologue
+  float* maxval_out;
+  float* table;  // nullptr -> no fused prologue
+  int M, E, K, sign_bits;
+};
+
+// estimator update rule for one channel; returns the updated (min, max)
+__device__ __forceinline__ void est_update(const EstArgs& e, int64_t c, float& mn, float& mx) {
+  if (e.initialized && e.est_mode == FP8FQ_EST_ALL) {           // range_estimators.py:96-98
+    mn = min_nan(e.cur_min[c], mn);
+    mx = max_nan(e.cur_max[c], mx);
+  } else if (e.initialized && e.est_mode == FP8FQ_EST_RUNNING) { // :121-123
+    mn = add_rn(mul_rn(e.w_new, mn), mul_rn(e.w_old, e.cur_min[c]));
+    mx = add_rn(mul_rn(e.w_new, mx), mul_rn(e.w_old, e.cur_max[c]));
+  }
+  e.cur_min[c] = mn;
+  e.cur_max[c] = mx;
+}
+
+constexpr int kMMThreads = 256;
+constexpr int kMMUnroll = 4;
+
+__global__ void __launch_bounds__(kMMThreads) minmax_tensor_kernel(const float* __restrict__ x, int64_t n,
+                                                                   int vec_ok, float* __restrict__ partial,
+                                                                   unsigned int* __restrict__ counter,
+                                                                   const EstArgs est) {
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  if (vec_ok) {
+    const int64_t nv = n >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const int64_t step = (int64_t)gridDim.x * kMMThreads;
+    int64_t i = (int64_t)blockIdx.x * kMMThreads + threadIdx.x;
+    for (; i + (kMMUnroll - 1) * step < nv; i += kMMUnroll * step) {
+      float4 t[kMMUnroll];
+#pragma unroll
+      for (int u = 0; u < kMMUnroll; ++u) t[u] = __ldcs(xv + i + u * step);
+#pragma unroll
+      for (int u = 0; u < kMMUnroll; ++u) {
+        mn = min_nan(min_nan(mn, t[u].x), min_nan(t[u].y, min_nan(t[u].z, t[u].w)));
+        mx = max_nan(max_nan(mx, t[u].x), max_nan(t[u].y, max_nan(t[u].z, t[u].w)));
+      }
+    }
+    for (; i < nv; i += step) {
+      const float4 t = __ldcs(xv + i);
+      mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
+      mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+      const float t = x[(nv << 2) + threadIdx.x];
+      mn = min_nan(mn, t);
+      mx = max_nan(mx, t);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kMMThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kMMThreads) {
+      const float t = x[i];
+      mn = min_nan(mn, t);
+      mx = max_nan(mx, t);
+    }
+  }
+  block_minmax(mn, mx);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mn;
+    partial[2 * blockIdx.x + 1] = mx;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  mn = __int_as_float(0x7f800000);
+  mx = __int_as_float(0xff800000);
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += kMMThreads) {
+    mn = min_nan(mn, __ldcg(partial + 2 * b));
+    mx = max_nan(mx, __ldcg(partial + 2 * b + 1));
+  }
+  block_minmax(mn, mx);
+  __shared__ float s_mv;
+  if (threadIdx.x == 0) {
+    *counter = 0u;  // leave the workspace ready for the next call
+    est_update(est, 0, mn, mx);
+    const float mv = range_to_maxval(mn, mx);
+    if (est.maxval_out != nullptr) est.maxval_out[0] = mv;
+    s_mv = mv;
+  }
+  __syncthreads();
+  if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table);
+}
+
+// per-channel: one CTA per row
+__global__ void __launch_bounds__(128) minmax_rows_kernel(const float* __restrict__ x, int64_t C, int64_t inner,
+                                                          int vec_ok, const EstArgs est) {
+  __shared__ float s_mv;
+  const int stride = est.table != nullptr ? table_stride(est.K) : 0;
+  for (int64_t row = blockIdx.x; row < C; row += gridDim.x) {
+    const float* xr = x + row * inner;
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    if (vec_ok) {
+      for (int64_t i = (int64_t)threadIdx.x * 4; i < inner; i += (int64_t)blockDim.x * 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+        mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
+        mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < inner; i += blockDim.x) {
+        const float t = __ldg(xr + i);
+        mn = min_nan(mn, t);
+        mx = max_nan(mx, t);
+      }
+    }
+    block_minmax(mn, mx);
+    if (threadIdx.x == 0) {
+      est_update(est, row, mn, mx);
+      const float mv = range_to_maxval(mn, mx);
+      if (est.maxval_out != nullptr) est.maxval_out[row] = mv;
+      s_mv = mv;
+    }
+    __syncthreads();
+    if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table + row * stride);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN fold
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_fold_kernel(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                               int64_t C, float* scale, float* shift) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = div_rn(1.0f, sqrtf(add_rn(var[c], eps)));
+  const float g = gamma != nullptr ? gamma[c] : 1.0f;
+  const float b = beta != nullptr ? beta[c] : 0.0f;
+  const float sc = mul_rn(g, invstd);
+  scale[c] = sc;
+  shift[c] = sub_rn(b, mul_rn(mean[c], sc));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: MSE grid.  grid = (chunks, C).  Each CTA keeps its slice of one channel row in registers and
+// sweeps the G candidate tables of the current mantissa width.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMseThreads = 256;
+constexpr int kMseEpt = 8;  // elements per thread
+
+__global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __restrict__ x, int64_t inner,
+                                                               int64_t C, const float* __restrict__ tables,
+                                                               int64_t G, int K, double* __restrict__ acc) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int stride = table_stride(K);
+  float* s_tab = s_dyn;                       // 2 * stride (double buffered)
+  double* s_sum = reinterpret_cast<double*>(s_dyn + 2 * ((stride + 3) & ~3));  // [G]
+  const int64_t c = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * kMseThreads * kMseEpt;
+  const float* xr = x + c * inner;
+  float v[kMseEpt];
+  bool ok[kMseEpt];
+#pragma unroll
+  for (int u = 0; u < kMseEpt; ++u) {
+    const int64_t i = beg + (int64_t)u * kMseThreads + threadIdx.x;
+    ok[u] = i < inner;
+    v[u] = ok[u] ? __ldg(xr + i) : 0.0f;
+  }
+  for (int g = threadIdx.x; g < G; g += kMseThreads) s_sum[g] = 0.0;
+  // table of candidate g for channel c lives at tables[(g * C + c) * stride]
+  for (int i = threadIdx.x; i < stride; i += kMseThreads) s_tab[i] = tables[(0 * C + c) * stride + i];
+  __syncthreads();
+  for (int64_t g = 0; g < G; ++g) {
+    float* cur = s_tab + (g & 1) * ((stride + 3) & ~3);
+    float* nxt = s_tab + ((g + 1) & 1) * ((stride + 3) & ~3);
+    if (g + 1 < G)
+      for (int i = threadIdx.x; i < stride; i += kMseThreads) nxt[i] = tables[((g + 1) * C + c) * stride + i];
+    ElemCtx<1> ctx;
+    ctx.hi = cur[H_HI]; ctx.lo = cur[H_LO]; ctx.guard = cur[H_GUARD]; ctx.K = K;
+    ctx.base = f2u(cur[H_BASE]);
+    ctx.irregular = (f2u(cur[H_FLAGS]) & FLAG_IRREGULAR) != 0;
+    ctx.stab = cur;
+    float err = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kMseEpt; ++u) {
+      int32_t cd;
+      const float y = quant_elem<1, false>(v[u], ctx, &cd);
+      const float d = sub_rn(v[u], y);
+      if (ok[u]) err = add_rn(err, mul_rn(d, d));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[g], (double)err);
+    __syncthreads();
+  }
+  for (int g = threadIdx.x; g < G; g += kMseThreads) atomicAdd(&acc[g * C + c], s_sum[g]);
+}
+
+__global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, double inv_count,
+                                  float* __restrict__ mses) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= GC) return;
+  mses[i] = add_rn(mses[i], (float)(acc[i] * inv_count));
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+template <int KMODE, int PRE, int VEC, bool CODES>
+int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fq_stream_kernel<KMODE, PRE, VEC, CODES>, kThreads, 0) !=
+            cudaSuccess || o <= 0)
+      o = 4;
+    occ = o;
+  }
+  const int64_t tile = (int64_t)kThreads * VEC * kUnroll;
+  int64_t ntiles = (a.n + tile - 1) / tile;
+  if (ntiles < 1) ntiles = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > ntiles) grid = ntiles;
+  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, 0, st>>>(a);
+  return launch_status();
+}
+
+template <int PRE, int VEC>
+int launch_stream(const StreamArgs& a, cudaStream_t st) {
+  const bool codes = a.codes != nullptr;
+  if (a.K <= 3) return codes ? launch_stream_t<0, PRE, VEC, true>(a, st) : launch_stream_t<0, PRE, VEC, false>(a, st);
+  return codes ? launch_stream_t<1, PRE, VEC, true>(a, st) : launch_stream_t<1, PRE, VEC, false>(a, st);
+}
+
+int check_format(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
+  if (sign_bits != 0 && sign_bits != 1) return FP8FQ_ERR_BAD_ARG;
+  int r = format_split(mantissa_bits, n_bits, sign_bits, M, E, K);
+  if (r == -1) return FP8FQ_ERR_BAD_ARG;
+  if (r == -2) return FP8FQ_ERR_UNSUPPORTED;
+  return FP8FQ_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int fp8fq_version(void) { return 100; }
+
+const char* fp8fq_build_info(void) { return "fp8fq 0.1 sm_100a " __DATE__ " " __TIME__; }
+
+int64_t fp8fq_launch_count(void) { return g_launches.load(); }
+
+int fp8fq_format_split(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
+  int m, e, k;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &m, &e, &k);
+  if (r != FP8FQ_OK) return r;
+  if (M) *M = m;
+  if (E) *E = e;
+  if (K) *K = k;
+  return FP8FQ_OK;
+}
+
+int64_t fp8fq_table_stride(float mantissa_bits, int n_bits, int sign_bits) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  return table_stride(K);
+}
+
+int64_t fp8fq_table_floats(float mantissa_bits, int n_bits, int sign_bits, int64_t C) {
+  int64_t s = fp8fq_table_stride(mantissa_bits, n_bits, sign_bits);
+  if (s < 0) return s;
+  if (C < 1) return FP8FQ_ERR_BAD_ARG;
+  return s * C;
+}
+
+static int prepare_impl(const float* maxval, const float* xmin, const float* xmax, float* maxval_out, int64_t C,
+                        float mantissa_bits, int n_bits, int sign_bits, float* table, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (table == nullptr || C < 1) return FP8FQ_ERR_BAD_ARG;
+  if (maxval == nullptr && (xmin == nullptr || xmax == nullptr)) return FP8FQ_ERR_BAD_ARG;
+  int threads = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
+  int64_t grid = C < 4096 ? C : 4096;
+  prepare_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(maxval, xmin, xmax, maxval_out, C, M, E, K,
+                                                                       sign_bits, table);
+  return launch_status();
+}
+
+int fp8fq_prepare_f32(const float* maxval, int64_t C, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                      void* stream) {
+  if (maxval == nullptr) return FP8FQ_ERR_BAD_ARG;
+  return prepare_impl(maxval, nullptr, nullptr, nullptr, C, mantissa_bits, n_bits, sign_bits, table, stream);
+}
+
+int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C, float* maxval_out,
+                                float mantissa_bits, int n_bits, int sign_bits, float* table, void* stream) {
+  if (xmin == nullptr || xmax == nullptr) return FP8FQ_ERR_BAD_ARG;
+  return prepare_impl(nullptr, xmin, xmax, maxval_out, C, mantissa_bits, n_bits, sign_bits, table, stream);
+}
+
+static int fake_quant_impl(const float* x, float* y, int32_t* codes, const float* table, int64_t n, int64_t C,
+                           int64_t inner, float mantissa_bits, int n_bits, int sign_bits, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (n < 0 || C < 1 || inner < 0 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr || table == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(x) || !aligned4(y) || (codes && !aligned4(codes))) return FP8FQ_ERR_ALIGNMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 1) {
+    StreamArgs a{};
+    a.x = x; a.y = y; a.codes = codes; a.table = table; a.n = n; a.K = K; a.act = 0;
+    const bool vec = aligned16(x) && aligned16(y) && (codes == nullptr || aligned16(codes));
+    return vec ? launch_stream<PRE_PLAIN, 4>(a, st) : launch_stream<PRE_PLAIN, 1>(a, st);
+  }
+  RowsArgs a{};
+  a.x = x; a.y = y; a.codes = codes; a.table = table; a.C = C; a.inner = inner; a.K = K;
+  a.vec_ok = (inner % 4 == 0) && aligned16(x) && aligned16(y) && (codes == nullptr || aligned16(codes));
+  a.chunk = 4096;
+  a.chunks_per_row = (inner + a.chunk - 1) / a.chunk;
+  int64_t nwork = C * a.chunks_per_row;
+  int64_t grid = (int64_t)sm_count() * 16;
+  if (grid > nwork) grid = nwork;
+  int threads = inner >= 512 ? 128 : (inner >= 128 ? 64 : 32);
+  if (K <= 3) {
+    if (codes) fq_rows_kernel<0, true><<<(unsigned)grid, threads, 0, st>>>(a);
+    else fq_rows_kernel<0, false><<<(unsigned)grid, threads, 0, st>>>(a);
+  } else {
+    if (codes) fq_rows_kernel<1, true><<<(unsigned)grid, threads, 0, st>>>(a);
+    else fq_rows_kernel<1, false><<<(unsigned)grid, threads, 0, st>>>(a);
+  }
+  return launch_status();
+}
+
+int fp8fq_fake_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
+                         float mantissa_bits, int n_bits, int sign_bits, void* stream) {
+  return fake_quant_impl(x, y, nullptr, table, n, C, inner, mantissa_bits, n_bits, sign_bits, stream);
+}
+
+int fp8fq_fake_quant_codes_f32(const float* x, float* y, int32_t* codes, const float* table, int64_t n, int64_t C,
+                               int64_t inner, float mantissa_bits, int n_bits, int sign_bits, void* stream) {
+  if (codes == nullptr) return FP8FQ_ERR_BAD_ARG;
+  return fake_quant_impl(x, y, codes, table, n, C, inner, mantissa_bits, n_bits, sign_bits, stream);
+}
+
+int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                      int64_t Cbn, float* bn_scale, float* bn_shift, void* stream) {
+  if (mean == nullptr || var == nullptr || bn_scale == nullptr || bn_shift == nullptr || Cbn < 1)
+    return FP8FQ_ERR_BAD_ARG;
+  const int threads = 128;
+  bn_fold_kernel<<<(unsigned)((Cbn + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      mean, var, gamma, beta, eps, Cbn, bn_scale, bn_shift);
+  return launch_status();
+}
+
+int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift, int64_t rows,
+                           int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table, float mantissa_bits,
+                           int n_bits, int sign_bits, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2) return FP8FQ_ERR_BAD_ARG;
+  const int64_t n = rows * hw;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr || bn_scale == nullptr || bn_shift == nullptr || table == nullptr)
+    return FP8FQ_ERR_BAD_ARG;
+  if (n >= (1ll << 32) || hw >= (1ll << 31) || Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
+  if (!aligned4(x) || !aligned4(y)) return FP8FQ_ERR_ALIGNMENT;
+  StreamArgs a{};
+  a.x = x; a.y = y; a.table = table; a.n = n; a.K = K; a.act = act;
+  a.bn_scale = bn_scale; a.bn_shift = bn_shift;
+  a.hw_div = make_fastdiv((uint32_t)hw);
+  a.c_div = make_fastdiv((uint32_t)Cbn);
+  a.bn_mode = bn_mode;
+  const bool vec = (hw % 4 == 0) && aligned16(x) && aligned16(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  return vec ? launch_stream<PRE_AFFINE, 4>(a, st) : launch_stream<PRE_AFFINE, 1>(a, st);
+}
+
+int fp8fq_add_act_quant_f32(const float* a_in, const float* b_in, float* y, int64_t n, int act, const float* table,
+                            float mantissa_bits, int n_bits, int sign_bits, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (n < 0 || act < 0 || act > 2) return FP8FQ_ERR_BAD_ARG;
+  if (n == 0) return FP8FQ_OK;
+  if (a_in == nullptr || b_in == nullptr || y == nullptr || table == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(a_in) || !aligned4(b_in) || !aligned4(y)) return FP8FQ_ERR_ALIGNMENT;
+  StreamArgs a{};
+  a.x = a_in; a.x2 = b_in; a.y = y; a.table = table; a.n = n; a.K = K; a.act = act;
+  const bool vec = aligned16(a_in) && aligned16(b_in) && aligned16(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  return vec ? launch_stream<PRE_ADD, 4>(a, st) : launch_stream<PRE_ADD, 1>(a, st);
+}
+
+int64_t fp8fq_minmax_workspace_bytes(void) { return 16384; }
+
+static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min, float* cur_max,
+                       int est_mode, int initialized, double momentum, float* maxval_out, bool fuse,
+                       float mantissa_bits, int n_bits, int sign_bits, float* table, void* workspace, void* stream) {
+  if (n < 1 || C < 1 || inner < 1 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
+  if (x == nullptr || cur_min == nullptr || cur_max == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (est_mode < 0 || est_mode > 2) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(x)) return FP8FQ_ERR_ALIGNMENT;
+  EstArgs e{};
+  e.cur_min = cur_min; e.cur_max = cur_max; e.est_mode = est_mode; e.initialized = initialized;
+  e.w_new = (float)(1.0 - momentum);
+  e.w_old = (float)momentum;
+  e.maxval_out = maxval_out;
+  e.table = nullptr;
+  if (fuse) {
+    int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
+    if (r != FP8FQ_OK) return r;
+    if (table == nullptr) return FP8FQ_ERR_BAD_ARG;
+    e.table = table;
+    e.sign_bits = sign_bits;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 1) {
+    if (workspace == nullptr) return FP8FQ_ERR_WORKSPACE;
+    float* partial = reinterpret_cast<float*>(workspace) + 4;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    const int max_grid = (int)((fp8fq_minmax_workspace_bytes() - 16) / 8);
+    int64_t grid = (int64_t)sm_count() * 8;
+    const int64_t need = (n / 4 + kMMThreads * kMMUnroll - 1) / (kMMThreads * kMMUnroll);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (grid > max_grid) grid = max_grid;
+    minmax_tensor_kernel<<<(unsigned)grid, kMMThreads, 0, st>>>(x, n, aligned16(x) ? 1 : 0, partial, counter, e);
+    return launch_status();
+  }
+  int threads = inner >= 512 ? 128 : (inner >= 128 ? 64 : 32);
+  if (fuse && e.K > threads) threads = e.K <= 64 ? 64 : 128;
+  int64_t grid = C < (int64_t)sm_count() * 16 ? C : (int64_t)sm_count() * 16;
+  minmax_rows_kernel<<<(unsigned)grid, threads, 0, st>>>(x, C, inner, (inner % 4 == 0 && aligned16(x)) ? 1 : 0, e);
+  return launch_status();
+}
+
+int fp8fq_minmax_f32(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min, float* cur_max,
+                     int est_mode, int initialized, double momentum, void* workspace, void* stream) {
+  return minmax_impl(x, n, C, inner, cur_min, cur_max, est_mode, initialized, momentum, nullptr, false, 0.f, 0, 0,
+                     nullptr, workspace, stream);
+}
+
+int fp8fq_estimate_prepare_f32(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min, float* cur_max,
+                               int est_mode, int initialized, double momentum, float* maxval_out,
+                               float mantissa_bits, int n_bits, int sign_bits, float* table, void* workspace,
+                               void* stream) {
+  return minmax_impl(x, n, C, inner, cur_min, cur_max, est_mode, initialized, momentum, maxval_out, true,
+                     mantissa_bits, n_bits, sign_bits, table, workspace, stream);
+}
+
+// ---- MSE grid -----------------------------------------------------------------------------------
+int64_t fp8fq_mse_table_floats(const float* mbits_host, int Mn, int n_bits, int sign_bits, int64_t G, int64_t C) {
+  if (mbits_host == nullptr || Mn < 1 || G < 1 || C < 1) return FP8FQ_ERR_BAD_ARG;
+  int64_t mx = 0;
+  for (int m = 0; m < Mn; ++m) {
+    int64_t s = fp8fq_table_stride(mbits_host[m], n_bits, sign_bits);
+    if (s < 0) return s;
+    if (s > mx) mx = s;
+  }
+  // tables of one mantissa width at a time + double accumulators [G*C]
+  return mx * G * C + 2 * G * C + 4;
+}
+
+int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, const float* grid, int64_t G,
+                       const float* mbits_host, int Mn, int n_bits, int sign_bits, float* mses, float* tables,
+                       void* stream) {
+  if (x == nullptr || grid == nullptr || mbits_host == nullptr || mses == nullptr || tables == nullptr)
+    return FP8FQ_ERR_BAD_ARG;
+  if (n < 1 || C < 1 || inner < 1 || n != C * inner || G < 1 || Mn < 1 || C > 65535) return FP8FQ_ERR_BAD_ARG;
+  int64_t tf = fp8fq_mse_table_floats(mbits_host, Mn, n_bits, sign_bits, G, C);
+  if (tf < 0) return (int)tf;
+  cudaStream_t st = (cudaStream_t)stream;
+  // accumulators live at the (8-byte aligned) tail of the scratch buffer
+  const int64_t acc_off = (tf - 2 * G * C - 2) & ~1ll;
+  double* acc = reinterpret_cast<double*>(tables + acc_off);
+  if ((reinterpret_cast<uintptr_t>(tables) & 7u) != 0) return FP8FQ_ERR_ALIGNMENT;
+  for (int m = 0; m < Mn; ++m) {
+    int M, E, K;
+    int r = check_format(mbits_host[m], n_bits, sign_bits, &M, &E, &K);
+    if (r != FP8FQ_OK) return r;
+    // candidate tables: "channel" index = g * C + c, maxval = grid[g, c]
+    r = prepare_impl(grid, nullptr, nullptr, nullptr, G * C, mbits_host[m], n_bits, sign_bits, tables, stream);
+    if (r != FP8FQ_OK) return r;
+    cudaError_t ce = cudaMemsetAsync(acc, 0, sizeof(double) * G * C, st);
+    if (ce != cudaSuccess) return (int)ce;
+    const int stride = table_stride(K);
+    const size_t smem = sizeof(float) * 2 * ((stride + 3) & ~3) + sizeof(double) * G;
+    const int64_t chunks = (inner + (int64_t)kMseThreads * kMseEpt - 1) / ((int64_t)kMseThreads * kMseEpt);
+    if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
+    dim3 gdim((unsigned)chunks, (unsigned)C);
+    mse_grid_kernel<<<gdim, kMseThreads, smem, st>>>(x, inner, C, tables, G, K, acc);
+    r = launch_status();
+    if (r != FP8FQ_OK) return r;
+    const int64_t GC = G * C;
+    mse_finish_kernel<<<(unsigned)((GC + 127) / 128), 128, 0, st>>>(acc, GC, 1.0 / (double)inner, mses + m * GC);
+    r = launch_status();
+    if (r != FP8FQ_OK) return r;
+  }
+  return FP8FQ_OK;
+}
+
+// ---- host-buffer end-to-end entry point -------------------------------------------------------------
+namespace {
+struct HostPipe {
+  static constexpr int kStreams = 3;
+  static constexpr int64_t kChunk = 8ll << 20;  // elements per chunk (32 MiB)
+  cudaStream_t st[kStreams] = {};
+  float* pin_in[kStreams] = {};
+  float* pin_out[kStreams] = {};
+  float* dev[kStreams] = {};
+  float* d_maxval = nullptr;
+  float* d_table = nullptr;
+  int64_t maxval_cap = 0, table_cap = 0;
+  int device = -1;
+  bool ready = false;
+};
+HostPipe g_pipe;
+std::mutex g_pipe_mu;
+}  // namespace
+
+int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* maxval_host, int64_t n, int64_t C,
+                              int64_t inner, float mantissa_bits, int n_bits, int sign_bits, int device) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (x_host == nullptr || y_host == nullptr || maxval_host == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (n < 0 || C < 1 || inner < 0 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
+  if (n == 0) return FP8FQ_OK;
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  cudaError_t ce;
+#define FQ_CK(call) do { ce = (call); if (ce != cudaSuccess) return (int)ce; } while (0)
+  FQ_CK(cudaSetDevice(device));
+  HostPipe& p = g_pipe;
+  if (p.ready && p.device != device) return FP8FQ_ERR_UNSUPPORTED;
+  if (!p.ready) {
+    for (int i = 0; i < HostPipe::kStreams; ++i) {
+      FQ_CK(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
+      FQ_CK(cudaMallocHost(&p.pin_in[i], HostPipe::kChunk * sizeof(float)));
+      FQ_CK(cudaMallocHost(&p.pin_out[i], HostPipe::kChunk * sizeof(float)));
+      FQ_CK(cudaMalloc(&p.dev[i], HostPipe::kChunk * sizeof(float)));
+    }
+    p.device = device;
+    p.ready = true;
+  }
+  const int64_t tfl = (int64_t)table_stride(K) * C;
+  if (p.maxval_cap < C) {
+    if (p.d_maxval) cudaFree(p.d_maxval);
+    FQ_CK(cudaMalloc(&p.d_maxval, C * sizeof(float)));
+    p.maxval_cap = C;
+  }
+  if (p.table_cap < tfl) {
+    if (p.d_table) cudaFree(p.d_table);
+    FQ_CK(cudaMalloc(&p.d_table, tfl * sizeof(float)));
+    p.table_cap = tfl;
+  }
+  FQ_CK(cudaMemcpyAsync(p.d_maxval, maxval_host, C * sizeof(float), cudaMemcpyHostToDevice, p.st[0]));
+  r = fp8fq_prepare_f32(p.d_maxval, C, mantissa_bits, n_bits, sign_bits, p.d_table, p.st[0]);
+  if (r != FP8FQ_OK) return r;
+  FQ_CK(cudaStreamSynchronize(p.st[0]));
+  // chunks are whole rows when per-channel, so each chunk sees a contiguous range of channel tables
+  int64_t rows_per_chunk = 1, chunk_elems = HostPipe::kChunk;
+  if (C > 1) {
+    if (inner > HostPipe::kChunk) return FP8FQ_ERR_UNSUPPORTED;
+    rows_per_chunk = HostPipe::kChunk / inner;
+    chunk_elems = rows_per_chunk * inner;
+  }
+  const int stride = table_stride(K);
+  int64_t done = 0;
+  int64_t k = 0;
+  int64_t pend_off[HostPipe::kStreams] = {-1, -1, -1}, pend_len[HostPipe::kStreams] = {0, 0, 0};
+  while (done < n) {
+    const int s = (int)(k % HostPipe::kStreams);
+    const int64_t len = (n - done) < chunk_elems ? (n - done) : chunk_elems;
+    FQ_CK(cudaStreamSynchronize(p.st[s]));
+    if (pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
+    memcpy(p.pin_in[s], x_host + done, len * sizeof(float));
+    FQ_CK(cudaMemcpyAsync(p.dev[s], p.pin_in[s], len * sizeof(float), cudaMemcpyHostToDevice, p.st[s]));
+    if (C == 1) {
+      r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table, len, 1, len, mantissa_bits, n_bits, sign_bits, p.st[s]);
+    } else {
+      const int64_t row0 = done / inner, nrows = len / inner;
+      r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table + row0 * stride, len, nrows, inner, mantissa_bits,
+                               n_bits, sign_bits, p.st[s]);
+    }
+    if (r != FP8FQ_OK) return r;
+    FQ_CK(cudaMemcpyAsync(p.pin_out[s], p.dev[s], len * sizeof(float), cudaMemcpyDeviceToHost, p.st[s]));
+    pend_off[s] = done;
+    pend_len[s] = len;
+    done += len;
+    ++k;
+  }
+  for (int s = 0; s < HostPipe::kStreams; ++s) {
+    FQ_CK(cudaStreamSynchronize(p.st[s]));
+    if (pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
+  }
+#undef FQ_CK
+  return FP8FQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""Tensor-level wrappers over the C ABI (include/fp8fq.h).  PyTorch is plumbing here: it owns the
+device memory and the stream; every function below is one (or a fixed small number of) kernel
+launch(es) from libfp8fq.so on the current CUDA stream, with no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import Fp8fqError, check, lib
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+EST_CURRENT, EST_ALL, EST_RUNNING = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise Fp8fqError(f"{name} must be a CUDA tensor (this engine has no CPU path); got device {t.device}")
+    if t.dtype != torch.float32:
+        raise Fp8fqError(f"{name} must be float32; got {t.dtype}")
+    if not t.is_contiguous():
+        raise Fp8fqError(f"{name} must be contiguous")
+
+
+def format_split(mantissa_bits: float, n_bits: int, sign_bits: int):
+    """(M, E, K) of fp8_quantizer.py:105-106; K = number of exponent codes."""
+    M, E, K = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib().fp8fq_format_split(float(mantissa_bits), int(n_bits), int(sign_bits), M, E, K), "format_split")
+    return M.value, E.value, K.value
+
+
+def table_stride(mantissa_bits: float, n_bits: int, sign_bits: int) -> int:
+    s = lib().fp8fq_table_stride(float(mantissa_bits), int(n_bits), int(sign_bits))
+    if s < 0:
+        check(int(s), "table_stride")
+    return int(s)
+
+
+def new_table(C: int, mantissa_bits: float, n_bits: int, sign_bits: int, device) -> torch.Tensor:
+    return torch.empty(table_stride(mantissa_bits, n_bits, sign_bits) * C, dtype=torch.float32, device=device)
+
+
+def prepare(maxval: torch.Tensor, mantissa_bits: float, n_bits: int, sign_bits: int, out: torch.Tensor = None):
+    """Table for maxval [C] (fp8_quantizer.py:105-113,128,130)."""
+    _require(maxval, "maxval")
+    C = maxval.numel()
+    if out is None:
+        out = new_table(C, mantissa_bits, n_bits, sign_bits, maxval.device)
+    check(lib().fp8fq_prepare_f32(maxval.data_ptr(), C, float(mantissa_bits), int(n_bits), int(sign_bits),
+                                  out.data_ptr(), _stream()), "fp8fq_prepare_f32")
+    return out
+
+
+def set_range_prepare(xmin: torch.Tensor, xmax: torch.Tensor, mantissa_bits: float, n_bits: int, sign_bits: int,
+                      maxval_out: torch.Tensor = None, table_out: torch.Tensor = None):
+    """set_quant_range (fp8_quantizer.py:236-237) + table; returns (maxval [C], table)."""
+    _require(xmin, "x_min")
+    _require(xmax, "x_max")
+    C = xmax.numel()
+    if xmin.numel() != C:
+        raise Fp8fqError("x_min and x_max must have the same number of elements")
+    if maxval_out is None:
+        maxval_out = torch.empty(C, dtype=torch.float32, device=xmax.device)
+    if table_out is None:
+        table_out = new_table(C, mantissa_bits, n_bits, sign_bits, xmax.device)
+    check(lib().fp8fq_set_range_prepare_f32(xmin.data_ptr(), xmax.data_ptr(), C, maxval_out.data_ptr(),
+                                            float(mantissa_bits), int(n_bits), int(sign_bits),
+                                            table_out.data_ptr(), _stream()), "fp8fq_set_range_prepare_f32")
+    return maxval_out, table_out
+
+
+def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int,
+               out: torch.Tensor = None):
+    """FPQuantizer.forward (fp8_quantizer.py:91-133).  C == 1: per tensor; else channel = dim 0."""
+    _require(x, "x")
+    n = x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    inner = n // C if C > 0 else 0
+    check(lib().fp8fq_fake_quant_f32(x.data_ptr(), out.data_ptr(), table.data_ptr(), n, C, inner,
+                                     float(mantissa_bits), int(n_bits), int(sign_bits), _stream()),
+          "fp8fq_fake_quant_f32")
+    return out
+
+
+def fake_quant_codes(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int):
+    """Returns (y, codes int32) -- codes = sign<<31 | e<<16 | q (parity tests)."""
+    _require(x, "x")
+    n = x.numel()
+    y = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    check(lib().fp8fq_fake_quant_codes_f32(x.data_ptr(), y.data_ptr(), codes.data_ptr(), table.data_ptr(), n, C,
+                                           n // C, float(mantissa_bits), int(n_bits), int(sign_bits), _stream()),
+          "fp8fq_fake_quant_codes_f32")
+    return y, codes
+
+
+def bn_fold(mean, var, gamma, beta, eps: float):
+    """Eval-mode batch norm as a per-channel affine map (scale, shift)."""
+    _require(mean, "running_mean")
+    _require(var, "running_var")
+    C = mean.numel()
+    scale = torch.empty_like(mean)
+    shift = torch.empty_like(mean)
+    check(lib().fp8fq_bn_fold_f32(mean.data_ptr(), var.data_ptr(),
+                                  gamma.data_ptr() if gamma is not None else None,
+                                  beta.data_ptr() if beta is not None else None, float(eps), C,
+                                  scale.data_ptr(), shift.data_ptr(), _stream()), "fp8fq_bn_fold_f32")
+    return scale, shift
+
+
+def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int,
+                 bn_mode: int = 0, out=None):
+    """quantized_folded_bn.py:39-55 in one pass: Q(act(bn(x))), x is [N, C, *spatial] contiguous."""
+    _require(x, "x")
+    Cbn = bn_scale.numel()
+    if x.dim() < 2 or x.shape[1] != Cbn:
+        raise Fp8fqError("bn_act_quant: x must be [N, C, ...] with C == len(bn_scale)")
+    hw = 1
+    for d in x.shape[2:]:
+        hw *= d
+    rows = x.shape[0] * Cbn
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().fp8fq_bn_act_quant_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), rows,
+                                       hw, Cbn, int(act), int(bn_mode), table.data_ptr(), float(mantissa_bits),
+                                       int(n_bits), int(sign_bits), _stream()), "fp8fq_bn_act_quant_f32")
+    return out
+
+
+def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int, out=None):
+    """models/resnet_quantized.py:43-46 in one pass: Q(act(a + b))."""
+    _require(a, "a")
+    _require(b, "b")
+    if a.shape != b.shape:
+        raise Fp8fqError("add_act_quant: shape mismatch")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().fp8fq_add_act_quant_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), int(act),
+                                        table.data_ptr(), float(mantissa_bits), int(n_bits), int(sign_bits),
+                                        _stream()), "fp8fq_add_act_quant_f32")
+    return out
+
+
+_workspaces = {}
+
+
+def _workspace(device):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib().fp8fq_minmax_workspace_bytes()) // 4, dtype=torch.int32, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def minmax(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float = 0.9):
+    """Estimator min/max + state update in place (range_estimators.py:61-125).  cur_min/cur_max: [C]."""
+    _require(x, "x")
+    n = x.numel()
+    C = x.shape[0] if per_channel else 1
+    check(lib().fp8fq_minmax_f32(x.data_ptr(), n, C, n // C, cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode),
+                                 1 if initialized else 0, float(momentum), _workspace(x.device).data_ptr(),
+                                 _stream()), "fp8fq_minmax_f32")
+    return cur_min, cur_max
+
+
+def estimate_prepare(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float,
+                     maxval_out, mantissa_bits: float, n_bits: int, sign_bits: int, table_out):
+    """estimator + set_quant_range + table in one launch (quantization_manager.py:114-122 minus the quantiser)."""
+    _require(x, "x")
+    n = x.numel()
+    C = x.shape[0] if per_channel else 1
+    check(lib().fp8fq_estimate_prepare_f32(x.data_ptr(), n, C, n // C, cur_min.data_ptr(), cur_max.data_ptr(),
+                                           int(est_mode), 1 if initialized else 0, float(momentum),
+                                           maxval_out.data_ptr(), float(mantissa_bits), int(n_bits), int(sign_bits),
+                                           table_out.data_ptr(), _workspace(x.device).data_ptr(), _stream()),
+          "fp8fq_estimate_prepare_f32")
+    return maxval_out, table_out
+
+
+def mse_grid(x, per_channel: bool, grid: torch.Tensor, mbit_list, n_bits: int, sign_bits: int, mses: torch.Tensor):
+    """mses[m, g, c] += mean((x - Q(x; grid[g, c], mbit_list[m]))^2)  (range_estimators.py:337-347)."""
+    _require(x, "x")
+    _require(grid, "grid")
+    _require(mses, "mses")
+    n = x.numel()
+    C = x.shape[0] if per_channel else 1
+    G = grid.shape[0]
+    Mn = len(mbit_list)
+    arr = (ctypes.c_float * Mn)(*[float(m) for m in mbit_list])
+    tf = lib().fp8fq_mse_table_floats(arr, Mn, int(n_bits), int(sign_bits), G, C)
+    if tf < 0:
+        check(int(tf), "fp8fq_mse_table_floats")
+    scratch = torch.empty(int(tf) + 2, dtype=torch.float32, device=x.device)
+    check(lib().fp8fq_mse_grid_f32(x.data_ptr(), n, C, n // C, grid.data_ptr(), G, arr, Mn, int(n_bits),
+                                   int(sign_bits), mses.data_ptr(), scratch.data_ptr(), _stream()),
+          "fp8fq_mse_grid_f32")
+    return mses
+
+
+def fake_quant_host(x_host: torch.Tensor, maxval_host: torch.Tensor, mantissa_bits: float, n_bits: int,
+                    sign_bits: int, per_channel: bool = False, out: torch.Tensor = None, device: int = None):
+    """End-to-end call with HOST tensors (fp8fq_fake_quant_host_f32): H2D, quantise, D2H inside."""
+    if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+        raise Fp8fqError("fake_quant_host: x must be a contiguous float32 CPU tensor")
+    if out is None:
+        out = torch.empty_like(x_host)
+    C = x_host.shape[0] if per_channel else 1
+    n = x_host.numel()
+    mv = maxval_host.detach().to(torch.float32).contiguous().cpu()
+    if mv.numel() != C:
+        raise Fp8fqError("fake_quant_host: maxval must have one entry per channel")
+    dev = torch.cuda.current_device() if device is None else device
+    check(lib().fp8fq_fake_quant_host_f32(x_host.data_ptr(), out.data_ptr(), mv.data_ptr(), n, C, n // C,
+                                          float(mantissa_bits), int(n_bits), int(sign_bits), int(dev)),
+          "fp8fq_fake_quant_host_f32")
+    return out
+
+
+def launch_count() -> int:
+    return int(lib().fp8fq_launch_count())

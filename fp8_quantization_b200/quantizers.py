@@ -1,0 +1,240 @@
+"""Drop-in ``FPQuantizer`` backed by libfp8fq.so.
+
+Mirrors the reference's quantizer contract:
+  * ``QuantizerBase``  -- quantization/quantizers/base_quantizers.py:8-47
+  * ``FPQuantizer``    -- quantization/quantizers/fp8_quantizer.py:151-272
+Same constructor kwargs, same public attributes (``n_bits, per_channel, mantissa_bits, maxval,
+ebits, default_bias, set_maxval, allow_unsigned, sign_bits, mse_include_mantissa_bits,
+learning_maxval, learning_mantissa_bits``), same ``set_quant_range`` semantics -- but ``forward`` is
+ONE kernel launch reading each element once and writing it once, and nothing on the calibration or
+validation path synchronises with the host (the reference does a D2H copy per activation quantiser
+per calibration batch, fp8_quantizer.py:239-240).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import Fp8fqError
+
+
+class QuantizerNotInitializedError(Exception):
+    """quantization/quantizers/utils.py:6-12."""
+
+    def __init__(self):
+        super().__init__("Quantizer has not been initialized yet")
+
+
+class QuantizerBase(nn.Module):
+    """base_quantizers.py:8-47 (type contract; properties raise until a subclass defines them)."""
+
+    def __init__(self, n_bits, per_channel=False, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.n_bits = n_bits
+        self.per_channel = per_channel
+        self.state = None
+        self.x_min_fp32 = self.x_max_fp32 = None
+
+    @property
+    def is_initialized(self):
+        raise NotImplementedError()
+
+    @property
+    def x_max(self):
+        raise NotImplementedError()
+
+    @property
+    def symmetric(self):
+        raise NotImplementedError()
+
+    @property
+    def x_min(self):
+        raise NotImplementedError()
+
+    def forward(self, x_float):
+        raise NotImplementedError()
+
+    def _adjust_params_per_channel(self, x):
+        raise NotImplementedError()
+
+    def set_quant_range(self, x_min, x_max):
+        raise NotImplementedError()
+
+    def extra_repr(self):
+        return "n_bits={}, per_channel={}, is_initalized={}".format(self.n_bits, self.per_channel, self.is_initialized)
+
+    def reset(self):
+        self._delta = None
+
+
+def default_maxval(n_bits: int, mantissa_bits: int) -> float:
+    """fp8_quantizer.py:171-179: largest value of the format with the default integer bias."""
+    ebits = n_bits - mantissa_bits - 1
+    return (2 - 2 ** (-mantissa_bits)) * 2 ** (2**ebits - 1 - 2 ** (ebits - 1))
+
+
+class FPQuantizer(QuantizerBase):
+    """8-bit (runtime bit-split) floating-point fake quantiser -- fp8_quantizer.py:151-272."""
+
+    def __init__(self, *args, scale_domain=None, mantissa_bits=4, maxval=3, set_maxval=False, learn_maxval=False,
+                 learn_mantissa_bits=False, mse_include_mantissa_bits=True, allow_unsigned=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.ebits = self.n_bits - mantissa_bits - 1
+        self.default_bias = 2 ** (self.ebits - 1)
+        mv = maxval if maxval is not None else default_maxval(self.n_bits, mantissa_bits)
+        self._table = None
+        self._table_key = None
+        self._mbits_host = float(mantissa_bits)
+        self._mantissa_bits = torch.Tensor([float(mantissa_bits)])
+        self._maxval = torch.Tensor([mv])
+        self.set_maxval = set_maxval
+        self.learning_maxval = learn_maxval
+        self.learning_mantissa_bits = learn_mantissa_bits
+        self.mse_include_mantissa_bits = mse_include_mantissa_bits
+        self.allow_unsigned = allow_unsigned
+        self.sign_bits = 1
+
+    # -- attributes the reference exposes as plain tensors (fp8_quantizer.py:183-184) -----------
+    @property
+    def maxval(self):
+        return self._maxval
+
+    @maxval.setter
+    def maxval(self, value):
+        if not isinstance(value, torch.Tensor):
+            value = torch.Tensor([float(value)])
+        if value.dim() == 0:
+            value = value.reshape(1)
+        self._maxval = value
+        self._table_key = None
+
+    @property
+    def mantissa_bits(self):
+        return self._mantissa_bits
+
+    @mantissa_bits.setter
+    def mantissa_bits(self, value):
+        # The format split decides the table layout, so the host needs the value; a CUDA tensor
+        # assigned here costs one .item() -- the library itself never does that.
+        if isinstance(value, torch.Tensor):
+            self._mbits_host = float(value.detach().reshape(-1)[0].item())
+            self._mantissa_bits = value
+        else:
+            self._mbits_host = float(value)
+            self._mantissa_bits = torch.Tensor([float(value)])
+        self._table_key = None
+
+    # -- table management -------------------------------------------------------------------------
+    def _ensure_table(self, device):
+        mv = self._maxval
+        if mv.device != device or mv.dtype != torch.float32 or not mv.is_contiguous():
+            mv = mv.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._maxval = mv  # same lazy move as fp8_quantizer.py:195-196
+        key = (mv.data_ptr(), mv._version, mv.numel(), self._mbits_host, self.n_bits, self.sign_bits)
+        if key != self._table_key:
+            self._table = ops.prepare(mv.detach(), self._mbits_host, self.n_bits, self.sign_bits)
+            self._table_key = key
+        return self._table
+
+    def adopt_range(self, maxval: torch.Tensor, table: torch.Tensor):
+        """Install a (maxval, table) pair produced on device by the fused estimate/set-range kernels."""
+        self._maxval = maxval
+        self._table = table
+        self._table_key = (maxval.data_ptr(), maxval._version, maxval.numel(), self._mbits_host, self.n_bits,
+                           self.sign_bits)
+
+    @property
+    def table(self):
+        return self._table
+
+    def table_for(self, x: torch.Tensor):
+        """(table, C) for quantising ``x`` -- validates the channel layout like fp8_quantizer.py:108-109."""
+        table = self._ensure_table(x.device)
+        C = self._maxval.numel()
+        if C != 1:
+            if x.dim() == 0 or x.shape[0] != C:
+                raise Fp8fqError(f"per-channel maxval has {C} entries but x has shape {tuple(x.shape)}")
+        return table, C
+
+    # -- the hot path ---------------------------------------------------------------------------------
+    def forward(self, x_float):
+        if torch.is_grad_enabled() and (x_float.requires_grad or isinstance(self._maxval, nn.Parameter)):
+            raise Fp8fqError("FPQuantizer: forward-only engine (STE backward is SURVEY section 8 row f4); "
+                             "call under torch.no_grad()")
+        x = x_float if x_float.is_contiguous() else x_float.contiguous()
+        table, C = self.table_for(x)
+        return ops.fake_quant(x, table, C, self._mbits_host, self.n_bits, self.sign_bits)
+
+    def quantize_with_codes(self, x_float):
+        """(y, codes) -- test hook exposing the reference's intermediate integers (:128, :132)."""
+        x = x_float.contiguous()
+        table, C = self.table_for(x)
+        return ops.fake_quant_codes(x, table, C, self._mbits_host, self.n_bits, self.sign_bits)
+
+    # -- reference API ------------------------------------------------------------------------------
+    def is_initialized(self):  # a METHOD in the reference (fp8_quantizer.py:207-208): always truthy
+        return True
+
+    def symmetric(self):
+        return False
+
+    def effective_bit_width(self):
+        return None
+
+    def _make_unsigned(self, x_min):
+        if isinstance(x_min, torch.Tensor):
+            return self.allow_unsigned and bool(torch.all(x_min >= 0))
+        return self.allow_unsigned and x_min >= 0
+
+    def set_quant_range(self, x_min, x_max):
+        """fp8_quantizer.py:222-240.  ``maxval`` stays on the device (shape [C] or [1])."""
+        if self._make_unsigned(x_min):
+            self.sign_bits = 0  # sticky, as in the reference
+            self._table_key = None
+        if not self.set_maxval:
+            return
+        if not isinstance(x_max, torch.Tensor):
+            dev = self._maxval.device if self._maxval.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            x_max = torch.tensor([float(x_max)], dtype=torch.float32, device=dev)
+            x_min = torch.tensor([float(x_min)], dtype=torch.float32, device=dev)
+        if not isinstance(x_min, torch.Tensor):
+            x_min = torch.full_like(x_max, float(x_min))
+        if not x_max.is_cuda:
+            raise Fp8fqError("set_quant_range: range tensors must live on the GPU (no CPU path)")
+        x_min = x_min.detach().to(torch.float32).reshape(-1).contiguous()
+        x_max = x_max.detach().to(torch.float32).reshape(-1).contiguous()
+        if x_min.numel() != x_max.numel():
+            x_min = x_min.expand_as(x_max).contiguous()
+        maxval, table = ops.set_range_prepare(x_min, x_max, self._mbits_host, self.n_bits, self.sign_bits)
+        self.adopt_range(maxval, table)
+
+    def make_range_trainable(self):
+        if self.learning_maxval or self.learning_mantissa_bits:
+            raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+
+    def learn_maxval(self):
+        raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+
+    def learn_mantissa_bits(self):
+        raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+
+    def fix_ranges(self):
+        pass  # nothing is an nn.Parameter here (fp8_quantizer.py:256-260 only acts on Parameters)
+
+    def extra_repr(self):
+        M, E, _ = ops.format_split(self._mbits_host, self.n_bits, self.sign_bits)
+        tag = "[per_channel]" if self._maxval.numel() > 1 else "per_tensor"
+        return f"Exponent: {E} bits; mantissa: {M} bits; sign: {self.sign_bits}; maxval: {tag}"
+
+    def __deepcopy__(self, memo):
+        # LineSearchEstimator deep-copies its quantiser (range_estimators.py:201); tables are plain tensors
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._table_key = None
+        return new

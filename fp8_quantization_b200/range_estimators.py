@@ -1,0 +1,236 @@
+"""Drop-in range estimators backed by libfp8fq.so.
+
+Mirrors quantization/range_estimators.py of the reference:
+  RangeEstimatorBase :15-53, CurrentMinMaxEstimator :56-76, AllMinMaxEstimator :79-100,
+  RunningMinMaxEstimator :103-125, FP_MSE_Estimator :285-369, enum RangeEstimators :389-393.
+
+Each min/max estimator is ONE pass over x (the reference's x.min() + x.max() read it twice) with the
+state update done inside the kernel.  Under data parallelism (fp8_quantization_b200.dist) the
+batch statistic is all-reduced across ranks *before* the update rule is applied, so every rank
+ends up with the range a single process would have computed on the concatenated batch.
+"""
+from __future__ import annotations
+
+from enum import Flag, auto
+from collections import namedtuple
+from functools import partial
+
+import torch
+from torch import nn
+
+from . import dist as fq_dist
+from . import ops
+
+
+class BaseEnumOptions(Flag):  # utils/utils.py:297-304
+    def __str__(self):
+        return self.name
+
+    @classmethod
+    def list_names(cls):
+        return [m.name for m in cls]
+
+
+class ClassEnumOptions(BaseEnumOptions):  # utils/utils.py:307-313
+    @property
+    def cls(self):
+        return self.value.cls
+
+    def __call__(self, *args, **kwargs):
+        return self.value.cls(*args, **kwargs)
+
+
+MethodMap = partial(namedtuple("MethodMap", ["value", "cls"]), auto())  # utils/utils.py:315
+
+
+class NoDataPassedError(Exception):  # range_estimators.py:382-386
+    def __init__(self):
+        super().__init__("Data must be pass through the range estimator to be initialized")
+
+
+class RangeEstimatorBase(nn.Module):
+    """range_estimators.py:15-53."""
+
+    def __init__(self, per_channel=False, quantizer=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.register_buffer("current_xmin", None)
+        self.register_buffer("current_xmax", None)
+        self.per_channel = per_channel
+        self.quantizer = quantizer
+
+    def forward(self, x):
+        raise NotImplementedError()
+
+    def reset(self):
+        self.current_xmin = None
+        self.current_xmax = None
+
+    def __repr__(self):
+        lines = self.extra_repr().split("\n")
+        extra_str = lines[0] if len(lines) == 1 else "\n  " + "\n  ".join(lines) + "\n"
+        return self._get_name() + "(" + extra_str + ")"
+
+
+class _MinMaxEstimator(RangeEstimatorBase):
+    """Shared driver of the three min/max estimators: one fused kernel, optional DP all-reduce."""
+
+    EST_MODE = ops.EST_CURRENT
+    momentum = 0.9
+
+    def _state(self, x):
+        """(cur_min, cur_max, initialized) with state buffers of the right shape on x's device."""
+        C = x.shape[0] if self.per_channel else 1
+        init = self.current_xmin is not None
+        if init and (self.current_xmin.numel() != C or self.current_xmin.device != x.device):
+            if self.current_xmin.numel() != C:
+                raise ops.Fp8fqError("range estimator was initialised with a different channel count")
+            self.current_xmin = self.current_xmin.to(x.device)
+            self.current_xmax = self.current_xmax.to(x.device)
+        if not init:
+            self.current_xmin = torch.empty(C, dtype=torch.float32, device=x.device)
+            self.current_xmax = torch.empty(C, dtype=torch.float32, device=x.device)
+        return self.current_xmin, self.current_xmax, init
+
+    def forward(self, x):
+        x = x.detach()
+        x = x if x.is_contiguous() else x.contiguous()
+        if fq_dist.active():
+            return self._forward_dp(x)
+        cmin, cmax, init = self._state(x)
+        ops.minmax(x, self.per_channel, cmin, cmax, self.EST_MODE, init, self.momentum)
+        return self.current_xmin, self.current_xmax
+
+    def _forward_dp(self, x):
+        C = x.shape[0] if self.per_channel else 1
+        init = self.current_xmin is not None
+        packed = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        bmin, bmax = packed[:C], packed[C:]
+        ops.minmax(x, self.per_channel, bmin, bmax, ops.EST_CURRENT, False)
+        bmin.neg_()
+        fq_dist.all_reduce_max(packed)  # one collective for [-min, max]
+        bmin.neg_()
+        if not init or self.EST_MODE == ops.EST_CURRENT:
+            self.current_xmin, self.current_xmax = bmin.clone(), bmax.clone()
+        elif self.EST_MODE == ops.EST_ALL:
+            self.current_xmin = torch.min(self.current_xmin, bmin)
+            self.current_xmax = torch.max(self.current_xmax, bmax)
+        else:
+            m = self.momentum
+            self.current_xmin = (1 - m) * bmin + m * self.current_xmin
+            self.current_xmax = (1 - m) * bmax + m * self.current_xmax
+        return self.current_xmin, self.current_xmax
+
+    def fused_supported(self) -> bool:
+        return not fq_dist.active()
+
+    def fused_estimate_prepare(self, x, quantizer):
+        """estimator update + set_quant_range + table in ONE launch; installs the result in ``quantizer``."""
+        x = x.detach()
+        x = x if x.is_contiguous() else x.contiguous()
+        cmin, cmax, init = self._state(x)
+        C = cmin.numel()
+        mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
+        maxval = torch.empty(C, dtype=torch.float32, device=x.device)
+        table = ops.new_table(C, mb, nb, sb, x.device)
+        ops.estimate_prepare(x, self.per_channel, cmin, cmax, self.EST_MODE, init, self.momentum, maxval, mb, nb, sb,
+                             table)
+        quantizer.adopt_range(maxval, table)
+        return x
+
+
+class CurrentMinMaxEstimator(_MinMaxEstimator):
+    """range_estimators.py:56-76 (the percentile branch is unreachable from the reference's CLI:
+    hijacker.py:57 compares a class with an enum member)."""
+
+    EST_MODE = ops.EST_CURRENT
+
+    def __init__(self, percentile=None, *args, **kwargs):
+        self.percentile = percentile
+        super().__init__(*args, **kwargs)
+        if percentile:
+            raise NotImplementedError("percentile ranges are a host/numpy path in the reference, out of scope")
+
+
+class AllMinMaxEstimator(_MinMaxEstimator):
+    """range_estimators.py:79-100."""
+
+    EST_MODE = ops.EST_ALL
+
+
+class RunningMinMaxEstimator(_MinMaxEstimator):
+    """range_estimators.py:103-125."""
+
+    EST_MODE = ops.EST_RUNNING
+
+    def __init__(self, momentum=0.9, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.momentum = momentum
+
+
+class OptMethod(BaseEnumOptions):  # range_estimators.py:128-130
+    grid = auto()
+    golden_section = auto()
+
+
+class FP_MSE_Estimator(RangeEstimatorBase):
+    """range_estimators.py:285-369 with the 111..666-iteration Python loop replaced by one kernel
+    launch per mantissa width that reads x once and sweeps all 111 candidate ranges in registers."""
+
+    NUM_GRID = 111  # range_estimators.py:306; num_candidates / range_margin are ignored there too
+
+    def __init__(self, num_candidates=100, opt_method=OptMethod.grid, range_margin=0.5, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert opt_method == OptMethod.grid
+        self.num_candidates = num_candidates
+        self.mses = self.search_grid = None
+
+    def _define_search_range(self, x, mbit_list):  # :295-316
+        if self.search_grid is None:
+            assert self.mses is None
+            C = x.shape[0] if self.per_channel else 1
+            packed = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+            ops.minmax(x, self.per_channel, packed[:C], packed[C:], ops.EST_CURRENT, False)
+            absmax = torch.max(packed[:C].abs(), packed[C:].abs())
+            if fq_dist.active():
+                fq_dist.all_reduce_max(absmax)
+            # The reference builds the grid on the host from .item() values with torch.linspace; do the
+            # same (one D2H copy of C floats, once per estimator) so the grid is bit-identical.
+            vals = absmax.cpu().tolist()
+            lsp = [torch.linspace(0.1 * v, 1.2 * v, self.NUM_GRID) for v in vals]
+            self.search_grid = torch.stack(lsp).to(x.device).transpose(0, 1).contiguous()  # [111, C]
+            self.mses = torch.zeros(len(mbit_list), self.NUM_GRID, C, dtype=torch.float32, device=x.device)
+        return self.search_grid, self.mses
+
+    def forward(self, x):  # :318-369
+        qz = self.quantizer
+        x = x.detach()
+        x = x if x.is_contiguous() else x.contiguous()
+        mbit_list = [float(qz._mbits_host)]
+        if qz.mse_include_mantissa_bits:
+            mbit_list = [float(m) for m in range(1, qz.n_bits - qz.sign_bits)]
+        grid, mses = self._define_search_range(x, mbit_list)
+        assert mses.shape[1:] == grid.shape, f"{mses.shape}, {grid.shape}"
+        sign_bits = int(torch.any(x < 0)) if qz.allow_unsigned else 1
+        if qz.allow_unsigned and sign_bits == 0:
+            qz.sign_bits = 0  # what set_quant_range(-0.0 * maxval, maxval) does in the reference loop (:341-342)
+        if fq_dist.active():
+            inc = torch.zeros_like(mses)
+            ops.mse_grid(x, self.per_channel, grid, mbit_list, qz.n_bits, qz.sign_bits, inc)
+            fq_dist.all_reduce_mean(inc)
+            mses += inc
+        else:
+            ops.mse_grid(x, self.per_channel, grid, mbit_list, qz.n_bits, qz.sign_bits, mses)
+        best_mbits_per_channel = mses.min(1)[0].argmin(0)
+        best_idx = int(torch.mode(best_mbits_per_channel).values.item())
+        best_mbits = float(mbit_list[best_idx])
+        arg = mses[best_idx].argmin(0)  # [C]
+        maxval = grid.gather(0, arg.view(1, -1)).reshape(-1)
+        qz.mantissa_bits = best_mbits
+        return sign_bits * -1.0 * maxval, maxval
+
+
+class RangeEstimators(ClassEnumOptions):  # range_estimators.py:389-393
+    current_minmax = MethodMap(CurrentMinMaxEstimator)
+    allminmax = MethodMap(AllMinMaxEstimator)
+    running_minmax = MethodMap(RunningMinMaxEstimator)
+    MSE = MethodMap(FP_MSE_Estimator)

@@ -1,0 +1,329 @@
+"""The two quantised CNN workloads of the reference, built on this package's module layer, plus the
+validate-quantized flow.  (They are the *callers* of the hot path -- SURVEY.md section 8 rows a12,
+a15, a16 -- needed on the GPU box where the reference checkout does not exist.)
+
+Mirrors:
+  QuantizedBlock / QuantizedResNet / resnet18_quantized   models/resnet_quantized.py:14-167
+  MobileNetV2 (fp32 definition)                            models/mobilenet_v2.py:16-132
+  QuantizedInvertedResidual / QuantizedMobileNetV2         models/mobilenet_v2_quantized.py:15-113
+  pass_data_for_range_estimation                           quantization/utils.py:74-115
+  validate_quantized (flow)                                image_net.py:48-96
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import dist as fq_dist
+from .modules import (BNQConv, FP32Acts, Flattener, QuantizedActivation, QuantizedActivationWrapper, QuantizedModel,
+                      quantize_model, quantize_sequential)
+from .quantizers import FPQuantizer
+from .range_estimators import AllMinMaxEstimator, CurrentMinMaxEstimator
+
+
+# ---------------------------------------------------------------------------------------------------
+# ResNet
+# ---------------------------------------------------------------------------------------------------
+class QuantizedBlock(QuantizedActivation):
+    """models/resnet_quantized.py:14-46."""
+
+    def __init__(self, block, **quant_params):
+        super().__init__(**quant_params)
+        from torchvision.models.resnet import BasicBlock, Bottleneck
+
+        if isinstance(block, Bottleneck):
+            features = nn.Sequential(block.conv1, block.bn1, block.relu, block.conv2, block.bn2, block.relu,
+                                     block.conv3, block.bn3)
+        elif isinstance(block, BasicBlock):
+            features = nn.Sequential(block.conv1, block.bn1, block.relu, block.conv2, block.bn2)
+        else:
+            raise ValueError(f"unsupported residual block {type(block)}")
+        self.features = quantize_model(features, **quant_params)
+        self.downsample = quantize_model(block.downsample, **quant_params) if block.downsample else None
+        self.relu = block.relu
+
+    def forward(self, x):
+        residual = x if self.downsample is None else self.downsample(x)
+        out = self.features(x)
+        # out += residual; relu; quantise  -> one fused kernel when ranges are fixed
+        return self.add_act_quantize(out, residual, self.relu)
+
+
+class QuantizedResNet(QuantizedModel):
+    """models/resnet_quantized.py:49-133."""
+
+    def __init__(self, resnet, input_size=(1, 3, 224, 224), quant_setup=None, **quant_params):
+        super().__init__(input_size)
+        from torchvision.models.resnet import BasicBlock, Bottleneck
+
+        specials = {BasicBlock: QuantizedBlock, Bottleneck: QuantizedBlock}
+        stem = [resnet.conv1, resnet.bn1, resnet.relu]
+        if hasattr(resnet, "maxpool"):
+            stem.append(resnet.maxpool)
+        features = nn.Sequential(*stem, resnet.layer1, resnet.layer2, resnet.layer3, resnet.layer4)
+        self.features = quantize_model(features, specials=specials, **quant_params)
+
+        if quant_setup and quant_setup == "LSQ_paper":
+            self.avgpool = resnet.avgpool
+        else:
+            self.avgpool = QuantizedActivationWrapper(
+                resnet.avgpool, tie_activation_quantizers=True,
+                input_quantizer=self.features[-1][-1].activation_quantizer, **quant_params)
+        self.flattener = Flattener()
+        self.fc = quantize_model(resnet.fc, **quant_params)
+
+        if quant_setup == "LSQ":
+            print("Set quantization to LSQ (first+last layer in 8 bits)")
+            self.features[0].weight_quantizer.quantizer.n_bits = 8
+            self.features[-1][-1].activation_quantizer.quantizer.n_bits = 8
+            self.features[-1][-1].features[-1].activation_quantizer.quantizer.n_bits = 8
+            self.fc.weight_quantizer.quantizer.n_bits = 8
+            self.fc.activation_quantizer = FP32Acts()
+        elif quant_setup == "LSQ_paper":
+            self.features[0].activation_quantizer = FP32Acts()
+            self.features[0].weight_quantizer.quantizer.n_bits = 8
+            self.fc.activation_quantizer.quantizer.n_bits = 8
+            self.fc.weight_quantizer.quantizer.n_bits = 8
+            for layer in self.features.modules():
+                if isinstance(layer, QuantizedActivation):
+                    layer.activation_quantizer = FP32Acts()
+        elif quant_setup == "FP_logits":
+            print("Do not quantize output of FC layer")
+            self.fc.activation_quantizer = FP32Acts()
+        elif quant_setup == "fc4":
+            self.features[0].weight_quantizer.quantizer.n_bits = 8
+            self.fc.weight_quantizer.quantizer.n_bits = 4
+        elif quant_setup is not None and quant_setup != "all":
+            raise ValueError("Quantization setup '{}' not supported for Resnet".format(quant_setup))
+
+    def forward(self, x):
+        x = self.features(x)
+        x = self.avgpool(x)
+        x = self.flattener(x)
+        return self.fc(x)
+
+
+def resnet18_quantized(pretrained=False, model_dir=None, load_type="fp32", **qparams):
+    """models/resnet_quantized.py:136-150.  No network on the GPU box -> random init unless a
+    state dict is given (``pretrained`` must stay False)."""
+    from torchvision.models import resnet18
+
+    if pretrained:
+        raise ValueError("pretrained weights cannot be downloaded here; load a state dict explicitly")
+    model = QuantizedResNet(resnet18(), **qparams)
+    if load_type == "quantized":
+        model.load_state_dict(torch.load(model_dir))
+    elif load_type != "fp32":
+        raise ValueError("wrong load_type specified")
+    return model
+
+
+def resnet50_quantized(pretrained=False, model_dir=None, load_type="fp32", **qparams):
+    from torchvision.models import resnet50
+
+    if pretrained:
+        raise ValueError("pretrained weights cannot be downloaded here; load a state dict explicitly")
+    model = QuantizedResNet(resnet50(), **qparams)
+    if load_type == "quantized":
+        model.load_state_dict(torch.load(model_dir))
+    elif load_type != "fp32":
+        raise ValueError("wrong load_type specified")
+    return model
+
+
+# ---------------------------------------------------------------------------------------------------
+# MobileNetV2
+# ---------------------------------------------------------------------------------------------------
+def _conv_bn_relu6(cin, cout, k, stride, groups=1):
+    return [nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, groups=groups, bias=False), nn.BatchNorm2d(cout),
+            nn.ReLU6(inplace=True)]
+
+
+class InvertedResidual(nn.Module):
+    """models/mobilenet_v2.py:28-69: (1x1 expand) -> 3x3 depthwise -> 1x1 linear projection."""
+
+    def __init__(self, inp, oup, stride, expand_ratio):
+        super().__init__()
+        assert stride in (1, 2)
+        self.stride = stride
+        hidden = round(inp * expand_ratio)
+        self.use_res_connect = stride == 1 and inp == oup
+        layers = []
+        if expand_ratio != 1:
+            layers += _conv_bn_relu6(inp, hidden, 1, 1)
+        layers += _conv_bn_relu6(hidden, hidden, 3, stride, groups=hidden)
+        layers += [nn.Conv2d(hidden, oup, 1, 1, 0, bias=False), nn.BatchNorm2d(oup)]
+        self.conv = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return x + self.conv(x) if self.use_res_connect else self.conv(x)
+
+
+class MobileNetV2(nn.Module):
+    """models/mobilenet_v2.py:72-132 (the tonylins/pytorch-mobilenet-v2 layout the reference uses)."""
+
+    SETTINGS = [  # expansion t, channels c, repeats n, stride s
+        (1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+
+    def __init__(self, n_class=1000, input_size=224, width_mult=1.0, dropout=0.0):
+        super().__init__()
+        assert input_size % 32 == 0
+        cin = int(32 * width_mult)
+        self.last_channel = int(1280 * width_mult) if width_mult > 1.0 else 1280
+        features = [nn.Sequential(*_conv_bn_relu6(3, cin, 3, 2))]
+        for t, c, n, s in self.SETTINGS:
+            cout = int(c * width_mult)
+            for i in range(n):
+                features.append(InvertedResidual(cin, cout, s if i == 0 else 1, expand_ratio=t))
+                cin = cout
+        features.append(nn.Sequential(*_conv_bn_relu6(cin, self.last_channel, 1, 1)))
+        features.append(nn.AvgPool2d(input_size // 32))
+        self.features = nn.Sequential(*features)
+        self.classifier = nn.Sequential(nn.Dropout(dropout), nn.Linear(self.last_channel, n_class))
+        self._initialize_weights()
+
+    def forward(self, x):
+        x = self.features(x)
+        x = F.adaptive_avg_pool2d(x, 1).squeeze()
+        return self.classifier(x)
+
+    def _initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+            elif isinstance(m, nn.Linear):
+                m.weight.data.normal_(0, 0.01)
+                m.bias.data.zero_()
+
+
+class QuantizedInvertedResidual(QuantizedActivation):
+    """models/mobilenet_v2_quantized.py:15-26."""
+
+    def __init__(self, inv_res_orig, **quant_params):
+        super().__init__(**quant_params)
+        self.use_res_connect = inv_res_orig.use_res_connect
+        self.conv = quantize_sequential(inv_res_orig.conv, **quant_params)
+
+    def forward(self, x):
+        if self.use_res_connect:
+            return self.add_act_quantize(x, self.conv(x), None)  # Q(x + conv(x))
+        return self.conv(x)
+
+
+class QuantizedMobileNetV2(QuantizedModel):
+    """models/mobilenet_v2_quantized.py:29-92."""
+
+    def __init__(self, model_fp, input_size=(1, 3, 224, 224), quant_setup=None, **quant_params):
+        super().__init__(input_size)
+        specials = {InvertedResidual: QuantizedInvertedResidual}
+        quantize_input = quant_setup and quant_setup == "LSQ_paper"
+        self.features = quantize_sequential(model_fp.features, tie_activation_quantizers=not quantize_input,
+                                            specials=specials, **quant_params)
+        self.flattener = Flattener()
+        self.classifier = quantize_model(model_fp.classifier, **quant_params)
+
+        if quant_setup == "FP_logits":
+            print("Do not quantize output of FC layer")
+            self.classifier[1].activation_quantizer = FP32Acts()
+        elif quant_setup == "fc4":
+            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
+            self.classifier[1].weight_quantizer.quantizer.n_bits = 4
+        elif quant_setup == "fc4_dw8":
+            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
+            self.classifier[1].weight_quantizer.quantizer.n_bits = 4
+            for name, module in self.named_modules():
+                if isinstance(module, BNQConv) and module.groups == module.in_channels:
+                    module.weight_quantizer.quantizer.n_bits = 8
+        elif quant_setup == "LSQ":
+            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
+            self.features[-2][0].activation_quantizer.quantizer.n_bits = 8
+            self.classifier[1].weight_quantizer.quantizer.n_bits = 8
+            self.classifier[1].activation_quantizer = FP32Acts()
+        elif quant_setup == "LSQ_paper":
+            self.features[0][0].activation_quantizer = FP32Acts()
+            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
+            self.classifier[1].weight_quantizer.quantizer.n_bits = 8
+            self.classifier[1].activation_quantizer.quantizer.n_bits = 8
+            for layer in self.features.modules():
+                if isinstance(layer, QuantizedActivation):
+                    layer.activation_quantizer = FP32Acts()
+        elif quant_setup is not None and quant_setup != "all":
+            raise ValueError("Quantization setup '{}' not supported for MobilenetV2".format(quant_setup))
+
+    def forward(self, x):
+        x = self.features(x)
+        x = self.flattener(x)
+        return self.classifier(x)
+
+
+def mobilenetv2_quantized(pretrained=False, model_dir=None, load_type="fp32", **qparams):
+    """models/mobilenet_v2_quantized.py:95-113; random init unless a state dict path is given."""
+    fp_model = MobileNetV2()
+    if load_type == "fp32":
+        if pretrained:
+            fp_model.load_state_dict(torch.load(model_dir))
+        return QuantizedMobileNetV2(fp_model, **qparams)
+    if load_type == "quantized":
+        model = QuantizedMobileNetV2(fp_model, **qparams)
+        model.load_state_dict(torch.load(model_dir), strict=False)
+        return model
+    raise ValueError("wrong load_type specified")
+
+
+# ---------------------------------------------------------------------------------------------------
+# configuration + flow
+# ---------------------------------------------------------------------------------------------------
+def readme_quant_params(mantissa_bits: int, *, method=FPQuantizer, weight_range_method=CurrentMinMaxEstimator,
+                        act_range_method=AllMinMaxEstimator, mse_include_mantissa_bits=False, act_range_options=None,
+                        weight_range_options=None, allow_unsigned=False):
+    """The kwargs dict utils/click_options.py:477-510 produces for the README command line
+    (README.md:63-68): --n-bits 8 --per-channel --quant-setup all --qmethod fp_quantizer
+    --fp8-mantissa-bits=M --fp8-set-maxval --no-fp8-mse-include-mantissa-bits
+    --weight-quant-method=current_minmax --act-quant-method=allminmax."""
+    return dict(
+        method=method, n_bits=8, n_bits_act=None, act_method=method, per_channel_weights=True, quant_setup="all",
+        weight_range_method=weight_range_method, weight_range_options=weight_range_options or {},
+        act_range_method=act_range_method, act_range_options=act_range_options or {}, quantize_input=False,
+        fp8_kwargs=dict(maxval=None, mantissa_bits=mantissa_bits, set_maxval=True, learn_maxval=False,
+                        learn_mantissa_bits=False, mse_include_mantissa_bits=mse_include_mantissa_bits,
+                        allow_unsigned=allow_unsigned))
+
+
+def pass_data_for_range_estimation(batches, model, act_quant=True, weight_quant=True, max_num_batches=1):
+    """quantization/utils.py:74-115: calibration forward passes in eval mode under no_grad."""
+    model.set_quant_state(weight_quant, act_quant)
+    model.eval()
+    with torch.no_grad():
+        for i, x in enumerate(batches):
+            model(x)
+            if i >= max_num_batches - 1 or not act_quant:
+                break
+
+
+@torch.no_grad()
+def validate(model, batches, labels=None):
+    """image_net.py:72-96 without ignite: top-1 / top-5 / mean CE loss over ``batches``; under data
+    parallelism the four counters are summed across ranks with one all-reduce."""
+    stats = None
+    for i, x in enumerate(batches):
+        logits = model(x)
+        y = labels[i] if labels is not None else torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
+        top5 = logits.topk(5, dim=1).indices
+        c1 = (top5[:, 0] == y).sum()
+        c5 = (top5 == y[:, None]).any(dim=1).sum()
+        loss = F.cross_entropy(logits, y, reduction="sum")
+        cur = torch.stack([c1.float(), c5.float(), loss.float(), torch.tensor(float(x.shape[0]), device=x.device)])
+        stats = cur if stats is None else stats + cur
+    if fq_dist.world_size() > 1:
+        fq_dist.all_reduce_sum(stats)
+    c1, c5, loss, n = stats.tolist()
+    return dict(top_1_accuracy=c1 / n, top_5_accuracy=c5 / n, loss=loss / n, count=int(n))

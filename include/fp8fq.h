@@ -1,0 +1,157 @@
+/*
+ * fp8fq.h -- C ABI of libfp8fq.so, the B200 (sm_100a) FP8 fake-quantization engine.
+ *
+ * This is the drop-in boundary for the hot path of Qualcomm-AI-research/FP8-quantization
+ * (reference paths below are relative to the reference checkout).  The reference has no
+ * native code at all; what a maintainer would bind is listed per entry point as the Python
+ * function the call replaces.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - All `const float*` / `float*` arguments are DEVICE pointers owned by the caller unless the
+ *     name ends in `_host`.  The library never allocates device memory, keeps no global state
+ *     and is re-entrant; every call is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*) and CUDA-graph capturable (no host synchronisation, no D2H reads) -- except the
+ *     `*_host_*` entry points, which own their staging buffers and synchronise before returning.
+ *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = FP8FQ_ERR_* argument error.  Never throws.
+ *   - Tensors are contiguous fp32.  "per-channel" means channel = dim 0 (reference
+ *     fp8_quantizer.py:108-109), i.e. a [C, inner] row-major view.
+ *   - The FP format is given at run time exactly as the reference carries it: `n_bits`,
+ *     `sign_bits` and the float `mantissa_bits`; M = clamp(round_half_even(mantissa_bits), 1,
+ *     n_bits - sign_bits), E = n_bits - sign_bits - M (fp8_quantizer.py:105-106).
+ *     Supported: E <= 7 (at most 127 exponent codes), M <= 12.
+ *
+ * Quantisation parameters ("table")
+ *   Everything the reference derives per channel from (maxval, M, E) -- `bias`
+ *   (fp8_quantizer.py:110), the clamp bounds (:112-113) and, per exponent code e in
+ *   [1, max(1, 2^E - 1)], the scale 2^(e - M - bias) (:130) and the |x| threshold at which
+ *   floor(log2|x| + bias) steps to e (:128) -- is computed ONCE by fp8fq_prepare_f32 into a
+ *   caller-owned device buffer of fp8fq_table_floats(...) floats and then consumed by the
+ *   streaming kernels.  Layout (floats, per channel, stride = fp8fq_table_stride(...)):
+ *     [0] maxval  [1] minval  [2] bucket base (int bits)  [3] bias  [4] flags (int bits)
+ *     [5] K (int bits)  [6..7] reserved
+ *     [8 .. 8+KP)            thr[j], j = 0..K      (KP = K+1 rounded up to even)
+ *     [8+KP .. 8+KP+2(K+1))  (scale, 1/scale)[e'], e' = 0..K
+ */
+#ifndef FP8FQ_H
+#define FP8FQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP8FQ_OK 0
+#define FP8FQ_ERR_BAD_ARG (-1)       /* null pointer, negative size, n != C*inner ... */
+#define FP8FQ_ERR_UNSUPPORTED (-2)   /* E > 7 or M > 12 */
+#define FP8FQ_ERR_ALIGNMENT (-3)     /* pointer not 4-byte aligned */
+#define FP8FQ_ERR_WORKSPACE (-4)     /* workspace too small */
+
+/* activation applied before quantisation by the fused entry points
+ * (quantized_folded_bn.py:50-51, models/resnet_quantized.py:44) */
+#define FP8FQ_ACT_NONE 0
+#define FP8FQ_ACT_RELU 1
+#define FP8FQ_ACT_RELU6 2
+
+/* range-estimator update rule applied to (current_xmin, current_xmax) */
+#define FP8FQ_EST_CURRENT 0 /* CurrentMinMaxEstimator, range_estimators.py:61-76  (overwrite) */
+#define FP8FQ_EST_ALL 1     /* AllMinMaxEstimator,     range_estimators.py:83-100 (running min/max) */
+#define FP8FQ_EST_RUNNING 2 /* RunningMinMaxEstimator, range_estimators.py:108-125 (EMA) */
+
+/* library / build introspection */
+int fp8fq_version(void);
+const char* fp8fq_build_info(void);
+
+/* Host helpers (no CUDA): format split and table sizing. */
+int fp8fq_format_split(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K);
+int64_t fp8fq_table_stride(float mantissa_bits, int n_bits, int sign_bits);
+int64_t fp8fq_table_floats(float mantissa_bits, int n_bits, int sign_bits, int64_t C);
+
+/* Replaces: the (M, E, bias) prologue of quantize_to_fp8_ste_MM (fp8_quantizer.py:105-113) plus
+ * the per-code evaluation of :128 and :130.  `maxval` is [C] on the device. */
+int fp8fq_prepare_f32(const float* maxval, int64_t C, float mantissa_bits, int n_bits, int sign_bits,
+                      float* table, void* stream);
+
+/* Replaces: FPQuantizer.set_quant_range (fp8_quantizer.py:222-240) followed by the prologue above:
+ * maxval[c] = | max(|xmin[c]|, xmax[c]) |, written to `maxval_out` ([C]) and turned into `table`. */
+int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C, float* maxval_out,
+                                float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                void* stream);
+
+/* Replaces: FPQuantizer.forward / quantize_to_fp8_ste_MM (fp8_quantizer.py:91-133,194-205).
+ * x, y: [n] = [C, inner]; C == 1 is the per-tensor case.  y may alias x. */
+int fp8fq_fake_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C,
+                         int64_t inner, float mantissa_bits, int n_bits, int sign_bits, void* stream);
+
+/* Same, additionally writing the reference's intermediate integers for parity tests:
+ * codes[i] = (sign << 31) | (e << 16) | q, with e = log_scales (:128) and q = |round(xc/scales)|
+ * (:132); NaN -> 0x7fffffff. */
+int fp8fq_fake_quant_codes_f32(const float* x, float* y, int32_t* codes, const float* table, int64_t n,
+                               int64_t C, int64_t inner, float mantissa_bits, int n_bits,
+                               int sign_bits, void* stream);
+
+/* Replaces: BNFusedHijacker.forward's epilogue (quantized_folded_bn.py:39-55): eval-mode
+ * F.batch_norm -> activation -> per-tensor activation quantiser, one pass, 8 B/element.
+ * x, y: [rows, hw] with channel(row) = row % Cbn (NCHW contiguous: rows = N*Cbn, hw = H*W).
+ * bn_scale/bn_shift: [Cbn] from fp8fq_bn_fold_f32.  `table` is a per-tensor (C == 1) table.
+ * bn_mode 0: y = fma(x, scale, shift); 1: y = (x * scale) + shift with two roundings. */
+int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift,
+                           int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table,
+                           float mantissa_bits, int n_bits, int sign_bits, void* stream);
+
+/* Per-channel affine form of eval-mode batch norm: scale = gamma * rsqrt(var + eps) (as 1/sqrt),
+ * shift = beta - mean * scale.  All [Cbn]. */
+int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, const float* beta,
+                      float eps, int64_t Cbn, float* bn_scale, float* bn_shift, void* stream);
+
+/* Replaces: QuantizedBlock.forward's tail (models/resnet_quantized.py:43-46) and
+ * QuantizedInvertedResidual.forward (models/mobilenet_v2_quantized.py:22-24):
+ * y = Q(act(a + b)), one pass, 12 B/element. */
+int fp8fq_add_act_quant_f32(const float* a, const float* b, float* y, int64_t n, int act,
+                            const float* table, float mantissa_bits, int n_bits, int sign_bits,
+                            void* stream);
+
+/* Replaces: the min/max of every range estimator (range_estimators.py:73-74, 85-91, 110-116) and
+ * its update rule, NaN-propagating like torch.min/max.  One pass over x (4 B/element).
+ *   per-tensor (C == 1): two-stage reduce finished by the last CTA; `workspace` must hold
+ *   fp8fq_minmax_workspace_bytes() bytes, zero-initialised once (the kernel leaves it zeroed).
+ *   cur_min/cur_max: [C] estimator state, updated in place according to `est_mode`;
+ *   `initialized` != 0 means the state already holds a previous estimate.
+ *   `momentum` is a double because the reference's EMA weights are Python floats:
+ *   (float)(1.0 - momentum) and (float)momentum (range_estimators.py:121-123). */
+int64_t fp8fq_minmax_workspace_bytes(void);
+int fp8fq_minmax_f32(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min, float* cur_max,
+                     int est_mode, int initialized, double momentum, void* workspace, void* stream);
+
+/* Calibration fast path = estimator + set_quant_range + prologue in one launch chain, all on device:
+ * QuantizationManager.forward in state estimate_ranges (quantization_manager.py:114-122) up to, not
+ * including, the quantiser call.  Equivalent to fp8fq_minmax_f32 + fp8fq_set_range_prepare_f32. */
+int fp8fq_estimate_prepare_f32(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min,
+                               float* cur_max, int est_mode, int initialized, double momentum,
+                               float* maxval_out, float mantissa_bits, int n_bits, int sign_bits,
+                               float* table, void* workspace, void* stream);
+
+/* Replaces: the double Python loop of FP_MSE_Estimator.forward (range_estimators.py:337-347):
+ * mses[m, g, c] += mean over the non-channel elements of (x - Q(x; maxval = grid[g, c], M = mbits[m]))^2.
+ * grid: [G, C] device; mbits_host: [Mn] HOST floats; mses: [Mn, G, C] device, accumulated.
+ * tables: caller-owned device scratch of fp8fq_mse_table_floats(...) floats. */
+int64_t fp8fq_mse_table_floats(const float* mbits_host, int Mn, int n_bits, int sign_bits, int64_t G,
+                               int64_t C);
+int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, const float* grid, int64_t G,
+                       const float* mbits_host, int Mn, int n_bits, int sign_bits, float* mses,
+                       float* tables, void* stream);
+
+/* End-to-end entry point with HOST buffers (what a caller without device memory binds):
+ * chunked H2D -> fake-quant -> D2H pipeline over internal pinned staging and `nstreams` streams.
+ * maxval_host: [C].  Synchronises before returning. */
+int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* maxval_host, int64_t n,
+                              int64_t C, int64_t inner, float mantissa_bits, int n_bits, int sign_bits,
+                              int device);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t fp8fq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FP8FQ_H */

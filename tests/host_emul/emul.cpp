@@ -1,0 +1,75 @@
+// tests/host_emul/emul.cpp -- host build of the product's table/bucket/tie-guard algorithm
+// (fp8_quantization_b200/csrc/fp8fq_core.h) so its logic can be tested without a GPU.  TEST ONLY:
+// the product has no CPU path; this file is never part of libfp8fq.so.
+#include <stdint.h>
+#include <vector>
+#include "../../fp8_quantization_b200/csrc/fp8fq_core.h"
+
+using namespace fp8fq;
+
+extern "C" {
+
+int emul_table_stride(float mantissa_bits, int n_bits, int sign_bits) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  return table_stride(K);
+}
+
+// serial equivalent of prepare_kernel
+int emul_prepare(const float* maxval, int64_t C, float mantissa_bits, int n_bits, int sign_bits, float* table) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  const int stride = table_stride(K);
+  for (int64_t c = 0; c < C; ++c) {
+    float* tab = table + c * stride;
+    const float bias = prep_header(tab, maxval[c], M, E, K, sign_bits);
+    for (int k = 1; k <= K; ++k) prep_entry(tab, k, M, K, bias);
+    prep_finish(tab, K, maxval[c]);
+  }
+  return 0;
+}
+
+// serial equivalent of quant_elem<1, true> over a [C, inner] tensor; force_irregular exercises the
+// linear-search lookup; codes as in fp8fq_fake_quant_codes_f32
+int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table, int64_t C, int64_t inner,
+                    float mantissa_bits, int n_bits, int sign_bits, int force_irregular, int64_t* slow_count) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  const int stride = table_stride(K);
+  int64_t slow = 0;
+  for (int64_t c = 0; c < C; ++c) {
+    const float* tab = table + c * stride;
+    const float hi = tab[H_HI], lo = tab[H_LO], guard = tab[H_GUARD];
+    const uint32_t base = f2u(tab[H_BASE]);
+    const bool irregular = force_irregular || (f2u(tab[H_FLAGS]) & FLAG_IRREGULAR);
+    for (int64_t i = 0; i < inner; ++i) {
+      const float v = x[c * inner + i];
+      const float xc = min_nan(max_nan(v, lo), hi);
+      const float a = fabsf(xc);
+      int e = lookup_code(a, tab, K, base, irregular, [](const float* p) { return *p; });
+      const float s = tab[off_sr(K) + 2 * e], rs = tab[off_sr(K) + 2 * e + 1];
+      e = e < 1 ? 1 : e;
+      float q;
+      {  // count how often the exact-division fallback fires
+        float r = mul_rn(xc, rs);
+        float qq = nearbyintf(r);
+        if (!(fabsf(r - qq) < guard)) ++slow;
+      }
+      const float yy = quant_core(xc, s, rs, guard, &q);
+      y[c * inner + i] = yy;
+      if (codes) {
+        if (yy != yy) codes[c * inner + i] = 0x7fffffff;
+        else codes[c * inner + i] = (int32_t)((f2u(yy) & 0x80000000u) | ((uint32_t)e << 16) | (uint32_t)fabsf(q));
+      }
+    }
+  }
+  if (slow_count) *slow_count = slow;
+  return 0;
+}
+
+int emul_table_flags(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  return (int)f2u(table[c * table_stride(K) + H_FLAGS]);
+}
+}
