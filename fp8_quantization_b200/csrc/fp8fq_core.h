@@ -153,12 +153,12 @@ FQ_HD bool ref_code_ge(float a, float bias, float k) {
   return v >= k;  // NaN -> false
 }
 // Smallest positive float a with ref_code_ge(a, bias, k), by bisection on the float ordering
-// (positive floats order like their bit patterns).  +inf if there is none.
+// (positive floats order like their bit patterns).  NaN ("a >= NaN" is never true) if there is none.
 FQ_HD float find_threshold(float bias, int k) {
   const float kf = (float)k;
   uint32_t lo = 0u;            // invariant: code(lo) < k   (a = +0 -> log2 = -inf)
   uint32_t hi = 0x7f800000u;   // invariant: code(hi) >= k, or hi == +inf
-  if (!ref_code_ge(u2f(hi), bias, kf)) return u2f(0x7f800000u);
+  if (!ref_code_ge(u2f(hi), bias, kf)) return u2f(0x7fc00000u);  // never reached: NaN compares false
   if (ref_code_ge(u2f(1u), bias, kf)) return u2f(1u);
   lo = 1u;
   // narrow bracket around the analytic switching point 2^(k - bias) first
@@ -203,8 +203,8 @@ FQ_HD float prep_header(float* tab, float mv, int M, int E, int K, int sign_bits
   tab[H_K] = u2f((uint32_t)K);
   tab[H_GUARD] = tie_guard(M);
   tab[7] = 0.0f;
-  thr[0] = u2f(0x7f800000u);
-  for (int j = K; j < k_pad(K); ++j) thr[j] = u2f(0x7f800000u);
+  thr[0] = u2f(0x7fc00000u);  // NaN: "a >= thr" is false for every a, including +inf
+  for (int j = K; j < k_pad(K); ++j) thr[j] = u2f(0x7fc00000u);
   return bias;
 }
 // step 2 (any thread, k = 1..K): scale pair of code k and the threshold at which code k starts

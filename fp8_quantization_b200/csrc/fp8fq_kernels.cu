@@ -228,7 +228,7 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, i
   c.irregular = (f2u(smem[H_FLAGS]) & FLAG_IRREGULAR) != 0;
   c.stab = smem;
   if (KMODE == 0) {
-    const float inf = __int_as_float(0x7f800000);
+    const float inf = __int_as_float(0x7fc00000);  // NaN: never selected
     const float* thr = smem + kHdr;
     const float* sr = smem + off_sr(K);
     c.rt.t2 = K >= 2 ? thr[1] : inf;

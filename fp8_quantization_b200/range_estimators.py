@@ -28,7 +28,7 @@ class BaseEnumOptions(Flag):  # utils/utils.py:297-304
 
     @classmethod
     def list_names(cls):
-        return [m.name for m in cls]
+        return list(cls.__members__)  # (Flag iteration skips non-integer values on Python >= 3.11)
 
 
 class ClassEnumOptions(BaseEnumOptions):  # utils/utils.py:307-313
@@ -102,12 +102,19 @@ class _MinMaxEstimator(RangeEstimatorBase):
 
     def _forward_dp(self, x):
         C = x.shape[0] if self.per_channel else 1
-        init = self.current_xmin is not None
         packed = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        ops.minmax(x, self.per_channel, packed[:C], packed[C:], ops.EST_CURRENT, False)
+        return self.dp_merge(packed)
+
+    def dp_merge(self, packed):
+        """All-reduce this rank's batch statistic ``packed = [min (C), max (C)]`` and apply the update rule.
+        Device agnostic (the CPU/gloo tests drive it directly): after it every rank holds the range a
+        single process would have computed on the concatenated batch (min/max are order independent)."""
+        C = packed.numel() // 2
+        init = self.current_xmin is not None
         bmin, bmax = packed[:C], packed[C:]
-        ops.minmax(x, self.per_channel, bmin, bmax, ops.EST_CURRENT, False)
         bmin.neg_()
-        fq_dist.all_reduce_max(packed)  # one collective for [-min, max]
+        fq_dist.all_reduce_max(packed)  # ONE collective for [-min, max]
         bmin.neg_()
         if not init or self.EST_MODE == ops.EST_CURRENT:
             self.current_xmin, self.current_xmax = bmin.clone(), bmax.clone()

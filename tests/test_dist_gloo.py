@@ -1,0 +1,72 @@
+"""CPU, world_size 2, gloo: the data-parallel plumbing.  The per-rank statistics come from
+the oracle here (the CUDA kernels are covered by -m gpu); what is tested is that after the collectives every
+rank holds exactly the range / metrics a single process computes on the concatenated batch."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import dist as fq_dist
+    from oracle import fp8_oracle as O
+
+    assert fq_dist.init_from_env(backend="gloo") and fq_dist.active()
+    assert fq_dist.world_size() == world and fq_dist.rank() == rank
+    torch.manual_seed(0)
+    ok = True
+    for cls, ocls, pc in ((fq.AllMinMaxEstimator, O.OracleAllMinMax, False),
+                          (fq.CurrentMinMaxEstimator, O.OracleCurrentMinMax, True),
+                          (fq.RunningMinMaxEstimator, O.OracleRunningMinMax, False)):
+        est = cls(per_channel=pc)
+        single = ocls(per_channel=pc)
+        for step in range(3):
+            gx = torch.randn(8, 6, 10) * (step + 1)           # the global batch, identical on every rank
+            if pc:
+                gx_shards = gx.reshape(6 * 8 // 6, 6, 10) if False else gx  # weights are replicated, not sharded
+                local = gx
+            else:
+                local = fq_dist.shard_batch(gx)
+            mn, mx = O.minmax(local, pc)
+            packed = torch.cat([mn.reshape(-1), mx.reshape(-1)]).clone()
+            cur_min, cur_max = est.dp_merge(packed)
+            smn, smx = single(gx)
+            ok &= torch.equal(cur_min.reshape(-1), smn.reshape(-1)) and torch.equal(cur_max.reshape(-1), smx.reshape(-1))
+    # MSE table: mean over ranks of per-shard means == global mean (equal shards)
+    gx = torch.randn(8, 4, 5, 5)
+    local = fq_dist.shard_batch(gx)
+    inc = ((local - local.round()) ** 2).mean().reshape(1)
+    fq_dist.all_reduce_mean(inc)
+    ok &= torch.allclose(inc, ((gx - gx.round()) ** 2).mean().reshape(1), rtol=1e-6)
+    # validation counters
+    stats = torch.tensor([1.0 + rank, 2.0, 3.0, 4.0])
+    fq_dist.all_reduce_sum(stats)
+    ok &= stats.tolist() == [3.0, 4.0, 6.0, 8.0]
+    with pytest.raises(ValueError):
+        fq_dist.shard_batch(torch.zeros(3, 2))
+    fq_dist.barrier()
+    q.put((rank, bool(ok)))
+    td.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

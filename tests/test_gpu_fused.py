@@ -1,0 +1,187 @@
+"""GPU: fused epilogue kernels == composition of the unfused steps, bit for bit, and the module layer
+(QuantLinear / BNQConv / QuantizedResNet) against golden outputs of the real reference modules."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import bits, load_golden, ulp_diff
+from oracle import fp8_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _quantizer(M, maxval, sb=1):
+    import fp8_quantization_b200 as fq
+
+    q = fq.FPQuantizer(8, mantissa_bits=M, maxval=maxval)
+    q.sign_bits = sb
+    return q
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56), (4, 512, 7, 7), (3, 96, 1, 1), (2, 32, 5, 3), (5, 1000)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_bn_act_quant_equals_composition(shape, act):
+    from fp8_quantization_b200 import ops
+
+    torch.manual_seed(7)
+    C = shape[1]
+    x = torch.randn(shape, device=DEV) * 3
+    mean, var = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.3
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    scale, shift = ops.bn_fold(mean, var, gamma, beta, 1e-5)
+    inv = 1.0 / torch.sqrt(var + 1e-5)
+    assert torch.equal(scale, gamma * inv) and torch.equal(shift, beta - mean * scale)
+    for M in (5, 4, 2):
+        q = _quantizer(M, 4.0)
+        table, _ = q.table_for(x)
+        y = ops.bn_act_quant(x, scale, shift, act, table, float(M), 8, 1)
+        view = [1, C] + [1] * (x.dim() - 2)
+        t = torch.addcmul(shift.view(view).double(), x.double(), scale.view(view).double()).float()  # fma
+        if act == 1:
+            t = torch.relu(t)
+        elif act == 2:
+            t = F.relu6(t)
+        assert torch.equal(bits(y), bits(q(t)))
+        # and against the reference composition F.batch_norm -> act -> quantiser: BN arithmetic differs from
+        # cuDNN's by ulps *before* quantisation, so allow a 1e-4 fraction of elements to land one code apart
+        ref = O.bn_act(x, mean, var, gamma, beta, 1e-5, {0: None, 1: "relu", 2: "relu6"}[act])
+        yr = q(ref)
+        assert (bits(y) != bits(yr)).float().mean().item() < 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, 64 * 128 * 28 * 28 + 3])
+def test_add_act_quant_equals_composition(n):
+    from fp8_quantization_b200 import ops
+
+    torch.manual_seed(8)
+    a, b = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+    for M, act in ((5, 1), (4, 0), (3, 2)):
+        q = _quantizer(M, 2.5)
+        table, _ = q.table_for(a)
+        y = ops.add_act_quant(a, b, act, table, float(M), 8, 1)
+        t = a + b
+        t = torch.relu(t) if act == 1 else (F.relu6(t) if act == 2 else t)
+        assert torch.equal(bits(y), bits(q(t)))
+        assert torch.equal(bits(y), bits(O.fake_quant(t, 8, q.maxval, torch.tensor([float(M)], device=DEV), 1)))
+
+
+def _qparams(M=5):
+    from fp8_quantization_b200 import workloads
+
+    qp = workloads.readme_quant_params(M)
+    qp.pop("quant_setup")
+    return qp
+
+
+def test_quantlinear_config1_matches_reference_golden():
+    """BASELINE config 1: Linear(1024,1024), E2M5 per-channel weights, against the real reference module."""
+    from fp8_quantization_b200 import modules
+
+    g = load_golden("modules.npz")
+    lin = modules.QuantLinear(1024, 1024, **_qparams(5)).to(DEV)
+    lin.weight.data = torch.from_numpy(g["lin_w"]).to(DEV)
+    lin.bias.data = torch.from_numpy(g["lin_b"]).to(DEV)
+    x = torch.from_numpy(g["lin_x"]).to(DEV)
+    lin.quantized()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y_cal = lin(x)
+            lin.fix_ranges()
+            y = lin(x)
+            wq = lin.weight_quantizer(lin.weight.detach())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert torch.equal(y_cal, y)
+    # weight ranges are exact (min/max); quantised weights: canonical parity -> <= 1 ulp except tie flips
+    assert np.array_equal(lin.weight_quantizer.quantizer.maxval.cpu().numpy(), g["lin_w_maxval"])
+    d = ulp_diff(wq.cpu(), torch.from_numpy(g["lin_wq"]))
+    assert (d > 1).float().mean().item() < 1e-4
+    # the activation range comes from a GEMM whose summation order differs between CPU and cuBLAS
+    np.testing.assert_allclose(lin.activation_quantizer.quantizer.maxval.cpu().numpy(), g["lin_a_maxval"], rtol=1e-4)
+    yr = torch.from_numpy(g["lin_y"])
+    step = float(g["lin_a_maxval"][0]) / 2 ** 5  # one quantisation step in the top binade
+    assert ((y.cpu() - yr).abs() > step).float().mean().item() < 1e-3
+
+
+def test_bnqconv_fused_matches_reference_golden():
+    from fp8_quantization_b200 import modules, ops
+
+    g = load_golden("modules.npz")
+    conv = modules.BNQConv(8, 16, 3, padding=1, activation=torch.nn.ReLU(), **_qparams(5)).to(DEV)
+    conv.weight.data = torch.from_numpy(g["conv_w"]).to(DEV)
+    conv.running_mean.data = torch.from_numpy(g["conv_mean"]).to(DEV)
+    conv.running_var.data = torch.from_numpy(g["conv_var"]).to(DEV)
+    conv.gamma.data = torch.from_numpy(g["conv_gamma"]).to(DEV)
+    conv.beta.data = torch.from_numpy(g["conv_beta"]).to(DEV)
+    conv.eval()
+    conv.quantized()
+    x = torch.from_numpy(g["conv_x"]).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y_cal = conv(x)            # calibration: unfused F.batch_norm path + fused estimate
+            conv.fix_ranges()
+            n0 = ops.launch_count()
+            y_fused = conv(x)          # validation: weight quant + bn_fold + ONE fused epilogue launch
+            assert ops.launch_count() - n0 == 3
+            modules.FUSE_EPILOGUES = False
+            y_unfused = conv(x)
+            modules.FUSE_EPILOGUES = True
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    np.testing.assert_allclose(conv.activation_quantizer.quantizer.maxval.cpu().numpy(), g["conv_a_maxval"], rtol=1e-5)
+    yr = torch.from_numpy(g["conv_y"])
+    step = float(g["conv_a_maxval"][0]) / 2 ** 5
+    for y in (y_cal, y_fused, y_unfused):
+        assert ((y.cpu() - yr).abs() > step).float().mean().item() < 2e-3
+    assert (bits(y_fused) != bits(y_unfused)).float().mean().item() < 1e-3
+
+
+def test_resnet18_m5_ranges_and_logits_vs_reference_golden():
+    """BASELINE config 2: the reference's QuantizedResNet(resnet18()) under seed 10 (CPU) vs ours (GPU):
+    every quantiser's calibrated range and the logits.  Conv summation order differs (cuDNN vs MKL-DNN), so
+    activations ranges agree to ~1e-3 and logits to a small fraction of their spread, not bit for bit."""
+    from torchvision.models import resnet18
+
+    from fp8_quantization_b200 import workloads
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    g = load_golden("resnet18_m5.npz")
+    torch.manual_seed(10)
+    net = resnet18()
+    model = workloads.QuantizedResNet(net, **workloads.readme_quant_params(5)).to(DEV).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+        model.fix_ranges()
+        with torch.no_grad():
+            logits = model(x)
+            from fp8_quantization_b200 import modules
+            modules.FUSE_EPILOGUES = False
+            logits_unfused = model(x)
+            modules.FUSE_EPILOGUES = True
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]
+    assert names == list(g["names"])  # same module tree, same quantiser order as the reference
+    for i, n in enumerate(names):
+        ours = dict(model.named_modules())[n].maxval.reshape(-1).cpu().numpy()
+        ref = g[f"maxval_{i:02d}"]
+        if ours.size > 1:  # per-channel weight ranges: pure min/max of identical weights -> exact
+            assert np.array_equal(ours, ref), n
+        else:
+            np.testing.assert_allclose(ours, ref, rtol=2e-2, err_msg=n)
+    ref_logits = torch.from_numpy(g["logits"])
+    spread = ref_logits.std().item()
+    assert (logits.cpu() - ref_logits).abs().max().item() < 0.5 * spread
+    cos = F.cosine_similarity(logits.cpu().flatten(), ref_logits.flatten(), dim=0).item()
+    assert cos > 0.98, cos
+    assert F.cosine_similarity(logits.flatten(), logits_unfused.flatten(), dim=0).item() > 0.995

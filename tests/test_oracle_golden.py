@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement against the committed golden vectors (produced by the REAL reference,
+tests/golden/make_golden.py).  Bit-exact where ATen takes the same libm path as when the fixtures
+were generated (AVX-512 Sleef, one thread); otherwise canonical codes + 1 ulp."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, load_golden, ulp_diff
+from oracle import fp8_oracle as O
+from oracle.reference_loader import reference_available
+
+STRICT = torch.backends.cpu.get_cpu_capability() == "AVX512"
+
+
+@pytest.fixture(autouse=True)
+def _one_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
+def test_fake_quant_matches_reference_golden():
+    g = load_golden("fp8_quantizer.npz")
+    n = int(g["num_cases"])
+    assert n == 98
+    for i in range(n):
+        name = f"c{i:03d}"
+        M, sb, pc = [int(v) for v in g[name + "_meta"]]
+        x = torch.from_numpy(g[name + "_x"])
+        y_ref = torch.from_numpy(g[name + "_y"])
+        maxval = torch.from_numpy(g[name + "_maxval"])
+        y, e, q = O.fake_quant(x, 8, maxval, torch.Tensor([float(M)]), sb, return_codes=True)
+        if STRICT:
+            same = (bits(y) == bits(y_ref)) | (torch.isnan(y) & torch.isnan(y_ref))
+            assert bool(same.all()), f"case {i} (M={M}, sign={sb}, per_channel={pc})"
+            assert np.array_equal(q.numpy(), g[name + "_q"], equal_nan=True)
+        else:
+            assert int(ulp_diff(y, y_ref).max()) <= 1
+
+
+def test_default_maxval_and_ideal_grid():
+    g = load_golden("fp8_format.npz")
+    for M in range(1, 8):
+        assert np.float32(O.default_maxval(8, M)) == g[f"M{M}"][0]
+    # with the default (integer-bias) maxval the quantiser's outputs lie on the
+    # reference's own enumerated grid exactly for M in {2, 3, 5} and within 1e-6 rel for the others
+    torch.manual_seed(0)
+    for M in (2, 3, 4, 5):
+        grid = g[f"grid_M{M}"]
+        mv = float(g[f"M{M}"][0])
+        x = torch.randn(4096) * mv / 3
+        y = O.fake_quant(x, 8, torch.Tensor([mv]), torch.Tensor([float(M)]), 1).double().numpy()
+        idx = np.clip(np.searchsorted(grid, y), 1, len(grid) - 1)
+        near = np.where(np.abs(grid[idx] - y) < np.abs(grid[idx - 1] - y), grid[idx], grid[idx - 1])
+        rel = np.abs(near - y) / np.maximum(np.abs(y), 1e-30)
+        rel[y == 0] = 0
+        assert rel.max() < (1e-12 if M in (2, 3, 5) else 1e-6), (M, rel.max())
+
+
+def test_estimators_match_reference_golden():
+    g = load_golden("estimators.npz")
+    for name, cls, kw in (("current", O.OracleCurrentMinMax, {}), ("all", O.OracleAllMinMax, {}),
+                          ("running", O.OracleRunningMinMax, {"momentum": 0.9})):
+        for pc in (False, True):
+            key = f"{name}_{'pc' if pc else 'pt'}"
+            est = cls(per_channel=pc, **kw)
+            for i, x in enumerate(g[key + "_x"]):
+                mn, mx = est(torch.from_numpy(x))
+                assert np.array_equal(mn.reshape(-1).numpy(), g[key + "_min"][i], equal_nan=True)
+                assert np.array_equal(mx.reshape(-1).numpy(), g[key + "_max"][i], equal_nan=True)
+
+
+def test_mse_estimator_matches_reference_golden():
+    g = load_golden("mse_estimator.npz")
+    for key, pc, include in (("pt_sweep", False, True), ("pt_fixed", False, False), ("pc_sweep", True, True),
+                             ("pc_fixed", True, False)):
+        x = torch.from_numpy(g[key + "_x"])
+        q = O.OracleFPQuantizer(8, per_channel=pc, mantissa_bits=4, set_maxval=True, mse_include_mantissa_bits=include)
+        est = O.OracleFPMSE(per_channel=pc, quantizer=q)
+        mn, mx = est(x)
+        assert float(q.mantissa_bits) == float(g[key + "_best_m"])
+        assert np.array_equal(est.search_grid.numpy(), g[key + "_grid"])
+        if STRICT:
+            assert np.array_equal(est.mses.numpy(), g[key + "_mses"])
+            assert np.array_equal(mx.numpy(), g[key + "_xmax"])
+        else:
+            assert np.allclose(est.mses.numpy(), g[key + "_mses"], rtol=1e-4)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+def test_oracle_equals_live_reference():
+    """In the build container the oracle is also compared with the live reference on fresh inputs."""
+    from oracle.reference_loader import load_reference
+
+    R = load_reference()
+    torch.manual_seed(123)
+    for M in (2, 3, 4, 5, 6):
+        for pc in (False, True):
+            x = torch.randn(32, 96)
+            q = R.FPQuantizer(8, per_channel=pc, mantissa_bits=M, set_maxval=True)
+            mn, mx = O.minmax(x, pc)
+            q.set_quant_range(mn, mx)
+            y_ref = q(x)
+            y = O.fake_quant(x, 8, q.maxval, q.mantissa_bits, 1)
+            assert torch.equal(bits(y), bits(y_ref))
+            oq = O.OracleFPQuantizer(8, per_channel=pc, mantissa_bits=M, set_maxval=True)
+            oq.set_quant_range(mn, mx)
+            assert torch.equal(oq.maxval, q.maxval)
+            assert torch.equal(bits(oq(x)), bits(y_ref))
