@@ -96,10 +96,17 @@ def test_quantlinear_config1_matches_reference_golden():
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     assert torch.equal(y_cal, y)
-    # weight ranges are exact (min/max); quantised weights: canonical parity -> <= 1 ulp except tie flips
+    # weight ranges are exact (min/max).  Quantised weights vs the reference on the CPU: same code everywhere
+    # except tie flips (< 1e-4); the dequantised float is within 1 ulp unless the two backends' log2f(maxval)
+    # differ by 1 ulp for that channel, which shifts the whole channel's scale by ~6 ulps (DESIGN.md section 3;
+    # measured: 1 of the 1024 channels here) -> bound the float error at 1e-6 relative, the code error at a step.
     assert np.array_equal(lin.weight_quantizer.quantizer.maxval.cpu().numpy(), g["lin_w_maxval"])
-    d = ulp_diff(wq.cpu(), torch.from_numpy(g["lin_wq"]))
-    assert (d > 1).float().mean().item() < 1e-4
+    ref_wq = torch.from_numpy(g["lin_wq"])
+    rel = (wq.cpu() - ref_wq).abs() / ref_wq.abs().clamp_min(1e-30)
+    rel[ref_wq == 0] = (wq.cpu()[ref_wq == 0] != 0).float()
+    assert (rel > 1e-6).float().mean().item() < 1e-4
+    d = ulp_diff(wq.cpu(), ref_wq)
+    assert (d > 1).float().mean().item() < 5e-3 and (d > 8).float().mean().item() < 1e-4
     # the activation range comes from a GEMM whose summation order differs between CPU and cuBLAS
     np.testing.assert_allclose(lin.activation_quantizer.quantizer.maxval.cpu().numpy(), g["lin_a_maxval"], rtol=1e-4)
     yr = torch.from_numpy(g["lin_y"])

@@ -5,7 +5,8 @@ Parity statement (measured on the B200):
        op sequence as its README runs it (--cuda) -- every output float is BIT-IDENTICAL, and so are the
        raw exponent code (:128) and mantissa integer (:132).
   (P2) against the oracle on the CPU and against the committed golden vectors (real reference, CPU):
-       canonical (sign, exponent-code, mantissa-int) identical and dequantised float within 1 ulp, with
+       canonical (sign, exponent-code, mantissa-int) identical and dequantised float within 1 ulp (8 ulps
+       in a channel whose log2f(maxval) the two backends round differently), with
        an exception budget equal to the reference's OWN CPU-vs-CUDA disagreement on the same input (its
        fp32 log2/pow come from Sleef/glibc on the CPU and libdevice on the GPU and differ by 1 ulp for a few
        percent of arguments, which moves ~1e-5 of the elements across a rounding tie).  The test asserts
@@ -70,10 +71,15 @@ def check_case(x_cpu, maxval_cpu, M, sb, pc, y_golden=None):
     bad_ref = canon_ne(cuda_c, cpu, M)
     assert torch.equal(bad_ours, bad_ref)
     assert bad_ours.float().mean().item() < 2e-3
-    assert int(ulp_diff(ours_c[0], cpu[0])[~bad_ours].max()) <= 1, "dequantised float more than 1 ulp from CPU oracle"
+    # float: 1 ulp where both backends computed the same per-channel bias; a 1-ulp difference in the backends'
+    # log2f(maxval) moves that channel's scales by up to ~6 ulps (same codes) -> bound at 8 ulps overall and
+    # require that the > 1 ulp set is exactly the reference's own CUDA-vs-CPU > 1 ulp set
+    d_ours = ulp_diff(ours_c[0], cpu[0])
+    assert int(d_ours[~bad_ours].max()) <= 8, "dequantised float more than 8 ulps from CPU oracle"
+    assert torch.equal(d_ours > 1, ulp_diff(cuda_c[0], cpu[0]) > 1)
     if y_golden is not None:
         d = ulp_diff(ours_c[0], y_golden)
-        assert (d > 1).float().mean().item() < 2e-3
+        assert (d > 8).float().mean().item() < 2e-3
         assert torch.equal(d > 1, ulp_diff(cuda_c[0], y_golden) > 1)
     return int(bad_ours.sum())
 
