@@ -7,8 +7,10 @@
 Workload ("step"): one pass of the hot path over one batch = every call the quantised ResNet-18 validate
 forward (M=5, per-channel weights, fixed ranges, README.md:63-68 parameters) makes into libfp8fq.so,
 recorded from a real forward of the model at batch B on synthetic 3x224x224 input and replayed on the
-recorded tensors (real conv outputs): 21 per-channel weight fake-quants, 20 BN folds, 20 fused
-BN(+ReLU)+quant, 8 fused residual-add+ReLU+quant, 2 plain per-tensor quants = 71 launches.  The
+recorded tensors (real conv outputs): the 21 per-channel weight fake-quants (one multi-tensor launch), 12 fused
+BN(+ReLU)+quant, 8 fused block tails (BN+quant+residual-add+ReLU+quant), 2 plain per-tensor quants = 23
+launches covering the same 51 quantiser applications per image as the reference (3,237,864 activation
+elements per image + 11.7 M weight elements).  The
 convolutions themselves (cuDNN, out of scope) are NOT in the timed step; the whole-model img/s is
 reported separately under "model".  Weak scaling: every rank runs the same per-GPU batch, no data-path
 collective.
@@ -102,7 +104,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # record the library calls of one real forward, replay them
 # ---------------------------------------------------------------------------------------------------------
-TRACED = ("fake_quant", "bn_fold", "bn_act_quant", "add_act_quant")
+TRACED = ("fake_quant", "fake_quant_multi", "bn_fold", "bn_act_quant", "bn_act_quant_raw", "add_act_quant",
+          "bn_quant_add_act_quant")
+# positions of the data tensors (the rest are parameters: tables, BN buffers) and algorithmic bytes / quantiser
+# applications per element of each op
+DATA_POS = {"fake_quant": (0,), "fake_quant_multi": (0,), "bn_act_quant": (0,), "bn_act_quant_raw": (0,),
+            "add_act_quant": (0, 1), "bn_quant_add_act_quant": (0, 1)}
+BYTES_PER_ELEM = {"fake_quant": 8, "fake_quant_multi": 8, "bn_act_quant": 8, "bn_act_quant_raw": 8, "add_act_quant": 12,
+                  "bn_quant_add_act_quant": 12}
+QUANTS_PER_ELEM = {"bn_quant_add_act_quant": 2}
 
 
 class Recorder:
@@ -131,86 +141,96 @@ class Recorder:
             setattr(self.ops, name, orig)
 
 
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
 def build_replay(calls, ops):
-    """Turns recorded calls into closures over static clones of their inputs.  Tensors that an earlier library
-    call produced (bn_fold's scale/shift) are re-wired to the replayed producer's output."""
+    """Turns recorded calls into a replayable plan over static clones of their inputs.  Tensors that an earlier
+    library call produced (e.g. the inner output feeding a residual add) are re-wired to the replayed producer."""
     produced = {}
     plan = []
+
+    def enc(v):
+        if isinstance(v, torch.Tensor):
+            key = (v.data_ptr(), tuple(v.shape))
+            if key in produced:
+                return ("dep", produced[key] + (tuple(v.shape),))
+            return ("const", v.detach().clone())
+        if isinstance(v, (list, tuple)) and len(v) > 0 and all(isinstance(t, torch.Tensor) for t in v):
+            return ("list", [enc(t) for t in v])
+        return ("val", v)
+
     for idx, (name, a, k, res) in enumerate(calls):
-        args = []
-        for v in a:
-            if isinstance(v, torch.Tensor):
-                key = (v.data_ptr(), tuple(v.shape))
-                if key in produced:
-                    args.append(("dep", produced[key] + (tuple(v.shape),)))
-                else:
-                    args.append(("const", v.detach().clone()))
-            else:
-                args.append(("val", v))
-        kw = {kk: vv for kk, vv in k.items() if kk != "out"}
-        outs = res if isinstance(res, tuple) else (res,)
+        args = [enc(v) for v in a]
+        kw = {kk: vv for kk, vv in k.items() if kk != "out" and kk != "outs"}
+        outs = res if isinstance(res, (tuple, list)) else (res,)
         for j, o in enumerate(outs):
-            produced[(o.data_ptr(), tuple(o.shape))] = (idx, j)
+            if isinstance(o, torch.Tensor):
+                produced[(o.data_ptr(), tuple(o.shape))] = (idx, j)
         plan.append((name, args, kw))
-    results = [None] * len(plan)
+    return plan
 
-    def step():
-        for i, (name, args, kw) in enumerate(plan):
-            real = []
-            for kind, v in args:
-                if kind == "dep":
-                    r = results[v[0]]
-                    real.append(r[v[1]] if isinstance(r, tuple) else r)
-                else:
-                    real.append(v)
+
+def materialise(arg, results):
+    kind, v = arg
+    if kind == "dep":
+        r = results[v[0]]
+        return r[v[1]] if isinstance(r, (tuple, list)) else r
+    if kind == "list":
+        return [materialise(t, results) for t in v]
+    return v
+
+
+def run_plan(plan, ops, results=None, hook=None):
+    results = [None] * len(plan) if results is None else results
+    for i, (name, args, kw) in enumerate(plan):
+        real = [materialise(a, results) for a in args]
+        if hook is not None:
+            results[i] = hook(i, name, args, real, kw)
+        else:
             results[i] = getattr(ops, name)(*real, **kw)
-        return results
+    return results
 
-    return plan, step
+
+def data_shapes(name, args):
+    """shapes of the data tensors of one call (first data position only = the elements quantised)."""
+    a0 = args[DATA_POS[name][0]]
+    items = a0[1] if a0[0] == "list" else [a0]
+    return [tuple(t[1].shape) if t[0] == "const" else t[1][2] for t in items]
+
+
+def is_stream_call(name, args):
+    if name in ("bn_act_quant", "bn_act_quant_raw", "add_act_quant", "bn_quant_add_act_quant"):
+        return True
+    if name == "fake_quant":
+        return [v for kind, v in args if kind == "val"][0] == 1
+    return False
 
 
 def plan_stats(plan):
-    """elements quantised, algorithmic bytes and launch counts per kernel family."""
+    """quantiser applications (elements), algorithmic bytes and launch counts per kernel family."""
     st = {"elems": 0, "launches": len(plan), "stream_bytes": 0, "stream_launches": 0, "stream_elems": 0,
           "weight_elems": 0, "weight_launches": 0, "bn_fold_launches": 0, "in_bytes": 0, "out_bytes": 0}
     for name, args, kw in plan:
         if name == "bn_fold":
             st["bn_fold_launches"] += 1
             continue
-        n = 1
-        for d in (args[0][1].shape if args[0][0] == "const" else args[0][1][2]):
-            n *= d
-        st["elems"] += n
+        n = sum(_numel(sh) for sh in data_shapes(name, args))
+        st["elems"] += n * QUANTS_PER_ELEM.get(name, 1)
         st["out_bytes"] += 4 * n
-        if name == "fake_quant":
-            C = [v for kind, v in args if kind == "val"][0]
-            st["in_bytes"] += 4 * n
-            if C == 1:
-                st["stream_bytes"] += 8 * n
-                st["stream_launches"] += 1
-                st["stream_elems"] += n
-            else:
-                st["weight_elems"] += n
-                st["weight_launches"] += 1
-        elif name == "bn_act_quant":
-            st["in_bytes"] += 4 * n
-            st["stream_bytes"] += 8 * n
+        st["in_bytes"] += (BYTES_PER_ELEM[name] - 4) * n
+        if is_stream_call(name, args):
+            st["stream_bytes"] += BYTES_PER_ELEM[name] * n
             st["stream_launches"] += 1
-            st["stream_elems"] += n
-        elif name == "add_act_quant":
-            st["in_bytes"] += 8 * n
-            st["stream_bytes"] += 12 * n
-            st["stream_launches"] += 1
-            st["stream_elems"] += n
+            st["stream_elems"] += n * QUANTS_PER_ELEM.get(name, 1)
+        else:
+            st["weight_elems"] += n
+            st["weight_launches"] += 1
     return st
-
-
-def is_stream_call(name, args):
-    if name in ("bn_act_quant", "add_act_quant"):
-        return True
-    if name == "fake_quant":
-        return [v for kind, v in args if kind == "val"][0] == 1
-    return False
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -336,8 +356,12 @@ def main():
         model(x_img)  # warm-up (cuDNN autotune, table builds)
         with Recorder(ops) as rec:
             logits = model(x_img)
-    plan, step = build_replay(rec.calls, ops)
+    plan = build_replay(rec.calls, ops)
     del rec
+
+    def step():
+        return run_plan(plan, ops)
+
     st = plan_stats(plan)
     torch.cuda.synchronize()
 
@@ -393,31 +417,29 @@ def main():
         except (OSError, ValueError):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        evs = []
+        evs, nbytes = [], []
         with torch.no_grad():
             for rep in range(3):
-                results = [None] * len(plan)
                 torch.cuda._sleep(int(6e6))  # ~3 ms head start: the host queues the whole pass behind it
-                for i, (name, a, kw) in enumerate(plan):
-                    real = []
-                    for kind, v in a:
-                        if kind == "dep":
-                            r = results[v[0]]
-                            real.append(r[v[1]] if isinstance(r, tuple) else r)
-                        else:
-                            real.append(v)
-                    if is_stream_call(name, a):
-                        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        a0.record()
-                        results[i] = getattr(ops, name)(*real, **kw)
-                        a1.record()
-                        if rep > 0:
-                            evs.append((a0, a1))
-                    else:
-                        results[i] = getattr(ops, name)(*real, **kw)
+
+                def hook(i, name, args, real, kw, rep=rep):
+                    if not is_stream_call(name, args):
+                        return getattr(ops, name)(*real, **kw)
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    out = getattr(ops, name)(*real, **kw)
+                    a1.record()
+                    if rep > 0:
+                        evs.append((a0, a1))
+                        nbytes.append(BYTES_PER_ELEM[name] * sum(_numel(sh) for sh in data_shapes(name, args)))
+                    return out
+
+                run_plan(plan, ops, hook=hook)
         torch.cuda.synchronize()
         k_ms = sum(a.elapsed_time(b) for a, b in evs) / 2  # per step
         achieved = st["stream_bytes"] / (k_ms * 1e-3) / 1e9
+        big = max(range(len(evs)), key=lambda j: nbytes[j])
+        big_ms = min(evs[j][0].elapsed_time(evs[j][1]) for j in range(len(evs)) if nbytes[j] == nbytes[big])
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json"))).get(
@@ -430,54 +452,55 @@ def main():
                 "traffic": traffic, "launches_per_step": st["stream_launches"],
                 "algorithmic_bytes_per_step": st["stream_bytes"],
                 "avg_launch_us": k_ms * 1e3 / st["stream_launches"], "share_of_step": k_ms / ms_per_step,
+                "largest_launch": {"algorithmic_bytes": nbytes[big], "us": big_ms * 1e3,
+                                   "achieved": nbytes[big] / (big_ms * 1e-3) / 1e9,
+                                   "frac": nbytes[big] / (big_ms * 1e-3) / 1e9 / peak},
                 "timing": "CUDA events around every launch of the kernel (host queued ahead of the GPU, so the "
                           "events bracket execution only), 2 instrumented passes after the timed region"}
 
     # ---- e2e: same step with inputs in pinned HOST memory and results read back to the host -----------------
     e2e = None
     if not args.no_e2e:
-        h_in, h_out, d_in = [], [], []
-        data_pos = {"fake_quant": (0,), "bn_act_quant": (0,), "add_act_quant": (0, 1)}
+        # host staging: every data tensor that is not produced on the device within the step (conv outputs,
+        # weights) lives in pinned host memory and is copied in; every output is copied back out
+        h_in, h_out = [], []
         h2d_bytes = d2h_bytes = 0
         for name, a, kw in plan:
             if name == "bn_fold":
-                h_in.append(None), h_out.append(None), d_in.append(None)
+                h_in.append(None), h_out.append(None)
                 continue
-            idxs = [j for j in data_pos[name] if a[j][0] == "const"]  # inputs not produced on the device this step
-            h_in.append([a[j][1].cpu().pin_memory() for j in idxs])
-            d_in.append([(j, a[j][1]) for j in idxs])
-            shape = a[0][1].shape if a[0][0] == "const" else a[0][1][2]
-            h_out.append(torch.empty(shape, dtype=torch.float32).pin_memory())
-            h2d_bytes += sum(t.numel() * 4 for t in h_in[-1])
-            d2h_bytes += h_out[-1].numel() * 4
+            pairs = []
+            for j in DATA_POS[name]:
+                items = a[j][1] if a[j][0] == "list" else [a[j]]
+                for t in items:
+                    if t[0] == "const":
+                        pairs.append((t[1], t[1].cpu().pin_memory()))
+            h_in.append(pairs)
+            h_out.append([torch.empty(sh, dtype=torch.float32).pin_memory() for sh in data_shapes(name, a)])
+            h2d_bytes += sum(h.numel() * 4 for _, h in pairs)
+            d2h_bytes += sum(h.numel() * 4 for h in h_out[-1])
         s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-        def e2e_step():
-            results = [None] * len(plan)
-            for i, (name, a, kw) in enumerate(plan):
-                real = []
-                for kind, v in a:
-                    if kind == "dep":
-                        r = results[v[0]]
-                        real.append(r[v[1]] if isinstance(r, tuple) else r)
-                    else:
-                        real.append(v)
-                if h_in[i] is None:
-                    with torch.cuda.stream(s_k):
-                        results[i] = getattr(ops, name)(*real, **kw)
-                    continue
-                with torch.cuda.stream(s_in):
-                    s_in.wait_stream(s_k)  # the device staging buffer of this site is free again
-                    for (j, dten), hten in zip(d_in[i], h_in[i]):
-                        dten.copy_(hten, non_blocking=True)
-                s_k.wait_stream(s_in)
+        def e2e_hook(i, name, args, real, kw):
+            if h_in[i] is None:
                 with torch.cuda.stream(s_k):
-                    results[i] = getattr(ops, name)(*real, **kw)
-                s_out.wait_stream(s_k)
-                with torch.cuda.stream(s_out):
-                    h_out[i].copy_(results[i], non_blocking=True)
-                    results[i].record_stream(s_out)
-            return results
+                    return getattr(ops, name)(*real, **kw)
+            with torch.cuda.stream(s_in):
+                s_in.wait_stream(s_k)  # the device staging buffers of this site are free again
+                for dten, hten in h_in[i]:
+                    dten.copy_(hten, non_blocking=True)
+            s_k.wait_stream(s_in)
+            with torch.cuda.stream(s_k):
+                out = getattr(ops, name)(*real, **kw)
+            s_out.wait_stream(s_k)
+            with torch.cuda.stream(s_out):
+                for o, h in zip(out if isinstance(out, (list, tuple)) else [out], h_out[i]):
+                    h.copy_(o, non_blocking=True)
+                    o.record_stream(s_out)
+            return out
+
+        def e2e_step():
+            return run_plan(plan, ops, hook=e2e_hook)
 
         e2e_steps = max(3, min(args.steps, 10))
         with torch.no_grad():

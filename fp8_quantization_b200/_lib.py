@@ -39,6 +39,21 @@ SIGNATURES = {
     "fp8fq_fake_quant_host_f32": (_c_i, [_c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_f, _c_i, _c_i, _c_i]),
 }
 
+
+
+class TensorDesc(ctypes.Structure):
+    """fp8fq_tensor_desc (include/fp8fq.h)."""
+
+    _fields_ = [("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("table", ctypes.c_void_p), ("C", ctypes.c_int64),
+                ("inner", ctypes.c_int64)]
+
+
+SIGNATURES["fp8fq_fake_quant_multi_f32"] = (_c_i, [ctypes.POINTER(TensorDesc), _c_i, _c_f, _c_i, _c_i, _c_p])
+SIGNATURES["fp8fq_bn_act_quant_raw_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_f, _c_l, _c_l, _c_l, _c_i, _c_i,
+                                                   _c_p, _c_f, _c_i, _c_i, _c_p])
+SIGNATURES["fp8fq_bn_quant_add_act_quant_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_f, _c_l, _c_l, _c_l,
+                                                         _c_i, _c_i, _c_p, _c_f, _c_i, _c_i, _c_p, _c_f, _c_i, _c_i, _c_p])
+
 _lib = None
 
 

@@ -149,22 +149,29 @@ __global__ void prepare_kernel(const float* __restrict__ maxval, const float* __
 // ------------------------------------------------------------------------------------------------
 // K1: streaming fake-quant
 // ------------------------------------------------------------------------------------------------
-enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2 };
+// PRE_AFFINE  : y = Q(act(bn(x)))                 channel from item-local row arithmetic, bn in smem
+// PRE_AFFINE_G: same, any shape                   channel from a flat 64-bit-safe division, bn from global
+// PRE_ADD     : y = Q(act(a + b))
+// PRE_BNQ_ADD : y = Q2(act(Q1(bn(x)) + b))        the whole residual-block tail in one pass (12 B/elem)
+// PRE_AFFINE_PL: PRE_AFFINE when H*W is not a multiple of the vector width (per-lane rows)
+enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2, PRE_AFFINE_G = 3, PRE_BNQ_ADD = 4, PRE_AFFINE_PL = 5 };
 
 struct StreamArgs {
   const float* x;
-  const float* x2;      // PRE_ADD: second addend
+  const float* x2;      // PRE_ADD / PRE_BNQ_ADD: second addend
   float* y;
   int32_t* codes;
-  const float* table;   // per-tensor table
+  const float* table;   // per-tensor table (PRE_BNQ_ADD: of the inner quantiser Q1)
+  const float* table2;  // PRE_BNQ_ADD: table of the outer quantiser Q2
   int64_t n;
-  int K;
-  int act;
-  const float* bn_scale;
-  const float* bn_shift;
-  FastDiv hw_div;       // PRE_AFFINE: row = idx / hw
-  FastDiv c_div;        //             c   = row % Cbn
-  int bn_mode;
+  int K, K2;
+  int act;              // activation before the (outer) quantiser
+  int bn_raw;           // 1: bn_p = (mean, var, gamma, beta) folded in the kernel prologue; 0: (scale, shift)
+  const float* bn_p[4];
+  float eps;
+  uint32_t hw, Cbn;
+  uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
+  FastDiv hw_div, c_div;
 };
 
 struct RegTab {  // K <= 3: everything in registers
@@ -188,31 +195,57 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
+// vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
+template <int KMODE, bool CODES, int N>
+__device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N]) {
+  float xc[N], s[N], rs[N], q[N];
+  int e[N];
+  bool slow = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
+    const float a = fabsf(xc[k]);
+    if (KMODE == 0) {
+      const bool p2 = a >= c.rt.t2, p3 = a >= c.rt.t3;
+      s[k] = p3 ? c.rt.s3 : (p2 ? c.rt.s2 : c.rt.s1);
+      rs[k] = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
+      e[k] = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+    } else {
+      int ee = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
+      const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * ee);
+      s[k] = p.x;
+      rs[k] = p.y;
+      e[k] = ee < 1 ? 1 : ee;
+    }
+    const float r = mul_rn(xc[k], rs[k]);
+    q[k] = nearbyintf(r);
+    slow |= !(fabsf(r - q[k]) < c.guard);
+  }
+  if (slow) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float r = mul_rn(xc[k], rs[k]);
+      if (!(fabsf(r - q[k]) < c.guard)) q[k] = nearbyintf(div_rn(xc[k], s[k]));  // near a tie, or rs unusable
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    y[k] = mul_rn(q[k], s[k]);
+    if (CODES) {
+      if (y[k] != y[k]) code[k] = 0x7fffffff;
+      else code[k] = (int32_t)((f2u(y[k]) & 0x80000000u) | ((uint32_t)e[k] << 16) | (uint32_t)fabsf(q[k]));
+    }
+  }
+}
+
 template <int KMODE, bool CODES>
 __device__ __forceinline__ float quant_elem(float v, const ElemCtx<KMODE>& c, int32_t* code) {
-  const float xc = min_nan(max_nan(v, c.lo), c.hi);
-  const float a = fabsf(xc);
-  float s, rs;
-  int e;
-  if (KMODE == 0) {
-    const bool p2 = a >= c.rt.t2, p3 = a >= c.rt.t3;
-    s = p3 ? c.rt.s3 : (p2 ? c.rt.s2 : c.rt.s1);
-    rs = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
-    e = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
-  } else {
-    e = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
-    const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * e);
-    s = p.x;
-    rs = p.y;
-    e = e < 1 ? 1 : e;
-  }
-  float q;
-  const float y = quant_core(xc, s, rs, c.guard, &q);
-  if (CODES) {
-    if (y != y) *code = 0x7fffffff;
-    else *code = (int32_t)((f2u(y) & 0x80000000u) | ((uint32_t)e << 16) | (uint32_t)fabsf(q));
-  }
-  return y;
+  float vi[1] = {v}, yo[1];
+  int32_t cd[1];
+  quant_vec<KMODE, CODES, 1>(vi, c, yo, cd);
+  if (CODES) *code = cd[0];
+  return yo[0];
 }
 
 template <int KMODE>
@@ -228,32 +261,63 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, i
   c.irregular = (f2u(smem[H_FLAGS]) & FLAG_IRREGULAR) != 0;
   c.stab = smem;
   if (KMODE == 0) {
-    const float inf = __int_as_float(0x7fc00000);  // NaN: never selected
+    const float never = __int_as_float(0x7fc00000);  // NaN: "a >= never" is false
     const float* thr = smem + kHdr;
     const float* sr = smem + off_sr(K);
-    c.rt.t2 = K >= 2 ? thr[1] : inf;
-    c.rt.t3 = K >= 3 ? thr[2] : inf;
+    c.rt.t2 = K >= 2 ? thr[1] : never;
+    c.rt.t3 = K >= 3 ? thr[2] : never;
     c.rt.s1 = sr[2]; c.rt.r1 = sr[3];
     c.rt.s2 = K >= 2 ? sr[4] : sr[2]; c.rt.r2 = K >= 2 ? sr[5] : sr[3];
     c.rt.s3 = K >= 3 ? sr[6] : c.rt.s2; c.rt.r3 = K >= 3 ? sr[7] : c.rt.r2;
   }
 }
 
+// eval-mode batch norm as an affine map; same arithmetic as bn_fold_kernel
+__device__ __forceinline__ void bn_fold_one(const StreamArgs& a, uint32_t c, float& sc, float& sh) {
+  if (a.bn_raw) {
+    const float invstd = div_rn(1.0f, sqrtf(add_rn(a.bn_p[1][c], a.eps)));
+    const float g = a.bn_p[2] != nullptr ? a.bn_p[2][c] : 1.0f;
+    const float b = a.bn_p[3] != nullptr ? a.bn_p[3][c] : 0.0f;
+    sc = mul_rn(g, invstd);
+    sh = sub_rn(b, mul_rn(a.bn_p[0][c], sc));
+  } else {
+    sc = a.bn_p[0][c];
+    sh = a.bn_p[1][c];
+  }
+}
+
+__device__ __forceinline__ float bn_apply(float v, float sc, float sh) { return fmaf(v, sc, sh); }
+
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
+constexpr int kTabSmem = kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1);
 
 template <int KMODE, int PRE, int VEC, bool CODES>
 __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a) {
-  __shared__ __align__(16) float s_tab[kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1)];
-  ElemCtx<KMODE> ctx;
+  __shared__ __align__(16) float s_tab[kTabSmem];
+  __shared__ __align__(16) float s_tab2[PRE == PRE_BNQ_ADD ? kTabSmem : 2];
+  extern __shared__ __align__(16) float s_bn[];  // PRE_AFFINE / PRE_BNQ_ADD: scale[Cbn], shift[Cbn]
+  ElemCtx<KMODE> ctx, ctx2;
   load_ctx<KMODE>(ctx, a.table, a.K, s_tab);
+  if (PRE == PRE_BNQ_ADD) load_ctx<KMODE>(ctx2, a.table2, a.K2, s_tab2);
+  constexpr bool kSmemBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD);
+  if (kSmemBn) {
+    for (uint32_t c = threadIdx.x; c < a.Cbn; c += kThreads) {
+      float sc, sh;
+      bn_fold_one(a, c, sc, sh);
+      s_bn[c] = sc;
+      s_bn[a.Cbn + c] = sh;
+    }
+    __syncthreads();
+  }
 
   constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
   const int64_t nvec_elems = a.n - (a.n % VEC);
   const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kTile + (int64_t)threadIdx.x * VEC;
+    const int64_t tile0 = tile * kTile;
+    const int64_t base = tile0 + (int64_t)threadIdx.x * VEC;
     Pack<VEC> in[kUnroll], in2[kUnroll];
     bool ok[kUnroll];
 #pragma unroll
@@ -262,53 +326,88 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
       ok[u] = i < nvec_elems;
       if (ok[u]) {
         in[u].load(a.x + i);
-        if (PRE == PRE_ADD) in2[u].load(a.x2 + i);
+        if (PRE == PRE_ADD || PRE == PRE_BNQ_ADD) in2[u].load(a.x2 + i);
       }
+    }
+    // item-local row arithmetic: one (uniform) division per tile, then multiplies / compares per vector
+    uint32_t col0 = 0, ch0 = 0;
+    if (kSmemBn) {
+      const uint32_t row0 = fdiv((uint32_t)tile0, a.hw_div);
+      col0 = (uint32_t)tile0 - row0 * a.hw;
+      ch0 = row0 - fdiv(row0, a.c_div) * a.Cbn;
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
       const int64_t i = base + (int64_t)u * kThreads * VEC;
-      float sc = 1.0f, sh = 0.0f;
-      if (PRE == PRE_AFFINE) {
+      float v[VEC], yv[VEC];
+      int32_t cd[VEC];
+      if (kSmemBn) {
+        const uint32_t p = col0 + (uint32_t)(i - tile0);
+        if (PRE != PRE_AFFINE_PL) {
+          uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
+          ch = ch >= a.Cbn ? ch - a.Cbn : ch;
+          const float sc = s_bn[ch], sh = s_bn[a.Cbn + ch];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            uint32_t ch = ch0 + __umulhi(p + k, a.hw_rcp);
+            ch = ch >= a.Cbn ? ch - a.Cbn : ch;
+            v[k] = bn_apply(in[u].v[k], s_bn[ch], s_bn[a.Cbn + ch]);
+          }
+        }
+      } else if (PRE == PRE_AFFINE_G) {
         // all VEC lanes of a vector share a row because hw % VEC == 0 (checked by the launcher)
         const uint32_t row = fdiv((uint32_t)i, a.hw_div);
-        const uint32_t ch = row - fdiv(row, a.c_div) * a.c_div.d;
-        sc = __ldg(a.bn_scale + ch);
-        sh = __ldg(a.bn_shift + ch);
-      }
-      Pack<VEC> out;
-      IPack<VEC> cd;
+        const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
+        float sc, sh;
+        bn_fold_one(a, ch, sc, sh);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float v = in[u].v[k];
-        if (PRE == PRE_AFFINE) {
-          v = a.bn_mode == 0 ? fmaf(v, sc, sh) : add_rn(mul_rn(v, sc), sh);
-          v = apply_act(v, a.act);
-        } else if (PRE == PRE_ADD) {
-          v = apply_act(add_rn(v, in2[u].v[k]), a.act);
-        }
-        out.v[k] = quant_elem<KMODE, CODES>(v, ctx, &cd.v[k]);
+        for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = in[u].v[k];
       }
+      if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(v[k], a.act);
+      } else if (PRE == PRE_ADD) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(v[k], in2[u].v[k]), a.act);
+      } else if (PRE == PRE_BNQ_ADD) {
+        float t[VEC];
+        quant_vec<KMODE, false, VEC>(v, ctx, t, cd);  // inner quantiser (output of the block's last BN)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(t[k], in2[u].v[k]), a.act);
+      }
+      if (PRE == PRE_BNQ_ADD) quant_vec<KMODE, CODES, VEC>(v, ctx2, yv, cd);
+      else quant_vec<KMODE, CODES, VEC>(v, ctx, yv, cd);
+      Pack<VEC> out;
+      IPack<VEC> co;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { out.v[k] = yv[k]; co.v[k] = cd[k]; }
       out.store(a.y + i);
-      if (CODES) cd.store(a.codes + i);
+      if (CODES) co.store(a.codes + i);
     }
   }
   // scalar tail (n % VEC elements), VEC == 4 only
   if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {
     const int64_t i = nvec_elems + threadIdx.x;
     float v = a.x[i];
-    if (PRE == PRE_AFFINE) {
+    if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD) {
       const uint32_t row = fdiv((uint32_t)i, a.hw_div);
-      const uint32_t ch = row - fdiv(row, a.c_div) * a.c_div.d;
-      const float sc = a.bn_scale[ch], sh = a.bn_shift[ch];
-      v = a.bn_mode == 0 ? fmaf(v, sc, sh) : add_rn(mul_rn(v, sc), sh);
-      v = apply_act(v, a.act);
-    } else if (PRE == PRE_ADD) {
-      v = apply_act(add_rn(v, a.x2[i]), a.act);
+      const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
+      float sc, sh;
+      bn_fold_one(a, ch, sc, sh);
+      v = bn_apply(v, sc, sh);
     }
     int32_t cd;
-    a.y[i] = quant_elem<KMODE, CODES>(v, ctx, &cd);
+    if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) v = apply_act(v, a.act);
+    else if (PRE == PRE_ADD) v = apply_act(add_rn(v, a.x2[i]), a.act);
+    else if (PRE == PRE_BNQ_ADD) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), a.act);
+    a.y[i] = PRE == PRE_BNQ_ADD ? quant_elem<KMODE, CODES>(v, ctx2, &cd) : quant_elem<KMODE, CODES>(v, ctx, &cd);
     if (CODES) a.codes[i] = cd;
   }
 }
@@ -316,41 +415,55 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
 // ------------------------------------------------------------------------------------------------
 // K1 per-channel: x is [C, inner]; one CTA per (row, chunk) work item, row table staged in smem
 // ------------------------------------------------------------------------------------------------
-struct RowsArgs {
+constexpr int kMaxMulti = 24;  // tensors per launch (descriptors travel in the kernel parameter space)
+
+struct RowsTensor {
   const float* x;
   float* y;
   int32_t* codes;
   const float* table;
   int64_t C, inner;
   int64_t chunks_per_row;   // ceil(inner / chunk)
-  int64_t chunk;            // elements per work item (multiple of 4)
-  int K;
+  int64_t work0;            // first work item of this tensor
   int vec_ok;               // inner % 4 == 0 and pointers 16B aligned
 };
 
+struct RowsArgs {
+  RowsTensor t[kMaxMulti];
+  int count;
+  int64_t nwork;
+  int64_t chunk;            // elements per work item (multiple of 4)
+  int K;
+};
+
+// One CTA per (tensor, row, chunk) work item; the row's table is staged in shared memory.  Several weight
+// tensors of the same format share one launch (a model's 21..53 weight tensors are each far too small to
+// fill the GPU or to amortise a launch on their own).
 template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(128) fq_rows_kernel(const RowsArgs a) {
-  __shared__ __align__(16) float s_tab[kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1)];
+__global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+  __shared__ __align__(16) float s_tab[kTabSmem];
   const int stride = table_stride(a.K);
-  const int64_t nwork = a.C * a.chunks_per_row;
-  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-    const int64_t row = w / a.chunks_per_row;
-    const int64_t ck = w - row * a.chunks_per_row;
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    int ti = 0;
+    while (ti + 1 < a.count && w >= a.t[ti + 1].work0) ++ti;
+    const RowsTensor& T = a.t[ti];
+    const int64_t lw = w - T.work0;
+    const int64_t row = lw / T.chunks_per_row;
+    const int64_t ck = lw - row * T.chunks_per_row;
     __syncthreads();  // previous iteration done with s_tab
     ElemCtx<KMODE> ctx;
-    load_ctx<KMODE>(ctx, a.table + row * stride, a.K, s_tab);
+    load_ctx<KMODE>(ctx, T.table + row * stride, a.K, s_tab);
     const int64_t beg = ck * a.chunk;
-    const int64_t end = (beg + a.chunk < a.inner) ? beg + a.chunk : a.inner;
-    const float* xr = a.x + row * a.inner;
-    float* yr = a.y + row * a.inner;
-    int32_t* cr = CODES ? a.codes + row * a.inner : nullptr;
-    if (a.vec_ok) {
+    const int64_t end = (beg + a.chunk < T.inner) ? beg + a.chunk : T.inner;
+    const float* xr = T.x + row * T.inner;
+    float* yr = T.y + row * T.inner;
+    int32_t* cr = CODES ? T.codes + row * T.inner : nullptr;
+    if (T.vec_ok) {
       for (int64_t i = beg + (int64_t)threadIdx.x * 4; i < end; i += (int64_t)blockDim.x * 4) {
         Pack<4> in, out;
         IPack<4> cd;
         in.load(xr + i);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) out.v[k] = quant_elem<KMODE, CODES>(in.v[k], ctx, &cd.v[k]);
+        quant_vec<KMODE, CODES, 4>(in.v, ctx, out.v, cd.v);
         out.store(yr + i);
         if (CODES) cd.store(cr + i);
       }
@@ -604,29 +717,47 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 template <int KMODE, int PRE, int VEC, bool CODES>
-int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
-  static int occ = 0;
-  if (occ == 0) {
+int launch_stream_t(const StreamArgs& a, size_t smem, cudaStream_t st) {
+  static int occ0 = 0;
+  int occ = occ0;
+  if (occ == 0 || smem > 0) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fq_stream_kernel<KMODE, PRE, VEC, CODES>, kThreads, 0) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fq_stream_kernel<KMODE, PRE, VEC, CODES>, kThreads, smem) !=
             cudaSuccess || o <= 0)
-      o = 4;
+      o = 2;
     occ = o;
+    if (smem == 0) occ0 = o;
   }
   const int64_t tile = (int64_t)kThreads * VEC * kUnroll;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > ntiles) grid = ntiles;
-  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, 0, st>>>(a);
+  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, smem, st>>>(a);
   return launch_status();
 }
 
 template <int PRE, int VEC>
-int launch_stream(const StreamArgs& a, cudaStream_t st) {
-  const bool codes = a.codes != nullptr;
-  if (a.K <= 3) return codes ? launch_stream_t<0, PRE, VEC, true>(a, st) : launch_stream_t<0, PRE, VEC, false>(a, st);
-  return codes ? launch_stream_t<1, PRE, VEC, true>(a, st) : launch_stream_t<1, PRE, VEC, false>(a, st);
+int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
+  const bool small = a.K <= 3 && (PRE != PRE_BNQ_ADD || a.K2 <= 3);
+  if (PRE == PRE_PLAIN && a.codes != nullptr)  // the code planes exist for the parity tests of the plain quantiser
+    return small ? launch_stream_t<0, PRE_PLAIN, VEC, true>(a, smem, st) : launch_stream_t<1, PRE_PLAIN, VEC, true>(a, smem, st);
+  return small ? launch_stream_t<0, PRE, VEC, false>(a, smem, st) : launch_stream_t<1, PRE, VEC, false>(a, smem, st);
+}
+
+// Fills the batch-norm / row-geometry part of StreamArgs and picks the affine variant.
+// Returns the dynamic shared-memory size for the fast variant, or -1 if the generic variant must be used.
+constexpr uint32_t kMaxSmemChannels = 5120;  // 40 KB of (scale, shift)
+int64_t setup_affine(StreamArgs& a, int64_t hw, int64_t Cbn) {
+  a.hw = (uint32_t)hw;
+  a.Cbn = (uint32_t)Cbn;
+  a.hw_div = make_fastdiv((uint32_t)hw);
+  a.c_div = make_fastdiv((uint32_t)Cbn);
+  a.hw_rcp = hw > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)hw - 1) / (uint64_t)hw) : 0u;
+  const int64_t max_local_rows = 1 + 4095 / hw;  // rows an item of <= 4096 elements can advance
+  const bool exact = (uint64_t)(hw + 4096) * (uint64_t)hw < (1ull << 32);  // umulhi(p, hw_rcp) == p / hw
+  if (hw > 1 && exact && Cbn <= kMaxSmemChannels && max_local_rows <= Cbn) return (int64_t)(2 * Cbn * sizeof(float));
+  return -1;
 }
 
 int check_format(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
@@ -700,6 +831,37 @@ int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C,
   return prepare_impl(nullptr, xmin, xmax, maxval_out, C, mantissa_bits, n_bits, sign_bits, table, stream);
 }
 
+static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, int K, cudaStream_t st) {
+  RowsArgs a{};
+  a.count = count;
+  a.K = K;
+  a.chunk = 4096;
+  int64_t work = 0, max_inner = 0;
+  for (int i = 0; i < count; ++i) {
+    RowsTensor& t = a.t[i];
+    t.x = d[i].x; t.y = d[i].y; t.table = d[i].table; t.C = d[i].C; t.inner = d[i].inner;
+    t.codes = i == 0 ? codes0 : nullptr;
+    t.vec_ok = (d[i].inner % 4 == 0) && aligned16(d[i].x) && aligned16(d[i].y) && (t.codes == nullptr || aligned16(t.codes));
+    t.chunks_per_row = (d[i].inner + a.chunk - 1) / a.chunk;
+    t.work0 = work;
+    work += d[i].C * t.chunks_per_row;
+    if (d[i].inner > max_inner) max_inner = d[i].inner;
+  }
+  a.nwork = work;
+  int64_t grid = (int64_t)sm_count() * 16;
+  if (grid > work) grid = work;
+  const int threads = max_inner >= 512 ? 128 : (max_inner >= 128 ? 64 : 32);
+  const bool codes = codes0 != nullptr;
+  if (K <= 3) {
+    if (codes) fq_rows_kernel<0, true><<<(unsigned)grid, threads, 0, st>>>(a);
+    else fq_rows_kernel<0, false><<<(unsigned)grid, threads, 0, st>>>(a);
+  } else {
+    if (codes) fq_rows_kernel<1, true><<<(unsigned)grid, threads, 0, st>>>(a);
+    else fq_rows_kernel<1, false><<<(unsigned)grid, threads, 0, st>>>(a);
+  }
+  return launch_status();
+}
+
 static int fake_quant_impl(const float* x, float* y, int32_t* codes, const float* table, int64_t n, int64_t C,
                            int64_t inner, float mantissa_bits, int n_bits, int sign_bits, void* stream) {
   int M, E, K;
@@ -714,25 +876,10 @@ static int fake_quant_impl(const float* x, float* y, int32_t* codes, const float
     StreamArgs a{};
     a.x = x; a.y = y; a.codes = codes; a.table = table; a.n = n; a.K = K; a.act = 0;
     const bool vec = aligned16(x) && aligned16(y) && (codes == nullptr || aligned16(codes));
-    return vec ? launch_stream<PRE_PLAIN, 4>(a, st) : launch_stream<PRE_PLAIN, 1>(a, st);
+    return vec ? launch_stream<PRE_PLAIN, 4>(a, 0, st) : launch_stream<PRE_PLAIN, 1>(a, 0, st);
   }
-  RowsArgs a{};
-  a.x = x; a.y = y; a.codes = codes; a.table = table; a.C = C; a.inner = inner; a.K = K;
-  a.vec_ok = (inner % 4 == 0) && aligned16(x) && aligned16(y) && (codes == nullptr || aligned16(codes));
-  a.chunk = 4096;
-  a.chunks_per_row = (inner + a.chunk - 1) / a.chunk;
-  int64_t nwork = C * a.chunks_per_row;
-  int64_t grid = (int64_t)sm_count() * 16;
-  if (grid > nwork) grid = nwork;
-  int threads = inner >= 512 ? 128 : (inner >= 128 ? 64 : 32);
-  if (K <= 3) {
-    if (codes) fq_rows_kernel<0, true><<<(unsigned)grid, threads, 0, st>>>(a);
-    else fq_rows_kernel<0, false><<<(unsigned)grid, threads, 0, st>>>(a);
-  } else {
-    if (codes) fq_rows_kernel<1, true><<<(unsigned)grid, threads, 0, st>>>(a);
-    else fq_rows_kernel<1, false><<<(unsigned)grid, threads, 0, st>>>(a);
-  }
-  return launch_status();
+  fp8fq_tensor_desc d{x, y, table, C, inner};
+  return launch_rows(&d, codes, 1, K, st);
 }
 
 int fp8fq_fake_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
@@ -746,6 +893,31 @@ int fp8fq_fake_quant_codes_f32(const float* x, float* y, int32_t* codes, const f
   return fake_quant_impl(x, y, codes, table, n, C, inner, mantissa_bits, n_bits, sign_bits, stream);
 }
 
+int fp8fq_fake_quant_multi_f32(const fp8fq_tensor_desc* descs_host, int count, float mantissa_bits, int n_bits,
+                               int sign_bits, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (count < 0 || (count > 0 && descs_host == nullptr)) return FP8FQ_ERR_BAD_ARG;
+  fp8fq_tensor_desc group[kMaxMulti];
+  int g = 0;
+  for (int i = 0; i < count; ++i) {
+    const fp8fq_tensor_desc& d = descs_host[i];
+    if (d.C < 1 || d.inner < 0) return FP8FQ_ERR_BAD_ARG;
+    if (d.C * d.inner == 0) continue;
+    if (d.x == nullptr || d.y == nullptr || d.table == nullptr) return FP8FQ_ERR_BAD_ARG;
+    if (!aligned4(d.x) || !aligned4(d.y)) return FP8FQ_ERR_ALIGNMENT;
+    group[g++] = d;
+    if (g == kMaxMulti) {
+      r = launch_rows(group, nullptr, g, K, (cudaStream_t)stream);
+      if (r != FP8FQ_OK) return r;
+      g = 0;
+    }
+  }
+  if (g > 0) return launch_rows(group, nullptr, g, K, (cudaStream_t)stream);
+  return FP8FQ_OK;
+}
+
 int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
                       int64_t Cbn, float* bn_scale, float* bn_shift, void* stream) {
   if (mean == nullptr || var == nullptr || bn_scale == nullptr || bn_shift == nullptr || Cbn < 1)
@@ -756,28 +928,72 @@ int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, c
   return launch_status();
 }
 
+static int bn_act_quant_impl(const float* x, const float* residual, float* y, const float* const bn_p[4], int bn_raw,
+                             float eps, int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
+                             const float* table, float mb, int nb, int sb, const float* table2, float mb2, int nb2,
+                             int sb2, void* stream) {
+  int M, E, K, K2 = 0;
+  int r = check_format(mb, nb, sb, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (table2 != nullptr) {
+    r = check_format(mb2, nb2, sb2, &M, &E, &K2);
+    if (r != FP8FQ_OK) return r;
+  }
+  if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode != 0) return FP8FQ_ERR_BAD_ARG;
+  const int64_t n = rows * hw;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr || table == nullptr || bn_p[0] == nullptr || bn_p[1] == nullptr)
+    return FP8FQ_ERR_BAD_ARG;
+  if (n >= (1ll << 32) || hw >= (1ll << 31) || Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
+  if (!aligned4(x) || !aligned4(y) || (residual && !aligned4(residual))) return FP8FQ_ERR_ALIGNMENT;
+  StreamArgs a{};
+  a.x = x; a.x2 = residual; a.y = y; a.table = table; a.table2 = table2; a.n = n; a.K = K; a.K2 = K2; a.act = act;
+  a.bn_raw = bn_raw; a.eps = eps;
+  for (int i = 0; i < 4; ++i) a.bn_p[i] = bn_p[i];
+  const bool al = aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tail = table2 != nullptr;
+  const int64_t smem = setup_affine(a, hw, Cbn);
+  if (smem >= 0) {
+    const bool v4 = al && (hw % 4 == 0);
+    if (tail) return v4 ? launch_stream<PRE_BNQ_ADD, 4>(a, (size_t)smem, st) : launch_stream<PRE_BNQ_ADD, 1>(a, (size_t)smem, st);
+    if (v4) return launch_stream<PRE_AFFINE, 4>(a, (size_t)smem, st);
+    if (al) return launch_stream<PRE_AFFINE_PL, 4>(a, (size_t)smem, st);  // 128-bit accesses, per-lane rows
+    return launch_stream<PRE_AFFINE, 1>(a, (size_t)smem, st);
+  }
+  if (tail) return FP8FQ_ERR_UNSUPPORTED;  // caller composes the two unfused kernels instead
+  const bool v4 = al && (hw % 4 == 0);
+  return v4 ? launch_stream<PRE_AFFINE_G, 4>(a, 0, st) : launch_stream<PRE_AFFINE_G, 1>(a, 0, st);
+}
+
 int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift, int64_t rows,
                            int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table, float mantissa_bits,
                            int n_bits, int sign_bits, void* stream) {
-  int M, E, K;
-  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
-  if (r != FP8FQ_OK) return r;
-  if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2) return FP8FQ_ERR_BAD_ARG;
-  const int64_t n = rows * hw;
-  if (n == 0) return FP8FQ_OK;
-  if (x == nullptr || y == nullptr || bn_scale == nullptr || bn_shift == nullptr || table == nullptr)
-    return FP8FQ_ERR_BAD_ARG;
-  if (n >= (1ll << 32) || hw >= (1ll << 31) || Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
-  if (!aligned4(x) || !aligned4(y)) return FP8FQ_ERR_ALIGNMENT;
-  StreamArgs a{};
-  a.x = x; a.y = y; a.table = table; a.n = n; a.K = K; a.act = act;
-  a.bn_scale = bn_scale; a.bn_shift = bn_shift;
-  a.hw_div = make_fastdiv((uint32_t)hw);
-  a.c_div = make_fastdiv((uint32_t)Cbn);
-  a.bn_mode = bn_mode;
-  const bool vec = (hw % 4 == 0) && aligned16(x) && aligned16(y);
-  cudaStream_t st = (cudaStream_t)stream;
-  return vec ? launch_stream<PRE_AFFINE, 4>(a, st) : launch_stream<PRE_AFFINE, 1>(a, st);
+  const float* bn_p[4] = {bn_scale, bn_shift, nullptr, nullptr};
+  return bn_act_quant_impl(x, nullptr, y, bn_p, 0, 0.0f, rows, hw, Cbn, act, bn_mode, table, mantissa_bits, n_bits,
+                           sign_bits, nullptr, 0.0f, 0, 0, stream);
+}
+
+int fp8fq_bn_act_quant_raw_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
+                               const float* beta, float eps, int64_t rows, int64_t hw, int64_t Cbn, int act,
+                               int bn_mode, const float* table, float mantissa_bits, int n_bits, int sign_bits,
+                               void* stream) {
+  const float* bn_p[4] = {mean, var, gamma, beta};
+  return bn_act_quant_impl(x, nullptr, y, bn_p, 1, eps, rows, hw, Cbn, act, bn_mode, table, mantissa_bits, n_bits,
+                           sign_bits, nullptr, 0.0f, 0, 0, stream);
+}
+
+int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* mean,
+                                     const float* var, const float* gamma, const float* beta, float eps,
+                                     int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
+                                     const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
+                                     int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
+                                     int n_bits_outer, int sign_bits_outer, void* stream) {
+  if (residual == nullptr || table_outer == nullptr) return FP8FQ_ERR_BAD_ARG;
+  const float* bn_p[4] = {mean, var, gamma, beta};
+  return bn_act_quant_impl(x, residual, y, bn_p, 1, eps, rows, hw, Cbn, act, bn_mode, table_inner,
+                           mantissa_bits_inner, n_bits_inner, sign_bits_inner, table_outer, mantissa_bits_outer,
+                           n_bits_outer, sign_bits_outer, stream);
 }
 
 int fp8fq_add_act_quant_f32(const float* a_in, const float* b_in, float* y, int64_t n, int act, const float* table,
@@ -793,7 +1009,7 @@ int fp8fq_add_act_quant_f32(const float* a_in, const float* b_in, float* y, int6
   a.x = a_in; a.x2 = b_in; a.y = y; a.table = table; a.n = n; a.K = K; a.act = act;
   const bool vec = aligned16(a_in) && aligned16(b_in) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
-  return vec ? launch_stream<PRE_ADD, 4>(a, st) : launch_stream<PRE_ADD, 1>(a, st);
+  return vec ? launch_stream<PRE_ADD, 4>(a, 0, st) : launch_stream<PRE_ADD, 1>(a, 0, st);
 }
 
 int64_t fp8fq_minmax_workspace_bytes(void) { return 16384; }

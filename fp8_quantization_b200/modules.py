@@ -35,8 +35,10 @@ from .range_estimators import CurrentMinMaxEstimator, RangeEstimatorBase, Runnin
 activations_set = [nn.ReLU, nn.ReLU6, nn.Hardtanh, nn.Sigmoid, nn.Tanh, nn.GELU, nn.PReLU, nn.SiLU, nn.Hardswish,
                    nn.Hardsigmoid]
 
-# Global switch for the fused epilogues (tests flip it to compare against the unfused composition).
-FUSE_EPILOGUES = True
+# Global switches (tests flip them to compare against the unfused composition).
+FUSE_EPILOGUES = True      # BN + act + quant in one launch; residual add + act + quant in one launch
+FUSE_BLOCK_TAIL = True     # BN + quant + residual add + act + quant of a residual block in one launch
+BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in one launch
 
 
 def _act_code(act):
@@ -198,6 +200,34 @@ class QuantizedActivation(QuantizedModule):
             out = act(out)
         return self.quantize_activations(out)
 
+    def block_tail(self, features, x, residual_fn, act):
+        """``Q(act(features(x) + residual))`` for a residual block whose ``features`` end in a BNFusedHijacker
+        without activation (models/resnet_quantized.py:39-46).  With fixed ranges the last layer's epilogue and the
+        block's add/act/quant run as ONE kernel: Q_outer(act(Q_inner(bn(conv)) + residual)), 12 B/element."""
+        last = features[-1] if isinstance(features, nn.Sequential) and len(features) > 0 else None
+        residual = residual_fn()
+        code = _act_code(act)
+        if (FUSE_BLOCK_TAIL and FUSE_EPILOGUES and isinstance(last, BNFusedHijacker) and last.activation_function is None
+                and self._qa and code is not None and _fusable_manager(self.activation_quantizer)):
+            h = x
+            for m in list(features)[:-1]:
+                h = m(h)
+            res = last.conv_only(h)
+            if last._fused_epilogue_ok(res) and residual.is_cuda and residual.shape == res.shape:
+                qi, qo = last.activation_quantizer.quantizer, self.activation_quantizer.quantizer
+                res = res if res.is_contiguous() else res.contiguous()
+                residual = residual if residual.is_contiguous() else residual.contiguous()
+                ti, _ = qi.table_for(res)
+                to, _ = qo.table_for(res)
+                out = ops.bn_quant_add_act_quant(res, residual, last.running_mean, last.running_var,
+                                                 last.gamma.detach(), last.beta.detach(), last.epsilon, code, ti,
+                                                 (qi._mbits_host, qi.n_bits, qi.sign_bits), to,
+                                                 (qo._mbits_host, qo.n_bits, qo.sign_bits))
+                if out is not None:
+                    return out
+            return self.add_act_quantize(last.epilogue(res), residual, act)
+        return self.add_act_quantize(features(x), residual, act)
+
     def forward(self, x):
         return self.quantize_activations(x)
 
@@ -244,7 +274,8 @@ class QuantizationHijacker(QuantizedModule):
     def get_params(self):
         weight, bias = self.get_weight_bias()
         if self._qw:
-            weight = self.quantize_weights(weight)
+            stash = self.__dict__.pop("_wq_stash", None)  # set by QuantizedModel.prequantize_weights for THIS forward
+            weight = stash if stash is not None else self.quantize_weights(weight)
         return weight, bias
 
     def quantize_weights(self, weights):
@@ -285,19 +316,24 @@ class BNFusedHijacker(QuantizationHijacker):
                 and res.dtype == torch.float32 and _act_code(self.activation_function) is not None
                 and _fusable_manager(self.activation_quantizer))
 
-    def forward(self, x):
+    def conv_only(self, x):
+        """Input quantisation (if configured), weight quantisation and the linear operation -- everything of
+        forward() up to, not including, the BN / activation / activation-quantiser epilogue."""
         if self.quantize_input and self._qa:
             x = self.activation_quantizer(x)
         weight, bias = self.get_params()
-        res = self.run_forward(x, weight, bias)
+        return self.run_forward(x, weight, bias)
+
+    def epilogue(self, res):
+        """quantized_folded_bn.py:39-55: F.batch_norm -> activation -> activation quantiser; ONE launch when the
+        ranges are fixed (the BN fold is part of the kernel prologue)."""
         if self._fused_epilogue_ok(res):
             q = self.activation_quantizer.quantizer
             res = res if res.is_contiguous() else res.contiguous()
-            scale, shift = ops.bn_fold(self.running_mean, self.running_var, self.gamma.detach(), self.beta.detach(),
-                                       self.epsilon)
             table, _ = q.table_for(res)
-            return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
-                                    q.n_bits, q.sign_bits, bn_mode=self.bn_mode)
+            return ops.bn_act_quant_raw(res, self.running_mean, self.running_var, self.gamma.detach(),
+                                        self.beta.detach(), self.epsilon, _act_code(self.activation_function), table,
+                                        q._mbits_host, q.n_bits, q.sign_bits)
         res = F.batch_norm(res, self.running_mean, self.running_var, self.gamma, self.beta, self.training,
                            self.momentum, self.epsilon)
         if self.activation_function is not None:
@@ -305,6 +341,9 @@ class BNFusedHijacker(QuantizationHijacker):
         if not self.quantize_input and self._qa:
             res = self.activation_quantizer(res)
         return res
+
+    def forward(self, x):
+        return self.epilogue(self.conv_only(x))
 
     def get_bn_dim(self):
         if isinstance(self, nn.Linear):
@@ -553,6 +592,32 @@ class QuantizedModel(nn.Module):
     def __init__(self, input_size=(1, 3, 224, 224)):
         super().__init__()
         self.input_size = input_size
+
+    def prequantize_weights(self):
+        """Quantises the weights of every hijacked layer whose weight range is fixed in ONE launch per format
+        and hands each layer its result for the forward that follows (same work as the per-layer
+        QuantizationHijacker.quantize_weights calls, hijacker.py:88-98, without 21..53 tiny launches).  Layers that
+        are still estimating ranges, or whose weights need a transposed layout, keep the per-layer path."""
+        if not BATCH_WEIGHT_QUANT:
+            return
+        groups = {}
+        for m in self.modules():
+            if not isinstance(m, QuantizationHijacker) or not m._qw or isinstance(m, QuantConvTransposeBase):
+                continue
+            mgr = m.weight_quantizer
+            q = mgr.quantizer
+            w = m.weight
+            if (not isinstance(mgr, QuantizationManager) or not isinstance(q, FPQuantizer) or mgr.estimating()
+                    or not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous()):
+                continue
+            w = w.detach()
+            table, C = q.table_for(w)
+            groups.setdefault((q._mbits_host, q.n_bits, q.sign_bits), []).append((m, w, table, C))
+        for (mb, nb, sb), items in groups.items():
+            outs = ops.fake_quant_multi([w for _, w, _, _ in items], [t for _, _, t, _ in items],
+                                        [c for _, _, _, c in items], mb, nb, sb)
+            for (m, _, _, _), out in zip(items, outs):
+                m.__dict__["_wq_stash"] = out
 
     def load_state_dict(self, state_dict, strict: bool = True):
         flags = {k: v for k, v in state_dict.items() if k.endswith("_quant_a") or k.endswith("_quant_w")}

@@ -8,7 +8,7 @@ import ctypes
 
 import torch
 
-from ._lib import Fp8fqError, check, lib
+from ._lib import Fp8fqError, TensorDesc, check, lib
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 EST_CURRENT, EST_ALL, EST_RUNNING = 0, 1, 2
@@ -133,6 +133,71 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
                                        hw, Cbn, int(act), int(bn_mode), table.data_ptr(), float(mantissa_bits),
                                        int(n_bits), int(sign_bits), _stream()), "fp8fq_bn_act_quant_f32")
     return out
+
+
+def _rows_hw(x, Cbn):
+    if x.dim() < 2 or x.shape[1] != Cbn:
+        raise Fp8fqError("x must be [N, C, ...] with C == number of batch-norm channels")
+    hw = 1
+    for d in x.shape[2:]:
+        hw *= d
+    return x.shape[0] * Cbn, hw
+
+
+def _opt_ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def bn_act_quant_raw(x, mean, var, gamma, beta, eps: float, act: int, table, mantissa_bits: float, n_bits: int,
+                     sign_bits: int, out=None):
+    """BNFusedHijacker epilogue (quantized_folded_bn.py:39-55) as ONE launch: the batch-norm fold happens in the
+    kernel prologue.  x is [N, C, *spatial] contiguous; gamma/beta may be None."""
+    _require(x, "x")
+    rows, hw = _rows_hw(x, mean.numel())
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().fp8fq_bn_act_quant_raw_f32(x.data_ptr(), out.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                           _opt_ptr(gamma), _opt_ptr(beta), float(eps), rows, hw, mean.numel(),
+                                           int(act), 0, table.data_ptr(), float(mantissa_bits), int(n_bits),
+                                           int(sign_bits), _stream()), "fp8fq_bn_act_quant_raw_f32")
+    return out
+
+
+def bn_quant_add_act_quant(x, residual, mean, var, gamma, beta, eps: float, act: int, table_inner, fmt_inner,
+                           table_outer, fmt_outer, out=None):
+    """Whole residual-block tail (models/resnet_quantized.py:39-46) in one pass:
+    Q_outer(act(Q_inner(bn(x)) + residual)).  fmt_* = (mantissa_bits, n_bits, sign_bits).
+    Returns None when the fused variant does not cover the shape (caller composes the two kernels)."""
+    _require(x, "x")
+    _require(residual, "residual")
+    if x.shape != residual.shape:
+        raise Fp8fqError("bn_quant_add_act_quant: shape mismatch")
+    rows, hw = _rows_hw(x, mean.numel())
+    if out is None:
+        out = torch.empty_like(x)
+    code = lib().fp8fq_bn_quant_add_act_quant_f32(
+        x.data_ptr(), residual.data_ptr(), out.data_ptr(), mean.data_ptr(), var.data_ptr(), _opt_ptr(gamma),
+        _opt_ptr(beta), float(eps), rows, hw, mean.numel(), int(act), 0, table_inner.data_ptr(), float(fmt_inner[0]),
+        int(fmt_inner[1]), int(fmt_inner[2]), table_outer.data_ptr(), float(fmt_outer[0]), int(fmt_outer[1]),
+        int(fmt_outer[2]), _stream())
+    if code == -2:
+        return None
+    check(code, "fp8fq_bn_quant_add_act_quant_f32")
+    return out
+
+
+def fake_quant_multi(xs, tables, Cs, mantissa_bits: float, n_bits: int, sign_bits: int, outs=None):
+    """Per-channel fake-quant of several tensors of one format in ONE launch (hijacker.py:88-98 for every
+    layer of a forward).  Returns the list of outputs."""
+    if outs is None:
+        outs = [torch.empty_like(x) for x in xs]
+    descs = (TensorDesc * len(xs))()
+    for d, x, y, t, C in zip(descs, xs, outs, tables, Cs):
+        _require(x, "x")
+        d.x, d.y, d.table, d.C, d.inner = x.data_ptr(), y.data_ptr(), t.data_ptr(), C, x.numel() // C
+    check(lib().fp8fq_fake_quant_multi_f32(descs, len(xs), float(mantissa_bits), int(n_bits), int(sign_bits),
+                                           _stream()), "fp8fq_fake_quant_multi_f32")
+    return outs
 
 
 def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int, out=None):

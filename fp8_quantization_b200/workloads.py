@@ -46,10 +46,9 @@ class QuantizedBlock(QuantizedActivation):
         self.relu = block.relu
 
     def forward(self, x):
-        residual = x if self.downsample is None else self.downsample(x)
-        out = self.features(x)
-        # out += residual; relu; quantise  -> one fused kernel when ranges are fixed
-        return self.add_act_quantize(out, residual, self.relu)
+        # residual = x | downsample(x); out = features(x); out += residual; relu; quantise.
+        # With fixed ranges the last BN + its quantiser + add + relu + quantiser run as one kernel.
+        return self.block_tail(self.features, x, lambda: x if self.downsample is None else self.downsample(x), self.relu)
 
 
 class QuantizedResNet(QuantizedModel):
@@ -100,6 +99,7 @@ class QuantizedResNet(QuantizedModel):
             raise ValueError("Quantization setup '{}' not supported for Resnet".format(quant_setup))
 
     def forward(self, x):
+        self.prequantize_weights()
         x = self.features(x)
         x = self.avgpool(x)
         x = self.flattener(x)
@@ -215,7 +215,7 @@ class QuantizedInvertedResidual(QuantizedActivation):
 
     def forward(self, x):
         if self.use_res_connect:
-            return self.add_act_quantize(x, self.conv(x), None)  # Q(x + conv(x))
+            return self.block_tail(self.conv, x, lambda: x, None)  # Q(x + conv(x)); the conv ends in BN + quantiser
         return self.conv(x)
 
 
@@ -260,6 +260,7 @@ class QuantizedMobileNetV2(QuantizedModel):
             raise ValueError("Quantization setup '{}' not supported for MobilenetV2".format(quant_setup))
 
     def forward(self, x):
+        self.prequantize_weights()
         x = self.features(x)
         x = self.flattener(x)
         return self.classifier(x)

@@ -83,6 +83,18 @@ int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C,
 int fp8fq_fake_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C,
                          int64_t inner, float mantissa_bits, int n_bits, int sign_bits, void* stream);
 
+/* Several per-channel tensors of the same format in ONE launch (a model's weight tensors are each too small to
+ * fill the GPU): replaces the per-layer QuantizationHijacker.quantize_weights calls (hijacker.py:88-98) of one
+ * forward.  `descs_host` is a HOST array; it is copied into the kernel parameters (no device allocation). */
+typedef struct {
+  const float* x;     /* [C, inner] device */
+  float* y;           /* [C, inner] device (may alias x) */
+  const float* table; /* C channel tables */
+  int64_t C, inner;
+} fp8fq_tensor_desc;
+int fp8fq_fake_quant_multi_f32(const fp8fq_tensor_desc* descs_host, int count, float mantissa_bits, int n_bits,
+                               int sign_bits, void* stream);
+
 /* Same, additionally writing the reference's intermediate integers for parity tests:
  * codes[i] = (sign << 31) | (e << 16) | q, with e = log_scales (:128) and q = |round(xc/scales)|
  * (:132); NaN -> 0x7fffffff. */
@@ -94,10 +106,29 @@ int fp8fq_fake_quant_codes_f32(const float* x, float* y, int32_t* codes, const f
  * F.batch_norm -> activation -> per-tensor activation quantiser, one pass, 8 B/element.
  * x, y: [rows, hw] with channel(row) = row % Cbn (NCHW contiguous: rows = N*Cbn, hw = H*W).
  * bn_scale/bn_shift: [Cbn] from fp8fq_bn_fold_f32.  `table` is a per-tensor (C == 1) table.
- * bn_mode 0: y = fma(x, scale, shift); 1: y = (x * scale) + shift with two roundings. */
+ * bn_mode must be 0: y = fma(x, scale, shift) (reserved for other batch-norm arithmetics). */
 int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift,
                            int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table,
                            float mantissa_bits, int n_bits, int sign_bits, void* stream);
+
+/* Same with the RAW batch-norm buffers: the fold (scale = gamma / sqrt(var + eps), shift = beta - mean * scale) is
+ * done in the kernel prologue, so a BNFusedHijacker layer's epilogue is exactly ONE launch. gamma/beta may be NULL. */
+int fp8fq_bn_act_quant_raw_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
+                               const float* beta, float eps, int64_t rows, int64_t hw, int64_t Cbn, int act,
+                               int bn_mode, const float* table, float mantissa_bits, int n_bits, int sign_bits,
+                               void* stream);
+
+/* Replaces: the whole tail of QuantizedBlock.forward (models/resnet_quantized.py:39-46): the last BNFusedHijacker's
+ * epilogue (BN -> inner activation quantiser, quantized_folded_bn.py:39-55) followed by
+ * `out += residual; relu; quantize_activations(out)`:  y = Q_outer(act(Q_inner(bn(x)) + residual)), one pass,
+ * 12 B/element instead of 8 + 12.  Returns FP8FQ_ERR_UNSUPPORTED for shapes the fused variant does not cover
+ * (the caller then issues fp8fq_bn_act_quant_raw_f32 + fp8fq_add_act_quant_f32). */
+int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* mean,
+                                     const float* var, const float* gamma, const float* beta, float eps,
+                                     int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
+                                     const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
+                                     int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
+                                     int n_bits_outer, int sign_bits_outer, void* stream);
 
 /* Per-channel affine form of eval-mode batch norm: scale = gamma * rsqrt(var + eps) (as 1/sqrt),
  * shift = beta - mean * scale.  All [Cbn]. */

@@ -5,8 +5,9 @@ Parity statement (measured on the B200):
        op sequence as its README runs it (--cuda) -- every output float is BIT-IDENTICAL, and so are the
        raw exponent code (:128) and mantissa integer (:132).
   (P2) against the oracle on the CPU and against the committed golden vectors (real reference, CPU):
-       canonical (sign, exponent-code, mantissa-int) identical and dequantised float within 1 ulp (8 ulps
-       in a channel whose log2f(maxval) the two backends round differently), with
+       canonical (sign, exponent-code, mantissa-int) identical and dequantised float within 1e-5 relative
+       (1 ulp when only pow(2, .) differs; ~ln2 * ulp(bias) in a channel whose log2f(maxval) the two backends
+       round differently -- the deviation is asserted to be element for element torch-CUDA-eager's own), with
        an exception budget equal to the reference's OWN CPU-vs-CUDA disagreement on the same input (its
        fp32 log2/pow come from Sleef/glibc on the CPU and libdevice on the GPU and differ by 1 ulp for a few
        percent of arguments, which moves ~1e-5 of the elements across a rounding tie).  The test asserts
@@ -71,16 +72,20 @@ def check_case(x_cpu, maxval_cpu, M, sb, pc, y_golden=None):
     bad_ref = canon_ne(cuda_c, cpu, M)
     assert torch.equal(bad_ours, bad_ref)
     assert bad_ours.float().mean().item() < 2e-3
-    # float: 1 ulp where both backends computed the same per-channel bias; a 1-ulp difference in the backends'
-    # log2f(maxval) moves that channel's scales by up to ~6 ulps (same codes) -> bound at 8 ulps overall and
-    # require that the > 1 ulp set is exactly the reference's own CUDA-vs-CPU > 1 ulp set
+    # float: identical codes give floats that differ only through the backends' fp32 log2/pow: 1 ulp when only
+    # pow(2, .) differs, ~ln2 * ulp(bias) relative (5..50 ulps of the result, growing with the exponent width) for a
+    # channel whose log2f(maxval) the backends round differently.  So: (i) our deviation from the CPU oracle is
+    # element for element the deviation torch-CUDA-eager has from torch-CPU, (ii) it is below 1e-5 relative.
     d_ours = ulp_diff(ours_c[0], cpu[0])
-    assert int(d_ours[~bad_ours].max()) <= 8, "dequantised float more than 8 ulps from CPU oracle"
-    assert torch.equal(d_ours > 1, ulp_diff(cuda_c[0], cpu[0]) > 1)
+    assert torch.equal(d_ours, ulp_diff(cuda_c[0], cpu[0]))
+    ok = ~bad_ours & ~torch.isnan(cpu[0])
+    rel = (ours_c[0] - cpu[0]).abs()[ok] / cpu[0].abs()[ok].clamp_min(1e-37)
+    assert float(rel.max()) <= 1e-5 if rel.numel() else True
     if y_golden is not None:
-        d = ulp_diff(ours_c[0], y_golden)
-        assert (d > 8).float().mean().item() < 2e-3
-        assert torch.equal(d > 1, ulp_diff(cuda_c[0], y_golden) > 1)
+        assert torch.equal(ulp_diff(ours_c[0], y_golden), ulp_diff(cuda_c[0], y_golden))
+        fin = ~torch.isnan(y_golden)
+        relg = (ours_c[0] - y_golden).abs()[fin] / y_golden.abs()[fin].clamp_min(1e-37)
+        assert (relg > 1e-5).float().mean().item() < 2e-3
     return int(bad_ours.sum())
 
 
@@ -140,9 +145,17 @@ def test_edge_semantics():
     qc.set_quant_range(w.min(1)[0], w.max(1)[0])
     yw = qc(w)
     assert torch.isnan(yw[2]).all() and torch.isfinite(yw[[0, 1, 3]]).all()
-    # M = 7 (E = 0): output may exceed maxval (128/127.5 * maxval)
-    q7 = fq.FPQuantizer(8, mantissa_bits=7, maxval=1.0)
-    assert q7(torch.tensor([1.0], device=DEV)).item() > 1.0
+    # M = 7 (E = 0): q reaches 128 = 2^(M+1), so the output may exceed maxval (128/127.5 * maxval) when the
+    # clipped value lands on the .5 tie; whether it does depends on the fp32 rounding of the scale -- follow the oracle
+    hit = 0
+    for mv in (1.0, 2.1152, 3.0, 0.7, 5.0):
+        q7 = fq.FPQuantizer(8, mantissa_bits=7, maxval=mv)
+        y7 = q7(torch.tensor([mv, -mv, 10 * mv], device=DEV))
+        o7 = O.fake_quant(torch.tensor([mv, -mv, 10 * mv], device=DEV), 8, torch.tensor([mv], device=DEV),
+                          torch.tensor([7.0], device=DEV), 1)
+        assert torch.equal(bits(y7), bits(o7))
+        hit += int(y7[0].item() > mv)
+    assert hit >= 1
     # unsigned: negatives clip to zero
     qu = fq.FPQuantizer(8, mantissa_bits=4, maxval=2.0)
     qu.sign_bits = 0
