@@ -104,13 +104,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # record the library calls of one real forward, replay them
 # ---------------------------------------------------------------------------------------------------------
-TRACED = ("fake_quant", "fake_quant_multi", "bn_fold", "bn_act_quant", "bn_act_quant_raw", "add_act_quant",
-          "bn_quant_add_act_quant")
+TRACED = ("fake_quant", "fake_quant_multi", "bn_fold", "bn_act_quant", "add_act_quant", "bn_quant_add_act_quant")
 # positions of the data tensors (the rest are parameters: tables, BN buffers) and algorithmic bytes / quantiser
 # applications per element of each op
-DATA_POS = {"fake_quant": (0,), "fake_quant_multi": (0,), "bn_act_quant": (0,), "bn_act_quant_raw": (0,),
-            "add_act_quant": (0, 1), "bn_quant_add_act_quant": (0, 1)}
-BYTES_PER_ELEM = {"fake_quant": 8, "fake_quant_multi": 8, "bn_act_quant": 8, "bn_act_quant_raw": 8, "add_act_quant": 12,
+DATA_POS = {"fake_quant": (0,), "fake_quant_multi": (0,), "bn_act_quant": (0,), "add_act_quant": (0, 1),
+            "bn_quant_add_act_quant": (0, 1)}
+BYTES_PER_ELEM = {"fake_quant": 8, "fake_quant_multi": 8, "bn_act_quant": 8, "add_act_quant": 12,
                   "bn_quant_add_act_quant": 12}
 QUANTS_PER_ELEM = {"bn_quant_add_act_quant": 2}
 
@@ -204,7 +203,7 @@ def data_shapes(name, args):
 
 
 def is_stream_call(name, args):
-    if name in ("bn_act_quant", "bn_act_quant_raw", "add_act_quant", "bn_quant_add_act_quant"):
+    if name in ("bn_act_quant", "add_act_quant", "bn_quant_add_act_quant"):
         return True
     if name == "fake_quant":
         return [v for kind, v in args if kind == "val"][0] == 1

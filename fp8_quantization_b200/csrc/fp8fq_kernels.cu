@@ -149,12 +149,20 @@ __global__ void prepare_kernel(const float* __restrict__ maxval, const float* __
 // ------------------------------------------------------------------------------------------------
 // K1: streaming fake-quant
 // ------------------------------------------------------------------------------------------------
-// PRE_AFFINE  : y = Q(act(bn(x)))                 channel from item-local row arithmetic, bn in smem
+// PRE_AFFINE  : y = Q(act(bn(x)))                 tile-local row arithmetic, bn of the tile's rows in smem
 // PRE_AFFINE_G: same, any shape                   channel from a flat 64-bit-safe division, bn from global
 // PRE_ADD     : y = Q(act(a + b))
 // PRE_BNQ_ADD : y = Q2(act(Q1(bn(x)) + b))        the whole residual-block tail in one pass (12 B/elem)
+// *_PL        : the same when H*W is not a multiple of the vector width (per-lane rows)
+//
+// Launch shape: ONE tile of 256 x VEC x 4 elements per CTA (grid = number of tiles).  Measured on B200
+// (tools/k1_variants.cu, profiles/k1_variants_r01.txt): a persistent grid of SMs x occupancy CTAs reaches
+// 5.85 TB/s on this kernel, one tile per CTA 6.80 TB/s -- resident CTAs in different phases (load / math / store)
+// keep HBM reads and writes overlapped, CTAs marching in lock step do not.  The per-CTA prologue is therefore kept
+// to a 20-float table copy, and batch norm is folded only for the <= 128 rows a tile touches, after the tile's
+// loads have been issued.
 // PRE_AFFINE_PL: PRE_AFFINE when H*W is not a multiple of the vector width (per-lane rows)
-enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2, PRE_AFFINE_G = 3, PRE_BNQ_ADD = 4, PRE_AFFINE_PL = 5 };
+enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2, PRE_AFFINE_G = 3, PRE_BNQ_ADD = 4, PRE_AFFINE_PL = 5, PRE_BNQ_ADD_PL = 6 };
 
 struct StreamArgs {
   const float* x;
@@ -166,9 +174,7 @@ struct StreamArgs {
   int64_t n;
   int K, K2;
   int act;              // activation before the (outer) quantiser
-  int bn_raw;           // 1: bn_p = (mean, var, gamma, beta) folded in the kernel prologue; 0: (scale, shift)
-  const float* bn_p[4];
-  float eps;
+  const float* bn_p[2]; // folded batch norm: (scale, shift), [Cbn] each
   uint32_t hw, Cbn;
   uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
   FastDiv hw_div, c_div;
@@ -182,7 +188,7 @@ template <int KMODE>
 struct ElemCtx {
   float hi, lo, guard;
   RegTab rt;            // KMODE 0
-  const float* stab;    // KMODE 1: table in shared memory
+  const float* stab;    // KMODE 1: the channel table (global memory, read through L1; or a shared-memory copy)
   int K;
   uint32_t base;
   bool irregular;
@@ -212,6 +218,7 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       rs[k] = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
       e[k] = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
     } else {
+      // generic-address loads: c.stab is the global table (stream kernel, L1-resident) or a shared-memory copy
       int ee = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
       const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * ee);
       s[k] = p.x;
@@ -272,17 +279,29 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, i
   }
 }
 
-// eval-mode batch norm as an affine map; same arithmetic as bn_fold_kernel
-__device__ __forceinline__ void bn_fold_one(const StreamArgs& a, uint32_t c, float& sc, float& sh) {
-  if (a.bn_raw) {
-    const float invstd = div_rn(1.0f, sqrtf(add_rn(a.bn_p[1][c], a.eps)));
-    const float g = a.bn_p[2] != nullptr ? a.bn_p[2][c] : 1.0f;
-    const float b = a.bn_p[3] != nullptr ? a.bn_p[3][c] : 0.0f;
-    sc = mul_rn(g, invstd);
-    sh = sub_rn(b, mul_rn(a.bn_p[0][c], sc));
+// Sync-free variant for the streaming kernel: every thread reads the (tiny, L1/L2-resident) channel table itself
+// with uniform loads -- no shared memory, no barrier, so a CTA is a fully independent streaming unit.
+template <int KMODE>
+__device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
+  c.hi = __ldg(gtab + H_HI);
+  c.lo = __ldg(gtab + H_LO);
+  c.guard = __ldg(gtab + H_GUARD);
+  c.K = K;
+  c.stab = gtab;
+  if (KMODE == 0) {
+    const float never = __int_as_float(0x7fc00000);  // NaN: "a >= never" is false
+    const float* thr = gtab + kHdr;
+    const float* sr = gtab + off_sr(K);
+    c.rt.t2 = K >= 2 ? __ldg(thr + 1) : never;
+    c.rt.t3 = K >= 3 ? __ldg(thr + 2) : never;
+    c.rt.s1 = __ldg(sr + 2); c.rt.r1 = __ldg(sr + 3);
+    c.rt.s2 = K >= 2 ? __ldg(sr + 4) : c.rt.s1; c.rt.r2 = K >= 2 ? __ldg(sr + 5) : c.rt.r1;
+    c.rt.s3 = K >= 3 ? __ldg(sr + 6) : c.rt.s2; c.rt.r3 = K >= 3 ? __ldg(sr + 7) : c.rt.r2;
+    c.base = 0;
+    c.irregular = false;
   } else {
-    sc = a.bn_p[0][c];
-    sh = a.bn_p[1][c];
+    c.base = f2u(__ldg(gtab + H_BASE));
+    c.irregular = (f2u(__ldg(gtab + H_FLAGS)) & FLAG_IRREGULAR) != 0;
   }
 }
 
@@ -294,30 +313,23 @@ constexpr int kTabSmem = kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1);
 
 template <int KMODE, int PRE, int VEC, bool CODES>
 __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a) {
-  __shared__ __align__(16) float s_tab[kTabSmem];
-  __shared__ __align__(16) float s_tab2[PRE == PRE_BNQ_ADD ? kTabSmem : 2];
-  extern __shared__ __align__(16) float s_bn[];  // PRE_AFFINE / PRE_BNQ_ADD: scale[Cbn], shift[Cbn]
-  ElemCtx<KMODE> ctx, ctx2;
-  load_ctx<KMODE>(ctx, a.table, a.K, s_tab);
-  if (PRE == PRE_BNQ_ADD) load_ctx<KMODE>(ctx2, a.table2, a.K2, s_tab2);
-  constexpr bool kSmemBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD);
-  if (kSmemBn) {
-    for (uint32_t c = threadIdx.x; c < a.Cbn; c += kThreads) {
-      float sc, sh;
-      bn_fold_one(a, c, sc, sh);
-      s_bn[c] = sc;
-      s_bn[a.Cbn + c] = sh;
-    }
-    __syncthreads();
-  }
+  constexpr bool kTail = (PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL);
+  constexpr bool kPerLane = (PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD_PL);
+  constexpr bool kLocalRows = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || kTail);
+  constexpr bool kTwoIn = (PRE == PRE_ADD || kTail);
 
   constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
   const int64_t nvec_elems = a.n - (a.n % VEC);
   const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
+  // per-CTA parameters: uniform loads, no barrier; issued first, consumed only after the data loads went out
+  ElemCtx<KMODE> ctx, ctx2;
+  load_ctx_direct<KMODE>(ctx, a.table, a.K);
+  if (kTail) load_ctx_direct<KMODE>(ctx2, a.table2, a.K2);
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTile;
     const int64_t base = tile0 + (int64_t)threadIdx.x * VEC;
+    // 1. all of this thread's loads go out before any of them is used
     Pack<VEC> in[kUnroll], in2[kUnroll];
     bool ok[kUnroll];
 #pragma unroll
@@ -326,28 +338,29 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
       ok[u] = i < nvec_elems;
       if (ok[u]) {
         in[u].load(a.x + i);
-        if (PRE == PRE_ADD || PRE == PRE_BNQ_ADD) in2[u].load(a.x2 + i);
+        if (kTwoIn) in2[u].load(a.x2 + i);
       }
     }
-    // item-local row arithmetic: one (uniform) division per tile, then multiplies / compares per vector
     uint32_t col0 = 0, ch0 = 0;
-    if (kSmemBn) {
+    if (kLocalRows) {
+      // tile-local row arithmetic: one division per tile, then one multiply-high per vector
       const uint32_t row0 = fdiv((uint32_t)tile0, a.hw_div);
       col0 = (uint32_t)tile0 - row0 * a.hw;
       ch0 = row0 - fdiv(row0, a.c_div) * a.Cbn;
     }
+    // 3. math + stores
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
       const int64_t i = base + (int64_t)u * kThreads * VEC;
       float v[VEC], yv[VEC];
       int32_t cd[VEC];
-      if (kSmemBn) {
+      if (kLocalRows) {
         const uint32_t p = col0 + (uint32_t)(i - tile0);
-        if (PRE != PRE_AFFINE_PL) {
+        if (!kPerLane) {
           uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
           ch = ch >= a.Cbn ? ch - a.Cbn : ch;
-          const float sc = s_bn[ch], sh = s_bn[a.Cbn + ch];
+          const float sc = __ldg(a.bn_p[0] + ch), sh = __ldg(a.bn_p[1] + ch);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
         } else {
@@ -355,15 +368,14 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
           for (int k = 0; k < VEC; ++k) {
             uint32_t ch = ch0 + __umulhi(p + k, a.hw_rcp);
             ch = ch >= a.Cbn ? ch - a.Cbn : ch;
-            v[k] = bn_apply(in[u].v[k], s_bn[ch], s_bn[a.Cbn + ch]);
+            v[k] = bn_apply(in[u].v[k], __ldg(a.bn_p[0] + ch), __ldg(a.bn_p[1] + ch));
           }
         }
       } else if (PRE == PRE_AFFINE_G) {
         // all VEC lanes of a vector share a row because hw % VEC == 0 (checked by the launcher)
         const uint32_t row = fdiv((uint32_t)i, a.hw_div);
         const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
-        float sc, sh;
-        bn_fold_one(a, ch, sc, sh);
+        const float sc = __ldg(a.bn_p[0] + ch), sh = __ldg(a.bn_p[1] + ch);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
       } else {
@@ -376,13 +388,13 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
       } else if (PRE == PRE_ADD) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(v[k], in2[u].v[k]), a.act);
-      } else if (PRE == PRE_BNQ_ADD) {
+      } else if (kTail) {
         float t[VEC];
         quant_vec<KMODE, false, VEC>(v, ctx, t, cd);  // inner quantiser (output of the block's last BN)
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(t[k], in2[u].v[k]), a.act);
       }
-      if (PRE == PRE_BNQ_ADD) quant_vec<KMODE, CODES, VEC>(v, ctx2, yv, cd);
+      if (kTail) quant_vec<KMODE, CODES, VEC>(v, ctx2, yv, cd);
       else quant_vec<KMODE, CODES, VEC>(v, ctx, yv, cd);
       Pack<VEC> out;
       IPack<VEC> co;
@@ -396,18 +408,16 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
   if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {
     const int64_t i = nvec_elems + threadIdx.x;
     float v = a.x[i];
-    if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD) {
+    if (kLocalRows || PRE == PRE_AFFINE_G) {
       const uint32_t row = fdiv((uint32_t)i, a.hw_div);
       const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
-      float sc, sh;
-      bn_fold_one(a, ch, sc, sh);
-      v = bn_apply(v, sc, sh);
+      v = bn_apply(v, a.bn_p[0][ch], a.bn_p[1][ch]);
     }
     int32_t cd;
     if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) v = apply_act(v, a.act);
     else if (PRE == PRE_ADD) v = apply_act(add_rn(v, a.x2[i]), a.act);
-    else if (PRE == PRE_BNQ_ADD) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), a.act);
-    a.y[i] = PRE == PRE_BNQ_ADD ? quant_elem<KMODE, CODES>(v, ctx2, &cd) : quant_elem<KMODE, CODES>(v, ctx, &cd);
+    else if (kTail) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), a.act);
+    a.y[i] = kTail ? quant_elem<KMODE, CODES>(v, ctx2, &cd) : quant_elem<KMODE, CODES>(v, ctx, &cd);
     if (CODES) a.codes[i] = cd;
   }
 }
@@ -717,47 +727,34 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 template <int KMODE, int PRE, int VEC, bool CODES>
-int launch_stream_t(const StreamArgs& a, size_t smem, cudaStream_t st) {
-  static int occ0 = 0;
-  int occ = occ0;
-  if (occ == 0 || smem > 0) {
-    int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fq_stream_kernel<KMODE, PRE, VEC, CODES>, kThreads, smem) !=
-            cudaSuccess || o <= 0)
-      o = 2;
-    occ = o;
-    if (smem == 0) occ0 = o;
-  }
+int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   const int64_t tile = (int64_t)kThreads * VEC * kUnroll;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
-  int64_t grid = (int64_t)sm_count() * occ;
-  if (grid > ntiles) grid = ntiles;
-  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, smem, st>>>(a);
+  const int64_t grid = ntiles < 0x7fffffffll ? ntiles : 0x7fffffffll;  // one tile per CTA (the kernel still strides)
+  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, 0, st>>>(a);
   return launch_status();
 }
 
 template <int PRE, int VEC>
-int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
-  const bool small = a.K <= 3 && (PRE != PRE_BNQ_ADD || a.K2 <= 3);
+int launch_stream(const StreamArgs& a, cudaStream_t st) {
+  const bool small = a.K <= 3 && ((PRE != PRE_BNQ_ADD && PRE != PRE_BNQ_ADD_PL) || a.K2 <= 3);
   if (PRE == PRE_PLAIN && a.codes != nullptr)  // the code planes exist for the parity tests of the plain quantiser
-    return small ? launch_stream_t<0, PRE_PLAIN, VEC, true>(a, smem, st) : launch_stream_t<1, PRE_PLAIN, VEC, true>(a, smem, st);
-  return small ? launch_stream_t<0, PRE, VEC, false>(a, smem, st) : launch_stream_t<1, PRE, VEC, false>(a, smem, st);
+    return small ? launch_stream_t<0, PRE_PLAIN, VEC, true>(a, st) : launch_stream_t<1, PRE_PLAIN, VEC, true>(a, st);
+  return small ? launch_stream_t<0, PRE, VEC, false>(a, st) : launch_stream_t<1, PRE, VEC, false>(a, st);
 }
 
-// Fills the batch-norm / row-geometry part of StreamArgs and picks the affine variant.
-// Returns the dynamic shared-memory size for the fast variant, or -1 if the generic variant must be used.
-constexpr uint32_t kMaxSmemChannels = 5120;  // 40 KB of (scale, shift)
-int64_t setup_affine(StreamArgs& a, int64_t hw, int64_t Cbn) {
+// Fills the row-geometry part of StreamArgs; true if the tile-local-rows variant applies, false if the generic
+// (flat division per vector) variant must be used.
+bool setup_affine(StreamArgs& a, int64_t hw, int64_t Cbn) {
   a.hw = (uint32_t)hw;
   a.Cbn = (uint32_t)Cbn;
   a.hw_div = make_fastdiv((uint32_t)hw);
   a.c_div = make_fastdiv((uint32_t)Cbn);
   a.hw_rcp = hw > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)hw - 1) / (uint64_t)hw) : 0u;
-  const int64_t max_local_rows = 1 + 4095 / hw;  // rows an item of <= 4096 elements can advance
+  const int64_t max_rows = 2 + 4095 / hw;  // rows a tile of <= 4096 elements can advance: one channel wrap at most
   const bool exact = (uint64_t)(hw + 4096) * (uint64_t)hw < (1ull << 32);  // umulhi(p, hw_rcp) == p / hw
-  if (hw > 1 && exact && Cbn <= kMaxSmemChannels && max_local_rows <= Cbn) return (int64_t)(2 * Cbn * sizeof(float));
-  return -1;
+  return hw > 1 && exact && max_rows <= Cbn;
 }
 
 int check_format(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
@@ -876,7 +873,7 @@ static int fake_quant_impl(const float* x, float* y, int32_t* codes, const float
     StreamArgs a{};
     a.x = x; a.y = y; a.codes = codes; a.table = table; a.n = n; a.K = K; a.act = 0;
     const bool vec = aligned16(x) && aligned16(y) && (codes == nullptr || aligned16(codes));
-    return vec ? launch_stream<PRE_PLAIN, 4>(a, 0, st) : launch_stream<PRE_PLAIN, 1>(a, 0, st);
+    return vec ? launch_stream<PRE_PLAIN, 4>(a, st) : launch_stream<PRE_PLAIN, 1>(a, st);
   }
   fp8fq_tensor_desc d{x, y, table, C, inner};
   return launch_rows(&d, codes, 1, K, st);
@@ -928,8 +925,8 @@ int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, c
   return launch_status();
 }
 
-static int bn_act_quant_impl(const float* x, const float* residual, float* y, const float* const bn_p[4], int bn_raw,
-                             float eps, int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
+static int bn_act_quant_impl(const float* x, const float* residual, float* y, const float* bn_scale,
+                             const float* bn_shift, int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
                              const float* table, float mb, int nb, int sb, const float* table2, float mb2, int nb2,
                              int sb2, void* stream) {
   int M, E, K, K2 = 0;
@@ -942,56 +939,47 @@ static int bn_act_quant_impl(const float* x, const float* residual, float* y, co
   if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode != 0) return FP8FQ_ERR_BAD_ARG;
   const int64_t n = rows * hw;
   if (n == 0) return FP8FQ_OK;
-  if (x == nullptr || y == nullptr || table == nullptr || bn_p[0] == nullptr || bn_p[1] == nullptr)
+  if (x == nullptr || y == nullptr || table == nullptr || bn_scale == nullptr || bn_shift == nullptr)
     return FP8FQ_ERR_BAD_ARG;
   if (n >= (1ll << 32) || hw >= (1ll << 31) || Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
   if (!aligned4(x) || !aligned4(y) || (residual && !aligned4(residual))) return FP8FQ_ERR_ALIGNMENT;
   StreamArgs a{};
   a.x = x; a.x2 = residual; a.y = y; a.table = table; a.table2 = table2; a.n = n; a.K = K; a.K2 = K2; a.act = act;
-  a.bn_raw = bn_raw; a.eps = eps;
-  for (int i = 0; i < 4; ++i) a.bn_p[i] = bn_p[i];
+  a.bn_p[0] = bn_scale; a.bn_p[1] = bn_shift;
   const bool al = aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
   cudaStream_t st = (cudaStream_t)stream;
   const bool tail = table2 != nullptr;
-  const int64_t smem = setup_affine(a, hw, Cbn);
-  if (smem >= 0) {
+  if (setup_affine(a, hw, Cbn)) {
     const bool v4 = al && (hw % 4 == 0);
-    if (tail) return v4 ? launch_stream<PRE_BNQ_ADD, 4>(a, (size_t)smem, st) : launch_stream<PRE_BNQ_ADD, 1>(a, (size_t)smem, st);
-    if (v4) return launch_stream<PRE_AFFINE, 4>(a, (size_t)smem, st);
-    if (al) return launch_stream<PRE_AFFINE_PL, 4>(a, (size_t)smem, st);  // 128-bit accesses, per-lane rows
-    return launch_stream<PRE_AFFINE, 1>(a, (size_t)smem, st);
+    if (tail) {
+      if (v4) return launch_stream<PRE_BNQ_ADD, 4>(a, st);
+      if (al) return launch_stream<PRE_BNQ_ADD_PL, 4>(a, st);  // 128-bit accesses, per-lane rows
+      return launch_stream<PRE_BNQ_ADD, 1>(a, st);
+    }
+    if (v4) return launch_stream<PRE_AFFINE, 4>(a, st);
+    if (al) return launch_stream<PRE_AFFINE_PL, 4>(a, st);
+    return launch_stream<PRE_AFFINE, 1>(a, st);
   }
   if (tail) return FP8FQ_ERR_UNSUPPORTED;  // caller composes the two unfused kernels instead
   const bool v4 = al && (hw % 4 == 0);
-  return v4 ? launch_stream<PRE_AFFINE_G, 4>(a, 0, st) : launch_stream<PRE_AFFINE_G, 1>(a, 0, st);
+  return v4 ? launch_stream<PRE_AFFINE_G, 4>(a, st) : launch_stream<PRE_AFFINE_G, 1>(a, st);
 }
 
 int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift, int64_t rows,
                            int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table, float mantissa_bits,
                            int n_bits, int sign_bits, void* stream) {
-  const float* bn_p[4] = {bn_scale, bn_shift, nullptr, nullptr};
-  return bn_act_quant_impl(x, nullptr, y, bn_p, 0, 0.0f, rows, hw, Cbn, act, bn_mode, table, mantissa_bits, n_bits,
-                           sign_bits, nullptr, 0.0f, 0, 0, stream);
+  return bn_act_quant_impl(x, nullptr, y, bn_scale, bn_shift, rows, hw, Cbn, act, bn_mode, table, mantissa_bits,
+                           n_bits, sign_bits, nullptr, 0.0f, 0, 0, stream);
 }
 
-int fp8fq_bn_act_quant_raw_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
-                               const float* beta, float eps, int64_t rows, int64_t hw, int64_t Cbn, int act,
-                               int bn_mode, const float* table, float mantissa_bits, int n_bits, int sign_bits,
-                               void* stream) {
-  const float* bn_p[4] = {mean, var, gamma, beta};
-  return bn_act_quant_impl(x, nullptr, y, bn_p, 1, eps, rows, hw, Cbn, act, bn_mode, table, mantissa_bits, n_bits,
-                           sign_bits, nullptr, 0.0f, 0, 0, stream);
-}
-
-int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* mean,
-                                     const float* var, const float* gamma, const float* beta, float eps,
-                                     int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
-                                     const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
-                                     int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
-                                     int n_bits_outer, int sign_bits_outer, void* stream) {
+int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* bn_scale,
+                                     const float* bn_shift, int64_t rows, int64_t hw, int64_t Cbn, int act,
+                                     int bn_mode, const float* table_inner, float mantissa_bits_inner,
+                                     int n_bits_inner, int sign_bits_inner, const float* table_outer,
+                                     float mantissa_bits_outer, int n_bits_outer, int sign_bits_outer,
+                                     void* stream) {
   if (residual == nullptr || table_outer == nullptr) return FP8FQ_ERR_BAD_ARG;
-  const float* bn_p[4] = {mean, var, gamma, beta};
-  return bn_act_quant_impl(x, residual, y, bn_p, 1, eps, rows, hw, Cbn, act, bn_mode, table_inner,
+  return bn_act_quant_impl(x, residual, y, bn_scale, bn_shift, rows, hw, Cbn, act, bn_mode, table_inner,
                            mantissa_bits_inner, n_bits_inner, sign_bits_inner, table_outer, mantissa_bits_outer,
                            n_bits_outer, sign_bits_outer, stream);
 }
@@ -1009,7 +997,7 @@ int fp8fq_add_act_quant_f32(const float* a_in, const float* b_in, float* y, int6
   a.x = a_in; a.x2 = b_in; a.y = y; a.table = table; a.n = n; a.K = K; a.act = act;
   const bool vec = aligned16(a_in) && aligned16(b_in) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
-  return vec ? launch_stream<PRE_ADD, 4>(a, 0, st) : launch_stream<PRE_ADD, 1>(a, 0, st);
+  return vec ? launch_stream<PRE_ADD, 4>(a, st) : launch_stream<PRE_ADD, 1>(a, st);
 }
 
 int64_t fp8fq_minmax_workspace_bytes(void) { return 16384; }

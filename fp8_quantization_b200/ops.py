@@ -148,23 +148,8 @@ def _opt_ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def bn_act_quant_raw(x, mean, var, gamma, beta, eps: float, act: int, table, mantissa_bits: float, n_bits: int,
-                     sign_bits: int, out=None):
-    """BNFusedHijacker epilogue (quantized_folded_bn.py:39-55) as ONE launch: the batch-norm fold happens in the
-    kernel prologue.  x is [N, C, *spatial] contiguous; gamma/beta may be None."""
-    _require(x, "x")
-    rows, hw = _rows_hw(x, mean.numel())
-    if out is None:
-        out = torch.empty_like(x)
-    check(lib().fp8fq_bn_act_quant_raw_f32(x.data_ptr(), out.data_ptr(), mean.data_ptr(), var.data_ptr(),
-                                           _opt_ptr(gamma), _opt_ptr(beta), float(eps), rows, hw, mean.numel(),
-                                           int(act), 0, table.data_ptr(), float(mantissa_bits), int(n_bits),
-                                           int(sign_bits), _stream()), "fp8fq_bn_act_quant_raw_f32")
-    return out
-
-
-def bn_quant_add_act_quant(x, residual, mean, var, gamma, beta, eps: float, act: int, table_inner, fmt_inner,
-                           table_outer, fmt_outer, out=None):
+def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inner, fmt_inner, table_outer, fmt_outer,
+                           out=None):
     """Whole residual-block tail (models/resnet_quantized.py:39-46) in one pass:
     Q_outer(act(Q_inner(bn(x)) + residual)).  fmt_* = (mantissa_bits, n_bits, sign_bits).
     Returns None when the fused variant does not cover the shape (caller composes the two kernels)."""
@@ -172,14 +157,13 @@ def bn_quant_add_act_quant(x, residual, mean, var, gamma, beta, eps: float, act:
     _require(residual, "residual")
     if x.shape != residual.shape:
         raise Fp8fqError("bn_quant_add_act_quant: shape mismatch")
-    rows, hw = _rows_hw(x, mean.numel())
+    rows, hw = _rows_hw(x, bn_scale.numel())
     if out is None:
         out = torch.empty_like(x)
     code = lib().fp8fq_bn_quant_add_act_quant_f32(
-        x.data_ptr(), residual.data_ptr(), out.data_ptr(), mean.data_ptr(), var.data_ptr(), _opt_ptr(gamma),
-        _opt_ptr(beta), float(eps), rows, hw, mean.numel(), int(act), 0, table_inner.data_ptr(), float(fmt_inner[0]),
-        int(fmt_inner[1]), int(fmt_inner[2]), table_outer.data_ptr(), float(fmt_outer[0]), int(fmt_outer[1]),
-        int(fmt_outer[2]), _stream())
+        x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), rows, hw,
+        bn_scale.numel(), int(act), 0, table_inner.data_ptr(), float(fmt_inner[0]), int(fmt_inner[1]),
+        int(fmt_inner[2]), table_outer.data_ptr(), float(fmt_outer[0]), int(fmt_outer[1]), int(fmt_outer[2]), _stream())
     if code == -2:
         return None
     check(code, "fp8fq_bn_quant_add_act_quant_f32")

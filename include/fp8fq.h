@@ -111,24 +111,17 @@ int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, cons
                            int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table,
                            float mantissa_bits, int n_bits, int sign_bits, void* stream);
 
-/* Same with the RAW batch-norm buffers: the fold (scale = gamma / sqrt(var + eps), shift = beta - mean * scale) is
- * done in the kernel prologue, so a BNFusedHijacker layer's epilogue is exactly ONE launch. gamma/beta may be NULL. */
-int fp8fq_bn_act_quant_raw_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
-                               const float* beta, float eps, int64_t rows, int64_t hw, int64_t Cbn, int act,
-                               int bn_mode, const float* table, float mantissa_bits, int n_bits, int sign_bits,
-                               void* stream);
-
 /* Replaces: the whole tail of QuantizedBlock.forward (models/resnet_quantized.py:39-46): the last BNFusedHijacker's
  * epilogue (BN -> inner activation quantiser, quantized_folded_bn.py:39-55) followed by
  * `out += residual; relu; quantize_activations(out)`:  y = Q_outer(act(Q_inner(bn(x)) + residual)), one pass,
  * 12 B/element instead of 8 + 12.  Returns FP8FQ_ERR_UNSUPPORTED for shapes the fused variant does not cover
- * (the caller then issues fp8fq_bn_act_quant_raw_f32 + fp8fq_add_act_quant_f32). */
-int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* mean,
-                                     const float* var, const float* gamma, const float* beta, float eps,
-                                     int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode,
-                                     const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
-                                     int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
-                                     int n_bits_outer, int sign_bits_outer, void* stream);
+ * (the caller then issues fp8fq_bn_act_quant_f32 + fp8fq_add_act_quant_f32). */
+int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, float* y, const float* bn_scale,
+                                     const float* bn_shift, int64_t rows, int64_t hw, int64_t Cbn, int act,
+                                     int bn_mode, const float* table_inner, float mantissa_bits_inner,
+                                     int n_bits_inner, int sign_bits_inner, const float* table_outer,
+                                     float mantissa_bits_outer, int n_bits_outer, int sign_bits_outer,
+                                     void* stream);
 
 /* Per-channel affine form of eval-mode batch norm: scale = gamma * rsqrt(var + eps) (as 1/sqrt),
  * shift = beta - mean * scale.  All [Cbn]. */
