@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfp8fq.so")
+# FP8FQ_LIB lets the tuning scripts under tools/ load an alternative build of the SAME library
+LIB_PATH = os.environ.get("FP8FQ_LIB") or os.path.join(_HERE, "libfp8fq.so")
 
 _c_f = ctypes.c_float
 _c_d = ctypes.c_double

@@ -38,8 +38,8 @@ constexpr int kMaxE = 7;         // at most 127 exponent codes
 constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
 constexpr int kMaxK = (1 << kMaxE) - 1;
 
-enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6 };
-enum : int { FLAG_IRREGULAR = 1 };
+enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
+enum : int { FLAG_IRREGULAR = 1, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -202,7 +202,7 @@ FQ_HD float prep_header(float* tab, float mv, int M, int E, int K, int sign_bits
   tab[H_BIAS] = bias;
   tab[H_K] = u2f((uint32_t)K);
   tab[H_GUARD] = tie_guard(M);
-  tab[7] = 0.0f;
+  tab[H_REF] = 0.0f;
   thr[0] = u2f(0x7fc00000u);  // NaN: "a >= thr" is false for every a, including +inf
   for (int j = K; j < k_pad(K); ++j) thr[j] = u2f(0x7fc00000u);
   return bias;
@@ -240,8 +240,30 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
       flags |= FLAG_IRREGULAR;
     }
   }
+  // Exponent-arithmetic fast path (lookup_code_fast): the thresholds are almost exact doublings of each other,
+  // T_k = T_2 * 2^(k-2) up to a few ulps d_k.  With ref = bits(T_2) + min d_k and band = max d_k - min d_k, every
+  // |xc| whose distance to ref is not within `band` ulps above a binade multiple has its code determined by
+  // integer arithmetic alone; the (band + 1) / 2^23 rest takes the table lookup.
+  uint32_t ref = 0, band = 0x7fffffu;  // band = all mantissas: always use the table
+  if (K >= 2 && !(flags & FLAG_IRREGULAR)) {
+    const int64_t t2 = (int64_t)f2u(thr[1]);
+    int64_t dmin = 0, dmax = 0;
+    for (int k = 3; k <= K; ++k) {
+      const int64_t d = (int64_t)f2u(thr[k - 1]) - (t2 + ((int64_t)(k - 2) << 23));
+      dmin = d < dmin ? d : dmin;
+      dmax = d > dmax ? d : dmax;
+    }
+    if (dmax - dmin < (1 << 20) && t2 + dmin > 0) {
+      ref = (uint32_t)(t2 + dmin);
+      band = (uint32_t)(dmax - dmin);
+    }
+  } else if (K == 1) {
+    ref = 0x7f800000u;  // every finite |xc| is below: code 1
+    band = 0;
+  }
   tab[H_BASE] = u2f(base);
-  tab[H_FLAGS] = u2f((uint32_t)flags);
+  tab[H_REF] = u2f(ref);
+  tab[H_FLAGS] = u2f((uint32_t)flags | (band << BAND_SHIFT));
 }
 
 // ---- element path ------------------------------------------------------------------------------
@@ -260,6 +282,17 @@ FQ_HD int lookup_code(float a, const float* tab, int K, uint32_t base, bool irre
   int e = 1;
   for (int k = 2; k <= K; ++k) e += (a >= ld(thr + (k - 1)) ? 1 : 0);
   return e;
+}
+
+// Exponent-arithmetic code lookup (see prep_finish).  Returns the code in [1, K]; *ambiguous is set when |xc| lies
+// in the band where the thresholds' mantissas differ and the caller must use lookup_code instead.
+FQ_HD int lookup_code_fast(float a, uint32_t ref, uint32_t band, int K, bool* ambiguous) {
+  const int32_t i = (int32_t)(f2u(a) - ref);
+  const int32_t q = i >> 23;  // arithmetic shift: floor(i / 2^23)
+  *ambiguous = (uint32_t)(i & 0x7fffff) <= band;
+  int e = q + 2;
+  e = e < 1 ? 1 : e;
+  return e > K ? K : e;
 }
 
 // Quantise xc (already clamped) with the selected (s, rs).  Returns y; *q_out = round(xc / s).

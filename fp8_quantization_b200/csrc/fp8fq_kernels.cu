@@ -192,6 +192,7 @@ struct ElemCtx {
   int K;
   uint32_t base;
   bool irregular;
+  uint32_t ref, band;   // KMODE 1: exponent-arithmetic fast path (lookup_code_fast)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -218,12 +219,18 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       rs[k] = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
       e[k] = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
     } else {
+      // exponent-arithmetic code, table lookup only in the (band + 1) / 2^23 ambiguous mantissa band.
       // generic-address loads: c.stab is the global table (stream kernel, L1-resident) or a shared-memory copy
-      int ee = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
+      bool amb;
+      int ee = lookup_code_fast(a, c.ref, c.band, c.K, &amb);
+      if (amb) {
+        ee = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
+        ee = ee < 1 ? 1 : ee;
+      }
       const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * ee);
       s[k] = p.x;
       rs[k] = p.y;
-      e[k] = ee < 1 ? 1 : ee;
+      e[k] = ee;
     }
     const float r = mul_rn(xc[k], rs[k]);
     q[k] = nearbyintf(r);
@@ -266,6 +273,8 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, i
   c.K = K;
   c.base = f2u(smem[H_BASE]);
   c.irregular = (f2u(smem[H_FLAGS]) & FLAG_IRREGULAR) != 0;
+  c.ref = f2u(smem[H_REF]);
+  c.band = f2u(smem[H_FLAGS]) >> BAND_SHIFT;
   c.stab = smem;
   if (KMODE == 0) {
     const float never = __int_as_float(0x7fc00000);  // NaN: "a >= never" is false
@@ -299,24 +308,48 @@ __device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* 
     c.rt.s3 = K >= 3 ? __ldg(sr + 6) : c.rt.s2; c.rt.r3 = K >= 3 ? __ldg(sr + 7) : c.rt.r2;
     c.base = 0;
     c.irregular = false;
+    c.ref = 0;
+    c.band = 0;
   } else {
+    const uint32_t fl = f2u(__ldg(gtab + H_FLAGS));
     c.base = f2u(__ldg(gtab + H_BASE));
-    c.irregular = (f2u(__ldg(gtab + H_FLAGS)) & FLAG_IRREGULAR) != 0;
+    c.irregular = (fl & FLAG_IRREGULAR) != 0;
+    c.ref = f2u(__ldg(gtab + H_REF));
+    c.band = fl >> BAND_SHIFT;
   }
 }
 
 __device__ __forceinline__ float bn_apply(float v, float sc, float sh) { return fmaf(v, sc, sh); }
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+// independent 128-bit loads in flight per thread: 4 vectors, or 2 vectors x 2 inputs for the residual variants
+// (same bytes in flight, 16 fewer live registers -> no spills at 5-6 resident CTAs per SM)
+template <int PRE>
+struct StreamUnroll {
+  static constexpr int value = (PRE == PRE_ADD || PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL) ? 2 : 4;
+};
 constexpr int kTabSmem = kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1);
 
+// Resident CTAs per SM the kernel is compiled for.  Measured (tools/bench_kernels.py, B200, [128,64,112,112]):
+// one-tile CTAs are short lived, so occupancy is what keeps HBM busy -- plain E2M5 5.9 -> 6.5 TB/s going from 4 to
+// 6 CTAs/SM; the two-input variants spill at 6 and are best at 5.  FQ_MINB overrides for tuning builds.
+template <int KMODE, int PRE>
+struct StreamMinBlocks {
+#ifdef FQ_MINB
+  static constexpr int value = FQ_MINB;
+#else
+  static constexpr int value =
+      ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE == 0) ? 6 : 5;
+#endif
+};
+
 template <int KMODE, int PRE, int VEC, bool CODES>
-__global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) fq_stream_kernel(const StreamArgs a) {
   constexpr bool kTail = (PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL);
   constexpr bool kPerLane = (PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD_PL);
   constexpr bool kLocalRows = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || kTail);
   constexpr bool kTwoIn = (PRE == PRE_ADD || kTail);
+  constexpr int kUnroll = StreamUnroll<PRE>::value;
 
   constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
   const int64_t nvec_elems = a.n - (a.n % VEC);
@@ -425,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) fq_stream_kernel(const StreamArgs a)
 // ------------------------------------------------------------------------------------------------
 // K1 per-channel: x is [C, inner]; one CTA per (row, chunk) work item, row table staged in smem
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxMulti = 24;  // tensors per launch (descriptors travel in the kernel parameter space)
+constexpr int kMaxMulti = 48;  // tensors per launch (descriptors travel in the kernel parameter space)
 
 struct RowsTensor {
   const float* x;
@@ -451,7 +484,6 @@ struct RowsArgs {
 // fill the GPU or to amortise a launch on their own).
 template <int KMODE, bool CODES>
 __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
-  __shared__ __align__(16) float s_tab[kTabSmem];
   const int stride = table_stride(a.K);
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     int ti = 0;
@@ -460,14 +492,13 @@ __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ Ro
     const int64_t lw = w - T.work0;
     const int64_t row = lw / T.chunks_per_row;
     const int64_t ck = lw - row * T.chunks_per_row;
-    __syncthreads();  // previous iteration done with s_tab
-    ElemCtx<KMODE> ctx;
-    load_ctx<KMODE>(ctx, T.table + row * stride, a.K, s_tab);
     const int64_t beg = ck * a.chunk;
     const int64_t end = (beg + a.chunk < T.inner) ? beg + a.chunk : T.inner;
     const float* xr = T.x + row * T.inner;
     float* yr = T.y + row * T.inner;
     int32_t* cr = CODES ? T.codes + row * T.inner : nullptr;
+    ElemCtx<KMODE> ctx;
+    load_ctx_direct<KMODE>(ctx, T.table + row * stride, a.K);  // uniform loads of the row's table, no barrier
     if (T.vec_ok) {
       for (int64_t i = beg + (int64_t)threadIdx.x * 4; i < end; i += (int64_t)blockDim.x * 4) {
         Pack<4> in, out;
@@ -696,6 +727,8 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
     ctx.hi = cur[H_HI]; ctx.lo = cur[H_LO]; ctx.guard = cur[H_GUARD]; ctx.K = K;
     ctx.base = f2u(cur[H_BASE]);
     ctx.irregular = (f2u(cur[H_FLAGS]) & FLAG_IRREGULAR) != 0;
+    ctx.ref = f2u(cur[H_REF]);
+    ctx.band = f2u(cur[H_FLAGS]) >> BAND_SHIFT;
     ctx.stab = cur;
     float err = 0.0f;
 #pragma unroll
@@ -728,7 +761,7 @@ inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3
 
 template <int KMODE, int PRE, int VEC, bool CODES>
 int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
-  const int64_t tile = (int64_t)kThreads * VEC * kUnroll;
+  const int64_t tile = (int64_t)kThreads * VEC * StreamUnroll<PRE>::value;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
   const int64_t grid = ntiles < 0x7fffffffll ? ntiles : 0x7fffffffll;  // one tile per CTA (the kernel still strides)

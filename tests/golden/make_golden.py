@@ -260,6 +260,45 @@ def gen_resnet18(R):
     print("resnet18_m5.npz", len(names), "quantizers")
 
 
+def gen_mobilenetv2(R):
+    """BASELINE config 3: reference QuantizedMobileNetV2(MobileNetV2()) under seed 10, README parameters with M=4:
+    calibrate on one batch, fix ranges, record every quantiser's range and the logits."""
+    Rm = load_reference_models()
+    RE = R.range_estimators
+    torch.manual_seed(10)
+    net = Rm.mobilenet_v2.MobileNetV2()
+    qp = dict(method=R.FPQuantizer, act_method=R.FPQuantizer, n_bits=8, n_bits_act=None, per_channel_weights=True,
+              quant_setup="all", weight_range_method=RE.CurrentMinMaxEstimator, weight_range_options={},
+              act_range_method=RE.AllMinMaxEstimator, act_range_options={}, quantize_input=False,
+              fp8_kwargs=dict(maxval=None, mantissa_bits=4, set_maxval=True, learn_maxval=False,
+                              learn_mantissa_bits=False, mse_include_mantissa_bits=False, allow_unsigned=False))
+    model = Rm.mobilenet_v2_quantized.QuantizedMobileNetV2(net, **qp)
+    model.eval()
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    model.set_quant_state(True, True)
+    with torch.no_grad():
+        model(x)
+        model.fix_ranges()
+        logits = model(x)
+    names, maxvals = [], []
+    for name, mod in model.named_modules():
+        if isinstance(mod, R.FPQuantizer):
+            names.append(name)
+            maxvals.append(mod.maxval.reshape(-1).numpy().copy())
+    out = {"logits": logits.numpy(), "names": np.array(names),
+           "state_keys": np.array([k for k in net.state_dict().keys()])}
+    # checksums of the fp32 parameters: the test rebuilds the network under the same seed with this package's
+    # MobileNetV2 (same construction and initialisation order) and verifies it got bit-identical weights
+    sd = net.state_dict()
+    out["w_checksums"] = np.array([int(sd[k].float().contiguous().view(torch.int32).to(torch.int64).sum())
+                                   for k in sd.keys()], dtype=np.int64)  # exact: sum of the fp32 bit patterns
+    for i, mv in enumerate(maxvals):
+        out[f"maxval_{i:03d}"] = mv
+    np.savez_compressed(os.path.join(OUT, "mobilenetv2_m4.npz"), **out)
+    print("mobilenetv2_m4.npz", len(names), "quantizers")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     R = load_reference()
@@ -269,6 +308,8 @@ if __name__ == "__main__":
     gen_mse(R)
     gen_modules(R)
     gen_resnet18(R)
+    if "--mobilenet" in sys.argv:
+        gen_mobilenetv2(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

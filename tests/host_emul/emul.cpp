@@ -42,11 +42,14 @@ int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table
     const float hi = tab[H_HI], lo = tab[H_LO], guard = tab[H_GUARD];
     const uint32_t base = f2u(tab[H_BASE]);
     const bool irregular = force_irregular || (f2u(tab[H_FLAGS]) & FLAG_IRREGULAR);
+    const uint32_t ref = f2u(tab[H_REF]), band = force_irregular ? 0x7fffffu : (f2u(tab[H_FLAGS]) >> BAND_SHIFT);
     for (int64_t i = 0; i < inner; ++i) {
       const float v = x[c * inner + i];
       const float xc = min_nan(max_nan(v, lo), hi);
       const float a = fabsf(xc);
-      int e = lookup_code(a, tab, K, base, irregular, [](const float* p) { return *p; });
+      bool amb;
+      int e = lookup_code_fast(a, ref, band, K, &amb);  // same two-level lookup as quant_vec<1, ...>
+      if (amb) e = lookup_code(a, tab, K, base, irregular, [](const float* p) { return *p; });
       const float s = tab[off_sr(K) + 2 * e], rs = tab[off_sr(K) + 2 * e + 1];
       e = e < 1 ? 1 : e;
       float q;
@@ -70,6 +73,13 @@ int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table
 int emul_table_flags(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
   int M, E, K;
   if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
-  return (int)f2u(table[c * table_stride(K) + H_FLAGS]);
+  return (int)(f2u(table[c * table_stride(K) + H_FLAGS]) & 0xff);
+}
+
+// mantissa band of the exponent-arithmetic fast path (ulps); 0x7fffff = fast path disabled for this channel
+int emul_table_band(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  return (int)(f2u(table[c * table_stride(K) + H_FLAGS]) >> BAND_SHIFT);
 }
 }

@@ -1,0 +1,173 @@
+"""GPU: the remaining BASELINE.json configurations as parity cases.
+  config 3: MobileNetV2-quantized, M=4, per-channel + BN-fused modules  (vs golden of the real reference)
+  config 4: mantissa sweep M in {2..7} with the MSE grid estimator on ResNet-18-like activations (vs oracle)
+  config 5: batch-sharded calibration: ranks' ranges == single-process ranges on the concatenated batch
+            (2 GPUs when available, see also tests/test_dist_gloo.py for the CPU/gloo version)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import bits, load_golden
+from oracle import fp8_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config3_mobilenetv2_m4_vs_reference_golden():
+    from fp8_quantization_b200 import modules, ops, workloads
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    g = load_golden("mobilenetv2_m4.npz")
+    torch.manual_seed(10)
+    net = workloads.MobileNetV2()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(g["state_keys"])
+    mine = np.array([int(sd[k].float().contiguous().view(torch.int32).to(torch.int64).sum()) for k in sd.keys()],
+                    dtype=np.int64)
+    assert np.array_equal(mine, g["w_checksums"])  # same fp32 network as the reference built under seed 10
+    model = workloads.QuantizedMobileNetV2(net, **workloads.readme_quant_params(4)).to(DEV).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+        model.fix_ranges()
+        with torch.no_grad():
+            model(x)  # folds the batch norms once
+            n0 = ops.launch_count()
+            logits = model(x)
+            n_fused = ops.launch_count() - n0
+            modules.FUSE_BLOCK_TAIL = False
+            modules.BATCH_WEIGHT_QUANT = False
+            n0 = ops.launch_count()
+            logits_layerwise = model(x)
+            n_layerwise = ops.launch_count() - n0
+            modules.FUSE_BLOCK_TAIL = True
+            modules.BATCH_WEIGHT_QUANT = True
+            modules.FUSE_EPILOGUES = False
+            logits_unfused = model(x)
+            modules.FUSE_EPILOGUES = True
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    # 117 quantiser calls of the reference (53 weights + 64 activations) -> 1 weight launch + 52 BN epilogues
+    # (10 of them fused with the residual add and its quantiser) + avgpool + fc output
+    assert n_layerwise == 53 + 52 + 10 + 2
+    assert n_fused == 2 + 42 + 10 + 2  # 53 weight tensors = 2 multi-tensor launches (48 descriptors per launch)
+    assert torch.equal(logits, logits_layerwise)  # fusing launches changes no bit
+    names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]
+    assert names == list(g["names"])
+    mods = dict(model.named_modules())
+    for i, n in enumerate(names):
+        ours = mods[n].maxval.reshape(-1).cpu().numpy()
+        ref = g[f"maxval_{i:03d}"]
+        if ours.size > 1:
+            assert np.array_equal(ours, ref), n       # per-channel weight ranges: exact
+        elif ref[0] != 3.0:                           # 3.0 = never-calibrated default of unused quantisers
+            np.testing.assert_allclose(ours, ref, rtol=3e-2, err_msg=n)
+    ref_logits = torch.from_numpy(g["logits"])
+    cos = F.cosine_similarity(logits.cpu().flatten(), ref_logits.flatten(), dim=0).item()
+    assert cos > 0.97, cos
+    assert F.cosine_similarity(logits.flatten(), logits_unfused.flatten(), dim=0).item() > 0.99
+
+
+@pytest.mark.parametrize("M", [2, 3, 4, 5, 6, 7])
+def test_config4_mse_grid_sweep_vs_oracle(M):
+    """FP_MSE_Estimator at every mantissa width on a post-ReLU activation tensor: identical search grid, MSE table
+    within fp32 summation noise of the oracle's 111-iteration loop, same selected range."""
+    import fp8_quantization_b200 as fq
+
+    torch.manual_seed(20 + M)
+    x = torch.relu(torch.randn(4, 16, 14, 14)) * 1.7 + 0.02 * torch.randn(4, 16, 14, 14)
+    q = fq.FPQuantizer(8, mantissa_bits=M, set_maxval=True, mse_include_mantissa_bits=False)
+    est = fq.FP_MSE_Estimator(quantizer=q)
+    mn, mx = est(x.to(DEV))
+    oq = O.OracleFPQuantizer(8, mantissa_bits=M, set_maxval=True, mse_include_mantissa_bits=False)
+    oest = O.OracleFPMSE(quantizer=oq)
+    omn, omx = oest(x)
+    assert torch.equal(est.search_grid.cpu(), oest.search_grid)
+    np.testing.assert_allclose(est.mses.cpu().numpy(), oest.mses.numpy(), rtol=3e-4, atol=1e-12)
+    row = oest.mses[0, :, 0]
+    gi = int((est.search_grid[:, 0].cpu() - mx.cpu()).abs().argmin())
+    assert float(row[gi]) <= float(row.min()) * (1 + 3e-4)  # same argmin, or a tie within summation noise
+    assert float(q._mbits_host) == float(oq.mantissa_bits) == float(M)
+    # whole-model: ResNet-18 calibrated with the MSE estimator on its activations runs and gives finite logits
+    if M == 5:
+        from fp8_quantization_b200 import workloads
+
+        torch.manual_seed(10)
+        qp = workloads.readme_quant_params(5, act_range_method=fq.FP_MSE_Estimator)
+        model = workloads.resnet18_quantized(**qp).to(DEV).eval()
+        xb = torch.randn(4, 3, 224, 224, device=DEV)
+        workloads.pass_data_for_range_estimation([xb], model, True, True, 1)
+        model.fix_ranges()
+        with torch.no_grad():
+            assert torch.isfinite(model(xb)).all()
+
+
+_DP_SCRIPT = r"""
+import os, sys, json, torch
+sys.path.insert(0, os.environ["FQ_ROOT"])
+import fp8_quantization_b200 as fq
+from fp8_quantization_b200 import dist as fq_dist, workloads
+from fp8_quantization_b200.quantizers import FPQuantizer
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+assert fq_dist.init_from_env("nccl")
+torch.manual_seed(10)
+model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(dev).eval()
+gen = torch.Generator().manual_seed(10)
+gx = torch.randn(4 * world, 3, 224, 224, generator=gen)
+workloads.pass_data_for_range_estimation([fq_dist.shard_batch(gx).to(dev)], model, True, True, 1)
+model.fix_ranges()
+ranges = [m.maxval.reshape(-1).cpu() for m in model.modules() if isinstance(m, FPQuantizer)]
+fq_dist.enable(False)
+with torch.no_grad():
+    logits = model(fq_dist.shard_batch(gx).to(dev))
+stats = workloads.validate(model, [fq_dist.shard_batch(gx).to(dev)])
+if rank == 0:
+    # single-process run on the concatenated batch
+    torch.manual_seed(10)
+    ref = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(dev).eval()
+    workloads.pass_data_for_range_estimation([gx.to(dev)], ref, True, True, 1)
+    ref.fix_ranges()
+    ref_ranges = [m.maxval.reshape(-1).cpu() for m in ref.modules() if isinstance(m, FPQuantizer)]
+    exact = sum(int(torch.equal(a, b)) for a, b in zip(ranges, ref_ranges))
+    close = all(torch.allclose(a, b, rtol=2e-2) for a, b in zip(ranges, ref_ranges))
+    with torch.no_grad():
+        ref_logits = ref(gx.to(dev))[: logits.shape[0]]
+    cos = torch.nn.functional.cosine_similarity(logits.flatten(), ref_logits.flatten(), dim=0).item()
+    print("DPRESULT " + json.dumps({"world": world, "quantizers": len(ranges), "bit_equal_ranges": exact,
+                                    "all_close": bool(close), "logits_cos": cos, "count": stats["count"]}))
+fq_dist.barrier()
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (run under gpurun --gpus 2)")
+def test_config5_sharded_calibration_matches_single_process(tmp_path):
+    """Weight ranges and the first layer's activation range are bit-identical to the single-process run (min/max
+    are order independent); deeper activation ranges agree to cuDNN's batch-size-dependent conv algorithm choice."""
+    script = tmp_path / "dp.py"
+    script.write_text(_DP_SCRIPT)
+    env = dict(os.environ, FQ_ROOT=ROOT)
+    world = min(torch.cuda.device_count(), 8)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("DPRESULT ")][-1]
+    import json
+    r = json.loads(line[len("DPRESULT "):])
+    print(r)
+    assert r["quantizers"] == 50 and r["all_close"] and r["count"] == 4 * world
+    assert r["bit_equal_ranges"] >= 22  # 21 weight quantisers + the stem's activation range at least
+    assert r["logits_cos"] > 0.98
