@@ -174,7 +174,8 @@ struct StreamArgs {
   int64_t n;
   int K, K2;
   int act;              // activation before the (outer) quantiser
-  const float* bn_p[2]; // folded batch norm: (scale, shift), [Cbn] each
+  const float* bn_p[2]; // bn_mode 0: (scale, shift), [Cbn] each; bn_mode 1: bn_p[0] = packed [4 * Cbn]
+  int bn_mode;          // 0: y = fma(x, scale, shift); 1: ATen-CUDA's eval batch norm, bit for bit (see BnParams)
   uint32_t hw, Cbn;
   uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
   FastDiv hw_div, c_div;
@@ -319,7 +320,34 @@ __device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* 
   }
 }
 
-__device__ __forceinline__ float bn_apply(float v, float sc, float sh) { return fmaf(v, sc, sh); }
+// Per-channel batch-norm parameters of one vector.
+//   mode 0 (affine):  y = fma(x, scale, shift), scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+//   mode 1 (exact) :  y = fma(gamma * (x - mean), rsqrtf(var + eps), beta) -- the arithmetic of ATen's eval-mode
+//                     batch norm on CUDA (native batch_norm_transform_input_kernel), measured bit-identical to
+//                     F.batch_norm on B200 for every element (tools/bn_formula.py, profiles/bn_formula_r01.json)
+struct BnParams {
+  float a, b, c, d;
+};
+template <int BNM>
+__device__ __forceinline__ BnParams bn_load(const StreamArgs& a, uint32_t ch) {
+  BnParams p;
+  if (BNM == 0) {
+    p.a = __ldg(a.bn_p[0] + ch);
+    p.b = __ldg(a.bn_p[1] + ch);
+    p.c = 0.0f;
+    p.d = 0.0f;
+  } else {
+    // one 128-bit load: {mean, gamma, rsqrtf(var + eps), beta} of channel ch
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.bn_p[0]) + ch);
+    p.a = q.x; p.b = q.y; p.c = q.z; p.d = q.w;
+  }
+  return p;
+}
+template <int BNM>
+__device__ __forceinline__ float bn_apply(float v, const BnParams& p) {
+  if (BNM == 0) return fmaf(v, p.a, p.b);
+  return fmaf(mul_rn(p.b, sub_rn(v, p.a)), p.c, p.d);
+}
 
 constexpr int kThreads = 256;
 // independent 128-bit loads in flight per thread: 4 vectors, or 2 vectors x 2 inputs for the residual variants
@@ -343,7 +371,7 @@ struct StreamMinBlocks {
 #endif
 };
 
-template <int KMODE, int PRE, int VEC, bool CODES>
+template <int KMODE, int PRE, int VEC, bool CODES, int BNM>
 __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) fq_stream_kernel(const StreamArgs a) {
   constexpr bool kTail = (PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL);
   constexpr bool kPerLane = (PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD_PL);
@@ -393,24 +421,24 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
         if (!kPerLane) {
           uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
           ch = ch >= a.Cbn ? ch - a.Cbn : ch;
-          const float sc = __ldg(a.bn_p[0] + ch), sh = __ldg(a.bn_p[1] + ch);
+          const BnParams bp = bn_load<BNM>(a, ch);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
+          for (int k = 0; k < VEC; ++k) v[k] = bn_apply<BNM>(in[u].v[k], bp);
         } else {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
             uint32_t ch = ch0 + __umulhi(p + k, a.hw_rcp);
             ch = ch >= a.Cbn ? ch - a.Cbn : ch;
-            v[k] = bn_apply(in[u].v[k], __ldg(a.bn_p[0] + ch), __ldg(a.bn_p[1] + ch));
+            v[k] = bn_apply<BNM>(in[u].v[k], bn_load<BNM>(a, ch));
           }
         }
       } else if (PRE == PRE_AFFINE_G) {
         // all VEC lanes of a vector share a row because hw % VEC == 0 (checked by the launcher)
         const uint32_t row = fdiv((uint32_t)i, a.hw_div);
         const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
-        const float sc = __ldg(a.bn_p[0] + ch), sh = __ldg(a.bn_p[1] + ch);
+        const BnParams bp = bn_load<BNM>(a, ch);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = bn_apply(in[u].v[k], sc, sh);
+        for (int k = 0; k < VEC; ++k) v[k] = bn_apply<BNM>(in[u].v[k], bp);
       } else {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = in[u].v[k];
@@ -444,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
     if (kLocalRows || PRE == PRE_AFFINE_G) {
       const uint32_t row = fdiv((uint32_t)i, a.hw_div);
       const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
-      v = bn_apply(v, a.bn_p[0][ch], a.bn_p[1][ch]);
+      v = bn_apply<BNM>(v, bn_load<BNM>(a, ch));
     }
     int32_t cd;
     if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) v = apply_act(v, a.act);
@@ -689,6 +717,15 @@ __global__ void bn_fold_kernel(const float* mean, const float* var, const float*
   shift[c] = sub_rn(b, mul_rn(mean[c], sc));
 }
 
+// packed parameters of the exact mode: [C][4] = {mean, gamma, rsqrtf(var + eps), beta} per channel
+__global__ void bn_pack_kernel(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                               int64_t C, float* packed) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  reinterpret_cast<float4*>(packed)[c] = make_float4(mean[c], gamma != nullptr ? gamma[c] : 1.0f,
+                                                     rsqrtf(add_rn(var[c], eps)), beta != nullptr ? beta[c] : 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2b: MSE grid.  grid = (chunks, C).  Each CTA keeps its slice of one channel row in registers and
 // sweeps the G candidate tables of the current mantissa width.
@@ -759,22 +796,27 @@ __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, do
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
-template <int KMODE, int PRE, int VEC, bool CODES>
+template <int KMODE, int PRE, int VEC, bool CODES, int BNM>
 int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   const int64_t tile = (int64_t)kThreads * VEC * StreamUnroll<PRE>::value;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
   const int64_t grid = ntiles < 0x7fffffffll ? ntiles : 0x7fffffffll;  // one tile per CTA (the kernel still strides)
-  fq_stream_kernel<KMODE, PRE, VEC, CODES><<<(unsigned)grid, kThreads, 0, st>>>(a);
+  fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM><<<(unsigned)grid, kThreads, 0, st>>>(a);
   return launch_status();
 }
 
 template <int PRE, int VEC>
 int launch_stream(const StreamArgs& a, cudaStream_t st) {
+  constexpr bool kHasBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD ||
+                           PRE == PRE_BNQ_ADD_PL);
   const bool small = a.K <= 3 && ((PRE != PRE_BNQ_ADD && PRE != PRE_BNQ_ADD_PL) || a.K2 <= 3);
   if (PRE == PRE_PLAIN && a.codes != nullptr)  // the code planes exist for the parity tests of the plain quantiser
-    return small ? launch_stream_t<0, PRE_PLAIN, VEC, true>(a, st) : launch_stream_t<1, PRE_PLAIN, VEC, true>(a, st);
-  return small ? launch_stream_t<0, PRE, VEC, false>(a, st) : launch_stream_t<1, PRE, VEC, false>(a, st);
+    return small ? launch_stream_t<0, PRE_PLAIN, VEC, true, 0>(a, st) : launch_stream_t<1, PRE_PLAIN, VEC, true, 0>(a, st);
+  if (kHasBn && a.bn_mode == 1)
+    return small ? launch_stream_t<0, PRE, VEC, false, kHasBn ? 1 : 0>(a, st)
+                 : launch_stream_t<1, PRE, VEC, false, kHasBn ? 1 : 0>(a, st);
+  return small ? launch_stream_t<0, PRE, VEC, false, 0>(a, st) : launch_stream_t<1, PRE, VEC, false, 0>(a, st);
 }
 
 // Fills the row-geometry part of StreamArgs; true if the tile-local-rows variant applies, false if the generic
@@ -969,16 +1011,17 @@ static int bn_act_quant_impl(const float* x, const float* residual, float* y, co
     r = check_format(mb2, nb2, sb2, &M, &E, &K2);
     if (r != FP8FQ_OK) return r;
   }
-  if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode != 0) return FP8FQ_ERR_BAD_ARG;
+  if (rows < 0 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1) return FP8FQ_ERR_BAD_ARG;
   const int64_t n = rows * hw;
   if (n == 0) return FP8FQ_OK;
-  if (x == nullptr || y == nullptr || table == nullptr || bn_scale == nullptr || bn_shift == nullptr)
+  if (x == nullptr || y == nullptr || table == nullptr || bn_scale == nullptr || (bn_mode == 0 && bn_shift == nullptr))
     return FP8FQ_ERR_BAD_ARG;
   if (n >= (1ll << 32) || hw >= (1ll << 31) || Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
   if (!aligned4(x) || !aligned4(y) || (residual && !aligned4(residual))) return FP8FQ_ERR_ALIGNMENT;
   StreamArgs a{};
   a.x = x; a.x2 = residual; a.y = y; a.table = table; a.table2 = table2; a.n = n; a.K = K; a.K2 = K2; a.act = act;
-  a.bn_p[0] = bn_scale; a.bn_p[1] = bn_shift;
+  if (bn_mode == 1 && !aligned16(bn_scale)) return FP8FQ_ERR_ALIGNMENT;
+  a.bn_p[0] = bn_scale; a.bn_p[1] = bn_shift; a.bn_mode = bn_mode;
   const bool al = aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
   cudaStream_t st = (cudaStream_t)stream;
   const bool tail = table2 != nullptr;
@@ -996,6 +1039,16 @@ static int bn_act_quant_impl(const float* x, const float* residual, float* y, co
   if (tail) return FP8FQ_ERR_UNSUPPORTED;  // caller composes the two unfused kernels instead
   const bool v4 = al && (hw % 4 == 0);
   return v4 ? launch_stream<PRE_AFFINE_G, 4>(a, st) : launch_stream<PRE_AFFINE_G, 1>(a, st);
+}
+
+int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                      int64_t Cbn, float* packed, void* stream) {
+  if (mean == nullptr || var == nullptr || packed == nullptr || Cbn < 1) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned16(packed)) return FP8FQ_ERR_ALIGNMENT;
+  const int threads = 128;
+  bn_pack_kernel<<<(unsigned)((Cbn + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      mean, var, gamma, beta, eps, Cbn, packed);
+  return launch_status();
 }
 
 int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift, int64_t rows,

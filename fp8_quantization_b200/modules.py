@@ -39,6 +39,9 @@ activations_set = [nn.ReLU, nn.ReLU6, nn.Hardtanh, nn.Sigmoid, nn.Tanh, nn.GELU,
 FUSE_EPILOGUES = True      # BN + act + quant in one launch; residual add + act + quant in one launch
 FUSE_BLOCK_TAIL = True     # BN + quant + residual add + act + quant of a residual block in one launch
 BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in one launch
+BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
+                           # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
+                           # from F.batch_norm before quantisation)
 
 
 def _act_code(act):
@@ -219,10 +222,10 @@ class QuantizedActivation(QuantizedModule):
                 residual = residual if residual.is_contiguous() else residual.contiguous()
                 ti, _ = qi.table_for(res)
                 to, _ = qo.table_for(res)
-                scale, shift = last.folded_bn()
+                scale, shift, mode = last.folded_bn()
                 out = ops.bn_quant_add_act_quant(res, residual, scale, shift, code, ti,
                                                  (qi._mbits_host, qi.n_bits, qi.sign_bits), to,
-                                                 (qo._mbits_host, qo.n_bits, qo.sign_bits))
+                                                 (qo._mbits_host, qo.n_bits, qo.sign_bits), bn_mode=mode)
                 if out is not None:
                     return out
             return self.add_act_quantize(last.epilogue(res), residual, act)
@@ -313,14 +316,19 @@ class BNFusedHijacker(QuantizationHijacker):
         self._bn_folded = None
 
     def folded_bn(self):
-        """Eval-mode batch norm as the per-channel affine map (scale, shift) the fused kernels consume.  Recomputed
+        """Eval-mode batch norm in the form the fused kernels consume: (params, shift | None, bn_mode).  Recomputed
         (one tiny launch) only when one of the four BN tensors or eps changed -- they are constants of the validate
         pass; BN re-estimation or a state-dict load bumps their version counters / storage and invalidates it."""
         ts = (self.running_mean, self.running_var, self.gamma, self.beta)
-        key = tuple((t.data_ptr(), t._version) for t in ts) + (float(self.epsilon),)
+        mode = 1 if BN_EXACT else 0
+        key = tuple((t.data_ptr(), t._version) for t in ts) + (float(self.epsilon), mode)
         if key != self._bn_key:
-            self._bn_folded = ops.bn_fold(self.running_mean, self.running_var, self.gamma.detach(), self.beta.detach(),
-                                          self.epsilon)
+            if mode == 1:
+                self._bn_folded = (ops.bn_pack(self.running_mean, self.running_var, self.gamma.detach(),
+                                               self.beta.detach(), self.epsilon), None, 1)
+            else:
+                self._bn_folded = ops.bn_fold(self.running_mean, self.running_var, self.gamma.detach(),
+                                              self.beta.detach(), self.epsilon) + (0,)
             self._bn_key = key
         return self._bn_folded
 
@@ -344,9 +352,9 @@ class BNFusedHijacker(QuantizationHijacker):
             q = self.activation_quantizer.quantizer
             res = res if res.is_contiguous() else res.contiguous()
             table, _ = q.table_for(res)
-            scale, shift = self.folded_bn()
+            scale, shift, mode = self.folded_bn()
             return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
-                                    q.n_bits, q.sign_bits)
+                                    q.n_bits, q.sign_bits, bn_mode=mode)
         res = F.batch_norm(res, self.running_mean, self.running_var, self.gamma, self.beta, self.training,
                            self.momentum, self.epsilon)
         if self.activation_function is not None:

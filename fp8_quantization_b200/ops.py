@@ -29,6 +29,10 @@ def _require(t: torch.Tensor, name: str):
         raise Fp8fqError(f"{name} must be contiguous")
 
 
+def _opt_ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
 def format_split(mantissa_bits: float, n_bits: int, sign_bits: int):
     """(M, E, K) of fp8_quantizer.py:105-106; K = number of exponent codes."""
     M, E, K = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -116,11 +120,23 @@ def bn_fold(mean, var, gamma, beta, eps: float):
     return scale, shift
 
 
+def bn_pack(mean, var, gamma, beta, eps: float):
+    """Packed parameters [mean | gamma | rsqrt(var + eps) | beta] for the bit-exact batch-norm mode (bn_mode 1)."""
+    _require(mean, "running_mean")
+    _require(var, "running_var")
+    C = mean.numel()
+    packed = torch.empty(4 * C, dtype=torch.float32, device=mean.device)
+    check(lib().fp8fq_bn_pack_f32(mean.data_ptr(), var.data_ptr(), _opt_ptr(gamma), _opt_ptr(beta), float(eps), C,
+                                  packed.data_ptr(), _stream()), "fp8fq_bn_pack_f32")
+    return packed
+
+
 def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int,
                  bn_mode: int = 0, out=None):
-    """quantized_folded_bn.py:39-55 in one pass: Q(act(bn(x))), x is [N, C, *spatial] contiguous."""
+    """quantized_folded_bn.py:39-55 in one pass: Q(act(bn(x))), x is [N, C, *spatial] contiguous.
+    bn_mode 0: (bn_scale, bn_shift) from bn_fold; bn_mode 1: bn_scale = bn_pack(...) (bit-exact ATen arithmetic)."""
     _require(x, "x")
-    Cbn = bn_scale.numel()
+    Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     if x.dim() < 2 or x.shape[1] != Cbn:
         raise Fp8fqError("bn_act_quant: x must be [N, C, ...] with C == len(bn_scale)")
     hw = 1
@@ -129,7 +145,7 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
     rows = x.shape[0] * Cbn
     if out is None:
         out = torch.empty_like(x)
-    check(lib().fp8fq_bn_act_quant_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), rows,
+    check(lib().fp8fq_bn_act_quant_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift), rows,
                                        hw, Cbn, int(act), int(bn_mode), table.data_ptr(), float(mantissa_bits),
                                        int(n_bits), int(sign_bits), _stream()), "fp8fq_bn_act_quant_f32")
     return out
@@ -144,12 +160,8 @@ def _rows_hw(x, Cbn):
     return x.shape[0] * Cbn, hw
 
 
-def _opt_ptr(t):
-    return t.data_ptr() if t is not None else None
-
-
 def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inner, fmt_inner, table_outer, fmt_outer,
-                           out=None):
+                           bn_mode: int = 0, out=None):
     """Whole residual-block tail (models/resnet_quantized.py:39-46) in one pass:
     Q_outer(act(Q_inner(bn(x)) + residual)).  fmt_* = (mantissa_bits, n_bits, sign_bits).
     Returns None when the fused variant does not cover the shape (caller composes the two kernels)."""
@@ -157,12 +169,13 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     _require(residual, "residual")
     if x.shape != residual.shape:
         raise Fp8fqError("bn_quant_add_act_quant: shape mismatch")
-    rows, hw = _rows_hw(x, bn_scale.numel())
+    Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
+    rows, hw = _rows_hw(x, Cbn)
     if out is None:
         out = torch.empty_like(x)
     code = lib().fp8fq_bn_quant_add_act_quant_f32(
-        x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), rows, hw,
-        bn_scale.numel(), int(act), 0, table_inner.data_ptr(), float(fmt_inner[0]), int(fmt_inner[1]),
+        x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift), rows, hw,
+        Cbn, int(act), int(bn_mode), table_inner.data_ptr(), float(fmt_inner[0]), int(fmt_inner[1]),
         int(fmt_inner[2]), table_outer.data_ptr(), float(fmt_outer[0]), int(fmt_outer[1]), int(fmt_outer[2]), _stream())
     if code == -2:
         return None

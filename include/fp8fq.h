@@ -106,7 +106,10 @@ int fp8fq_fake_quant_codes_f32(const float* x, float* y, int32_t* codes, const f
  * F.batch_norm -> activation -> per-tensor activation quantiser, one pass, 8 B/element.
  * x, y: [rows, hw] with channel(row) = row % Cbn (NCHW contiguous: rows = N*Cbn, hw = H*W).
  * bn_scale/bn_shift: [Cbn] from fp8fq_bn_fold_f32.  `table` is a per-tensor (C == 1) table.
- * bn_mode must be 0: y = fma(x, scale, shift) (reserved for other batch-norm arithmetics). */
+ * bn_mode 0 ("affine"): bn_scale/bn_shift from fp8fq_bn_fold_f32, y = fma(x, scale, shift).
+ * bn_mode 1 ("exact") : bn_scale = the packed [4 * Cbn] buffer from fp8fq_bn_pack_f32, bn_shift ignored;
+ *                       y = fma(gamma * (x - mean), rsqrtf(var + eps), beta), the arithmetic of ATen's eval-mode batch
+ *                       norm on CUDA -- bit-identical to F.batch_norm on the same GPU (measured, profiles/). */
 int fp8fq_bn_act_quant_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift,
                            int64_t rows, int64_t hw, int64_t Cbn, int act, int bn_mode, const float* table,
                            float mantissa_bits, int n_bits, int sign_bits, void* stream);
@@ -122,6 +125,11 @@ int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, floa
                                      int n_bits_inner, int sign_bits_inner, const float* table_outer,
                                      float mantissa_bits_outer, int n_bits_outer, int sign_bits_outer,
                                      void* stream);
+
+/* Packed batch-norm parameters for bn_mode 1: [Cbn][4] = {mean, gamma (1 if NULL), rsqrtf(var + eps), beta (0 if NULL)}
+ * per channel; `packed` must be 16-byte aligned. */
+int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                      int64_t Cbn, float* packed, void* stream);
 
 /* Per-channel affine form of eval-mode batch norm: scale = gamma * rsqrt(var + eps) (as 1/sqrt),
  * shift = beta - mean * scale.  All [Cbn]. */

@@ -63,6 +63,7 @@ def test_config3_mobilenetv2_m4_vs_reference_golden():
     assert n_layerwise == 53 + 52 + 10 + 2
     assert n_fused == 2 + 42 + 10 + 2  # 53 weight tensors = 2 multi-tensor launches (48 descriptors per launch)
     assert torch.equal(logits, logits_layerwise)  # fusing launches changes no bit
+    assert torch.equal(logits, logits_unfused)    # nor does fusing batch norm / ReLU6 / add into the quantiser
     names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]
     assert names == list(g["names"])
     mods = dict(model.named_modules())

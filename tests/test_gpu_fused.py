@@ -79,6 +79,45 @@ def test_bn_act_quant_all_layout_classes(shape):
     assert torch.equal(s1, 1.0 / torch.sqrt(var + 1e-5)) and torch.equal(h1, 0.0 - mean * s1)
 
 
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56), (16, 512, 7, 7), (3, 96, 1, 1), (2, 32, 5, 3), (5, 1000), (2, 3, 224, 224),
+                                   (7, 5, 3, 3), (9, 24, 9, 5)])
+def test_exact_bn_mode_is_bit_identical_to_torch_batch_norm(shape):
+    """bn_mode 1: Q(act(F.batch_norm(x))) computed by ATen + our quantiser == the single fused launch, for EVERY
+    element, on every layout class; and the fused block tail == F.batch_norm -> Q -> add -> ReLU -> Q."""
+    from fp8_quantization_b200 import ops
+
+    torch.manual_seed(21)
+    C = shape[1]
+    x = torch.randn(shape, device=DEV) * 2
+    res = torch.relu(torch.randn(shape, device=DEV))
+    mean, var = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.3
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    packed = ops.bn_pack(mean, var, gamma, beta, 1e-5)
+    ref_bn = F.batch_norm(x, mean, var, gamma, beta, False, 0.0, 1e-5)
+    for M, act in ((5, 1), (4, 2), (3, 0)):
+        q = _quantizer(M, 3.0)
+        table, _ = q.table_for(x)
+        y = ops.bn_act_quant(x, packed, None, act, table, float(M), 8, 1, bn_mode=1)
+        t = torch.relu(ref_bn) if act == 1 else (F.relu6(ref_bn) if act == 2 else ref_bn)
+        assert torch.equal(bits(y), bits(q(t)))
+        # and == the reference composition evaluated entirely by ATen on the same device (oracle with CUDA tensors)
+        yo = O.fake_quant(t, 8, q.maxval, torch.tensor([float(M)], device=DEV), 1)
+        assert torch.equal(bits(y), bits(yo))
+    qi, qo = _quantizer(5, 2.7), _quantizer(5, 4.1)
+    ti, _ = qi.table_for(x)
+    to, _ = qo.table_for(x)
+    y = ops.bn_quant_add_act_quant(x, res, packed, None, 1, ti, (5, 8, 1), to, (5, 8, 1), bn_mode=1)
+    if y is not None:
+        out = qi(ref_bn)
+        out += res                       # models/resnet_quantized.py:43-46, literally
+        out = torch.relu(out)
+        assert torch.equal(bits(y), bits(qo(out)))
+    # affine-free batch norm (gamma = beta = None)
+    p2 = ops.bn_pack(mean, var, None, None, 1e-5)
+    y2 = ops.bn_act_quant(x, p2, None, 0, table, 3.0, 8, 1, bn_mode=1)
+    assert torch.equal(bits(y2), bits(q(F.batch_norm(x, mean, var, None, None, False, 0.0, 1e-5))))
+
+
 @pytest.mark.parametrize("shape", [(8, 64, 56, 56), (16, 512, 7, 7), (4, 128, 28, 28), (3, 24, 9, 5), (2, 8, 3, 3)])
 def test_block_tail_equals_composition(shape):
     """Q_outer(relu(Q_inner(bn(x)) + residual)) in one pass == the two kernels it replaces."""
@@ -226,7 +265,9 @@ def test_bnqconv_fused_matches_reference_golden():
     step = float(g["conv_a_maxval"][0]) / 2 ** 5
     for y in (y_cal, y_fused, y_unfused):
         assert ((y.cpu() - yr).abs() > step).float().mean().item() < 2e-3
-    assert (bits(y_fused) != bits(y_unfused)).float().mean().item() < 1e-3
+    # exact batch-norm mode: the fused launch and the reference composition (F.batch_norm -> ReLU -> quantiser)
+    # give the same bits, so calibration (unfused), fused validation and unfused validation all agree exactly
+    assert torch.equal(bits(y_fused), bits(y_unfused)) and torch.equal(bits(y_fused), bits(y_cal))
 
 
 def test_resnet18_m5_ranges_and_logits_vs_reference_golden():
@@ -265,8 +306,12 @@ def test_resnet18_m5_ranges_and_logits_vs_reference_golden():
             modules.BATCH_WEIGHT_QUANT = True
             assert torch.equal(logits, logits_layerwise)  # restructuring launches changes no bit
             modules.FUSE_EPILOGUES = False
-            logits_unfused = model(x)
+            n0 = ops.launch_count()
+            logits_unfused = model(x)     # F.batch_norm / relu / add by ATen, one quantiser launch per call
+            assert ops.launch_count() - n0 == 1 + 30
             modules.FUSE_EPILOGUES = True
+            # exact batch-norm mode: 23 fused launches == the reference's op-by-op composition, bit for bit
+            assert torch.equal(logits, logits_unfused)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]

@@ -45,6 +45,7 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
     y = torch.empty(shape, device=dev)
     mean, var = torch.randn(C, device=dev), torch.rand(C, device=dev) + 0.5
     sc, sh = ops.bn_fold(mean, var, None, None, 1e-5)
+    pk = ops.bn_pack(mean, var, None, None, 1e-5)
     tb, _ = q.table_for(xs[0])
     tb4, _ = q4.table_for(xs[0])
     rec = {"shape": list(shape), "elems": n, "buffers": nbuf}
@@ -58,6 +59,9 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
         ("block_tail", 12, [lambda x=x, r=rs[i % len(rs)]: ops.bn_quant_add_act_quant(x, r, sc, sh, 1, tb, (5.0, 8, 1), tb,
                                                                                       (5.0, 8, 1), out=y)
                             for i, x in enumerate(xs)]),
+        ("bn_relu_quant_exact", 8, [lambda x=x: ops.bn_act_quant(x, pk, None, 1, tb, 5.0, 8, 1, bn_mode=1, out=y) for x in xs]),
+        ("block_tail_exact", 12, [lambda x=x, r=rs[i % len(rs)]: ops.bn_quant_add_act_quant(
+            x, r, pk, None, 1, tb, (5.0, 8, 1), tb, (5.0, 8, 1), bn_mode=1, out=y) for i, x in enumerate(xs)]),
         ("torch_copy", 8, [lambda x=x: y.copy_(x) for x in xs]),
     ):
         med, mn = timeit(fns)
