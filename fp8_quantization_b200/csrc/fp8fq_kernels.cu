@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -801,7 +802,21 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   const int64_t tile = (int64_t)kThreads * VEC * StreamUnroll<PRE>::value;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
-  const int64_t grid = ntiles < 0x7fffffffll ? ntiles : 0x7fffffffll;  // one tile per CTA (the kernel still strides)
+  // Tiles per CTA.  Measured (tools/bench_kernels.py, [128,64,112,112]): the plain and residual-add kernels are
+  // fastest with one tile per CTA (6.56 / 6.68 TB/s); the batch-norm variants, which are instruction-issue bound
+  // (ncu: 78 % issue slots busy), gain from amortising their longer per-CTA prologue over 4 tiles (5.64 -> 6.16 and
+  // 4.97 -> 5.84 TB/s) -- as long as that still leaves >= 2 full waves of CTAs.  FP8FQ_TILES_PER_CTA overrides.
+  constexpr bool kHasBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD ||
+                           PRE == PRE_BNQ_ADD_PL);
+  static const int tpc_env = [] {
+    const char* e = getenv("FP8FQ_TILES_PER_CTA");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 64 ? v : 0;
+  }();
+  int tpc = tpc_env ? tpc_env : ((kHasBn && KMODE == 0) ? 4 : 1);
+  while (tpc > 1 && !tpc_env && ntiles / tpc < (int64_t)sm_count() * 12) tpc >>= 1;
+  int64_t grid = (ntiles + tpc - 1) / tpc;
+  if (grid > 0x7fffffffll) grid = 0x7fffffffll;  // the kernel strides over the remaining tiles
   fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM><<<(unsigned)grid, kThreads, 0, st>>>(a);
   return launch_status();
 }
