@@ -18,6 +18,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <utility>
 
 #include "../../include/fp8fq.h"
 #include "fp8fq_core.h"
@@ -46,6 +47,41 @@ int sm_count() {
     g_dev[dev].ok = true;
   }
   return g_dev[dev].sms;
+}
+
+// Programmatic dependent launch (PDL): kernels of this library that follow each other on a stream (23 per ResNet-18
+// forward) overlap the next kernel's launch latency, CTA rasterisation and prologue with the previous kernel's
+// last wave.  Every participating kernel calls pdl_prologue() before its first global-memory access:
+//   griddepcontrol.launch_dependents  -- the next kernel in the stream may be scheduled once all CTAs of this grid
+//                                        have started (i.e. during this grid's last wave);
+//   griddepcontrol.wait               -- block until the previous grid has completed and its writes are visible.
+// Launched without the attribute (FP8FQ_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FP8FQ_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 inline int launch_status() {
@@ -357,7 +393,6 @@ template <int PRE>
 struct StreamUnroll {
   static constexpr int value = (PRE == PRE_ADD || PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL) ? 2 : 4;
 };
-constexpr int kTabSmem = kHdr + 2 + kMaxK + 1 + 2 * (kMaxK + 1);
 
 // Resident CTAs per SM the kernel is compiled for.  Measured (tools/bench_kernels.py, B200, [128,64,112,112]):
 // one-tile CTAs are short lived, so occupancy is what keeps HBM busy -- plain E2M5 5.9 -> 6.5 TB/s going from 4 to
@@ -383,6 +418,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
   const int64_t nvec_elems = a.n - (a.n % VEC);
   const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
+  pdl_prologue();
   // per-CTA parameters: uniform loads, no barrier; issued first, consumed only after the data loads went out
   ElemCtx<KMODE> ctx, ctx2;
   load_ctx_direct<KMODE>(ctx, a.table, a.K);
@@ -513,6 +549,7 @@ struct RowsArgs {
 // fill the GPU or to amortise a launch on their own).
 template <int KMODE, bool CODES>
 __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+  pdl_prologue();
   const int stride = table_stride(a.K);
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     int ti = 0;
@@ -817,7 +854,7 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   while (tpc > 1 && !tpc_env && ntiles / tpc < (int64_t)sm_count() * 12) tpc >>= 1;
   int64_t grid = (ntiles + tpc - 1) / tpc;
   if (grid > 0x7fffffffll) grid = 0x7fffffffll;  // the kernel strides over the remaining tiles
-  fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM><<<(unsigned)grid, kThreads, 0, st>>>(a);
+  launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM>, dim3((unsigned)grid), dim3(kThreads), 0, st, a);
   return launch_status();
 }
 
@@ -940,11 +977,11 @@ static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, i
   const int threads = max_inner >= 512 ? 128 : (max_inner >= 128 ? 64 : 32);
   const bool codes = codes0 != nullptr;
   if (K <= 3) {
-    if (codes) fq_rows_kernel<0, true><<<(unsigned)grid, threads, 0, st>>>(a);
-    else fq_rows_kernel<0, false><<<(unsigned)grid, threads, 0, st>>>(a);
+    if (codes) launch_kernel(fq_rows_kernel<0, true>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+    else launch_kernel(fq_rows_kernel<0, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
   } else {
-    if (codes) fq_rows_kernel<1, true><<<(unsigned)grid, threads, 0, st>>>(a);
-    else fq_rows_kernel<1, false><<<(unsigned)grid, threads, 0, st>>>(a);
+    if (codes) launch_kernel(fq_rows_kernel<1, true>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+    else launch_kernel(fq_rows_kernel<1, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
   }
   return launch_status();
 }
