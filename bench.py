@@ -471,7 +471,8 @@ def main():
         roof = {"kernel": "fq_stream_kernel (fused BN/add + act + FP8 fake-quant, per-tensor)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "traffic": traffic, "launches_per_step": st["stream_launches"],
+                "traffic": traffic, "traffic_of": "largest_launch (ncu --set full, profiles/ncu_summary_r01.json)",
+                "launches_per_step": st["stream_launches"],
                 "algorithmic_bytes_per_step": st["stream_bytes"],
                 "avg_launch_us": k_ms * 1e3 / st["stream_launches"], "share_of_step": k_ms / ms_per_step,
                 "largest_launch": {"algorithmic_bytes": nbytes[big], "us": big_ms * 1e3,
@@ -595,6 +596,10 @@ def main():
                               "reference on the same GPU) captured in one CUDA graph; weights re-quantised every "
                               "forward as the reference does; random-init weights, synthetic images"}
 
+    if world > 1:
+        fq_dist.barrier()
+        import torch.distributed as td
+        td.destroy_process_group()
     if rank != 0:
         return 0
 

@@ -248,28 +248,44 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
   int e[N];
   bool slow = false;
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
-    const float a = fabsf(xc[k]);
-    if (KMODE == 0) {
+  for (int k = 0; k < N; ++k) xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
+  if (KMODE == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float a = fabsf(xc[k]);
       const bool p2 = a >= c.rt.t2, p3 = a >= c.rt.t3;
       s[k] = p3 ? c.rt.s3 : (p2 ? c.rt.s2 : c.rt.s1);
       rs[k] = p3 ? c.rt.r3 : (p2 ? c.rt.r2 : c.rt.r1);
       e[k] = 1 + (p2 ? 1 : 0) + (p3 ? 1 : 0);
-    } else {
-      // exponent-arithmetic code, table lookup only in the (band + 1) / 2^23 ambiguous mantissa band.
-      // generic-address loads: c.stab is the global table (stream kernel, L1-resident) or a shared-memory copy
-      bool amb;
-      int ee = lookup_code_fast(a, c.ref, c.band, c.K, &amb);
-      if (amb) {
-        ee = lookup_code(a, c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
-        ee = ee < 1 ? 1 : ee;
+    }
+  } else {
+    // exponent-arithmetic code; the table lookup runs for the whole vector only when a lane's mantissa lies in the
+    // (band + 1) / 2^23 ambiguous band.  c.stab is the global table (stream/row kernels, L1-resident) or a
+    // shared-memory copy (MSE kernel), hence generic-address loads.
+    bool amb = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      bool ak;
+      e[k] = lookup_code_fast(fabsf(xc[k]), c.ref, c.band, c.K, &ak);
+      amb |= ak;
+    }
+    if (amb) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int ee = lookup_code(fabsf(xc[k]), c.stab, c.K, c.base, c.irregular, [](const float* p) { return *p; });
+        e[k] = ee < 1 ? 1 : ee;
       }
-      const float2 p = *reinterpret_cast<const float2*>(c.stab + off_sr(c.K) + 2 * ee);
+    }
+    const float2* sr = reinterpret_cast<const float2*>(c.stab + off_sr(c.K));
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float2 p = sr[e[k]];
       s[k] = p.x;
       rs[k] = p.y;
-      e[k] = ee;
     }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
     const float r = mul_rn(xc[k], rs[k]);
     q[k] = nearbyintf(r);
     slow |= !(fabsf(r - q[k]) < c.guard);
