@@ -26,6 +26,7 @@ from torch import nn
 from torch.nn.modules.conv import _ConvNd
 from torch.nn.modules.pooling import _AdaptiveAvgPoolNd, _AvgPoolNd
 
+from . import dist as fq_dist
 from . import ops
 from .quantization_manager import QuantizationManager
 from .quantizers import FPQuantizer, QuantizerBase
@@ -42,6 +43,35 @@ BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in on
 BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
                            # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
                            # from F.batch_norm before quantisation)
+
+
+def _sync_batch_norm_train(x, running_mean, running_var, gamma, beta, momentum, eps):
+    """Training-mode batch norm over the GLOBAL (all-rank) batch: per-channel sum and sum of squares are all-reduced
+    (one collective of 2C+1 floats), so that every rank normalises with -- and records -- the statistics a single
+    process would compute on the concatenated batch.  Used by BN re-estimation under data parallelism
+    (utils/qat_utils.py:45-90 + SURVEY.md section 8f1); running stats follow F.batch_norm's update rule
+    (unbiased variance, momentum)."""
+    C = x.shape[1]
+    dims = [0] + list(range(2, x.dim()))
+    n_local = x.numel() // C
+    stats = torch.cat([x.sum(dims, dtype=torch.float64), (x.double() * x.double()).sum(dims),
+                       torch.tensor([float(n_local)], dtype=torch.float64, device=x.device)])
+    fq_dist.all_reduce_sum(stats)
+    n = stats[-1]
+    mean = stats[:C] / n
+    var = (stats[C:2 * C] / n - mean * mean).clamp_min(0.0)
+    with torch.no_grad():
+        m = 1.0 if momentum is None else momentum
+        running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
+        running_var.mul_(1 - m).add_((var * (n / (n - 1))).float(), alpha=m)
+    view = [1, C] + [1] * (x.dim() - 2)
+    inv = torch.rsqrt(var.float() + eps)
+    y = (x - mean.float().view(view)) * inv.view(view)
+    if gamma is not None:
+        y = y * gamma.view(view)
+    if beta is not None:
+        y = y + beta.view(view)
+    return y
 
 
 def _act_code(act):
@@ -355,8 +385,12 @@ class BNFusedHijacker(QuantizationHijacker):
             scale, shift, mode = self.folded_bn()
             return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
                                     q.n_bits, q.sign_bits, bn_mode=mode)
-        res = F.batch_norm(res, self.running_mean, self.running_var, self.gamma, self.beta, self.training,
-                           self.momentum, self.epsilon)
+        if self.training and fq_dist.active():
+            res = _sync_batch_norm_train(res, self.running_mean, self.running_var, self.gamma, self.beta,
+                                         self.momentum, self.epsilon)
+        else:
+            res = F.batch_norm(res, self.running_mean, self.running_var, self.gamma, self.beta, self.training,
+                               self.momentum, self.epsilon)
         if self.activation_function is not None:
             res = self.activation_function(res)
         if not self.quantize_input and self._qa:

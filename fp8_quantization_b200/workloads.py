@@ -311,6 +311,65 @@ def pass_data_for_range_estimation(batches, model, act_quant=True, weight_quant=
 
 
 @torch.no_grad()
+def reestimate_BN_stats(model, batches, num_batches=50, store_ema_stats=False):
+    """utils/qat_utils.py:45-90: re-estimate the batch-norm statistics of the QUANTISED network.  Every
+    BNFusedHijacker runs with momentum 1 in training mode (its children do not), so after each forward its running
+    statistics are the current batch statistics; these are averaged over ``num_batches`` batches and written back.
+    Under data parallelism (fp8_quantization_b200.dist active) the batch statistics are those of the global batch
+    (per-channel sum / sum-of-squares all-reduce), so every rank ends with the statistics a single process would
+    compute on the concatenated batches."""
+    from .modules import BNFusedHijacker
+
+    model.eval()
+    layers = [(n, m) for n, m in model.named_modules() if isinstance(m, BNFusedHijacker)]
+    org_momentum = {}
+    for name, module in layers:
+        org_momentum[name] = module.momentum
+        module.momentum = 1.0
+        module.running_mean_sum = torch.zeros_like(module.running_mean)
+        module.running_var_sum = torch.zeros_like(module.running_var)
+        module.training = True  # this module only, not its children (quantisers keep their state)
+        if store_ema_stats:
+            import copy
+
+            if not hasattr(module, "running_mean_ema"):
+                module.register_buffer("running_mean_ema", copy.deepcopy(module.running_mean))
+                module.register_buffer("running_var_ema", copy.deepcopy(module.running_var))
+            else:
+                module.running_mean_ema = copy.deepcopy(module.running_mean)
+                module.running_var_ema = copy.deepcopy(module.running_var)
+    batch_count = 0
+    for x in batches:
+        model(x)
+        for _, module in layers:
+            module.running_mean_sum += module.running_mean
+            module.running_var_sum += module.running_var
+        batch_count += 1
+        if batch_count == num_batches:
+            break
+    for name, module in layers:
+        module.running_mean = module.running_mean_sum / batch_count
+        module.running_var = module.running_var_sum / batch_count
+        module.momentum = org_momentum[name]
+        del module.running_mean_sum, module.running_var_sum
+    model.eval()
+    return batch_count
+
+
+class ReestimateBNStats:
+    """utils/qat_utils.py:33-42 (callable handler)."""
+
+    def __init__(self, model, data_loader, num_batches=50):
+        self.model = model
+        self.data_loader = data_loader
+        self.num_batches = num_batches
+
+    def __call__(self, engine=None):
+        print("-- Reestimate current BN statistics --")
+        reestimate_BN_stats(self.model, self.data_loader, self.num_batches)
+
+
+@torch.no_grad()
 def validate(model, batches, labels=None):
     """image_net.py:72-96 without ignite: top-1 / top-5 / mean CE loss over ``batches``; under data
     parallelism the four counters are summed across ranks with one all-reduce."""

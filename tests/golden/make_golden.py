@@ -260,6 +260,58 @@ def gen_resnet18(R):
     print("resnet18_m5.npz", len(names), "quantizers")
 
 
+def gen_bn_reestimate(R):
+    """the reference's reestimate_BN_stats (utils/qat_utils.py:45-90) on a small quantised
+    conv-BN-ReLU-conv-BN stack with fixed ranges, 3 batches."""
+    import importlib
+
+    qat = importlib.import_module("utils.qat_utils") if False else None
+    # utils/qat_utils.py imports the ImageNet data loaders (torchvision ok); import the function directly
+    import utils.qat_utils as qat_utils
+
+    aq = R.autoquant_utils
+    RE = R.range_estimators
+    torch.manual_seed(10)
+    qp = dict(method=R.FPQuantizer, n_bits=8, per_channel_weights=True, weight_range_method=RE.CurrentMinMaxEstimator,
+              act_range_method=RE.AllMinMaxEstimator,
+              fp8_kwargs=dict(mantissa_bits=5, set_maxval=True, maxval=None, mse_include_mantissa_bits=False))
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 6, 1, bias=False), torch.nn.BatchNorm2d(6))
+    seq[1].running_mean.normal_()
+    seq[1].running_var.uniform_(0.5, 2.0)
+    seq[4].running_mean.normal_()
+    seq[4].running_var.uniform_(0.5, 2.0)
+    state = {k: v.clone() for k, v in seq.state_dict().items()}
+    model = aq.quantize_model(seq, **qp)
+    from quantization.base_quantized_model import QuantizedModel
+
+    class Wrap(QuantizedModel):
+        def __init__(self, f):
+            super().__init__((1, 3, 16, 16))
+            self.f = f
+
+        def forward(self, x):
+            return self.f(x)
+
+    wm = Wrap(model)
+    wm.eval()
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.randn(8, 3, 16, 16, generator=g) for _ in range(3)]
+    wm.set_quant_state(True, True)
+    with torch.no_grad():
+        wm(xs[0])
+    wm.fix_ranges()
+    qat_utils.reestimate_BN_stats(wm, [(x, None) for x in xs], num_batches=3)
+    out = {"x": torch.stack(xs).numpy()}
+    for k, v in state.items():
+        out["init_" + k.replace(".", "_")] = v.numpy()
+    for i in (0, 1):
+        out[f"mean_{i}"] = model[i].running_mean.numpy()
+        out[f"var_{i}"] = model[i].running_var.numpy()
+    np.savez_compressed(os.path.join(OUT, "bn_reestimate.npz"), **out)
+    print("bn_reestimate.npz")
+
+
 def gen_mobilenetv2(R):
     """BASELINE config 3: reference QuantizedMobileNetV2(MobileNetV2()) under seed 10, README parameters with M=4:
     calibrate on one batch, fix ranges, record every quantiser's range and the logits."""
@@ -308,6 +360,7 @@ if __name__ == "__main__":
     gen_mse(R)
     gen_modules(R)
     gen_resnet18(R)
+    gen_bn_reestimate(R)
     if "--mobilenet" in sys.argv:
         gen_mobilenetv2(R)
     for f in sorted(os.listdir(OUT)):

@@ -51,6 +51,36 @@ def _worker(rank, world, port, q):
     stats = torch.tensor([1.0 + rank, 2.0, 3.0, 4.0])
     fq_dist.all_reduce_sum(stats)
     ok &= stats.tolist() == [3.0, 4.0, 6.0, 8.0]
+    # BN re-estimation: ranks see half the batch each, statistics must equal the single-process ones on
+    # the concatenated batch (quantisers off here -- the CUDA quantisers are covered by -m gpu)
+    from fp8_quantization_b200 import modules, workloads
+    torch.manual_seed(1)
+    qp = workloads.readme_quant_params(5)
+    qp.pop("quant_setup")
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, bias=False), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 4, 1, bias=False), torch.nn.BatchNorm2d(4))
+
+    class Wrap(modules.QuantizedModel):
+        def __init__(self, f):
+            super().__init__((1, 3, 8, 8))
+            self.f = f
+
+        def forward(self, x):
+            return self.f(x)
+
+    import copy
+    dp_model = Wrap(modules.quantize_model(copy.deepcopy(seq), **qp))
+    sp_model = Wrap(modules.quantize_model(copy.deepcopy(seq), **qp))
+    dp_model.full_precision()
+    sp_model.full_precision()
+    gxs = [torch.randn(8, 3, 8, 8) for _ in range(3)]
+    workloads.reestimate_BN_stats(dp_model, [fq_dist.shard_batch(g) for g in gxs], 3)   # global-batch statistics
+    fq_dist.enable(False)
+    workloads.reestimate_BN_stats(sp_model, gxs, 3)                                      # single process, whole batch
+    fq_dist.enable(True)
+    for a, b in zip(dp_model.f, sp_model.f):
+        ok &= torch.allclose(a.running_mean, b.running_mean, rtol=1e-5, atol=1e-6)
+        ok &= torch.allclose(a.running_var, b.running_var, rtol=1e-4, atol=1e-6)
     with pytest.raises(ValueError):
         fq_dist.shard_batch(torch.zeros(3, 2))
     fq_dist.barrier()

@@ -114,6 +114,49 @@ def test_config4_mse_grid_sweep_vs_oracle(M):
             assert torch.isfinite(model(xb)).all()
 
 
+def test_next_row_f1_bn_reestimation_vs_reference_golden():
+    """reestimate_BN_stats of the quantised network (utils/qat_utils.py:45-90) vs the real reference run
+    on the CPU: same flow (momentum 1, BN-train mode on the fused layers only, mean over batches)."""
+    from fp8_quantization_b200 import modules, workloads
+
+    g = load_golden("bn_reestimate.npz")
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 6, 1, bias=False), torch.nn.BatchNorm2d(6))
+    sd = {k: torch.from_numpy(g["init_" + k.replace(".", "_")]) for k in seq.state_dict().keys()}
+    seq.load_state_dict(sd)
+    qp = workloads.readme_quant_params(5)
+    qp.pop("quant_setup")
+
+    class Wrap(modules.QuantizedModel):
+        def __init__(self, f):
+            super().__init__((1, 3, 16, 16))
+            self.f = f
+
+        def forward(self, x):
+            return self.f(x)
+
+    model = Wrap(modules.quantize_model(seq, **qp)).to(DEV).eval()
+    xs = [torch.from_numpy(x).to(DEV) for x in g["x"]]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        workloads.pass_data_for_range_estimation([xs[0]], model, True, True, 1)
+        model.fix_ranges()
+        n = workloads.reestimate_BN_stats(model, xs, num_batches=3)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert n == 3 and not model.f[0].training and model.f[0].momentum == 0.1
+    for i in (0, 1):
+        np.testing.assert_allclose(model.f[i].running_mean.cpu().numpy(), g[f"mean_{i}"], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(model.f[i].running_var.cpu().numpy(), g[f"var_{i}"], rtol=2e-3, atol=2e-5)
+    with torch.no_grad():   # the fused epilogue picks up the new statistics (cached fold is invalidated)
+        y_fused = model(xs[1])
+        modules.FUSE_EPILOGUES = False
+        y_unfused = model(xs[1])
+        modules.FUSE_EPILOGUES = True
+    assert torch.equal(y_fused, y_unfused)
+
+
 _DP_SCRIPT = r"""
 import os, sys, json, torch
 sys.path.insert(0, os.environ["FQ_ROOT"])
