@@ -7,7 +7,8 @@ arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in ``inclu
 """
 from ._lib import Fp8fqError, LIB_PATH, lib  # noqa: F401
 from . import ops  # noqa: F401
-from .quantizers import FPQuantizer, QuantizerBase, QuantizerNotInitializedError  # noqa: F401
+from .quantizers import (AsymmetricUniformQuantizer, FPQuantizer, QuantizerBase,  # noqa: F401
+                         QuantizerNotInitializedError, SymmetricUniformQuantizer)
 from .range_estimators import (AllMinMaxEstimator, CurrentMinMaxEstimator, FP_MSE_Estimator,  # noqa: F401
                                RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator)
 from .quantization_manager import QMethods, Qstates, QuantizationManager  # noqa: F401

@@ -295,6 +295,40 @@ FQ_HD int lookup_code_fast(float a, uint32_t ref, uint32_t band, int K, bool* am
   return e > K ? K : e;
 }
 
+// ---- INT uniform quantisers (quantization/quantizers/uniform_quantizers.py:107-164) ------------------------
+//   scale = clamp(delta, min=eps); zp = clamp(round(zero_float), int_min, int_max) | 0 (symmetric)
+//   x_int = clamp(round(x / scale) + zp, int_min, int_max);  y = scale * (x_int - zp)
+// Channel table (kUStride floats): scale, 1/scale, zp, int_min, int_max, tie guard, saturation bound.
+constexpr int kUStride = 8;
+enum : int { U_SCALE = 0, U_RS = 1, U_ZP = 2, U_IMIN = 3, U_IMAX = 4, U_GUARD = 5, U_SAT = 6 };
+
+FQ_HD void uq_build(float* tab, float delta, float zero_float, float int_min, float int_max, float eps, int n_bits,
+                    bool symmetric) {
+  const float scale = delta < eps ? eps : delta;  // torch.clamp(delta, min=eps): NaN stays NaN
+  float rs = rcp_rn(scale);
+  if (!(is_normal_pos(scale) && is_normal_pos(rs))) rs = u2f(0x7fc00000u);
+  float zp = 0.0f;
+  if (!symmetric) zp = min_nan(max_nan(nearbyintf(zero_float), int_min), int_max);
+  tab[U_SCALE] = scale;
+  tab[U_RS] = rs;
+  tab[U_ZP] = zp;
+  tab[U_IMIN] = int_min;
+  tab[U_IMAX] = int_max;
+  // |x/scale| < sat = 2^(n_bits+2): multiplying by RN(1/scale) perturbs the quotient by < 1.6 * 2^(n_bits-21), the
+  // guard leaves 2^(n_bits-19); beyond sat the clamp saturates whatever the rounding was
+  tab[U_GUARD] = 0.5f - ldexpf(1.0f, n_bits - 19);
+  tab[U_SAT] = ldexpf(1.0f, n_bits + 2);
+  tab[7] = 0.0f;
+}
+
+FQ_HD float uq_quant(float x, float scale, float rs, float zp, float imin, float imax, float guard, float sat) {
+  const float r = mul_rn(x, rs);
+  float q = nearbyintf(r);
+  if (!(fabsf(r - q) < guard) && !(fabsf(r) >= sat)) q = nearbyintf(div_rn(x, scale));
+  const float xi = min_nan(max_nan(add_rn(q, zp), imin), imax);
+  return mul_rn(scale, sub_rn(xi, zp));
+}
+
 // Quantise xc (already clamped) with the selected (s, rs).  Returns y; *q_out = round(xc / s).
 FQ_HD float quant_core(float xc, float s, float rs, float guard, float* q_out) {
   float r = mul_rn(xc, rs);

@@ -244,6 +244,30 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
 template <int KMODE, bool CODES, int N>
 __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N]) {
+  if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
+    float q[N];
+    bool slow = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float r = mul_rn(v[k], c.rt.r1);
+      q[k] = nearbyintf(r);
+      slow |= !(fabsf(r - q[k]) < c.guard) && !(fabsf(r) >= c.rt.t3);
+    }
+    if (slow) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float r = mul_rn(v[k], c.rt.r1);
+        if (!(fabsf(r - q[k]) < c.guard) && !(fabsf(r) >= c.rt.t3)) q[k] = nearbyintf(div_rn(v[k], c.rt.s1));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float xi = min_nan(max_nan(add_rn(q[k], c.rt.t2), c.lo), c.hi);
+      y[k] = mul_rn(c.rt.s1, sub_rn(xi, c.rt.t2));
+      if (CODES) code[k] = (y[k] != y[k]) ? 0x7fffffff : (int32_t)xi;
+    }
+    return;
+  }
   float xc[N], s[N], rs[N], q[N];
   int e[N];
   bool slow = false;
@@ -346,6 +370,18 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, i
 // with uniform loads -- no shared memory, no barrier, so a CTA is a fully independent streaming unit.
 template <int KMODE>
 __device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
+  if (KMODE == 2) {  // uniform table
+    c.hi = __ldg(gtab + U_IMAX);
+    c.lo = __ldg(gtab + U_IMIN);
+    c.guard = __ldg(gtab + U_GUARD);
+    c.rt.s1 = __ldg(gtab + U_SCALE);
+    c.rt.r1 = __ldg(gtab + U_RS);
+    c.rt.t2 = __ldg(gtab + U_ZP);
+    c.rt.t3 = __ldg(gtab + U_SAT);
+    c.rt.s2 = c.rt.s3 = c.rt.r2 = c.rt.r3 = 0.0f;
+    c.K = 1; c.stab = gtab; c.base = 0; c.irregular = false; c.ref = 0; c.band = 0;
+    return;
+  }
   c.hi = __ldg(gtab + H_HI);
   c.lo = __ldg(gtab + H_LO);
   c.guard = __ldg(gtab + H_GUARD);
@@ -419,7 +455,7 @@ struct StreamMinBlocks {
   static constexpr int value = FQ_MINB;
 #else
   static constexpr int value =
-      ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE == 0) ? 6 : 5;
+      ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE != 1) ? 6 : 5;
 #endif
 };
 
@@ -558,6 +594,7 @@ struct RowsArgs {
   int64_t nwork;
   int64_t chunk;            // elements per work item (multiple of 4)
   int K;
+  int stride;               // floats per channel table
 };
 
 // One CTA per (tensor, row, chunk) work item; the row's table is staged in shared memory.  Several weight
@@ -566,7 +603,7 @@ struct RowsArgs {
 template <int KMODE, bool CODES>
 __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
   pdl_prologue();
-  const int stride = table_stride(a.K);
+  const int stride = a.stride;
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     int ti = 0;
     while (ti + 1 < a.count && w >= a.t[ti + 1].work0) ++ti;
@@ -781,6 +818,43 @@ __global__ void bn_pack_kernel(const float* mean, const float* var, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// INT uniform quantisers: set_quant_range (uniform_quantizers.py:224-246, 303-314) + channel tables, one CTA
+// ------------------------------------------------------------------------------------------------
+__global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* __restrict__ xmax, int64_t C,
+                                  int n_bits, int symmetric, float eps, float* __restrict__ delta_out,
+                                  float* __restrict__ zero_float_out, float* __restrict__ signed_out,
+                                  float* __restrict__ table) {
+  __shared__ float s_min;
+  // x_min = min(x_min, 0) over all channels decides `signed` (uniform_quantizers.py:306): x_min.min() < 0
+  float mn = __int_as_float(0x7f800000), dummy = __int_as_float(0xff800000);
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) mn = min_nan(mn, min_nan(xmin[c], 0.0f));
+  block_minmax(mn, dummy);
+  if (threadIdx.x == 0) s_min = mn;
+  __syncthreads();
+  const bool is_signed = s_min < 0.0f;  // NaN -> false, like `tensor(nan) < 0`
+  float int_min = 0.0f, int_max = ldexpf(1.0f, n_bits) - 1.0f;
+  if (symmetric) {
+    int_min = is_signed ? -ldexpf(1.0f, n_bits - 1) : 0.0f;
+    int_max = ldexpf(1.0f, n_bits - (is_signed ? 1 : 0)) - 1.0f;
+  }
+  if (threadIdx.x == 0 && signed_out != nullptr) signed_out[0] = is_signed ? 1.0f : 0.0f;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
+    const float xm = min_nan(xmin[c], 0.0f);   // torch.min(x_min, zeros)
+    const float xM = max_nan(xmax[c], eps);    // torch.max(x_max, ones * eps)
+    float delta, zf = 0.0f;
+    if (symmetric) {
+      delta = div_rn(max_nan(fabsf(xm), xM), int_max);
+    } else {
+      delta = div_rn(sub_rn(xM, xm), int_max);
+      zf = div_rn(-xm, delta);
+    }
+    if (delta_out != nullptr) delta_out[c] = delta;
+    if (zero_float_out != nullptr) zero_float_out[c] = zf;
+    uq_build(table + c * kUStride, delta, zf, int_min, int_max, eps, n_bits, symmetric != 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: MSE grid.  grid = (chunks, C).  Each CTA keeps its slice of one channel row in registers and
 // sweeps the G candidate tables of the current mantissa width.
 // ------------------------------------------------------------------------------------------------
@@ -971,10 +1045,12 @@ int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C,
   return prepare_impl(nullptr, xmin, xmax, maxval_out, C, mantissa_bits, n_bits, sign_bits, table, stream);
 }
 
-static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, int K, cudaStream_t st) {
+static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, int K, cudaStream_t st,
+                       bool uniform = false) {
   RowsArgs a{};
   a.count = count;
   a.K = K;
+  a.stride = uniform ? kUStride : table_stride(K);
   a.chunk = 4096;
   int64_t work = 0, max_inner = 0;
   for (int i = 0; i < count; ++i) {
@@ -992,7 +1068,9 @@ static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, i
   if (grid > work) grid = work;
   const int threads = max_inner >= 512 ? 128 : (max_inner >= 128 ? 64 : 32);
   const bool codes = codes0 != nullptr;
-  if (K <= 3) {
+  if (uniform) {
+    launch_kernel(fq_rows_kernel<2, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+  } else if (K <= 3) {
     if (codes) launch_kernel(fq_rows_kernel<0, true>, dim3((unsigned)grid), dim3(threads), 0, st, a);
     else launch_kernel(fq_rows_kernel<0, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
   } else {
@@ -1056,6 +1134,35 @@ int fp8fq_fake_quant_multi_f32(const fp8fq_tensor_desc* descs_host, int count, f
   }
   if (g > 0) return launch_rows(group, nullptr, g, K, (cudaStream_t)stream);
   return FP8FQ_OK;
+}
+
+int64_t fp8fq_uniform_table_floats(int64_t C) { return C < 1 ? FP8FQ_ERR_BAD_ARG : C * kUStride; }
+
+int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric, float eps,
+                              float* delta_out, float* zero_float_out, float* signed_out, float* table,
+                              void* stream) {
+  if (xmin == nullptr || xmax == nullptr || table == nullptr || C < 1) return FP8FQ_ERR_BAD_ARG;
+  if (n_bits < 1 || n_bits > 16) return FP8FQ_ERR_UNSUPPORTED;
+  uq_prepare_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(xmin, xmax, C, n_bits, symmetric ? 1 : 0, eps, delta_out,
+                                                         zero_float_out, signed_out, table);
+  return launch_status();
+}
+
+int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
+                            void* stream) {
+  if (n < 0 || C < 1 || inner < 0 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr || table == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(x) || !aligned4(y)) return FP8FQ_ERR_ALIGNMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 1) {
+    StreamArgs a{};
+    a.x = x; a.y = y; a.table = table; a.n = n; a.K = 1;
+    const bool vec = aligned16(x) && aligned16(y);
+    return vec ? launch_stream_t<2, PRE_PLAIN, 4, false, 0>(a, st) : launch_stream_t<2, PRE_PLAIN, 1, false, 0>(a, st);
+  }
+  fp8fq_tensor_desc d{x, y, table, C, inner};
+  return launch_rows(&d, nullptr, 1, 1, st, true);
 }
 
 int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,

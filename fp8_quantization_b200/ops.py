@@ -222,6 +222,33 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     return out
 
 
+def uniform_prepare(xmin, xmax, n_bits: int, symmetric: bool, eps: float):
+    """set_quant_range of the INT uniform quantisers (uniform_quantizers.py:224-246, 303-314) on the device.
+    Returns (delta [C], zero_float [C], signed [1] as 0./1., table)."""
+    _require(xmin, "x_min")
+    _require(xmax, "x_max")
+    C = xmax.numel()
+    delta = torch.empty(C, dtype=torch.float32, device=xmax.device)
+    zero_float = torch.empty(C, dtype=torch.float32, device=xmax.device)
+    signed = torch.empty(1, dtype=torch.float32, device=xmax.device)
+    table = torch.empty(int(lib().fp8fq_uniform_table_floats(C)), dtype=torch.float32, device=xmax.device)
+    check(lib().fp8fq_uniform_prepare_f32(xmin.data_ptr(), xmax.data_ptr(), C, int(n_bits), 1 if symmetric else 0,
+                                          float(eps), delta.data_ptr(), zero_float.data_ptr(), signed.data_ptr(),
+                                          table.data_ptr(), _stream()), "fp8fq_uniform_prepare_f32")
+    return delta, zero_float, signed, table
+
+
+def uniform_quant(x, table, C: int, out=None):
+    """Asymmetric/SymmetricUniformQuantizer.forward (uniform_quantizers.py:107-164), one launch."""
+    _require(x, "x")
+    n = x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().fp8fq_uniform_quant_f32(x.data_ptr(), out.data_ptr(), table.data_ptr(), n, C, n // C if C else 0,
+                                        _stream()), "fp8fq_uniform_quant_f32")
+    return out
+
+
 _workspaces = {}
 
 

@@ -10,12 +10,15 @@ from enum import auto
 
 from torch import nn
 
-from .quantizers import FPQuantizer, QuantizerBase, QuantizerNotInitializedError
+from .quantizers import (AsymmetricUniformQuantizer, FPQuantizer, QuantizerBase, QuantizerNotInitializedError,
+                         SymmetricUniformQuantizer)
 from .range_estimators import (BaseEnumOptions, ClassEnumOptions, MethodMap, RangeEstimatorBase, RangeEstimators,
                                _MinMaxEstimator)
 
 
-class QMethods(ClassEnumOptions):  # quantization_manager.py:22-25 (INT quantisers are out of scope)
+class QMethods(ClassEnumOptions):  # quantization_manager.py:22-25
+    symmetric_uniform = MethodMap(SymmetricUniformQuantizer)
+    asymmetric_uniform = MethodMap(AsymmetricUniformQuantizer)
     fp_quantizer = MethodMap(FPQuantizer)
 
 

@@ -238,3 +238,143 @@ class FPQuantizer(QuantizerBase):
             setattr(new, k, copy.deepcopy(v, memo))
         new._table_key = None
         return new
+
+
+class AsymmetricUniformQuantizer(QuantizerBase):
+    """INT asymmetric uniform fake quantiser -- quantization/quantizers/uniform_quantizers.py:13-256, the reference's
+    default ``method`` and comparison baseline.  Forward path, ``scale_domain="linear"``,
+    round-to-nearest-even discretizer; ``delta`` / ``zero_float`` live on the device as in the reference."""
+
+    _SYMMETRIC = False
+
+    def __init__(self, n_bits, scale_domain="linear", discretizer=None, discretizer_args=tuple(), grad_scaling=False,
+                 eps=1e-8, **kwargs):
+        kwargs.pop("mantissa_bits", None)  # fp8_kwargs are forwarded to every quantiser by QuantizedModule
+        for k in ("maxval", "set_maxval", "learn_maxval", "learn_mantissa_bits", "mse_include_mantissa_bits",
+                  "allow_unsigned"):
+            kwargs.pop(k, None)
+        super().__init__(n_bits=n_bits, **kwargs)
+        if scale_domain != "linear":
+            raise NotImplementedError("only scale_domain='linear' is implemented")
+        if grad_scaling:
+            raise NotImplementedError("forward-only engine: grad_scaling needs the STE backward")
+        self.register_buffer("_delta", None)
+        self.register_buffer("_zero_float", None)
+        self.register_buffer("_signed", None)
+        self.scale_domain = scale_domain
+        self.grad_scaling = grad_scaling
+        self.eps = eps
+        self._table = None
+
+    @property
+    def delta(self):
+        if self._delta is None:
+            raise QuantizerNotInitializedError()
+        return self._delta
+
+    @property
+    def zero_float(self):
+        if self._zero_float is None:
+            raise QuantizerNotInitializedError()
+        return self._zero_float
+
+    @property
+    def is_initialized(self):
+        return self._delta is not None
+
+    @property
+    def symmetric(self):
+        return self._SYMMETRIC
+
+    @property
+    def int_min(self):
+        return 0.0
+
+    @property
+    def int_max(self):
+        return 2.0**self.n_bits - 1
+
+    @property
+    def scale(self):
+        return torch.clamp(self.delta, min=self.eps)
+
+    @property
+    def zero_point(self):
+        return torch.clamp(torch.round(self.zero_float), self.int_min, self.int_max)
+
+    @property
+    def x_max(self):
+        return self.scale * (self.int_max - self.zero_point)
+
+    @property
+    def x_min(self):
+        return self.scale * (self.int_min - self.zero_point)
+
+    def _as_device_ranges(self, x_min, x_max):
+        if not torch.is_tensor(x_max):
+            dev = torch.device("cuda", torch.cuda.current_device())
+            x_min = torch.tensor([float(x_min)], dtype=torch.float32, device=dev)
+            x_max = torch.tensor([float(x_max)], dtype=torch.float32, device=dev)
+        if x_min.dim() > 0 and x_min.numel() > 1 and not self.per_channel:
+            raise ValueError("x_min and x_max must be a float or 1-D Tensor for per-tensor quantization "
+                             "(per_channel=False)")
+        if not x_max.is_cuda:
+            raise Fp8fqError("set_quant_range: range tensors must live on the GPU (no CPU path)")
+        return (x_min.detach().to(torch.float32).reshape(-1).contiguous(),
+                x_max.detach().to(torch.float32).reshape(-1).contiguous())
+
+    def set_quant_range(self, x_min, x_max):
+        self.x_min_fp32, self.x_max_fp32 = x_min, x_max
+        mn, mx = self._as_device_ranges(x_min, x_max)
+        delta, zero_float, signed, table = ops.uniform_prepare(mn, mx, self.n_bits, self._SYMMETRIC, self.eps)
+        self._delta = delta if delta.numel() > 1 else delta.reshape(())
+        if not self._SYMMETRIC:
+            self._zero_float = zero_float if zero_float.numel() > 1 else zero_float.reshape(())
+        self._signed = signed
+        self._table = table
+
+    def forward(self, x_float, *args, **kwargs):
+        if self._table is None:
+            raise QuantizerNotInitializedError()
+        if torch.is_grad_enabled() and x_float.requires_grad:
+            raise Fp8fqError("uniform quantiser: forward-only engine; call under torch.no_grad()")
+        x = x_float if x_float.is_contiguous() else x_float.contiguous()
+        C = self._table.numel() // 8
+        if C != 1 and (x.dim() == 0 or x.shape[0] != C):
+            raise Fp8fqError(f"per-channel range has {C} entries but x has shape {tuple(x.shape)}")
+        return ops.uniform_quant(x, self._table, C)
+
+    def make_range_trainable(self):
+        raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+
+    def fix_ranges(self):
+        pass
+
+    def reset(self):
+        self._delta = None
+        self._zero_float = None
+        self._table = None
+
+
+class SymmetricUniformQuantizer(AsymmetricUniformQuantizer):
+    """uniform_quantizers.py:259-331."""
+
+    _SYMMETRIC = True
+
+    @property
+    def signed(self):
+        if self._signed is None:
+            raise QuantizerNotInitializedError()
+        return bool(self._signed.item())
+
+    @property
+    def int_min(self):
+        return -(2.0 ** (self.n_bits - 1)) if self.signed else 0
+
+    @property
+    def int_max(self):
+        return 2.0 ** (self.n_bits - int(self.signed)) - 1
+
+    @property
+    def zero_point(self):
+        return 0.0

@@ -143,6 +143,20 @@ int fp8fq_add_act_quant_f32(const float* a, const float* b, float* y, int64_t n,
                             const float* table, float mantissa_bits, int n_bits, int sign_bits,
                             void* stream);
 
+/* INT uniform quantisers -- the reference's comparison baseline.
+ * fp8fq_uniform_prepare_f32 replaces Asymmetric/SymmetricUniformQuantizer.set_quant_range
+ * (quantization/quantizers/uniform_quantizers.py:224-246, 303-314): from (x_min [C], x_max [C]) it writes delta [C],
+ * zero_float [C] (asymmetric), the `signed` flag (symmetric; 1.0 / 0.0) and the channel tables
+ * (fp8fq_uniform_table_floats(C) floats).  fp8fq_uniform_quant_f32 replaces .forward (uniform_quantizers.py:107-164):
+ * y = scale * (clamp(round(x / scale) + zero_point, int_min, int_max) - zero_point), scale = clamp(delta, min=eps).
+ * Only scale_domain="linear" with the round-to-nearest-even discretizer. */
+int64_t fp8fq_uniform_table_floats(int64_t C);
+int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric, float eps,
+                              float* delta_out, float* zero_float_out, float* signed_out, float* table,
+                              void* stream);
+int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
+                            void* stream);
+
 /* Replaces: the min/max of every range estimator (range_estimators.py:73-74, 85-91, 110-116) and
  * its update rule, NaN-propagating like torch.min/max.  One pass over x (4 B/element).
  *   per-tensor (C == 1): two-stage reduce finished by the last CTA; `workspace` must hold

@@ -161,6 +161,109 @@ class OracleFPQuantizer(torch.nn.Module):
 
 
 # --------------------------------------------------------------------------------------
+# INT uniform quantisers (quantization/quantizers/uniform_quantizers.py) -- SURVEY section 8f3, the reference's
+# comparison baseline.  Forward path only, scale_domain="linear", round-to-nearest-even STE discretizer.
+# --------------------------------------------------------------------------------------
+
+
+class OracleAsymmetricUniform(torch.nn.Module):
+    """AsymmetricUniformQuantizer, uniform_quantizers.py:13-256."""
+
+    symmetric = False
+
+    def __init__(self, n_bits, per_channel=False, eps=1e-8):
+        super().__init__()
+        self.n_bits = n_bits
+        self.per_channel = per_channel
+        self.eps = eps
+        self._delta = None
+        self._zero_float = None
+        self.state = None
+
+    @property
+    def is_initialized(self):  # :68-70
+        return self._delta is not None
+
+    @property
+    def int_min(self):  # :76-79
+        return 0.0
+
+    @property
+    def int_max(self):  # :81-84
+        return 2.0**self.n_bits - 1
+
+    @property
+    def scale(self):  # :86-91
+        return torch.clamp(self._delta, min=self.eps)
+
+    @property
+    def zero_point(self):  # :93-97
+        return torch.clamp(torch.round(self._zero_float), self.int_min, self.int_max)
+
+    def _tensorize_min_max(self, x_min, x_max):  # :193-222
+        if not torch.is_tensor(x_min):
+            x_min = torch.tensor(x_min).float()
+            x_max = torch.tensor(x_max).float()
+        x_min = torch.min(x_min, torch.zeros_like(x_min))
+        x_max = torch.max(x_max, torch.ones_like(x_max) * self.eps)
+        return x_min, x_max
+
+    def set_quant_range(self, x_min, x_max):  # :224-246
+        x_min, x_max = self._tensorize_min_max(x_min, x_max)
+        self._delta = (x_max - x_min) / self.int_max
+        self._zero_float = -x_min / self._delta
+
+    def _params_for(self, x):  # :176-191
+        d, z = self._delta, self._zero_float
+        if self.per_channel and x.ndim != d.ndim:
+            shape = [-1] + [1] * (x.dim() - 1)
+            d = d.view(shape)
+            z = z.view(shape) if z is not None else None
+        return d, z
+
+    def forward(self, x):  # :107-164
+        d, z = self._params_for(x)
+        scale = torch.clamp(d, min=self.eps)
+        zero_point = torch.clamp(torch.round(z), self.int_min, self.int_max)
+        x_int = torch.round(x / scale) + zero_point
+        x_int = torch.clamp(x_int, self.int_min, self.int_max)
+        return scale * (x_int - zero_point)
+
+    def reset(self):
+        self._delta = None
+
+
+class OracleSymmetricUniform(OracleAsymmetricUniform):
+    """SymmetricUniformQuantizer, uniform_quantizers.py:259-331."""
+
+    symmetric = True
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._signed = None
+
+    @property
+    def int_min(self):  # :290-292
+        return -(2.0 ** (self.n_bits - 1)) if bool(self._signed) else 0
+
+    @property
+    def int_max(self):  # :294-297
+        return 2.0 ** (self.n_bits - int(bool(self._signed))) - 1
+
+    def set_quant_range(self, x_min, x_max):  # :303-314
+        x_min, x_max = self._tensorize_min_max(x_min, x_max)
+        self._signed = x_min.min() < 0
+        self._delta = torch.max(x_min.abs(), x_max) / self.int_max
+
+    def forward(self, x):
+        d, _ = self._params_for(x)
+        scale = torch.clamp(d, min=self.eps)
+        x_int = torch.round(x / scale) + 0.0
+        x_int = torch.clamp(x_int, self.int_min, self.int_max)
+        return scale * (x_int - 0.0)
+
+
+# --------------------------------------------------------------------------------------
 # Range estimators (quantization/range_estimators.py)
 # --------------------------------------------------------------------------------------
 

@@ -260,6 +260,47 @@ def gen_resnet18(R):
     print("resnet18_m5.npz", len(names), "quantizers")
 
 
+def gen_uniform(R):
+    """Asymmetric / SymmetricUniformQuantizer (uniform_quantizers.py) on seeded tensors; the
+    arithmetic is IEEE-exact (div, round, clamp, mul), so these vectors must be reproduced bit for bit everywhere."""
+    import quantization.quantizers.uniform_quantizers as uq
+
+    out = {}
+    g = torch.Generator().manual_seed(13)
+    idx = 0
+    for cls, ocls, tag in ((uq.AsymmetricUniformQuantizer, O.OracleAsymmetricUniform, "asym"),
+                           (uq.SymmetricUniformQuantizer, O.OracleSymmetricUniform, "sym")):
+        for n_bits in (8, 4, 2):
+            for pc in (False, True):
+                for kind in ("signed", "unsigned"):
+                    shape = (16, 96) if pc else (1536,)
+                    x = torch.randn(shape, generator=g) * 3
+                    if kind == "unsigned":
+                        x = x.abs()
+                    if pc:
+                        x = x * torch.linspace(0.1, 5.0, shape[0]).view(-1, 1)
+                    x.view(-1)[:6] = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1e-30])
+                    q = cls(n_bits=n_bits, per_channel=pc)
+                    oq = ocls(n_bits, per_channel=pc)
+                    mn, mx = O.minmax(torch.nan_to_num(x, nan=0.0, posinf=9.0, neginf=-9.0 if kind == "signed" else 0.0), pc)
+                    q.set_quant_range(mn * 0.8, mx * 0.8)
+                    oq.set_quant_range(mn * 0.8, mx * 0.8)
+                    y = q(x)
+                    yo = oq(x)
+                    assert same_bits(y, yo), (tag, n_bits, pc, kind)
+                    name = f"u{idx:02d}"
+                    out[name + "_x"] = x.numpy()
+                    out[name + "_y"] = y.numpy()
+                    out[name + "_min"] = (mn * 0.8).reshape(-1).numpy()
+                    out[name + "_max"] = (mx * 0.8).reshape(-1).numpy()
+                    out[name + "_delta"] = q.delta.reshape(-1).numpy()
+                    out[name + "_meta"] = np.array([tag == "sym", n_bits, pc], dtype=np.int32)
+                    idx += 1
+    out["num_cases"] = np.array(idx)
+    np.savez_compressed(os.path.join(OUT, "uniform_quantizers.npz"), **out)
+    print("uniform_quantizers.npz:", idx, "cases")
+
+
 def gen_bn_reestimate(R):
     """the reference's reestimate_BN_stats (utils/qat_utils.py:45-90) on a small quantised
     conv-BN-ReLU-conv-BN stack with fixed ranges, 3 batches."""
@@ -360,6 +401,7 @@ if __name__ == "__main__":
     gen_mse(R)
     gen_modules(R)
     gen_resnet18(R)
+    gen_uniform(R)
     gen_bn_reestimate(R)
     if "--mobilenet" in sys.argv:
         gen_mobilenetv2(R)

@@ -70,6 +70,37 @@ int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table
   return 0;
 }
 
+// serial equivalents of uq_prepare_kernel / quant_vec<2, ...> (INT uniform quantisers)
+int emul_uq_prepare(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric, float eps, float* delta,
+                    float* table) {
+  float mn = INFINITY;
+  for (int64_t c = 0; c < C; ++c) mn = min_nan(mn, min_nan(xmin[c], 0.0f));
+  const bool is_signed = mn < 0.0f;
+  float int_min = 0.0f, int_max = ldexpf(1.0f, n_bits) - 1.0f;
+  if (symmetric) {
+    int_min = is_signed ? -ldexpf(1.0f, n_bits - 1) : 0.0f;
+    int_max = ldexpf(1.0f, n_bits - (is_signed ? 1 : 0)) - 1.0f;
+  }
+  for (int64_t c = 0; c < C; ++c) {
+    const float xm = min_nan(xmin[c], 0.0f), xM = max_nan(xmax[c], eps);
+    float d, zf = 0.0f;
+    if (symmetric) d = div_rn(max_nan(fabsf(xm), xM), int_max);
+    else { d = div_rn(sub_rn(xM, xm), int_max); zf = div_rn(-xm, d); }
+    if (delta) delta[c] = d;
+    uq_build(table + c * kUStride, d, zf, int_min, int_max, eps, n_bits, symmetric != 0);
+  }
+  return 0;
+}
+
+int emul_uq_quant(const float* x, float* y, const float* table, int64_t C, int64_t inner) {
+  for (int64_t c = 0; c < C; ++c) {
+    const float* t = table + c * kUStride;
+    for (int64_t i = 0; i < inner; ++i)
+      y[c * inner + i] = uq_quant(x[c * inner + i], t[U_SCALE], t[U_RS], t[U_ZP], t[U_IMIN], t[U_IMAX], t[U_GUARD], t[U_SAT]);
+  }
+  return 0;
+}
+
 int emul_table_flags(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
   int M, E, K;
   if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;

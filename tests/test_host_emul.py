@@ -109,3 +109,26 @@ def test_c_restatement_vs_torch_oracle(oracle_c, host_emul):
         assert bad.float().mean() < 1e-4
         rel = ((torch.from_numpy(y0) - y).abs() / y.abs().clamp_min(1e-30))[~bad]
         assert rel.max() < 2.5e-7
+
+
+def test_uniform_quantizer_algorithm_equals_reference_golden(host_emul):
+    """the INT uniform quantiser path of csrc/fp8fq_core.h (set_quant_range + reciprocal-multiply with tie
+    guard + saturation shortcut) reproduces the REAL reference's outputs bit for bit -- its arithmetic is IEEE-exact
+    (div, round, clamp, mul), so there is no libm caveat here."""
+    from conftest import load_golden
+
+    g = load_golden("uniform_quantizers.npz")
+    for i in range(int(g["num_cases"])):
+        n = f"u{i:02d}"
+        sym, nb, pc = [int(v) for v in g[n + "_meta"]]
+        x = g[n + "_x"]
+        x2 = np.ascontiguousarray(x.reshape(x.shape[0], -1) if pc else x.reshape(1, -1))
+        C, inner = x2.shape
+        mn, mx = np.ascontiguousarray(g[n + "_min"]), np.ascontiguousarray(g[n + "_max"])
+        tab, d = np.zeros(C * 8, np.float32), np.zeros(C, np.float32)
+        assert host_emul.emul_uq_prepare(P(mn), P(mx), ctypes.c_int64(C), nb, sym, ctypes.c_float(1e-8), P(d), P(tab)) == 0
+        y = np.empty_like(x2)
+        host_emul.emul_uq_quant(P(x2), P(y), P(tab), ctypes.c_int64(C), ctypes.c_int64(inner))
+        yr = g[n + "_y"].reshape(C, inner)
+        assert np.array_equal(d, g[n + "_delta"]), n
+        assert ((y.view(np.int32) == yr.view(np.int32)) | (np.isnan(y) & np.isnan(yr))).all(), n

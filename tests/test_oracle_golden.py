@@ -88,6 +88,21 @@ def test_mse_estimator_matches_reference_golden():
             assert np.allclose(est.mses.numpy(), g[key + "_mses"], rtol=1e-4)
 
 
+def test_uniform_quantizers_match_reference_golden():
+    g = load_golden("uniform_quantizers.npz")
+    for i in range(int(g["num_cases"])):
+        n = f"u{i:02d}"
+        sym, nb, pc = [int(v) for v in g[n + "_meta"]]
+        q = (O.OracleSymmetricUniform if sym else O.OracleAsymmetricUniform)(nb, per_channel=bool(pc))
+        mn, mx = torch.from_numpy(g[n + "_min"]), torch.from_numpy(g[n + "_max"])
+        if not pc:
+            mn, mx = mn.reshape(()), mx.reshape(())
+        q.set_quant_range(mn, mx)
+        y = q(torch.from_numpy(g[n + "_x"]))
+        yr = torch.from_numpy(g[n + "_y"])
+        assert bool(((bits(y) == bits(yr)) | (torch.isnan(y) & torch.isnan(yr))).all()), n  # IEEE-exact everywhere
+
+
 @pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
 def test_oracle_equals_live_reference():
     """In the build container the oracle is also compared with the live reference on fresh inputs."""
