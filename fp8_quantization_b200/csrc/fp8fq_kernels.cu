@@ -821,7 +821,7 @@ __global__ void bn_pack_kernel(const float* mean, const float* var, const float*
 // INT uniform quantisers: set_quant_range (uniform_quantizers.py:224-246, 303-314) + channel tables, one CTA
 // ------------------------------------------------------------------------------------------------
 __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* __restrict__ xmax, int64_t C,
-                                  int n_bits, int symmetric, float eps, float* __restrict__ delta_out,
+                                  int n_bits, int symmetric, int recip_div, float eps, float* __restrict__ delta_out,
                                   float* __restrict__ zero_float_out, float* __restrict__ signed_out,
                                   float* __restrict__ table) {
   __shared__ float s_min;
@@ -841,13 +841,11 @@ __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* _
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
     const float xm = min_nan(xmin[c], 0.0f);   // torch.min(x_min, zeros)
     const float xM = max_nan(xmax[c], eps);    // torch.max(x_max, ones * eps)
-    float delta, zf = 0.0f;
-    if (symmetric) {
-      delta = div_rn(max_nan(fabsf(xm), xM), int_max);
-    } else {
-      delta = div_rn(sub_rn(xM, xm), int_max);
-      zf = div_rn(-xm, delta);
-    }
+    // `tensor / python_scalar` (uniform_quantizers.py:239, 309): ATen divides on the CPU but multiplies by the
+    // fp32 reciprocal of the scalar on CUDA -- recip_div selects which of the reference's two behaviours to match
+    const float num = symmetric ? max_nan(fabsf(xm), xM) : sub_rn(xM, xm);
+    const float delta = recip_div ? mul_rn(num, div_rn(1.0f, int_max)) : div_rn(num, int_max);
+    const float zf = symmetric ? 0.0f : div_rn(-xm, delta);
     if (delta_out != nullptr) delta_out[c] = delta;
     if (zero_float_out != nullptr) zero_float_out[c] = zf;
     uq_build(table + c * kUStride, delta, zf, int_min, int_max, eps, n_bits, symmetric != 0);
@@ -1138,13 +1136,14 @@ int fp8fq_fake_quant_multi_f32(const fp8fq_tensor_desc* descs_host, int count, f
 
 int64_t fp8fq_uniform_table_floats(int64_t C) { return C < 1 ? FP8FQ_ERR_BAD_ARG : C * kUStride; }
 
-int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric, float eps,
-                              float* delta_out, float* zero_float_out, float* signed_out, float* table,
-                              void* stream) {
+int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric,
+                              int aten_cuda_scalar_div, float eps, float* delta_out, float* zero_float_out,
+                              float* signed_out, float* table, void* stream) {
   if (xmin == nullptr || xmax == nullptr || table == nullptr || C < 1) return FP8FQ_ERR_BAD_ARG;
   if (n_bits < 1 || n_bits > 16) return FP8FQ_ERR_UNSUPPORTED;
-  uq_prepare_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(xmin, xmax, C, n_bits, symmetric ? 1 : 0, eps, delta_out,
-                                                         zero_float_out, signed_out, table);
+  uq_prepare_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(xmin, xmax, C, n_bits, symmetric ? 1 : 0,
+                                                         aten_cuda_scalar_div ? 1 : 0, eps, delta_out, zero_float_out,
+                                                         signed_out, table);
   return launch_status();
 }
 

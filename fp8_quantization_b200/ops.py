@@ -222,7 +222,7 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     return out
 
 
-def uniform_prepare(xmin, xmax, n_bits: int, symmetric: bool, eps: float):
+def uniform_prepare(xmin, xmax, n_bits: int, symmetric: bool, eps: float, aten_cuda_scalar_div: bool = True):
     """set_quant_range of the INT uniform quantisers (uniform_quantizers.py:224-246, 303-314) on the device.
     Returns (delta [C], zero_float [C], signed [1] as 0./1., table)."""
     _require(xmin, "x_min")
@@ -233,7 +233,7 @@ def uniform_prepare(xmin, xmax, n_bits: int, symmetric: bool, eps: float):
     signed = torch.empty(1, dtype=torch.float32, device=xmax.device)
     table = torch.empty(int(lib().fp8fq_uniform_table_floats(C)), dtype=torch.float32, device=xmax.device)
     check(lib().fp8fq_uniform_prepare_f32(xmin.data_ptr(), xmax.data_ptr(), C, int(n_bits), 1 if symmetric else 0,
-                                          float(eps), delta.data_ptr(), zero_float.data_ptr(), signed.data_ptr(),
+                                          1 if aten_cuda_scalar_div else 0, float(eps), delta.data_ptr(), zero_float.data_ptr(), signed.data_ptr(),
                                           table.data_ptr(), _stream()), "fp8fq_uniform_prepare_f32")
     return delta, zero_float, signed, table
 

@@ -246,6 +246,9 @@ class AsymmetricUniformQuantizer(QuantizerBase):
     round-to-nearest-even discretizer; ``delta`` / ``zero_float`` live on the device as in the reference."""
 
     _SYMMETRIC = False
+    # ``delta = range / int_max`` divides by a Python scalar: ATen does a true division on the CPU and multiplies by the
+    # fp32 reciprocal on CUDA.  True (default) reproduces the reference as run on the GPU; False the CPU run.
+    aten_cuda_scalar_div = True
 
     def __init__(self, n_bits, scale_domain="linear", discretizer=None, discretizer_args=tuple(), grad_scaling=False,
                  eps=1e-8, **kwargs):
@@ -326,7 +329,8 @@ class AsymmetricUniformQuantizer(QuantizerBase):
     def set_quant_range(self, x_min, x_max):
         self.x_min_fp32, self.x_max_fp32 = x_min, x_max
         mn, mx = self._as_device_ranges(x_min, x_max)
-        delta, zero_float, signed, table = ops.uniform_prepare(mn, mx, self.n_bits, self._SYMMETRIC, self.eps)
+        delta, zero_float, signed, table = ops.uniform_prepare(mn, mx, self.n_bits, self._SYMMETRIC, self.eps,
+                                                               self.aten_cuda_scalar_div)
         self._delta = delta if delta.numel() > 1 else delta.reshape(())
         if not self._SYMMETRIC:
             self._zero_float = zero_float if zero_float.numel() > 1 else zero_float.reshape(())

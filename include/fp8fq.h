@@ -149,11 +149,14 @@ int fp8fq_add_act_quant_f32(const float* a, const float* b, float* y, int64_t n,
  * zero_float [C] (asymmetric), the `signed` flag (symmetric; 1.0 / 0.0) and the channel tables
  * (fp8fq_uniform_table_floats(C) floats).  fp8fq_uniform_quant_f32 replaces .forward (uniform_quantizers.py:107-164):
  * y = scale * (clamp(round(x / scale) + zero_point, int_min, int_max) - zero_point), scale = clamp(delta, min=eps).
- * Only scale_domain="linear" with the round-to-nearest-even discretizer. */
+ * Only scale_domain="linear" with the round-to-nearest-even discretizer.
+ * aten_cuda_scalar_div: the reference computes delta = range / int_max with a Python scalar divisor; ATen performs a
+ * true division on the CPU and a multiplication by the fp32 reciprocal on CUDA (1 ulp apart for some ranges).
+ * 0 reproduces the reference run on the CPU bit for bit, 1 the reference run on the GPU. */
 int64_t fp8fq_uniform_table_floats(int64_t C);
-int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric, float eps,
-                              float* delta_out, float* zero_float_out, float* signed_out, float* table,
-                              void* stream);
+int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, int n_bits, int symmetric,
+                              int aten_cuda_scalar_div, float eps, float* delta_out, float* zero_float_out,
+                              float* signed_out, float* table, void* stream);
 int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
                             void* stream);
 

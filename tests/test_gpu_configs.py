@@ -160,7 +160,8 @@ def test_next_row_f1_bn_reestimation_vs_reference_golden():
 def test_next_row_f3_uniform_quantizers_bit_exact_vs_reference_golden():
     """Asymmetric / SymmetricUniformQuantizer classes on the GPU vs the real reference (CPU): delta,
     zero-point and every output bit identical (IEEE-exact arithmetic), incl. +-0, +-inf, NaN, 2/4/8 bits,
-    per-tensor and per-channel; and through the QuantizationManager with a min/max estimator."""
+    per-tensor and per-channel; and through the QuantizationManager with a min/max estimator, bit-identical to the
+    reference's op sequence on the same GPU (default mode: ATen-CUDA's reciprocal-multiply for `range / int_max`)."""
     import fp8_quantization_b200 as fq
 
     g = load_golden("uniform_quantizers.npz")
@@ -169,6 +170,7 @@ def test_next_row_f3_uniform_quantizers_bit_exact_vs_reference_golden():
         sym, nb, pc = [int(v) for v in g[n + "_meta"]]
         cls = fq.SymmetricUniformQuantizer if sym else fq.AsymmetricUniformQuantizer
         q = cls(n_bits=nb, per_channel=bool(pc))
+        q.aten_cuda_scalar_div = False  # the golden vectors come from the reference run on the CPU (true division)
         assert not q.is_initialized
         q.set_quant_range(torch.from_numpy(g[n + "_min"]).to(DEV), torch.from_numpy(g[n + "_max"]).to(DEV))
         assert q.is_initialized and q.symmetric == bool(sym)
