@@ -10,7 +10,8 @@ from . import ops  # noqa: F401
 from .quantizers import (AsymmetricUniformQuantizer, FPQuantizer, QuantizerBase,  # noqa: F401
                          QuantizerNotInitializedError, SymmetricUniformQuantizer)
 from .range_estimators import (AllMinMaxEstimator, CurrentMinMaxEstimator, FP_MSE_Estimator,  # noqa: F401
-                               RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator)
+                               LineSearchEstimator, RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator,
+                               estimate_range_line_search)
 from .quantization_manager import QMethods, Qstates, QuantizationManager  # noqa: F401
 
 __version__ = "0.1.0"

@@ -236,6 +236,101 @@ class FP_MSE_Estimator(RangeEstimatorBase):
         return sign_bits * -1.0 * maxval, maxval
 
 
+class LineSearchEstimator(RangeEstimatorBase):
+    """range_estimators.py:133-282 -- the 1-D grid search (the only branch that exists for a quantiser whose
+    ``symmetric`` is truthy, as FPQuantizer's is): ``num_candidates`` clipping thresholds ``step * i``, loss = sum of
+    squared quantisation error (per row when per_channel), accumulated over calls, argmin.  SURVEY section 8f2: the
+    reference deep-copies the quantiser and launches 13 kernels + a D2H copy per candidate (1000 x per call in
+    compute_quant_error.py); here all candidates are swept by ONE launch of the MSE-grid kernel that reads the data
+    once."""
+
+    def __init__(self, num_candidates=1000, opt_method=OptMethod.grid, range_margin=0.5, expand_range=10.0, *args,
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        assert opt_method in OptMethod
+        if opt_method != OptMethod.grid:
+            raise NotImplementedError("only the grid search exists in the reference (golden-section methods are "
+                                      "referenced but not defined there)")
+        self.opt_method = opt_method
+        self.num_candidates = num_candidates
+        self.expand_range = expand_range
+        self.range_margin = range_margin
+        self.loss_array = None
+        self.max_pos_thr = self.max_neg_thr = self.max_search_range = None
+        self.one_sided_dist = None
+        if self.quantizer is None:
+            raise NotImplementedError("A Quantizer must be given as an argument to the MSE Range" "Estimator")
+        self.max_int_skew = (2**self.quantizer.n_bits) // 4
+
+    @property
+    def step_size(self):
+        if self.one_sided_dist is None:
+            raise NoDataPassedError()
+        return self.max_search_range / self.num_candidates
+
+    def _define_search_range(self, data, dmin, dmax):  # :203-234, 1-D branch
+        import numpy as np
+
+        self.channel_groups = len(data) if self.per_channel else 1
+        self.loss_array = np.zeros((self.channel_groups, self.num_candidates + 1))
+        self.loss_array[:, 0] = np.inf
+        self.max_pos_thr = max(abs(dmin), dmax) + self.range_margin
+        self.max_neg_thr = -self.max_pos_thr * self.expand_range
+        self.max_search_range = self.max_pos_thr * self.expand_range
+
+    def forward(self, data):
+        import numpy as np
+
+        from .quantizers import FPQuantizer
+
+        qz = self.quantizer
+        if not isinstance(qz, FPQuantizer):
+            raise NotImplementedError("the fused line search is implemented for FPQuantizer")
+        data = data.detach()
+        data = data if data.is_contiguous() else data.contiguous()
+        if self.loss_array is None:
+            mm = torch.empty(2, dtype=torch.float32, device=data.device)
+            ops.minmax(data, False, mm[:1], mm[1:], ops.EST_CURRENT, False)
+            dmin, dmax = mm.tolist()  # the reference reads float(data.min()) / float(data.max()) here too
+            if self.one_sided_dist is None:
+                self.one_sided_dist = bool(dmin >= 0)
+            self._define_search_range(data, dmin, dmax)
+        step = self.step_size
+        C = self.channel_groups
+        if qz.set_maxval:
+            thr = torch.tensor([step * i for i in range(1, self.num_candidates + 1)], dtype=torch.float32)
+        else:  # set_quant_range ignores the candidates (fp8_quantizer.py:227): every candidate is the current range
+            thr = qz.maxval.detach().reshape(-1)[:1].cpu().expand(self.num_candidates).clone()
+        grid = thr.to(data.device).view(-1, 1).expand(-1, C).contiguous()
+        # the reference evaluates a deep copy whose set_quant_range(0, thr) may switch it to unsigned (:199-206)
+        sign_bits = 0 if (qz.allow_unsigned and self.one_sided_dist) else qz.sign_bits
+        mses = torch.zeros(1, self.num_candidates, C, dtype=torch.float32, device=data.device)
+        ops.mse_grid(data, self.per_channel, grid, [qz._mbits_host], qz.n_bits, sign_bits, mses)
+        inner = data.numel() // C
+        loss = (mses[0].double() * inner).t().cpu().numpy()  # [C, G] sums of squared error
+        self.loss_array[:, 1:] += loss
+        min_cand = self.loss_array.argmin(axis=1)
+        xmin = (np.zeros(C) if self.one_sided_dist else -step * min_cand).astype(np.single)
+        xmax = (step * min_cand).astype(np.single)
+        self.current_xmax = torch.tensor(xmax).to(device=data.device)
+        self.current_xmin = torch.tensor(xmin).to(device=data.device)
+        return self.current_xmin, self.current_xmax
+
+    def reset(self):
+        super().reset()
+        self.loss_array = None
+
+    def extra_repr(self):
+        return "opt_method={} ,num_candidates={}".format(self.opt_method.name, self.num_candidates)
+
+
+def estimate_range_line_search(W, quant, num_candidates=None):
+    """range_estimators.py:372-379."""
+    est = LineSearchEstimator(quantizer=quant) if num_candidates is None else \
+        LineSearchEstimator(quantizer=quant, num_candidates=num_candidates)
+    return est.forward(W)
+
+
 class RangeEstimators(ClassEnumOptions):  # range_estimators.py:389-393
     current_minmax = MethodMap(CurrentMinMaxEstimator)
     allminmax = MethodMap(AllMinMaxEstimator)

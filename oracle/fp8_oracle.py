@@ -380,6 +380,50 @@ class OracleFPMSE(OracleEstimatorBase):
         return sign_bits * -1.0 * maxval, maxval
 
 
+class OracleLineSearch(OracleEstimatorBase):
+    """LineSearchEstimator, 1-D grid search (range_estimators.py:133-282; the only branch that exists for a
+    quantiser whose ``symmetric`` is truthy, as FPQuantizer's bound method is) -- SURVEY section 8f2."""
+
+    def __init__(self, num_candidates=1000, range_margin=0.5, expand_range=10.0, **kw):
+        super().__init__(**kw)
+        self.num_candidates = num_candidates
+        self.range_margin = range_margin
+        self.expand_range = expand_range
+        self.loss_array = None
+        self.one_sided_dist = None
+
+    def forward(self, data):  # :258-273
+        import copy
+
+        import numpy as np
+
+        if self.loss_array is None:
+            if self.one_sided_dist is None:
+                self.one_sided_dist = bool((data.min() >= 0).item())
+            self.channel_groups = len(data) if self.per_channel else 1  # :204-214
+            self.loss_array = np.zeros((self.channel_groups, self.num_candidates + 1))
+            self.loss_array[:, 0] = np.inf
+            self.max_pos_thr = max(abs(float(data.min())), float(data.max())) + self.range_margin
+            self.max_search_range = self.max_pos_thr * self.expand_range
+        step = self.max_search_range / self.num_candidates  # :169-174
+        for i in range(1, self.num_candidates + 1):  # :236-256
+            neg_thr = 0 if self.one_sided_dist else -step * i
+            pos_thr = step * i
+            q = copy.deepcopy(self.quantizer)  # :199-206
+            q.per_channel = False
+            if neg_thr or pos_thr:
+                q.set_quant_range(neg_thr, pos_thr)
+            y = q(data)
+            per_row = torch.sum(((data - y) ** 2).view(len(data), -1), dim=1)  # :154-162
+            self.loss_array[:, i] += per_row.cpu().numpy() if self.per_channel else float(torch.sum(per_row))
+        min_cand = self.loss_array.argmin(axis=1)
+        xmin = (np.zeros(self.channel_groups) if self.one_sided_dist else -step * min_cand).astype(np.single)
+        xmax = (step * min_cand).astype(np.single)
+        self.current_xmax = torch.tensor(xmax).to(device=data.device)
+        self.current_xmin = torch.tensor(xmin).to(device=data.device)
+        return self.current_xmin, self.current_xmax
+
+
 # --------------------------------------------------------------------------------------
 # QuantizationManager.forward (quantization/quantization_manager.py:114-122)
 # --------------------------------------------------------------------------------------

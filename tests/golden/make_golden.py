@@ -301,6 +301,33 @@ def gen_uniform(R):
     print("uniform_quantizers.npz:", idx, "cases")
 
 
+def gen_line_search(R):
+    """LineSearchEstimator's 1-D grid search (range_estimators.py:236-256) with an FP quantiser,
+    as compute_quant_error.py uses it (there with 1000 candidates on 5 M samples)."""
+    RE = R.range_estimators
+    out = {}
+    g = torch.Generator().manual_seed(14)
+    for key, shape, pc, ncand, M in (("pt", (4096,), False, 200, 4), ("pc", (6, 512), True, 120, 3),
+                                     ("pt_onesided", (2048,), False, 150, 5)):
+        x = torch.randn(shape, generator=g)
+        if key == "pt_onesided":
+            x = x.abs()
+        q = R.FPQuantizer(8, mantissa_bits=M, set_maxval=True)
+        est = RE.LineSearchEstimator(quantizer=q, per_channel=pc, num_candidates=ncand)
+        oq = O.OracleFPQuantizer(8, mantissa_bits=M, set_maxval=True)
+        oest = O.OracleLineSearch(quantizer=oq, per_channel=pc, num_candidates=ncand)
+        mn, mx = est(x)
+        omn, omx = oest(x)
+        assert np.array_equal(est.loss_array, oest.loss_array) and torch.equal(mx, omx) and torch.equal(mn, omn)
+        out[key + "_x"] = x.numpy()
+        out[key + "_loss"] = est.loss_array
+        out[key + "_xmin"] = mn.numpy()
+        out[key + "_xmax"] = mx.numpy()
+        out[key + "_meta"] = np.array([ncand, M, int(pc)])
+    np.savez_compressed(os.path.join(OUT, "line_search.npz"), **out)
+    print("line_search.npz")
+
+
 def gen_bn_reestimate(R):
     """the reference's reestimate_BN_stats (utils/qat_utils.py:45-90) on a small quantised
     conv-BN-ReLU-conv-BN stack with fixed ranges, 3 batches."""
@@ -402,6 +429,7 @@ if __name__ == "__main__":
     gen_modules(R)
     gen_resnet18(R)
     gen_uniform(R)
+    gen_line_search(R)
     gen_bn_reestimate(R)
     if "--mobilenet" in sys.argv:
         gen_mobilenetv2(R)

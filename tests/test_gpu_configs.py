@@ -157,6 +157,34 @@ def test_next_row_f1_bn_reestimation_vs_reference_golden():
     assert torch.equal(y_fused, y_unfused)
 
 
+def test_next_row_f2_line_search_estimator_vs_reference_golden():
+    """LineSearchEstimator's 1-D grid search vs the real reference (range_estimators.py:236-256): loss
+    array within fp32 summation noise, same argmin (or a tie within that noise), same returned range."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("line_search.npz")
+    for key in ("pt", "pc", "pt_onesided"):
+        ncand, M, pc = [int(v) for v in g[key + "_meta"]]
+        x = torch.from_numpy(g[key + "_x"]).to(DEV)
+        q = fq.FPQuantizer(8, mantissa_bits=M, set_maxval=True)
+        est = fq.LineSearchEstimator(quantizer=q, per_channel=bool(pc), num_candidates=ncand)
+        mn, mx = est(x)
+        ref_loss = g[key + "_loss"]
+        np.testing.assert_allclose(est.loss_array[:, 1:], ref_loss[:, 1:], rtol=3e-4)
+        assert np.isinf(est.loss_array[:, 0]).all()
+        for c in range(ref_loss.shape[0]):
+            ours_i = int(round(float(mx[c]) / est.step_size))
+            assert ref_loss[c, ours_i] <= ref_loss[c].min() * (1 + 3e-4)
+        agree = (mx.cpu().numpy() == g[key + "_xmax"]).mean()
+        assert agree >= 0.8 and np.array_equal(mn.cpu().numpy() == 0, g[key + "_xmin"] == 0)
+        # accumulation over a second call, and the helper
+        est(x)
+        np.testing.assert_allclose(est.loss_array[:, 1:], 2 * ref_loss[:, 1:], rtol=3e-4)
+    mn, mx = fq.estimate_range_line_search(torch.from_numpy(g["pt_x"]).to(DEV),
+                                           fq.FPQuantizer(8, mantissa_bits=4, set_maxval=True), num_candidates=200)
+    assert float(mx) == float(g["pt_xmax"][0])
+
+
 def test_next_row_f3_uniform_quantizers_bit_exact_vs_reference_golden():
     """Asymmetric / SymmetricUniformQuantizer classes on the GPU vs the real reference (CPU): delta,
     zero-point and every output bit identical (IEEE-exact arithmetic), incl. +-0, +-inf, NaN, 2/4/8 bits,

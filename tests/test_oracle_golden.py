@@ -88,6 +88,20 @@ def test_mse_estimator_matches_reference_golden():
             assert np.allclose(est.mses.numpy(), g[key + "_mses"], rtol=1e-4)
 
 
+def test_line_search_matches_reference_golden():
+    g = load_golden("line_search.npz")
+    for key in ("pt", "pc", "pt_onesided"):
+        ncand, M, pc = [int(v) for v in g[key + "_meta"]]
+        q = O.OracleFPQuantizer(8, mantissa_bits=M, set_maxval=True)
+        est = O.OracleLineSearch(quantizer=q, per_channel=bool(pc), num_candidates=ncand)
+        mn, mx = est(torch.from_numpy(g[key + "_x"]))
+        if STRICT:
+            assert np.array_equal(est.loss_array, g[key + "_loss"])
+            assert np.array_equal(mx.numpy(), g[key + "_xmax"]) and np.array_equal(mn.numpy(), g[key + "_xmin"])
+        else:
+            assert np.allclose(est.loss_array[:, 1:], g[key + "_loss"][:, 1:], rtol=1e-4)
+
+
 def test_uniform_quantizers_match_reference_golden():
     g = load_golden("uniform_quantizers.npz")
     for i in range(int(g["num_cases"])):
