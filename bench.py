@@ -383,12 +383,12 @@ def main():
             fq_dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # samples every 100 ms from the warm-up until the end of the roofline passes
     for _ in range(args.warmup):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -398,6 +398,9 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    for _ in range(200):  # keep the GPU under the same load long enough for the 100 ms clock sampler (not timed)
+        run_step()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     launches = (ops.launch_count() - launches0) if graph is None else st["launches"] * args.steps
     if world > 1:
