@@ -32,6 +32,7 @@ SIGNATURES = {
     "fp8fq_bn_act_quant_f32": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_i, _c_i, _c_p, _c_f, _c_i, _c_i, _c_p]),
     "fp8fq_bn_fold_f32": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_f, _c_l, _c_p, _c_p, _c_p]),
     "fp8fq_bn_pack_f32": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_f, _c_l, _c_p, _c_p]),
+    "fp8fq_fake_quant_backward_f32": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_f, _c_i, _c_i, _c_p, _c_p]),
     "fp8fq_uniform_table_floats": (_c_l, [_c_l]),
     "fp8fq_uniform_prepare_f32": (_c_i, [_c_p, _c_p, _c_l, _c_i, _c_i, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "fp8fq_uniform_quant_f32": (_c_i, [_c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_p]),

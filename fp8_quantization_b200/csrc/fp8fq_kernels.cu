@@ -340,33 +340,7 @@ __device__ __forceinline__ float quant_elem(float v, const ElemCtx<KMODE>& c, in
   return yo[0];
 }
 
-template <int KMODE>
-__device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* gtab, int K, float* smem) {
-  const int stride = table_stride(K);
-  for (int i = threadIdx.x; i < stride; i += blockDim.x) smem[i] = gtab[i];
-  __syncthreads();
-  c.hi = smem[H_HI];
-  c.lo = smem[H_LO];
-  c.guard = smem[H_GUARD];
-  c.K = K;
-  c.base = f2u(smem[H_BASE]);
-  c.irregular = (f2u(smem[H_FLAGS]) & FLAG_IRREGULAR) != 0;
-  c.ref = f2u(smem[H_REF]);
-  c.band = f2u(smem[H_FLAGS]) >> BAND_SHIFT;
-  c.stab = smem;
-  if (KMODE == 0) {
-    const float never = __int_as_float(0x7fc00000);  // NaN: "a >= never" is false
-    const float* thr = smem + kHdr;
-    const float* sr = smem + off_sr(K);
-    c.rt.t2 = K >= 2 ? thr[1] : never;
-    c.rt.t3 = K >= 3 ? thr[2] : never;
-    c.rt.s1 = sr[2]; c.rt.r1 = sr[3];
-    c.rt.s2 = K >= 2 ? sr[4] : sr[2]; c.rt.r2 = K >= 2 ? sr[5] : sr[3];
-    c.rt.s3 = K >= 3 ? sr[6] : c.rt.s2; c.rt.r3 = K >= 3 ? sr[7] : c.rt.r2;
-  }
-}
-
-// Sync-free variant for the streaming kernel: every thread reads the (tiny, L1/L2-resident) channel table itself
+// Every thread reads the (tiny, L1/L2-resident) channel table itself
 // with uniform loads -- no shared memory, no barrier, so a CTA is a fully independent streaming unit.
 template <int KMODE>
 __device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
@@ -634,6 +608,80 @@ __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ Ro
         yr[i] = quant_elem<KMODE, CODES>(xr[i], ctx, &cd);
         if (CODES) cr[i] = cd;
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// STE backward of the fake-quantiser.  With round_ste and the detached exponent code
+// (fp8_quantizer.py:128-132), y = round(xc / s) * s gives   dy/dxc = 1,   dy/ds = q - xc/s,   and s depends on
+// maxval and M only through the bias: ds/dmaxval = s / maxval, ds/dM = s * ln2 * (-1 - dbias/dM).  The clamp
+// (:112-113, torch.max / torch.min) passes the gradient to x inside the range, to +-maxval outside, and splits it
+// evenly on exact ties.  The kernel writes grad_x and accumulates per channel
+//   acc[2c]   = sum g * (d xc / d maxval)            (clipping term)
+//   acc[2c+1] = sum g * (q - xc/s) * s               (scale term; grad_maxval += acc / maxval, grad_M = coef * sum)
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* g;
+  const float* x;
+  float* gx;
+  const float* table;
+  double* acc;
+  int64_t C, inner, chunks_per_row, chunk;
+  int K, stride, sign_bits;
+};
+
+template <int KMODE>
+__global__ void __launch_bounds__(128) fq_backward_kernel(const BwdArgs a) {
+  __shared__ float s_a1[4], s_a2[4];
+  const int64_t nwork = a.C * a.chunks_per_row;
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t row = w / a.chunks_per_row;
+    const int64_t ck = w - row * a.chunks_per_row;
+    const int64_t beg = ck * a.chunk;
+    const int64_t end = (beg + a.chunk < a.inner) ? beg + a.chunk : a.inner;
+    ElemCtx<KMODE> ctx;
+    load_ctx_direct<KMODE>(ctx, a.table + row * a.stride, a.K);
+    const float* xr = a.x + row * a.inner;
+    const float* gr = a.g + row * a.inner;
+    float* gxr = a.gx + row * a.inner;
+    float a1 = 0.0f, a2 = 0.0f;
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const float x = xr[i], g = gr[i];
+      // torch.max(x, minval): gradient to x where x > minval, half on a tie, else to minval
+      float wx = x < ctx.lo ? 0.0f : (x == ctx.lo ? 0.5f : 1.0f);
+      float clip = a.sign_bits ? -(1.0f - wx) : 0.0f;          // d minval / d maxval = -1 (signed only)
+      const float t = max_nan(x, ctx.lo);
+      const float wt = t > ctx.hi ? 0.0f : (t == ctx.hi ? 0.5f : 1.0f);  // torch.min(t, maxval)
+      clip = clip * wt + (1.0f - wt);
+      wx *= wt;
+      const float xc = min_nan(t, ctx.hi);
+      float xi[1] = {xc}, yo[1];
+      int32_t cd[1];
+      quant_vec<KMODE, true, 1>(xi, ctx, yo, cd);              // code = sign | e << 16 | q
+      const int e = (cd[0] >> 16) & 0x7fff;
+      float s;
+      if (KMODE == 0) s = e >= 3 ? ctx.rt.s3 : (e == 2 ? ctx.rt.s2 : ctx.rt.s1);
+      else s = ctx.stab[off_sr(ctx.K) + 2 * e];
+      const float u = div_rn(xc, s);
+      const float q = nearbyintf(u);
+      gxr[i] = mul_rn(g, wx);
+      a1 += g * clip;
+      if (yo[0] == yo[0]) a2 += g * (q - u) * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_a1[threadIdx.x >> 5] = a1; s_a2[threadIdx.x >> 5] = a2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int k = 0; k < (int)((blockDim.x + 31) >> 5); ++k) { t1 += s_a1[k]; t2 += s_a2[k]; }
+      atomicAdd(a.acc + 2 * row, t1);
+      atomicAdd(a.acc + 2 * row + 1, t2);
     }
   }
 }
@@ -1133,6 +1181,32 @@ int fp8fq_fake_quant_multi_f32(const fp8fq_tensor_desc* descs_host, int count, f
   }
   if (g > 0) return launch_rows(group, nullptr, g, K, (cudaStream_t)stream);
   return FP8FQ_OK;
+}
+
+int fp8fq_fake_quant_backward_f32(const float* grad_y, const float* x, float* grad_x, const float* table, int64_t n,
+                                  int64_t C, int64_t inner, float mantissa_bits, int n_bits, int sign_bits,
+                                  double* acc, void* stream) {
+  int M, E, K;
+  int r = check_format(mantissa_bits, n_bits, sign_bits, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (n < 0 || C < 1 || inner < 0 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
+  if (acc == nullptr) return FP8FQ_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce = cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st);
+  if (ce != cudaSuccess) return (int)ce;
+  if (n == 0) return FP8FQ_OK;
+  if (grad_y == nullptr || x == nullptr || grad_x == nullptr || table == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(grad_y) || !aligned4(x) || !aligned4(grad_x) || (reinterpret_cast<uintptr_t>(acc) & 7u)) return FP8FQ_ERR_ALIGNMENT;
+  BwdArgs a{};
+  a.g = grad_y; a.x = x; a.gx = grad_x; a.table = table; a.acc = acc; a.C = C; a.inner = inner;
+  a.chunk = 4096;
+  a.chunks_per_row = (inner + a.chunk - 1) / a.chunk;
+  a.K = K; a.stride = table_stride(K); a.sign_bits = sign_bits;
+  int64_t grid = C * a.chunks_per_row;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  if (K <= 3) fq_backward_kernel<0><<<(unsigned)grid, 128, 0, st>>>(a);
+  else fq_backward_kernel<1><<<(unsigned)grid, 128, 0, st>>>(a);
+  return launch_status();
 }
 
 int64_t fp8fq_uniform_table_floats(int64_t C) { return C < 1 ? FP8FQ_ERR_BAD_ARG : C * kUStride; }

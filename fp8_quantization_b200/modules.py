@@ -87,8 +87,10 @@ def _act_code(act):
 
 def _fusable_manager(mgr) -> bool:
     """A per-tensor FP activation quantiser with fixed ranges: its table can be consumed by a fused kernel."""
-    return (FUSE_EPILOGUES and isinstance(mgr, QuantizationManager) and isinstance(mgr.quantizer, FPQuantizer)
-            and not mgr.estimating() and not mgr.per_channel and mgr.quantizer.maxval.numel() == 1)
+    # (the fused kernels are forward-only: with autograd recording, the op-by-op path keeps the graph intact)
+    return (FUSE_EPILOGUES and not torch.is_grad_enabled() and isinstance(mgr, QuantizationManager)
+            and isinstance(mgr.quantizer, FPQuantizer) and not mgr.estimating() and not mgr.per_channel
+            and mgr.quantizer.maxval.numel() == 1)
 
 
 # ---- state switches applied with nn.Module.apply (base_quantized_classes.py:16-37) ------------------
@@ -653,7 +655,7 @@ class QuantizedModel(nn.Module):
         and hands each layer its result for the forward that follows (same work as the per-layer
         QuantizationHijacker.quantize_weights calls, hijacker.py:88-98, without 21..53 tiny launches).  Layers that
         are still estimating ranges, or whose weights need a transposed layout, keep the per-layer path."""
-        if not BATCH_WEIGHT_QUANT:
+        if not BATCH_WEIGHT_QUANT or torch.is_grad_enabled():
             return
         groups = {}
         for m in self.modules():

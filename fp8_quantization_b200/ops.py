@@ -222,6 +222,20 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     return out
 
 
+def fake_quant_backward(grad_y, x, table, C: int, mantissa_bits: float, n_bits: int, sign_bits: int):
+    """STE backward (fp8fq_fake_quant_backward_f32): returns (grad_x, acc [C, 2] float64) with acc[:, 0] the clipping
+    term and acc[:, 1] the scale term of d/dmaxval."""
+    _require(x, "x")
+    _require(grad_y, "grad_y")
+    n = x.numel()
+    gx = torch.empty_like(x)
+    acc = torch.empty(C, 2, dtype=torch.float64, device=x.device)
+    check(lib().fp8fq_fake_quant_backward_f32(grad_y.data_ptr(), x.data_ptr(), gx.data_ptr(), table.data_ptr(), n, C,
+                                              n // C if C else 0, float(mantissa_bits), int(n_bits), int(sign_bits),
+                                              acc.data_ptr(), _stream()), "fp8fq_fake_quant_backward_f32")
+    return gx, acc
+
+
 def uniform_prepare(xmin, xmax, n_bits: int, symmetric: bool, eps: float, aten_cuda_scalar_div: bool = True):
     """set_quant_range of the INT uniform quantisers (uniform_quantizers.py:224-246, 303-314) on the device.
     Returns (delta [C], zero_float [C], signed [1] as 0./1., table)."""

@@ -74,6 +74,38 @@ def default_maxval(n_bits: int, mantissa_bits: int) -> float:
     return (2 - 2 ** (-mantissa_bits)) * 2 ** (2**ebits - 1 - 2 ** (ebits - 1))
 
 
+class _FakeQuantSTE(torch.autograd.Function):
+    """Autograd node of the fake-quantiser with the reference's gradient semantics (round_ste_func, detached
+    exponent code, torch.max/min clamp): forward = the streaming kernel, backward = fq_backward_kernel + a few
+    [C]-sized tensor ops.  SURVEY section 8f4 (fp8_quantizer.py:242-254, rounding_utils.py:12-19)."""
+
+    @staticmethod
+    def forward(ctx, x, maxval, mantissa_bits, table, C, mbits_host, n_bits, sign_bits):
+        x = x.contiguous()
+        ctx.save_for_backward(x, maxval.detach(), table)
+        ctx.fmt = (C, mbits_host, n_bits, sign_bits)
+        return ops.fake_quant(x.detach(), table, C, mbits_host, n_bits, sign_bits)
+
+    @staticmethod
+    def backward(ctx, g):
+        import math
+
+        x, maxval, table = ctx.saved_tensors
+        C, mb, nb, sb = ctx.fmt
+        gx, acc = ops.fake_quant_backward(g.contiguous(), x, table, C, mb, nb, sb)
+        g_maxval = g_mbits = None
+        if ctx.needs_input_grad[1]:
+            g_maxval = (acc[:, 0] + acc[:, 1] / maxval.reshape(-1).double()).float().reshape(maxval.shape)
+        if ctx.needs_input_grad[2]:
+            M, E, _ = ops.format_split(mb, nb, sb)
+            rb = round(mb)
+            inside = 1.0 if 1 <= rb <= nb - sb else 0.0  # torch.clamp passes the gradient inside [min, max]
+            dbias_dM = -(2.0**E) * math.log(2.0) + 2.0 ** (-M) / (2.0 - 2.0 ** (-M))
+            coef = math.log(2.0) * (-1.0 - dbias_dM) * inside
+            g_mbits = (acc[:, 1].sum() * coef).float().reshape(1)
+        return (gx if ctx.needs_input_grad[0] else None), g_maxval, g_mbits, None, None, None, None, None
+
+
 class FPQuantizer(QuantizerBase):
     """8-bit (runtime bit-split) floating-point fake quantiser -- fp8_quantizer.py:151-272."""
 
@@ -106,6 +138,8 @@ class FPQuantizer(QuantizerBase):
             value = torch.Tensor([float(value)])
         if value.dim() == 0:
             value = value.reshape(1)
+        if isinstance(self._maxval, nn.Parameter) and not isinstance(value, nn.Parameter):
+            del self._maxval  # un-register the Parameter before storing a plain tensor under the same name
         self._maxval = value
         self._table_key = None
 
@@ -139,6 +173,8 @@ class FPQuantizer(QuantizerBase):
 
     def adopt_range(self, maxval: torch.Tensor, table: torch.Tensor):
         """Install a (maxval, table) pair produced on device by the fused estimate/set-range kernels."""
+        if isinstance(self._maxval, nn.Parameter):
+            del self._maxval
         self._maxval = maxval
         self._table = table
         self._table_key = (maxval.data_ptr(), maxval._version, maxval.numel(), self._mbits_host, self.n_bits,
@@ -159,11 +195,20 @@ class FPQuantizer(QuantizerBase):
 
     # -- the hot path ---------------------------------------------------------------------------------
     def forward(self, x_float):
-        if torch.is_grad_enabled() and (x_float.requires_grad or isinstance(self._maxval, nn.Parameter)):
-            raise Fp8fqError("FPQuantizer: forward-only engine (STE backward is SURVEY section 8 row f4); "
-                             "call under torch.no_grad()")
         x = x_float if x_float.is_contiguous() else x_float.contiguous()
+        if isinstance(self._mantissa_bits, nn.Parameter):  # learnable mantissa width: re-read the value (one .item())
+            mb = float(self._mantissa_bits.detach().reshape(-1)[0].item())
+            if mb != self._mbits_host:
+                self._mbits_host = mb
+                self._table_key = None
         table, C = self.table_for(x)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or self._maxval.requires_grad
+                                                  or self._mantissa_bits.requires_grad)
+        if needs_grad:  # straight-through estimator, as the reference's autograd graph
+            mbt = self._mantissa_bits
+            if mbt.device != x.device and not isinstance(mbt, nn.Parameter):
+                mbt = mbt.to(x.device)
+            return _FakeQuantSTE.apply(x, self._maxval, mbt, table, C, self._mbits_host, self.n_bits, self.sign_bits)
         return ops.fake_quant(x, table, C, self._mbits_host, self.n_bits, self.sign_bits)
 
     def quantize_with_codes(self, x_float):
@@ -209,18 +254,36 @@ class FPQuantizer(QuantizerBase):
         maxval, table = ops.set_range_prepare(x_min, x_max, self._mbits_host, self.n_bits, self.sign_bits)
         self.adopt_range(maxval, table)
 
-    def make_range_trainable(self):
-        if self.learning_maxval or self.learning_mantissa_bits:
-            raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+    def make_range_trainable(self):  # fp8_quantizer.py:242-246
+        if self.learning_maxval:
+            self.learn_maxval()
+        if self.learning_mantissa_bits:
+            self.learn_mantissa_bits()
 
-    def learn_maxval(self):
-        raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+    def _param_device(self):
+        return self._maxval.device if self._maxval.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
-    def learn_mantissa_bits(self):
-        raise NotImplementedError("learnable ranges need the STE backward (SURVEY section 8 row f4)")
+    def learn_maxval(self):  # :248-250 (registered as ``_maxval``; ``.maxval`` returns the Parameter)
+        self.learning_maxval = True
+        if not isinstance(self._maxval, nn.Parameter):
+            self._maxval = nn.Parameter(self._maxval.detach().to(self._param_device(), torch.float32).contiguous())
+            self._table_key = None
 
-    def fix_ranges(self):
-        pass  # nothing is an nn.Parameter here (fp8_quantizer.py:256-260 only acts on Parameters)
+    def learn_mantissa_bits(self):  # :252-254
+        self.learning_mantissa_bits = True
+        if not isinstance(self._mantissa_bits, nn.Parameter):
+            self._mantissa_bits = nn.Parameter(self._mantissa_bits.detach().to(self._param_device(), torch.float32)
+                                               .reshape(-1).contiguous())
+
+    def fix_ranges(self):  # :256-260 (the reference calls an undefined helper here; this is what it intends)
+        if isinstance(self._maxval, nn.Parameter):
+            self._maxval = self._maxval.detach().clone()
+            self._table_key = None
+        if isinstance(self._mantissa_bits, nn.Parameter):
+            mb = self._mantissa_bits.detach().clone()
+            self._mantissa_bits = mb
+            self._mbits_host = float(mb.reshape(-1)[0].item())
+            self._table_key = None
 
     def extra_repr(self):
         M, E, _ = ops.format_split(self._mbits_host, self.n_bits, self.sign_bits)

@@ -143,6 +143,16 @@ int fp8fq_add_act_quant_f32(const float* a, const float* b, float* y, int64_t n,
                             const float* table, float mantissa_bits, int n_bits, int sign_bits,
                             void* stream);
 
+/* STE backward of the fake-quantiser: what autograd computes through quantize_to_fp8_ste_MM
+ * (fp8_quantizer.py:91-133; round_ste_func, detached exponent code) for learnable ranges (:242-254).
+ * grad_x[i] = grad_y[i] * (1 inside the clipping range, 0 outside, 1/2 on exact ties);
+ * acc[2c] = sum_i grad_y * d xc/d maxval (clipping term), acc[2c+1] = sum_i grad_y * (q - xc/s) * s (scale term), in
+ * double; the caller finishes  grad_maxval[c] = acc[2c] + acc[2c+1] / maxval[c]  and
+ * grad_mantissa_bits = ln2 * (-1 - dbias/dM) * sum_c acc[2c+1].  `acc` ([2*C] doubles) is zeroed by the call. */
+int fp8fq_fake_quant_backward_f32(const float* grad_y, const float* x, float* grad_x, const float* table, int64_t n,
+                                  int64_t C, int64_t inner, float mantissa_bits, int n_bits, int sign_bits,
+                                  double* acc, void* stream);
+
 /* INT uniform quantisers -- the reference's comparison baseline.
  * fp8fq_uniform_prepare_f32 replaces Asymmetric/SymmetricUniformQuantizer.set_quant_range
  * (quantization/quantizers/uniform_quantizers.py:224-246, 303-314): from (x_min [C], x_max [C]) it writes delta [C],

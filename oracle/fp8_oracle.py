@@ -53,6 +53,33 @@ def fake_quant(x, n_bits: int, maxval, mantissa_bits, sign_bits: int, return_cod
     return y
 
 
+class _RoundSTE(torch.autograd.Function):
+    """rounding_utils.py:12-19: forward torch.round, backward identity."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return torch.round(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def fake_quant_ste(x, n_bits: int, maxval, mantissa_bits, sign_bits: int):
+    """fp8_quantizer.py:105-133 with the reference's autograd semantics (round_ste_func, detached log_scales):
+    differentiable w.r.t. x, maxval and mantissa_bits -- the checker of the STE backward kernel."""
+    M = torch.clamp(_RoundSTE.apply(mantissa_bits), 1, n_bits - sign_bits)
+    E = n_bits - sign_bits - M
+    if maxval.shape[0] != 1 and len(maxval.shape) != len(x.shape):
+        maxval = maxval.view([-1] + [1] * (len(x.shape) - 1))
+    bias = 2**E - torch.log2(maxval) + torch.log2(2 - 2 ** (-M)) - 1
+    minval = -maxval if sign_bits == 1 else torch.zeros_like(maxval)
+    xc = torch.min(torch.max(x, minval), maxval)
+    log_scales = torch.clamp((torch.floor(torch.log2(torch.abs(xc)) + bias)).detach(), 1.0)
+    scales = 2.0 ** (log_scales - M - bias)
+    return _RoundSTE.apply(xc / scales) * scales
+
+
 def quant_tables(n_bits: int, maxval, mantissa_bits, sign_bits: int):
     """The per-channel quantities the reference derives from (maxval, M): ``bias``
     (:110) and, for every exponent code e in [1, max(1, 2^E-1)], the scale

@@ -328,6 +328,51 @@ def gen_line_search(R):
     print("line_search.npz")
 
 
+def gen_backward(R):
+    """gradients of the reference's FPQuantizer (learnable maxval / mantissa_bits,
+    fp8_quantizer.py:242-254) w.r.t. x, maxval and mantissa_bits for L = sum(y * w)."""
+    out = {}
+    g = torch.Generator().manual_seed(15)
+    idx = 0
+    for M in (2, 3, 4, 5):
+        for pc in (False, True):
+            for sb in (1, 0):
+                shape = (8, 192) if pc else (1536,)
+                x = (torch.randn(shape, generator=g) * 1.5)
+                if sb == 0:
+                    x = x.abs() - 0.1
+                w = torch.randn(shape, generator=g)
+                q = R.FPQuantizer(8, per_channel=pc, mantissa_bits=M, set_maxval=True)
+                q.sign_bits = sb
+                mn, mx = O.minmax(x, pc)
+                q.set_quant_range(mn * 0.7, mx * 0.7)
+                x.view(-1)[:3] = torch.stack([q.maxval.reshape(-1)[0], -q.maxval.reshape(-1)[0] * sb, torch.tensor(0.0)])
+                q.learn_maxval()
+                q.learn_mantissa_bits()
+                xr = x.clone().requires_grad_(True)
+                y = q(xr)
+                (y * w).sum().backward()
+                mv = q.maxval.detach().clone().requires_grad_(True)
+                mb = q.mantissa_bits.detach().clone().requires_grad_(True)
+                xo = x.clone().requires_grad_(True)
+                yo = O.fake_quant_ste(xo, 8, mv, mb, sb)
+                (yo * w).sum().backward()
+                assert same_bits(y.detach(), yo.detach()) and same_bits(xr.grad, xo.grad)
+                assert same_bits(q.maxval.grad, mv.grad) and same_bits(q.mantissa_bits.grad, mb.grad)
+                n = f"b{idx:02d}"
+                out[n + "_x"] = x.numpy()
+                out[n + "_w"] = w.numpy()
+                out[n + "_maxval"] = q.maxval.detach().numpy()
+                out[n + "_gx"] = xr.grad.numpy()
+                out[n + "_gmaxval"] = q.maxval.grad.numpy()
+                out[n + "_gmbits"] = q.mantissa_bits.grad.numpy()
+                out[n + "_meta"] = np.array([M, sb, int(pc)])
+                idx += 1
+    out["num_cases"] = np.array(idx)
+    np.savez_compressed(os.path.join(OUT, "backward.npz"), **out)
+    print("backward.npz:", idx, "cases")
+
+
 def gen_bn_reestimate(R):
     """the reference's reestimate_BN_stats (utils/qat_utils.py:45-90) on a small quantised
     conv-BN-ReLU-conv-BN stack with fixed ranges, 3 batches."""
@@ -430,6 +475,7 @@ if __name__ == "__main__":
     gen_resnet18(R)
     gen_uniform(R)
     gen_line_search(R)
+    gen_backward(R)
     gen_bn_reestimate(R)
     if "--mobilenet" in sys.argv:
         gen_mobilenetv2(R)

@@ -185,6 +185,54 @@ def test_next_row_f2_line_search_estimator_vs_reference_golden():
     assert float(mx) == float(g["pt_xmax"][0])
 
 
+def test_next_row_f4_ste_backward_vs_reference_golden():
+    """gradients through FPQuantizer with learnable maxval / mantissa_bits vs the real reference's autograd
+    (CPU): grad_x bit-identical (it is g times 0 / 0.5 / 1), grad_maxval and grad_mantissa_bits within fp32 summation
+    noise; and vs the oracle's autograd graph on the same GPU."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("backward.npz")
+    for i in range(int(g["num_cases"])):
+        n = f"b{i:02d}"
+        M, sb, pc = [int(v) for v in g[n + "_meta"]]
+        x = torch.from_numpy(g[n + "_x"]).to(DEV).requires_grad_(True)
+        w = torch.from_numpy(g[n + "_w"]).to(DEV)
+        q = fq.FPQuantizer(8, per_channel=bool(pc), mantissa_bits=M, set_maxval=True)
+        q.sign_bits = sb
+        q.maxval = torch.from_numpy(g[n + "_maxval"]).to(DEV)
+        q.learn_maxval()
+        q.learn_mantissa_bits()
+        assert isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 2
+        y = q(x)
+        (y * w).sum().backward()
+        assert torch.equal(bits(x.grad.cpu()), bits(torch.from_numpy(g[n + "_gx"]))), n
+        np.testing.assert_allclose(q.maxval.grad.cpu().numpy().reshape(-1), g[n + "_gmaxval"].reshape(-1), rtol=2e-3,
+                                   atol=2e-3)
+        np.testing.assert_allclose(q.mantissa_bits.grad.cpu().numpy().reshape(-1), g[n + "_gmbits"].reshape(-1),
+                                   rtol=2e-3, atol=5e-2)
+        # same graph evaluated by ATen autograd on the GPU
+        xo = torch.from_numpy(g[n + "_x"]).to(DEV).requires_grad_(True)
+        mv = q.maxval.detach().clone().requires_grad_(True)
+        mb = torch.tensor([float(M)], device=DEV, requires_grad=True)
+        yo = O.fake_quant_ste(xo, 8, mv, mb, sb)
+        (yo * w).sum().backward()
+        assert torch.equal(bits(y.detach()), bits(yo.detach())) and torch.equal(bits(x.grad), bits(xo.grad))
+        np.testing.assert_allclose(q.maxval.grad.cpu().numpy(), mv.grad.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # an optimiser step on maxval changes the table (Parameter version bump) and the output
+    q = fq.FPQuantizer(8, mantissa_bits=5, maxval=2.0, learn_maxval=True)
+    q.make_range_trainable()
+    x = torch.randn(4096, device=DEV) * 3
+    y0 = q(x).detach().clone()
+    opt = torch.optim.SGD(q.parameters(), lr=0.5)
+    q(x).sum().backward()
+    opt.step()
+    assert float(q.maxval) != 2.0 and not torch.equal(q(x).detach(), y0)
+    q.fix_ranges()
+    assert not isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 0
+    with torch.no_grad():
+        assert torch.equal(q(x), O.fake_quant(x, 8, q.maxval, torch.tensor([5.0], device=DEV), 1))
+
+
 def test_next_row_f3_uniform_quantizers_bit_exact_vs_reference_golden():
     """Asymmetric / SymmetricUniformQuantizer classes on the GPU vs the real reference (CPU): delta,
     zero-point and every output bit identical (IEEE-exact arithmetic), incl. +-0, +-inf, NaN, 2/4/8 bits,

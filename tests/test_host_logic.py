@@ -25,8 +25,7 @@ def test_quantizer_constructor_contract():
     import copy
     q2 = copy.deepcopy(q)                   # LineSearchEstimator deep-copies its quantiser
     assert q2 is not q and float(q2.maxval) == float(q.maxval)
-    with pytest.raises(NotImplementedError):
-        fq.FPQuantizer(8, learn_maxval=True).make_range_trainable()
+    assert fq.FPQuantizer(8, learn_maxval=True).learning_maxval
 
 
 def test_enums_and_manager_state_machine():
