@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ Ro
 // ------------------------------------------------------------------------------------------------
 // STE backward of the fake-quantiser.  With round_ste and the detached exponent code
 // (fp8_quantizer.py:128-132), y = round(xc / s) * s gives   dy/dxc = 1,   dy/ds = q - xc/s,   and s depends on
-// maxval and M only through the bias: ds/dmaxval = s / maxval, ds/dM = s * ln2 * (-1 - dbias/dM).  The clamp
+// maxval and M only through the bias (grad_x = ((g * s) / s) * clamp weight, rounded as ATen does): ds/dmaxval = s / maxval, ds/dM = s * ln2 * (-1 - dbias/dM).  The clamp
 // (:112-113, torch.max / torch.min) passes the gradient to x inside the range, to +-maxval outside, and splits it
 // evenly on exact ties.  The kernel writes grad_x and accumulates per channel
 //   acc[2c]   = sum g * (d xc / d maxval)            (clipping term)
@@ -665,9 +665,12 @@ __global__ void __launch_bounds__(128) fq_backward_kernel(const BwdArgs a) {
       else s = ctx.stab[off_sr(ctx.K) + 2 * e];
       const float u = div_rn(xc, s);
       const float q = nearbyintf(u);
-      gxr[i] = mul_rn(g, wx);
-      a1 += g * clip;
-      if (yo[0] == yo[0]) a2 += g * (q - u) * s;
+      // autograd's own rounding: mul backward gives g * s, div backward (g * s) / s -- exact only when the
+      // libdevice powf scale is an exact power of two, so it is reproduced instead of simplified to g
+      const bool isnan_x = !(x == x);   // the reference's s is NaN there: every gradient it touches becomes NaN
+      gxr[i] = isnan_x ? x : mul_rn(div_rn(mul_rn(g, s), s), wx);
+      a1 += isnan_x ? x : g * clip;
+      a2 += isnan_x ? x : g * (q - u) * s;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -151,6 +151,9 @@ class FPQuantizer(QuantizerBase):
     def mantissa_bits(self, value):
         # The format split decides the table layout, so the host needs the value; a CUDA tensor
         # assigned here costs one .item() -- the library itself never does that.
+        if isinstance(self.__dict__.get("_parameters", {}).get("_mantissa_bits"), nn.Parameter) and not isinstance(
+                value, nn.Parameter):
+            del self._mantissa_bits
         if isinstance(value, torch.Tensor):
             self._mbits_host = float(value.detach().reshape(-1)[0].item())
             self._mantissa_bits = value
@@ -277,10 +280,13 @@ class FPQuantizer(QuantizerBase):
 
     def fix_ranges(self):  # :256-260 (the reference calls an undefined helper here; this is what it intends)
         if isinstance(self._maxval, nn.Parameter):
-            self._maxval = self._maxval.detach().clone()
+            mv = self._maxval.detach().clone()
+            del self._maxval  # un-register before storing a plain tensor under the same name
+            self._maxval = mv
             self._table_key = None
         if isinstance(self._mantissa_bits, nn.Parameter):
             mb = self._mantissa_bits.detach().clone()
+            del self._mantissa_bits
             self._mantissa_bits = mb
             self._mbits_host = float(mb.reshape(-1)[0].item())
             self._table_key = None

@@ -13,7 +13,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import bits, load_golden
+from conftest import bits, load_golden, ulp_diff
 from oracle import fp8_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -187,8 +187,10 @@ def test_next_row_f2_line_search_estimator_vs_reference_golden():
 
 def test_next_row_f4_ste_backward_vs_reference_golden():
     """gradients through FPQuantizer with learnable maxval / mantissa_bits vs the real reference's autograd
-    (CPU): grad_x bit-identical (it is g times 0 / 0.5 / 1), grad_maxval and grad_mantissa_bits within fp32 summation
-    noise; and vs the oracle's autograd graph on the same GPU."""
+    (CPU): grad_x = ((g * s) / s) * {0, 0.5, 1} within 2 ulp (s is ATen's pow result, an exact power of two on
+    neither backend every time, and the two backends' pow differ -- DESIGN.md section 3) with the clamp mask
+    identical, grad_maxval and grad_mantissa_bits within fp32 summation noise; and grad_x value-identical to the
+    oracle's autograd graph evaluated by ATen on the same GPU (parity statement P1), NaN inputs included."""
     import fp8_quantization_b200 as fq
 
     g = load_golden("backward.npz")
@@ -205,7 +207,9 @@ def test_next_row_f4_ste_backward_vs_reference_golden():
         assert isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 2
         y = q(x)
         (y * w).sum().backward()
-        assert torch.equal(bits(x.grad.cpu()), bits(torch.from_numpy(g[n + "_gx"]))), n
+        gx_ref = torch.from_numpy(g[n + "_gx"])
+        assert torch.equal(x.grad.cpu() == 0, gx_ref == 0), n               # same clamp mask
+        assert int(ulp_diff(x.grad.cpu(), gx_ref)[gx_ref != 0].max()) <= 2, n
         np.testing.assert_allclose(q.maxval.grad.cpu().numpy().reshape(-1), g[n + "_gmaxval"].reshape(-1), rtol=2e-3,
                                    atol=2e-3)
         np.testing.assert_allclose(q.mantissa_bits.grad.cpu().numpy().reshape(-1), g[n + "_gmbits"].reshape(-1),
@@ -216,17 +220,29 @@ def test_next_row_f4_ste_backward_vs_reference_golden():
         mb = torch.tensor([float(M)], device=DEV, requires_grad=True)
         yo = O.fake_quant_ste(xo, 8, mv, mb, sb)
         (yo * w).sum().backward()
-        assert torch.equal(bits(y.detach()), bits(yo.detach())) and torch.equal(bits(x.grad), bits(xo.grad))
+        assert torch.equal(bits(y.detach()), bits(yo.detach())) and torch.equal(x.grad, xo.grad)
         np.testing.assert_allclose(q.maxval.grad.cpu().numpy(), mv.grad.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # a NaN input poisons its own grad_x entry and both parameter gradients, as in the reference
+    q = fq.FPQuantizer(8, mantissa_bits=3, maxval=3.0)
+    q.learn_maxval()
+    xn = torch.tensor([float("nan"), 1.0, 5.0, -5.0, float("inf")], device=DEV, requires_grad=True)
+    wn = torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0], device=DEV)
+    (q(xn) * wn).sum().backward()
+    xo = xn.detach().clone().requires_grad_(True)
+    mv = torch.tensor([3.0], device=DEV, requires_grad=True)
+    (O.fake_quant_ste(xo, 8, mv, torch.tensor([3.0], device=DEV), 1) * wn).sum().backward()
+    assert torch.equal(torch.isnan(xn.grad), torch.isnan(xo.grad)) and bool(torch.isnan(xn.grad[0]))
+    assert torch.equal(xn.grad[1:], xo.grad[1:]) and bool(torch.isnan(q.maxval.grad).all() and torch.isnan(mv.grad).all())
     # an optimiser step on maxval changes the table (Parameter version bump) and the output
     q = fq.FPQuantizer(8, mantissa_bits=5, maxval=2.0, learn_maxval=True)
     q.make_range_trainable()
-    x = torch.randn(4096, device=DEV) * 3
+    x = torch.randn(4096, device=DEV, generator=torch.Generator(DEV).manual_seed(4)) * 3
     y0 = q(x).detach().clone()
-    opt = torch.optim.SGD(q.parameters(), lr=0.5)
+    opt = torch.optim.SGD(q.parameters(), lr=1e-3)
     q(x).sum().backward()
     opt.step()
-    assert float(q.maxval) != 2.0 and not torch.equal(q(x).detach(), y0)
+    assert 0.5 < float(q.maxval.detach()) < 8.0 and float(q.maxval.detach()) != 2.0
+    assert not torch.equal(q(x).detach(), y0)
     q.fix_ranges()
     assert not isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 0
     with torch.no_grad():

@@ -111,3 +111,24 @@ def test_resnet18_and_mobilenetv2_census():
         workloads.resnet18_quantized(**{**workloads.readme_quant_params(5), "quant_setup": setup})
     with pytest.raises(ValueError):
         workloads.resnet18_quantized(**{**workloads.readme_quant_params(5), "quant_setup": "nope"})
+
+
+def test_learnable_range_parameter_registration():
+    """fp8_quantizer.py:242-260: learn_maxval / learn_mantissa_bits register Parameters, fix_ranges and plain
+    assignments un-register them again (host bookkeeping only; the device of the Parameter is forced to the CPU
+    here because this suite runs without a GPU)."""
+    import fp8_quantization_b200 as fq
+
+    q = fq.FPQuantizer(8, mantissa_bits=5, maxval=2.0, learn_maxval=True, learn_mantissa_bits=True)
+    q._param_device = lambda: torch.device("cpu")
+    assert list(q.parameters()) == []
+    q.make_range_trainable()
+    assert sorted(n for n, _ in q.named_parameters()) == ["_mantissa_bits", "_maxval"]
+    assert isinstance(q.maxval, torch.nn.Parameter) and isinstance(q.mantissa_bits, torch.nn.Parameter)
+    q.fix_ranges()
+    assert list(q.parameters()) == [] and float(q.maxval) == 2.0 and float(q.mantissa_bits) == 5.0
+    q.learn_maxval()
+    q.learn_mantissa_bits()
+    q.maxval = torch.tensor([3.0])
+    q.mantissa_bits = 3
+    assert list(q.parameters()) == [] and float(q.maxval) == 3.0 and q._mbits_host == 3.0

@@ -70,8 +70,13 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
     cm, cx = torch.empty(1, device=dev), torch.empty(1, device=dev)
     med, mn = timeit([lambda x=x: ops.minmax(x, False, cm, cx, ops.EST_CURRENT, False) for x in xs])
     rec["minmax"] = {"us": med * 1e3, "gbs": 4 * n / (med * 1e-3) / 1e9, "frac": 4 * n / (med * 1e-3) / 1e9 / PEAK}
+    gy = torch.randn(shape, device=dev)
+    med, mn = timeit([lambda x=x: ops.fake_quant_backward(gy, x, tb, 1, 5.0, 8, 1) for x in xs])
+    rec["backward_M5"] = {"us": med * 1e3, "gbs": 12 * n / (med * 1e-3) / 1e9, "frac": 12 * n / (med * 1e-3) / 1e9 / PEAK}
+    med, mn = timeit([lambda x=x: ops.fake_quant_backward(gy, x, tb4, 1, 4.0, 8, 1) for x in xs])
+    rec["backward_M4"] = {"us": med * 1e3, "gbs": 12 * n / (med * 1e-3) / 1e9, "frac": 12 * n / (med * 1e-3) / 1e9 / PEAK}
     out["sites"].append(rec)
-    del xs, rs, y
+    del xs, rs, y, gy
     torch.cuda.empty_cache()
 
 # weights: all 21 ResNet-18 tensors in one launch vs one launch each
