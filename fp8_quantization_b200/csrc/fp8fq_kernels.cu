@@ -243,7 +243,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
 // vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
 template <int KMODE, bool CODES, int N>
-__device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N]) {
+__device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N],
+                                          float* s_out = nullptr) {
   if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
     float q[N];
     bool slow = false;
@@ -324,6 +325,7 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     y[k] = mul_rn(q[k], s[k]);
+    if (s_out) s_out[k] = s[k];
     if (CODES) {
       if (y[k] != y[k]) code[k] = 0x7fffffff;
       else code[k] = (int32_t)((f2u(y[k]) & 0x80000000u) | ((uint32_t)e[k] << 16) | (uint32_t)fabsf(q[k]));
@@ -631,9 +633,43 @@ struct BwdArgs {
   int K, stride, sign_bits;
 };
 
-template <int KMODE>
-__global__ void __launch_bounds__(128) fq_backward_kernel(const BwdArgs a) {
-  __shared__ float s_a1[4], s_a2[4];
+// N elements of one channel.  grad_x reproduces autograd's roundings: mul backward g * s, div backward (g * s) / s.
+// When s is an exact power of two (the common case) the division is a multiplication by the exactly representable
+// 2^-k, which rounds identically; a vector with any other scale takes IEEE division.
+template <int KMODE, int N>
+__device__ __forceinline__ void bwd_vec(const float (&g)[N], const float (&x)[N], const ElemCtx<KMODE>& ctx,
+                                        int sign_bits, float (&gx)[N], float& a1, float& a2) {
+  float y[N], s[N], t[N];
+  int32_t cd[N];
+  quant_vec<KMODE, false, N>(x, ctx, y, cd, s);
+  bool slow = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const uint32_t sb = f2u(s[k]);
+    slow |= (sb & 0x007fffffu) != 0u || sb < 0x01000000u || sb > 0x7e000000u;
+    t[k] = mul_rn(g[k], s[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    // torch.max(x, minval): gradient to x where x > minval, half on a tie, else to minval (d minval/d maxval = -1)
+    float wx = x[k] < ctx.lo ? 0.0f : (x[k] == ctx.lo ? 0.5f : 1.0f);
+    float clip = sign_bits ? wx - 1.0f : 0.0f;
+    const float tt = max_nan(x[k], ctx.lo);
+    const float wt = tt > ctx.hi ? 0.0f : (tt == ctx.hi ? 0.5f : 1.0f);  // torch.min(t, maxval)
+    clip = clip * wt + (1.0f - wt);
+    wx *= wt;
+    const float xc = min_nan(tt, ctx.hi);
+    const float d = slow ? div_rn(t[k], s[k]) : mul_rn(t[k], u2f(0x7f000000u - f2u(s[k])));
+    const bool nan_x = !(x[k] == x[k]);   // the reference's s is NaN there: every gradient it touches becomes NaN
+    gx[k] = nan_x ? x[k] : mul_rn(d, wx);
+    a1 += nan_x ? x[k] : g[k] * clip;
+    a2 += g[k] * (y[k] - xc);             // = g * (q - xc / s) * s; NaN for a NaN input
+  }
+}
+
+template <int KMODE, bool VEC>
+__global__ void __launch_bounds__(256, 4) fq_backward_kernel(const BwdArgs a) {
+  __shared__ float s_a1[8], s_a2[8];
   const int64_t nwork = a.C * a.chunks_per_row;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int64_t row = w / a.chunks_per_row;
@@ -646,31 +682,30 @@ __global__ void __launch_bounds__(128) fq_backward_kernel(const BwdArgs a) {
     const float* gr = a.g + row * a.inner;
     float* gxr = a.gx + row * a.inner;
     float a1 = 0.0f, a2 = 0.0f;
-    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-      const float x = xr[i], g = gr[i];
-      // torch.max(x, minval): gradient to x where x > minval, half on a tie, else to minval
-      float wx = x < ctx.lo ? 0.0f : (x == ctx.lo ? 0.5f : 1.0f);
-      float clip = a.sign_bits ? -(1.0f - wx) : 0.0f;          // d minval / d maxval = -1 (signed only)
-      const float t = max_nan(x, ctx.lo);
-      const float wt = t > ctx.hi ? 0.0f : (t == ctx.hi ? 0.5f : 1.0f);  // torch.min(t, maxval)
-      clip = clip * wt + (1.0f - wt);
-      wx *= wt;
-      const float xc = min_nan(t, ctx.hi);
-      float xi[1] = {xc}, yo[1];
-      int32_t cd[1];
-      quant_vec<KMODE, true, 1>(xi, ctx, yo, cd);              // code = sign | e << 16 | q
-      const int e = (cd[0] >> 16) & 0x7fff;
-      float s;
-      if (KMODE == 0) s = e >= 3 ? ctx.rt.s3 : (e == 2 ? ctx.rt.s2 : ctx.rt.s1);
-      else s = ctx.stab[off_sr(ctx.K) + 2 * e];
-      const float u = div_rn(xc, s);
-      const float q = nearbyintf(u);
-      // autograd's own rounding: mul backward gives g * s, div backward (g * s) / s -- exact only when the
-      // libdevice powf scale is an exact power of two, so it is reproduced instead of simplified to g
-      const bool isnan_x = !(x == x);   // the reference's s is NaN there: every gradient it touches becomes NaN
-      gxr[i] = isnan_x ? x : mul_rn(div_rn(mul_rn(g, s), s), wx);
-      a1 += isnan_x ? x : g * clip;
-      a2 += isnan_x ? x : g * (q - u) * s;
+    if (VEC) {   // inner % 4 == 0 and 16-byte aligned bases (checked by the host), chunk % 4 == 0
+      const int64_t step = 4 * (int64_t)blockDim.x;
+      int64_t i = beg + 4 * (int64_t)threadIdx.x;
+      for (; i + step < end; i += 2 * step) {
+        Pack<4> g0, x0, g1, x1, o0, o1;
+        g0.load(gr + i); x0.load(xr + i);
+        g1.load(gr + i + step); x1.load(xr + i + step);
+        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, o0.v, a1, a2);
+        bwd_vec<KMODE, 4>(g1.v, x1.v, ctx, a.sign_bits, o1.v, a1, a2);
+        o0.store(gxr + i);
+        o1.store(gxr + i + step);
+      }
+      if (i < end) {
+        Pack<4> g0, x0, o0;
+        g0.load(gr + i); x0.load(xr + i);
+        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, o0.v, a1, a2);
+        o0.store(gxr + i);
+      }
+    } else {
+      for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        float gi[1] = {gr[i]}, xi[1] = {xr[i]}, oi[1];
+        bwd_vec<KMODE, 1>(gi, xi, ctx, a.sign_bits, oi, a1, a2);
+        gxr[i] = oi[0];
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1202,13 +1237,19 @@ int fp8fq_fake_quant_backward_f32(const float* grad_y, const float* x, float* gr
   if (!aligned4(grad_y) || !aligned4(x) || !aligned4(grad_x) || (reinterpret_cast<uintptr_t>(acc) & 7u)) return FP8FQ_ERR_ALIGNMENT;
   BwdArgs a{};
   a.g = grad_y; a.x = x; a.gx = grad_x; a.table = table; a.acc = acc; a.C = C; a.inner = inner;
-  a.chunk = 4096;
+  const bool vec = (inner % 4 == 0) && aligned16(grad_y) && aligned16(x) && aligned16(grad_x);
+  a.chunk = inner >= 4 * 16384 ? 16384 : 4096;   // 4 or 16 vectors per thread; two double atomics per chunk
   a.chunks_per_row = (inner + a.chunk - 1) / a.chunk;
   a.K = K; a.stride = table_stride(K); a.sign_bits = sign_bits;
   int64_t grid = C * a.chunks_per_row;
-  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  if (K <= 3) fq_backward_kernel<0><<<(unsigned)grid, 128, 0, st>>>(a);
-  else fq_backward_kernel<1><<<(unsigned)grid, 128, 0, st>>>(a);
+  if (grid > (int64_t)1 << 30) grid = (int64_t)1 << 30;
+  if (K <= 3) {
+    if (vec) fq_backward_kernel<0, true><<<(unsigned)grid, 256, 0, st>>>(a);
+    else fq_backward_kernel<0, false><<<(unsigned)grid, 256, 0, st>>>(a);
+  } else {
+    if (vec) fq_backward_kernel<1, true><<<(unsigned)grid, 256, 0, st>>>(a);
+    else fq_backward_kernel<1, false><<<(unsigned)grid, 256, 0, st>>>(a);
+  }
   return launch_status();
 }
 

@@ -222,6 +222,29 @@ def test_next_row_f4_ste_backward_vs_reference_golden():
         (yo * w).sum().backward()
         assert torch.equal(bits(y.detach()), bits(yo.detach())) and torch.equal(x.grad, xo.grad)
         np.testing.assert_allclose(q.maxval.grad.cpu().numpy(), mv.grad.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # scalar-access variant (4-byte aligned view, ragged length) == vector variant, E2M5 and E4M3 tables
+    from fp8_quantization_b200 import ops
+    gen = torch.Generator(DEV).manual_seed(11)
+    for M in (5, 3):
+        qq = fq.FPQuantizer(8, mantissa_bits=M, maxval=2.5)
+        big = torch.randn(3 * 70001 + 4, device=DEV, generator=gen) * 2
+        gbig = torch.randn(3 * 70001 + 4, device=DEV, generator=gen)
+        tb, _ = qq.table_for(big)
+        for C, n0 in ((1, 70001 * 3), (1, 210000), (3, 70001 * 3), (1, 70000), (4, 4 * 16388)):
+            xa, ga = big[1:1 + n0], gbig[1:1 + n0]                         # unaligned
+            xb, gb = xa.clone(), ga.clone()                                # aligned copies
+            tbc = tb if C == 1 else ops.prepare(torch.full((C,), 2.5, device=DEV), float(M), 8, 1)
+            gx_a, acc_a = ops.fake_quant_backward(ga, xa, tbc, C, float(M), 8, 1)
+            gx_b, acc_b = ops.fake_quant_backward(gb, xb, tbc, C, float(M), 8, 1)
+            assert torch.equal(bits(gx_a), bits(gx_b))
+            np.testing.assert_allclose(acc_a.cpu().numpy(), acc_b.cpu().numpy(), rtol=1e-4, atol=1e-3)
+            xo = xb.clone().requires_grad_(True)
+            mv = torch.full((C, 1) if C > 1 else (1,), 2.5, device=DEV, requires_grad=True)
+            yo = O.fake_quant_ste(xo.reshape(C, -1) if C > 1 else xo, 8, mv, torch.tensor([float(M)], device=DEV), 1)
+            (yo.reshape(-1) * gb).sum().backward()
+            assert torch.equal(gx_b, xo.grad)
+            gmv = (acc_b[:, 0] + acc_b[:, 1] / 2.5).float().cpu().numpy()
+            np.testing.assert_allclose(gmv, mv.grad.reshape(-1).cpu().numpy(), rtol=2e-3, atol=2e-2)
     # a NaN input poisons its own grad_x entry and both parameter gradients, as in the reference
     q = fq.FPQuantizer(8, mantissa_bits=3, maxval=3.0)
     q.learn_maxval()
