@@ -39,7 +39,7 @@ constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
 constexpr int kMaxK = (1 << kMaxE) - 1;
 
 enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
-enum : int { FLAG_IRREGULAR = 1, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
+enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -260,6 +260,17 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
   } else if (K == 1) {
     ref = 0x7f800000u;  // every finite |xc| is below: code 1
     band = 0;
+  }
+  // FLAG_POW2: every scale is an exact power of two 2^k with 2^-k representable, so x / s == x * 2^-k bit for bit
+  // (used by the STE backward kernel, which reproduces autograd's (g * s) / s)
+  {
+    const float* sr = tab + off_sr(K);
+    bool pow2 = true;
+    for (int k = 1; k <= K; ++k) {
+      const uint32_t sb = f2u(sr[2 * k]);
+      pow2 = pow2 && (sb & 0x007fffffu) == 0u && sb >= 0x01000000u && sb <= 0x7e000000u;
+    }
+    if (pow2) flags |= FLAG_POW2;
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);

@@ -634,20 +634,27 @@ struct BwdArgs {
 };
 
 // N elements of one channel.  grad_x reproduces autograd's roundings: mul backward g * s, div backward (g * s) / s.
-// When s is an exact power of two (the common case) the division is a multiplication by the exactly representable
-// 2^-k, which rounds identically; a vector with any other scale takes IEEE division.
+// When every scale of the channel is an exact power of two (FLAG_POW2, the common case) the division is a
+// multiplication by the exactly representable 2^-k, which rounds identically; otherwise IEEE division.
+// One range test per vector: lanes strictly inside (lo, hi) have clamp weight 1 and no clipping term.
 template <int KMODE, int N>
 __device__ __forceinline__ void bwd_vec(const float (&g)[N], const float (&x)[N], const ElemCtx<KMODE>& ctx,
-                                        int sign_bits, float (&gx)[N], float& a1, float& a2) {
-  float y[N], s[N], t[N];
+                                        int sign_bits, bool pow2, float (&gx)[N], float& a1, float& a2) {
+  float y[N], s[N];
   int32_t cd[N];
   quant_vec<KMODE, false, N>(x, ctx, y, cd, s);
-  bool slow = false;
+  float vmin = x[0], vmax = x[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) { vmin = min_nan(vmin, x[k]); vmax = max_nan(vmax, x[k]); }
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    const uint32_t sb = f2u(s[k]);
-    slow |= (sb & 0x007fffffu) != 0u || sb < 0x01000000u || sb > 0x7e000000u;
-    t[k] = mul_rn(g[k], s[k]);
+    const float t = mul_rn(g[k], s[k]);
+    gx[k] = pow2 ? mul_rn(t, u2f(0x7f000000u - f2u(s[k]))) : div_rn(t, s[k]);
+  }
+  if (vmin > ctx.lo && vmax < ctx.hi) {   // false when any lane is NaN
+#pragma unroll
+    for (int k = 0; k < N; ++k) a2 += g[k] * (y[k] - x[k]);   // = g * (q - xc / s) * s
+    return;
   }
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -659,16 +666,18 @@ __device__ __forceinline__ void bwd_vec(const float (&g)[N], const float (&x)[N]
     clip = clip * wt + (1.0f - wt);
     wx *= wt;
     const float xc = min_nan(tt, ctx.hi);
-    const float d = slow ? div_rn(t[k], s[k]) : mul_rn(t[k], u2f(0x7f000000u - f2u(s[k])));
     const bool nan_x = !(x[k] == x[k]);   // the reference's s is NaN there: every gradient it touches becomes NaN
-    gx[k] = nan_x ? x[k] : mul_rn(d, wx);
+    gx[k] = nan_x ? x[k] : mul_rn(gx[k], wx);
     a1 += nan_x ? x[k] : g[k] * clip;
-    a2 += g[k] * (y[k] - xc);             // = g * (q - xc / s) * s; NaN for a NaN input
+    a2 += g[k] * (y[k] - xc);             // NaN for a NaN input
   }
 }
 
+#ifndef BWD_MINB
+#define BWD_MINB 4
+#endif
 template <int KMODE, bool VEC>
-__global__ void __launch_bounds__(256, 4) fq_backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, BWD_MINB) fq_backward_kernel(const BwdArgs a) {
   __shared__ float s_a1[8], s_a2[8];
   const int64_t nwork = a.C * a.chunks_per_row;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -678,6 +687,7 @@ __global__ void __launch_bounds__(256, 4) fq_backward_kernel(const BwdArgs a) {
     const int64_t end = (beg + a.chunk < a.inner) ? beg + a.chunk : a.inner;
     ElemCtx<KMODE> ctx;
     load_ctx_direct<KMODE>(ctx, a.table + row * a.stride, a.K);
+    const bool pow2 = (f2u(__ldg(a.table + row * a.stride + H_FLAGS)) & FLAG_POW2) != 0;
     const float* xr = a.x + row * a.inner;
     const float* gr = a.g + row * a.inner;
     float* gxr = a.gx + row * a.inner;
@@ -689,21 +699,21 @@ __global__ void __launch_bounds__(256, 4) fq_backward_kernel(const BwdArgs a) {
         Pack<4> g0, x0, g1, x1, o0, o1;
         g0.load(gr + i); x0.load(xr + i);
         g1.load(gr + i + step); x1.load(xr + i + step);
-        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, o0.v, a1, a2);
-        bwd_vec<KMODE, 4>(g1.v, x1.v, ctx, a.sign_bits, o1.v, a1, a2);
+        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, pow2, o0.v, a1, a2);
+        bwd_vec<KMODE, 4>(g1.v, x1.v, ctx, a.sign_bits, pow2, o1.v, a1, a2);
         o0.store(gxr + i);
         o1.store(gxr + i + step);
       }
       if (i < end) {
         Pack<4> g0, x0, o0;
         g0.load(gr + i); x0.load(xr + i);
-        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, o0.v, a1, a2);
+        bwd_vec<KMODE, 4>(g0.v, x0.v, ctx, a.sign_bits, pow2, o0.v, a1, a2);
         o0.store(gxr + i);
       }
     } else {
       for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
         float gi[1] = {gr[i]}, xi[1] = {xr[i]}, oi[1];
-        bwd_vec<KMODE, 1>(gi, xi, ctx, a.sign_bits, oi, a1, a2);
+        bwd_vec<KMODE, 1>(gi, xi, ctx, a.sign_bits, pow2, oi, a1, a2);
         gxr[i] = oi[0];
       }
     }
@@ -1238,7 +1248,10 @@ int fp8fq_fake_quant_backward_f32(const float* grad_y, const float* x, float* gr
   BwdArgs a{};
   a.g = grad_y; a.x = x; a.gx = grad_x; a.table = table; a.acc = acc; a.C = C; a.inner = inner;
   const bool vec = (inner % 4 == 0) && aligned16(grad_y) && aligned16(x) && aligned16(grad_x);
-  a.chunk = inner >= 4 * 16384 ? 16384 : 4096;   // 4 or 16 vectors per thread; two double atomics per chunk
+  // 4 or 8 vectors per thread and two double atomics per chunk (tools/bench_backward.py: 8192 is the best of
+  // 2048..65536 at the ResNet-18 activation shapes; FP8FQ_BWD_CHUNK overrides for experiments)
+  a.chunk = inner >= 4 * 8192 ? 8192 : 4096;
+  if (const char* e = getenv("FP8FQ_BWD_CHUNK")) { const long v = atol(e); if (v >= 1024 && v % 1024 == 0) a.chunk = v; }
   a.chunks_per_row = (inner + a.chunk - 1) / a.chunk;
   a.K = K; a.stride = table_stride(K); a.sign_bits = sign_bits;
   int64_t grid = C * a.chunks_per_row;
