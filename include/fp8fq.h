@@ -145,7 +145,9 @@ int fp8fq_add_act_quant_f32(const float* a, const float* b, float* y, int64_t n,
 
 /* STE backward of the fake-quantiser: what autograd computes through quantize_to_fp8_ste_MM
  * (fp8_quantizer.py:91-133; round_ste_func, detached exponent code) for learnable ranges (:242-254).
- * grad_x[i] = grad_y[i] * (1 inside the clipping range, 0 outside, 1/2 on exact ties);
+ * grad_x[i] = ((grad_y[i] * s) / s) * (1 inside the clipping range, 0 outside, 1/2 on exact ties), s the element's
+ * scale and the two roundings those of autograd's mul / div backward (the identity whenever s is a power of two);
+ * a NaN x[i] gives NaN in grad_x[i] and in both sums, as in the reference;
  * acc[2c] = sum_i grad_y * d xc/d maxval (clipping term), acc[2c+1] = sum_i grad_y * (q - xc/s) * s (scale term), in
  * double; the caller finishes  grad_maxval[c] = acc[2c] + acc[2c+1] / maxval[c]  and
  * grad_mantissa_bits = ln2 * (-1 - dbias/dM) * sum_c acc[2c+1].  `acc` ([2*C] doubles) is zeroed by the call. */
