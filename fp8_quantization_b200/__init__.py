@@ -13,5 +13,6 @@ from .range_estimators import (AllMinMaxEstimator, CurrentMinMaxEstimator, FP_MS
                                LineSearchEstimator, RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator,
                                estimate_range_line_search)
 from .quantization_manager import QMethods, Qstates, QuantizationManager  # noqa: F401
+from . import integration  # noqa: F401,E402
 
 __version__ = "0.1.0"

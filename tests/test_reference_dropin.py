@@ -1,0 +1,97 @@
+"""CPU, build container only (skipped where /root/reference is absent): the two integration routes of
+INTEGRATION.md exercised against the REAL reference -- its model builders, QuantizationManager and QuantizedModel
+drive our classes.  Structure and state machine only; no kernel launches (there is no CPU compute path)."""
+import pytest
+import torch
+from torch import nn
+
+import fp8_quantization_b200 as fq
+from fp8_quantization_b200 import integration, modules as fqm, workloads
+from fp8_quantization_b200.quantization_manager import QuantizationManager as OurManager
+from oracle.reference_loader import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+
+
+def _ref_params(R, M):
+    """The README quant-params dict holding the reference's own classes (what quant_params_dict builds)."""
+    qp = workloads.readme_quant_params(M)
+    qp.update(method=R.FPQuantizer, act_method=R.FPQuantizer,
+              weight_range_method=R.range_estimators.CurrentMinMaxEstimator,
+              act_range_method=R.range_estimators.AllMinMaxEstimator)
+    return qp
+
+
+def test_route1_reference_builders_construct_and_drive_our_quantizers():
+    R = load_reference()
+    import models.resnet_quantized as rq  # the reference's model file
+    from torchvision.models import resnet18
+
+    qp = integration.patch_quant_params(_ref_params(R, 5))
+    assert qp["method"] is fq.FPQuantizer and qp["act_range_method"] is fq.AllMinMaxEstimator
+    assert integration.patch_quant_params(qp) == qp            # idempotent
+    enum_qp = dict(qp, act_range_method=R.range_estimators.RangeEstimators.MSE)
+    assert integration.patch_quant_params(enum_qp)["act_range_method"] is fq.FP_MSE_Estimator
+    model = rq.QuantizedResNet(resnet18(), **qp)
+    RefManager = R.quantization_manager.QuantizationManager
+    mgrs = [m for m in model.modules() if isinstance(m, RefManager)]
+    assert len(mgrs) == 50                                     # 21 + 29
+    assert all(type(m.quantizer) is fq.FPQuantizer for m in mgrs)
+    assert sum(type(m.range_estimator) is fq.CurrentMinMaxEstimator and m.per_channel for m in mgrs) == 21
+    assert sum(type(m.range_estimator) is fq.AllMinMaxEstimator for m in mgrs) == 29
+    assert all(float(m.quantizer.mantissa_bits) == 5.0 and m.quantizer.set_maxval for m in mgrs)
+    # the reference's state machine runs on our objects (quantization_manager.py:88-111)
+    model.set_quant_state(True, True)
+    model.fix_ranges()
+    Q = R.quantization_manager.Qstates
+    assert all(m.state == Q.fix_ranges and m.quantizer.state == Q.fix_ranges for m in mgrs)
+    model.estimate_ranges()
+    assert all(m.state == Q.estimate_ranges for m in mgrs)
+    for m in mgrs:
+        m.reset_ranges()                                       # quantization_manager.py:109-112
+    assert all(m.range_estimator.current_xmin is None for m in mgrs)
+    # the hijackers reach into the quantiser the way models/resnet_quantized.py:97-122 does
+    model.features[0].weight_quantizer.quantizer.n_bits = 8
+    # CPU tensors are refused loudly -- no eager fall-back hides behind the reference's call
+    with pytest.raises(fq.Fp8fqError):
+        mgrs[0].quantizer(torch.zeros(4, 4))
+
+
+def test_route2_reference_builders_emit_our_fused_modules():
+    R = load_reference()
+    import quantization
+    import models.mobilenet_v2_quantized as mq
+    import models.resnet_quantized as rq
+    from models.mobilenet_v2 import MobileNetV2
+    from torchvision.models import resnet18
+
+    aq = R.autoquant_utils
+    before = (dict(aq.bn_module_map), dict(aq.non_bn_module_map), aq.QuantizedModule)
+    h = integration.install_fused_modules(quantization)
+    try:
+        qp = integration.patch_quant_params(_ref_params(R, 4))
+        model = mq.QuantizedMobileNetV2(MobileNetV2(), **qp)   # ties the pooling quantiser to OUR last BNQConv
+        ours = [m for m in model.modules() if isinstance(m, fqm.QuantizedModule)]
+        assert sum(isinstance(m, fqm.BNQConv) for m in ours) == 52 and sum(isinstance(m, fqm.QuantLinear) for m in ours) == 1
+        our_mgrs = [m for m in model.modules() if isinstance(m, OurManager)]
+        ref_mgrs = [m for m in model.modules() if isinstance(m, R.quantization_manager.QuantizationManager)]
+        assert len(our_mgrs) == 2 * 53 and len(ref_mgrs) > 0   # weight + activation manager per layer; block-level ones stay the reference's
+        assert sum(m.per_channel for m in our_mgrs) == 53
+        # QuantizedModel's switches (base_quantized_model.py:64-135) now reach both kinds of layer
+        model.set_quant_state(True, True)
+        assert all(m._qa and m._qw and bool(m._quant_a) and bool(m._quant_w) for m in ours)
+        model.set_quant_state(False, True)
+        assert all(not m._qw and m._qa for m in ours)
+        model.fix_ranges()
+        assert all(m.state.name == "fix_ranges" for m in our_mgrs + ref_mgrs)
+        model.estimate_ranges()
+        assert all(m.state.name == "estimate_ranges" for m in our_mgrs + ref_mgrs)
+        # ResNet-18 through the reference's QuantizedResNet: 20 fused conv+BN layers, fc, reference-side blocks
+        r18 = rq.QuantizedResNet(resnet18(), **integration.patch_quant_params(_ref_params(R, 5)))
+        assert sum(isinstance(m, fqm.BNQConv) for m in r18.modules()) == 20 and isinstance(r18.fc, fqm.QuantLinear)
+        assert isinstance(r18.features[4][0], rq.QuantizedBlock)
+        assert isinstance(r18.state_dict()["fc._quant_w"], torch.Tensor)
+    finally:
+        h.restore()
+    assert (dict(aq.bn_module_map), dict(aq.non_bn_module_map), aq.QuantizedModule) == before
+    assert aq.bn_module_map[nn.Conv2d] is aq.BNQConv
