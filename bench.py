@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--mantissa-bits", type=int, default=5)
+    ap.add_argument("--memory-format", choices=["nchw", "channels_last"], default="channels_last",
+                    help="activation/weight memory layout inside the network (images always arrive NCHW); "
+                         "channels_last is what cuDNN's tensor-core convolutions produce natively")
     return ap.parse_args()
 
 
@@ -340,8 +343,14 @@ def main():
     fq.lib()
 
     # ---- build the model, calibrate on one batch, fix ranges (image_net.py:48-70 flow) -----------------
-    torch.manual_seed(10)
-    model = workloads.resnet18_quantized(**workloads.readme_quant_params(M)).to(dev).eval()
+    def build_model(memory_format):
+        torch.manual_seed(10)
+        m = workloads.resnet18_quantized(**workloads.readme_quant_params(M)).to(dev).eval()
+        if memory_format == "channels_last":
+            m = m.to(memory_format=torch.channels_last)
+        return m
+
+    model = build_model(args.memory_format)
     gen = torch.Generator(device=dev).manual_seed(10 + rank)
     B = args.batch
     x_img = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
@@ -493,7 +502,9 @@ def main():
         # weights) lives in pinned host memory and is copied in; every output is copied back out
         h_in, h_out = [], []
         h2d_bytes = d2h_bytes = 0
-        for name, a, kw in plan:
+        with torch.no_grad():
+            ref_results = run_plan(plan, ops)  # output tensors of every site: host buffers mirror their strides
+        for (name, a, kw), ref_out in zip(plan, ref_results):
             if name == "bn_fold":
                 h_in.append(None), h_out.append(None)
                 continue
@@ -504,7 +515,8 @@ def main():
                     if t[0] == "const":
                         pairs.append((t[1], t[1].cpu().pin_memory()))
             h_in.append(pairs)
-            h_out.append([torch.empty(sh, dtype=torch.float32).pin_memory() for sh in data_shapes(name, a)])
+            h_out.append([torch.empty_like(o, device="cpu").pin_memory()
+                          for o in (ref_out if isinstance(ref_out, (list, tuple)) else [ref_out])])
             h2d_bytes += sum(h.numel() * 4 for _, h in pairs)
             d2h_bytes += sum(h.numel() * 4 for h in h_out[-1])
         s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -555,7 +567,7 @@ def main():
                "note": "every site's externally produced inputs (conv outputs, weights) copied from pinned host "
                        "memory and every site's output copied back to pinned host memory, per step; "
                        "3 streams (H2D / kernels / D2H); wall clock around synchronised region, max over ranks"}
-        del h_in, h_out
+        del h_in, h_out, ref_results
         # what the host link can do on this box: the same copies alone and in both directions at once
         nprobe = 64 << 20  # 256 MB per buffer
         hp_a, hp_b = torch.empty(nprobe).pin_memory(), torch.empty(nprobe).pin_memory()
@@ -659,11 +671,39 @@ def main():
             dt = time.perf_counter() - t0
             if not torch.equal(h_log[0], static_logits.cpu()):
                 raise RuntimeError("e2e logits differ from the device-resident forward")
-        vals = torch.tensor([mms, dt], device=dev)
+            # the same network in the other memory layout (device-resident forward only), for comparison
+            other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
+            del g2
+            m2 = build_model(other_fmt)
+            workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
+            m2.fix_ranges()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    m2(static_x)
+            torch.cuda.current_stream().wait_stream(s)
+            g3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g3):
+                m2(static_x)
+            for _ in range(3):
+                g3.replay()
+            barrier()
+            m0.record()
+            for _ in range(iters):
+                g3.replay()
+            m1.record()
+            barrier()
+            mms_other = m0.elapsed_time(m1) / iters
+            del g3, m2
+        vals = torch.tensor([mms, dt, mms_other], device=dev)
         if world > 1:
             fq_dist.all_reduce_max(vals)
-        mms, dt = vals.tolist()
+        mms, dt, mms_other = vals.tolist()
         model_info = {"resnet18_quantized_img_per_s": B * world / (mms * 1e-3), "ms_per_forward": mms,
+                      "memory_format": args.memory_format,
+                      "other_layout": {"memory_format": other_fmt, "ms_per_forward": mms_other,
+                                       "img_per_s": B * world / (mms_other * 1e-3)},
                       "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
                       "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
                       "e2e_note": "images from pinned host memory every step, logits back to pinned host memory; H2D of "
@@ -690,6 +730,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "mantissa_bits": M,
                    "n_bits": 8, "per_channel_weights": True, "ranges": "fixed (calibrated on 1 batch, allminmax)",
+                   "memory_format": args.memory_format,
                    "elems_per_step_per_gpu": st["elems"], "launches_per_step": st["launches"],
                    "cuda_graph": graph is not None, "parallelism": f"dp{world}",
                    "l2": f"per-step working set {(st['in_bytes'] + st['out_bytes']) / 1e9:.2f} GB >> 126 MB L2; "

@@ -58,6 +58,11 @@ SIGNATURES["fp8fq_fake_quant_multi_f32"] = (_c_i, [ctypes.POINTER(TensorDesc), _
 SIGNATURES["fp8fq_bn_quant_add_act_quant_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_i, _c_i, _c_p, _c_f,
                                                          _c_i, _c_i, _c_p, _c_f, _c_i, _c_i, _c_p])
 
+SIGNATURES["fp8fq_bn_act_quant_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_l, _c_l, _c_i, _c_i, _c_p, _c_f, _c_i, _c_i,
+                                                    _c_p])
+SIGNATURES["fp8fq_bn_quant_add_act_quant_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_l, _c_l, _c_i, _c_i, _c_p,
+                                                              _c_f, _c_i, _c_i, _c_p, _c_f, _c_i, _c_i, _c_p])
+
 _lib = None
 
 

@@ -199,7 +199,24 @@ __global__ void prepare_kernel(const float* __restrict__ maxval, const float* __
 // to a 20-float table copy, and batch norm is folded only for the <= 128 rows a tile touches, after the tile's
 // loads have been issued.
 // PRE_AFFINE_PL: PRE_AFFINE when H*W is not a multiple of the vector width (per-lane rows)
-enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2, PRE_AFFINE_G = 3, PRE_BNQ_ADD = 4, PRE_AFFINE_PL = 5, PRE_BNQ_ADD_PL = 6 };
+// PRE_AFFINE_CL / PRE_BNQ_ADD_CL: the same two fusions for channel-innermost memory ([pixels, C]: channels_last
+//               activations -- the layout cuDNN's tensor-core convolutions produce natively -- and Linear outputs):
+//               channel = flat index % C, a 128-bit vector spans 4 consecutive channels, and when C divides the
+//               per-pass stride (1024 elements) every vector of a thread has the SAME 4 channels, so the
+//               batch-norm parameters are loaded once per tile.
+enum { PRE_PLAIN = 0, PRE_AFFINE = 1, PRE_ADD = 2, PRE_AFFINE_G = 3, PRE_BNQ_ADD = 4, PRE_AFFINE_PL = 5, PRE_BNQ_ADD_PL = 6,
+       PRE_AFFINE_CL = 7, PRE_BNQ_ADD_CL = 8 };
+
+template <int PRE>
+struct PreTraits {
+  static constexpr bool kCL = (PRE == PRE_AFFINE_CL || PRE == PRE_BNQ_ADD_CL);
+  static constexpr bool kTail = (PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL || PRE == PRE_BNQ_ADD_CL);
+  static constexpr bool kPerLane = (PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD_PL);
+  static constexpr bool kLocalRows = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL);
+  static constexpr bool kTwoIn = (PRE == PRE_ADD || kTail);
+  static constexpr bool kHasBn = (kLocalRows || kCL || PRE == PRE_AFFINE_G);
+  static constexpr bool kBnAct = kHasBn && !kTail;   // y = Q(act(bn(x)))
+};
 
 struct StreamArgs {
   const float* x;
@@ -216,6 +233,7 @@ struct StreamArgs {
   uint32_t hw, Cbn;
   uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
   FastDiv hw_div, c_div;
+  int cl_same;          // *_CL: Cbn divides kThreads * VEC, i.e. a thread sees the same channels in every vector
 };
 
 struct RegTab {  // K <= 3: everything in registers
@@ -419,7 +437,7 @@ constexpr int kThreads = 256;
 // (same bytes in flight, 16 fewer live registers -> no spills at 5-6 resident CTAs per SM)
 template <int PRE>
 struct StreamUnroll {
-  static constexpr int value = (PRE == PRE_ADD || PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL) ? 2 : 4;
+  static constexpr int value = PreTraits<PRE>::kTwoIn ? 2 : 4;
 };
 
 // Resident CTAs per SM the kernel is compiled for.  Measured (tools/bench_kernels.py, B200, [128,64,112,112]):
@@ -430,17 +448,24 @@ struct StreamMinBlocks {
 #ifdef FQ_MINB
   static constexpr int value = FQ_MINB;
 #else
+  // (the *_CL variants keep the parameters of 4 channels -- up to 16 floats -- live: 5 CTAs/SM = 48 registers)
+#ifndef FQ_MINB_CL
+#define FQ_MINB_CL 5
+#endif
   static constexpr int value =
-      ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE != 1) ? 6 : 5;
+      PreTraits<PRE>::kCL ? FQ_MINB_CL
+      : ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE != 1) ? 6 : 5;
 #endif
 };
 
 template <int KMODE, int PRE, int VEC, bool CODES, int BNM>
 __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) fq_stream_kernel(const StreamArgs a) {
-  constexpr bool kTail = (PRE == PRE_BNQ_ADD || PRE == PRE_BNQ_ADD_PL);
-  constexpr bool kPerLane = (PRE == PRE_AFFINE_PL || PRE == PRE_BNQ_ADD_PL);
-  constexpr bool kLocalRows = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || kTail);
-  constexpr bool kTwoIn = (PRE == PRE_ADD || kTail);
+  constexpr bool kTail = PreTraits<PRE>::kTail;
+  constexpr bool kPerLane = PreTraits<PRE>::kPerLane;
+  constexpr bool kLocalRows = PreTraits<PRE>::kLocalRows;
+  constexpr bool kTwoIn = PreTraits<PRE>::kTwoIn;
+  constexpr bool kCL = PreTraits<PRE>::kCL;
+  constexpr bool kBnAct = PreTraits<PRE>::kBnAct;
   constexpr int kUnroll = StreamUnroll<PRE>::value;
 
   constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
@@ -475,13 +500,42 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
       ch0 = row0 - fdiv(row0, a.c_div) * a.Cbn;
     }
     // 3. math + stores
+    if (kCL) {
+      // channel-innermost: lanes are channels ch .. ch + VEC - 1 (Cbn % VEC == 0, checked by the launcher).  Batch norm
+      // is applied to ALL of the thread's vectors first, in place, so that the parameter registers are dead before
+      // the quantiser's table registers come alive.
+      // One channel's parameters are live at a time (lane k of every vector, then lane k + 1, ...).
+      if (a.cl_same) {       // Cbn divides the pass stride: every vector of this thread has the same channels
+        const uint32_t i32 = (uint32_t)base;
+        const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const BnParams bp = bn_load<BNM>(a, ch + k);
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (ok[u]) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bp);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (!ok[u]) continue;
+          const uint32_t i32 = (uint32_t)(base + (int64_t)u * kThreads * VEC);
+          const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bn_load<BNM>(a, ch + k));
+        }
+      }
+    }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
       const int64_t i = base + (int64_t)u * kThreads * VEC;
       float v[VEC], yv[VEC];
       int32_t cd[VEC];
-      if (kLocalRows) {
+      if (kCL) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = in[u].v[k];
+      } else if (kLocalRows) {
         const uint32_t p = col0 + (uint32_t)(i - tile0);
         if (!kPerLane) {
           uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
@@ -508,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = in[u].v[k];
       }
-      if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) {
+      if (kBnAct) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = apply_act(v[k], a.act);
       } else if (PRE == PRE_ADD) {
@@ -534,13 +588,16 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {
     const int64_t i = nvec_elems + threadIdx.x;
     float v = a.x[i];
-    if (kLocalRows || PRE == PRE_AFFINE_G) {
+    if (kCL) {
+      const uint32_t ch = (uint32_t)i - fdiv((uint32_t)i, a.c_div) * a.Cbn;
+      v = bn_apply<BNM>(v, bn_load<BNM>(a, ch));
+    } else if (kLocalRows || PRE == PRE_AFFINE_G) {
       const uint32_t row = fdiv((uint32_t)i, a.hw_div);
       const uint32_t ch = row - fdiv(row, a.c_div) * a.Cbn;
       v = bn_apply<BNM>(v, bn_load<BNM>(a, ch));
     }
     int32_t cd;
-    if (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) v = apply_act(v, a.act);
+    if (kBnAct) v = apply_act(v, a.act);
     else if (PRE == PRE_ADD) v = apply_act(add_rn(v, a.x2[i]), a.act);
     else if (kTail) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), a.act);
     a.y[i] = kTail ? quant_elem<KMODE, CODES>(v, ctx2, &cd) : quant_elem<KMODE, CODES>(v, ctx, &cd);
@@ -1028,8 +1085,7 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   // fastest with one tile per CTA (6.56 / 6.68 TB/s); the batch-norm variants, which are instruction-issue bound
   // (ncu: 78 % issue slots busy), gain from amortising their longer per-CTA prologue over 4 tiles (5.64 -> 6.16 and
   // 4.97 -> 5.84 TB/s) -- as long as that still leaves >= 2 full waves of CTAs.  FP8FQ_TILES_PER_CTA overrides.
-  constexpr bool kHasBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD ||
-                           PRE == PRE_BNQ_ADD_PL);
+  constexpr bool kHasBn = PreTraits<PRE>::kHasBn;
   static const int tpc_env = [] {
     const char* e = getenv("FP8FQ_TILES_PER_CTA");
     const int v = e ? atoi(e) : 0;
@@ -1045,9 +1101,8 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
 
 template <int PRE, int VEC>
 int launch_stream(const StreamArgs& a, cudaStream_t st) {
-  constexpr bool kHasBn = (PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G || PRE == PRE_BNQ_ADD ||
-                           PRE == PRE_BNQ_ADD_PL);
-  const bool small = a.K <= 3 && ((PRE != PRE_BNQ_ADD && PRE != PRE_BNQ_ADD_PL) || a.K2 <= 3);
+  constexpr bool kHasBn = PreTraits<PRE>::kHasBn;
+  const bool small = a.K <= 3 && (!PreTraits<PRE>::kTail || a.K2 <= 3);
   if (PRE == PRE_PLAIN && a.codes != nullptr)  // the code planes exist for the parity tests of the plain quantiser
     return small ? launch_stream_t<0, PRE_PLAIN, VEC, true, 0>(a, st) : launch_stream_t<1, PRE_PLAIN, VEC, true, 0>(a, st);
   if (kHasBn && a.bn_mode == 1)
@@ -1345,6 +1400,56 @@ static int bn_act_quant_impl(const float* x, const float* residual, float* y, co
   if (tail) return FP8FQ_ERR_UNSUPPORTED;  // caller composes the two unfused kernels instead
   const bool v4 = al && (hw % 4 == 0);
   return v4 ? launch_stream<PRE_AFFINE_G, 4>(a, st) : launch_stream<PRE_AFFINE_G, 1>(a, st);
+}
+
+// channel-innermost twin of bn_act_quant_impl: x is [pixels, Cbn] (channels_last activations, Linear outputs)
+static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* y, const float* bn_scale,
+                                  const float* bn_shift, int64_t pixels, int64_t Cbn, int act, int bn_mode,
+                                  const float* table, float mb, int nb, int sb, const float* table2, float mb2,
+                                  int nb2, int sb2, void* stream) {
+  int M, E, K, K2 = 0;
+  int r = check_format(mb, nb, sb, &M, &E, &K);
+  if (r != FP8FQ_OK) return r;
+  if (table2 != nullptr) {
+    r = check_format(mb2, nb2, sb2, &M, &E, &K2);
+    if (r != FP8FQ_OK) return r;
+  }
+  if (pixels < 0 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1) return FP8FQ_ERR_BAD_ARG;
+  if (Cbn >= (1ll << 31) || pixels >= (1ll << 32) || pixels * Cbn >= (1ll << 32)) return FP8FQ_ERR_UNSUPPORTED;
+  const int64_t n = pixels * Cbn;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr || table == nullptr || bn_scale == nullptr || (bn_mode == 0 && bn_shift == nullptr))
+    return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(x) || !aligned4(y) || (residual && !aligned4(residual))) return FP8FQ_ERR_ALIGNMENT;
+  if (bn_mode == 1 && !aligned16(bn_scale)) return FP8FQ_ERR_ALIGNMENT;
+  StreamArgs a{};
+  a.x = x; a.x2 = residual; a.y = y; a.table = table; a.table2 = table2; a.n = n; a.K = K; a.K2 = K2; a.act = act;
+  a.bn_p[0] = bn_scale; a.bn_p[1] = bn_shift; a.bn_mode = bn_mode;
+  a.Cbn = (uint32_t)Cbn;
+  a.c_div = make_fastdiv((uint32_t)Cbn);
+  const bool v4 = (Cbn % 4 == 0) && aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
+  a.cl_same = ((int64_t)kThreads * (v4 ? 4 : 1)) % Cbn == 0 ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (table2 != nullptr) return v4 ? launch_stream<PRE_BNQ_ADD_CL, 4>(a, st) : launch_stream<PRE_BNQ_ADD_CL, 1>(a, st);
+  return v4 ? launch_stream<PRE_AFFINE_CL, 4>(a, st) : launch_stream<PRE_AFFINE_CL, 1>(a, st);
+}
+
+int fp8fq_bn_act_quant_nhwc_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift,
+                                int64_t pixels, int64_t Cbn, int act, int bn_mode, const float* table,
+                                float mantissa_bits, int n_bits, int sign_bits, void* stream) {
+  return bn_act_quant_nhwc_impl(x, nullptr, y, bn_scale, bn_shift, pixels, Cbn, act, bn_mode, table, mantissa_bits,
+                                n_bits, sign_bits, nullptr, 0.0f, 0, 0, stream);
+}
+
+int fp8fq_bn_quant_add_act_quant_nhwc_f32(const float* x, const float* residual, float* y, const float* bn_scale,
+                                          const float* bn_shift, int64_t pixels, int64_t Cbn, int act, int bn_mode,
+                                          const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
+                                          int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
+                                          int n_bits_outer, int sign_bits_outer, void* stream) {
+  if (residual == nullptr || table_outer == nullptr) return FP8FQ_ERR_BAD_ARG;
+  return bn_act_quant_nhwc_impl(x, residual, y, bn_scale, bn_shift, pixels, Cbn, act, bn_mode, table_inner,
+                                mantissa_bits_inner, n_bits_inner, sign_bits_inner, table_outer,
+                                mantissa_bits_outer, n_bits_outer, sign_bits_outer, stream);
 }
 
 int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,

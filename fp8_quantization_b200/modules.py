@@ -74,6 +74,16 @@ def _sync_batch_norm_train(x, running_mean, running_var, gamma, beta, momentum, 
     return y
 
 
+def _like(t, ref):
+    """``t`` in a layout the kernels address and with the same strides as ``ref`` (the residual of a block may come
+    from a different producer than the features: NCHW images into a channels_last network, a pooling layer, ...)."""
+    t = ops.dense(t)
+    if t.stride() != ref.stride():
+        t = t.contiguous(memory_format=torch.channels_last if ops.is_channels_last(ref) and t.dim() == 4
+                         else torch.contiguous_format)
+    return t
+
+
 def _act_code(act):
     """Kernel activation code for a fusable activation module, or None if it cannot be fused."""
     if act is None:
@@ -226,8 +236,8 @@ class QuantizedActivation(QuantizedModule):
         mgr = self.activation_quantizer
         if self._qa and code is not None and _fusable_manager(mgr) and a.is_cuda:
             q = mgr.quantizer
-            a = a if a.is_contiguous() else a.contiguous()
-            b = b if b.is_contiguous() else b.contiguous()
+            a = ops.dense(a)
+            b = _like(b, a)
             table, _ = q.table_for(a)
             return ops.add_act_quant(a, b, code, table, q._mbits_host, q.n_bits, q.sign_bits)
         out = a + b
@@ -250,8 +260,8 @@ class QuantizedActivation(QuantizedModule):
             res = last.conv_only(h)
             if last._fused_epilogue_ok(res) and residual.is_cuda and residual.shape == res.shape:
                 qi, qo = last.activation_quantizer.quantizer, self.activation_quantizer.quantizer
-                res = res if res.is_contiguous() else res.contiguous()
-                residual = residual if residual.is_contiguous() else residual.contiguous()
+                res = ops.dense(res)
+                residual = _like(residual, res)
                 ti, _ = qi.table_for(res)
                 to, _ = qo.table_for(res)
                 scale, shift, mode = last.folded_bn()
@@ -382,7 +392,7 @@ class BNFusedHijacker(QuantizationHijacker):
         ranges are fixed."""
         if self._fused_epilogue_ok(res):
             q = self.activation_quantizer.quantizer
-            res = res if res.is_contiguous() else res.contiguous()
+            res = ops.dense(res)
             table, _ = q.table_for(res)
             scale, shift, mode = self.folded_bn()
             return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
@@ -420,7 +430,9 @@ class _Conv1dForward:
 
 class _Conv2dForward:
     def run_forward(self, x, weight, bias, offsets=None):
-        return F.conv2d(x.contiguous(), weight.contiguous(), bias=bias, stride=self.stride, padding=self.padding,
+        # (the reference forces NCHW here; a channels_last network -- model.to(memory_format=torch.channels_last) --
+        # keeps its layout so that cuDNN runs its NHWC tensor-core kernels without the transposes around them)
+        return F.conv2d(ops.dense(x), ops.dense(weight), bias=bias, stride=self.stride, padding=self.padding,
                         dilation=self.dilation, groups=self.groups)
 
 
@@ -665,7 +677,8 @@ class QuantizedModel(nn.Module):
             q = mgr.quantizer
             w = m.weight
             if (not isinstance(mgr, QuantizationManager) or not isinstance(q, FPQuantizer) or mgr.estimating()
-                    or not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous()):
+                    or not w.is_cuda or w.dtype != torch.float32
+                    or not (w.is_contiguous() or ops.is_channels_last(w))):
                 continue
             w = w.detach()
             table, C = q.table_for(w)

@@ -26,6 +26,20 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def is_channels_last(t: torch.Tensor) -> bool:
+    """Dense channel-innermost memory ([N, H, W, C] / [N, D, H, W, C]) that is not also plain contiguous."""
+    if t.is_contiguous():
+        return False
+    return ((t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+            or (t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d)))
+
+
+def dense(t: torch.Tensor) -> torch.Tensor:
+    """``t`` itself when its memory is dense in one of the two layouts the kernels address (contiguous, or
+    channels_last -- the layout cuDNN's tensor-core convolutions produce natively); a contiguous copy otherwise."""
+    return t if (t.is_contiguous() or is_channels_last(t)) else t.contiguous()
+
+
 def _require(t: torch.Tensor, name: str):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
@@ -33,11 +47,18 @@ def _require(t: torch.Tensor, name: str):
         raise Fp8fqError(f"{name} must be a CUDA tensor (this engine has no CPU path); got device {t.device}")
     if t.dtype != torch.float32:
         raise Fp8fqError(f"{name} must be float32; got {t.dtype}")
-    if not t.is_contiguous():
-        raise Fp8fqError(f"{name} must be contiguous")
+    if not t.is_contiguous() and not is_channels_last(t):
+        raise Fp8fqError(f"{name} must be contiguous (or dense channels_last)")
     if t.device.index != torch.cuda.current_device():
         raise Fp8fqError(f"{name} lives on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
                          "kernels are launched on the current device's current stream (use torch.cuda.device(...))")
+
+
+def _require_same_layout(a: torch.Tensor, b: torch.Tensor, what: str):
+    if a.shape != b.shape:
+        raise Fp8fqError(f"{what}: shape mismatch")
+    if a.stride() != b.stride():
+        raise Fp8fqError(f"{what}: both tensors must use the same memory layout (strides {a.stride()} vs {b.stride()})")
 
 
 def _opt_ptr(t):
@@ -94,7 +115,7 @@ def set_range_prepare(xmin: torch.Tensor, xmax: torch.Tensor, mantissa_bits: flo
 def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int,
                out: torch.Tensor = None):
     """FPQuantizer.forward (fp8_quantizer.py:91-133).  C == 1: per tensor; else channel = dim 0."""
-    _require(x, "x")
+    _require(x, "x")   # channels_last x: elementwise over the same memory; channel = dim 0 stays the outermost stride
     n = x.numel()
     if out is None:
         out = torch.empty_like(x)
@@ -110,7 +131,7 @@ def fake_quant_codes(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits
     _require(x, "x")
     n = x.numel()
     y = torch.empty_like(x)
-    codes = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    codes = torch.empty_like(x, dtype=torch.int32)
     check(lib().fp8fq_fake_quant_codes_f32(x.data_ptr(), y.data_ptr(), codes.data_ptr(), table.data_ptr(), n, C,
                                            n // C, float(mantissa_bits), int(n_bits), int(sign_bits), _stream()),
           "fp8fq_fake_quant_codes_f32")
@@ -148,14 +169,15 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
     bn_mode 0: (bn_scale, bn_shift) from bn_fold; bn_mode 1: bn_scale = bn_pack(...) (bit-exact ATen arithmetic)."""
     _require(x, "x")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
-    if x.dim() < 2 or x.shape[1] != Cbn:
-        raise Fp8fqError("bn_act_quant: x must be [N, C, ...] with C == len(bn_scale)")
-    hw = 1
-    for d in x.shape[2:]:
-        hw *= d
-    rows = x.shape[0] * Cbn
+    rows, hw = _rows_hw(x, Cbn)
     if out is None:
         out = torch.empty_like(x)
+    if hw == 1 or is_channels_last(x):   # channel-innermost memory: [N, C] Linear outputs, channels_last activations
+        check(lib().fp8fq_bn_act_quant_nhwc_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift),
+                                                x.numel() // Cbn, Cbn, int(act), int(bn_mode), table.data_ptr(),
+                                                float(mantissa_bits), int(n_bits), int(sign_bits), _stream()),
+              "fp8fq_bn_act_quant_nhwc_f32")
+        return out
     check(lib().fp8fq_bn_act_quant_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift), rows,
                                        hw, Cbn, int(act), int(bn_mode), table.data_ptr(), float(mantissa_bits),
                                        int(n_bits), int(sign_bits), _stream()), "fp8fq_bn_act_quant_f32")
@@ -178,12 +200,18 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     Returns None when the fused variant does not cover the shape (caller composes the two kernels)."""
     _require(x, "x")
     _require(residual, "residual")
-    if x.shape != residual.shape:
-        raise Fp8fqError("bn_quant_add_act_quant: shape mismatch")
+    _require_same_layout(x, residual, "bn_quant_add_act_quant")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
     if out is None:
         out = torch.empty_like(x)
+    if hw == 1 or is_channels_last(x):
+        check(lib().fp8fq_bn_quant_add_act_quant_nhwc_f32(
+            x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift),
+            x.numel() // Cbn, Cbn, int(act), int(bn_mode), table_inner.data_ptr(), float(fmt_inner[0]),
+            int(fmt_inner[1]), int(fmt_inner[2]), table_outer.data_ptr(), float(fmt_outer[0]), int(fmt_outer[1]),
+            int(fmt_outer[2]), _stream()), "fp8fq_bn_quant_add_act_quant_nhwc_f32")
+        return out
     code = lib().fp8fq_bn_quant_add_act_quant_f32(
         x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift), rows, hw,
         Cbn, int(act), int(bn_mode), table_inner.data_ptr(), float(fmt_inner[0]), int(fmt_inner[1]),
@@ -212,8 +240,7 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     """models/resnet_quantized.py:43-46 in one pass: Q(act(a + b))."""
     _require(a, "a")
     _require(b, "b")
-    if a.shape != b.shape:
-        raise Fp8fqError("add_act_quant: shape mismatch")
+    _require_same_layout(a, b, "add_act_quant")
     if out is None:
         out = torch.empty_like(a)
     check(lib().fp8fq_add_act_quant_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), int(act),
@@ -227,6 +254,7 @@ def fake_quant_backward(grad_y, x, table, C: int, mantissa_bits: float, n_bits: 
     term and acc[:, 1] the scale term of d/dmaxval."""
     _require(x, "x")
     _require(grad_y, "grad_y")
+    _require_same_layout(x, grad_y, "fake_quant_backward")
     n = x.numel()
     gx = torch.empty_like(x)
     acc = torch.empty(C, 2, dtype=torch.float64, device=x.device)

@@ -198,7 +198,7 @@ class FPQuantizer(QuantizerBase):
 
     # -- the hot path ---------------------------------------------------------------------------------
     def forward(self, x_float):
-        x = x_float if x_float.is_contiguous() else x_float.contiguous()
+        x = ops.dense(x_float)
         if isinstance(self._mantissa_bits, nn.Parameter):  # learnable mantissa width: re-read the value (one .item())
             mb = float(self._mantissa_bits.detach().reshape(-1)[0].item())
             if mb != self._mbits_host:
@@ -411,7 +411,7 @@ class AsymmetricUniformQuantizer(QuantizerBase):
             raise QuantizerNotInitializedError()
         if torch.is_grad_enabled() and x_float.requires_grad:
             raise Fp8fqError("uniform quantiser: forward-only engine; call under torch.no_grad()")
-        x = x_float if x_float.is_contiguous() else x_float.contiguous()
+        x = ops.dense(x_float)
         C = self._table.numel() // 8
         if C != 1 and (x.dim() == 0 or x.shape[0] != C):
             raise Fp8fqError(f"per-channel range has {C} entries but x has shape {tuple(x.shape)}")

@@ -93,7 +93,7 @@ class _MinMaxEstimator(RangeEstimatorBase):
 
     def forward(self, x):
         x = x.detach()
-        x = x if x.is_contiguous() else x.contiguous()
+        x = ops.dense(x)
         if fq_dist.active():
             return self._forward_dp(x)
         cmin, cmax, init = self._state(x)
@@ -133,7 +133,7 @@ class _MinMaxEstimator(RangeEstimatorBase):
     def fused_estimate_prepare(self, x, quantizer):
         """estimator update + set_quant_range + table in ONE launch; installs the result in ``quantizer``."""
         x = x.detach()
-        x = x if x.is_contiguous() else x.contiguous()
+        x = ops.dense(x)
         cmin, cmax, init = self._state(x)
         C = cmin.numel()
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
@@ -211,7 +211,7 @@ class FP_MSE_Estimator(RangeEstimatorBase):
     def forward(self, x):  # :318-369
         qz = self.quantizer
         x = x.detach()
-        x = x if x.is_contiguous() else x.contiguous()
+        x = ops.dense(x)
         mbit_list = [float(qz._mbits_host)]
         if qz.mse_include_mantissa_bits:
             mbit_list = [float(m) for m in range(1, qz.n_bits - qz.sign_bits)]

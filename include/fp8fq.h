@@ -126,6 +126,21 @@ int fp8fq_bn_quant_add_act_quant_f32(const float* x, const float* residual, floa
                                      float mantissa_bits_outer, int n_bits_outer, int sign_bits_outer,
                                      void* stream);
 
+/* Channel-innermost twins of the two fused epilogues above: x, residual, y are [pixels, Cbn] with
+ * channel(i) = i % Cbn -- channels_last ([N, H, W, C] in memory) activations, which is the layout cuDNN's
+ * tensor-core convolutions produce natively (in NCHW it brackets every convolution with two transpose kernels), and
+ * the [N, C] outputs of Linear layers (quantized_folded_bn.py:39-55 for BNQLinear).  Same arithmetic, same
+ * parameters (bn_scale/bn_shift or the packed buffer), same results element for element as the NCHW entry points
+ * on the permuted tensor; 128-bit accesses need Cbn % 4 == 0 and 16-byte aligned pointers (scalar path otherwise). */
+int fp8fq_bn_act_quant_nhwc_f32(const float* x, float* y, const float* bn_scale, const float* bn_shift,
+                                int64_t pixels, int64_t Cbn, int act, int bn_mode, const float* table,
+                                float mantissa_bits, int n_bits, int sign_bits, void* stream);
+int fp8fq_bn_quant_add_act_quant_nhwc_f32(const float* x, const float* residual, float* y, const float* bn_scale,
+                                          const float* bn_shift, int64_t pixels, int64_t Cbn, int act, int bn_mode,
+                                          const float* table_inner, float mantissa_bits_inner, int n_bits_inner,
+                                          int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
+                                          int n_bits_outer, int sign_bits_outer, void* stream);
+
 /* Packed batch-norm parameters for bn_mode 1: [Cbn][4] = {mean, gamma (1 if NULL), rsqrtf(var + eps), beta (0 if NULL)}
  * per channel; `packed` must be 16-byte aligned. */
 int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,

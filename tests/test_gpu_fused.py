@@ -329,3 +329,126 @@ def test_resnet18_m5_ranges_and_logits_vs_reference_golden():
     cos = F.cosine_similarity(logits.cpu().flatten(), ref_logits.flatten(), dim=0).item()
     assert cos > 0.98, cos
     assert F.cosine_similarity(logits.flatten(), logits_unfused.flatten(), dim=0).item() > 0.995
+
+
+# ---- channels_last (channel-innermost) variants -----------------------------------------------------------
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56), (16, 512, 7, 7), (4, 128, 28, 28), (3, 24, 9, 5), (2, 30, 5, 3),
+                                   (2, 1280, 7, 7), (5, 3, 17, 13), (3, 96, 14, 14), (2, 2048, 2, 2)])
+@pytest.mark.parametrize("bn_mode", [0, 1])
+def test_channels_last_epilogues_equal_nchw_bit_for_bit(shape, bn_mode):
+    """The channel-innermost kernels (fp8fq_*_nhwc_f32) on a channels_last tensor give, element for element, the
+    bits the NCHW kernels give on the same logical tensor: C dividing the pass stride (parameters loaded once per
+    tile), C % 4 == 0 otherwise (per-vector channel), C % 4 != 0 (scalar accesses); both batch-norm modes; the
+    BN+act+quant epilogue and the residual-block tail (falls back to the unfused pair where NCHW has no fused form)."""
+    from fp8_quantization_b200 import ops
+
+    torch.manual_seed(31)
+    C = shape[1]
+    x = torch.randn(shape, device=DEV) * 2
+    res = torch.relu(torch.randn(shape, device=DEV))
+    x_cl = x.contiguous(memory_format=torch.channels_last)
+    res_cl = res.contiguous(memory_format=torch.channels_last)
+    assert ops.is_channels_last(x_cl) and not ops.is_channels_last(x)
+    mean, var = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.3
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    if bn_mode == 1:
+        p0, p1 = ops.bn_pack(mean, var, gamma, beta, 1e-5), None
+    else:
+        p0, p1 = ops.bn_fold(mean, var, gamma, beta, 1e-5)
+    for M, act in ((5, 1), (4, 2), (3, 0)):
+        q = _quantizer(M, 3.0)
+        table, _ = q.table_for(x)
+        y = ops.bn_act_quant(x, p0, p1, act, table, float(M), 8, 1, bn_mode=bn_mode)
+        y_cl = ops.bn_act_quant(x_cl, p0, p1, act, table, float(M), 8, 1, bn_mode=bn_mode)
+        assert y_cl.stride() == x_cl.stride()           # the output keeps the layout
+        assert torch.equal(bits(y_cl), bits(y))         # same logical tensor, same bits
+    for (Mi, Mo), act in (((5, 5), 1), ((4, 3), 0)):
+        qi, qo = _quantizer(Mi, 2.7), _quantizer(Mo, 4.1)
+        ti, _ = qi.table_for(x)
+        to, _ = qo.table_for(x)
+        inner = ops.bn_act_quant(x, p0, p1, 0, ti, float(Mi), 8, 1, bn_mode=bn_mode)
+        ref = ops.add_act_quant(inner, res, act, to, float(Mo), 8, 1)
+        y_cl = ops.bn_quant_add_act_quant(x_cl, res_cl, p0, p1, act, ti, (Mi, 8, 1), to, (Mo, 8, 1), bn_mode=bn_mode)
+        assert y_cl is not None and y_cl.stride() == x_cl.stride()
+        assert torch.equal(bits(y_cl), bits(ref))
+    # plain per-tensor / residual-add quantisers are layout agnostic: same memory walk, layout preserved
+    q = _quantizer(5, 2.5)
+    assert torch.equal(bits(q(x_cl)), bits(q(x))) and q(x_cl).stride() == x_cl.stride()
+    table, _ = q.table_for(x)
+    assert torch.equal(bits(ops.add_act_quant(x_cl, res_cl, 1, table, 5.0, 8, 1)),
+                       bits(ops.add_act_quant(x, res, 1, table, 5.0, 8, 1)))
+    if x_cl.stride() != res.stride():
+        with pytest.raises(ops.Fp8fqError):     # mixed layouts are rejected, never silently mis-addressed
+            ops.add_act_quant(x_cl, res, 1, table, 5.0, 8, 1)
+
+
+def test_channels_last_per_channel_weights_and_estimators():
+    """Per-channel weight quantisation and the min/max estimators on channels_last weights ([O, kh, kw, I] in
+    memory): channel = dim 0 stays the outermost stride, so rows are the same sets of values."""
+    import fp8_quantization_b200 as fq
+
+    torch.manual_seed(32)
+    w = torch.randn(64, 32, 3, 3, device=DEV) * 0.1
+    w_cl = w.contiguous(memory_format=torch.channels_last)
+    for M in (5, 3):
+        outs = []
+        for t in (w, w_cl):
+            mgr = fq.QuantizationManager(qmethod=fq.FPQuantizer, init=fq.CurrentMinMaxEstimator, per_channel=True,
+                                         qparams=dict(n_bits=8, mantissa_bits=M, set_maxval=True))
+            y = mgr(t)
+            assert y.stride() == t.stride()
+            outs.append((y, mgr.quantizer.maxval.clone()))
+        assert torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(bits(outs[0][0]), bits(outs[1][0]))
+    y, codes = fq.FPQuantizer(8, mantissa_bits=5, maxval=1.0).quantize_with_codes(w)
+    assert codes.stride() == y.stride()
+
+
+def test_channels_last_resnet18_fused_equals_unfused_and_tracks_nchw():
+    """A channels_last QuantizedResNet (model.to(memory_format=torch.channels_last), NCHW images in): the fused
+    forward is still 23 launches, now through the channel-innermost kernels; the one-launch block tail equals the
+    two-kernel composition bit for bit; ranges and logits track the NCHW network (different cuDNN kernels, so
+    close, not bitwise)."""
+    from torchvision.models import resnet18
+
+    from fp8_quantization_b200 import modules, ops, workloads
+
+    torch.manual_seed(10)
+    net = resnet18()
+    m_nchw = workloads.QuantizedResNet(net, **workloads.readme_quant_params(5)).to(DEV).eval()
+    torch.manual_seed(10)
+    m_cl = workloads.QuantizedResNet(resnet18(), **workloads.readme_quant_params(5)).to(DEV).eval()
+    m_cl = m_cl.to(memory_format=torch.channels_last)
+    for (n0, p0), (n1, p1) in zip(m_nchw.named_parameters(), m_cl.named_parameters()):
+        assert n0 == n1 and torch.equal(p0, p1)
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(4, 3, 224, 224, generator=gen).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for m in (m_nchw, m_cl):
+            workloads.pass_data_for_range_estimation([x], m, True, True, 1)
+            m.fix_ranges()
+        with torch.no_grad():
+            m_cl(x)
+            n0 = ops.launch_count()
+            y_cl = m_cl(x)                       # NCHW images in, channels_last inside
+            assert ops.launch_count() - n0 == 23
+            modules.FUSE_BLOCK_TAIL = False
+            y_cl_pair = m_cl(x)                  # separate BN+quant and add+relu+quant kernels
+            modules.FUSE_BLOCK_TAIL = True
+            assert torch.equal(y_cl, y_cl_pair)
+            y_nchw = m_nchw(x)
+    finally:
+        modules.FUSE_BLOCK_TAIL = True
+        torch.backends.cudnn.allow_tf32 = prev
+    # the two layouts run different cuDNN kernels (summation order): ranges and logits agree closely, not bitwise
+    cos = F.cosine_similarity(y_cl.flatten(), y_nchw.flatten(), dim=0).item()
+    assert cos > 0.995, cos
+    a = [q.maxval.reshape(-1) for q in m_nchw.modules() if isinstance(q, modules.FPQuantizer)]
+    b = [q.maxval.reshape(-1) for q in m_cl.modules() if isinstance(q, modules.FPQuantizer)]
+    for u, v in zip(a, b):
+        if u.numel() > 1:
+            assert torch.equal(u, v)             # weight ranges: pure min/max of identical weights
+        else:
+            assert torch.allclose(u, v, rtol=2e-2)

@@ -14,7 +14,10 @@ from fp8_quantization_b200 import ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda:0")
-PEAK = 6570.3
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except (OSError, ValueError, KeyError):
+    PEAK = 6650.0
 out = {"batch": B, "peak_gbs": PEAK, "sites": []}
 
 
@@ -49,6 +52,10 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
     tb, _ = q.table_for(xs[0])
     tb4, _ = q4.table_for(xs[0])
     rec = {"shape": list(shape), "elems": n, "buffers": nbuf}
+    CL = torch.channels_last
+    xs_cl = [x.contiguous(memory_format=CL) for x in xs[:min(nbuf, 12)]]
+    rs_cl = [r.contiguous(memory_format=CL) for r in rs[:4]]
+    y_cl = torch.empty_like(xs_cl[0])
     for name, bytes_pe, fns in (
         ("plain_M5", 8, [lambda x=x: ops.fake_quant(x, tb, 1, 5.0, 8, 1, out=y) for x in xs]),
         ("plain_M4", 8, [lambda x=x: ops.fake_quant(x, tb4, 1, 4.0, 8, 1, out=y) for x in xs]),
@@ -62,6 +69,13 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
         ("bn_relu_quant_exact", 8, [lambda x=x: ops.bn_act_quant(x, pk, None, 1, tb, 5.0, 8, 1, bn_mode=1, out=y) for x in xs]),
         ("block_tail_exact", 12, [lambda x=x, r=rs[i % len(rs)]: ops.bn_quant_add_act_quant(
             x, r, pk, None, 1, tb, (5.0, 8, 1), tb, (5.0, 8, 1), bn_mode=1, out=y) for i, x in enumerate(xs)]),
+        ("bn_relu_quant_cl", 8, [lambda x=x: ops.bn_act_quant(x, sc, sh, 1, tb, 5.0, 8, 1, out=y_cl) for x in xs_cl]),
+        ("bn_relu_quant_exact_cl", 8, [lambda x=x: ops.bn_act_quant(x, pk, None, 1, tb, 5.0, 8, 1, bn_mode=1, out=y_cl)
+                                       for x in xs_cl]),
+        ("bn_relu6_quant_M4_exact_cl", 8, [lambda x=x: ops.bn_act_quant(x, pk, None, 2, tb4, 4.0, 8, 1, bn_mode=1, out=y_cl)
+                                           for x in xs_cl]),
+        ("block_tail_exact_cl", 12, [lambda x=x, r=rs_cl[i % len(rs_cl)]: ops.bn_quant_add_act_quant(
+            x, r, pk, None, 1, tb, (5.0, 8, 1), tb, (5.0, 8, 1), bn_mode=1, out=y_cl) for i, x in enumerate(xs_cl)]),
         ("torch_copy", 8, [lambda x=x: y.copy_(x) for x in xs]),
     ):
         med, mn = timeit(fns)
@@ -76,7 +90,7 @@ for (C, H) in ((64, 112), (64, 56), (128, 28), (256, 14), (512, 7)):
     med, mn = timeit([lambda x=x: ops.fake_quant_backward(gy, x, tb4, 1, 4.0, 8, 1) for x in xs])
     rec["backward_M4"] = {"us": med * 1e3, "gbs": 12 * n / (med * 1e-3) / 1e9, "frac": 12 * n / (med * 1e-3) / 1e9 / PEAK}
     out["sites"].append(rec)
-    del xs, rs, y, gy
+    del xs, rs, y, gy, xs_cl, rs_cl, y_cl
     torch.cuda.empty_cache()
 
 # weights: all 21 ResNet-18 tensors in one launch vs one launch each
@@ -98,7 +112,7 @@ med, mn = timeit([lambda: [ops.fake_quant(w, t, w.shape[0], 5.0, 8, 1, out=o) fo
 out["weights_21_launches"] = {"us": med * 1e3, "gbs": 8 * nw / (med * 1e-3) / 1e9}
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kernels.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("KERNELS_JSON", "kernels.json")), "w"), indent=1)
 for s in out["sites"]:
     print(s["shape"], " ".join(f"{k}={v['gbs']:.0f}({v['us']:.1f}us)" for k, v in s.items() if isinstance(v, dict)))
 print("weights", out["weights_multi"], out["weights_21_launches"])
