@@ -260,7 +260,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
 // vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
-template <int KMODE, bool CODES, int N>
+template <int KMODE, bool CODES, int N, bool STAB_SHARED = false>
 __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N],
                                           float* s_out = nullptr) {
   if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
@@ -320,11 +320,18 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       }
     }
     const float2* sr = reinterpret_cast<const float2*>(c.stab + off_sr(c.K));
+    if (STAB_SHARED) {  // the table is a shared-memory copy: ld.shared instead of a generic-address load
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sr);
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const float2 p = sr[e[k]];
-      s[k] = p.x;
-      rs[k] = p.y;
+      for (int k = 0; k < N; ++k)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s[k]), "=f"(rs[k]) : "r"(sbase + 8u * (uint32_t)e[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float2 p = sr[e[k]];
+        s[k] = p.x;
+        rs[k] = p.y;
+      }
     }
   }
 #pragma unroll
@@ -360,47 +367,52 @@ __device__ __forceinline__ float quant_elem(float v, const ElemCtx<KMODE>& c, in
   return yo[0];
 }
 
-// Every thread reads the (tiny, L1/L2-resident) channel table itself
-// with uniform loads -- no shared memory, no barrier, so a CTA is a fully independent streaming unit.
-template <int KMODE>
-__device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
+// Fills the element context from a channel table through `ld` (global: uniform __ldg loads -- every thread reads the
+// tiny, L1/L2-resident table itself, no shared memory, no barrier, so a CTA is a fully independent streaming unit;
+// the MSE kernel passes a shared-memory copy).
+template <int KMODE, typename Ld>
+__device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, int K, Ld ld) {
   if (KMODE == 2) {  // uniform table
-    c.hi = __ldg(gtab + U_IMAX);
-    c.lo = __ldg(gtab + U_IMIN);
-    c.guard = __ldg(gtab + U_GUARD);
-    c.rt.s1 = __ldg(gtab + U_SCALE);
-    c.rt.r1 = __ldg(gtab + U_RS);
-    c.rt.t2 = __ldg(gtab + U_ZP);
-    c.rt.t3 = __ldg(gtab + U_SAT);
+    c.hi = ld(tab + U_IMAX);
+    c.lo = ld(tab + U_IMIN);
+    c.guard = ld(tab + U_GUARD);
+    c.rt.s1 = ld(tab + U_SCALE);
+    c.rt.r1 = ld(tab + U_RS);
+    c.rt.t2 = ld(tab + U_ZP);
+    c.rt.t3 = ld(tab + U_SAT);
     c.rt.s2 = c.rt.s3 = c.rt.r2 = c.rt.r3 = 0.0f;
-    c.K = 1; c.stab = gtab; c.base = 0; c.irregular = false; c.ref = 0; c.band = 0;
+    c.K = 1; c.stab = tab; c.base = 0; c.irregular = false; c.ref = 0; c.band = 0;
     return;
   }
-  c.hi = __ldg(gtab + H_HI);
-  c.lo = __ldg(gtab + H_LO);
-  c.guard = __ldg(gtab + H_GUARD);
+  c.hi = ld(tab + H_HI);
+  c.lo = ld(tab + H_LO);
+  c.guard = ld(tab + H_GUARD);
   c.K = K;
-  c.stab = gtab;
+  c.stab = tab;
   if (KMODE == 0) {
     const float never = __int_as_float(0x7fc00000);  // NaN: "a >= never" is false
-    const float* thr = gtab + kHdr;
-    const float* sr = gtab + off_sr(K);
-    c.rt.t2 = K >= 2 ? __ldg(thr + 1) : never;
-    c.rt.t3 = K >= 3 ? __ldg(thr + 2) : never;
-    c.rt.s1 = __ldg(sr + 2); c.rt.r1 = __ldg(sr + 3);
-    c.rt.s2 = K >= 2 ? __ldg(sr + 4) : c.rt.s1; c.rt.r2 = K >= 2 ? __ldg(sr + 5) : c.rt.r1;
-    c.rt.s3 = K >= 3 ? __ldg(sr + 6) : c.rt.s2; c.rt.r3 = K >= 3 ? __ldg(sr + 7) : c.rt.r2;
+    const float* thr = tab + kHdr;
+    const float* sr = tab + off_sr(K);
+    c.rt.t2 = K >= 2 ? ld(thr + 1) : never;
+    c.rt.t3 = K >= 3 ? ld(thr + 2) : never;
+    c.rt.s1 = ld(sr + 2); c.rt.r1 = ld(sr + 3);
+    c.rt.s2 = K >= 2 ? ld(sr + 4) : c.rt.s1; c.rt.r2 = K >= 2 ? ld(sr + 5) : c.rt.r1;
+    c.rt.s3 = K >= 3 ? ld(sr + 6) : c.rt.s2; c.rt.r3 = K >= 3 ? ld(sr + 7) : c.rt.r2;
     c.base = 0;
     c.irregular = false;
     c.ref = 0;
     c.band = 0;
   } else {
-    const uint32_t fl = f2u(__ldg(gtab + H_FLAGS));
-    c.base = f2u(__ldg(gtab + H_BASE));
+    const uint32_t fl = f2u(ld(tab + H_FLAGS));
+    c.base = f2u(ld(tab + H_BASE));
     c.irregular = (fl & FLAG_IRREGULAR) != 0;
-    c.ref = f2u(__ldg(gtab + H_REF));
+    c.ref = f2u(ld(tab + H_REF));
     c.band = fl >> BAND_SHIFT;
   }
+}
+template <int KMODE>
+__device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
+  load_ctx<KMODE>(c, gtab, K, [](const float* p) { return __ldg(p); });
 }
 
 // Per-channel batch-norm parameters of one vector.
@@ -665,6 +677,69 @@ __global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ Ro
       for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
         int32_t cd;
         yr[i] = quant_elem<KMODE, CODES>(xr[i], ctx, &cd);
+        if (CODES) cr[i] = cd;
+      }
+    }
+  }
+}
+
+// Warp-per-work-item variant: one WARP per (tensor, row, 1024-element chunk), all of the lane's (up to 8) 128-bit
+// loads issued before the first is used.  The CTA-per-item kernel above keeps one load in flight per thread and walks
+// a 4096-element chunk in 8 dependent round trips; weight rows are short (ResNet-18: 147 .. 4608 elements,
+// MobileNetV2: 9 .. 1280), so memory-level parallelism has to come from within the thread, and a warp is the unit
+// that matches a row.
+constexpr int kRowsWarpChunk = 1024;
+constexpr int kRowsWarps = 4;
+template <int KMODE, bool CODES>
+__global__ void __launch_bounds__(kRowsWarps * 32) fq_rows_warp_kernel(const __grid_constant__ RowsArgs a) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
+  if (w >= a.nwork) return;
+  int ti = 0;
+  while (ti + 1 < a.count && w >= a.t[ti + 1].work0) ++ti;
+  const RowsTensor& T = a.t[ti];
+  const int64_t lw = w - T.work0;
+  const int64_t row = lw / T.chunks_per_row;
+  const int64_t beg = (lw - row * T.chunks_per_row) * kRowsWarpChunk;
+  const int n = (int)((T.inner - beg < kRowsWarpChunk) ? T.inner - beg : kRowsWarpChunk);  // elements of this item
+  const float* xr = T.x + row * T.inner + beg;
+  float* yr = T.y + row * T.inner + beg;
+  int32_t* cr = CODES ? T.codes + row * T.inner + beg : nullptr;
+  ElemCtx<KMODE> ctx;
+  if (T.vec_ok) {
+    constexpr int kU = kRowsWarpChunk / 128;  // vectors per lane
+    Pack<4> in[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if ((u * 32 + lane) * 4 < n) in[u].load(xr + (u * 32 + lane) * 4);
+    load_ctx_direct<KMODE>(ctx, T.table + row * a.stride, a.K);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = (u * 32 + lane) * 4;
+      if (i >= n) break;
+      Pack<4> out;
+      IPack<4> cd;
+      quant_vec<KMODE, CODES, 4>(in[u].v, ctx, out.v, cd.v);
+      out.store(yr + i);
+      if (CODES) cd.store(cr + i);
+    }
+  } else {
+    load_ctx_direct<KMODE>(ctx, T.table + row * a.stride, a.K);
+    constexpr int kU = 8;  // scalar loads in flight per lane
+    for (int i0 = 0; i0 < n; i0 += 32 * kU) {
+      float v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 32 + lane;
+        v[u] = i < n ? __ldcs(xr + i) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i >= n) break;
+        int32_t cd;
+        yr[i] = quant_elem<KMODE, CODES>(v[u], ctx, &cd);
         if (CODES) cr[i] = cd;
       }
     }
@@ -1070,6 +1145,75 @@ __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, do
   mses[i] = add_rn(mses[i], (float)(acc[i] * inv_count));
 }
 
+// K2b, second version.  What changed against mse_grid_kernel (kept selectable with FP8FQ_MSE_V1=1 for A/B runs):
+//   * candidate tables are staged in shared memory a GROUP at a time (as many as fit in ~40 KB: all 111 for the
+//     8-bit formats with M >= 2), so the candidate loop runs without a barrier per candidate;
+//   * per-warp partial sums go to a [warps][G] shared array (plain stores, fixed summation order) instead of
+//     shared-memory double atomics;
+//   * EPT = 16 elements per thread in registers (4 for short rows) halves the per-candidate overhead per element;
+//   * formats with <= 3 exponent codes (M >= 5) select scales with compares on registers (KMODE 0), the others read
+//     the (s, 1/s) pair with ld.shared;
+//   * x is padded with zeros, not masked: Q(0) = 0 contributes nothing (and a degenerate candidate whose table is
+//     NaN poisons the sum through the real elements already, like the reference).
+constexpr int kMse2Threads = 256;
+template <int KMODE, int EPT>
+__global__ void __launch_bounds__(kMse2Threads) mse_grid_kernel2(const float* __restrict__ x, int64_t inner, int64_t C,
+                                                                  const float* __restrict__ tables, int G, int K,
+                                                                  int gpb, double* __restrict__ acc) {
+  extern __shared__ __align__(16) float s_dyn[];
+  constexpr int kWarps = kMse2Threads / 32;
+  const int stride = table_stride(K);
+  const int strideP = (stride + 3) & ~3;
+  float* s_tab = s_dyn;                       // [gpb][strideP]
+  float* s_part = s_dyn + (size_t)gpb * strideP;  // [kWarps][G]
+  const int64_t c = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * kMse2Threads * EPT;
+  const float* xr = x + c * inner;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float v[EPT];
+#pragma unroll
+  for (int u = 0; u < EPT; ++u) {
+    const int64_t i = beg + (int64_t)u * kMse2Threads + threadIdx.x;
+    v[u] = i < inner ? __ldg(xr + i) : 0.0f;
+  }
+  for (int g0 = 0; g0 < G; g0 += gpb) {
+    const int ng = (G - g0 < gpb) ? G - g0 : gpb;
+    __syncthreads();  // the previous group's tables are no longer read
+    // table of candidate g for channel c lives at tables[(g * C + c) * stride]
+    for (int g = warp; g < ng; g += kWarps) {
+      const float* src = tables + ((int64_t)(g0 + g) * C + c) * stride;
+      for (int j = lane; j < stride; j += 32) s_tab[g * strideP + j] = __ldg(src + j);
+    }
+    __syncthreads();
+    for (int g = 0; g < ng; ++g) {
+      ElemCtx<KMODE> ctx;
+      load_ctx<KMODE>(ctx, s_tab + g * strideP, K, [](const float* p) { return *p; });
+      float err = 0.0f;
+#pragma unroll
+      for (int u = 0; u < EPT; u += 4) {
+        float vi[4] = {v[u], v[u + 1], v[u + 2], v[u + 3]}, yo[4];
+        int32_t cd[4];
+        quant_vec<KMODE, false, 4, true>(vi, ctx, yo, cd);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d = sub_rn(vi[k], yo[k]);
+          err = fmaf(d, d, err);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+      if (lane == 0) s_part[warp * G + g0 + g] = err;
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += kMse2Threads) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += (double)s_part[w * G + g];
+    atomicAdd(&acc[(int64_t)g * C + c], t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -1122,6 +1266,12 @@ bool setup_affine(StreamArgs& a, int64_t hw, int64_t Cbn) {
   const int64_t max_rows = 2 + 4095 / hw;  // rows a tile of <= 4096 elements can advance: one channel wrap at most
   const bool exact = (uint64_t)(hw + 4096) * (uint64_t)hw < (1ull << 32);  // umulhi(p, hw_rcp) == p / hw
   return hw > 1 && exact && max_rows <= Cbn;
+}
+
+template <int KMODE, bool CODES>
+void launch_rows_t(const RowsArgs& a, bool warp_items, int64_t grid, int threads, cudaStream_t st) {
+  if (warp_items) launch_kernel(fq_rows_warp_kernel<KMODE, CODES>, dim3((unsigned)grid), dim3(kRowsWarps * 32), 0, st, a);
+  else launch_kernel(fq_rows_kernel<KMODE, CODES>, dim3((unsigned)grid), dim3(threads), 0, st, a);
 }
 
 int check_format(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
@@ -1197,11 +1347,13 @@ int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C,
 
 static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, int K, cudaStream_t st,
                        bool uniform = false) {
+  // FP8FQ_ROWS_CTA=1 selects the older CTA-per-item kernel (kept for A/B measurements)
+  static const bool cta_items = [] { const char* e = getenv("FP8FQ_ROWS_CTA"); return e && e[0] == '1'; }();
   RowsArgs a{};
   a.count = count;
   a.K = K;
   a.stride = uniform ? kUStride : table_stride(K);
-  a.chunk = 4096;
+  a.chunk = cta_items ? 4096 : kRowsWarpChunk;
   int64_t work = 0, max_inner = 0;
   for (int i = 0; i < count; ++i) {
     RowsTensor& t = a.t[i];
@@ -1214,18 +1366,24 @@ static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, i
     if (d[i].inner > max_inner) max_inner = d[i].inner;
   }
   a.nwork = work;
-  int64_t grid = (int64_t)sm_count() * 16;
-  if (grid > work) grid = work;
+  int64_t grid;
+  if (cta_items) {
+    grid = (int64_t)sm_count() * 16;
+    if (grid > work) grid = work;
+  } else {
+    grid = (work + kRowsWarps - 1) / kRowsWarps;
+    if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
+  }
   const int threads = max_inner >= 512 ? 128 : (max_inner >= 128 ? 64 : 32);
   const bool codes = codes0 != nullptr;
   if (uniform) {
-    launch_kernel(fq_rows_kernel<2, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+    launch_rows_t<2, false>(a, !cta_items, grid, threads, st);
   } else if (K <= 3) {
-    if (codes) launch_kernel(fq_rows_kernel<0, true>, dim3((unsigned)grid), dim3(threads), 0, st, a);
-    else launch_kernel(fq_rows_kernel<0, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+    if (codes) launch_rows_t<0, true>(a, !cta_items, grid, threads, st);
+    else launch_rows_t<0, false>(a, !cta_items, grid, threads, st);
   } else {
-    if (codes) launch_kernel(fq_rows_kernel<1, true>, dim3((unsigned)grid), dim3(threads), 0, st, a);
-    else launch_kernel(fq_rows_kernel<1, false>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+    if (codes) launch_rows_t<1, true>(a, !cta_items, grid, threads, st);
+    else launch_rows_t<1, false>(a, !cta_items, grid, threads, st);
   }
   return launch_status();
 }
@@ -1590,13 +1748,41 @@ int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, cons
     cudaError_t ce = cudaMemsetAsync(acc, 0, sizeof(double) * G * C, st);
     if (ce != cudaSuccess) return (int)ce;
     const int stride = table_stride(K);
-    const size_t smem = sizeof(float) * 2 * ((stride + 3) & ~3) + sizeof(double) * G;
-    const int64_t chunks = (inner + (int64_t)kMseThreads * kMseEpt - 1) / ((int64_t)kMseThreads * kMseEpt);
-    if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
-    dim3 gdim((unsigned)chunks, (unsigned)C);
-    mse_grid_kernel<<<gdim, kMseThreads, smem, st>>>(x, inner, C, tables, G, K, acc);
-    r = launch_status();
-    if (r != FP8FQ_OK) return r;
+    static const bool mse_v1 = [] { const char* e = getenv("FP8FQ_MSE_V1"); return e && e[0] == '1'; }();
+    if (mse_v1) {
+      const size_t smem = sizeof(float) * 2 * ((stride + 3) & ~3) + sizeof(double) * G;
+      const int64_t chunks = (inner + (int64_t)kMseThreads * kMseEpt - 1) / ((int64_t)kMseThreads * kMseEpt);
+      if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
+      dim3 gdim((unsigned)chunks, (unsigned)C);
+      mse_grid_kernel<<<gdim, kMseThreads, smem, st>>>(x, inner, C, tables, G, K, acc);
+      r = launch_status();
+      if (r != FP8FQ_OK) return r;
+    } else {
+      // candidates are processed in slices of <= 1024 so that the [warps][G] partial sums fit in shared memory
+      const int strideP = (stride + 3) & ~3;
+      const int ept = inner > 1024 ? 16 : 4;
+      const int64_t chunks = (inner + (int64_t)kMse2Threads * ept - 1) / ((int64_t)kMse2Threads * ept);
+      if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
+      dim3 gdim((unsigned)chunks, (unsigned)C);
+      for (int64_t gs = 0; gs < G; gs += 1024) {
+        const int Gs = (int)((G - gs < 1024) ? G - gs : 1024);
+        const size_t part_bytes = sizeof(float) * (kMse2Threads / 32) * (size_t)Gs;
+        int gpb = (int)((48 * 1024 - part_bytes) / (sizeof(float) * strideP));   // >= 9: strideP <= 392 floats
+        if (gpb > Gs) gpb = Gs;
+        const size_t smem = sizeof(float) * (size_t)gpb * strideP + part_bytes;
+        const float* tb = tables + gs * C * stride;
+        double* ac = acc + gs * C;
+        if (K <= 3) {
+          if (ept == 16) mse_grid_kernel2<0, 16><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+          else mse_grid_kernel2<0, 4><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        } else {
+          if (ept == 16) mse_grid_kernel2<1, 16><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+          else mse_grid_kernel2<1, 4><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        }
+        r = launch_status();
+        if (r != FP8FQ_OK) return r;
+      }
+    }
     const int64_t GC = G * C;
     mse_finish_kernel<<<(unsigned)((GC + 127) / 128), 128, 0, st>>>(acc, GC, 1.0 / (double)inner, mses + m * GC);
     r = launch_status();

@@ -35,4 +35,4 @@ run("act_64x64x56x56_fixedM", torch.relu(torch.randn(64, 64, 56, 56, device=dev)
 run("weight_128x64x3x3_sweep", torch.randn(128, 64, 3, 3, device=dev), True, True)
 run("weight_512x512x3x3_sweep", torch.randn(512, 512, 3, 3, device=dev), True, True)
 print(json.dumps(out, indent=1))
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "mse.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("MSE_JSON", "mse.json")), "w"), indent=1)
