@@ -476,9 +476,9 @@ def main():
         achieved = st["stream_bytes"] / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json"))).get(
-                "fq_stream_kernel_dram_bytes_per_launch")
-        except (OSError, ValueError):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))["by_memory_format"][
+                args.memory_format]["fq_stream_kernel_dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": "fq_stream_kernel (fused BN/add + act + FP8 fake-quant, per-tensor)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

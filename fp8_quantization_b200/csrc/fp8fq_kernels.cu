@@ -9,8 +9,10 @@
 //                         (range_estimators.py:61-125)
 //   mse_grid_kernel       K2b: FP_MSE_Estimator's candidate loop (range_estimators.py:337-347)
 //
-// All HBM-bound kernels use 128-bit coalesced global accesses, UNROLL independent loads in flight per
-// thread, tables staged in shared memory / registers, and persistent grids sized to SMs x occupancy.
+//   fq_backward_kernel    STE backward (autograd through fp8_quantizer.py:112-132)
+//
+// All HBM-bound kernels use 128-bit coalesced global accesses with several independent loads in flight per thread,
+// quantiser tables in registers (read with uniform loads), and short-lived one-tile CTAs (see fq_stream_kernel).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -628,7 +630,7 @@ struct RowsTensor {
   int32_t* codes;
   const float* table;
   int64_t C, inner;
-  int64_t chunks_per_row;   // ceil(inner / chunk)
+  int64_t chunks_per_row;   // ceil(inner / kRowsWarpChunk)
   int64_t work0;            // first work item of this tensor
   int vec_ok;               // inner % 4 == 0 and pointers 16B aligned
 };
@@ -637,61 +639,21 @@ struct RowsArgs {
   RowsTensor t[kMaxMulti];
   int count;
   int64_t nwork;
-  int64_t chunk;            // elements per work item (multiple of 4)
   int K;
   int stride;               // floats per channel table
 };
 
-// One CTA per (tensor, row, chunk) work item; the row's table is staged in shared memory.  Several weight
-// tensors of the same format share one launch (a model's 21..53 weight tensors are each far too small to
-// fill the GPU or to amortise a launch on their own).
-template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(128) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
-  pdl_prologue();
-  const int stride = a.stride;
-  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
-    int ti = 0;
-    while (ti + 1 < a.count && w >= a.t[ti + 1].work0) ++ti;
-    const RowsTensor& T = a.t[ti];
-    const int64_t lw = w - T.work0;
-    const int64_t row = lw / T.chunks_per_row;
-    const int64_t ck = lw - row * T.chunks_per_row;
-    const int64_t beg = ck * a.chunk;
-    const int64_t end = (beg + a.chunk < T.inner) ? beg + a.chunk : T.inner;
-    const float* xr = T.x + row * T.inner;
-    float* yr = T.y + row * T.inner;
-    int32_t* cr = CODES ? T.codes + row * T.inner : nullptr;
-    ElemCtx<KMODE> ctx;
-    load_ctx_direct<KMODE>(ctx, T.table + row * stride, a.K);  // uniform loads of the row's table, no barrier
-    if (T.vec_ok) {
-      // (batching 4 loads per thread here measured slower: 46.6 vs 38.3 us for ResNet-18's 21 tensors)
-      for (int64_t i = beg + (int64_t)threadIdx.x * 4; i < end; i += (int64_t)blockDim.x * 4) {
-        Pack<4> in, out;
-        IPack<4> cd;
-        in.load(xr + i);
-        quant_vec<KMODE, CODES, 4>(in.v, ctx, out.v, cd.v);
-        out.store(yr + i);
-        if (CODES) cd.store(cr + i);
-      }
-    } else {
-      for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-        int32_t cd;
-        yr[i] = quant_elem<KMODE, CODES>(xr[i], ctx, &cd);
-        if (CODES) cr[i] = cd;
-      }
-    }
-  }
-}
-
-// Warp-per-work-item variant: one WARP per (tensor, row, 1024-element chunk), all of the lane's (up to 8) 128-bit
-// loads issued before the first is used.  The CTA-per-item kernel above keeps one load in flight per thread and walks
-// a 4096-element chunk in 8 dependent round trips; weight rows are short (ResNet-18: 147 .. 4608 elements,
-// MobileNetV2: 9 .. 1280), so memory-level parallelism has to come from within the thread, and a warp is the unit
-// that matches a row.
+// One WARP per (tensor, row, 1024-element chunk) work item, all of the lane's (up to 8) 128-bit loads issued before
+// the first is used.  Several weight tensors of the same format share one launch (a model's 21..53 weight tensors
+// are each far too small to fill the GPU or to amortise a launch on their own).  Weight rows are short (ResNet-18:
+// 147 .. 4608 elements, MobileNetV2: 9 .. 1280), so memory-level parallelism has to come from within the thread, and
+// a warp is the unit that matches a row.  Measured on B200 (tools/bench_kernels.py, ResNet-18's 21 tensors, 93 MB,
+// L2 flushed): 20.2 us = 4.6 TB/s; the earlier CTA-per-(row, 4096-chunk) kernel with one load in flight per thread
+// took 27.0 us.
 constexpr int kRowsWarpChunk = 1024;
 constexpr int kRowsWarps = 4;
 template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(kRowsWarps * 32) fq_rows_warp_kernel(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__(kRowsWarps * 32) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
@@ -1082,62 +1044,8 @@ __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b: MSE grid.  grid = (chunks, C).  Each CTA keeps its slice of one channel row in registers and
-// sweeps the G candidate tables of the current mantissa width.
+// K2b: MSE grid (kernel below mse_finish_kernel)
 // ------------------------------------------------------------------------------------------------
-constexpr int kMseThreads = 256;
-constexpr int kMseEpt = 8;  // elements per thread
-
-__global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __restrict__ x, int64_t inner,
-                                                               int64_t C, const float* __restrict__ tables,
-                                                               int64_t G, int K, double* __restrict__ acc) {
-  extern __shared__ __align__(16) float s_dyn[];
-  const int stride = table_stride(K);
-  float* s_tab = s_dyn;                       // 2 * stride (double buffered)
-  double* s_sum = reinterpret_cast<double*>(s_dyn + 2 * ((stride + 3) & ~3));  // [G]
-  const int64_t c = blockIdx.y;
-  const int64_t beg = (int64_t)blockIdx.x * kMseThreads * kMseEpt;
-  const float* xr = x + c * inner;
-  float v[kMseEpt];
-  bool ok[kMseEpt];
-#pragma unroll
-  for (int u = 0; u < kMseEpt; ++u) {
-    const int64_t i = beg + (int64_t)u * kMseThreads + threadIdx.x;
-    ok[u] = i < inner;
-    v[u] = ok[u] ? __ldg(xr + i) : 0.0f;
-  }
-  for (int g = threadIdx.x; g < G; g += kMseThreads) s_sum[g] = 0.0;
-  // table of candidate g for channel c lives at tables[(g * C + c) * stride]
-  for (int i = threadIdx.x; i < stride; i += kMseThreads) s_tab[i] = tables[(0 * C + c) * stride + i];
-  __syncthreads();
-  for (int64_t g = 0; g < G; ++g) {
-    float* cur = s_tab + (g & 1) * ((stride + 3) & ~3);
-    float* nxt = s_tab + ((g + 1) & 1) * ((stride + 3) & ~3);
-    if (g + 1 < G)
-      for (int i = threadIdx.x; i < stride; i += kMseThreads) nxt[i] = tables[((g + 1) * C + c) * stride + i];
-    ElemCtx<1> ctx;
-    ctx.hi = cur[H_HI]; ctx.lo = cur[H_LO]; ctx.guard = cur[H_GUARD]; ctx.K = K;
-    ctx.base = f2u(cur[H_BASE]);
-    ctx.irregular = (f2u(cur[H_FLAGS]) & FLAG_IRREGULAR) != 0;
-    ctx.ref = f2u(cur[H_REF]);
-    ctx.band = f2u(cur[H_FLAGS]) >> BAND_SHIFT;
-    ctx.stab = cur;
-    float err = 0.0f;
-#pragma unroll
-    for (int u = 0; u < kMseEpt; ++u) {
-      int32_t cd;
-      const float y = quant_elem<1, false>(v[u], ctx, &cd);
-      const float d = sub_rn(v[u], y);
-      if (ok[u]) err = add_rn(err, mul_rn(d, d));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[g], (double)err);
-    __syncthreads();
-  }
-  for (int g = threadIdx.x; g < G; g += kMseThreads) atomicAdd(&acc[g * C + c], s_sum[g]);
-}
-
 __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, double inv_count,
                                   float* __restrict__ mses) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1145,35 +1053,37 @@ __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, do
   mses[i] = add_rn(mses[i], (float)(acc[i] * inv_count));
 }
 
-// K2b, second version.  What changed against mse_grid_kernel (kept selectable with FP8FQ_MSE_V1=1 for A/B runs):
+// K2b: MSE grid.  grid = (chunks, C).  Each CTA keeps its slice of one channel row in registers (EPT = 16 elements
+// per thread, 4 for short rows) and sweeps the G candidate tables of the current mantissa width:
 //   * candidate tables are staged in shared memory a GROUP at a time (as many as fit in ~40 KB: all 111 for the
 //     8-bit formats with M >= 2), so the candidate loop runs without a barrier per candidate;
-//   * per-warp partial sums go to a [warps][G] shared array (plain stores, fixed summation order) instead of
-//     shared-memory double atomics;
-//   * EPT = 16 elements per thread in registers (4 for short rows) halves the per-candidate overhead per element;
+//   * per-warp partial sums go to a [warps][G] shared array (plain stores, fixed summation order), then one double
+//     atomicAdd per (CTA, candidate) into the global accumulators;
 //   * formats with <= 3 exponent codes (M >= 5) select scales with compares on registers (KMODE 0), the others read
 //     the (s, 1/s) pair with ld.shared;
 //   * x is padded with zeros, not masked: Q(0) = 0 contributes nothing (and a degenerate candidate whose table is
 //     NaN poisons the sum through the real elements already, like the reference).
-constexpr int kMse2Threads = 256;
+// Measured on B200 (tools/bench_mse.py): 1.33 T candidate evaluations/s on [64,64,56,56] x 666 candidates; the first
+// version (table double-buffered per candidate behind a barrier, 8 elements per thread, shared double atomics) 0.75 T.
+constexpr int kMseThreads = 256;
 template <int KMODE, int EPT>
-__global__ void __launch_bounds__(kMse2Threads) mse_grid_kernel2(const float* __restrict__ x, int64_t inner, int64_t C,
+__global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __restrict__ x, int64_t inner, int64_t C,
                                                                   const float* __restrict__ tables, int G, int K,
                                                                   int gpb, double* __restrict__ acc) {
   extern __shared__ __align__(16) float s_dyn[];
-  constexpr int kWarps = kMse2Threads / 32;
+  constexpr int kWarps = kMseThreads / 32;
   const int stride = table_stride(K);
   const int strideP = (stride + 3) & ~3;
   float* s_tab = s_dyn;                       // [gpb][strideP]
   float* s_part = s_dyn + (size_t)gpb * strideP;  // [kWarps][G]
   const int64_t c = blockIdx.y;
-  const int64_t beg = (int64_t)blockIdx.x * kMse2Threads * EPT;
+  const int64_t beg = (int64_t)blockIdx.x * kMseThreads * EPT;
   const float* xr = x + c * inner;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float v[EPT];
 #pragma unroll
   for (int u = 0; u < EPT; ++u) {
-    const int64_t i = beg + (int64_t)u * kMse2Threads + threadIdx.x;
+    const int64_t i = beg + (int64_t)u * kMseThreads + threadIdx.x;
     v[u] = i < inner ? __ldg(xr + i) : 0.0f;
   }
   for (int g0 = 0; g0 < G; g0 += gpb) {
@@ -1206,7 +1116,7 @@ __global__ void __launch_bounds__(kMse2Threads) mse_grid_kernel2(const float* __
     }
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += kMse2Threads) {
+  for (int g = threadIdx.x; g < G; g += kMseThreads) {
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) t += (double)s_part[w * G + g];
@@ -1266,12 +1176,6 @@ bool setup_affine(StreamArgs& a, int64_t hw, int64_t Cbn) {
   const int64_t max_rows = 2 + 4095 / hw;  // rows a tile of <= 4096 elements can advance: one channel wrap at most
   const bool exact = (uint64_t)(hw + 4096) * (uint64_t)hw < (1ull << 32);  // umulhi(p, hw_rcp) == p / hw
   return hw > 1 && exact && max_rows <= Cbn;
-}
-
-template <int KMODE, bool CODES>
-void launch_rows_t(const RowsArgs& a, bool warp_items, int64_t grid, int threads, cudaStream_t st) {
-  if (warp_items) launch_kernel(fq_rows_warp_kernel<KMODE, CODES>, dim3((unsigned)grid), dim3(kRowsWarps * 32), 0, st, a);
-  else launch_kernel(fq_rows_kernel<KMODE, CODES>, dim3((unsigned)grid), dim3(threads), 0, st, a);
 }
 
 int check_format(float mantissa_bits, int n_bits, int sign_bits, int* M, int* E, int* K) {
@@ -1347,43 +1251,33 @@ int fp8fq_set_range_prepare_f32(const float* xmin, const float* xmax, int64_t C,
 
 static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, int K, cudaStream_t st,
                        bool uniform = false) {
-  // FP8FQ_ROWS_CTA=1 selects the older CTA-per-item kernel (kept for A/B measurements)
-  static const bool cta_items = [] { const char* e = getenv("FP8FQ_ROWS_CTA"); return e && e[0] == '1'; }();
   RowsArgs a{};
   a.count = count;
   a.K = K;
   a.stride = uniform ? kUStride : table_stride(K);
-  a.chunk = cta_items ? 4096 : kRowsWarpChunk;
-  int64_t work = 0, max_inner = 0;
+  int64_t work = 0;
   for (int i = 0; i < count; ++i) {
     RowsTensor& t = a.t[i];
     t.x = d[i].x; t.y = d[i].y; t.table = d[i].table; t.C = d[i].C; t.inner = d[i].inner;
     t.codes = i == 0 ? codes0 : nullptr;
     t.vec_ok = (d[i].inner % 4 == 0) && aligned16(d[i].x) && aligned16(d[i].y) && (t.codes == nullptr || aligned16(t.codes));
-    t.chunks_per_row = (d[i].inner + a.chunk - 1) / a.chunk;
+    t.chunks_per_row = (d[i].inner + kRowsWarpChunk - 1) / kRowsWarpChunk;
     t.work0 = work;
     work += d[i].C * t.chunks_per_row;
-    if (d[i].inner > max_inner) max_inner = d[i].inner;
   }
   a.nwork = work;
-  int64_t grid;
-  if (cta_items) {
-    grid = (int64_t)sm_count() * 16;
-    if (grid > work) grid = work;
-  } else {
-    grid = (work + kRowsWarps - 1) / kRowsWarps;
-    if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
-  }
-  const int threads = max_inner >= 512 ? 128 : (max_inner >= 128 ? 64 : 32);
+  const int64_t grid = (work + kRowsWarps - 1) / kRowsWarps;
+  if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
+  const dim3 g((unsigned)grid), b(kRowsWarps * 32);
   const bool codes = codes0 != nullptr;
   if (uniform) {
-    launch_rows_t<2, false>(a, !cta_items, grid, threads, st);
+    launch_kernel(fq_rows_kernel<2, false>, g, b, 0, st, a);
   } else if (K <= 3) {
-    if (codes) launch_rows_t<0, true>(a, !cta_items, grid, threads, st);
-    else launch_rows_t<0, false>(a, !cta_items, grid, threads, st);
+    if (codes) launch_kernel(fq_rows_kernel<0, true>, g, b, 0, st, a);
+    else launch_kernel(fq_rows_kernel<0, false>, g, b, 0, st, a);
   } else {
-    if (codes) launch_rows_t<1, true>(a, !cta_items, grid, threads, st);
-    else launch_rows_t<1, false>(a, !cta_items, grid, threads, st);
+    if (codes) launch_kernel(fq_rows_kernel<1, true>, g, b, 0, st, a);
+    else launch_kernel(fq_rows_kernel<1, false>, g, b, 0, st, a);
   }
   return launch_status();
 }
@@ -1748,40 +1642,29 @@ int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, cons
     cudaError_t ce = cudaMemsetAsync(acc, 0, sizeof(double) * G * C, st);
     if (ce != cudaSuccess) return (int)ce;
     const int stride = table_stride(K);
-    static const bool mse_v1 = [] { const char* e = getenv("FP8FQ_MSE_V1"); return e && e[0] == '1'; }();
-    if (mse_v1) {
-      const size_t smem = sizeof(float) * 2 * ((stride + 3) & ~3) + sizeof(double) * G;
-      const int64_t chunks = (inner + (int64_t)kMseThreads * kMseEpt - 1) / ((int64_t)kMseThreads * kMseEpt);
-      if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
-      dim3 gdim((unsigned)chunks, (unsigned)C);
-      mse_grid_kernel<<<gdim, kMseThreads, smem, st>>>(x, inner, C, tables, G, K, acc);
+    // candidates are processed in slices of <= 1024 so that the [warps][G] partial sums fit in shared memory
+    const int strideP = (stride + 3) & ~3;
+    const int ept = inner > 1024 ? 16 : 4;
+    const int64_t chunks = (inner + (int64_t)kMseThreads * ept - 1) / ((int64_t)kMseThreads * ept);
+    if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
+    dim3 gdim((unsigned)chunks, (unsigned)C);
+    for (int64_t gs = 0; gs < G; gs += 1024) {
+      const int Gs = (int)((G - gs < 1024) ? G - gs : 1024);
+      const size_t part_bytes = sizeof(float) * (kMseThreads / 32) * (size_t)Gs;
+      int gpb = (int)((48 * 1024 - part_bytes) / (sizeof(float) * strideP));   // >= 9: strideP <= 392 floats
+      if (gpb > Gs) gpb = Gs;
+      const size_t smem = sizeof(float) * (size_t)gpb * strideP + part_bytes;
+      const float* tb = tables + gs * C * stride;
+      double* ac = acc + gs * C;
+      if (K <= 3) {
+        if (ept == 16) mse_grid_kernel<0, 16><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        else mse_grid_kernel<0, 4><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+      } else {
+        if (ept == 16) mse_grid_kernel<1, 16><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        else mse_grid_kernel<1, 4><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+      }
       r = launch_status();
       if (r != FP8FQ_OK) return r;
-    } else {
-      // candidates are processed in slices of <= 1024 so that the [warps][G] partial sums fit in shared memory
-      const int strideP = (stride + 3) & ~3;
-      const int ept = inner > 1024 ? 16 : 4;
-      const int64_t chunks = (inner + (int64_t)kMse2Threads * ept - 1) / ((int64_t)kMse2Threads * ept);
-      if (chunks > 2147483647ll) return FP8FQ_ERR_UNSUPPORTED;
-      dim3 gdim((unsigned)chunks, (unsigned)C);
-      for (int64_t gs = 0; gs < G; gs += 1024) {
-        const int Gs = (int)((G - gs < 1024) ? G - gs : 1024);
-        const size_t part_bytes = sizeof(float) * (kMse2Threads / 32) * (size_t)Gs;
-        int gpb = (int)((48 * 1024 - part_bytes) / (sizeof(float) * strideP));   // >= 9: strideP <= 392 floats
-        if (gpb > Gs) gpb = Gs;
-        const size_t smem = sizeof(float) * (size_t)gpb * strideP + part_bytes;
-        const float* tb = tables + gs * C * stride;
-        double* ac = acc + gs * C;
-        if (K <= 3) {
-          if (ept == 16) mse_grid_kernel2<0, 16><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-          else mse_grid_kernel2<0, 4><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-        } else {
-          if (ept == 16) mse_grid_kernel2<1, 16><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-          else mse_grid_kernel2<1, 4><<<gdim, kMse2Threads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-        }
-        r = launch_status();
-        if (r != FP8FQ_OK) return r;
-      }
     }
     const int64_t GC = G * C;
     mse_finish_kernel<<<(unsigned)((GC + 127) / 128), 128, 0, st>>>(acc, GC, 1.0 / (double)inner, mses + m * GC);
