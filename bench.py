@@ -602,100 +602,71 @@ def main():
         e2e["host_link_bound_ms_per_step"] = bound_ms
         e2e["frac_of_host_link_bound"] = bound_ms / e2e["ms_per_step"]
         del hp_a, hp_b, dp_a, dp_b
+        # the C-ABI host-buffer entry point itself (fp8fq_fake_quant_host_f32: what a caller without device memory
+        # binds): one per-tensor E2M5 fake-quant of a page-locked 2^27-element host tensor, H2D + kernel + D2H inside
+        nh = 1 << 27
+        hx, hy = torch.randn(nh).pin_memory(), torch.empty(nh).pin_memory()
+        mvh = torch.tensor([3.0])
+        ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # warm-up: allocates the pipeline's buffers
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # synchronises before returning
+            dth = time.perf_counter() - t0
+            best = dth if best is None else min(best, dth)
+        e2e["c_abi_host_call"] = {"entry": "fp8fq_fake_quant_host_f32", "elems": nh, "ms": best * 1e3,
+                                  "value": nh / best / 1e9, "unit": UNIT, "h2d_bytes": nh * 4, "d2h_bytes": nh * 4,
+                                  "frac_of_host_link_bound": (nh * 4 / (link["bidirectional_each_gbs"] * 1e9)) / best}
+        del hx, hy
 
     # ---- whole-model extras: quantised ResNet-18 validate forward img/s (convs = cuDNN, TF32 default) --------
     model_info = None
     if not args.no_model:
         with torch.no_grad():
-            static_x = x_img.clone()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(3):
-                    model(static_x)
-            torch.cuda.current_stream().wait_stream(s)
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                static_logits = model(static_x)
+            # public API: workloads.GraphedForward = the validate forward as one CUDA graph
+            gf = workloads.GraphedForward(model, x_img)
             for _ in range(3):
-                g2.replay()
+                gf.replay()
             barrier()
             m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             iters = max(5, min(args.steps, 20))
             m0.record()
             for _ in range(iters):
-                g2.replay()
+                gf.replay()
             m1.record()
             barrier()
             mms = m0.elapsed_time(m1) / iters
-            # e2e: images from pinned host memory, logits back to the host, every step.  Double-buffered: the H2D
-            # copy of batch k+1 (copy stream) overlaps the forward of batch k; logits leave on a third stream.
+            ref_logits = gf.static_out.clone()
+            # e2e: images from pinned host memory, logits back to the host, every step (GraphedForward.run_pipelined:
+            # the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the forward of batch k)
             h_img = x_img.cpu().pin_memory()
-            cur = torch.cuda.current_stream()
-            s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-            stage = [torch.empty_like(static_x) for _ in range(2)]
-            d_log = [torch.empty_like(static_logits) for _ in range(2)]
-            h_log = [torch.empty(static_logits.shape).pin_memory() for _ in range(2)]
-            ev_in = [torch.cuda.Event() for _ in range(2)]
-            ev_free = [torch.cuda.Event() for _ in range(2)]
-            ev_out = [torch.cuda.Event() for _ in range(2)]
-            ev_host = [torch.cuda.Event() for _ in range(2)]
-
-            def e2e_forward(it):
-                k = it & 1
-                with torch.cuda.stream(s_h2d):
-                    if it >= 2:
-                        s_h2d.wait_event(ev_free[k])
-                    stage[k].copy_(h_img, non_blocking=True)
-                    ev_in[k].record(s_h2d)
-                cur.wait_event(ev_in[k])
-                static_x.copy_(stage[k])
-                ev_free[k].record(cur)
-                g2.replay()
-                if it >= 2:
-                    cur.wait_event(ev_host[k])
-                d_log[k].copy_(static_logits)
-                ev_out[k].record(cur)
-                with torch.cuda.stream(s_d2h):
-                    s_d2h.wait_event(ev_out[k])
-                    h_log[k].copy_(d_log[k], non_blocking=True)
-                    ev_host[k].record(s_d2h)
-
-            for it in range(2):
-                e2e_forward(it)
+            h_log = torch.empty((iters,) + tuple(ref_logits.shape)).pin_memory()
+            gf.run_pipelined([h_img] * 2, h_log[:2])
             barrier()
             t0 = time.perf_counter()
-            for it in range(2, 2 + iters):
-                e2e_forward(it)
+            gf.run_pipelined([h_img] * iters, h_log)
             barrier()
             dt = time.perf_counter() - t0
-            if not torch.equal(h_log[0], static_logits.cpu()):
+            if not (torch.equal(h_log[0], ref_logits.cpu()) and torch.equal(h_log[iters - 1], ref_logits.cpu())):
                 raise RuntimeError("e2e logits differ from the device-resident forward")
+            static_x = gf.static_in
+            del gf
             # the same network in the other memory layout (device-resident forward only), for comparison
             other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
-            del g2
             m2 = build_model(other_fmt)
             workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
             m2.fix_ranges()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(3):
-                    m2(static_x)
-            torch.cuda.current_stream().wait_stream(s)
-            g3 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g3):
-                m2(static_x)
+            gf2 = workloads.GraphedForward(m2, static_x)
             for _ in range(3):
-                g3.replay()
+                gf2.replay()
             barrier()
             m0.record()
             for _ in range(iters):
-                g3.replay()
+                gf2.replay()
             m1.record()
             barrier()
             mms_other = m0.elapsed_time(m1) / iters
-            del g3, m2
+            del gf2, m2
         vals = torch.tensor([mms, dt, mms_other], device=dev)
         if world > 1:
             fq_dist.all_reduce_max(vals)
@@ -706,8 +677,9 @@ def main():
                                        "img_per_s": B * world / (mms_other * 1e-3)},
                       "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
                       "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
-                      "e2e_note": "images from pinned host memory every step, logits back to pinned host memory; H2D of "
-                                  "batch k+1 overlaps the forward of batch k (2 staging buffers, 3 streams)",
+                      "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
+                                  "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "
+                                  "(2 staging buffers, 3 streams)",
                       "note": "full validate forward (cuDNN convs with torch's default TF32 policy, like the "
                               "reference on the same GPU) captured in one CUDA graph; weights re-quantised every "
                               "forward as the reference does; random-init weights, synthetic images"}

@@ -1740,16 +1740,30 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
     chunk_elems = rows_per_chunk * inner;
   }
   const int stride = table_stride(K);
+  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch's pin_memory()) are DMA'd directly;
+  // pageable ones go through the internal pinned staging buffers with a host memcpy on either side.
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool pin_x = is_pinned(x_host), pin_y = is_pinned(y_host);
   int64_t done = 0;
   int64_t k = 0;
   int64_t pend_off[HostPipe::kStreams] = {-1, -1, -1}, pend_len[HostPipe::kStreams] = {0, 0, 0};
   while (done < n) {
     const int s = (int)(k % HostPipe::kStreams);
     const int64_t len = (n - done) < chunk_elems ? (n - done) : chunk_elems;
-    FQ_CK(cudaStreamSynchronize(p.st[s]));
-    if (pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
-    memcpy(p.pin_in[s], x_host + done, len * sizeof(float));
-    FQ_CK(cudaMemcpyAsync(p.dev[s], p.pin_in[s], len * sizeof(float), cudaMemcpyHostToDevice, p.st[s]));
+    if (!pin_x || !pin_y) {  // a staging buffer of this stream is about to be reused
+      FQ_CK(cudaStreamSynchronize(p.st[s]));
+      if (!pin_y && pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
+    }
+    const float* src = x_host + done;
+    if (!pin_x) {
+      memcpy(p.pin_in[s], x_host + done, len * sizeof(float));
+      src = p.pin_in[s];
+    }
+    FQ_CK(cudaMemcpyAsync(p.dev[s], src, len * sizeof(float), cudaMemcpyHostToDevice, p.st[s]));
     if (C == 1) {
       r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table, len, 1, len, mantissa_bits, n_bits, sign_bits, p.st[s]);
     } else {
@@ -1758,7 +1772,8 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
                                n_bits, sign_bits, p.st[s]);
     }
     if (r != FP8FQ_OK) return r;
-    FQ_CK(cudaMemcpyAsync(p.pin_out[s], p.dev[s], len * sizeof(float), cudaMemcpyDeviceToHost, p.st[s]));
+    FQ_CK(cudaMemcpyAsync(pin_y ? y_host + done : p.pin_out[s], p.dev[s], len * sizeof(float), cudaMemcpyDeviceToHost,
+                          p.st[s]));
     pend_off[s] = done;
     pend_len[s] = len;
     done += len;
@@ -1766,7 +1781,7 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
   }
   for (int s = 0; s < HostPipe::kStreams; ++s) {
     FQ_CK(cudaStreamSynchronize(p.st[s]));
-    if (pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
+    if (!pin_y && pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
   }
 #undef FQ_CK
   return FP8FQ_OK;

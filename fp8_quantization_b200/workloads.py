@@ -387,3 +387,107 @@ def validate(model, batches, labels=None):
         fq_dist.all_reduce_sum(stats)
     c1, c5, loss, n = stats.tolist()
     return dict(top_1_accuracy=c1 / n, top_5_accuracy=c5 / n, loss=loss / n, count=int(n))
+
+
+# ---------------------------------------------------------------------------------------------------
+# validate forward as one CUDA graph
+# ---------------------------------------------------------------------------------------------------
+class GraphedForward:
+    """``model(x)`` for one input shape captured in a CUDA graph and replayed.
+
+    The validate pass of the reference (image_net.py:72-96) calls the model once per batch from Python: 51..117
+    quantiser calls, each a handful of eager launches.  With fixed ranges nothing in this package's forward touches
+    the host (no ``.item()``, tables and batch-norm parameters device-resident), so the whole forward -- cuDNN
+    convolutions, the fused epilogues, the per-forward weight re-quantisation -- is capturable and replays with no
+    Python or launch overhead.
+
+    Valid only while the model's state does not change: ranges fixed, eval mode, same weights / batch-norm tensors
+    (storage, not values -- in-place updates are seen).  Call :meth:`capture` again after changing any of that.
+    """
+
+    def __init__(self, model, example: torch.Tensor, warmup: int = 3):
+        self.model = model
+        self.graph = None
+        self.static_in = None
+        self.static_out = None
+        self.capture(example, warmup)
+
+    def _check_state(self):
+        from .quantization_manager import QuantizationManager
+
+        if self.model.training:
+            raise RuntimeError("GraphedForward: model.eval() first (training-mode batch norm updates host-visible state)")
+        for m in self.model.modules():
+            if isinstance(m, QuantizationManager) and m.estimating():
+                raise RuntimeError("GraphedForward: ranges must be fixed (model.fix_ranges()) before capture: range "
+                                   "estimation mutates quantiser state on every call")
+
+    @torch.no_grad()
+    def capture(self, example: torch.Tensor, warmup: int = 3):
+        self._check_state()
+        if not example.is_cuda:
+            raise ValueError("GraphedForward: the example input must live on the GPU")
+        self.static_in = example.detach().clone()
+        side = torch.cuda.Stream(device=example.device)
+        side.wait_stream(torch.cuda.current_stream(example.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):  # cuDNN algorithm selection, table builds, batch-norm packing
+                self.model(self.static_in)
+        torch.cuda.current_stream(example.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = self.model(self.static_in)
+        return self
+
+    def replay(self):
+        """Runs the forward on whatever ``static_in`` currently holds; returns ``static_out`` (overwritten by the
+        next replay)."""
+        self.graph.replay()
+        return self.static_out
+
+    def __call__(self, x: torch.Tensor):
+        if tuple(x.shape) != tuple(self.static_in.shape):
+            raise ValueError(f"GraphedForward was captured for shape {tuple(self.static_in.shape)}, got {tuple(x.shape)}")
+        self.static_in.copy_(x, non_blocking=True)
+        return self.replay()
+
+    @torch.no_grad()
+    def run_pipelined(self, host_batches, host_out: torch.Tensor):
+        """Validate loop over batches that live in (pinned) HOST memory, results written to ``host_out``
+        ([len(host_batches), *output shape], pinned): the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap
+        the forward of batch k (copy-in stream, compute stream, copy-out stream; two staging buffers each way).
+        Synchronises before returning."""
+        dev = self.static_in.device
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        stage = [torch.empty_like(self.static_in) for _ in range(2)]
+        d_out = [torch.empty_like(self.static_out) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_host = [torch.cuda.Event() for _ in range(2)]
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        for it, hb in enumerate(host_batches):
+            k = it & 1
+            with torch.cuda.stream(s_in):
+                if it >= 2:
+                    s_in.wait_event(ev_free[k])      # the forward that read stage[k] two batches ago has consumed it
+                stage[k].copy_(hb, non_blocking=True)
+                ev_in[k].record(s_in)
+            cur.wait_event(ev_in[k])
+            self.static_in.copy_(stage[k])
+            ev_free[k].record(cur)
+            self.graph.replay()
+            if it >= 2:
+                cur.wait_event(ev_host[k])           # d_out[k] has left for the host
+            d_out[k].copy_(self.static_out)
+            ev_out[k].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_out[k])
+                host_out[it].copy_(d_out[k], non_blocking=True)
+                ev_host[k].record(s_out)
+        cur.wait_stream(s_in)
+        cur.wait_stream(s_out)
+        torch.cuda.synchronize(dev)
+        return host_out

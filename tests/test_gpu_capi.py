@@ -28,6 +28,14 @@ def test_host_buffer_entry_point_matches_device_path():
     qw = fq.FPQuantizer(8, per_channel=True, mantissa_bits=4, maxval=1.0)
     qw.maxval = mvw.to(DEV)
     assert torch.equal(bits(yw), bits(qw(w.to(DEV)).cpu()))
+    # page-locked caller buffers are DMA'd directly (no staging copies); mixed pinned / pageable also works
+    xp, yp = x.pin_memory(), torch.empty_like(x).pin_memory()
+    assert torch.equal(bits(ops.fake_quant_host(xp, mv, 5.0, 8, 1, out=yp)), bits(y))
+    assert torch.equal(bits(ops.fake_quant_host(xp, mv, 5.0, 8, 1)), bits(y))
+    assert torch.equal(bits(ops.fake_quant_host(x, mv, 5.0, 8, 1, out=yp)), bits(y))
+    wp = w.pin_memory()
+    assert torch.equal(bits(ops.fake_quant_host(wp, mvw, 4.0, 8, 1, per_channel=True, out=torch.empty_like(w).pin_memory())),
+                       bits(yw))
 
 
 def test_error_codes_with_device_pointers():

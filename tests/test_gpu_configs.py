@@ -372,3 +372,40 @@ def test_config5_sharded_calibration_matches_single_process(tmp_path):
     assert r["quantizers"] == 50 and r["all_close"] and r["count"] == 4 * world
     assert r["bit_equal_ranges"] >= 22  # 21 weight quantisers + the stem's activation range at least
     assert r["logits_cos"] > 0.98
+
+
+@pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
+def test_graphed_forward_equals_eager_and_pipelines_host_batches(memory_format):
+    """workloads.GraphedForward: the validate forward as one CUDA graph gives the eager forward's logits bit for
+    bit (both layouts), refuses to capture while ranges are being estimated, and run_pipelined() (pinned host
+    batches in, pinned host logits out, copies overlapped with the forwards) returns the same logits per batch."""
+    from fp8_quantization_b200 import workloads
+
+    torch.manual_seed(10)
+    model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(DEV).eval()
+    if memory_format == "channels_last":
+        model = model.to(memory_format=torch.channels_last)
+    gen = torch.Generator().manual_seed(3)
+    xs = [torch.randn(4, 3, 224, 224, generator=gen) for _ in range(5)]
+    x0 = xs[0].to(DEV)
+    model.set_quant_state(True, True)
+    with pytest.raises(RuntimeError):
+        workloads.GraphedForward(model, x0)          # still estimating ranges
+    workloads.pass_data_for_range_estimation([x0], model, True, True, 1)
+    model.fix_ranges()
+    with torch.no_grad():
+        eager = [model(x.to(DEV)).clone() for x in xs]
+    gf = workloads.GraphedForward(model, x0)
+    for x, e in zip(xs, eager):
+        assert torch.equal(gf(x.to(DEV)), e)
+    with pytest.raises(ValueError):
+        gf(torch.zeros(2, 3, 224, 224, device=DEV))
+    host = [x.pin_memory() for x in xs]
+    out = torch.empty(len(xs), 4, 1000).pin_memory()
+    gf.run_pipelined(host, out)
+    for i, e in enumerate(eager):
+        assert torch.equal(out[i], e.cpu()), i
+    # validate() accepts the graphed forward in place of the model
+    stats = workloads.validate(gf, [x.to(DEV) for x in xs])
+    ref = workloads.validate(model, [x.to(DEV) for x in xs])
+    assert stats == ref
