@@ -39,7 +39,7 @@ constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
 constexpr int kMaxK = (1 << kMaxE) - 1;
 
 enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
-enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
+enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -271,6 +271,11 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
       pow2 = pow2 && (sb & 0x007fffffu) == 0u && sb >= 0x01000000u && sb <= 0x7e000000u;
     }
     if (pow2) flags |= FLAG_POW2;
+    // FLAG_RSNAN: some 1/s is not usable (stored as NaN): the multiply-by-reciprocal path must keep its guard, which
+    // then routes every element to the IEEE division (consumers that otherwise skip the guard: the MSE kernel)
+    bool rsnan = false;
+    for (int k = 1; k <= K; ++k) rsnan = rsnan || !(sr[2 * k + 1] == sr[2 * k + 1]);
+    if (rsnan) flags |= FLAG_RSNAN;
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);

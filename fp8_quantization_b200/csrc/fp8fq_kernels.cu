@@ -262,7 +262,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
 // vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
-template <int KMODE, bool CODES, int N, bool STAB_SHARED = false>
+// GUARD = false drops the exactness check of the reciprocal multiply (only for consumers that tolerate q off by one
+// on an exact rounding tie -- the MSE kernel, where either neighbour is equally far from x -- and only for tables
+// without FLAG_RSNAN).
+template <int KMODE, bool CODES, int N, bool STAB_SHARED = false, bool GUARD = true>
 __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N],
                                           float* s_out = nullptr) {
   if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
@@ -340,9 +343,9 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
   for (int k = 0; k < N; ++k) {
     const float r = mul_rn(xc[k], rs[k]);
     q[k] = nearbyintf(r);
-    slow |= !(fabsf(r - q[k]) < c.guard);
+    if (GUARD) slow |= !(fabsf(r - q[k]) < c.guard);
   }
-  if (slow) {
+  if (GUARD && slow) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const float r = mul_rn(xc[k], rs[k]);
@@ -1063,7 +1066,7 @@ __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, do
 //     the (s, 1/s) pair with ld.shared;
 //   * x is padded with zeros, not masked: Q(0) = 0 contributes nothing (and a degenerate candidate whose table is
 //     NaN poisons the sum through the real elements already, like the reference).
-// Measured on B200 (tools/bench_mse.py): 1.33 T candidate evaluations/s on [64,64,56,56] x 666 candidates; the first
+// Measured on B200 (tools/bench_mse.py): 1.47 T candidate evaluations/s on [64,64,56,56] x 666 candidates; the first
 // version (table double-buffered per candidate behind a barrier, 8 elements per thread, shared double atomics) 0.75 T.
 constexpr int kMseThreads = 256;
 template <int KMODE, int EPT>
@@ -1098,12 +1101,19 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
     for (int g = 0; g < ng; ++g) {
       ElemCtx<KMODE> ctx;
       load_ctx<KMODE>(ctx, s_tab + g * strideP, K, [](const float* p) { return *p; });
+      // A rounding tie of an UNCLIPPED x resolved the other way moves y to the neighbouring code on the other side
+      // of x: |x - y| is unchanged to ~1e-6 relative, so the tie guard of the reciprocal multiply is skipped here (3
+      // of ~20 instructions per evaluation).  It is kept where it matters: tables with an unusable reciprocal, and
+      // the E = 0 formats (K == 1), whose top code maxval / s = 2^M - 1/2 puts every CLIPPED element exactly on a
+      // tie while x itself is elsewhere.
+      const bool guarded = K == 1 || (f2u(s_tab[g * strideP + H_FLAGS]) & FLAG_RSNAN) != 0;
       float err = 0.0f;
 #pragma unroll
       for (int u = 0; u < EPT; u += 4) {
         float vi[4] = {v[u], v[u + 1], v[u + 2], v[u + 3]}, yo[4];
         int32_t cd[4];
-        quant_vec<KMODE, false, 4, true>(vi, ctx, yo, cd);
+        if (guarded) quant_vec<KMODE, false, 4, true, true>(vi, ctx, yo, cd);
+        else quant_vec<KMODE, false, 4, true, false>(vi, ctx, yo, cd);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float d = sub_rn(vi[k], yo[k]);
