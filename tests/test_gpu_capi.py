@@ -1,6 +1,5 @@
 """GPU: C-ABI behaviours that need a device: host-buffer end-to-end entry point, error codes with real
 pointers, stream semantics / CUDA-graph capture."""
-import ctypes
 
 import pytest
 import torch
