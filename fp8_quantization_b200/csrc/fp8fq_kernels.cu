@@ -885,6 +885,43 @@ __device__ __forceinline__ void est_update(const EstArgs& e, int64_t c, float& m
 constexpr int kMMThreads = 256;
 constexpr int kMMUnroll = 4;
 
+// Second stage of the per-tensor reduction (all threads of every CTA call it with their running min / max): block
+// reduce, publish the CTA's partial, and the LAST CTA to arrive reduces the partials, applies the estimator's update
+// rule, set_quant_range and -- optionally -- builds the quantiser table.  Leaves the ticket counter at zero.
+__device__ __forceinline__ void minmax_tensor_finish(float mn, float mx, float* __restrict__ partial,
+                                                     unsigned int* __restrict__ counter, const EstArgs& est) {
+  block_minmax(mn, mx);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mn;
+    partial[2 * blockIdx.x + 1] = mx;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  mn = __int_as_float(0x7f800000);
+  mx = __int_as_float(0xff800000);
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    mn = min_nan(mn, __ldcg(partial + 2 * b));
+    mx = max_nan(mx, __ldcg(partial + 2 * b + 1));
+  }
+  block_minmax(mn, mx);
+  __shared__ float s_mv;
+  if (threadIdx.x == 0) {
+    *counter = 0u;  // leave the workspace ready for the next call
+    est_update(est, 0, mn, mx);
+    const float mv = range_to_maxval(mn, mx);
+    if (est.maxval_out != nullptr) est.maxval_out[0] = mv;
+    s_mv = mv;
+  }
+  __syncthreads();
+  if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table);
+}
+
+
 __global__ void __launch_bounds__(kMMThreads) minmax_tensor_kernel(const float* __restrict__ x, int64_t n,
                                                                    int vec_ok, float* __restrict__ partial,
                                                                    unsigned int* __restrict__ counter,
@@ -922,35 +959,80 @@ __global__ void __launch_bounds__(kMMThreads) minmax_tensor_kernel(const float* 
       mx = max_nan(mx, t);
     }
   }
-  block_minmax(mn, mx);
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) {
-    partial[2 * blockIdx.x] = mn;
-    partial[2 * blockIdx.x + 1] = mx;
-    __threadfence();
-    const unsigned int ticket = atomicAdd(counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
+  minmax_tensor_finish(mn, mx, partial, counter, est);
+}
+
+// Calibration epilogue of a BN-fused layer (quantized_folded_bn.py:39-55 in state estimate_ranges): min / max of
+// act(bn(x)) WITHOUT materialising it -- the reference (and the op-by-op path) writes F.batch_norm's output, reads
+// and writes it again for the activation and reads it a third time for the estimator (20 B/element before the
+// quantiser even starts); this reads the convolution output once (4 B/element).  Same tile / channel arithmetic as
+// fq_stream_kernel's PRE_AFFINE (LAYOUT 0: NCHW rows, H*W % 4 == 0) and PRE_AFFINE_CL (LAYOUT 1) variants, same
+// batch-norm arithmetic (bn_mode), same NaN-propagating activation; the finish is minmax_tensor_kernel's.
+template <int LAYOUT, int BNM>
+__global__ void __launch_bounds__(kMMThreads) minmax_bn_act_kernel(const StreamArgs a, float* __restrict__ partial,
+                                                                   unsigned int* __restrict__ counter,
+                                                                   const EstArgs est) {
+  constexpr int kTile = kMMThreads * 4 * kMMUnroll;
+  const int64_t ntiles = (a.n + kTile - 1) / kTile;   // a.n % 4 == 0 (checked by the launcher)
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t tile0 = tile * kTile;
+    const int64_t base = tile0 + (int64_t)threadIdx.x * 4;
+    Pack<4> in[kMMUnroll];
+    bool ok[kMMUnroll];
+#pragma unroll
+    for (int u = 0; u < kMMUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * kMMThreads * 4;
+      ok[u] = i < a.n;
+      if (ok[u]) in[u].load(a.x + i);
+    }
+    if (LAYOUT == 1) {
+      if (a.cl_same) {
+        const uint32_t i32 = (uint32_t)base;
+        const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const BnParams bp = bn_load<BNM>(a, ch + k);
+#pragma unroll
+          for (int u = 0; u < kMMUnroll; ++u)
+            if (ok[u]) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bp);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kMMUnroll; ++u) {
+          if (!ok[u]) continue;
+          const uint32_t i32 = (uint32_t)(base + (int64_t)u * kMMThreads * 4);
+          const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bn_load<BNM>(a, ch + k));
+        }
+      }
+    } else {
+      const uint32_t row0 = fdiv((uint32_t)tile0, a.hw_div);
+      const uint32_t col0 = (uint32_t)tile0 - row0 * a.hw;
+      const uint32_t ch0 = row0 - fdiv(row0, a.c_div) * a.Cbn;
+#pragma unroll
+      for (int u = 0; u < kMMUnroll; ++u) {
+        if (!ok[u]) continue;
+        const uint32_t p = col0 + (uint32_t)(threadIdx.x * 4 + u * kMMThreads * 4);
+        uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
+        ch = ch >= a.Cbn ? ch - a.Cbn : ch;
+        const BnParams bp = bn_load<BNM>(a, ch);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kMMUnroll; ++u) {
+      if (!ok[u]) continue;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = apply_act(in[u].v[k], a.act);
+      mn = min_nan(min_nan(mn, v[0]), min_nan(v[1], min_nan(v[2], v[3])));
+      mx = max_nan(max_nan(mx, v[0]), max_nan(v[1], max_nan(v[2], v[3])));
+    }
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  mn = __int_as_float(0x7f800000);
-  mx = __int_as_float(0xff800000);
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += kMMThreads) {
-    mn = min_nan(mn, __ldcg(partial + 2 * b));
-    mx = max_nan(mx, __ldcg(partial + 2 * b + 1));
-  }
-  block_minmax(mn, mx);
-  __shared__ float s_mv;
-  if (threadIdx.x == 0) {
-    *counter = 0u;  // leave the workspace ready for the next call
-    est_update(est, 0, mn, mx);
-    const float mv = range_to_maxval(mn, mx);
-    if (est.maxval_out != nullptr) est.maxval_out[0] = mv;
-    s_mv = mv;
-  }
-  __syncthreads();
-  if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table);
+  minmax_tensor_finish(mn, mx, partial, counter, est);
 }
 
 // per-channel: one CTA per row
@@ -1614,6 +1696,64 @@ int fp8fq_estimate_prepare_f32(const float* x, int64_t n, int64_t C, int64_t inn
                                void* stream) {
   return minmax_impl(x, n, C, inner, cur_min, cur_max, est_mode, initialized, momentum, maxval_out, true,
                      mantissa_bits, n_bits, sign_bits, table, workspace, stream);
+}
+
+int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                      const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                      float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                      float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                      void* workspace, void* stream) {
+  if (outer < 1 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1 || est_mode < 0 || est_mode > 2)
+    return FP8FQ_ERR_BAD_ARG;
+  if (x == nullptr || cur_min == nullptr || cur_max == nullptr || bn_scale == nullptr ||
+      (bn_mode == 0 && bn_shift == nullptr))
+    return FP8FQ_ERR_BAD_ARG;
+  if (workspace == nullptr) return FP8FQ_ERR_WORKSPACE;
+  if (nhwc) hw = 1;                               // [pixels, Cbn]
+  if (Cbn >= (1ll << 31) || hw >= (1ll << 31) || outer >= (1ll << 32)) return FP8FQ_ERR_UNSUPPORTED;
+  const int64_t n = nhwc ? outer * Cbn : outer * hw;   // NCHW: outer = N * Cbn rows of hw elements
+  if (n >= (1ll << 32)) return FP8FQ_ERR_UNSUPPORTED;
+  if (!aligned16(x) || (bn_mode == 1 && !aligned16(bn_scale))) return FP8FQ_ERR_UNSUPPORTED;  // 128-bit accesses only
+  EstArgs e{};
+  e.cur_min = cur_min; e.cur_max = cur_max; e.est_mode = est_mode; e.initialized = initialized;
+  e.w_new = (float)(1.0 - momentum);
+  e.w_old = (float)momentum;
+  e.maxval_out = maxval_out;
+  e.table = nullptr;
+  if (table != nullptr) {
+    int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
+    if (r != FP8FQ_OK) return r;
+    e.table = table;
+    e.sign_bits = sign_bits;
+  }
+  StreamArgs a{};
+  a.x = x; a.n = n; a.act = act;
+  a.bn_p[0] = bn_scale; a.bn_p[1] = bn_shift; a.bn_mode = bn_mode;
+  if (nhwc) {
+    if (Cbn % 4 != 0) return FP8FQ_ERR_UNSUPPORTED;
+    a.Cbn = (uint32_t)Cbn;
+    a.c_div = make_fastdiv((uint32_t)Cbn);
+    a.cl_same = ((int64_t)kMMThreads * 4) % Cbn == 0 ? 1 : 0;
+  } else {
+    if (hw % 4 != 0 || !setup_affine(a, hw, Cbn)) return FP8FQ_ERR_UNSUPPORTED;
+  }
+  float* partial = reinterpret_cast<float*>(workspace) + 4;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+  const int max_grid = (int)((fp8fq_minmax_workspace_bytes() - 16) / 8);
+  int64_t grid = (int64_t)sm_count() * 8;
+  const int64_t ntiles = (n + (int64_t)kMMThreads * 4 * kMMUnroll - 1) / ((int64_t)kMMThreads * 4 * kMMUnroll);
+  if (grid > ntiles) grid = ntiles;
+  if (grid > max_grid) grid = max_grid;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 g((unsigned)grid), b(kMMThreads);
+  if (nhwc) {
+    if (bn_mode == 1) minmax_bn_act_kernel<1, 1><<<g, b, 0, st>>>(a, partial, counter, e);
+    else minmax_bn_act_kernel<1, 0><<<g, b, 0, st>>>(a, partial, counter, e);
+  } else {
+    if (bn_mode == 1) minmax_bn_act_kernel<0, 1><<<g, b, 0, st>>>(a, partial, counter, e);
+    else minmax_bn_act_kernel<0, 0><<<g, b, 0, st>>>(a, partial, counter, e);
+  }
+  return launch_status();
 }
 
 // ---- MSE grid -----------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ activations_set = [nn.ReLU, nn.ReLU6, nn.Hardtanh, nn.Sigmoid, nn.Tanh, nn.GELU,
 FUSE_EPILOGUES = True      # BN + act + quant in one launch; residual add + act + quant in one launch
 FUSE_BLOCK_TAIL = True     # BN + quant + residual add + act + quant of a residual block in one launch
 BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in one launch
+FUSE_CALIBRATION = True    # estimate_ranges state of a BN-fused layer: statistics of act(bn(x)) without materialising it
 BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
                            # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
                            # from F.batch_norm before quantisation)
@@ -379,6 +380,13 @@ class BNFusedHijacker(QuantizationHijacker):
                 and res.dtype == torch.float32 and _act_code(self.activation_function) is not None
                 and _fusable_manager(self.activation_quantizer))
 
+    def _fused_calibration_ok(self, res) -> bool:
+        mgr = self.activation_quantizer
+        return (FUSE_EPILOGUES and FUSE_CALIBRATION and self._qa and not self.quantize_input and not self.training
+                and not torch.is_grad_enabled() and res.is_cuda and res.dim() >= 2 and res.dtype == torch.float32
+                and _act_code(self.activation_function) is not None and isinstance(mgr, QuantizationManager)
+                and mgr.estimating() and not mgr.per_channel and mgr.device_resident_calibration())
+
     def conv_only(self, x):
         """Input quantisation (if configured), weight quantisation and the linear operation -- everything of
         forward() up to, not including, the BN / activation / activation-quantiser epilogue."""
@@ -397,6 +405,18 @@ class BNFusedHijacker(QuantizationHijacker):
             scale, shift, mode = self.folded_bn()
             return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
                                     q.n_bits, q.sign_bits, bn_mode=mode)
+        if self._fused_calibration_ok(res):
+            # calibration: statistics of act(bn(conv)) + range + table in one launch (4 B/element), then the fused
+            # epilogue -- instead of F.batch_norm, the activation, the estimator and the quantiser as separate passes
+            mgr = self.activation_quantizer
+            q = mgr.quantizer
+            res = ops.dense(res)
+            scale, shift, mode = self.folded_bn()
+            code = _act_code(self.activation_function)
+            if mgr.range_estimator.fused_bn_estimate_prepare(res, q, scale, shift, mode, code):
+                table, _ = q.table_for(res)
+                return ops.bn_act_quant(res, scale, shift, code, table, q._mbits_host, q.n_bits, q.sign_bits,
+                                        bn_mode=mode)
         if self.training and fq_dist.active():
             res = _sync_batch_norm_train(res, self.running_mean, self.running_var, self.gamma, self.beta,
                                          self.momentum, self.epsilon)

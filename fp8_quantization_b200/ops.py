@@ -328,6 +328,27 @@ def estimate_prepare(x, per_channel: bool, cur_min, cur_max, est_mode: int, init
     return maxval_out, table_out
 
 
+def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_min, cur_max, est_mode: int,
+                            initialized: bool, momentum: float, maxval_out=None, fmt=None, table_out=None) -> bool:
+    """Per-tensor estimator statistics of act(bn(x)) without materialising it (+ estimator update, and with
+    ``table_out``: set_quant_range + table) -- fp8fq_bn_act_estimate_prepare_f32.  Returns False when the shape is
+    not covered by the fused kernel (the caller then composes the unfused ops)."""
+    _require(x, "x")
+    Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
+    rows, hw = _rows_hw(x, Cbn)
+    nhwc = hw == 1 or is_channels_last(x)
+    mb, nb, sb = fmt if fmt is not None else (0.0, 0, 0)
+    code = lib().fp8fq_bn_act_estimate_prepare_f32(
+        x.data_ptr(), x.numel() // Cbn if nhwc else rows, hw, Cbn, 1 if nhwc else 0, bn_scale.data_ptr(),
+        _opt_ptr(bn_shift), int(bn_mode), int(act), cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode),
+        1 if initialized else 0, float(momentum), _opt_ptr(maxval_out), float(mb), int(nb), int(sb),
+        _opt_ptr(table_out), _workspace(x.device).data_ptr(), _stream())
+    if code == -2:
+        return False
+    check(code, "fp8fq_bn_act_estimate_prepare_f32")
+    return True
+
+
 def mse_grid(x, per_channel: bool, grid: torch.Tensor, mbit_list, n_bits: int, sign_bits: int, mses: torch.Tensor):
     """mses[m, g, c] += mean((x - Q(x; grid[g, c], mbit_list[m]))^2)  (range_estimators.py:337-347)."""
     _require(x, "x")

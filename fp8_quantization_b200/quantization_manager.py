@@ -86,10 +86,14 @@ class QuantizationManager(nn.Module):
     def estimating(self) -> bool:
         return self.state == Qstates.estimate_ranges or (self.state == Qstates.estimate_ranges_train and self.training)
 
-    def _fusable(self) -> bool:
+    def device_resident_calibration(self) -> bool:
+        """Estimator, set_quant_range and the table build can all stay on the device (no host-visible decision such
+        as the sticky unsigned switch of fp8_quantizer.py:224-225)."""
         q, r = self.quantizer, self.range_estimator
-        return (isinstance(q, FPQuantizer) and isinstance(r, _MinMaxEstimator) and q.set_maxval
-                and not q.allow_unsigned and r.fused_supported())
+        return isinstance(q, FPQuantizer) and isinstance(r, _MinMaxEstimator) and q.set_maxval and not q.allow_unsigned
+
+    def _fusable(self) -> bool:
+        return self.device_resident_calibration() and self.range_estimator.fused_supported()
 
     def forward(self, x):  # quantization_manager.py:114-122
         if self.estimating():

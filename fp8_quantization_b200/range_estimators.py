@@ -145,6 +145,34 @@ class _MinMaxEstimator(RangeEstimatorBase):
         return x
 
 
+    def fused_bn_estimate_prepare(self, x, quantizer, bn_scale, bn_shift, bn_mode, act_code) -> bool:
+        """Calibration epilogue of a BN-fused layer: the statistics of ``act(bn(x))`` straight from the convolution
+        output ``x`` (one read, nothing written), the estimator update, set_quant_range and the quantiser table in ONE
+        launch -- or, under data parallelism, the local statistics, the all-reduce and ``set_quant_range``.  Returns
+        False (state untouched) when the fused kernel does not cover the shape."""
+        assert not self.per_channel
+        x = ops.dense(x.detach())
+        mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
+        if fq_dist.active():
+            packed = torch.empty(2, dtype=torch.float32, device=x.device)
+            if not ops.bn_act_estimate_prepare(x, bn_scale, bn_shift, act_code, bn_mode, packed[:1], packed[1:],
+                                               ops.EST_CURRENT, False, self.momentum):
+                return False
+            quantizer.set_quant_range(*self.dp_merge(packed))
+            return True
+        was_init = self.current_xmin is not None
+        cmin, cmax, init = self._state(x)
+        maxval = torch.empty(1, dtype=torch.float32, device=x.device)
+        table = ops.new_table(1, mb, nb, sb, x.device)
+        if not ops.bn_act_estimate_prepare(x, bn_scale, bn_shift, act_code, bn_mode, cmin, cmax, self.EST_MODE, init,
+                                           self.momentum, maxval, (mb, nb, sb), table):
+            if not was_init:
+                self.current_xmin = self.current_xmax = None
+            return False
+        quantizer.adopt_range(maxval, table)
+        return True
+
+
 class CurrentMinMaxEstimator(_MinMaxEstimator):
     """range_estimators.py:56-76 (the percentile branch is unreachable from the reference's CLI:
     hijacker.py:57 compares a class with an enum member)."""

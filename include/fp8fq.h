@@ -207,6 +207,22 @@ int fp8fq_estimate_prepare_f32(const float* x, int64_t n, int64_t C, int64_t inn
                                float* maxval_out, float mantissa_bits, int n_bits, int sign_bits,
                                float* table, void* workspace, void* stream);
 
+/* Calibration epilogue of a BN-fused layer: BNFusedHijacker.forward in state estimate_ranges
+ * (quantized_folded_bn.py:39-55 -> quantization_manager.py:114-122): the per-tensor estimator statistics of
+ * act(bn(x)) computed WITHOUT materialising it (the convolution output is read once, 4 B/element; the op-by-op
+ * path moves 20 B/element before the quantiser starts), then the estimator update, and -- when `table` is not NULL --
+ * set_quant_range + the quantiser table, exactly as fp8fq_estimate_prepare_f32.  The caller follows it with
+ * fp8fq_bn_act_quant(_nhwc)_f32 on the same x.  x: NCHW ([outer = N*Cbn rows, hw]) or, with nhwc != 0,
+ * channel-innermost ([outer = pixels, Cbn]; hw ignored).  bn_scale / bn_shift / bn_mode / act as in
+ * fp8fq_bn_act_quant_f32.  Only 128-bit-addressable shapes (16-byte aligned x; hw % 4 == 0 resp. Cbn % 4 == 0; at most
+ * one channel wrap per 4096-element tile): FP8FQ_ERR_UNSUPPORTED otherwise, and the caller composes the unfused ops.
+ * maxval_out may be NULL (statistics only, e.g. before a data-parallel all-reduce). */
+int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                      const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                      float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                      float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                      void* workspace, void* stream);
+
 /* Replaces: the double Python loop of FP_MSE_Estimator.forward (range_estimators.py:337-347):
  * mses[m, g, c] += mean over the non-channel elements of (x - Q(x; maxval = grid[g, c], M = mbits[m]))^2.
  * grid: [G, C] device; mbits_host: [Mn] HOST floats; mses: [Mn, G, C] device, accumulated.

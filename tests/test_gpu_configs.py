@@ -409,3 +409,41 @@ def test_graphed_forward_equals_eager_and_pipelines_host_batches(memory_format):
     stats = workloads.validate(gf, [x.to(DEV) for x in xs])
     ref = workloads.validate(model, [x.to(DEV) for x in xs])
     assert stats == ref
+
+
+def test_config3_mobilenetv2_channels_last_fused_equals_layerwise():
+    """MobileNetV2 M=4 in channels_last (channel counts 16..1280, none dividing the 1024-element pass stride except
+    16/32/64: exercises the per-vector channel path of the channel-innermost kernels, depthwise weights, ReLU6, the
+    10 residual tails): same launch counts as NCHW, fused == layer-wise bit for bit, logits track the NCHW network."""
+    from fp8_quantization_b200 import modules, ops, workloads
+
+    torch.manual_seed(10)
+    m_cl = workloads.QuantizedMobileNetV2(workloads.MobileNetV2(), **workloads.readme_quant_params(4)).to(DEV).eval()
+    m_cl = m_cl.to(memory_format=torch.channels_last)
+    torch.manual_seed(10)
+    m_nchw = workloads.QuantizedMobileNetV2(workloads.MobileNetV2(), **workloads.readme_quant_params(4)).to(DEV).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for m in (m_cl, m_nchw):
+            workloads.pass_data_for_range_estimation([x], m, True, True, 1)
+            m.fix_ranges()
+        with torch.no_grad():
+            m_cl(x)
+            n0 = ops.launch_count()
+            y = m_cl(x)
+            assert ops.launch_count() - n0 == 2 + 42 + 10 + 2
+            modules.FUSE_BLOCK_TAIL = False
+            modules.BATCH_WEIGHT_QUANT = False
+            y_layerwise = m_cl(x)
+            modules.FUSE_BLOCK_TAIL = True
+            modules.BATCH_WEIGHT_QUANT = True
+            y_nchw = m_nchw(x)
+    finally:
+        modules.FUSE_BLOCK_TAIL = True
+        modules.BATCH_WEIGHT_QUANT = True
+        torch.backends.cudnn.allow_tf32 = prev
+    assert torch.equal(y, y_layerwise)
+    assert F.cosine_similarity(y.flatten(), y_nchw.flatten(), dim=0).item() > 0.99

@@ -147,3 +147,102 @@ def test_mse_estimator_accumulates_across_batches_like_oracle():
         omn, omx = oest(x)
     np.testing.assert_allclose(est.mses.cpu().numpy(), oest.mses.numpy(), rtol=2e-4)
     assert float(mx) == float(omx)
+
+
+# ---- fused calibration epilogue: statistics of act(bn(x)) without materialising it ---------------------------
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56), (4, 512, 7, 7), (3, 24, 9, 4), (6, 96, 14, 14), (5, 1000), (2, 3, 224, 224)])
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_bn_act_estimate_prepare_equals_unfused_statistics(shape, layout):
+    """fp8fq_bn_act_estimate_prepare_f32 == min / max of act(F.batch_norm(x)) (exact-BN mode reproduces ATen's NCHW
+    arithmetic, so the statistics are the same bits), the estimator update rules over several calls, the fused
+    set_quant_range + table == fp8fq_set_range_prepare_f32, NaN poisons the range like torch.min / torch.max."""
+    import torch.nn.functional as F
+
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import ops
+
+    if layout == "channels_last" and len(shape) != 4:
+        pytest.skip("channels_last is a 4-D layout")
+    torch.manual_seed(41)
+    C = shape[1]
+    mean, var = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.3
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    pk = ops.bn_pack(mean, var, gamma, beta, 1e-5)
+    for act, est_mode in ((1, ops.EST_ALL), (2, ops.EST_RUNNING), (0, ops.EST_CURRENT)):
+        cmin, cmax = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+        rmin = rmax = None
+        for call in range(3):
+            x = torch.randn(shape, device=DEV) * (1.0 + call)
+            xin = x.contiguous(memory_format=torch.channels_last) if layout == "channels_last" else x
+            maxval = torch.empty(1, device=DEV)
+            table = ops.new_table(1, 5.0, 8, 1, DEV)
+            ok = ops.bn_act_estimate_prepare(xin, pk, None, act, 1, cmin, cmax, est_mode, call > 0, 0.9, maxval,
+                                             (5.0, 8, 1), table)
+            hw = x[0, 0].numel() if x.dim() > 2 else 1
+            covered = ((layout == "channels_last" or hw == 1) and C % 4 == 0) or \
+                      (layout == "nchw" and hw > 1 and hw % 4 == 0 and 2 + 4095 // hw <= C)
+            if not covered:
+                assert not ok
+                return
+            assert ok
+            t = F.batch_norm(x, mean, var, gamma, beta, False, 0.0, 1e-5)
+            t = torch.relu(t) if act == 1 else (F.relu6(t) if act == 2 else t)
+            bmin, bmax = t.min().reshape(1), t.max().reshape(1)
+            if call == 0 or est_mode == ops.EST_CURRENT:
+                rmin, rmax = bmin, bmax
+            elif est_mode == ops.EST_ALL:
+                rmin, rmax = torch.min(rmin, bmin), torch.max(rmax, bmax)
+            else:
+                rmin, rmax = (1 - 0.9) * bmin + 0.9 * rmin, (1 - 0.9) * bmax + 0.9 * rmax
+            assert torch.equal(bits(cmin), bits(rmin)) and torch.equal(bits(cmax), bits(rmax)), (act, call)
+            mv2, tb2 = ops.set_range_prepare(rmin, rmax, 5.0, 8, 1)
+            assert torch.equal(bits(maxval), bits(mv2)) and torch.equal(bits(table), bits(tb2))
+    x = torch.randn(shape, device=DEV)
+    x.view(-1)[x.numel() // 2] = float("nan")
+    xin = x.contiguous(memory_format=torch.channels_last) if layout == "channels_last" else x
+    assert ops.bn_act_estimate_prepare(xin, pk, None, 1, 1, cmin, cmax, ops.EST_CURRENT, False, 0.9)
+    assert torch.isnan(cmin).all() and torch.isnan(cmax).all()
+
+
+@pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
+def test_fused_calibration_of_resnet18_equals_op_by_op_calibration(memory_format):
+    """Calibrating QuantizedResNet with the fused calibration epilogues gives the ranges of the op-by-op path.  In NCHW
+    they are the same bits for every quantiser, and so are the logits; in channels_last the op-by-op path runs ATen's
+    channels_last batch-norm kernel, whose arithmetic differs from its NCHW kernel by ulps (tools/bn_cl_check.py), so
+    the comparison there is to 1e-6 relative."""
+    from fp8_quantization_b200 import modules, ops, workloads
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(4, 3, 224, 224, generator=gen).to(DEV)
+    out = {}
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for fused in (True, False):
+            modules.FUSE_CALIBRATION = fused
+            torch.manual_seed(10)
+            m = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(DEV).eval()
+            if memory_format == "channels_last":
+                m = m.to(memory_format=torch.channels_last)
+            n0 = ops.launch_count()
+            workloads.pass_data_for_range_estimation([x], m, True, True, 1)
+            launches = ops.launch_count() - n0
+            m.fix_ranges()
+            with torch.no_grad():
+                y = m(x)
+            out[fused] = ([q.maxval.clone() for q in m.modules() if isinstance(q, FPQuantizer)], y, launches)
+    finally:
+        modules.FUSE_CALIBRATION = True
+        torch.backends.cudnn.allow_tf32 = prev
+    for a, b in zip(out[True][0], out[False][0]):
+        if memory_format == "nchw":
+            assert torch.equal(bits(a), bits(b))
+        else:
+            assert torch.allclose(a, b, rtol=1e-5)
+    if memory_format == "nchw":
+        assert torch.equal(out[True][1], out[False][1])
+    # same number of estimate / quantise launches either way (the 20 batch-norm parameter packs merely happen during
+    # calibration instead of at the first fused forward); what disappears are ATen's batch-norm and ReLU kernels and
+    # 16 of the 28 bytes moved per element
+    assert out[True][2] == out[False][2] + 20
