@@ -9,7 +9,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from fp8_quantization_b200 import ops, workloads  # noqa: E402
+import time  # noqa: E402
+
+from fp8_quantization_b200 import modules, ops, workloads  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda:0")
@@ -71,6 +73,20 @@ for name, M in (("resnet18", 5), ("mobilenet_v2", 4)):
     for fmt in ("nchw", "channels_last"):
         m = build(name, M, fmt)
         workloads.pass_data_for_range_estimation([x], m, True, True, 1)
+        # calibration forward (estimate_ranges state, eager: every site updates its range), fused vs op-by-op epilogues
+        calib = {}
+        for fused in (True, False):
+            modules.FUSE_CALIBRATION = fused
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                workloads.pass_data_for_range_estimation([x], m, True, True, 1)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            calib["fused_ms" if fused else "op_by_op_ms"] = best * 1e3
+        modules.FUSE_CALIBRATION = True
         m.fix_ranges()
         with torch.no_grad():
             m(x)
@@ -80,7 +96,7 @@ for name, M in (("resnet18", 5), ("mobilenet_v2", 4)):
         ms, y = graph_ms(lambda: m(x))
         logits[fmt] = y.clone()
         pms, _ = graph_ms(lambda p=plain(name, fmt): p(x))
-        rec[fmt] = {"ms_per_forward": ms, "img_per_s": B / (ms * 1e-3), "fp8fq_launches_per_forward": launches,
+        rec[fmt] = {"ms_per_forward": ms, "img_per_s": B / (ms * 1e-3), "fp8fq_launches_per_forward": launches, "calibration_forward": calib,
                     "unquantised_fp32_ms": pms, "unquantised_fp32_img_per_s": B / (pms * 1e-3)}
         del m
         torch.cuda.empty_cache()
