@@ -498,191 +498,201 @@ def main():
     # ---- e2e: same step with inputs in pinned HOST memory and results read back to the host -----------------
     e2e = None
     if not args.no_e2e:
-        # host staging: every data tensor that is not produced on the device within the step (conv outputs,
-        # weights) lives in pinned host memory and is copied in; every output is copied back out
-        h_in, h_out = [], []
-        h2d_bytes = d2h_bytes = 0
-        with torch.no_grad():
-            ref_results = run_plan(plan, ops)  # output tensors of every site: host buffers mirror their strides
-        for (name, a, kw), ref_out in zip(plan, ref_results):
-            if name == "bn_fold":
-                h_in.append(None), h_out.append(None)
-                continue
-            pairs = []
-            for j in DATA_POS[name]:
-                items = a[j][1] if a[j][0] == "list" else [a[j]]
-                for t in items:
-                    if t[0] == "const":
-                        pairs.append((t[1], t[1].cpu().pin_memory()))
-            h_in.append(pairs)
-            h_out.append([torch.empty_like(o, device="cpu").pin_memory()
-                          for o in (ref_out if isinstance(ref_out, (list, tuple)) else [ref_out])])
-            h2d_bytes += sum(h.numel() * 4 for _, h in pairs)
-            d2h_bytes += sum(h.numel() * 4 for h in h_out[-1])
-        s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        ev_site = [None] * len(plan)
+        try:
+            # host staging: every data tensor that is not produced on the device within the step (conv outputs,
+            # weights) lives in pinned host memory and is copied in; every output is copied back out
+            h_in, h_out = [], []
+            h2d_bytes = d2h_bytes = 0
+            with torch.no_grad():
+                ref_results = run_plan(plan, ops)  # output tensors of every site: host buffers mirror their strides
+            for (name, a, kw), ref_out in zip(plan, ref_results):
+                if name == "bn_fold":
+                    h_in.append(None), h_out.append(None)
+                    continue
+                pairs = []
+                for j in DATA_POS[name]:
+                    items = a[j][1] if a[j][0] == "list" else [a[j]]
+                    for t in items:
+                        if t[0] == "const":
+                            pairs.append((t[1], t[1].cpu().pin_memory()))
+                h_in.append(pairs)
+                h_out.append([torch.empty_like(o, device="cpu").pin_memory()
+                              for o in (ref_out if isinstance(ref_out, (list, tuple)) else [ref_out])])
+                h2d_bytes += sum(h.numel() * 4 for _, h in pairs)
+                d2h_bytes += sum(h.numel() * 4 for h in h_out[-1])
+            s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+            ev_site = [None] * len(plan)
 
-        def e2e_hook(i, name, args, real, kw):
-            if h_in[i] is None:
+            def e2e_hook(i, name, args, real, kw):
+                if h_in[i] is None:
+                    with torch.cuda.stream(s_k):
+                        return getattr(ops, name)(*real, **kw)
+                with torch.cuda.stream(s_in):
+                    if ev_site[i] is not None:
+                        s_in.wait_event(ev_site[i])  # last step's kernel of this site has consumed its staging buffers
+                    for dten, hten in h_in[i]:
+                        dten.copy_(hten, non_blocking=True)
+                s_k.wait_stream(s_in)
                 with torch.cuda.stream(s_k):
-                    return getattr(ops, name)(*real, **kw)
-            with torch.cuda.stream(s_in):
-                if ev_site[i] is not None:
-                    s_in.wait_event(ev_site[i])  # last step's kernel of this site has consumed its staging buffers
-                for dten, hten in h_in[i]:
-                    dten.copy_(hten, non_blocking=True)
-            s_k.wait_stream(s_in)
-            with torch.cuda.stream(s_k):
-                out = getattr(ops, name)(*real, **kw)
-                if ev_site[i] is None:
-                    ev_site[i] = torch.cuda.Event()
-                ev_site[i].record(s_k)
-            s_out.wait_stream(s_k)
-            with torch.cuda.stream(s_out):
-                for o, h in zip(out if isinstance(out, (list, tuple)) else [out], h_out[i]):
-                    h.copy_(o, non_blocking=True)
-                    o.record_stream(s_out)
-            return out
+                    out = getattr(ops, name)(*real, **kw)
+                    if ev_site[i] is None:
+                        ev_site[i] = torch.cuda.Event()
+                    ev_site[i].record(s_k)
+                s_out.wait_stream(s_k)
+                with torch.cuda.stream(s_out):
+                    for o, h in zip(out if isinstance(out, (list, tuple)) else [out], h_out[i]):
+                        h.copy_(o, non_blocking=True)
+                        o.record_stream(s_out)
+                return out
 
-        def e2e_step():
-            return run_plan(plan, ops, hook=e2e_hook)
+            def e2e_step():
+                return run_plan(plan, ops, hook=e2e_hook)
 
-        e2e_steps = max(3, min(args.steps, 10))
-        with torch.no_grad():
-            for _ in range(2):
-                e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            fq_dist.all_reduce_max(t)
-            dt = float(t.item())
-        e2e = {"value": st["elems"] * world * e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-               "ms_per_step": dt / e2e_steps * 1e3,
-               "note": "every site's externally produced inputs (conv outputs, weights) copied from pinned host "
-                       "memory and every site's output copied back to pinned host memory, per step; "
-                       "3 streams (H2D / kernels / D2H); wall clock around synchronised region, max over ranks"}
-        del h_in, h_out, ref_results
-        # what the host link can do on this box: the same copies alone and in both directions at once
-        nprobe = 64 << 20  # 256 MB per buffer
-        hp_a, hp_b = torch.empty(nprobe).pin_memory(), torch.empty(nprobe).pin_memory()
-        dp_a, dp_b = torch.empty(nprobe, device=dev), torch.empty(nprobe, device=dev)
-
-        def timed(fn_in, fn_out, reps=3):
-            best = None
-            for _ in range(reps):
-                torch.cuda.synchronize()
+            e2e_steps = max(3, min(args.steps, 10))
+            with torch.no_grad():
+                for _ in range(2):
+                    e2e_step()
+                barrier()
                 t0 = time.perf_counter()
-                if fn_in:
-                    with torch.cuda.stream(s_in):
-                        fn_in()
-                if fn_out:
-                    with torch.cuda.stream(s_out):
-                        fn_out()
-                torch.cuda.synchronize()
-                dtp = time.perf_counter() - t0
-                best = dtp if best is None else min(best, dtp)
-            return nprobe * 4 / best / 1e9
+                for _ in range(e2e_steps):
+                    e2e_step()
+                barrier()
+                dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                fq_dist.all_reduce_max(t)
+                dt = float(t.item())
+            e2e = {"value": st["elems"] * world * e2e_steps / dt / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                   "ms_per_step": dt / e2e_steps * 1e3,
+                   "note": "every site's externally produced inputs (conv outputs, weights) copied from pinned host "
+                           "memory and every site's output copied back to pinned host memory, per step; "
+                           "3 streams (H2D / kernels / D2H); wall clock around synchronised region, max over ranks"}
+            del h_in, h_out, ref_results
+            # what the host link can do on this box: the same copies alone and in both directions at once
+            nprobe = 64 << 20  # 256 MB per buffer
+            hp_a, hp_b = torch.empty(nprobe).pin_memory(), torch.empty(nprobe).pin_memory()
+            dp_a, dp_b = torch.empty(nprobe, device=dev), torch.empty(nprobe, device=dev)
 
-        def cp_in():
-            dp_a.copy_(hp_a, non_blocking=True)
+            def timed(fn_in, fn_out, reps=3):
+                best = None
+                for _ in range(reps):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    if fn_in:
+                        with torch.cuda.stream(s_in):
+                            fn_in()
+                    if fn_out:
+                        with torch.cuda.stream(s_out):
+                            fn_out()
+                    torch.cuda.synchronize()
+                    dtp = time.perf_counter() - t0
+                    best = dtp if best is None else min(best, dtp)
+                return nprobe * 4 / best / 1e9
 
-        def cp_out():
-            hp_b.copy_(dp_b, non_blocking=True)
+            def cp_in():
+                dp_a.copy_(hp_a, non_blocking=True)
 
-        link = {"h2d_alone_gbs": timed(cp_in, None), "d2h_alone_gbs": timed(None, cp_out),
-                "bidirectional_each_gbs": timed(cp_in, cp_out)}
-        bound_ms = max(h2d_bytes, d2h_bytes) / (link["bidirectional_each_gbs"] * 1e9) * 1e3
-        e2e["host_link"] = link
-        e2e["host_link_bound_ms_per_step"] = bound_ms
-        e2e["frac_of_host_link_bound"] = bound_ms / e2e["ms_per_step"]
-        del hp_a, hp_b, dp_a, dp_b
-        # the C-ABI host-buffer entry point itself (fp8fq_fake_quant_host_f32: what a caller without device memory
-        # binds): one per-tensor E2M5 fake-quant of a page-locked 2^27-element host tensor, H2D + kernel + D2H inside
-        nh = 1 << 27
-        hx, hy = torch.randn(nh).pin_memory(), torch.empty(nh).pin_memory()
-        mvh = torch.tensor([3.0])
-        ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # warm-up: allocates the pipeline's buffers
-        best = None
-        for _ in range(3):
-            t0 = time.perf_counter()
-            ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # synchronises before returning
-            dth = time.perf_counter() - t0
-            best = dth if best is None else min(best, dth)
-        e2e["c_abi_host_call"] = {"entry": "fp8fq_fake_quant_host_f32", "elems": nh, "ms": best * 1e3,
-                                  "value": nh / best / 1e9, "unit": UNIT, "h2d_bytes": nh * 4, "d2h_bytes": nh * 4,
-                                  "frac_of_host_link_bound": (nh * 4 / (link["bidirectional_each_gbs"] * 1e9)) / best}
-        del hx, hy
+            def cp_out():
+                hp_b.copy_(dp_b, non_blocking=True)
+
+            link = {"h2d_alone_gbs": timed(cp_in, None), "d2h_alone_gbs": timed(None, cp_out),
+                    "bidirectional_each_gbs": timed(cp_in, cp_out)}
+            bound_ms = max(h2d_bytes, d2h_bytes) / (link["bidirectional_each_gbs"] * 1e9) * 1e3
+            e2e["host_link"] = link
+            e2e["host_link_bound_ms_per_step"] = bound_ms
+            e2e["frac_of_host_link_bound"] = bound_ms / e2e["ms_per_step"]
+            del hp_a, hp_b, dp_a, dp_b
+            # the C-ABI host-buffer entry point itself (fp8fq_fake_quant_host_f32: what a caller without device memory
+            # binds): one per-tensor E2M5 fake-quant of a page-locked 2^27-element host tensor, H2D + kernel + D2H inside
+            nh = 1 << 27
+            hx, hy = torch.randn(nh).pin_memory(), torch.empty(nh).pin_memory()
+            mvh = torch.tensor([3.0])
+            ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # warm-up: allocates the pipeline's buffers
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ops.fake_quant_host(hx, mvh, float(M), 8, 1, out=hy)  # synchronises before returning
+                dth = time.perf_counter() - t0
+                best = dth if best is None else min(best, dth)
+            e2e["c_abi_host_call"] = {"entry": "fp8fq_fake_quant_host_f32", "elems": nh, "ms": best * 1e3,
+                                      "value": nh / best / 1e9, "unit": UNIT, "h2d_bytes": nh * 4, "d2h_bytes": nh * 4,
+                                      "frac_of_host_link_bound": (nh * 4 / (link["bidirectional_each_gbs"] * 1e9)) / best}
+            del hx, hy
+        except Exception as exc:  # an optional leg must not cost the headline number (single process only:
+            if world > 1:         # with several ranks a silent skip would desynchronise the collectives)
+                raise
+            e2e = {"error": repr(exc)}
 
     # ---- whole-model extras: quantised ResNet-18 validate forward img/s (convs = cuDNN, TF32 default) --------
     model_info = None
     if not args.no_model:
-        with torch.no_grad():
-            # public API: workloads.GraphedForward = the validate forward as one CUDA graph
-            gf = workloads.GraphedForward(model, x_img)
-            for _ in range(3):
-                gf.replay()
-            barrier()
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            iters = max(5, min(args.steps, 20))
-            m0.record()
-            for _ in range(iters):
-                gf.replay()
-            m1.record()
-            barrier()
-            mms = m0.elapsed_time(m1) / iters
-            ref_logits = gf.static_out.clone()
-            # e2e: images from pinned host memory, logits back to the host, every step (GraphedForward.run_pipelined:
-            # the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the forward of batch k)
-            h_img = x_img.cpu().pin_memory()
-            h_log = torch.empty((iters,) + tuple(ref_logits.shape)).pin_memory()
-            gf.run_pipelined([h_img] * 2, h_log[:2])
-            barrier()
-            t0 = time.perf_counter()
-            gf.run_pipelined([h_img] * iters, h_log)
-            barrier()
-            dt = time.perf_counter() - t0
-            if not (torch.equal(h_log[0], ref_logits.cpu()) and torch.equal(h_log[iters - 1], ref_logits.cpu())):
-                raise RuntimeError("e2e logits differ from the device-resident forward")
-            static_x = gf.static_in
-            del gf
-            # the same network in the other memory layout (device-resident forward only), for comparison
-            other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
-            m2 = build_model(other_fmt)
-            workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
-            m2.fix_ranges()
-            gf2 = workloads.GraphedForward(m2, static_x)
-            for _ in range(3):
-                gf2.replay()
-            barrier()
-            m0.record()
-            for _ in range(iters):
-                gf2.replay()
-            m1.record()
-            barrier()
-            mms_other = m0.elapsed_time(m1) / iters
-            del gf2, m2
-        vals = torch.tensor([mms, dt, mms_other], device=dev)
-        if world > 1:
-            fq_dist.all_reduce_max(vals)
-        mms, dt, mms_other = vals.tolist()
-        model_info = {"resnet18_quantized_img_per_s": B * world / (mms * 1e-3), "ms_per_forward": mms,
-                      "memory_format": args.memory_format,
-                      "other_layout": {"memory_format": other_fmt, "ms_per_forward": mms_other,
-                                       "img_per_s": B * world / (mms_other * 1e-3)},
-                      "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
-                      "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
-                      "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
-                                  "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "
-                                  "(2 staging buffers, 3 streams)",
-                      "note": "full validate forward (cuDNN convs with torch's default TF32 policy, like the "
-                              "reference on the same GPU) captured in one CUDA graph; weights re-quantised every "
-                              "forward as the reference does; random-init weights, synthetic images"}
+        try:
+            with torch.no_grad():
+                # public API: workloads.GraphedForward = the validate forward as one CUDA graph
+                gf = workloads.GraphedForward(model, x_img)
+                for _ in range(3):
+                    gf.replay()
+                barrier()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                iters = max(5, min(args.steps, 20))
+                m0.record()
+                for _ in range(iters):
+                    gf.replay()
+                m1.record()
+                barrier()
+                mms = m0.elapsed_time(m1) / iters
+                ref_logits = gf.static_out.clone()
+                # e2e: images from pinned host memory, logits back to the host, every step (GraphedForward.run_pipelined:
+                # the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the forward of batch k)
+                h_img = x_img.cpu().pin_memory()
+                h_log = torch.empty((iters,) + tuple(ref_logits.shape)).pin_memory()
+                gf.run_pipelined([h_img] * 2, h_log[:2])
+                barrier()
+                t0 = time.perf_counter()
+                gf.run_pipelined([h_img] * iters, h_log)
+                barrier()
+                dt = time.perf_counter() - t0
+                if not (torch.equal(h_log[0], ref_logits.cpu()) and torch.equal(h_log[iters - 1], ref_logits.cpu())):
+                    raise RuntimeError("e2e logits differ from the device-resident forward")
+                static_x = gf.static_in
+                del gf
+                # the same network in the other memory layout (device-resident forward only), for comparison
+                other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
+                m2 = build_model(other_fmt)
+                workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
+                m2.fix_ranges()
+                gf2 = workloads.GraphedForward(m2, static_x)
+                for _ in range(3):
+                    gf2.replay()
+                barrier()
+                m0.record()
+                for _ in range(iters):
+                    gf2.replay()
+                m1.record()
+                barrier()
+                mms_other = m0.elapsed_time(m1) / iters
+                del gf2, m2
+            vals = torch.tensor([mms, dt, mms_other], device=dev)
+            if world > 1:
+                fq_dist.all_reduce_max(vals)
+            mms, dt, mms_other = vals.tolist()
+            model_info = {"resnet18_quantized_img_per_s": B * world / (mms * 1e-3), "ms_per_forward": mms,
+                          "memory_format": args.memory_format,
+                          "other_layout": {"memory_format": other_fmt, "ms_per_forward": mms_other,
+                                           "img_per_s": B * world / (mms_other * 1e-3)},
+                          "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
+                          "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
+                          "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
+                                      "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "
+                                      "(2 staging buffers, 3 streams)",
+                          "note": "full validate forward (cuDNN convs with torch's default TF32 policy, like the "
+                                  "reference on the same GPU) captured in one CUDA graph; weights re-quantised every "
+                                  "forward as the reference does; random-init weights, synthetic images"}
+        except Exception as exc:  # an optional leg must not cost the headline number (single process only:
+            if world > 1:         # with several ranks a silent skip would desynchronise the collectives)
+                raise
+            model_info = {"error": repr(exc)}
 
     if world > 1:
         fq_dist.barrier()
