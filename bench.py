@@ -276,9 +276,11 @@ def run_cpu_reference(steps, warmup, batch, M):
         torch.set_num_threads(t)
         with torch.no_grad():
             O.fake_quant(probe, 8, pmv, mb, 1)
-            t0 = time.perf_counter()
-            O.fake_quant(probe, 8, pmv, mb, 1)
-            dt = time.perf_counter() - t0
+            dt = float("inf")
+            for _ in range(3):  # best of 3: a shared / virtualised host is noisy
+                t0 = time.perf_counter()
+                O.fake_quant(probe, 8, pmv, mb, 1)
+                dt = min(dt, time.perf_counter() - t0)
         if dt < best_dt:
             best_t, best_dt = t, dt
         if dt > 4 * best_dt:

@@ -66,6 +66,8 @@ SIGNATURES["fp8fq_bn_quant_add_act_quant_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_p, 
 SIGNATURES["fp8fq_bn_act_estimate_prepare_f32"] = (_c_i, [_c_p, _c_l, _c_l, _c_l, _c_i, _c_p, _c_p, _c_i, _c_i, _c_p, _c_p,
                                                           _c_i, _c_i, _c_d, _c_p, _c_f, _c_i, _c_i, _c_p, _c_p, _c_p])
 
+SIGNATURES["fp8fq_space_to_depth2_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_l, _c_l, _c_l, _c_l, _c_l, _c_l, _c_l, _c_p])
+
 _lib = None
 
 

@@ -1094,6 +1094,45 @@ __global__ void bn_pack_kernel(const float* mean, const float* var, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2x2 space-to-depth of an NCHW image into channel-innermost memory, with the convolution's zero padding applied:
+//   y[n, Y, X, c*4 + p*2 + q] = xpad[n, c, 2Y + p, 2X + q],   xpad[r, t] = x[r - pad, t - pad] or 0,
+// channels >= 4C zero.  With it a stride-2 k x k stem convolution (k odd, padding k/2) over C <= 4 input channels
+// becomes a stride-1 (k+1)/2 x (k+1)/2 convolution over 16 channels -- the same sum re-indexed -- which is a shape
+// cuDNN's tensor-core kernels handle (ResNet-18 stem at batch 128: 720 -> 294 us, tools/s2d_probe.py).
+// One thread per output pixel: 4C scalar loads (coalesced across the warp: consecutive X read consecutive column
+// pairs), four 128-bit stores (64 contiguous bytes per thread).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t npix,
+                                                       int C, int H, int W, int pad, int Hs, int Ws) {
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int X = (int)(pix % Ws);
+  const int64_t t = pix / Ws;
+  const int Y = (int)(t % Hs);
+  const int64_t n = t / Hs;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+  const float* xn = x + n * (int64_t)C * H * W;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= C) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int r = 2 * Y + p - pad;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int col = 2 * X + q - pad;
+        if (r >= 0 && r < H && col >= 0 && col < W) v[c * 4 + p * 2 + q] = __ldg(xn + ((int64_t)c * H + r) * W + col);
+      }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(y + pix * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // INT uniform quantisers: set_quant_range (uniform_quantizers.py:224-246, 303-314) + channel tables, one CTA
 // ------------------------------------------------------------------------------------------------
 __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* __restrict__ xmax, int64_t C,
@@ -1639,6 +1678,22 @@ int fp8fq_add_act_quant_f32(const float* a_in, const float* b_in, float* y, int6
   const bool vec = aligned16(a_in) && aligned16(b_in) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
   return vec ? launch_stream<PRE_ADD, 4>(a, st) : launch_stream<PRE_ADD, 1>(a, st);
+}
+
+int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t pad,
+                                   int64_t Hs, int64_t Ws, void* stream) {
+  if (N < 0 || C < 1 || C > 4 || H < 1 || W < 1 || pad < 0 || Hs < 1 || Ws < 1) return FP8FQ_ERR_BAD_ARG;
+  if (H >= (1ll << 30) || W >= (1ll << 30) || Hs >= (1ll << 30) || Ws >= (1ll << 30) || pad >= (1ll << 20))
+    return FP8FQ_ERR_UNSUPPORTED;
+  const int64_t npix = N * Hs * Ws;
+  if (npix == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(x) || !aligned16(y)) return FP8FQ_ERR_ALIGNMENT;
+  const int64_t grid = (npix + 255) / 256;
+  if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
+  s2d_nhwc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, npix, (int)C, (int)H, (int)W, (int)pad,
+                                                                     (int)Hs, (int)Ws);
+  return launch_status();
 }
 
 int64_t fp8fq_minmax_workspace_bytes(void) { return 16384; }

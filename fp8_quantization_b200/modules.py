@@ -41,6 +41,8 @@ FUSE_EPILOGUES = True      # BN + act + quant in one launch; residual add + act 
 FUSE_BLOCK_TAIL = True     # BN + quant + residual add + act + quant of a residual block in one launch
 BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in one launch
 FUSE_CALIBRATION = True    # estimate_ranges state of a BN-fused layer: statistics of act(bn(x)) without materialising it
+STEM_SPACE_TO_DEPTH = True  # channels_last network, NCHW image: stride-2 k x k stem conv over <= 4 channels as a stride-1
+                            # conv over the 2x2 space-to-depth image (same sum re-indexed; a shape cuDNN handles well)
 BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
                            # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
                            # from F.batch_norm before quantisation)
@@ -448,8 +450,37 @@ class _Conv1dForward:
                         dilation=self.dilation, groups=self.groups)
 
 
+def _space_to_depth_weight(w):
+    """[O, C, k, k] (k odd) -> [O, 16, (k+1)/2, (k+1)/2], channels_last: the stride-2 kernel zero-extended to k+1 and
+    split into its four (row parity, column parity) phases, channel order c*4 + p*2 + q as ops.space_to_depth2."""
+    O, C, k, _ = w.shape
+    a = (k + 1) // 2
+    w = F.pad(w, (0, 1, 0, 1)).reshape(O, C, a, 2, a, 2).permute(0, 1, 3, 5, 2, 4).reshape(O, C * 4, a, a)
+    if C * 4 < 16:
+        w = F.pad(w, (0, 0, 0, 0, 0, 16 - C * 4))
+    return w.contiguous(memory_format=torch.channels_last)
+
+
 class _Conv2dForward:
+    def _stem_s2d_ok(self, x, weight) -> bool:
+        k = self.kernel_size[0]
+        return (STEM_SPACE_TO_DEPTH and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+                and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 4 and x.shape[2] % 2 == 0
+                and x.shape[3] % 2 == 0 and ops.is_channels_last(weight) and self.groups == 1
+                and tuple(self.kernel_size) == (k, k) and k % 2 == 1 and k >= 3 and tuple(self.stride) == (2, 2)
+                and tuple(self.padding) == (k // 2, k // 2) and tuple(self.dilation) == (1, 1)
+                and self.padding_mode == "zeros")
+
     def run_forward(self, x, weight, bias, offsets=None):
+        if self._stem_s2d_ok(x, weight):
+            # NCHW image into a channels_last network: cuDNN's kernels for a stride-2 convolution over 3 input channels
+            # run at a fraction of their roofline; the same sum as a stride-1 convolution over the space-to-depth
+            # image (one HBM-bound gather + a 16-channel convolution) is 2x faster.  Exact re-indexing: only the
+            # summation order inside the convolution changes, as between any two cuDNN algorithms.
+            k = self.kernel_size[0]
+            a = (k + 1) // 2
+            hs, ws = x.shape[2] // 2 + a - 1, x.shape[3] // 2 + a - 1
+            return F.conv2d(ops.space_to_depth2(x, k // 2, hs, ws), _space_to_depth_weight(weight), bias=bias)
         # (the reference forces NCHW here; a channels_last network -- model.to(memory_format=torch.channels_last) --
         # keeps its layout so that cuDNN runs its NHWC tensor-core kernels without the transposes around them)
         return F.conv2d(ops.dense(x), ops.dense(weight), bias=bias, stride=self.stride, padding=self.padding,

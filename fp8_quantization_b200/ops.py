@@ -61,6 +61,16 @@ def _require_same_layout(a: torch.Tensor, b: torch.Tensor, what: str):
         raise Fp8fqError(f"{what}: both tensors must use the same memory layout (strides {a.stride()} vs {b.stride()})")
 
 
+def _out_like(x: torch.Tensor, out, what: str) -> torch.Tensor:
+    """Output buffer of an elementwise op: a fresh tensor with x's layout, or the caller's -- which must be a dense
+    fp32 CUDA tensor with exactly x's shape and strides (the kernels address input and output identically)."""
+    if out is None:
+        return torch.empty_like(x)
+    _require(out, "out")
+    _require_same_layout(x, out, what)
+    return out
+
+
 def _opt_ptr(t):
     return t.data_ptr() if t is not None else None
 
@@ -117,8 +127,7 @@ def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: floa
     """FPQuantizer.forward (fp8_quantizer.py:91-133).  C == 1: per tensor; else channel = dim 0."""
     _require(x, "x")   # channels_last x: elementwise over the same memory; channel = dim 0 stays the outermost stride
     n = x.numel()
-    if out is None:
-        out = torch.empty_like(x)
+    out = _out_like(x, out, "fake_quant")
     inner = n // C if C > 0 else 0
     check(lib().fp8fq_fake_quant_f32(x.data_ptr(), out.data_ptr(), table.data_ptr(), n, C, inner,
                                      float(mantissa_bits), int(n_bits), int(sign_bits), _stream()),
@@ -170,8 +179,7 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
     _require(x, "x")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
-    if out is None:
-        out = torch.empty_like(x)
+    out = _out_like(x, out, "bn_act_quant")
     if hw == 1 or is_channels_last(x):   # channel-innermost memory: [N, C] Linear outputs, channels_last activations
         check(lib().fp8fq_bn_act_quant_nhwc_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift),
                                                 x.numel() // Cbn, Cbn, int(act), int(bn_mode), table.data_ptr(),
@@ -203,8 +211,7 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     _require_same_layout(x, residual, "bn_quant_add_act_quant")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
-    if out is None:
-        out = torch.empty_like(x)
+    out = _out_like(x, out, "bn_quant_add_act_quant")
     if hw == 1 or is_channels_last(x):
         check(lib().fp8fq_bn_quant_add_act_quant_nhwc_f32(
             x.data_ptr(), residual.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift),
@@ -230,6 +237,7 @@ def fake_quant_multi(xs, tables, Cs, mantissa_bits: float, n_bits: int, sign_bit
     descs = (TensorDesc * len(xs))()
     for d, x, y, t, C in zip(descs, xs, outs, tables, Cs):
         _require(x, "x")
+        _out_like(x, y, "fake_quant_multi")
         d.x, d.y, d.table, d.C, d.inner = x.data_ptr(), y.data_ptr(), t.data_ptr(), C, x.numel() // C
     check(lib().fp8fq_fake_quant_multi_f32(descs, len(xs), float(mantissa_bits), int(n_bits), int(sign_bits),
                                            _stream()), "fp8fq_fake_quant_multi_f32")
@@ -241,8 +249,7 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     _require(a, "a")
     _require(b, "b")
     _require_same_layout(a, b, "add_act_quant")
-    if out is None:
-        out = torch.empty_like(a)
+    out = _out_like(a, out, "add_act_quant")
     check(lib().fp8fq_add_act_quant_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), int(act),
                                         table.data_ptr(), float(mantissa_bits), int(n_bits), int(sign_bits),
                                         _stream()), "fp8fq_add_act_quant_f32")
@@ -284,11 +291,24 @@ def uniform_quant(x, table, C: int, out=None):
     """Asymmetric/SymmetricUniformQuantizer.forward (uniform_quantizers.py:107-164), one launch."""
     _require(x, "x")
     n = x.numel()
-    if out is None:
-        out = torch.empty_like(x)
+    out = _out_like(x, out, "uniform_quant")
     check(lib().fp8fq_uniform_quant_f32(x.data_ptr(), out.data_ptr(), table.data_ptr(), n, C, n // C if C else 0,
                                         _stream()), "fp8fq_uniform_quant_f32")
     return out
+
+
+def space_to_depth2(x: torch.Tensor, pad: int, hs: int, ws: int) -> torch.Tensor:
+    """2x2 space-to-depth of an NCHW image [N, C <= 4, H, W] with ``pad`` zero rows / columns on the top / left (and
+    whatever is needed on the bottom / right to fill ``hs x ws``): returns [N, 16, hs, ws] in channels_last memory with
+    channel ``c*4 + p*2 + q`` = padded pixel ``(2Y + p, 2X + q)`` of input channel c (fp8fq_space_to_depth2_nhwc_f32)."""
+    _require(x, "x")
+    if x.dim() != 4 or not x.is_contiguous() or x.shape[1] > 4:
+        raise Fp8fqError("space_to_depth2: x must be an NCHW-contiguous [N, C <= 4, H, W] tensor")
+    N, C, H, W = x.shape
+    y = torch.empty((N, 16, hs, ws), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    check(lib().fp8fq_space_to_depth2_nhwc_f32(x.data_ptr(), y.data_ptr(), N, C, H, W, int(pad), int(hs), int(ws),
+                                               _stream()), "fp8fq_space_to_depth2_nhwc_f32")
+    return y
 
 
 _workspaces = {}

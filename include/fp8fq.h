@@ -187,6 +187,16 @@ int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, i
 int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_t n, int64_t C, int64_t inner,
                             void* stream);
 
+/* Data format on the caller's side of the path (no counterpart in the reference, which hands the NCHW image to
+ * F.conv2d, hijacker.py:70-98 -> autoquant_utils.py:34-44): 2x2 space-to-depth of an NCHW image x [N, C <= 4, H, W] into
+ * channel-innermost y [N, Hs, Ws, 16] with the convolution's zero padding applied,
+ *   y[n, Y, X, c*4 + p*2 + q] = xpad[n, c, 2Y + p, 2X + q],  xpad[r, t] = x[r - pad, t - pad] or 0,  channels >= 4C zero.
+ * A stride-2 k x k convolution (k odd, padding k/2) over x equals the stride-1 (k+1)/2 x (k+1)/2 convolution of y with
+ * the correspondingly re-indexed (zero-extended to k+1) weights: the same products, summed in a different order.
+ * Hs >= (H + 2 pad + 1) / 2 rows are written (rows / columns beyond the padded image are zero); y 16-byte aligned. */
+int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t pad,
+                                   int64_t Hs, int64_t Ws, void* stream);
+
 /* Replaces: the min/max of every range estimator (range_estimators.py:73-74, 85-91, 110-116) and
  * its update rule, NaN-propagating like torch.min/max.  One pass over x (4 B/element).
  *   per-tensor (C == 1): two-stage reduce finished by the last CTA; `workspace` must hold

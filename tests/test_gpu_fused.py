@@ -433,7 +433,7 @@ def test_channels_last_resnet18_fused_equals_unfused_and_tracks_nchw():
             m_cl(x)
             n0 = ops.launch_count()
             y_cl = m_cl(x)                       # NCHW images in, channels_last inside
-            assert ops.launch_count() - n0 == 23
+            assert ops.launch_count() - n0 == 23 + 1   # + the space-to-depth gather feeding the stem convolution
             modules.FUSE_BLOCK_TAIL = False
             y_cl_pair = m_cl(x)                  # separate BN+quant and add+relu+quant kernels
             modules.FUSE_BLOCK_TAIL = True
@@ -452,3 +452,38 @@ def test_channels_last_resnet18_fused_equals_unfused_and_tracks_nchw():
             assert torch.equal(u, v)             # weight ranges: pure min/max of identical weights
         else:
             assert torch.allclose(u, v, rtol=2e-2)
+
+
+@pytest.mark.parametrize("k,cin,cout,hw", [(7, 3, 64, (224, 224)), (3, 3, 32, (224, 224)), (5, 1, 8, (30, 18)), (3, 4, 16, (8, 8))])
+def test_space_to_depth_stem_is_the_same_convolution(k, cin, cout, hw):
+    """ops.space_to_depth2 is a pure gather (bit-equal to pad + pixel_unshuffle), and a channels_last stride-2 stem
+    layer fed with an NCHW image gives the direct convolution's result up to summation order."""
+    from fp8_quantization_b200 import modules, ops
+
+    torch.manual_seed(51)
+    x = torch.randn(3, cin, *hw, device=DEV)
+    a = (k + 1) // 2
+    hs, ws = hw[0] // 2 + a - 1, hw[1] // 2 + a - 1
+    y = ops.space_to_depth2(x, k // 2, hs, ws)
+    assert y.shape == (3, 16, hs, ws) and ops.is_channels_last(y)
+    xp = torch.zeros(3, cin, 2 * hs, 2 * ws, device=DEV)
+    xp[:, :, k // 2:k // 2 + hw[0], k // 2:k // 2 + hw[1]] = x
+    ref = F.pad(F.pixel_unshuffle(xp, 2), (0, 0, 0, 0, 0, 16 - 4 * cin))
+    assert torch.equal(y, ref)
+    conv = modules.QuantConv(cin, cout, k, stride=2, padding=k // 2, bias=True, **_qparams(5)).to(DEV)
+    conv = conv.to(memory_format=torch.channels_last)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            n0 = ops.launch_count()
+            out_s2d = conv(x)                    # full precision state: just the convolution
+            assert ops.launch_count() - n0 == (1 if ops.is_channels_last(conv.weight) else 0)  # 1 input channel: layout ambiguous
+            modules.STEM_SPACE_TO_DEPTH = False
+            out_direct = conv(x)
+    finally:
+        modules.STEM_SPACE_TO_DEPTH = True
+        torch.backends.cudnn.allow_tf32 = prev
+    assert out_s2d.shape == out_direct.shape and ops.is_channels_last(out_s2d) == ops.is_channels_last(out_direct)
+    scale = out_direct.abs().max().item()
+    assert (out_s2d - out_direct).abs().max().item() <= 2e-5 * max(scale, 1.0)

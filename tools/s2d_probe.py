@@ -1,6 +1,6 @@
-"""Probe (GPU box): the ResNet stem (7x7, stride 2, pad 3, 3 -> 64) rewritten as a 4x4 stride-1 convolution over the
-2x2 space-to-depth input (12 channels, optionally zero-padded to 16): exact re-indexing of the same sum.  Times
-cuDNN on it, the input transform, and checks the result against the direct convolution."""
+"""Probe (GPU box): stride-2 stem convolutions (ResNet: 7x7 pad 3, 3 -> 64; MobileNetV2: 3x3 pad 1, 3 -> 32) rewritten
+as stride-1 convolutions over the 2x2 space-to-depth input (12 channels, zero-padded to 16): exact re-indexing of the
+same sum.  Times cuDNN on both forms and checks the result against the direct convolution."""
 import json
 import os
 import sys
@@ -36,17 +36,20 @@ def gtime(fn, iters=20):
 
 
 def s2d_weight(w, cpad):
-    O, C = w.shape[:2]
-    w8 = F.pad(w, (0, 1, 0, 1))                                  # [O, C, 8, 8], zero row / column 7
-    w8 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4)   # [O, C, p, q, a, b]
-    w4 = w8.reshape(O, C * 4, 4, 4)
+    O, C, k, _ = w.shape
+    w8 = F.pad(w, (0, 1, 0, 1))                                            # [O, C, k+1, k+1], zero last row / column
+    a = (k + 1) // 2
+    w8 = w8.reshape(O, C, a, 2, a, 2).permute(0, 1, 3, 5, 2, 4)             # [O, C, p, q, a, b]
+    w4 = w8.reshape(O, C * 4, a, a)
     if cpad > C * 4:
         w4 = F.pad(w4, (0, 0, 0, 0, 0, cpad - C * 4))
     return w4.contiguous(memory_format=CL)
 
 
-def s2d_input(x, cpad):
-    s = F.pixel_unshuffle(F.pad(x, (3, 3, 3, 3)), 2)             # [N, C*4 (c, p, q), 115, 115]
+def s2d_input(x, k, cpad):
+    p = k // 2
+    s = F.pixel_unshuffle(F.pad(x, (p, p + (k + 1) % 2 + 1 - 1 + (1 if (x.shape[-1] + 2 * p) % 2 else 0), p,
+                                    p + (1 if (x.shape[-2] + 2 * p) % 2 else 0))), 2)
     if cpad > s.shape[1]:
         s = F.pad(s, (0, 0, 0, 0, 0, cpad - s.shape[1]))
     return s.contiguous(memory_format=CL)
@@ -55,24 +58,21 @@ def s2d_input(x, cpad):
 out = {}
 torch.manual_seed(0)
 x = torch.randn(B, 3, 224, 224, device=dev)
-w = torch.randn(64, 3, 7, 7, device=dev) * 0.05
-torch.backends.cudnn.allow_tf32 = False
-ref32 = F.conv2d(x, w, stride=2, padding=3)
-y32 = F.conv2d(s2d_input(x, 12), s2d_weight(w, 12))
-out["fp32_max_abs_diff"] = (ref32 - y32).abs().max().item()
-out["fp32_ref_absmax"] = ref32.abs().max().item()
-torch.backends.cudnn.allow_tf32 = True
-ref = F.conv2d(x.contiguous(memory_format=CL), w.contiguous(memory_format=CL), stride=2, padding=3)
-out["direct_cl_us"] = gtime(lambda: F.conv2d(x.contiguous(memory_format=CL), w.contiguous(memory_format=CL), stride=2, padding=3))
-for cpad in (12, 16):
-    xs, ws = s2d_input(x, cpad), s2d_weight(w, cpad)
-    y = F.conv2d(xs, ws)
-    assert y.shape == ref.shape, (y.shape, ref.shape)
-    out[f"s2d_c{cpad}"] = {"conv_us": gtime(lambda: F.conv2d(xs, ws)), "input_transform_us": gtime(lambda: s2d_input(x, cpad)),
-                           "weight_transform_us": gtime(lambda: s2d_weight(w, cpad)),
-                           "tf32_max_abs_diff_vs_direct": (y - ref).abs().max().item(),
-                           "out_is_channels_last": y.is_contiguous(memory_format=CL)}
-    print(cpad, out[f"s2d_c{cpad}"], flush=True)
-print(out)
+for name, cout, k in (("resnet_7x7", 64, 7), ("mobilenet_3x3", 32, 3)):
+    w = torch.randn(cout, 3, k, k, device=dev) * 0.05
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, w, stride=2, padding=k // 2)
+    y32 = F.conv2d(s2d_input(x, k, 16), s2d_weight(w, 16))
+    rec = {"fp32_max_abs_diff": (ref32 - y32[..., :ref32.shape[-2], :ref32.shape[-1]]).abs().max().item(),
+           "shapes": [list(ref32.shape), list(y32.shape)]}
+    torch.backends.cudnn.allow_tf32 = True
+    xc, wc = x.contiguous(memory_format=CL), w.contiguous(memory_format=CL)
+    rec["direct_cl_us"] = gtime(lambda: F.conv2d(xc, wc, stride=2, padding=k // 2))
+    rec["direct_cl_nchw_image_us"] = gtime(lambda: F.conv2d(x, wc, stride=2, padding=k // 2))
+    for cpad in (12, 16):
+        xs, ws = s2d_input(x, k, cpad), s2d_weight(w, cpad)
+        rec[f"s2d_c{cpad}_conv_us"] = gtime(lambda: F.conv2d(xs, ws))
+    out[name] = rec
+    print(name, rec, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/s2d_probe.json", "w"), indent=1)
