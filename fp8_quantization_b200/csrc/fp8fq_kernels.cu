@@ -1133,6 +1133,51 @@ __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Max-pool over channel-innermost memory ([N, H, W, C], C % 4 == 0): the op that consumes the stem's quantised
+// activation (models/resnet_quantized.py:73-78 keeps torchvision's nn.MaxPool2d).  ATen's max_pool_forward_nhwc takes
+// 440 us for [128,64,112,112] -> [128,64,56,56] on B200 (5.5x its HBM bound; profiles/forward_r01_summary.json); this
+// is one thread per (output pixel, 4 channels): kh*kw independent 128-bit loads (window overlap served by L1/L2), one
+// 128-bit store.  Same selection rule as ATen (`val > max || isnan(val)`, row-major window order), so NaN
+// propagation and the sign of a zero result are ATen's.
+// ------------------------------------------------------------------------------------------------
+struct PoolArgs {
+  const float* x;
+  float* y;
+  int64_t nvec;   // N * Ho * Wo * (C / 4)
+  int H, W, C4, Ho, Wo, kh, kw, sh, sw, ph, pw;
+};
+
+__global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const PoolArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nvec) return;
+  const int c4 = (int)(t % a.C4);
+  int64_t r = t / a.C4;
+  const int ow = (int)(r % a.Wo);
+  r /= a.Wo;
+  const int oh = (int)(r % a.Ho);
+  const int64_t n = r / a.Ho;
+  const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
+  const float4* xn = reinterpret_cast<const float4*>(a.x) + n * (int64_t)a.H * a.W * a.C4 + c4;
+  const float ninf = __int_as_float(0xff800000);
+  float4 m = make_float4(ninf, ninf, ninf, ninf);
+  for (int i = 0; i < a.kh; ++i) {
+    const int h = h0 + i;
+    if (h < 0 || h >= a.H) continue;
+#pragma unroll 3
+    for (int j = 0; j < a.kw; ++j) {
+      const int w = w0 + j;
+      if (w < 0 || w >= a.W) continue;
+      const float4 v = __ldg(xn + ((int64_t)h * a.W + w) * a.C4);
+      m.x = (v.x > m.x || v.x != v.x) ? v.x : m.x;
+      m.y = (v.y > m.y || v.y != v.y) ? v.y : m.y;
+      m.z = (v.z > m.z || v.z != v.z) ? v.z : m.z;
+      m.w = (v.w > m.w || v.w != v.w) ? v.w : m.w;
+    }
+  }
+  reinterpret_cast<float4*>(a.y)[t] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // INT uniform quantisers: set_quant_range (uniform_quantizers.py:224-246, 303-314) + channel tables, one CTA
 // ------------------------------------------------------------------------------------------------
 __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* __restrict__ xmax, int64_t C,
@@ -1693,6 +1738,24 @@ int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t 
   if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
   s2d_nhwc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, npix, (int)C, (int)H, (int)W, (int)pad,
                                                                      (int)Hs, (int)Ws);
+  return launch_status();
+}
+
+int fp8fq_max_pool2d_nhwc_f32(const float* x, float* y, int64_t N, int64_t H, int64_t W, int64_t C, int kh, int kw,
+                              int sh, int sw, int ph, int pw, void* stream) {
+  if (N < 0 || H < 1 || W < 1 || C < 1 || kh < 1 || kw < 1 || sh < 1 || sw < 1 || ph < 0 || pw < 0) return FP8FQ_ERR_BAD_ARG;
+  if (2 * ph > kh || 2 * pw > kw) return FP8FQ_ERR_BAD_ARG;            // torch: pad <= kernel / 2
+  if (C % 4 != 0 || H >= (1ll << 30) || W >= (1ll << 30) || C >= (1ll << 30)) return FP8FQ_ERR_UNSUPPORTED;
+  const int64_t Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;   // floor mode, dilation 1
+  if (Ho < 1 || Wo < 1) return FP8FQ_ERR_BAD_ARG;
+  const int64_t nvec = N * Ho * Wo * (C / 4);
+  if (nvec == 0) return FP8FQ_OK;
+  if (x == nullptr || y == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned16(x) || !aligned16(y)) return FP8FQ_ERR_ALIGNMENT;
+  const int64_t grid = (nvec + 255) / 256;
+  if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
+  PoolArgs a{x, y, nvec, (int)H, (int)W, (int)(C / 4), (int)Ho, (int)Wo, kh, kw, sh, sw, ph, pw};
+  maxpool_nhwc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
 

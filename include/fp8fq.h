@@ -197,6 +197,14 @@ int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_
 int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t pad,
                                    int64_t Hs, int64_t Ws, void* stream);
 
+/* Replaces (for channel-innermost activations): the nn.MaxPool2d that consumes the stem's quantised activation
+ * (models/resnet_quantized.py:73-78 keeps torchvision's module; ATen: max_pool_forward_nhwc).  x [N, H, W, C] ->
+ * y [N, Ho, Wo, C], Ho = (H + 2 ph - kh) / sh + 1 (floor mode, dilation 1, no indices); C % 4 == 0, 16-byte aligned.
+ * ATen's selection rule (`val > max || isnan(val)` in row-major window order): NaN propagates, results are the same
+ * bits as F.max_pool2d. */
+int fp8fq_max_pool2d_nhwc_f32(const float* x, float* y, int64_t N, int64_t H, int64_t W, int64_t C, int kh, int kw,
+                              int sh, int sw, int ph, int pw, void* stream);
+
 /* Replaces: the min/max of every range estimator (range_estimators.py:73-74, 85-91, 110-116) and
  * its update rule, NaN-propagating like torch.min/max.  One pass over x (4 B/element).
  *   per-tensor (C == 1): two-stage reduce finished by the last CTA; `workspace` must hold

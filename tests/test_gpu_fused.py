@@ -433,7 +433,7 @@ def test_channels_last_resnet18_fused_equals_unfused_and_tracks_nchw():
             m_cl(x)
             n0 = ops.launch_count()
             y_cl = m_cl(x)                       # NCHW images in, channels_last inside
-            assert ops.launch_count() - n0 == 23 + 1   # + the space-to-depth gather feeding the stem convolution
+            assert ops.launch_count() - n0 == 23 + 2   # + the space-to-depth gather feeding the stem, + the max-pool
             modules.FUSE_BLOCK_TAIL = False
             y_cl_pair = m_cl(x)                  # separate BN+quant and add+relu+quant kernels
             modules.FUSE_BLOCK_TAIL = True
@@ -487,3 +487,32 @@ def test_space_to_depth_stem_is_the_same_convolution(k, cin, cout, hw):
     assert out_s2d.shape == out_direct.shape and ops.is_channels_last(out_s2d) == ops.is_channels_last(out_direct)
     scale = out_direct.abs().max().item()
     assert (out_s2d - out_direct).abs().max().item() <= 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((8, 64, 112, 112), 3, 2, 1), ((2, 8, 7, 9), 3, 2, 1), ((3, 16, 10, 10), 2, 2, 0),
+                                         ((2, 4, 5, 5), 3, 1, 1), ((1, 32, 13, 6), (3, 2), (2, 1), (1, 0))])
+def test_native_max_pool_equals_aten_bit_for_bit(shape, k, s, p):
+    """NativeMaxPool2d on channels_last activations == F.max_pool2d (values, -0 / +0, NaN propagation, layout); NCHW
+    inputs and unsupported options go to ATen."""
+    from fp8_quantization_b200 import modules, ops
+
+    torch.manual_seed(61)
+    x = torch.randn(shape, device=DEV)
+    x.view(-1)[::97] = float("nan")
+    x.view(-1)[1::53] = -0.0
+    x.view(-1)[2::59] = 0.0
+    x_cl = x.contiguous(memory_format=torch.channels_last)
+    pool = modules.NativeMaxPool2d(k, s, p)
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        y = pool(x_cl)
+    assert ops.launch_count() - n0 == 1
+    assert pool(x_cl).stride() == y.stride() and ops.launch_count() - n0 == 1   # grad mode on: ATen (autograd-capable)
+    ref = F.max_pool2d(x_cl, k, s, p)
+    assert y.shape == ref.shape and y.stride() == ref.stride()
+    assert torch.equal(bits(y), bits(ref))
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        assert torch.equal(bits(pool(x)), bits(F.max_pool2d(x, k, s, p)))   # NCHW: ATen
+    assert ops.launch_count() == n0
+    assert isinstance(modules.quantize_model(torch.nn.MaxPool2d(3, 2, 1)), modules.NativeMaxPool2d)
