@@ -235,7 +235,8 @@ struct StreamArgs {
   uint32_t hw, Cbn;
   uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
   FastDiv hw_div, c_div;
-  int cl_same;          // *_CL: Cbn divides kThreads * VEC, i.e. a thread sees the same channels in every vector
+  int cl_same;          // *_CL: Cbn divides threads * VEC, i.e. a thread sees the same channels in every vector
+  int threads;          // *_CL: threads per CTA (<= kThreads), chosen so that cl_same holds; 0 = kThreads
 };
 
 struct RegTab {  // K <= 3: everything in registers
@@ -475,7 +476,9 @@ struct StreamMinBlocks {
 #endif
 };
 
-template <int KMODE, int PRE, int VEC, bool CODES, int BNM>
+// DYN: the CTA size is a launch parameter (channel-innermost variants whose channel count does not divide
+// kThreads * VEC); everywhere else it is the compile-time kThreads, which keeps the index arithmetic constant-folded.
+template <int KMODE, int PRE, int VEC, bool CODES, int BNM, bool DYN = false>
 __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) fq_stream_kernel(const StreamArgs a) {
   constexpr bool kTail = PreTraits<PRE>::kTail;
   constexpr bool kPerLane = PreTraits<PRE>::kPerLane;
@@ -485,7 +488,10 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   constexpr bool kBnAct = PreTraits<PRE>::kBnAct;
   constexpr int kUnroll = StreamUnroll<PRE>::value;
 
-  constexpr int64_t kTile = (int64_t)kThreads * VEC * kUnroll;
+  // the channel-innermost variants run with the largest CTA size <= kThreads whose pass stride (threads * VEC) is a
+  // multiple of the channel count, so that a thread meets the same channels in every vector (launch_stream_t)
+  const int nthr = DYN ? (int)blockDim.x : kThreads;
+  const int64_t kTile = (int64_t)nthr * VEC * kUnroll;
   const int64_t nvec_elems = a.n - (a.n % VEC);
   const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
   pdl_prologue();
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
     bool ok[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = base + (int64_t)u * kThreads * VEC;
+      const int64_t i = base + (int64_t)u * nthr * VEC;
       ok[u] = i < nvec_elems;
       if (ok[u]) {
         in[u].load(a.x + i);
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           if (!ok[u]) continue;
-          const uint32_t i32 = (uint32_t)(base + (int64_t)u * kThreads * VEC);
+          const uint32_t i32 = (uint32_t)(base + (int64_t)u * nthr * VEC);
           const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
 #pragma unroll
           for (int k = 0; k < VEC; ++k) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bn_load<BNM>(a, ch + k));
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
-      const int64_t i = base + (int64_t)u * kThreads * VEC;
+      const int64_t i = base + (int64_t)u * nthr * VEC;
       float v[VEC], yv[VEC];
       int32_t cd[VEC];
       if (kCL) {
@@ -1306,9 +1312,10 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
-template <int KMODE, int PRE, int VEC, bool CODES, int BNM>
+template <int KMODE, int PRE, int VEC, bool CODES, int BNM, bool DYN = false>
 int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
-  const int64_t tile = (int64_t)kThreads * VEC * StreamUnroll<PRE>::value;
+  const int threads = DYN ? a.threads : kThreads;
+  const int64_t tile = (int64_t)threads * VEC * StreamUnroll<PRE>::value;
   int64_t ntiles = (a.n + tile - 1) / tile;
   if (ntiles < 1) ntiles = 1;
   // Tiles per CTA.  Measured (tools/bench_kernels.py, [128,64,112,112]): the plain and residual-add kernels are
@@ -1325,7 +1332,7 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   while (tpc > 1 && !tpc_env && ntiles / tpc < (int64_t)sm_count() * 12) tpc >>= 1;
   int64_t grid = (ntiles + tpc - 1) / tpc;
   if (grid > 0x7fffffffll) grid = 0x7fffffffll;  // the kernel strides over the remaining tiles
-  launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM>, dim3((unsigned)grid), dim3(kThreads), 0, st, a);
+  launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, dim3((unsigned)grid), dim3(threads), 0, st, a);
   return launch_status();
 }
 
@@ -1335,6 +1342,12 @@ int launch_stream(const StreamArgs& a, cudaStream_t st) {
   const bool small = a.K <= 3 && (!PreTraits<PRE>::kTail || a.K2 <= 3);
   if (PRE == PRE_PLAIN && a.codes != nullptr)  // the code planes exist for the parity tests of the plain quantiser
     return small ? launch_stream_t<0, PRE_PLAIN, VEC, true, 0>(a, st) : launch_stream_t<1, PRE_PLAIN, VEC, true, 0>(a, st);
+  if (PreTraits<PRE>::kCL && a.threads > 0 && a.threads != kThreads) {   // CTA size fitted to the channel count
+    constexpr bool kDyn = PreTraits<PRE>::kCL;
+    if (a.bn_mode == 1)
+      return small ? launch_stream_t<0, PRE, VEC, false, 1, kDyn>(a, st) : launch_stream_t<1, PRE, VEC, false, 1, kDyn>(a, st);
+    return small ? launch_stream_t<0, PRE, VEC, false, 0, kDyn>(a, st) : launch_stream_t<1, PRE, VEC, false, 0, kDyn>(a, st);
+  }
   if (kHasBn && a.bn_mode == 1)
     return small ? launch_stream_t<0, PRE, VEC, false, kHasBn ? 1 : 0>(a, st)
                  : launch_stream_t<1, PRE, VEC, false, kHasBn ? 1 : 0>(a, st);
@@ -1656,7 +1669,12 @@ static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* 
   a.Cbn = (uint32_t)Cbn;
   a.c_div = make_fastdiv((uint32_t)Cbn);
   const bool v4 = (Cbn % 4 == 0) && aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
-  a.cl_same = ((int64_t)kThreads * (v4 ? 4 : 1)) % Cbn == 0 ? 1 : 0;
+  // CTA size: the largest multiple of (channels per pass-lane group) = Cbn / VEC that fits in kThreads, so that the
+  // pass stride threads * VEC is a multiple of Cbn (MobileNetV2: C = 96 -> 240 threads, 144 -> 252, 576 -> 144, ...);
+  // wider layers (Cbn / VEC > kThreads) keep kThreads and look the channel up per vector
+  const int64_t lanes = Cbn / (v4 ? 4 : 1);
+  a.threads = lanes <= kThreads ? (int)((kThreads / lanes) * lanes) : kThreads;
+  a.cl_same = ((int64_t)a.threads * (v4 ? 4 : 1)) % Cbn == 0 ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (table2 != nullptr) return v4 ? launch_stream<PRE_BNQ_ADD_CL, 4>(a, st) : launch_stream<PRE_BNQ_ADD_CL, 1>(a, st);
   return v4 ? launch_stream<PRE_AFFINE_CL, 4>(a, st) : launch_stream<PRE_AFFINE_CL, 1>(a, st);
