@@ -9,7 +9,7 @@
  * Conventions
  *   - All `const float*` / `float*` arguments are DEVICE pointers owned by the caller unless the
  *     name ends in `_host`.  The library never allocates device memory, keeps no global state
- *     and is re-entrant; every call is asynchronous on `stream` (a cudaStream_t passed as
+ *     (other than the monotonic launch counter read by fp8fq_launch_count) and is re-entrant; every call is asynchronous on `stream` (a cudaStream_t passed as
  *     void*) and CUDA-graph capturable (no host synchronisation, no D2H reads) -- except the
  *     `*_host_*` entry points, which own their staging buffers and synchronise before returning.
  *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = FP8FQ_ERR_* argument error.  Never throws.
@@ -141,13 +141,15 @@ int fp8fq_bn_quant_add_act_quant_nhwc_f32(const float* x, const float* residual,
                                           int sign_bits_inner, const float* table_outer, float mantissa_bits_outer,
                                           int n_bits_outer, int sign_bits_outer, void* stream);
 
-/* Packed batch-norm parameters for bn_mode 1: [Cbn][4] = {mean, gamma (1 if NULL), rsqrtf(var + eps), beta (0 if NULL)}
+/* Replaces: the per-channel parameter arithmetic of the eval-mode F.batch_norm call in BNFusedHijacker.forward
+ * (quantized_folded_bn.py:39-48), done once per change of the BN tensors instead of once per element.
+ * Packed batch-norm parameters for bn_mode 1: [Cbn][4] = {mean, gamma (1 if NULL), rsqrtf(var + eps), beta (0 if NULL)}
  * per channel; `packed` must be 16-byte aligned. */
 int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
                       int64_t Cbn, float* packed, void* stream);
 
-/* Per-channel affine form of eval-mode batch norm: scale = gamma * rsqrt(var + eps) (as 1/sqrt),
- * shift = beta - mean * scale.  All [Cbn]. */
+/* Same call site (quantized_folded_bn.py:39-48), bn_mode 0: per-channel affine form of eval-mode batch norm,
+ * scale = gamma * rsqrt(var + eps) (as 1/sqrt), shift = beta - mean * scale.  All [Cbn]. */
 int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, const float* beta,
                       float eps, int64_t Cbn, float* bn_scale, float* bn_shift, void* stream);
 

@@ -1,4 +1,5 @@
 """First-contact GPU script: parity statistics, libm questions and first throughput numbers.
+Lives under tests/ because it uses the oracle (test infrastructure) as the checker.
 Writes gpurun_out/explore.json.  Diagnostic only (bench.py is the measured artefact)."""
 import json
 import os
@@ -7,7 +8,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import fp8_quantization_b200 as fq  # noqa: E402
