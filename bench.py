@@ -36,6 +36,12 @@ UNIT = "Gelem/s"
 WORKLOAD = "resnet18_quantized_fp8_m5_per_channel_hot_path"
 
 
+def base_config(M):
+    """The workload keys both arms print (the reference arm adds its bounded sample, ours the per-GPU sizes)."""
+    return {"workload": WORKLOAD, "mantissa_bits": M, "n_bits": 8, "per_channel_weights": True,
+            "ranges": "fixed (calibrated on 1 batch, allminmax)"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -43,7 +49,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="images per step of the bounded CPU sample; 0 = sized on the spot so that one step is about "
+                         "1 s of work on this host's cores (2..32 images)")
     ap.add_argument("--no-graph", action="store_true", help="launch the 71 kernels eagerly instead of one CUDA graph")
     ap.add_argument("--no-model", action="store_true", help="skip the whole-model img/s extras")
     ap.add_argument("--no-e2e", action="store_true")
@@ -255,21 +263,16 @@ def cpu_sample_inputs(batch, M, seed=10):
     return weights, acts
 
 
-def run_cpu_reference(steps, warmup, batch, M):
-    """Times oracle.fp8_oracle.fake_quant (fp8_quantizer.py:91-133 op for op, ATen CPU, all host threads) over
-    the site list.  Ranges are fixed beforehand, as in the validate pass."""
-    from oracle import fp8_oracle as O
-
-    weights, acts = cpu_sample_inputs(batch, M)
-    mb = torch.Tensor([float(M)])
-    # "all the host threads it can use": os.cpu_count() threads thrash on a shared / cgroup-limited host (measured
-    # on the GPU box: 128 threads -> 40 s per pass, 64 -> 0.25 s), so probe and keep the fastest setting.
+def _cpu_threads(O, mb):
+    """"All the host threads it can use": os.cpu_count() threads thrash on a shared / cgroup-limited host (measured
+    on the GPU box: 128 threads -> 40 s per pass, 64 -> 0.25 s), so probe and keep the fastest setting."""
     ncpu = os.cpu_count() or 1
     try:
         ncpu = min(ncpu, len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         pass
-    probe = acts[0]
+    torch.manual_seed(10)
+    probe = torch.relu(torch.randn(2, 64, 112, 112))
     pmv = probe.abs().max().reshape(1)
     best_t, best_dt = 1, float("inf")
     for t in sorted({c for c in (4, 8, 16, 32, 64, 128, ncpu) if c <= ncpu}):
@@ -286,27 +289,58 @@ def run_cpu_reference(steps, warmup, batch, M):
         if dt > 4 * best_dt:
             break
     torch.set_num_threads(best_t)
-    w_mv = [w.reshape(w.shape[0], -1).abs().max(1)[0] for w in weights]
-    a_mv = [a.abs().max().reshape(1) for a in acts]
-    elems = sum(w.numel() for w in weights) + sum(a.numel() for a in acts)
+    return best_t
 
-    def one_pass():
-        with torch.no_grad():
-            for w, mv in zip(weights, w_mv):
-                O.fake_quant(w, 8, mv, mb, 1)
-            for a, mv in zip(acts, a_mv):
-                O.fake_quant(a, 8, mv, mb, 1)
+
+def run_cpu_reference(steps, warmup, batch, M, min_seconds=0.0):
+    """Times oracle.fp8_oracle.fake_quant (fp8_quantizer.py:91-133 op for op, ATen CPU, all host threads) over
+    the site list.  Ranges are fixed beforehand, as in the validate pass.  ``batch`` 0: the sample is sized here so
+    that one step is about 1 s of CPU work; ``min_seconds``: keep stepping until that much time has been measured
+    (the cpu_baseline leg asks for >= 10 s, the reference arm runs exactly ``steps``)."""
+    from oracle import fp8_oracle as O
+
+    mb = torch.Tensor([float(M)])
+    _cpu_threads(O, mb)
+
+    def prepare(b):
+        weights, acts = cpu_sample_inputs(b, M)
+        w_mv = [w.reshape(w.shape[0], -1).abs().max(1)[0] for w in weights]
+        a_mv = [a.abs().max().reshape(1) for a in acts]
+        elems = sum(w.numel() for w in weights) + sum(a.numel() for a in acts)
+
+        def one_pass():
+            with torch.no_grad():
+                for w, mv in zip(weights, w_mv):
+                    O.fake_quant(w, 8, mv, mb, 1)
+                for a, mv in zip(acts, a_mv):
+                    O.fake_quant(a, 8, mv, mb, 1)
+
+        return one_pass, elems
+
+    if batch <= 0:
+        one_pass, elems = prepare(2)
+        one_pass()
+        t0 = time.perf_counter()
+        one_pass()
+        t2 = time.perf_counter() - t0
+        batch = int(max(2, min(32, round(2 * 1.0 / max(t2, 1e-3)))))
+        if batch != 2:
+            one_pass, elems = prepare(batch)
+    else:
+        one_pass, elems = prepare(batch)
 
     for _ in range(warmup):
         one_pass()
+    done, dt = 0, 0.0
     t0 = time.perf_counter()
-    for _ in range(steps):
+    while done < steps or (dt < min_seconds and done < 200):
         one_pass()
-    dt = time.perf_counter() - t0
-    return {"value": elems * steps / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} passes over the 51 ResNet-18 quantiser sites at batch {batch} "
-                      f"({elems / 1e6:.1f} M elements/pass; oracle = reference ATen op sequence on CPU)",
-            "seconds": dt, "ms_per_step": dt / steps * 1e3, "elems_per_step": elems}
+        done += 1
+        dt = time.perf_counter() - t0
+    return {"value": elems * done / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} passes over the 51 ResNet-18 quantiser sites at batch {batch} "
+                      f"({elems / 1e6:.1f} M elements/pass, {dt:.1f} s; oracle = reference ATen op sequence on CPU)",
+            "seconds": dt, "ms_per_step": dt / done * 1e3, "elems_per_step": elems, "steps": done, "batch": batch}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -323,10 +357,12 @@ def main():
         cpu_steps = max(1, args.steps)
         cb = run_cpu_reference(cpu_steps, max(0, args.warmup), args.cpu_batch, M)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": cpu_steps, "warmup": max(0, args.warmup), "ms_per_step": cb["ms_per_step"],
+                "steps": cb["steps"], "warmup": max(0, args.warmup), "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": args.cpu_batch, "mantissa_bits": M,
-                           "note": "reference CPU path (ATen eager op sequence of fp8_quantizer.py:91-133), bounded sample"},
+                "config": dict(base_config(M), batch_per_gpu=cb["batch"], sample=cb["sample"],
+                               note="reference CPU path (ATen eager op sequence of fp8_quantizer.py:91-133) on the "
+                                    "host cores; each step is a bounded sample of the workload (same 51 sites, "
+                                    "smaller batch)"),
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -409,7 +445,8 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    for _ in range(200):  # keep the GPU under the same load long enough for the 100 ms clock sampler (not timed)
+    # keep the GPU under the same load for ~1 s so that the 100 ms clock sampler sees it (not timed)
+    for _ in range(max(200, min(20000, int(1000.0 / max(ms / args.steps, 1e-3))))):
         run_step()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
@@ -705,20 +742,19 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu and world == 1:
-        cb = run_cpu_reference(3, 1, args.cpu_batch, M)
+        cb = run_cpu_reference(3, 1, args.cpu_batch, M, min_seconds=10.0)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "mantissa_bits": M,
-                   "n_bits": 8, "per_channel_weights": True, "ranges": "fixed (calibrated on 1 batch, allminmax)",
+        "config": dict(base_config(M), **{"batch_per_gpu": B, "global_batch": B * world,
                    "memory_format": args.memory_format,
                    "elems_per_step_per_gpu": st["elems"], "launches_per_step": st["launches"],
                    "cuda_graph": graph is not None, "parallelism": f"dp{world}",
                    "l2": f"per-step working set {(st['in_bytes'] + st['out_bytes']) / 1e9:.2f} GB >> 126 MB L2; "
-                         "every buffer is touched once per step, so no tensor survives in L2 between steps"},
+                         "every buffer is touched once per step, so no tensor survives in L2 between steps"}),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu_baseline,
         "model": model_info,
         "hbm_gbs_step": (st["stream_bytes"] + 8 * st["weight_elems"]) / (ms_per_step * 1e-3) / 1e9,
