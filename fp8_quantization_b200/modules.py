@@ -324,7 +324,12 @@ class QuantizationHijacker(QuantizedModule):
         weight, bias = self.get_weight_bias()
         if self._qw:
             stash = self.__dict__.pop("_wq_stash", None)  # set by QuantizedModel.prequantize_weights for THIS forward
-            weight = stash if stash is not None else self.quantize_weights(weight)
+            # (stamped with the weight's storage and version: a layer skipped by one forward must not hand a stale
+            # result to a later one after the weights have changed)
+            if stash is not None and stash[0] == (weight.data_ptr(), weight._version):
+                weight = stash[1]
+            else:
+                weight = self.quantize_weights(weight)
         return weight, bias
 
     def quantize_weights(self, weights):
@@ -766,7 +771,7 @@ class QuantizedModel(nn.Module):
             outs = ops.fake_quant_multi([w for _, w, _, _ in items], [t for _, _, t, _ in items],
                                         [c for _, _, _, c in items], mb, nb, sb)
             for (m, _, _, _), out in zip(items, outs):
-                m.__dict__["_wq_stash"] = out
+                m.__dict__["_wq_stash"] = ((m.weight.data_ptr(), m.weight._version), out)
 
     def load_state_dict(self, state_dict, strict: bool = True):
         flags = {k: v for k, v in state_dict.items() if k.endswith("_quant_a") or k.endswith("_quant_w")}
