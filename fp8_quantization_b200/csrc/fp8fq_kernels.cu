@@ -59,8 +59,10 @@ int sm_count() {
 //   griddepcontrol.wait               -- block until the previous grid has completed and its writes are visible.
 // Launched without the attribute (FP8FQ_PDL=0) both instructions are no-ops.
 __device__ __forceinline__ void pdl_prologue() {
+#ifndef FP8FQ_HOST_SIM
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 
 bool pdl_enabled() {
@@ -71,8 +73,18 @@ bool pdl_enabled() {
   return on;
 }
 
+// Every kernel launch of the library goes through launch_impl.  `pdl`: with the programmatic-stream-serialization
+// attribute (kernels that call pdl_prologue()); without it, it is the launch a triple-chevron call issues.
+// FP8FQ_HOST_SIM (tests/host_sim: a g++ build of this file that runs the kernels' code on the CPU for the
+// -m "not gpu" tests, never part of libfp8fq.so) substitutes its own grid runner here.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+cudaError_t launch_impl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                        Args&&... args) {
+#ifdef FP8FQ_HOST_SIM
+  (void)pdl; (void)st;
+  fp8fq_sim::launch(kernel, grid, block, smem, std::forward<Args>(args)...);
+  return cudaSuccess;
+#else
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -82,8 +94,17 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+#endif
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_impl(true, kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_impl(false, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 inline int launch_status() {
@@ -326,12 +347,15 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       }
     }
     const float2* sr = reinterpret_cast<const float2*>(c.stab + off_sr(c.K));
+#ifndef FP8FQ_HOST_SIM
     if (STAB_SHARED) {  // the table is a shared-memory copy: ld.shared instead of a generic-address load
       const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sr);
 #pragma unroll
       for (int k = 0; k < N; ++k)
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s[k]), "=f"(rs[k]) : "r"(sbase + 8u * (uint32_t)e[k]));
-    } else {
+    } else
+#endif
+    {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const float2 p = sr[e[k]];
@@ -1245,7 +1269,11 @@ template <int KMODE, int EPT>
 __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __restrict__ x, int64_t inner, int64_t C,
                                                                   const float* __restrict__ tables, int G, int K,
                                                                   int gpb, double* __restrict__ acc) {
+#ifdef FP8FQ_HOST_SIM
+  float* s_dyn = fp8fq_sim::dynamic_smem();
+#else
   extern __shared__ __align__(16) float s_dyn[];
+#endif
   constexpr int kWarps = kMseThreads / 32;
   const int stride = table_stride(K);
   const int strideP = (stride + 3) & ~3;
@@ -1421,7 +1449,7 @@ static int prepare_impl(const float* maxval, const float* xmin, const float* xma
   if (maxval == nullptr && (xmin == nullptr || xmax == nullptr)) return FP8FQ_ERR_BAD_ARG;
   int threads = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
   int64_t grid = C < 4096 ? C : 4096;
-  prepare_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(maxval, xmin, xmax, maxval_out, C, M, E, K,
+  launch_plain(prepare_kernel, dim3((unsigned)grid), dim3(threads), 0, (cudaStream_t)stream, maxval, xmin, xmax, maxval_out, C, M, E, K,
                                                                        sign_bits, table);
   return launch_status();
 }
@@ -1553,11 +1581,11 @@ int fp8fq_fake_quant_backward_f32(const float* grad_y, const float* x, float* gr
   int64_t grid = C * a.chunks_per_row;
   if (grid > (int64_t)1 << 30) grid = (int64_t)1 << 30;
   if (K <= 3) {
-    if (vec) fq_backward_kernel<0, true><<<(unsigned)grid, 256, 0, st>>>(a);
-    else fq_backward_kernel<0, false><<<(unsigned)grid, 256, 0, st>>>(a);
+    if (vec) launch_plain(fq_backward_kernel<0, true>, dim3((unsigned)grid), dim3(256), 0, st, a);
+    else launch_plain(fq_backward_kernel<0, false>, dim3((unsigned)grid), dim3(256), 0, st, a);
   } else {
-    if (vec) fq_backward_kernel<1, true><<<(unsigned)grid, 256, 0, st>>>(a);
-    else fq_backward_kernel<1, false><<<(unsigned)grid, 256, 0, st>>>(a);
+    if (vec) launch_plain(fq_backward_kernel<1, true>, dim3((unsigned)grid), dim3(256), 0, st, a);
+    else launch_plain(fq_backward_kernel<1, false>, dim3((unsigned)grid), dim3(256), 0, st, a);
   }
   return launch_status();
 }
@@ -1569,7 +1597,7 @@ int fp8fq_uniform_prepare_f32(const float* xmin, const float* xmax, int64_t C, i
                               float* signed_out, float* table, void* stream) {
   if (xmin == nullptr || xmax == nullptr || table == nullptr || C < 1) return FP8FQ_ERR_BAD_ARG;
   if (n_bits < 1 || n_bits > 16) return FP8FQ_ERR_UNSUPPORTED;
-  uq_prepare_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(xmin, xmax, C, n_bits, symmetric ? 1 : 0,
+  launch_plain(uq_prepare_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, xmin, xmax, C, n_bits, symmetric ? 1 : 0,
                                                          aten_cuda_scalar_div ? 1 : 0, eps, delta_out, zero_float_out,
                                                          signed_out, table);
   return launch_status();
@@ -1597,7 +1625,7 @@ int fp8fq_bn_fold_f32(const float* mean, const float* var, const float* gamma, c
   if (mean == nullptr || var == nullptr || bn_scale == nullptr || bn_shift == nullptr || Cbn < 1)
     return FP8FQ_ERR_BAD_ARG;
   const int threads = 128;
-  bn_fold_kernel<<<(unsigned)((Cbn + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+  launch_plain(bn_fold_kernel, dim3((unsigned)((Cbn + threads - 1) / threads)), dim3(threads), 0, (cudaStream_t)stream, 
       mean, var, gamma, beta, eps, Cbn, bn_scale, bn_shift);
   return launch_status();
 }
@@ -1703,7 +1731,7 @@ int fp8fq_bn_pack_f32(const float* mean, const float* var, const float* gamma, c
   if (mean == nullptr || var == nullptr || packed == nullptr || Cbn < 1) return FP8FQ_ERR_BAD_ARG;
   if (!aligned16(packed)) return FP8FQ_ERR_ALIGNMENT;
   const int threads = 128;
-  bn_pack_kernel<<<(unsigned)((Cbn + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+  launch_plain(bn_pack_kernel, dim3((unsigned)((Cbn + threads - 1) / threads)), dim3(threads), 0, (cudaStream_t)stream, 
       mean, var, gamma, beta, eps, Cbn, packed);
   return launch_status();
 }
@@ -1754,7 +1782,7 @@ int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t 
   if (!aligned4(x) || !aligned16(y)) return FP8FQ_ERR_ALIGNMENT;
   const int64_t grid = (npix + 255) / 256;
   if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
-  s2d_nhwc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, npix, (int)C, (int)H, (int)W, (int)pad,
+  launch_plain(s2d_nhwc_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, x, y, npix, (int)C, (int)H, (int)W, (int)pad,
                                                                      (int)Hs, (int)Ws);
   return launch_status();
 }
@@ -1773,7 +1801,7 @@ int fp8fq_max_pool2d_nhwc_f32(const float* x, float* y, int64_t N, int64_t H, in
   const int64_t grid = (nvec + 255) / 256;
   if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
   PoolArgs a{x, y, nvec, (int)H, (int)W, (int)(C / 4), (int)Ho, (int)Wo, kh, kw, sh, sw, ph, pw};
-  maxpool_nhwc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_plain(maxpool_nhwc_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1810,13 +1838,13 @@ static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, floa
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > max_grid) grid = max_grid;
-    minmax_tensor_kernel<<<(unsigned)grid, kMMThreads, 0, st>>>(x, n, aligned16(x) ? 1 : 0, partial, counter, e);
+    launch_plain(minmax_tensor_kernel, dim3((unsigned)grid), dim3(kMMThreads), 0, st, x, n, aligned16(x) ? 1 : 0, partial, counter, e);
     return launch_status();
   }
   int threads = inner >= 512 ? 128 : (inner >= 128 ? 64 : 32);
   if (fuse && e.K > threads) threads = e.K <= 64 ? 64 : 128;
   int64_t grid = C < (int64_t)sm_count() * 16 ? C : (int64_t)sm_count() * 16;
-  minmax_rows_kernel<<<(unsigned)grid, threads, 0, st>>>(x, C, inner, (inner % 4 == 0 && aligned16(x)) ? 1 : 0, e);
+  launch_plain(minmax_rows_kernel, dim3((unsigned)grid), dim3(threads), 0, st, x, C, inner, (inner % 4 == 0 && aligned16(x)) ? 1 : 0, e);
   return launch_status();
 }
 
@@ -1883,11 +1911,11 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 g((unsigned)grid), b(kMMThreads);
   if (nhwc) {
-    if (bn_mode == 1) minmax_bn_act_kernel<1, 1><<<g, b, 0, st>>>(a, partial, counter, e);
-    else minmax_bn_act_kernel<1, 0><<<g, b, 0, st>>>(a, partial, counter, e);
+    if (bn_mode == 1) launch_plain(minmax_bn_act_kernel<1, 1>, g, b, 0, st, a, partial, counter, e);
+    else launch_plain(minmax_bn_act_kernel<1, 0>, g, b, 0, st, a, partial, counter, e);
   } else {
-    if (bn_mode == 1) minmax_bn_act_kernel<0, 1><<<g, b, 0, st>>>(a, partial, counter, e);
-    else minmax_bn_act_kernel<0, 0><<<g, b, 0, st>>>(a, partial, counter, e);
+    if (bn_mode == 1) launch_plain(minmax_bn_act_kernel<0, 1>, g, b, 0, st, a, partial, counter, e);
+    else launch_plain(minmax_bn_act_kernel<0, 0>, g, b, 0, st, a, partial, counter, e);
   }
   return launch_status();
 }
@@ -1943,17 +1971,17 @@ int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, cons
       const float* tb = tables + gs * C * stride;
       double* ac = acc + gs * C;
       if (K <= 3) {
-        if (ept == 16) mse_grid_kernel<0, 16><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-        else mse_grid_kernel<0, 4><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        if (ept == 16) launch_plain(mse_grid_kernel<0, 16>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
+        else launch_plain(mse_grid_kernel<0, 4>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
       } else {
-        if (ept == 16) mse_grid_kernel<1, 16><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
-        else mse_grid_kernel<1, 4><<<gdim, kMseThreads, smem, st>>>(x, inner, C, tb, Gs, K, gpb, ac);
+        if (ept == 16) launch_plain(mse_grid_kernel<1, 16>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
+        else launch_plain(mse_grid_kernel<1, 4>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
       }
       r = launch_status();
       if (r != FP8FQ_OK) return r;
     }
     const int64_t GC = G * C;
-    mse_finish_kernel<<<(unsigned)((GC + 127) / 128), 128, 0, st>>>(acc, GC, 1.0 / (double)inner, mses + m * GC);
+    launch_plain(mse_finish_kernel, dim3((unsigned)((GC + 127) / 128)), dim3(128), 0, st, acc, GC, 1.0 / (double)inner, mses + m * GC);
     r = launch_status();
     if (r != FP8FQ_OK) return r;
   }

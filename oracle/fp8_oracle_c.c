@@ -103,3 +103,28 @@ void oracle_c_minmax(const float* x, int64_t C, int64_t inner, float* mn, float*
     mx[c] = hi;
   }
 }
+
+/* quantized_folded_bn.py:39-51: eval-mode F.batch_norm followed by the fused activation, per element, with the plainest
+ * possible indexing (the CUDA kernels' tile / channel arithmetic is what this checks).
+ *   layout 0: x is [N, C, hw] (NCHW), channel = (i / hw) % C;  layout 1: x is [pixels, C], channel = i % C.
+ *   bn_mode 0: y = fma(x, p0[c], p1[c])  (p0 = gamma / sqrt(var + eps), p1 = beta - mean * p0, computed by the caller);
+ *   bn_mode 1: y = fma(gamma * (x - mean), invstd, beta) with p0 = [C][4] = {mean, gamma, invstd, beta} -- the arithmetic
+ *              ATen's eval batch norm performs on CUDA (measured).
+ *   act: 0 none, 1 relu, 2 relu6 (torch.relu / hardtanh propagate NaN). */
+void oracle_c_bn_act(const float* x, float* y, int64_t n, int64_t hw, int64_t C, int layout, int bn_mode,
+                     const float* p0, const float* p1, int act) {
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t c = layout == 1 ? i % C : (i / hw) % C;
+    float v;
+    if (bn_mode == 0) {
+      v = fmaf(x[i], p0[c], p1[c]);
+    } else {
+      volatile float d = x[i] - p0[4 * c];
+      volatile float g = p0[4 * c + 1] * d;
+      v = fmaf(g, p0[4 * c + 2], p0[4 * c + 3]);
+    }
+    if (act >= 1) v = f_max_nan(v, 0.0f);
+    if (act == 2) v = f_min_nan(v, 6.0f);
+    y[i] = v;
+  }
+}
