@@ -41,7 +41,8 @@ def sim(built):
     """libfp8fq_sim.so with the product's own ctypes signature table applied (so the table is exercised too)."""
     from fp8_quantization_b200._lib import SIGNATURES
 
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim.so"))
+    # FP8FQ_SIM_LIB: an alternative build of the same simulation (e.g. -fsanitize=address, see tests/host_sim/README.md)
+    lib = ctypes.CDLL(os.environ.get("FP8FQ_SIM_LIB") or os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim.so"))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
@@ -58,8 +59,13 @@ def ref(oracle_c):
 
 
 def aligned(n, dtype=np.float32, offset_elems=0):
-    """A float32 array of n elements whose address is 16-byte aligned + 4 * offset_elems bytes."""
-    raw = np.zeros(n + 8 + offset_elems, dtype=dtype)
+    """An n-element array whose address is 16-byte aligned + 4 * offset_elems bytes and which ENDS where its allocation
+    ends (malloc returns 16-byte aligned blocks), so that under the AddressSanitizer build of the simulation an access
+    one element past the end -- or before the start -- lands in a redzone."""
+    raw = np.zeros(n + offset_elems, dtype=dtype)
+    if raw.ctypes.data % 16 == 0:
+        return raw[offset_elems:]
+    raw = np.zeros(n + 8 + offset_elems, dtype=dtype)      # allocator without 16-byte alignment: align by hand
     start = ((-raw.ctypes.data) % 16) // 4 + offset_elems
     return raw[start:start + n]
 
@@ -382,3 +388,318 @@ def test_add_act_quant_equals_composition(sim, ref):
                     if act == ACT_RELU6:
                         v = np.where(np.isnan(v), v, np.minimum(v, 6))
                     assert same_bits(y, ref_quant(ref, v.astype(np.float32), mv, M)[0]), (M, n, off, act)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2a: min/max + estimator update rules (+ fused set_quant_range / prologue)
+# ---------------------------------------------------------------------------------------------------------------------
+def workspace(sim):
+    return np.zeros(sim.fp8fq_minmax_workspace_bytes() // 4, np.int32)
+
+
+def np_minmax(x):
+    """torch.min / torch.max semantics: NaN propagates (numpy's min / max do the same)."""
+    with np.errstate(invalid="ignore"):
+        return np.float32(np.min(x)), np.float32(np.max(x))
+
+
+def est_rule(mode, init, cur, new, momentum):
+    if not init or mode == EST_CURRENT:
+        return new
+    if mode == EST_ALL:
+        return tuple(np.float32(f(c, v)) if not (np.isnan(c) or np.isnan(v)) else np.float32(np.nan)
+                     for f, c, v in ((min, cur[0], new[0]), (max, cur[1], new[1])))
+    w_new, w_old = np.float32(1.0 - momentum), np.float32(momentum)     # range_estimators.py:121-123
+    return tuple(np.float32(np.float32(w_new * v) + np.float32(w_old * c)) for c, v in zip(cur, new))
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1000, 4099, 70001, 150001])
+def test_minmax_per_tensor_two_stage_reduction_and_update_rules(sim, n):
+    """minmax_tensor_kernel: grid-stride 128-bit loads, warp shuffles, block reduce, last-CTA finish; the three
+    estimator update rules (range_estimators.py:61-125); NaN propagation; misaligned base; the workspace's ticket
+    counter is left at zero."""
+    rng = np.random.default_rng(n)
+    ws = workspace(sim)
+    for off in (0, 1):
+        for with_nan in (False, True):
+            for mode in (EST_CURRENT, EST_ALL, EST_RUNNING):
+                cur = None
+                cmin, cmax = aligned(1), aligned(1)
+                for call in range(3):
+                    x = aligned(n, offset_elems=off)
+                    x[:] = rand(rng, n, specials=False) * (call + 1)
+                    if with_nan and call == 1:
+                        x[rng.integers(n)] = np.nan
+                    assert sim.fp8fq_minmax_f32(P(x), n, 1, n, P(cmin), P(cmax), mode, int(call > 0), 0.9, P(ws), None) == 0
+                    cur = est_rule(mode, call > 0, cur, np_minmax(x), 0.9)
+                    assert same_bits(np.array([cmin[0], cmax[0]]), np.array(cur, np.float32)), (n, off, with_nan, mode, call)
+                    assert ws[0] == 0
+
+
+def test_minmax_per_channel_rows_and_fused_prologue(sim, host_emul):
+    """minmax_rows_kernel (CTA per row) incl. the fused set_quant_range + table build (fp8fq_estimate_prepare_f32 ==
+    fp8fq_minmax_f32 + fp8fq_set_range_prepare_f32), per-channel and per-tensor."""
+    rng = np.random.default_rng(5)
+    ws = workspace(sim)
+    for C, inner in ((1, 5000), (7, 1), (64, 147), (5, 576), (3, 4097), (1000, 12)):
+        for M in (5, 3):
+            x = aligned(C * inner)
+            x[:] = rand(rng, C * inner, specials=False)
+            if C > 1:
+                x.reshape(C, inner)[C // 2, inner // 2] = np.nan
+            cmin, cmax, mv = aligned(C), aligned(C), aligned(C)
+            stride = sim.fp8fq_table_stride(M, 8, 1)
+            tab = aligned(stride * C)
+            assert sim.fp8fq_estimate_prepare_f32(P(x), C * inner, C, inner, P(cmin), P(cmax), EST_CURRENT, 0, 0.9, P(mv),
+                                                  M, 8, 1, P(tab), P(ws), None) == 0
+            with np.errstate(invalid="ignore"):
+                rmin, rmax = x.reshape(C, inner).min(1), x.reshape(C, inner).max(1)
+            assert same_bits(cmin, rmin) and same_bits(cmax, rmax)
+            with np.errstate(invalid="ignore"):
+                want_mv = np.abs(np.maximum(np.abs(rmin), rmax)).astype(np.float32)
+            assert same_bits(mv, want_mv)
+            tab2 = np.zeros_like(tab)
+            host_emul.emul_prepare(P(np.ascontiguousarray(mv)), L(C), F(M), 8, 1, P(tab2))
+            assert same_bits(tab, tab2), (C, inner, M)
+            # second call in "all" mode keeps the running extremes
+            x2 = aligned(C * inner)
+            x2[:] = x * 0.5
+            assert sim.fp8fq_minmax_f32(P(x2), C * inner, C, inner, P(cmin), P(cmax), EST_ALL, 1, 0.9, P(ws), None) == 0
+            with np.errstate(invalid="ignore"):       # np.minimum / np.maximum propagate NaN like torch.min / torch.max
+                want_min = np.minimum(rmin, x2.reshape(C, inner).min(1))
+                want_max = np.maximum(rmax, x2.reshape(C, inner).max(1))
+            assert same_bits(cmin, want_min) and same_bits(cmax, want_max)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn_act_estimate_prepare_statistics_without_materialising(sim, ref, host_emul, mode):
+    """minmax_bn_act_kernel: min / max of act(bn(x)) straight from x, NCHW rows and channel-innermost, then estimator
+    update + set_quant_range + table; unsupported shapes answer FP8FQ_ERR_UNSUPPORTED (caller composes)."""
+    rng = np.random.default_rng(8 + mode)
+    ws = workspace(sim)
+    cases = [(0, (2, 64, 28 * 28)), (0, (3, 128, 8 * 8)), (0, (1, 2, 9000)), (0, (3, 16, 8 * 8)), (0, (2, 24, 45)),
+             (1, (300, 64)), (1, (196, 96)), (1, (49, 1280)), (1, (100, 24)), (1, (40, 30))]
+    for nhwc, shape in cases:
+        if nhwc:
+            pixels, C = shape
+            hw, outer, n = 1, pixels, pixels * C
+            supported = C % 4 == 0
+        else:
+            N, C, hw = shape
+            outer, n = N * C, N * C * hw
+            supported = hw % 4 == 0 and 2 + 4095 // hw <= C
+        p0, p1 = bn_params(sim, rng, C, mode)
+        for act in (ACT_RELU, ACT_RELU6, ACT_NONE):
+            x = aligned(n)
+            x[:] = rand(rng, n, specials=False)
+            cmin, cmax, mv = aligned(1), aligned(1), aligned(1)
+            stride = sim.fp8fq_table_stride(5, 8, 1)
+            tab = aligned(stride)
+            code = sim.fp8fq_bn_act_estimate_prepare_f32(P(x), outer, hw, C, nhwc, P(p0), P(p1), mode, act, P(cmin), P(cmax),
+                                                         EST_CURRENT, 0, 0.9, P(mv), 5, 8, 1, P(tab), P(ws), None)
+            if not supported:
+                assert code == -2, (nhwc, shape)
+                continue
+            assert code == 0, (nhwc, shape)
+            v = ref_bn_act(ref, x, hw, C, nhwc, mode, p0, p1, act)
+            lo, hi = np_minmax(v)
+            assert same_bits(np.array([cmin[0], cmax[0]]), np.array([lo, hi])), (nhwc, shape, act)
+            assert same_bits(mv, np.array([abs(max(abs(lo), hi))], np.float32))
+            tab2 = np.zeros_like(tab)
+            host_emul.emul_prepare(P(np.ascontiguousarray(mv)), L(1), F(5), 8, 1, P(tab2))
+            assert same_bits(tab, tab2)
+            assert ws[0] == 0
+            # statistics only (maxval_out / table NULL), running update on top of the previous state
+            x2 = aligned(n)
+            x2[:] = x * 1.5
+            assert sim.fp8fq_bn_act_estimate_prepare_f32(P(x2), outer, hw, C, nhwc, P(p0), P(p1), mode, act, P(cmin),
+                                                         P(cmax), EST_RUNNING, 1, 0.9, None, 0.0, 0, 0, None, P(ws),
+                                                         None) == 0
+            v2 = ref_bn_act(ref, x2, hw, C, nhwc, mode, p0, p1, act)
+            want = est_rule(EST_RUNNING, True, (lo, hi), np_minmax(v2), 0.9)
+            assert same_bits(np.array([cmin[0], cmax[0]]), np.array(want, np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2b: MSE grid (FP_MSE_Estimator's candidate loop, range_estimators.py:337-347)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,inner,G", [(1, 9000, 111), (1, 777, 111), (5, 576, 40), (3, 1025, 37), (2, 1100, 1030)])
+def test_mse_grid_kernel_equals_candidate_loop(sim, ref, C, inner, G):
+    """mses[m, g, c] += mean((x - Q(x; grid[g, c], M_m))^2) for all candidates in one sweep: register-resident slices
+    (16 or 4 elements per thread), candidate tables staged in shared memory a group at a time, [warps][G] partials,
+    double atomics; the mantissa sweep M = 1..6 covers K <= 3 and K > 3, and accumulation across calls."""
+    rng = np.random.default_rng(C * 1000 + G)
+    n = C * inner
+    x = aligned(n)
+    x[:] = rand(rng, n, specials=False)
+    absmax = np.abs(x.reshape(C, inner)).max(1)
+    grid = np.ascontiguousarray(np.linspace(0.1 * absmax, 1.2 * absmax, G, dtype=np.float32))     # [G, C]
+    mbits = [5.0] if G > 200 else [float(m) for m in range(1, 7)]
+    arr = (F * len(mbits))(*mbits)
+    tf = sim.fp8fq_mse_table_floats(arr, len(mbits), 8, 1, G, C)
+    assert tf > 0
+    scratch = np.zeros(tf // 2 + 2, np.float64).view(np.float32)          # 8-byte aligned
+    mses = np.zeros((len(mbits), G, C), np.float32)
+    for rep in range(2):
+        assert sim.fp8fq_mse_grid_f32(P(x), n, C, inner, P(grid), G, arr, len(mbits), 8, 1, P(mses), P(scratch), None) == 0
+    want = np.zeros((len(mbits), G, C), np.float64)
+    for mi, M in enumerate(mbits):
+        for g in range(G):
+            y = ref_quant(ref, x, grid[g], M, per_channel=True)[0]
+            d = (x - y).astype(np.float32).astype(np.float64).reshape(C, inner)
+            want[mi, g] = (d * d).mean(1)
+    np.testing.assert_allclose(mses, 2 * want, rtol=2e-5, atol=1e-12)
+    # same selection as the reference's argmin over candidates
+    assert np.array_equal(mses[-1].argmin(0), (2 * want[-1]).astype(np.float32).argmin(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# STE backward (autograd through fp8_quantizer.py:112-132)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,sb,pc", [(5, 1, False), (4, 1, True), (3, 0, False), (2, 1, True), (5, 0, True)])
+def test_backward_kernel_gradients(sim, ref, M, sb, pc):
+    """grad_x = ((g * s) / s) * clamp weight with autograd's roundings; acc[2c] the clipping term and acc[2c+1] the scale
+    term of d/dmaxval (include/fp8fq.h); exact clamp ties get weight 1/2; NaN inputs poison their gradients."""
+    rng = np.random.default_rng(M * 10 + sb)
+    for C, inner in (((6, 4096 + 8), (3, 77)) if pc else ((1, 40000), (1, 13))):
+        for off in (0, 1):
+            n = C * inner
+            x, g = aligned(n, offset_elems=off), aligned(n, offset_elems=off)
+            x[:] = rand(rng, n, scale=2.0, specials=False)
+            g[:] = rng.standard_normal(n).astype(np.float32)
+            mv = (np.full(C, 2.25, np.float32) if C == 1 else (1.0 + rng.random(C) * 2).astype(np.float32))
+            xv = x.reshape(C, inner)
+            xv[:, 0] = mv                   # exact ties with the clamp bounds
+            xv[:, 1 % inner] = -mv if sb else 0.0
+            if inner > 4:
+                xv[0, 3] = np.nan
+            tab = table_for(sim, mv, M, 8, sb)
+            gx = aligned(n, offset_elems=off)
+            acc = np.zeros(2 * C, np.float64)
+            assert sim.fp8fq_fake_quant_backward_f32(P(g), P(x), P(gx), P(tab), n, C, inner, M, 8, sb, P(acc), None) == 0
+            # reference, element by element from the documented formula
+            y, e, _ = ref_quant(ref, x, mv, M, 8, sb, per_channel=True)
+            K = max(1, 2 ** (8 - sb - M) - 1)
+            stride, KP = tab.size // C, (K + 2) & ~1
+            tabv = tab.reshape(C, stride)
+            with np.errstate(invalid="ignore"):
+                ei = np.nan_to_num(e.reshape(C, inner), nan=1).astype(np.int64)
+            s = np.take_along_axis(tabv[:, 8 + KP:8 + KP + 2 * (K + 1):2], ei, axis=1)
+            gv, yv = g.reshape(C, inner), y.reshape(C, inner)
+            hi = mv[:, None]
+            lo = -hi if sb else np.zeros_like(hi)
+            with np.errstate(invalid="ignore", over="ignore"):
+                wx = np.where(xv < lo, 0.0, np.where(xv == lo, 0.5, 1.0)).astype(np.float32)
+                tt = np.maximum(xv, lo)
+                wt = np.where(tt > hi, 0.0, np.where(tt == hi, 0.5, 1.0)).astype(np.float32)
+                clip = ((wx - 1.0) if sb else np.zeros_like(wx)) * wt + (1.0 - wt)
+                xc = np.minimum(tt, hi)
+                want_gx = ((gv * s).astype(np.float32) / s).astype(np.float32) * (wx * wt)
+                want_gx = np.where(np.isnan(xv), np.float32(np.nan), want_gx).astype(np.float32)
+                a1 = np.where(np.isnan(xv), np.nan, gv.astype(np.float64) * clip)
+                a2 = gv.astype(np.float64) * (yv.astype(np.float64) - xc.astype(np.float64))
+            assert same_bits(gx.reshape(C, inner), want_gx), (M, sb, C, inner, off)
+            accv = acc.reshape(C, 2)
+            for c in range(C):
+                if np.isnan(xv[c]).any():
+                    assert np.isnan(accv[c]).all()
+                else:
+                    np.testing.assert_allclose(accv[c, 0], a1[c].sum(), rtol=1e-4, atol=1e-4)
+                    np.testing.assert_allclose(accv[c, 1], a2[c].sum(), rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# INT uniform quantisers (uniform_quantizers.py:107-164, 224-246, 303-314)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("symmetric", [0, 1])
+def test_uniform_quantisers_equal_serial_emulation(sim, host_emul, symmetric):
+    rng = np.random.default_rng(40 + symmetric)
+    for n_bits in (8, 4, 2):
+        for C, inner in ((1, 30001), (1, 5), (9, 147), (4, 1025)):
+            x = aligned(C * inner)
+            x[:] = rand(rng, C * inner)
+            fin = np.where(np.isfinite(x), x, 0).reshape(C, inner)
+            xmin, xmax = fin.min(1).astype(np.float32), fin.max(1).astype(np.float32)
+            if symmetric and n_bits == 4:
+                xmin = np.abs(xmin)                      # unsigned range
+            delta, zf, sg = aligned(C), aligned(C), aligned(1)
+            tab = aligned(sim.fp8fq_uniform_table_floats(C))
+            assert sim.fp8fq_uniform_prepare_f32(P(xmin), P(xmax), C, n_bits, symmetric, 0, 1e-8, P(delta), P(zf), P(sg),
+                                                 P(tab), None) == 0
+            delta2, tab2 = np.zeros(C, np.float32), np.zeros_like(tab)
+            assert host_emul.emul_uq_prepare(P(xmin), P(xmax), L(C), n_bits, symmetric, F(1e-8), P(delta2), P(tab2)) == 0
+            assert same_bits(delta, delta2) and same_bits(tab, tab2)
+            assert sg[0] == (1.0 if np.minimum(xmin, 0).min() < 0 else 0.0)
+            y, y2 = aligned(C * inner), np.zeros(C * inner, np.float32)
+            assert sim.fp8fq_uniform_quant_f32(P(x), P(y), P(tab), C * inner, C, inner, None) == 0
+            host_emul.emul_uq_quant(P(x), P(y2), P(tab2), L(C), L(inner))
+            assert same_bits(y, y2), (symmetric, n_bits, C, inner)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# data formats either side of the path
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,C,H,W,k", [(2, 3, 16, 12, 7), (1, 1, 8, 8, 3), (3, 4, 10, 14, 5), (1, 3, 224, 224, 7)])
+def test_space_to_depth_gather(sim, N, C, H, W, k):
+    """y[n, Y, X, c*4 + p*2 + q] = xpad[n, c, 2Y + p, 2X + q] with `pad` zero rows / columns; channels >= 4C zero."""
+    rng = np.random.default_rng(N * 100 + k)
+    pad, a = k // 2, (k + 1) // 2
+    hs, ws = H // 2 + a - 1, W // 2 + a - 1
+    x = aligned(N * C * H * W)
+    x[:] = rng.standard_normal(x.size).astype(np.float32)
+    y = aligned(N * hs * ws * 16)
+    y[:] = 7.0
+    assert sim.fp8fq_space_to_depth2_nhwc_f32(P(x), P(y), N, C, H, W, pad, hs, ws, None) == 0
+    xp = np.zeros((N, C, 2 * hs, 2 * ws), np.float32)
+    xv = x.reshape(N, C, H, W)
+    hh, wwid = min(H, 2 * hs - pad), min(W, 2 * ws - pad)
+    xp[:, :, pad:pad + hh, pad:pad + wwid] = xv[:, :, :hh, :wwid]
+    want = np.zeros((N, hs, ws, 16), np.float32)
+    for c in range(C):
+        for p in range(2):
+            for q in range(2):
+                want[..., c * 4 + p * 2 + q] = xp[:, c, p::2, q::2]
+    assert same_bits(y.reshape(N, hs, ws, 16), want)
+
+
+@pytest.mark.parametrize("N,H,W,C,k,s,p", [(2, 12, 10, 8, 3, 2, 1), (1, 7, 7, 4, 2, 2, 0), (2, 9, 11, 12, 3, 1, 1),
+                                           (1, 112, 112, 64, 3, 2, 1), (3, 5, 4, 16, 5, 3, 2)])
+def test_max_pool_channel_innermost(sim, N, H, W, C, k, s, p):
+    """ATen's selection rule (val > max || isnan(val), row-major window order, -inf padding): NaN propagates."""
+    rng = np.random.default_rng(H * W + C)
+    x = aligned(N * H * W * C)
+    x[:] = rng.standard_normal(x.size).astype(np.float32)
+    x[rng.choice(x.size, size=5, replace=False)] = np.nan
+    ho, wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    y = aligned(N * ho * wo * C)
+    assert sim.fp8fq_max_pool2d_nhwc_f32(P(x), P(y), N, H, W, C, k, k, s, s, p, p, None) == 0
+    xv = np.full((N, H + 2 * p, W + 2 * p, C), -np.inf, np.float32)
+    xv[:, p:p + H, p:p + W] = x.reshape(N, H, W, C)
+    want = np.full((N, ho, wo, C), -np.inf, np.float32)
+    with np.errstate(invalid="ignore"):
+        for i in range(k):
+            for j in range(k):
+                v = xv[:, i:i + s * ho:s, j:j + s * wo:s][:, :ho, :wo]
+                want = np.where((v > want) | np.isnan(v), v, want)
+    assert same_bits(y.reshape(N, ho, wo, C), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host-buffer entry point: chunked H2D -> quantise -> D2H pipeline (memcpy stands in for the copies)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pinned", [0, 1])
+def test_host_entry_point_chunking(sim, ref, pinned):
+    """fp8fq_fake_quant_host_f32 splits the tensor into 8 Mi-element chunks (whole rows when per-channel, each chunk
+    seeing its own slice of the channel tables) over three rotating staging buffers; pageable and page-locked callers."""
+    sim.fp8fq_sim_report_pinned(pinned)
+    try:
+        rng = np.random.default_rng(50 + pinned)
+        for C, inner in ((1, (8 << 20) + 4099), (5, 3 << 20)):
+            n = C * inner
+            x = rng.standard_normal(n).astype(np.float32)
+            mv = np.abs(x.reshape(C, inner)).max(1).astype(np.float32)
+            y = np.zeros(n, np.float32)
+            assert sim.fp8fq_fake_quant_host_f32(P(x), P(y), P(mv), n, C, inner, 5, 8, 1, 0) == 0
+            assert same_bits(y, ref_quant(ref, x, mv, 5, per_channel=True)[0]), (C, inner, pinned)
+    finally:
+        sim.fp8fq_sim_report_pinned(0)

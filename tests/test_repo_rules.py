@@ -57,6 +57,7 @@ def test_only_tests_smoke_and_bench_import_the_oracle():
     for p in _py_files("fp8_quantization_b200"):
         text = open(p).read()
         assert "fp8_oracle" not in text and "oracle/_build" not in text and "host_emul" not in text, p
+        assert "fp8fq_sim" not in text and "host_sim" not in text, p   # the host simulation is test infrastructure
 
 
 def test_bench_and_entry_touch_the_oracle_only_where_allowed():
