@@ -36,6 +36,11 @@ def same_bits(a, b):
     return a.shape == b.shape and np.array_equal(bits(a), bits(b))
 
 
+def same_values(a, b):
+    """Bit equality, any NaN equal to any NaN (payload and sign of a NaN are not part of the contract)."""
+    return a.shape == b.shape and bool(np.all((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))))
+
+
 @pytest.fixture(scope="module")
 def sim(built):
     """libfp8fq_sim.so with the product's own ctypes signature table applied (so the table is exercised too)."""
@@ -703,3 +708,54 @@ def test_host_entry_point_chunking(sim, ref, pinned):
             assert same_bits(y, ref_quant(ref, x, mv, 5, per_channel=True)[0]), (C, inner, pinned)
     finally:
         sim.fp8fq_sim_report_pinned(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# degenerate ranges and the format limits, through the kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def test_degenerate_ranges_through_the_kernels(sim, ref):
+    """maxval 0 (whole channel NaN), inf, NaN, denormal, tiny and huge: tables flagged irregular / reciprocal-unusable
+    take the linear-scan and IEEE-division paths inside the row and stream kernels; results are the direct formula's."""
+    rng = np.random.default_rng(77)
+    mvs = np.array([0.0, np.inf, np.nan, 1e-45, 1e-39, 1.1754944e-38, 1e-30, 1e30, 3.0e38, 1.0, 2.0 ** -126 * 3],
+                   np.float32)
+    C, inner = mvs.size, 515
+    for M, sb in ((5, 1), (4, 1), (2, 1), (7, 1), (1, 1), (3, 0), (8, 0)):
+        x = aligned(C * inner)
+        base = rand(rng, (C, inner))
+        with np.errstate(invalid="ignore", over="ignore"):
+            scale = np.where(np.isfinite(mvs) & (mvs > 0), mvs, np.float32(1.0))[:, None]
+            x[:] = (base * scale).reshape(-1)
+        tab = table_for(sim, mvs, M, 8, sb)
+        y = aligned(C * inner)
+        assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), C * inner, C, inner, M, 8, sb, None) == 0
+        yr = ref_quant(ref, x, mvs, M, 8, sb, per_channel=True)[0]
+        bad = (bits(y) != bits(yr)) & ~(np.isnan(y) & np.isnan(yr))
+        assert not bad.any(), (M, sb, [int(c) for c in np.unique(np.nonzero(bad)[0] // inner)])
+        assert np.all(np.isnan(y.reshape(C, inner)[[0, 2]]))         # maxval 0 and NaN: the whole channel is NaN
+        # the same ranges one at a time through the per-tensor stream kernel
+        for c in range(C):
+            xt, yt = aligned(inner), aligned(inner)
+            xt[:] = x.reshape(C, inner)[c]
+            tc = table_for(sim, mvs[c:c + 1], M, 8, sb)
+            assert sim.fp8fq_fake_quant_f32(P(xt), P(yt), P(tc), inner, 1, inner, M, 8, sb, None) == 0
+            assert same_values(yt, yr.reshape(C, inner)[c]), (M, sb, c)
+
+
+@pytest.mark.parametrize("nb,M,sb", [(4, 1, 1), (4, 2, 1), (6, 3, 1), (8, 1, 1), (16, 12, 1), (16, 9, 1), (12, 4, 1),
+                                      (13, 12, 0), (2, 1, 1), (5, 5, 0)])
+def test_format_limits_through_the_stream_kernel(sim, ref, nb, M, sb):
+    """Run-time bit widths other than 8: up to E = 7 (127 exponent codes, the largest table) and M = 12."""
+    rng = np.random.default_rng(nb * 100 + M)
+    E = nb - sb - M
+    assert 0 <= E <= 7
+    n = 6001
+    x = aligned(n)
+    # spread the inputs over the format's whole exponent range
+    x[:] = (rng.standard_normal(n) * np.exp2(rng.uniform(-min(2 ** E, 60), 2, n))).astype(np.float32)
+    mv = np.array([3.7], np.float32)
+    tab = table_for(sim, mv, M, nb, sb)
+    y = aligned(n)
+    assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), n, 1, n, M, nb, sb, None) == 0
+    assert same_bits(y, ref_quant(ref, x, mv, M, nb, sb)[0]), (nb, M, sb)
+    assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), n, 1, n, 1, 16, 1, None) == -2      # E = 14: unsupported
