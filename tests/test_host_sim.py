@@ -759,3 +759,49 @@ def test_format_limits_through_the_stream_kernel(sim, ref, nb, M, sb):
     assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), n, 1, n, M, nb, sb, None) == 0
     assert same_bits(y, ref_quant(ref, x, mv, M, nb, sb)[0]), (nb, M, sb)
     assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), n, 1, n, 1, 16, 1, None) == -2      # E = 14: unsupported
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the kernels' code against the REAL reference's golden vectors
+# ---------------------------------------------------------------------------------------------------------------------
+def test_simulated_kernels_against_the_real_reference_golden_vectors(sim):
+    """tests/golden/fp8_quantizer.npz was written by the real reference (ATen on the CPU: Sleef / glibc log2 and pow).
+    The simulated kernels use the host libm for the prologue, so a scale-table entry can differ from ATen's by an ulp
+    (the reference's own backends differ from each other the same way); an ulp in a scale moves
+    ~1e-5 of the elements across a rounding tie.  Asserted per case: same exponent code and mantissa integer for all
+    but <= 2e-3 of the elements, dequantised floats within 1e-5 relative, NaN / zero-range channels identical."""
+    from conftest import load_golden
+
+    g = load_golden("fp8_quantizer.npz")
+    n_cases = int(g["num_cases"])
+    assert n_cases == 98
+    total = mism = 0
+    for i in range(n_cases):
+        name = f"c{i:03d}"
+        M, sb, pc = [int(v) for v in g[name + "_meta"]]
+        xs, y_ref, q_ref = g[name + "_x"], g[name + "_y"], g[name + "_q"]
+        mv = np.ascontiguousarray(g[name + "_maxval"], np.float32).reshape(-1)
+        C = mv.size if pc else 1
+        n = xs.size
+        x, y, codes = aligned(n), aligned(n), aligned(n, np.int32)
+        x[:] = xs.reshape(-1)
+        tab = table_for(sim, mv, M, 8, sb)
+        assert sim.fp8fq_fake_quant_codes_f32(P(x), P(y), P(codes), P(tab), n, C, n // C, M, 8, sb, None) == 0
+        y_ref, q_ref = y_ref.reshape(-1), q_ref.reshape(-1)
+        nan_ref = np.isnan(y_ref)
+        assert np.array_equal(np.isnan(y), nan_ref), name
+        ok = ~nan_ref
+        with np.errstate(invalid="ignore"):
+            q_ours = (codes & 0xFFFF).astype(np.float32)
+            diff = ok & (q_ours != np.abs(q_ref))
+            rel = np.abs(y[ok].astype(np.float64) - y_ref[ok]) / np.maximum(np.abs(y_ref[ok].astype(np.float64)), 1e-30)
+        # a differing mantissa integer is a tie resolved the other way (or the (e, 2^(M+1)) / (e+1, 2^M) double code)
+        assert diff.sum() <= max(2, 2e-3 * n), (name, M, sb, pc, int(diff.sum()), n)
+        same_q = ok & ~diff
+        with np.errstate(invalid="ignore"):
+            rel_same = np.abs(y[same_q].astype(np.float64) - y_ref[same_q]) / np.maximum(np.abs(y_ref[same_q].astype(np.float64)), 1e-30)
+        assert rel_same.size == 0 or rel_same.max() < 1e-5, (name, rel_same.max())
+        assert rel.size == 0 or np.all((rel < 2.0 ** -(M - 1)) | (y_ref[ok] == 0)), name   # never more than one code away
+        total += int(ok.sum())
+        mism += int(diff.sum())
+    assert mism / total < 1e-4, (mism, total)
