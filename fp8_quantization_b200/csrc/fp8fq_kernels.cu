@@ -81,8 +81,8 @@ template <typename... KArgs, typename... Args>
 cudaError_t launch_impl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                         Args&&... args) {
 #ifdef FP8FQ_HOST_SIM
-  (void)pdl; (void)st;
-  fp8fq_sim::launch(kernel, grid, block, smem, std::forward<Args>(args)...);
+  (void)st;  // the PDL kernels are exactly the barrier-free streaming kernels: the simulation runs those without fibers
+  fp8fq_sim::launch(kernel, grid, block, smem, /*cooperative=*/!pdl, std::forward<Args>(args)...);
   return cudaSuccess;
 #else
   cudaLaunchConfig_t cfg{};

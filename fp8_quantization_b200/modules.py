@@ -238,7 +238,7 @@ class QuantizedActivation(QuantizedModule):
         models/mobilenet_v2_quantized.py:22-24) as one kernel when the ranges are fixed."""
         code = _act_code(act)
         mgr = self.activation_quantizer
-        if self._qa and code is not None and _fusable_manager(mgr) and a.is_cuda:
+        if self._qa and code is not None and _fusable_manager(mgr) and ops.on_device(a):
             q = mgr.quantizer
             a = ops.dense(a)
             b = _like(b, a)
@@ -262,7 +262,7 @@ class QuantizedActivation(QuantizedModule):
             for m in list(features)[:-1]:
                 h = m(h)
             res = last.conv_only(h)
-            if last._fused_epilogue_ok(res) and residual.is_cuda and residual.shape == res.shape:
+            if last._fused_epilogue_ok(res) and ops.on_device(residual) and residual.shape == res.shape:
                 qi, qo = last.activation_quantizer.quantizer, self.activation_quantizer.quantizer
                 res = ops.dense(res)
                 residual = _like(residual, res)
@@ -384,14 +384,14 @@ class BNFusedHijacker(QuantizationHijacker):
         return self._bn_folded
 
     def _fused_epilogue_ok(self, res) -> bool:
-        return (self._qa and not self.quantize_input and not self.training and res.is_cuda and res.dim() >= 2
+        return (self._qa and not self.quantize_input and not self.training and ops.on_device(res) and res.dim() >= 2
                 and res.dtype == torch.float32 and _act_code(self.activation_function) is not None
                 and _fusable_manager(self.activation_quantizer))
 
     def _fused_calibration_ok(self, res) -> bool:
         mgr = self.activation_quantizer
         return (FUSE_EPILOGUES and FUSE_CALIBRATION and self._qa and not self.quantize_input and not self.training
-                and not torch.is_grad_enabled() and res.is_cuda and res.dim() >= 2 and res.dtype == torch.float32
+                and not torch.is_grad_enabled() and ops.on_device(res) and res.dim() >= 2 and res.dtype == torch.float32
                 and _act_code(self.activation_function) is not None and isinstance(mgr, QuantizationManager)
                 and mgr.estimating() and not mgr.per_channel and mgr.device_resident_calibration())
 
@@ -470,7 +470,7 @@ def _space_to_depth_weight(w):
 class _Conv2dForward:
     def _stem_s2d_ok(self, x, weight) -> bool:
         k = self.kernel_size[0]
-        return (STEM_SPACE_TO_DEPTH and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+        return (STEM_SPACE_TO_DEPTH and not torch.is_grad_enabled() and ops.on_device(x) and x.dtype == torch.float32
                 and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 4 and x.shape[2] % 2 == 0
                 and x.shape[3] % 2 == 0 and ops.is_channels_last(weight) and self.groups == 1
                 and tuple(self.kernel_size) == (k, k) and k % 2 == 1 and k >= 3 and tuple(self.stride) == (2, 2)
@@ -598,7 +598,7 @@ class NativeMaxPool2d(nn.MaxPool2d):
     def forward(self, x):
         k, s, p = _pair(self.kernel_size), _pair(self.stride if self.stride is not None else self.kernel_size), \
             _pair(self.padding)
-        if (NATIVE_MAX_POOL and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        if (NATIVE_MAX_POOL and not torch.is_grad_enabled() and ops.on_device(x) and x.dtype == torch.float32 and x.dim() == 4
                 and ops.is_channels_last(x) and x.shape[1] % 4 == 0 and _pair(self.dilation) == (1, 1)
                 and not self.ceil_mode and not self.return_indices and x.numel() > 0
                 and x.shape[2] + 2 * p[0] >= k[0] and x.shape[3] + 2 * p[1] >= k[1]):
@@ -761,7 +761,7 @@ class QuantizedModel(nn.Module):
             q = mgr.quantizer
             w = m.weight
             if (not isinstance(mgr, QuantizationManager) or not isinstance(q, FPQuantizer) or mgr.estimating()
-                    or not w.is_cuda or w.dtype != torch.float32
+                    or not ops.on_device(w) or w.dtype != torch.float32
                     or not (w.is_contiguous() or ops.is_channels_last(w))):
                 continue
             w = w.detach()

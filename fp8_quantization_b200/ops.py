@@ -26,6 +26,19 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def on_device(t) -> bool:
+    """The one gate that decides whether a tensor may go to the kernels: it must live on a CUDA device.  Every fused
+    path of the module layer asks this (and ``_require`` enforces it), so the package has no CPU path.  (Being the
+    single gate is also what lets the test-suite put a functional simulation of the kernels behind the same Python
+    layer; nothing in the package itself ever does.)"""
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
+def default_device() -> torch.device:
+    """Where range scalars given as Python floats are materialised: the current CUDA device."""
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def is_channels_last(t: torch.Tensor) -> bool:
     """Dense channel-innermost memory ([N, H, W, C] / [N, D, H, W, C]) that is not also plain contiguous."""
     if t.is_contiguous():

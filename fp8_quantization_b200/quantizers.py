@@ -243,12 +243,12 @@ class FPQuantizer(QuantizerBase):
         if not self.set_maxval:
             return
         if not isinstance(x_max, torch.Tensor):
-            dev = self._maxval.device if self._maxval.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            dev = self._maxval.device if ops.on_device(self._maxval) else ops.default_device()
             x_max = torch.tensor([float(x_max)], dtype=torch.float32, device=dev)
             x_min = torch.tensor([float(x_min)], dtype=torch.float32, device=dev)
         if not isinstance(x_min, torch.Tensor):
             x_min = torch.full_like(x_max, float(x_min))
-        if not x_max.is_cuda:
+        if not ops.on_device(x_max):
             raise Fp8fqError("set_quant_range: range tensors must live on the GPU (no CPU path)")
         x_min = x_min.detach().to(torch.float32).reshape(-1).contiguous()
         x_max = x_max.detach().to(torch.float32).reshape(-1).contiguous()
@@ -264,7 +264,7 @@ class FPQuantizer(QuantizerBase):
             self.learn_mantissa_bits()
 
     def _param_device(self):
-        return self._maxval.device if self._maxval.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        return self._maxval.device if ops.on_device(self._maxval) else ops.default_device()
 
     def learn_maxval(self):  # :248-250 (registered as ``_maxval``; ``.maxval`` returns the Parameter)
         self.learning_maxval = True
@@ -384,13 +384,13 @@ class AsymmetricUniformQuantizer(QuantizerBase):
 
     def _as_device_ranges(self, x_min, x_max):
         if not torch.is_tensor(x_max):
-            dev = torch.device("cuda", torch.cuda.current_device())
+            dev = ops.default_device()
             x_min = torch.tensor([float(x_min)], dtype=torch.float32, device=dev)
             x_max = torch.tensor([float(x_max)], dtype=torch.float32, device=dev)
         if x_min.dim() > 0 and x_min.numel() > 1 and not self.per_channel:
             raise ValueError("x_min and x_max must be a float or 1-D Tensor for per-tensor quantization "
                              "(per_channel=False)")
-        if not x_max.is_cuda:
+        if not ops.on_device(x_max):
             raise Fp8fqError("set_quant_range: range tensors must live on the GPU (no CPU path)")
         return (x_min.detach().to(torch.float32).reshape(-1).contiguous(),
                 x_max.detach().to(torch.float32).reshape(-1).contiguous())

@@ -132,15 +132,17 @@ namespace fp8fq_sim {
 float* dynamic_smem();
 void cta_barrier();                       // __syncthreads
 float warp_exchange(float v, int lane_xor);  // __shfl_xor_sync over the full mask
-void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_body);
+// cooperative = false: the kernel is declared barrier-free (no __syncthreads, no shuffles) and its threads run as plain
+// calls, one after another, without fibers (10x faster); reaching a barrier in that mode aborts with a message.
+void run_grid(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& thread_body);
 int64_t launches();
 int64_t ctas_run();
 
 template <typename... KArgs, typename... Args>
-void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, bool cooperative, Args&&... args) {
   // kernel parameters are passed by value, converted to the parameter types like a real launch does
   std::tuple<std::decay_t<KArgs>...> params(static_cast<std::decay_t<KArgs>>(std::forward<Args>(args))...);
-  run_grid(grid, block, smem, [&]() { std::apply(kernel, params); });
+  run_grid(grid, block, smem, cooperative, [&]() { std::apply(kernel, params); });
 }
 
 }  // namespace fp8fq_sim

@@ -13,20 +13,95 @@ constexpr size_t kDynSmemFloats = 64 * 1024;  // 256 KB >= any dynamic shared me
 
 enum State { RUNNABLE, AT_CTA_BARRIER, AT_WARP_BARRIER, DONE };
 
+// Context switch.  glibc's swapcontext saves and restores the signal mask with two system calls per switch, which
+// dominates the run time of the barrier-heavy kernels; on x86-64 a fiber is therefore just a saved stack pointer and the
+// switch saves / restores the callee-saved registers (System V ABI: rbx, rbp, r12-r15, plus the SSE / x87 control words).
+// Other architectures use ucontext.
+#if defined(__x86_64__) && !defined(FP8FQ_SIM_UCONTEXT)
+#define FP8FQ_SIM_ASM_SWITCH 1
+extern "C" void fp8fq_sim_switch(void** save_sp, void* load_sp);
+asm(R"(
+    .text
+    .hidden fp8fq_sim_switch
+    .globl fp8fq_sim_switch
+    .type fp8fq_sim_switch,@function
+fp8fq_sim_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size fp8fq_sim_switch,.-fp8fq_sim_switch
+)");
+struct Fiber {
+  void* sp;
+  State st;
+};
+void* g_sched_sp = nullptr;
+#else
 struct Fiber {
   ucontext_t ctx;
   State st;
 };
+ucontext_t g_sched;
+#endif
 
 alignas(16) float g_dyn_smem[kDynSmemFloats];
 std::vector<Fiber> g_fibers;
 std::vector<char> g_stacks;
 std::vector<float> g_warp_slots;  // [warps][32]
-ucontext_t g_sched;
 const std::function<void()>* g_body = nullptr;
 int g_cur = -1;
 int64_t g_launches = 0, g_ctas = 0;
 
+#ifdef FP8FQ_SIM_ASM_SWITCH
+void yield_to_scheduler() { fp8fq_sim_switch(&g_fibers[g_cur].sp, g_sched_sp); }
+
+// first activation of a fiber "returns" here; it never returns itself (there is no caller frame): after the body it
+// marks the fiber done and switches to the scheduler for good
+__attribute__((no_sanitize_address)) void trampoline() {
+  (*g_body)();
+  g_fibers[g_cur].st = DONE;
+  yield_to_scheduler();
+  abort();  // a finished fiber is never resumed
+}
+
+void init_fiber(Fiber& f, char* stack, size_t bytes) {
+  // stack image popped by fp8fq_sim_switch: [mxcsr | x87 cw][r15][r14][r13][r12][rbx][rbp][return address]
+  uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+  uint64_t* sp = reinterpret_cast<uint64_t*>(top) - 1;  // slot the ABI expects above the return address (alignment)
+  *sp = 0;
+  *--sp = reinterpret_cast<uint64_t>(&trampoline);       // after `ret`: rsp = top - 8, i.e. 8 mod 16 as at a call
+  for (int i = 0; i < 6; ++i) *--sp = 0;                 // rbp, rbx, r12-r15
+  uint32_t csr[2];
+  asm volatile("stmxcsr %0" : "=m"(csr[0]));
+  uint16_t cw;
+  asm volatile("fnstcw %0" : "=m"(cw));
+  csr[1] = cw;
+  --sp;
+  memcpy(sp, csr, 8);
+  f.sp = sp;
+  f.st = RUNNABLE;
+}
+
+void resume(Fiber& f) { fp8fq_sim_switch(&g_sched_sp, f.sp); }
+#else
 void yield_to_scheduler() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
 
 void trampoline() {
@@ -34,6 +109,18 @@ void trampoline() {
   g_fibers[g_cur].st = DONE;
   // returning resumes uc_link = the scheduler
 }
+
+void init_fiber(Fiber& f, char* stack, size_t bytes) {
+  getcontext(&f.ctx);
+  f.ctx.uc_stack.ss_sp = stack;
+  f.ctx.uc_stack.ss_size = bytes;
+  f.ctx.uc_link = &g_sched;
+  makecontext(&f.ctx, trampoline, 0);
+  f.st = RUNNABLE;
+}
+
+void resume(Fiber& f) { swapcontext(&g_sched, &f.ctx); }
+#endif
 
 void warp_barrier() {
   g_fibers[g_cur].st = AT_WARP_BARRIER;
@@ -45,15 +132,7 @@ void run_cta(unsigned nthreads) {
   g_fibers.resize(nthreads);
   if (g_stacks.size() < (size_t)nthreads * kStackBytes) g_stacks.resize((size_t)nthreads * kStackBytes);
   g_warp_slots.assign((size_t)nwarps * 32, 0.0f);
-  for (unsigned t = 0; t < nthreads; ++t) {
-    Fiber& f = g_fibers[t];
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = g_stacks.data() + (size_t)t * kStackBytes;
-    f.ctx.uc_stack.ss_size = kStackBytes;
-    f.ctx.uc_link = &g_sched;
-    makecontext(&f.ctx, trampoline, 0);
-    f.st = RUNNABLE;
-  }
+  for (unsigned t = 0; t < nthreads; ++t) init_fiber(g_fibers[t], g_stacks.data() + (size_t)t * kStackBytes, kStackBytes);
   unsigned alive = nthreads;
   while (alive > 0) {
     bool progressed = false;
@@ -61,7 +140,7 @@ void run_cta(unsigned nthreads) {
       if (g_fibers[t].st != RUNNABLE) continue;
       g_cur = (int)t;
       threadIdx = uint3{t % blockDim.x, (t / blockDim.x) % blockDim.y, t / (blockDim.x * blockDim.y)};
-      swapcontext(&g_sched, &g_fibers[t].ctx);
+      resume(g_fibers[t]);
       progressed = true;
       if (g_fibers[t].st == DONE) --alive;
     }
@@ -103,12 +182,20 @@ void run_cta(unsigned nthreads) {
 
 float* dynamic_smem() { return g_dyn_smem; }
 
+void not_cooperative(const char* what) {
+  fprintf(stderr, "fp8fq_sim: %s reached in a kernel that was launched as barrier-free (launch_impl's `pdl` kernels); "
+                  "launch it cooperatively\n", what);
+  abort();
+}
+
 void cta_barrier() {
+  if (g_cur < 0) not_cooperative("__syncthreads");
   g_fibers[g_cur].st = AT_CTA_BARRIER;
   yield_to_scheduler();
 }
 
 float warp_exchange(float v, int lane_xor) {
+  if (g_cur < 0) not_cooperative("__shfl_xor_sync");
   const int warp = g_cur >> 5, lane = g_cur & 31;
   float* slots = g_warp_slots.data() + (size_t)warp * 32;
   slots[lane] = v;
@@ -122,7 +209,7 @@ float warp_exchange(float v, int lane_xor) {
   return r;
 }
 
-void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_body) {
+void run_grid(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& thread_body) {
   if (g_cur != -1) {
     fprintf(stderr, "fp8fq_sim: nested launch\n");
     abort();
@@ -146,7 +233,16 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& t
         blockIdx = uint3{bx, by, bz};
         // shared memory is uninitialised on the GPU: poison the dynamic part so that a read-before-write shows up
         if (smem) memset(g_dyn_smem, 0xff, smem);
-        run_cta(nthreads);
+        if (cooperative) {
+          run_cta(nthreads);
+        } else {
+          g_cur = -2;   // plain mode: a barrier aborts
+          for (unsigned t = 0; t < nthreads; ++t) {
+            threadIdx = uint3{t % blockDim.x, (t / blockDim.x) % blockDim.y, t / (blockDim.x * blockDim.y)};
+            thread_body();
+          }
+          g_cur = -1;
+        }
         ++g_ctas;
       }
   g_body = nullptr;

@@ -1,0 +1,369 @@
+"""CPU: the product's Python layer (quantisers, estimators, manager, fused modules, whole-model flows) running on the
+host SIMULATION of the kernels (fixture ``simdev``: tests/host_sim), against the golden vectors written by the REAL
+reference (tests/golden/make_golden.py).  The reference produced them on the CPU, so the convolutions here are the same
+MKL-DNN ones; what differs is libm inside the prologue (glibc here, Sleef in ATen), i.e. ulps in a few scale-table
+entries -- tolerances are stated at each assertion.  These are the model-level checks of tests/test_gpu_fused.py and
+tests/test_gpu_configs.py, runnable without a GPU; the GPU runs remain the parity tests proper."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import bits, load_golden, ulp_diff
+
+
+def _qparams(M, **kw):
+    from fp8_quantization_b200 import workloads
+
+    qp = workloads.readme_quant_params(M, **kw)
+    qp.pop("quant_setup")
+    return qp
+
+
+def test_quantizer_and_manager_flow(simdev):
+    """FPQuantizer / QuantizationManager through the simulation: estimate -> fix -> quantise, and the product still
+    refuses CPU tensors once the fixture is gone (checked in tests/test_capi_symbols.py)."""
+    import fp8_quantization_b200 as fq
+    from oracle import fp8_oracle as O
+
+    torch.manual_seed(3)
+    x = torch.randn(4, 16, 14, 14)
+    mgr = fq.QuantizationManager(qmethod=fq.FPQuantizer, init=fq.AllMinMaxEstimator,
+                                 qparams=dict(n_bits=8, mantissa_bits=5, set_maxval=True))
+    with torch.no_grad():
+        y = mgr(x)
+        assert float(mgr.quantizer.maxval) == float(x.abs().max())
+        mgr.fix_ranges()
+        assert torch.equal(mgr(x), y)
+        mgr.estimate_ranges()
+        mgr(x * 0.5)                       # allminmax keeps the running extremes
+        assert float(mgr.quantizer.maxval) == float(x.abs().max())
+    yo = O.fake_quant(x, 8, mgr.quantizer.maxval, torch.tensor([5.0]), 1)
+    assert int(ulp_diff(y, yo).max()) <= 1 or (ulp_diff(y, yo) > 1).float().mean().item() < 1e-4
+
+
+def test_quantlinear_config1_matches_reference_golden(simdev):
+    """BASELINE config 1: Linear(1024,1024), E2M5 per-channel weights, against the real reference module."""
+    from fp8_quantization_b200 import modules
+
+    g = load_golden("modules.npz")
+    lin = modules.QuantLinear(1024, 1024, **_qparams(5))
+    lin.weight.data = torch.from_numpy(g["lin_w"])
+    lin.bias.data = torch.from_numpy(g["lin_b"])
+    x = torch.from_numpy(g["lin_x"])
+    lin.quantized()
+    with torch.no_grad():
+        y_cal = lin(x)
+        lin.fix_ranges()
+        y = lin(x)
+        wq = lin.weight_quantizer(lin.weight.detach())
+    assert torch.equal(y_cal, y)
+    assert np.array_equal(lin.weight_quantizer.quantizer.maxval.numpy(), g["lin_w_maxval"])   # min/max: exact
+    ref_wq = torch.from_numpy(g["lin_wq"])
+    rel = (wq - ref_wq).abs() / ref_wq.abs().clamp_min(1e-30)
+    rel[ref_wq == 0] = (wq[ref_wq == 0] != 0).float()
+    assert (rel > 1e-5).float().mean().item() < 1e-4          # tie flips only
+    assert (ulp_diff(wq, ref_wq) > 1).float().mean().item() < 5e-3
+    # same GEMM library as the reference run: the activation range is reproduced to fp32 noise
+    np.testing.assert_allclose(lin.activation_quantizer.quantizer.maxval.numpy(), g["lin_a_maxval"], rtol=1e-5)
+    yr = torch.from_numpy(g["lin_y"])
+    step = float(g["lin_a_maxval"][0]) / 2 ** 5
+    assert ((y - yr).abs() > step).float().mean().item() < 1e-3
+
+
+def test_bnqconv_fused_matches_reference_golden(simdev):
+    """BNFusedHijacker: calibration (fused statistics kernel), fused validation (one epilogue launch), unfused
+    composition -- all against the real reference's output."""
+    from fp8_quantization_b200 import modules, ops
+
+    g = load_golden("modules.npz")
+    conv = modules.BNQConv(8, 16, 3, padding=1, activation=torch.nn.ReLU(), **_qparams(5))
+    conv.weight.data = torch.from_numpy(g["conv_w"])
+    conv.running_mean.data = torch.from_numpy(g["conv_mean"])
+    conv.running_var.data = torch.from_numpy(g["conv_var"])
+    conv.gamma.data = torch.from_numpy(g["conv_gamma"])
+    conv.beta.data = torch.from_numpy(g["conv_beta"])
+    conv.eval()
+    conv.quantized()
+    x = torch.from_numpy(g["conv_x"])
+    with torch.no_grad():
+        y_cal = conv(x)
+        conv.fix_ranges()
+        conv(x)
+        n0 = ops.launch_count()
+        y_fused = conv(x)                       # weight quant + ONE fused epilogue launch
+        assert ops.launch_count() - n0 == 2
+        conv.running_mean.add_(0.0)             # touching a BN tensor invalidates the cached parameters
+        n0 = ops.launch_count()
+        conv(x)
+        assert ops.launch_count() - n0 == 3
+        modules.FUSE_EPILOGUES = False
+        try:
+            y_unfused = conv(x)
+        finally:
+            modules.FUSE_EPILOGUES = True
+    np.testing.assert_allclose(conv.activation_quantizer.quantizer.maxval.numpy(), g["conv_a_maxval"], rtol=1e-5)
+    yr = torch.from_numpy(g["conv_y"])
+    step = float(g["conv_a_maxval"][0]) / 2 ** 5
+    for y in (y_cal, y_fused, y_unfused):
+        assert ((y - yr).abs() > step).float().mean().item() < 2e-3
+    # calibration pass and fused validation pass run the same fused epilogue kernel: same bits
+    assert torch.equal(bits(y_fused), bits(y_cal))
+    # the unfused composition goes through ATen-CPU's batch norm, whose fp32 arithmetic is not ATen-CUDA's (which the
+    # exact mode reproduces): agreement to a rounding tie, not bit for bit, on this backend
+    assert (bits(y_fused) != bits(y_unfused)).float().mean().item() < 2e-3
+
+
+def test_resnet18_m5_ranges_and_logits_vs_reference_golden(simdev):
+    """BASELINE config 2 at batch 2: the reference's QuantizedResNet(resnet18()) under seed 10 vs ours on the
+    simulation: same module tree, every quantiser's calibrated range, the logits, the launch counts of the fused
+    forward, and that restructuring the launches changes no bit."""
+    from torchvision.models import resnet18
+
+    from fp8_quantization_b200 import modules, ops, workloads
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    g = load_golden("resnet18_m5.npz")
+    torch.manual_seed(10)
+    model = workloads.QuantizedResNet(resnet18(), **workloads.readme_quant_params(5)).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen)
+    workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+    model.fix_ranges()
+    with torch.no_grad():
+        model(x)  # first fused forward packs the 20 batch norms (cached afterwards)
+        n0 = ops.launch_count()
+        logits = model(x)
+        # 1 multi-tensor weight launch + 12 BN epilogues + 8 block tails + avgpool + fc output = 23 launches
+        assert ops.launch_count() - n0 == 23
+        modules.FUSE_BLOCK_TAIL = modules.BATCH_WEIGHT_QUANT = False
+        try:
+            n0 = ops.launch_count()
+            logits_layerwise = model(x)
+            assert ops.launch_count() - n0 == 21 + 20 + 8 + 2
+        finally:
+            modules.FUSE_BLOCK_TAIL = modules.BATCH_WEIGHT_QUANT = True
+        assert torch.equal(logits, logits_layerwise)       # restructuring launches changes no bit
+        modules.FUSE_EPILOGUES = False
+        try:
+            n0 = ops.launch_count()
+            logits_unfused = model(x)                      # F.batch_norm / relu / add by ATen, one launch per quantiser
+            assert ops.launch_count() - n0 == 1 + 30
+        finally:
+            modules.FUSE_EPILOGUES = True
+    names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]
+    assert names == list(g["names"])
+    mods = dict(model.named_modules())
+    for i, n in enumerate(names):
+        ours = mods[n].maxval.reshape(-1).numpy()
+        ref = g[f"maxval_{i:02d}"]
+        if ours.size > 1:
+            assert np.array_equal(ours, ref), n            # per-channel weight ranges: min/max of identical weights
+        else:
+            # same convolution library as the reference run; upstream tie flips move a range by a step at most
+            np.testing.assert_allclose(ours, ref, rtol=2e-2, err_msg=n)
+    ref_logits = torch.from_numpy(g["logits"])
+    assert (logits - ref_logits).abs().max().item() < 0.5 * ref_logits.std().item()
+    assert F.cosine_similarity(logits.flatten(), ref_logits.flatten(), dim=0).item() > 0.98
+    # ATen-CPU's batch norm rounds differently from the ATen-CUDA arithmetic the fused epilogue reproduces
+    assert F.cosine_similarity(logits.flatten(), logits_unfused.flatten(), dim=0).item() > 0.995
+
+
+def test_resnet18_channels_last_network_on_the_simulation(simdev):
+    """model.to(memory_format=channels_last): channel-innermost epilogues, space-to-depth stem, native max-pool -- same
+    ranges as the NCHW network up to the convolutions' summation order, logits tracking it."""
+    from torchvision.models import resnet18
+
+    from fp8_quantization_b200 import modules, ops, workloads
+
+    def build(cl):
+        torch.manual_seed(10)
+        m = workloads.QuantizedResNet(resnet18(), **workloads.readme_quant_params(5)).eval()
+        return m.to(memory_format=torch.channels_last) if cl else m
+
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen)
+    outs = {}
+    for cl in (False, True):
+        model = build(cl)
+        workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+        model.fix_ranges()
+        with torch.no_grad():
+            model(x)
+            n0 = ops.launch_count()
+            outs[cl] = model(x)
+            n = ops.launch_count() - n0
+        # channels_last adds the space-to-depth gather and the native max-pool to the 23 quantiser launches
+        assert n == (25 if cl else 23), (cl, n)
+        if cl:
+            modules.STEM_SPACE_TO_DEPTH = modules.NATIVE_MAX_POOL = False
+            try:
+                with torch.no_grad():
+                    plain = model(x)
+            finally:
+                modules.STEM_SPACE_TO_DEPTH = modules.NATIVE_MAX_POOL = True
+            # max-pool: same bits; the re-indexed stem convolution: same sum in another order
+            assert F.cosine_similarity(outs[cl].flatten(), plain.flatten(), dim=0).item() > 0.999
+    assert F.cosine_similarity(outs[False].flatten(), outs[True].flatten(), dim=0).item() > 0.995
+
+
+def test_mobilenetv2_m4_vs_reference_golden(simdev):
+    """BASELINE config 3: QuantizedMobileNetV2 (M=4, per-channel weights, BN-fused modules, ReLU6) vs the real
+    reference: same fp32 network, same quantiser tree, ranges, logits; launch structure of the fused forward."""
+    from fp8_quantization_b200 import modules, ops, workloads
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    g = load_golden("mobilenetv2_m4.npz")
+    torch.manual_seed(10)
+    net = workloads.MobileNetV2()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(g["state_keys"])
+    mine = np.array([int(sd[k].float().contiguous().view(torch.int32).to(torch.int64).sum()) for k in sd.keys()],
+                    dtype=np.int64)
+    assert np.array_equal(mine, g["w_checksums"])
+    model = workloads.QuantizedMobileNetV2(net, **workloads.readme_quant_params(4)).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 3, 224, 224, generator=gen)
+    workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+    model.fix_ranges()
+    with torch.no_grad():
+        model(x)
+        n0 = ops.launch_count()
+        logits = model(x)
+        n_fused = ops.launch_count() - n0
+        modules.FUSE_BLOCK_TAIL = modules.BATCH_WEIGHT_QUANT = False
+        try:
+            n0 = ops.launch_count()
+            logits_layerwise = model(x)
+            n_layerwise = ops.launch_count() - n0
+        finally:
+            modules.FUSE_BLOCK_TAIL = modules.BATCH_WEIGHT_QUANT = True
+    assert n_layerwise == 53 + 52 + 10 + 2
+    assert n_fused == 2 + 42 + 10 + 2
+    assert torch.equal(logits, logits_layerwise)
+    names = [n for n, m in model.named_modules() if isinstance(m, FPQuantizer)]
+    assert names == list(g["names"])
+    mods = dict(model.named_modules())
+    for i, n in enumerate(names):
+        ours = mods[n].maxval.reshape(-1).numpy()
+        ref = g[f"maxval_{i:03d}"]
+        if ours.size > 1:
+            assert np.array_equal(ours, ref), n
+        elif ref[0] != 3.0:
+            np.testing.assert_allclose(ours, ref, rtol=3e-2, err_msg=n)
+    ref_logits = torch.from_numpy(g["logits"])
+    assert F.cosine_similarity(logits.flatten(), ref_logits.flatten(), dim=0).item() > 0.97
+
+
+def test_minmax_estimators_match_reference_golden_bit_exact(simdev):
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("estimators.npz")
+    for name, cls, kw in (("current", fq.CurrentMinMaxEstimator, {}), ("all", fq.AllMinMaxEstimator, {}),
+                          ("running", fq.RunningMinMaxEstimator, {"momentum": 0.9})):
+        for pc in (False, True):
+            key = f"{name}_{'pc' if pc else 'pt'}"
+            est = cls(per_channel=pc, **kw)
+            for i, x in enumerate(g[key + "_x"]):
+                mn, mx = est(torch.from_numpy(x))
+                assert np.array_equal(mn.numpy().reshape(-1), g[key + "_min"][i], equal_nan=True), (key, i)
+                assert np.array_equal(mx.numpy().reshape(-1), g[key + "_max"][i], equal_nan=True), (key, i)
+            est.reset()
+            assert est.current_xmin is None
+
+
+def test_mse_estimator_matches_reference_golden(simdev):
+    """FP_MSE_Estimator (range_estimators.py:285-369): same grid bit for bit, MSE table within fp32 summation noise,
+    same mantissa vote; a channel may pick a neighbouring candidate only when the two MSEs tie to 2e-4."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("mse_estimator.npz")
+    for key, pc, include in (("pt_sweep", False, True), ("pt_fixed", False, False), ("pc_sweep", True, True),
+                             ("pc_fixed", True, False)):
+        x = torch.from_numpy(g[key + "_x"])
+        q = fq.FPQuantizer(8, per_channel=pc, mantissa_bits=4, set_maxval=True, mse_include_mantissa_bits=include)
+        est = fq.FP_MSE_Estimator(per_channel=pc, quantizer=q)
+        mn, mx = est(x)
+        assert np.array_equal(est.search_grid.numpy(), g[key + "_grid"])
+        np.testing.assert_allclose(est.mses.numpy(), g[key + "_mses"], rtol=2e-4, atol=1e-12)
+        assert float(q._mbits_host) == float(g[key + "_best_m"]), key
+        ref_mx = g[key + "_xmax"]
+        same = mx.numpy() == ref_mx
+        if not same.all():
+            m_idx = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0].index(float(g[key + "_best_m"])) if include else 0
+            row = g[key + "_mses"][m_idx]
+            for c in np.nonzero(~same)[0]:
+                gi = int(np.argmin(np.abs(g[key + "_grid"][:, c] - mx.numpy()[c])))
+                assert abs(row[gi, c] - row[:, c].min()) <= 2e-4 * row[:, c].min()
+        q.set_quant_range(mn, mx)
+        assert torch.isfinite(q(x)).all()
+
+
+def test_line_search_estimator_vs_reference_golden(simdev):
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("line_search.npz")
+    for key in ("pt", "pc", "pt_onesided"):
+        ncand, M, pc = [int(v) for v in g[key + "_meta"]]
+        x = torch.from_numpy(g[key + "_x"])
+        q = fq.FPQuantizer(8, mantissa_bits=M, set_maxval=True)
+        est = fq.LineSearchEstimator(quantizer=q, per_channel=bool(pc), num_candidates=ncand)
+        mn, mx = est(x)
+        ref_loss = g[key + "_loss"]
+        np.testing.assert_allclose(est.loss_array[:, 1:], ref_loss[:, 1:], rtol=3e-4)
+        for c in range(ref_loss.shape[0]):
+            ours_i = int(round(float(mx[c]) / est.step_size))
+            assert ref_loss[c, ours_i] <= ref_loss[c].min() * (1 + 3e-4)
+        assert np.array_equal(mn.numpy() == 0, g[key + "_xmin"] == 0)
+
+
+def test_bn_reestimation_vs_reference_golden(simdev):
+    """utils/qat_utils.py:45-90 on the quantised network (default-on step of the reference's validate flow)."""
+    from fp8_quantization_b200 import modules, workloads
+
+    g = load_golden("bn_reestimate.npz")
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 6, 1, bias=False), torch.nn.BatchNorm2d(6))
+    seq.load_state_dict({k: torch.from_numpy(g["init_" + k.replace(".", "_")]) for k in seq.state_dict().keys()})
+
+    class Wrap(modules.QuantizedModel):
+        def __init__(self, f):
+            super().__init__((1, 3, 16, 16))
+            self.f = f
+
+        def forward(self, x):
+            return self.f(x)
+
+    model = Wrap(modules.quantize_model(seq, **_qparams(5))).eval()
+    xs = [torch.from_numpy(x) for x in g["x"]]
+    workloads.pass_data_for_range_estimation([xs[0]], model, True, True, 1)
+    model.fix_ranges()
+    n = workloads.reestimate_BN_stats(model, xs, num_batches=3)
+    assert n == 3 and not model.f[0].training and model.f[0].momentum == 0.1
+    for i in (0, 1):
+        np.testing.assert_allclose(model.f[i].running_mean.numpy(), g[f"mean_{i}"], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(model.f[i].running_var.numpy(), g[f"var_{i}"], rtol=2e-3, atol=2e-5)
+
+
+def test_uniform_quantisers_match_reference_golden(simdev):
+    """INT baselines (uniform_quantizers.py): IEEE-exact arithmetic -> bit-identical to the real reference's CPU run
+    with the CPU's scalar-division semantics selected."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("uniform_quantizers.npz")
+    n = int(g["num_cases"])
+    assert n == 24
+    for i in range(n):
+        name = f"u{i:02d}"
+        sym, nb, pc = [int(v) for v in g[name + "_meta"]]
+        cls = fq.SymmetricUniformQuantizer if sym else fq.AsymmetricUniformQuantizer
+        q = cls(n_bits=nb, per_channel=bool(pc))
+        q.aten_cuda_scalar_div = False
+        assert not q.is_initialized
+        q.set_quant_range(torch.from_numpy(g[name + "_min"]), torch.from_numpy(g[name + "_max"]))
+        assert q.is_initialized and q.symmetric == bool(sym)
+        assert np.array_equal(q.delta.reshape(-1).numpy(), g[name + "_delta"])
+        with torch.no_grad():
+            y = q(torch.from_numpy(g[name + "_x"]))
+        yr = torch.from_numpy(g[name + "_y"])
+        assert bool(((bits(y) == bits(yr)) | (torch.isnan(y) & torch.isnan(yr))).all()), name
