@@ -74,35 +74,15 @@ def ulp_diff(a, b):
 def simdev(built):
     """Puts the host SIMULATION of the kernels (tests/host_sim: the product's own .cu compiled by g++) behind the
     product's Python layer for the duration of one test, so that module / estimator / whole-model logic can be
-    checked on CPU tensors without a GPU.  Substitutes the package's single device gate (ops.on_device), the argument
-    check, the stream handle and the min/max workspace, and the loaded library.  TEST ONLY: the product has no CPU
-    path -- without this fixture a CPU tensor raises Fp8fqError (tests/test_capi_symbols.py)."""
-    import ctypes
-
-    from fp8_quantization_b200 import _lib, ops
-
-    handle = ctypes.CDLL(os.environ.get("FP8FQ_SIM_LIB") or os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim.so"))
-    for name, (res, args) in _lib.SIGNATURES.items():
-        fn = getattr(handle, name)
-        fn.restype, fn.argtypes = res, args
-
-    def require(t, name):
-        if not isinstance(t, torch.Tensor):
-            raise TypeError(f"{name} must be a torch.Tensor")
-        if t.dtype != torch.float32:
-            raise ops.Fp8fqError(f"{name} must be float32; got {t.dtype}")
-        if not t.is_contiguous() and not ops.is_channels_last(t):
-            raise ops.Fp8fqError(f"{name} must be contiguous (or dense channels_last)")
-
-    ws = torch.zeros(int(handle.fp8fq_minmax_workspace_bytes()) // 4, dtype=torch.int32)
-    saved = (_lib._lib, ops.on_device, ops.default_device, ops._require, ops._stream, ops._workspace)
-    _lib._lib = handle
-    ops.on_device = lambda t: isinstance(t, torch.Tensor)
-    ops.default_device = lambda: torch.device("cpu")
-    ops._require = require
-    ops._stream = lambda: None
-    ops._workspace = lambda device: ws
+    checked on CPU tensors without a GPU (tests/host_sim/harness.py).  TEST ONLY: the product has no CPU path --
+    without this fixture a CPU tensor raises Fp8fqError (tests/test_capi_symbols.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host_sim"))
+    try:
+        from harness import install_simulation
+    finally:
+        sys.path.pop(0)
+    restore = install_simulation()
     try:
         yield torch.device("cpu")
     finally:
-        _lib._lib, ops.on_device, ops.default_device, ops._require, ops._stream, ops._workspace = saved
+        restore()

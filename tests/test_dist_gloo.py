@@ -100,3 +100,107 @@ def test_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def _sim_worker(rank, world, port, q):
+    """BASELINE config 5 in miniature, through the product's real path on the host simulation of the kernels: the
+    quantised ResNet-18 calibrated on a batch sharded over the ranks (one MAX all-reduce of [-min, max] per activation
+    quantiser, incl. the fused calibration epilogue's statistics-only launch), validate counters summed across ranks,
+    and the MSE estimator's MAX / MEAN exchanges -- against a single process on the concatenated batch."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host_sim"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    from harness import install_simulation
+    install_simulation()
+    import numpy as np
+    from torchvision.models import resnet18
+
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import dist as fq_dist
+    from fp8_quantization_b200 import workloads
+
+    assert fq_dist.init_from_env(backend="gloo") and fq_dist.active()
+    report = {}
+
+    def build():
+        torch.manual_seed(10)
+        return workloads.QuantizedResNet(resnet18(), **workloads.readme_quant_params(5)).eval()
+
+    gen = torch.Generator().manual_seed(10)
+    gx = torch.randn(4, 3, 64, 64, generator=gen)        # the global batch, identical on every rank
+    labels = torch.tensor([1, 2, 3, 4])
+    local = fq_dist.shard_batch(gx)
+    dp = build()
+    workloads.pass_data_for_range_estimation([local], dp, True, True, 1)   # collectives inside
+    dp.fix_ranges()
+    m_dp = workloads.validate(dp, [local], [fq_dist.shard_batch(labels)])  # SUM of the four counters
+    fq_dist.enable(False)
+    sp = build()
+    workloads.pass_data_for_range_estimation([gx], sp, True, True, 1)      # single process, whole batch
+    sp.fix_ranges()
+    m_sp = workloads.validate(sp, [gx], [labels])
+    fq_dist.enable(True)
+    qs_dp = [(n, m) for n, m in dp.named_modules() if isinstance(m, fq.FPQuantizer)]
+    qs_sp = dict((n, m) for n, m in sp.named_modules() if isinstance(m, fq.FPQuantizer))
+    exact = close = 0
+    for n, m in qs_dp:
+        a, b = m.maxval.reshape(-1), qs_sp[n].maxval.reshape(-1)
+        if torch.equal(a, b):
+            exact += 1
+        elif torch.allclose(a, b, rtol=2e-2):
+            close += 1      # the convolution library may sum in another order at another batch size -> a tie flips
+        else:
+            report["range_mismatch"] = n
+    report["ranges"] = (exact, close, len(qs_dp))
+    # validate() sums its counters whenever a process group exists: the sharded run counts the 4 images once, the
+    # "single process" leg (every rank evaluating the whole batch) counts them once per rank; the means must agree
+    report["metrics"] = (m_dp["count"] == 4 and m_sp["count"] == 4 * world
+                         and abs(m_dp["loss"] - m_sp["loss"]) < 1e-3 * abs(m_sp["loss"])
+                         and m_dp["top_1_accuracy"] == m_sp["top_1_accuracy"]
+                         and m_dp["top_5_accuracy"] == m_sp["top_5_accuracy"])
+    report["metric_values"] = (m_dp, m_sp)
+    # every rank ends with the same ranges (they came out of the same all-reduces)
+    flat = torch.cat([m.maxval.reshape(-1) for _, m in qs_dp])
+    other = flat.clone()
+    fq_dist.all_reduce_max(other)
+    report["ranks_agree"] = bool(torch.equal(flat, other))
+
+    # FP_MSE_Estimator under DP: MAX of absmax defines the grid, MEAN of the per-shard MSE tables
+    g2 = torch.Generator().manual_seed(3)
+    gt = torch.randn(8, 16, 6, 6, generator=g2) * 2
+    q_dp = fq.FPQuantizer(8, mantissa_bits=4, set_maxval=True, mse_include_mantissa_bits=True)
+    e_dp = fq.FP_MSE_Estimator(quantizer=q_dp)
+    mn_dp, mx_dp = e_dp(fq_dist.shard_batch(gt))
+    fq_dist.enable(False)
+    q_sp = fq.FPQuantizer(8, mantissa_bits=4, set_maxval=True, mse_include_mantissa_bits=True)
+    e_sp = fq.FP_MSE_Estimator(quantizer=q_sp)
+    mn_sp, mx_sp = e_sp(gt)
+    fq_dist.enable(True)
+    report["mse"] = (bool(torch.equal(e_dp.search_grid, e_sp.search_grid))
+                     and bool(np.allclose(e_dp.mses.numpy(), e_sp.mses.numpy(), rtol=1e-5, atol=1e-12))
+                     and q_dp._mbits_host == q_sp._mbits_host and bool(torch.equal(mx_dp, mx_sp)))
+    fq_dist.barrier()
+    q.put((rank, report))
+    td.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_calibration_through_the_simulated_kernels(built):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sim_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        r = res[rank]
+        assert "range_mismatch" not in r, r
+        exact, close, total = r["ranges"]
+        # 21 weight + 29 activation quantisers (the tied one is shared); measured here: all 50 bit-identical
+        assert total == 50 and exact + close == total and exact >= 40, r["ranges"]
+        assert r["metrics"] and r["ranks_agree"] and r["mse"], r
