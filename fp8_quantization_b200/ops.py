@@ -88,6 +88,29 @@ def _opt_ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+_stride_cache = {}
+
+
+def _require_table(table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int, what: str):
+    """``table`` must hold the C channel tables of this format (include/fp8fq.h): the kernels index it by the format's
+    stride, so a table built for another format / channel count would be read out of bounds."""
+    key = (float(mantissa_bits), int(n_bits), int(sign_bits))
+    stride = _stride_cache.get(key)
+    if stride is None:
+        stride = _stride_cache[key] = table_stride(*key)
+    _require(table, what)
+    if table.numel() < stride * max(int(C), 1):
+        raise Fp8fqError(f"{what}: {table.numel()} floats, but {C} channel table(s) of this format need {stride * max(int(C), 1)}"
+                         " (was it prepared for another format or channel count?)")
+
+
+def _require_state(t: torch.Tensor, C: int, what: str):
+    """Per-channel estimator / range buffers written by the kernels: fp32, dense, at least C entries."""
+    _require(t, what)
+    if t.numel() < C:
+        raise Fp8fqError(f"{what}: {t.numel()} entries for {C} channel(s)")
+
+
 def format_split(mantissa_bits: float, n_bits: int, sign_bits: int):
     """(M, E, K) of fp8_quantizer.py:105-106; K = number of exponent codes."""
     M, E, K = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -112,6 +135,8 @@ def prepare(maxval: torch.Tensor, mantissa_bits: float, n_bits: int, sign_bits: 
     C = maxval.numel()
     if out is None:
         out = new_table(C, mantissa_bits, n_bits, sign_bits, maxval.device)
+    else:
+        _require_table(out, C, mantissa_bits, n_bits, sign_bits, "table")
     check(lib().fp8fq_prepare_f32(maxval.data_ptr(), C, float(mantissa_bits), int(n_bits), int(sign_bits),
                                   out.data_ptr(), _stream()), "fp8fq_prepare_f32")
     return out
@@ -127,8 +152,12 @@ def set_range_prepare(xmin: torch.Tensor, xmax: torch.Tensor, mantissa_bits: flo
         raise Fp8fqError("x_min and x_max must have the same number of elements")
     if maxval_out is None:
         maxval_out = torch.empty(C, dtype=torch.float32, device=xmax.device)
+    else:
+        _require_state(maxval_out, C, "maxval_out")
     if table_out is None:
         table_out = new_table(C, mantissa_bits, n_bits, sign_bits, xmax.device)
+    else:
+        _require_table(table_out, C, mantissa_bits, n_bits, sign_bits, "table_out")
     check(lib().fp8fq_set_range_prepare_f32(xmin.data_ptr(), xmax.data_ptr(), C, maxval_out.data_ptr(),
                                             float(mantissa_bits), int(n_bits), int(sign_bits),
                                             table_out.data_ptr(), _stream()), "fp8fq_set_range_prepare_f32")
@@ -139,6 +168,7 @@ def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: floa
                out: torch.Tensor = None):
     """FPQuantizer.forward (fp8_quantizer.py:91-133).  C == 1: per tensor; else channel = dim 0."""
     _require(x, "x")   # channels_last x: elementwise over the same memory; channel = dim 0 stays the outermost stride
+    _require_table(table, C, mantissa_bits, n_bits, sign_bits, "table")
     n = x.numel()
     out = _out_like(x, out, "fake_quant")
     inner = n // C if C > 0 else 0
@@ -151,6 +181,7 @@ def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: floa
 def fake_quant_codes(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int):
     """Returns (y, codes int32) -- codes = sign<<31 | e<<16 | q (parity tests)."""
     _require(x, "x")
+    _require_table(table, C, mantissa_bits, n_bits, sign_bits, "table")
     n = x.numel()
     y = torch.empty_like(x)
     codes = torch.empty_like(x, dtype=torch.int32)
@@ -192,6 +223,7 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
     _require(x, "x")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
+    _require_table(table, 1, mantissa_bits, n_bits, sign_bits, "table")
     out = _out_like(x, out, "bn_act_quant")
     if hw == 1 or is_channels_last(x):   # channel-innermost memory: [N, C] Linear outputs, channels_last activations
         check(lib().fp8fq_bn_act_quant_nhwc_f32(x.data_ptr(), out.data_ptr(), bn_scale.data_ptr(), _opt_ptr(bn_shift),
@@ -224,6 +256,8 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     _require_same_layout(x, residual, "bn_quant_add_act_quant")
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
+    _require_table(table_inner, 1, *fmt_inner, "table_inner")
+    _require_table(table_outer, 1, *fmt_outer, "table_outer")
     out = _out_like(x, out, "bn_quant_add_act_quant")
     if hw == 1 or is_channels_last(x):
         check(lib().fp8fq_bn_quant_add_act_quant_nhwc_f32(
@@ -250,6 +284,7 @@ def fake_quant_multi(xs, tables, Cs, mantissa_bits: float, n_bits: int, sign_bit
     descs = (TensorDesc * len(xs))()
     for d, x, y, t, C in zip(descs, xs, outs, tables, Cs):
         _require(x, "x")
+        _require_table(t, C, mantissa_bits, n_bits, sign_bits, "table")
         _out_like(x, y, "fake_quant_multi")
         d.x, d.y, d.table, d.C, d.inner = x.data_ptr(), y.data_ptr(), t.data_ptr(), C, x.numel() // C
     check(lib().fp8fq_fake_quant_multi_f32(descs, len(xs), float(mantissa_bits), int(n_bits), int(sign_bits),
@@ -262,6 +297,7 @@ def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign
     _require(a, "a")
     _require(b, "b")
     _require_same_layout(a, b, "add_act_quant")
+    _require_table(table, 1, mantissa_bits, n_bits, sign_bits, "table")
     out = _out_like(a, out, "add_act_quant")
     check(lib().fp8fq_add_act_quant_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), int(act),
                                         table.data_ptr(), float(mantissa_bits), int(n_bits), int(sign_bits),
@@ -275,6 +311,7 @@ def fake_quant_backward(grad_y, x, table, C: int, mantissa_bits: float, n_bits: 
     _require(x, "x")
     _require(grad_y, "grad_y")
     _require_same_layout(x, grad_y, "fake_quant_backward")
+    _require_table(table, C, mantissa_bits, n_bits, sign_bits, "table")
     n = x.numel()
     gx = torch.empty_like(x)
     acc = torch.empty(C, 2, dtype=torch.float64, device=x.device)
@@ -356,6 +393,8 @@ def minmax(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: b
     _require(x, "x")
     n = x.numel()
     C = x.shape[0] if per_channel else 1
+    _require_state(cur_min, C, "cur_min")
+    _require_state(cur_max, C, "cur_max")
     check(lib().fp8fq_minmax_f32(x.data_ptr(), n, C, n // C, cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode),
                                  1 if initialized else 0, float(momentum), _workspace(x.device).data_ptr(),
                                  _stream()), "fp8fq_minmax_f32")
@@ -368,6 +407,10 @@ def estimate_prepare(x, per_channel: bool, cur_min, cur_max, est_mode: int, init
     _require(x, "x")
     n = x.numel()
     C = x.shape[0] if per_channel else 1
+    _require_state(cur_min, C, "cur_min")
+    _require_state(cur_max, C, "cur_max")
+    _require_state(maxval_out, C, "maxval_out")
+    _require_table(table_out, C, mantissa_bits, n_bits, sign_bits, "table_out")
     check(lib().fp8fq_estimate_prepare_f32(x.data_ptr(), n, C, n // C, cur_min.data_ptr(), cur_max.data_ptr(),
                                            int(est_mode), 1 if initialized else 0, float(momentum),
                                            maxval_out.data_ptr(), float(mantissa_bits), int(n_bits), int(sign_bits),
@@ -386,6 +429,12 @@ def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_m
     rows, hw = _rows_hw(x, Cbn)
     nhwc = hw == 1 or is_channels_last(x)
     mb, nb, sb = fmt if fmt is not None else (0.0, 0, 0)
+    _require_state(cur_min, 1, "cur_min")
+    _require_state(cur_max, 1, "cur_max")
+    if maxval_out is not None:
+        _require_state(maxval_out, 1, "maxval_out")
+    if table_out is not None:
+        _require_table(table_out, 1, mb, nb, sb, "table_out")
     code = lib().fp8fq_bn_act_estimate_prepare_f32(
         x.data_ptr(), x.numel() // Cbn if nhwc else rows, hw, Cbn, 1 if nhwc else 0, bn_scale.data_ptr(),
         _opt_ptr(bn_shift), int(bn_mode), int(act), cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode),
@@ -406,6 +455,8 @@ def mse_grid(x, per_channel: bool, grid: torch.Tensor, mbit_list, n_bits: int, s
     C = x.shape[0] if per_channel else 1
     G = grid.shape[0]
     Mn = len(mbit_list)
+    if grid.numel() != G * C or mses.numel() != Mn * G * C:
+        raise Fp8fqError(f"mse_grid: grid must be [G, C] = [{G}, {C}] and mses [Mn, G, C] = [{Mn}, {G}, {C}]")
     arr = (ctypes.c_float * Mn)(*[float(m) for m in mbit_list])
     tf = lib().fp8fq_mse_table_floats(arr, Mn, int(n_bits), int(sign_bits), G, C)
     if tf < 0:

@@ -367,3 +367,39 @@ def test_uniform_quantisers_match_reference_golden(simdev):
             y = q(torch.from_numpy(g[name + "_x"]))
         yr = torch.from_numpy(g[name + "_y"])
         assert bool(((bits(y) == bits(yr)) | (torch.isnan(y) & torch.isnan(yr))).all()), name
+
+
+def test_ops_reject_tables_and_state_buffers_of_the_wrong_size(simdev):
+    """ops.py refuses a quantiser table prepared for another format / channel count and estimator-state buffers that
+    are too small, instead of letting a kernel index past their end."""
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import ops
+
+    x = torch.randn(8, 16)
+    t5 = ops.prepare(torch.tensor([3.0]), 5.0, 8, 1)                    # E2M5: 20 floats
+    t4 = ops.prepare(torch.tensor([3.0]), 4.0, 8, 1)                    # E3M4: 32 floats
+    assert t5.numel() == ops.table_stride(5, 8, 1) < ops.table_stride(4, 8, 1) == t4.numel()
+    ops.fake_quant(x, t5, 1, 5.0, 8, 1)
+    ops.fake_quant(x, t4, 1, 5.0, 8, 1)                                 # larger than needed is fine
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x, t5, 1, 4.0, 8, 1)                             # E2M5 table read as E3M4
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x, t5, 8, 5.0, 8, 1)                             # one table for 8 channels
+    with pytest.raises(fq.Fp8fqError):
+        ops.add_act_quant(x, x, 0, t5, 4.0, 8, 1)
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant_multi([x], [t5], [8], 5.0, 8, 1)
+    sc, sh = ops.bn_fold(torch.zeros(16), torch.ones(16), None, None, 1e-5)
+    with pytest.raises(fq.Fp8fqError):
+        ops.bn_act_quant(x, sc, sh, 0, t5, 4.0, 8, 1)
+    with pytest.raises(fq.Fp8fqError):
+        ops.bn_quant_add_act_quant(x, x, sc, sh, 0, t5, (5.0, 8, 1), t5, (4.0, 8, 1))
+    with pytest.raises(fq.Fp8fqError):
+        ops.minmax(x, True, torch.empty(4), torch.empty(8), 0, False)   # 8 channels, 4 slots
+    with pytest.raises(fq.Fp8fqError):
+        ops.estimate_prepare(x, True, torch.empty(8), torch.empty(8), 0, False, 0.9, torch.empty(8), 5.0, 8, 1,
+                             torch.empty(20))                            # table for 1 channel, 8 needed
+    with pytest.raises(fq.Fp8fqError):
+        ops.mse_grid(x, False, torch.ones(5, 2), [5.0], 8, 1, torch.zeros(1, 5, 1))
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x.double(), t5, 1, 5.0, 8, 1)
