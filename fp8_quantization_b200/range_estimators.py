@@ -312,8 +312,6 @@ class LineSearchEstimator(RangeEstimatorBase):
         from .quantizers import FPQuantizer
 
         qz = self.quantizer
-        if not isinstance(qz, FPQuantizer):
-            raise NotImplementedError("the fused line search is implemented for FPQuantizer")
         data = data.detach()
         data = data if data.is_contiguous() else data.contiguous()
         if self.loss_array is None:
@@ -322,7 +320,13 @@ class LineSearchEstimator(RangeEstimatorBase):
             dmin, dmax = mm.tolist()  # the reference reads float(data.min()) / float(data.max()) here too
             if self.one_sided_dist is None:
                 self.one_sided_dist = bool(dmin >= 0)
+            if not isinstance(qz, FPQuantizer) and not (self.one_sided_dist or qz.symmetric):
+                # range_estimators.py:190: the 2-D search of asymmetric quantisers is referenced there but not defined
+                raise NotImplementedError("2-D grid search (asymmetric quantiser, two-sided data) does not exist in the "
+                                          "reference either")
             self._define_search_range(data, dmin, dmax)
+        if not isinstance(qz, FPQuantizer):
+            return self._search_per_candidate(data)
         step = self.step_size
         C = self.channel_groups
         if qz.set_maxval:
@@ -337,6 +341,33 @@ class LineSearchEstimator(RangeEstimatorBase):
         inner = data.numel() // C
         loss = (mses[0].double() * inner).t().cpu().numpy()  # [C, G] sums of squared error
         self.loss_array[:, 1:] += loss
+        min_cand = self.loss_array.argmin(axis=1)
+        xmin = (np.zeros(C) if self.one_sided_dist else -step * min_cand).astype(np.single)
+        xmax = (step * min_cand).astype(np.single)
+        self.current_xmax = torch.tensor(xmax).to(device=data.device)
+        self.current_xmin = torch.tensor(xmin).to(device=data.device)
+        return self.current_xmin, self.current_xmax
+
+    def _search_per_candidate(self, data):
+        """range_estimators.py:236-256 as written, for quantisers the MSE-grid kernel does not cover (the INT uniform
+        ones -- the E = 0 row of compute_quant_error.py:24-27): per candidate a deep copy of the quantiser gets the range
+        (two launches of this library: range -> table, quantise) and the squared error is summed on the device; the
+        losses come back to the host in ONE copy at the end instead of one per candidate."""
+        import copy
+
+        import numpy as np
+
+        step = self.step_size
+        C = self.channel_groups
+        rows = data.reshape(len(data), -1) if self.per_channel else data.reshape(1, -1)
+        losses = torch.empty(self.num_candidates, C, dtype=torch.float64, device=data.device)
+        for i in range(1, self.num_candidates + 1):
+            temp_q = copy.deepcopy(self.quantizer)
+            temp_q.per_channel = False                      # :198-199
+            temp_q.set_quant_range(0.0 if self.one_sided_dist else -step * i, step * i)
+            y = temp_q(data)
+            losses[i - 1] = ((rows - y.reshape(rows.shape)) ** 2).sum(dim=1, dtype=torch.float64)
+        self.loss_array[:, 1:] += losses.t().cpu().numpy()
         min_cand = self.loss_array.argmin(axis=1)
         xmin = (np.zeros(C) if self.one_sided_dist else -step * min_cand).astype(np.single)
         xmax = (step * min_cand).astype(np.single)

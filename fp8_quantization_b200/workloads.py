@@ -390,6 +390,60 @@ def validate(model, batches, labels=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# empirical quantisation error (the data-parallel half of compute_quant_error.py)
+# ---------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def estimate_rounding_error_empirical(W, quantizer, range_min, range_max) -> float:
+    """quantization/quant_error_estimator.py:68-75: mean((Q(W) - W)^2) with the given range."""
+    quantizer.set_quant_range(range_min, range_max)
+    return torch.mean(((quantizer(W) - W) ** 2).flatten()).item()
+
+
+@torch.no_grad()
+def estimate_dot_prod_error_empirical(x, y, quantizer_x, quantizer_y, x_range_min, x_range_max, y_range_min,
+                                      y_range_max) -> float:
+    """quant_error_estimator.py:78-89: mean((x*y - Q(x)*Q(y))^2)."""
+    quantizer_x.set_quant_range(x_range_min, x_range_max)
+    quantizer_y.set_quant_range(y_range_min, y_range_max)
+    return torch.mean((torch.mul(x, y) - torch.mul(quantizer_x(x), quantizer_y(y))) ** 2).item()
+
+
+@torch.no_grad()
+def compute_quant_error_empirical(sample, sample_y=None, n_bits=8, num_candidates=1000, exp_bits_list=(5, 4, 3, 2, 0)):
+    """The empirical flow of compute_quant_error.py:18-57 on a device-resident sample: for every format of the script
+    (E5M2 .. E2M5 with FPQuantizer, E = 0 with SymmetricUniformQuantizer) the clipping range found by the line search
+    (all candidates in one launch of the MSE-grid kernel for the FP formats), the empirical rounding MSE / SQNR and the
+    empirical dot-product MSE / SQNR (``sample_y``: the second operand; default the sample itself, reversed).  The
+    analytic expectations the script prints next to them (scipy integrals over the format's grid,
+    quant_error_estimator.py:32-66, utils/distributions.py) are CPU-side analytics and out of scope."""
+    import math
+
+    from .quantizers import SymmetricUniformQuantizer
+    from .range_estimators import LineSearchEstimator
+
+    if sample_y is None:
+        sample_y = sample.flip(0).contiguous()
+    rows = []
+    for exp_bits in exp_bits_list:
+        mantissa_bits = n_bits - 1 - exp_bits
+
+        def make():
+            if exp_bits > 0:
+                return FPQuantizer(n_bits=n_bits, mantissa_bits=mantissa_bits, set_maxval=True)
+            return SymmetricUniformQuantizer(n_bits=n_bits)
+
+        quant = make()
+        rmin, rmax = LineSearchEstimator(quantizer=quant, num_candidates=num_candidates).forward(sample)
+        mse = estimate_rounding_error_empirical(sample, quant, rmin, rmax)
+        dot = estimate_dot_prod_error_empirical(sample, sample_y, make(), make(), rmin, rmax, rmin, rmax)
+        rows.append(dict(exp_bits=exp_bits, mantissa_bits=mantissa_bits, range_min=float(rmin.reshape(-1)[0]),
+                         range_max=float(rmax.reshape(-1)[0]), mse=mse,
+                         sqnr=-10.0 * math.log10(mse) if mse > 0 else float("inf"), dot_prod_mse=dot,
+                         dot_prod_sqnr=-10.0 * math.log10(dot) if dot > 0 else float("inf")))
+    return rows
+
+
+# ---------------------------------------------------------------------------------------------------
 # validate forward as one CUDA graph
 # ---------------------------------------------------------------------------------------------------
 class GraphedForward:
