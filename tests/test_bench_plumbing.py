@@ -1,0 +1,72 @@
+"""CPU: bench.py's record / replay machinery and workload accounting, driven on the host simulation of the kernels
+(fixture ``simdev``) -- the numbers the bench line is built from: launches per step, quantiser applications per image
+(3,237,864 activation elements + 11.7 M weight elements for ResNet-18), algorithmic bytes, and
+that replaying the recorded plan reproduces the recorded outputs.  The timing legs need a GPU and are not covered."""
+import importlib.util
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_record_replay_and_workload_accounting(simdev):
+    from fp8_quantization_b200 import ops, workloads
+
+    bench = _bench()
+    torch.manual_seed(10)
+    B = 1
+    for fmt in ("nchw", "channels_last"):
+        model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).eval()
+        if fmt == "channels_last":
+            model = model.to(memory_format=torch.channels_last)
+        x = torch.randn(B, 3, 224, 224)
+        workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+        model.fix_ranges()
+        with torch.no_grad():
+            model(x)
+            with bench.Recorder(ops) as rec:
+                model(x)
+        recorded = [(name, res) for name, _, _, res in rec.calls]
+        plan = bench.build_replay(rec.calls, ops)
+        st = bench.plan_stats(plan)
+        # 1 multi-tensor weight launch + 12 BN epilogues + 8 block tails + 2 plain quantisers (avgpool, fc output)
+        assert st["launches"] == 23 and st["weight_launches"] == 1 and st["stream_launches"] == 22, (fmt, st)
+        assert st["weight_elems"] == 11_678_912            # the 20 convolution weights + the fc weight
+        act_elems = st["elems"] - st["weight_elems"]
+        # the reference applies 30 activation quantisers per image = 3,237,864 elements; the fused block tail applies
+        # two of them per element it touches, and the count is per quantiser APPLICATION
+        assert act_elems == 3_237_864 * B, (fmt, act_elems)
+        # algorithmic bytes: 8 B per element of a BN+act+quant / plain site, 12 B per element of a residual tail
+        tails = sum(bench._numel(sh) for n_, a_, _ in plan if n_ == "bn_quant_add_act_quant"
+                    for sh in bench.data_shapes(n_, a_))
+        plain = sum(bench._numel(sh) for n_, a_, _ in plan if bench.is_stream_call(n_, a_) and n_ != "bn_quant_add_act_quant"
+                    for sh in bench.data_shapes(n_, a_))
+        assert st["stream_bytes"] == 12 * tails + 8 * plain
+        assert st["stream_elems"] == 2 * tails + plain == act_elems
+        # replaying the plan on the recorded inputs reproduces every recorded output, bit for bit
+        with torch.no_grad():
+            results = bench.run_plan(plan, ops)
+        for (name, res), out in zip(recorded, results):
+            a = res if isinstance(res, (list, tuple)) else [res]
+            b = out if isinstance(out, (list, tuple)) else [out]
+            for u, v in zip(a, b):
+                assert torch.equal(u.contiguous().view(torch.int32), v.contiguous().view(torch.int32)), (fmt, name)
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the oracle timed on the host cores) prints the same config keys as our arm."""
+    bench = _bench()
+    cfg = bench.base_config(5)
+    assert cfg["workload"] == bench.WORKLOAD and cfg["mantissa_bits"] == 5 and cfg["n_bits"] == 8
+    cb = bench.run_cpu_reference(1, 0, 2, 5)
+    for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "steps", "batch"):
+        assert k in cb
+    assert cb["kind"] == "port" and cb["unit"] == "Gelem/s" and cb["steps"] == 1 and cb["batch"] == 2 and cb["value"] > 0
