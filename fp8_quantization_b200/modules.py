@@ -411,9 +411,11 @@ class BNFusedHijacker(QuantizationHijacker):
             res = ops.dense(res)
             table, _ = q.table_for(res)
             scale, shift, mode = self.folded_bn()
-            return ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
-                                    q.n_bits, q.sign_bits, bn_mode=mode)
-        if self._fused_calibration_ok(res):
+            out = ops.bn_act_quant(res, scale, shift, _act_code(self.activation_function), table, q._mbits_host,
+                                   q.n_bits, q.sign_bits, bn_mode=mode)
+            if out is not None:     # None: beyond the fused kernels' 32-bit index range -> op-by-op composition below
+                return out
+        elif self._fused_calibration_ok(res):
             # calibration: statistics of act(bn(conv)) + range + table in one launch (4 B/element), then the fused
             # epilogue -- instead of F.batch_norm, the activation, the estimator and the quantiser as separate passes
             mgr = self.activation_quantizer
@@ -423,8 +425,10 @@ class BNFusedHijacker(QuantizationHijacker):
             code = _act_code(self.activation_function)
             if mgr.range_estimator.fused_bn_estimate_prepare(res, q, scale, shift, mode, code):
                 table, _ = q.table_for(res)
-                return ops.bn_act_quant(res, scale, shift, code, table, q._mbits_host, q.n_bits, q.sign_bits,
-                                        bn_mode=mode)
+                out = ops.bn_act_quant(res, scale, shift, code, table, q._mbits_host, q.n_bits, q.sign_bits,
+                                       bn_mode=mode)
+                if out is not None:
+                    return out
         if self.training and fq_dist.active():
             res = _sync_batch_norm_train(res, self.running_mean, self.running_var, self.gamma, self.beta,
                                          self.momentum, self.epsilon)

@@ -216,11 +216,20 @@ def bn_pack(mean, var, gamma, beta, eps: float):
     return packed
 
 
+# The fused batch-norm epilogues index with 32 bits (their row / channel arithmetic is built on 32-bit multiply-high
+# divisions); the C ABI answers FP8FQ_ERR_UNSUPPORTED from this size on and the callers compose the unfused steps
+# (F.batch_norm, activation, the 64-bit-indexed plain quantiser) instead.
+MAX_FUSED_ELEMS = 1 << 32
+
+
 def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int,
                  bn_mode: int = 0, out=None):
     """quantized_folded_bn.py:39-55 in one pass: Q(act(bn(x))), x is [N, C, *spatial] contiguous.
-    bn_mode 0: (bn_scale, bn_shift) from bn_fold; bn_mode 1: bn_scale = bn_pack(...) (bit-exact ATen arithmetic)."""
+    bn_mode 0: (bn_scale, bn_shift) from bn_fold; bn_mode 1: bn_scale = bn_pack(...) (bit-exact ATen arithmetic).
+    Returns None for tensors of MAX_FUSED_ELEMS elements or more (the caller composes the unfused ops)."""
     _require(x, "x")
+    if x.numel() >= MAX_FUSED_ELEMS:
+        return None
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
     _require_table(table, 1, mantissa_bits, n_bits, sign_bits, "table")
@@ -254,6 +263,8 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     _require(x, "x")
     _require(residual, "residual")
     _require_same_layout(x, residual, "bn_quant_add_act_quant")
+    if x.numel() >= MAX_FUSED_ELEMS:
+        return None
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
     _require_table(table_inner, 1, *fmt_inner, "table_inner")
@@ -425,6 +436,8 @@ def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_m
     ``table_out``: set_quant_range + table) -- fp8fq_bn_act_estimate_prepare_f32.  Returns False when the shape is
     not covered by the fused kernel (the caller then composes the unfused ops)."""
     _require(x, "x")
+    if x.numel() >= MAX_FUSED_ELEMS:
+        return False
     Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
     rows, hw = _rows_hw(x, Cbn)
     nhwc = hw == 1 or is_channels_last(x)

@@ -437,3 +437,40 @@ def test_empirical_quant_error_flow_vs_reference_golden(simdev):
     np.testing.assert_allclose(est.loss_array[:, 1:], g["gauss_e0_loss"][:, 1:], rtol=3e-4)
     with pytest.raises(NotImplementedError):     # 2-D search: referenced but not defined in the reference either
         fq.LineSearchEstimator(quantizer=fq.AsymmetricUniformQuantizer(n_bits=8), num_candidates=10)(x)
+
+
+def test_fused_epilogues_fall_back_beyond_their_index_range(simdev):
+    """Tensors of ops.MAX_FUSED_ELEMS (2^32) elements or more are outside the fused batch-norm kernels' 32-bit index
+    arithmetic: the module layer composes F.batch_norm -> activation -> the (64-bit-indexed) plain quantiser instead of
+    raising.  Exercised here by lowering the limit."""
+    from fp8_quantization_b200 import modules, ops
+
+    torch.manual_seed(4)
+    conv = modules.BNQConv(4, 8, 3, padding=1, activation=torch.nn.ReLU(), **_qparams(5)).eval()
+    conv.running_mean.normal_()
+    conv.running_var.uniform_(0.5, 1.5)
+    conv.quantized()
+    x = torch.randn(2, 4, 12, 12)
+    with torch.no_grad():
+        conv(x)
+        conv.fix_ranges()
+        conv(x)
+        n0 = ops.launch_count()
+        y_fused = conv(x)
+        assert ops.launch_count() - n0 == 2            # weight quantiser + one fused epilogue
+        saved = ops.MAX_FUSED_ELEMS
+        ops.MAX_FUSED_ELEMS = 100
+        try:
+            n0 = ops.launch_count()
+            y_fallback = conv(x)
+            assert ops.launch_count() - n0 == 2        # weight quantiser + plain quantiser (BN / ReLU by ATen)
+            assert ops.bn_act_quant(x, *ops.bn_fold(torch.zeros(4), torch.ones(4), None, None, 1e-5), 0,
+                                    ops.prepare(torch.tensor([3.0]), 5.0, 8, 1), 5.0, 8, 1) is None
+            # calibration falls back the same way (estimator + quantiser as separate steps)
+            conv.estimate_ranges()
+            y_cal = conv(x)
+            conv.fix_ranges()
+        finally:
+            ops.MAX_FUSED_ELEMS = saved
+    assert (bits(y_fused) != bits(y_fallback)).float().mean().item() < 5e-3     # ATen-CPU batch norm: ulps -> tie flips
+    assert torch.equal(y_cal, y_fallback)
