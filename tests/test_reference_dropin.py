@@ -1,6 +1,8 @@
 """CPU, build container only (skipped where /root/reference is absent): the two integration routes of
 INTEGRATION.md exercised against the REAL reference -- its model builders, QuantizationManager and QuantizedModel
-drive our classes.  Structure and state machine only; no kernel launches (there is no CPU compute path)."""
+drive our classes.  First the structure and the state machine (no kernel launches: the product has no CPU compute
+path); then both routes EXECUTED on the host simulation of the kernels (fixture ``simdev``): the reference's own model
+code with our plugin classes / fused modules against the pure reference on the same weights and input."""
 import pytest
 import torch
 from torch import nn
@@ -95,3 +97,82 @@ def test_route2_reference_builders_emit_our_fused_modules():
         h.restore()
     assert (dict(aq.bn_module_map), dict(aq.non_bn_module_map), aq.QuantizedModule) == before
     assert aq.bn_module_map[nn.Conv2d] is aq.BNQConv
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the same two routes EXECUTED: the reference's code driving our plugin on the host simulation of the kernels
+# (fixture simdev, tests/host_sim) vs the pure reference, same weights, same input
+# ---------------------------------------------------------------------------------------------------------------------
+def _calibrate_and_run(model, x):
+    """image_net.py:48-70 in miniature: quantised state, one calibration batch, fixed ranges, forward."""
+    model.eval()
+    model.set_quant_state(True, True)
+    with torch.no_grad():
+        model(x)                       # estimate_ranges is the initial state (quantization_manager.py:73)
+        model.fix_ranges()
+        return model(x)
+
+
+def _ranges(model, manager_types):
+    out = []
+    for name, m in model.named_modules():
+        if isinstance(m, manager_types):
+            out.append((name, m.quantizer.maxval.detach().reshape(-1).cpu().clone()))
+    return out
+
+
+def _compare(ref_logits, our_logits, ref_ranges, our_ranges):
+    assert [n for n, _ in ref_ranges] == [n for n, _ in our_ranges]          # same module tree
+    for (name, a), (_, b) in zip(ref_ranges, our_ranges):
+        if a.numel() > 1:
+            assert torch.equal(a, b), name                                       # per-channel weight ranges: exact
+        else:
+            assert torch.allclose(a, b, rtol=2e-2), (name, a, b)                 # a tie flipped upstream moves a range
+    cos = torch.nn.functional.cosine_similarity(ref_logits.flatten(), our_logits.flatten(), dim=0).item()
+    assert cos > 0.98, cos
+    assert (ref_logits - our_logits).abs().max().item() < 0.5 * ref_logits.std().item()
+
+
+def test_route1_executed_reference_model_with_our_quantizers_equals_pure_reference(simdev):
+    R = load_reference()
+    import models.resnet_quantized as rq
+    from torchvision.models import resnet18
+
+    torch.manual_seed(10)
+    net = resnet18()
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(10))
+    RefManager = R.quantization_manager.QuantizationManager
+    import copy
+    ref_model = rq.QuantizedResNet(copy.deepcopy(net), **_ref_params(R, 5))
+    ref_logits = _calibrate_and_run(ref_model, x)
+    our_model = rq.QuantizedResNet(copy.deepcopy(net), **integration.patch_quant_params(_ref_params(R, 5)))
+    from fp8_quantization_b200 import ops
+    n0 = ops.launch_count()
+    our_logits = _calibrate_and_run(our_model, x)
+    # the reference's module code issued every quantiser call into libfp8fq: 51 per forward, two launches per call while
+    # estimating (estimator, then set_quant_range + quantise are separate calls of the reference's manager)
+    assert ops.launch_count() - n0 >= 51 * 2
+    _compare(ref_logits, our_logits, _ranges(ref_model, RefManager), _ranges(our_model, RefManager))
+
+
+def test_route2_executed_reference_builders_with_our_fused_modules_equal_pure_reference(simdev):
+    R = load_reference()
+    import quantization
+    import models.mobilenet_v2_quantized as mq
+    from models.mobilenet_v2 import MobileNetV2
+    import copy
+
+    torch.manual_seed(10)
+    net = MobileNetV2()
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(10))   # its AvgPool2d(7) fixes the input size
+    RefManager = R.quantization_manager.QuantizationManager
+    ref_model = mq.QuantizedMobileNetV2(copy.deepcopy(net), **_ref_params(R, 4))
+    ref_logits = _calibrate_and_run(ref_model, x)
+    h = integration.install_fused_modules(quantization)
+    try:
+        our_model = mq.QuantizedMobileNetV2(copy.deepcopy(net), **integration.patch_quant_params(_ref_params(R, 4)))
+        assert sum(isinstance(m, fqm.BNQConv) for m in our_model.modules()) == 52
+        our_logits = _calibrate_and_run(our_model, x)
+        _compare(ref_logits, our_logits, _ranges(ref_model, RefManager), _ranges(our_model, (RefManager, OurManager)))
+    finally:
+        h.restore()
