@@ -474,3 +474,49 @@ def test_fused_epilogues_fall_back_beyond_their_index_range(simdev):
             ops.MAX_FUSED_ELEMS = saved
     assert (bits(y_fused) != bits(y_fallback)).float().mean().item() < 5e-3     # ATen-CPU batch norm: ulps -> tie flips
     assert torch.equal(y_cal, y_fallback)
+
+
+def test_ste_backward_and_learnable_ranges_vs_reference_golden(simdev):
+    """Row f4 through the autograd node on the simulation: gradients through FPQuantizer with learnable maxval /
+    mantissa_bits vs the real reference's autograd (tests/golden/backward.npz): same clamp mask, grad_x within 2 ulp
+    (the scale is a `pow` result that two libms round differently), grad_maxval / grad_mantissa_bits within fp32
+    summation noise; NaN poisoning; an optimiser step invalidates the table; fix_ranges un-registers the Parameters."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("backward.npz")
+    for i in range(int(g["num_cases"])):
+        n = f"b{i:02d}"
+        M, sb, pc = [int(v) for v in g[n + "_meta"]]
+        x = torch.from_numpy(g[n + "_x"]).requires_grad_(True)
+        w = torch.from_numpy(g[n + "_w"])
+        q = fq.FPQuantizer(8, per_channel=bool(pc), mantissa_bits=M, set_maxval=True)
+        q.sign_bits = sb
+        q.maxval = torch.from_numpy(g[n + "_maxval"])
+        q.learn_maxval()
+        q.learn_mantissa_bits()
+        assert isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 2
+        y = q(x)
+        (y * w).sum().backward()
+        gx_ref = torch.from_numpy(g[n + "_gx"])
+        assert torch.equal(x.grad == 0, gx_ref == 0), n
+        assert int(ulp_diff(x.grad, gx_ref)[gx_ref != 0].max()) <= 2, n
+        np.testing.assert_allclose(q.maxval.grad.numpy().reshape(-1), g[n + "_gmaxval"].reshape(-1), rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(q.mantissa_bits.grad.numpy().reshape(-1), g[n + "_gmbits"].reshape(-1), rtol=2e-3,
+                                   atol=5e-2)
+    q = fq.FPQuantizer(8, mantissa_bits=3, maxval=3.0)
+    q.learn_maxval()
+    xn = torch.tensor([float("nan"), 1.0, 5.0, -5.0, float("inf")], requires_grad=True)
+    (q(xn) * torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0])).sum().backward()
+    assert bool(torch.isnan(xn.grad[0])) and xn.grad[1].item() == 2.0 and xn.grad[2].item() == 0.0
+    assert bool(torch.isnan(q.maxval.grad).all())
+    q = fq.FPQuantizer(8, mantissa_bits=5, maxval=2.0, learn_maxval=True)
+    q.make_range_trainable()
+    x = torch.randn(4096, generator=torch.Generator().manual_seed(4)) * 3
+    y0 = q(x).detach().clone()
+    opt = torch.optim.SGD(q.parameters(), lr=1e-3)
+    q(x).sum().backward()
+    opt.step()
+    assert 0.5 < float(q.maxval.detach()) < 8.0 and float(q.maxval.detach()) != 2.0
+    assert not torch.equal(q(x).detach(), y0)
+    q.fix_ranges()
+    assert not isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 0
