@@ -5,7 +5,6 @@ C oracle.  The fixed shape lists of tests/test_host_sim.py cover the layout clas
 for the ones nobody thought of (exact unsigned divisions by run-time constants, multiply-high row look-ups, CTA sizes
 fitted to the channel count, ragged tails)."""
 import numpy as np
-import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
