@@ -176,3 +176,47 @@ def test_route2_executed_reference_builders_with_our_fused_modules_equal_pure_re
         _compare(ref_logits, our_logits, _ranges(ref_model, RefManager), _ranges(our_model, (RefManager, OurManager)))
     finally:
         h.restore()
+
+
+@pytest.mark.parametrize("include_mbits", [False, True])
+def test_config4_mse_estimator_on_resnet18_activations_vs_pure_reference(simdev, include_mbits):
+    """BASELINE config 4 at model level: activation ranges (and, with mse_include_mantissa_bits, the mantissa width) of
+    the quantised ResNet-18 chosen by FP_MSE_Estimator -- the reference's 111..666-iteration Python loop per
+    quantiser vs our one-sweep kernel -- through the reference's own model code.  A quantiser may land on a
+    neighbouring grid point / width only where the reference's own MSE table ties to fp32 noise; upstream of that the
+    choices are identical, so most sites must agree exactly."""
+    R = load_reference()
+    import models.resnet_quantized as rq
+    from torchvision.models import resnet18
+    import copy
+
+    torch.manual_seed(10)
+    net = resnet18()
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(10))
+    qp = _ref_params(R, 4)
+    qp["act_range_method"] = R.range_estimators.FP_MSE_Estimator
+    qp["fp8_kwargs"] = dict(qp["fp8_kwargs"], mse_include_mantissa_bits=include_mbits)
+    RefManager = R.quantization_manager.QuantizationManager
+    ref_model = rq.QuantizedResNet(copy.deepcopy(net), **qp)
+    ref_logits = _calibrate_and_run(ref_model, x)
+    our_model = rq.QuantizedResNet(copy.deepcopy(net), **integration.patch_quant_params(qp))
+    our_logits = _calibrate_and_run(our_model, x)
+    ref_q = [(n, m.quantizer) for n, m in ref_model.named_modules() if isinstance(m, RefManager) and not m.per_channel]
+    our_q = [(n, m.quantizer) for n, m in our_model.named_modules() if isinstance(m, RefManager) and not m.per_channel]
+    assert [n for n, _ in ref_q] == [n for n, _ in our_q] and len(ref_q) == 29
+    same_m = same_range = 0
+    for (name, a), (_, b) in zip(ref_q, our_q):
+        ma, mb = float(torch.as_tensor(a.mantissa_bits).reshape(-1)[0]), float(torch.as_tensor(b.mantissa_bits).reshape(-1)[0])
+        same_m += ma == mb
+        assert abs(ma - mb) <= 1, (name, ma, mb)
+        ra, rb = float(a.maxval.reshape(-1)[0]), float(b.maxval.reshape(-1)[0])
+        same_range += ra == rb
+        assert abs(ra - rb) <= 0.35 * abs(ra), (name, ra, rb)   # a flat MSE curve can tie between distant candidates
+    rel = [abs(float(a.maxval.reshape(-1)[0]) - float(b.maxval.reshape(-1)[0])) / abs(float(a.maxval.reshape(-1)[0]))
+           for (_, a), (_, b) in zip(ref_q, our_q)]
+    # once one site lands on the neighbouring grid point (1 % of the range apart) every downstream activation -- and with
+    # it every downstream grid -- shifts a little, so bit-equal ranges are expected only up to the first such site
+    # (measured here: 29 / 29 widths equal, 14-16 ranges bit-equal, median difference 0, one flat-curve site 21 % apart)
+    assert same_m >= 27 and same_range >= 8 and sorted(rel)[len(rel) // 2] < 0.02, (same_m, same_range, rel)
+    cos = torch.nn.functional.cosine_similarity(ref_logits.flatten(), our_logits.flatten(), dim=0).item()
+    assert cos > 0.97, cos
