@@ -8,7 +8,8 @@ arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in ``inclu
 from ._lib import Fp8fqError, LIB_PATH, lib  # noqa: F401
 from . import ops  # noqa: F401
 from .quantizers import (AsymmetricUniformQuantizer, FPQuantizer, QuantizerBase,  # noqa: F401
-                         QuantizerNotInitializedError, SymmetricUniformQuantizer)
+                         QuantizerNotInitializedError, SymmetricUniformQuantizer, get_max_value,
+                         quantize_to_fp8_ste_MM)
 from .range_estimators import (AllMinMaxEstimator, CurrentMinMaxEstimator, FP_MSE_Estimator,  # noqa: F401
                                LineSearchEstimator, RangeEstimatorBase, RangeEstimators, RunningMinMaxEstimator,
                                estimate_range_line_search)

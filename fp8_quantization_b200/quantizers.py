@@ -106,6 +106,44 @@ class _FakeQuantSTE(torch.autograd.Function):
         return (gx if ctx.needs_input_grad[0] else None), g_maxval, g_mbits, None, None, None, None, None
 
 
+def quantize_to_fp8_ste_MM(x_float, n_bits, maxval, num_mantissa_bits, sign_bits):
+    """The reference's functional entry point, fp8_quantizer.py:91-133, with its signature: ``maxval`` a ``[1]`` (per
+    tensor) or ``[C]`` / ``[C, 1, ...]`` (per channel, C = x.shape[0], :108-109) tensor, ``num_mantissa_bits`` a ``[1]``
+    tensor or a number.  Two launches -- the per-channel prologue (:105-110) and the streaming kernel (:112-132);
+    ``FPQuantizer`` caches the prologue's table, this function rebuilds it on every call.  The format split decides the
+    table layout on the host, so a device-resident ``num_mantissa_bits`` costs one ``.item()`` here (the module keeps
+    a host copy instead).  With grad mode on and a differentiable input it returns the STE graph node, like the
+    reference (round_ste_func, rounding_utils.py:12-19)."""
+    x = ops.dense(x_float)
+    if not isinstance(maxval, torch.Tensor):
+        maxval = torch.tensor([float(maxval)], dtype=torch.float32, device=x.device)
+    if isinstance(num_mantissa_bits, torch.Tensor):
+        mb = float(num_mantissa_bits.detach().reshape(-1)[0].item())
+        mbt = num_mantissa_bits
+    else:
+        mb = float(num_mantissa_bits)
+        mbt = torch.tensor([mb], dtype=torch.float32, device=x.device)
+    mv = maxval.reshape(-1)
+    if mv.device != x.device or mv.dtype != torch.float32:
+        mv = mv.to(device=x.device, dtype=torch.float32)
+    mv = mv.contiguous()
+    C = mv.numel()
+    if C != 1 and (x.dim() == 0 or x.shape[0] != C):
+        raise Fp8fqError(f"per-channel maxval has {C} entries but x has shape {tuple(x.shape)}")
+    table = ops.prepare(mv.detach(), mb, int(n_bits), int(sign_bits))
+    if torch.is_grad_enabled() and (x.requires_grad or mv.requires_grad or mbt.requires_grad):
+        if mbt.device != x.device:
+            mbt = mbt.to(x.device)
+        return _FakeQuantSTE.apply(x, mv, mbt, table, C, mb, int(n_bits), int(sign_bits))
+    return ops.fake_quant(x, table, C, mb, int(n_bits), int(sign_bits))
+
+
+def get_max_value(num_exponent_bits: int = 4, bias: int = 8):
+    """fp8_quantizer.py:82-88: largest value of an 8-bit format with integer bias (no inf / NaN codes reserved)."""
+    num_fraction_bits = 7 - num_exponent_bits
+    return 2 ** (2**num_exponent_bits - 1 - bias) * (2 - 2**-num_fraction_bits)
+
+
 class FPQuantizer(QuantizerBase):
     """8-bit (runtime bit-split) floating-point fake quantiser -- fp8_quantizer.py:151-272."""
 

@@ -1,0 +1,63 @@
+"""GPU: cases written after round 1's GPU budget was spent, so their first run on a device is the driver's round-end
+run.  Kept in their own module, collected after the other GPU modules (whose every test has run green on a B200).
+  * next row f5 -- the empirical flow of compute_quant_error.py (workloads.compute_quant_error_empirical) against the
+    real reference's golden vectors (tests/golden/quant_error.npz, made by tests/golden/make_golden_quant_error.py);
+  * row a1 by name -- quantize_to_fp8_ste_MM(x, n_bits, maxval, num_mantissa_bits, sign_bits), the functional form.
+Both also run on the host simulation in tests/test_host_sim_models.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, load_golden
+from oracle import fp8_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_next_row_f5_empirical_quant_error_flow_vs_reference_golden():
+    """compute_quant_error.py:18-57, empirical half (workloads.compute_quant_error_empirical), vs the real reference run
+    on the CPU (tests/golden/make_golden_quant_error.py): four sample distributions x the script's five formats.  The
+    loss curves are flat near their minimum, so the chosen threshold may be another point of the same plateau: it must
+    be optimal for the REFERENCE's loss; the empirical errors agree to the backends' ulp-level differences."""
+    from fp8_quantization_b200 import workloads
+
+    g = load_golden("quant_error.npz")
+    ncand = int(g["num_candidates"])
+    for name in g["names"]:
+        x, y = torch.from_numpy(g[f"{name}_x"]).to(DEV), torch.from_numpy(g[f"{name}_y"]).to(DEV)
+        rows = workloads.compute_quant_error_empirical(x, y, n_bits=8, num_candidates=ncand)
+        assert [r["exp_bits"] for r in rows] == list(g["exp_bits"])
+        for r in rows:
+            key = f"{name}_e{r['exp_bits']}"
+            ref_loss = g[key + "_loss"][0]
+            step = float(g[key + "_xmax"][0]) / max(int(np.argmin(ref_loss)), 1)
+            ours_i = int(round(r["range_max"] / step))
+            assert 1 <= ours_i <= ncand and ref_loss[ours_i] <= ref_loss.min() * (1 + 1e-3), (key, ours_i)
+            assert (r["range_min"] == 0.0) == (float(g[key + "_xmin"][0]) == 0.0), key
+            np.testing.assert_allclose(r["mse"], float(g[key + "_mse"]), rtol=5e-3, err_msg=key)
+            np.testing.assert_allclose(r["dot_prod_mse"], float(g[key + "_dot"]), rtol=5e-3, err_msg=key)
+
+
+@pytest.mark.parametrize("M,sb,pc", [(5, 1, False), (4, 1, True), (3, 0, False), (2, 1, True), (7, 1, False)])
+def test_functional_entry_point_quantize_to_fp8_ste_MM(M, sb, pc):
+    """fp8_quantizer.py:91-133 under its own name and signature: the bits of the module (same two launches), hence of
+    the reference's op sequence run by ATen on this GPU (the parity bar of tests/test_gpu_parity.py)."""
+    import fp8_quantization_b200 as fq
+
+    gen = torch.Generator().manual_seed(10 + M)
+    x = (torch.randn(64, 3, 37, generator=gen) * 1.5).to(DEV)
+    if sb == 0:
+        x = x.abs()
+    mv = x.reshape(64, -1).abs().max(1)[0] if pc else x.abs().max().reshape(1)
+    mb = torch.tensor([float(M)], device=DEV)
+    y = fq.quantize_to_fp8_ste_MM(x, 8, mv, mb, sb)
+    assert y.shape == x.shape and y.dtype == torch.float32 and y.device == x.device
+    y_view = fq.quantize_to_fp8_ste_MM(x, 8, mv.reshape(-1, 1, 1) if pc else mv, float(M), sb)   # :108-109
+    assert torch.equal(bits(y), bits(y_view))
+    qz = fq.FPQuantizer(8, per_channel=pc, mantissa_bits=M, maxval=1.0)
+    qz.sign_bits = sb
+    qz.maxval = mv.clone()
+    assert torch.equal(bits(y), bits(qz(x)))
+    y_ref = O.fake_quant(x, 8, mv, mb, sb)
+    assert bool(((bits(y) == bits(y_ref)) | (torch.isnan(y) & torch.isnan(y_ref))).all())

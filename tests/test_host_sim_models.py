@@ -520,3 +520,50 @@ def test_ste_backward_and_learnable_ranges_vs_reference_golden(simdev):
     assert not torch.equal(q(x).detach(), y0)
     q.fix_ranges()
     assert not isinstance(q.maxval, torch.nn.Parameter) and len(list(q.parameters())) == 0
+
+
+def test_functional_entry_point_quantize_to_fp8_ste_MM(simdev):
+    """fp8_quantizer.py:91-133 by its own name and signature: the same launches as the
+    module, so the same bits; against the real reference's golden cases within the simulation's libm tolerance
+    (cf. tests/test_host_sim.py); maxval given as [C] or [C, 1, ...] (:108-109), mantissa width as a tensor or a number;
+    gradients through the STE node like the module's."""
+    import fp8_quantization_b200 as fq
+
+    g = load_golden("fp8_quantizer.npz")
+    checked = 0
+    for i in range(0, int(g["num_cases"]), 3):
+        name = f"c{i:03d}"
+        M, sb, pc = [int(v) for v in g[name + "_meta"]]
+        x = torch.from_numpy(np.ascontiguousarray(g[name + "_x"]))
+        if x.dim() == 0 or x.numel() == 0:
+            continue
+        mv = torch.from_numpy(np.ascontiguousarray(g[name + "_maxval"], np.float32))
+        y = fq.quantize_to_fp8_ste_MM(x, 8, mv, torch.Tensor([float(M)]), sb)
+        qz = fq.FPQuantizer(n_bits=8, per_channel=bool(pc), mantissa_bits=M)
+        qz.sign_bits = sb
+        qz.maxval = mv.reshape(-1)
+        assert torch.equal(bits(y), bits(qz(x))), name                       # the module's bits
+        if pc and x.dim() > 1:                                                   # the broadcast form of :108-109
+            y2 = fq.quantize_to_fp8_ste_MM(x, 8, mv.reshape([-1] + [1] * (x.dim() - 1)), float(M), sb)
+            assert torch.equal(bits(y), bits(y2)), name
+        y_ref = torch.from_numpy(g[name + "_y"]).reshape(y.shape)
+        assert torch.equal(torch.isnan(y), torch.isnan(y_ref)), name
+        ok = ~torch.isnan(y_ref)
+        rel = (y[ok].double() - y_ref[ok].double()).abs() / y_ref[ok].double().abs().clamp_min(1e-30)
+        far = int((rel > 1e-5).sum())                      # a tie resolved the other way after an ulp in a scale
+        assert far <= max(2, 2e-3 * x.numel()), (name, far)
+        checked += 1
+    assert checked >= 25
+    assert fq.get_max_value(4, 8) == 240.0 and fq.get_max_value(5, 16) == 57344.0 and fq.get_max_value(2, 2) == 3.9375
+    with pytest.raises(fq.Fp8fqError):
+        fq.quantize_to_fp8_ste_MM(torch.randn(3, 5), 8, torch.ones(4), 5.0, 1)
+    # STE node: same gradients as the module
+    torch.manual_seed(2)
+    x = (torch.randn(6, 40) * 2).requires_grad_(True)
+    mv = torch.full((1,), 2.5, requires_grad=True)
+    fq.quantize_to_fp8_ste_MM(x, 8, mv, torch.Tensor([4.0]), 1).sum().backward()
+    qz = fq.FPQuantizer(n_bits=8, mantissa_bits=4, maxval=2.5, learn_maxval=True)
+    qz.make_range_trainable()
+    x2 = x.detach().clone().requires_grad_(True)
+    qz(x2).sum().backward()
+    assert torch.equal(x.grad, x2.grad) and torch.equal(mv.grad, qz.maxval.grad)
