@@ -489,3 +489,7 @@ class SymmetricUniformQuantizer(AsymmetricUniformQuantizer):
     @property
     def zero_point(self):
         return 0.0
+
+    def generate_grid(self):  # uniform_quantizers.py:328-331
+        x_int_rng = torch.arange(self.int_min, self.int_max + 1, device=self.delta.device)
+        return self.scale * (x_int_rng - self.zero_point)

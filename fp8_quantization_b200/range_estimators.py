@@ -296,6 +296,31 @@ class LineSearchEstimator(RangeEstimatorBase):
             raise NoDataPassedError()
         return self.max_search_range / self.num_candidates
 
+    @property
+    def optimization_method(self):  # :180-197 -- only the 1-D grid search is defined in the reference
+        if self.one_sided_dist is None:
+            raise NoDataPassedError()
+        if not (self.one_sided_dist or self.quantizer.symmetric):
+            raise NotImplementedError("2-D grid search (asymmetric quantiser, two-sided data) does not exist in the "
+                                      "reference either")
+        return self.forward
+
+    def quantize(self, x_float, x_min=None, x_max=None):  # :199-206
+        import copy
+
+        temp_q = copy.deepcopy(self.quantizer)
+        temp_q.per_channel = False
+        if x_min or x_max:
+            temp_q.set_quant_range(x_min, x_max)
+        return temp_q(x_float)
+
+    def loss_fx(self, data, neg_thr, pos_thr, per_channel_loss=False):
+        """:161-169 -- the loss of ONE candidate (sum of squared error, per row or in total), as a numpy value; the
+        search itself evaluates all candidates in one launch (``forward``)."""
+        y = self.quantize(data, x_min=neg_thr, x_max=pos_thr)
+        temp_sum = torch.sum(((data - y) ** 2).reshape(len(data), -1), dim=1)
+        return (temp_sum if per_channel_loss else torch.sum(temp_sum)).cpu().numpy()
+
     def _define_search_range(self, data, dmin, dmax):  # :203-234, 1-D branch
         import numpy as np
 

@@ -437,6 +437,21 @@ def test_empirical_quant_error_flow_vs_reference_golden(simdev):
     np.testing.assert_allclose(est.loss_array[:, 1:], g["gauss_e0_loss"][:, 1:], rtol=3e-4)
     with pytest.raises(NotImplementedError):     # 2-D search: referenced but not defined in the reference either
         fq.LineSearchEstimator(quantizer=fq.AsymmetricUniformQuantizer(n_bits=8), num_candidates=10)(x)
+    sq = est.quantizer
+    sq.set_quant_range(-1.0, 1.0)
+    grid = sq.generate_grid()                      # uniform_quantizers.py:328-331
+    assert grid.numel() == 256 and torch.equal(sq(grid.clone()), grid)
+    # loss_fx / quantize (range_estimators.py:161-169, 199-206): one candidate's loss == that column of the sweep
+    est = fq.LineSearchEstimator(quantizer=fq.FPQuantizer(n_bits=8, mantissa_bits=3, set_maxval=True), num_candidates=ncand)
+    with pytest.raises(fq.range_estimators.NoDataPassedError):
+        est.optimization_method
+    est(x)
+    assert est.optimization_method == est.forward
+    for i in (7, 60, ncand):
+        thr = est.step_size * i
+        one = float(est.loss_fx(x.reshape(1, -1), -thr, thr))
+        np.testing.assert_allclose(one, est.loss_array[0, i], rtol=1e-5)
+        assert est.loss_fx(x.reshape(4, -1), -thr, thr, per_channel_loss=True).shape == (4,)
 
 
 def test_fused_epilogues_fall_back_beyond_their_index_range(simdev):
