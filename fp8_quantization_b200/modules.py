@@ -29,7 +29,7 @@ from torch.nn.modules.pooling import _AdaptiveAvgPoolNd, _AvgPoolNd
 from . import dist as fq_dist
 from . import ops
 from .quantization_manager import QuantizationManager
-from .quantizers import FPQuantizer, QuantizerBase
+from .quantizers import AsymmetricUniformQuantizer, FPQuantizer, QuantizerBase
 from .range_estimators import CurrentMinMaxEstimator, RangeEstimatorBase, RunningMinMaxEstimator
 
 # hijacker.py:15-29 minus the timm classes (timm is not a dependency of this package)
@@ -133,7 +133,7 @@ class QuantizedModule(nn.Module):
     (utils/click_options.py:490-508); classes are selected by passing them as ``method`` /
     ``act_method`` / ``weight_range_method`` / ``act_range_method``."""
 
-    def __init__(self, *args, method: QuantizerBase = FPQuantizer, act_method=None,
+    def __init__(self, *args, method: QuantizerBase = AsymmetricUniformQuantizer, act_method=None,
                  weight_range_method: RangeEstimatorBase = CurrentMinMaxEstimator,
                  act_range_method: RangeEstimatorBase = RunningMinMaxEstimator, n_bits=8, n_bits_act=None,
                  per_channel_weights=False, percentile=None, weight_range_options=None, act_range_options=None,

@@ -32,7 +32,7 @@ class Qstates(BaseEnumOptions):  # quantization_manager.py:131-136
 class QuantizationManager(nn.Module):
     """quantization_manager.py:28-128."""
 
-    def __init__(self, qmethod: QuantizerBase = QMethods.fp_quantizer.cls,
+    def __init__(self, qmethod: QuantizerBase = QMethods.symmetric_uniform.cls,  # the reference's defaults (:52-61)
                  init: RangeEstimatorBase = RangeEstimators.current_minmax.cls, per_channel=False, x_min=None,
                  x_max=None, qparams=None, range_estim_params=None):
         super().__init__()

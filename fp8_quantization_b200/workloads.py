@@ -299,19 +299,35 @@ def readme_quant_params(mantissa_bits: int, *, method=FPQuantizer, weight_range_
                         allow_unsigned=allow_unsigned))
 
 
-def pass_data_for_range_estimation(batches, model, act_quant=True, weight_quant=True, max_num_batches=1):
-    """quantization/utils.py:74-115: calibration forward passes in eval mode under no_grad."""
+def pass_data_for_range_estimation(loader, model, act_quant, weight_quant, max_num_batches=20, cross_entropy_layer=None,
+                                   inp_idx=0):
+    """quantization/utils.py:74-115: calibration forward passes in eval mode under no_grad.  ``loader`` yields what the
+    reference's loaders yield -- ``(x, y)`` tuples / lists (``inp_idx`` selects the input), dicts of keyword tensors --
+    or bare input tensors; inputs are moved to the model's device.  Returns the inputs that were passed (the reference
+    returns host numpy copies of them, :103; that device-to-host copy per batch is not made here).  The cross-entropy
+    range estimator the reference can install here (:82-94) is not part of the FP8 path."""
+    if cross_entropy_layer is not None:
+        raise NotImplementedError("the cross-entropy range estimator is outside the FP8 fake-quantisation path")
     model.set_quant_state(weight_quant, act_quant)
-    model.eval()
+    model.eval()  # BN EMA must not be updated
+    device = next(model.parameters()).device
+    passed = []
     with torch.no_grad():
-        for i, x in enumerate(batches):
-            model(x)
+        for i, data in enumerate(loader):
+            if isinstance(data, dict):
+                model(**{k: v.to(device=device) for k, v in data.items()})
+            else:
+                x = data[inp_idx] if isinstance(data, (tuple, list)) else data
+                x = x.to(device=device)
+                passed.append(x)
+                model(x)
             if i >= max_num_batches - 1 or not act_quant:
                 break
+    return passed
 
 
 @torch.no_grad()
-def reestimate_BN_stats(model, batches, num_batches=50, store_ema_stats=False):
+def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=False):
     """utils/qat_utils.py:45-90: re-estimate the batch-norm statistics of the QUANTISED network.  Every
     BNFusedHijacker runs with momentum 1 in training mode (its children do not), so after each forward its running
     statistics are the current batch statistics; these are averaged over ``num_batches`` batches and written back.
@@ -338,9 +354,11 @@ def reestimate_BN_stats(model, batches, num_batches=50, store_ema_stats=False):
             else:
                 module.running_mean_ema = copy.deepcopy(module.running_mean)
                 module.running_var_ema = copy.deepcopy(module.running_var)
+    device = next(model.parameters()).device
     batch_count = 0
-    for x in batches:
-        model(x)
+    for data in data_loader:  # the reference's loaders yield (x, y) (:72); bare input tensors are accepted too
+        x = data[0] if isinstance(data, (tuple, list)) else data
+        model(x.to(device))
         for _, module in layers:
             module.running_mean_sum += module.running_mean
             module.running_var_sum += module.running_var

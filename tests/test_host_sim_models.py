@@ -336,9 +336,10 @@ def test_bn_reestimation_vs_reference_golden(simdev):
 
     model = Wrap(modules.quantize_model(seq, **_qparams(5))).eval()
     xs = [torch.from_numpy(x) for x in g["x"]]
-    workloads.pass_data_for_range_estimation([xs[0]], model, True, True, 1)
+    passed = workloads.pass_data_for_range_estimation([(xs[0], None)], model, True, True)   # (x, y) items, :100-102
+    assert len(passed) == 1 and passed[0] is xs[0]
     model.fix_ranges()
-    n = workloads.reestimate_BN_stats(model, xs, num_batches=3)
+    n = workloads.reestimate_BN_stats(model, [(x, None) for x in xs], num_batches=3)        # qat_utils.py:72
     assert n == 3 and not model.f[0].training and model.f[0].momentum == 0.1
     for i in (0, 1):
         np.testing.assert_allclose(model.f[i].running_mean.numpy(), g[f"mean_{i}"], rtol=2e-3, atol=2e-4)
