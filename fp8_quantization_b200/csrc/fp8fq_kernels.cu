@@ -31,24 +31,18 @@ namespace {
 
 std::atomic<int64_t> g_launches{0};
 
-struct DevInfo {
-  int sms = 0;
-  bool ok = false;
-};
-DevInfo g_dev[64];
-std::mutex g_dev_mu;
+// SM count per device, read once (0 = not read yet; concurrent first callers read the same attribute value).
+std::atomic<int> g_sms[64];
 
 int sm_count() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (!g_dev[dev].ok) {
-    std::lock_guard<std::mutex> lk(g_dev_mu);
-    int n = 0;
+  int n = g_sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    g_dev[dev].sms = n;
-    g_dev[dev].ok = true;
+    g_sms[dev].store(n, std::memory_order_relaxed);
   }
-  return g_dev[dev].sms;
+  return n;
 }
 
 // Programmatic dependent launch (PDL): kernels of this library that follow each other on a stream (23 per ResNet-18
@@ -2005,6 +1999,12 @@ struct HostPipe {
 };
 HostPipe g_pipe;
 std::mutex g_pipe_mu;
+
+struct DeviceGuard {  // the entry point selects `device`; the caller's current device is restored on every exit
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 }  // namespace
 
 int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* maxval_host, int64_t n, int64_t C,
@@ -2018,6 +2018,7 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
   std::lock_guard<std::mutex> lk(g_pipe_mu);
   cudaError_t ce;
 #define FQ_CK(call) do { ce = (call); if (ce != cudaSuccess) return (int)ce; } while (0)
+  DeviceGuard restore_device;
   FQ_CK(cudaSetDevice(device));
   HostPipe& p = g_pipe;
   if (p.ready && p.device != device) return FP8FQ_ERR_UNSUPPORTED;
