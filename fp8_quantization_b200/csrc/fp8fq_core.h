@@ -103,14 +103,19 @@ FQ_HD float max_nan(float a, float b) {
 #if defined(__CUDA_ARCH__)
   float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
 #else
-  if (a != a) return a; if (b != b) return b; return a > b ? a : b;
+  // host builds (tests): PTX max.NaN semantics incl. the signed-zero order -0.0 < +0.0
+  if (a != a) return a; if (b != b) return b;
+  if (a == b) return u2f(f2u(a) & f2u(b));   // equal values: +0.0 unless both are -0.0
+  return a > b ? a : b;
 #endif
 }
 FQ_HD float min_nan(float a, float b) {
 #if defined(__CUDA_ARCH__)
   float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
 #else
-  if (a != a) return a; if (b != b) return b; return a < b ? a : b;
+  if (a != a) return a; if (b != b) return b;
+  if (a == b) return u2f(f2u(a) | f2u(b));   // equal values: -0.0 if either is -0.0 (PTX min.NaN)
+  return a < b ? a : b;
 #endif
 }
 FQ_HD bool is_normal_pos(float f) {

@@ -276,6 +276,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// FP8FQ_FOLD_ACT (build option, default off; candidate for round 2 -- bits proven on the host simulation, not yet run
+// on a device): ReLU / ReLU6 in front of an FP quantiser are folded into the quantiser's clamp,
+//   min(max(act(v), lo), hi) == min(max(v, max(lo, 0)), min(hi, 6 for ReLU6)),
+// which holds for every input including NaN (max.NaN / min.NaN propagate), +-inf and signed zeros (PTX orders
+// -0.0 < +0.0, and lo <= 0 <= hi or NaN): the two bounds are adjusted once per thread and the 1-2 min/max per element
+// of the activation disappear from the issue-bound BN variants.  Not applied to the INT quantisers (KMODE 2), whose
+// clamp comes after the rounding.
+#ifndef FP8FQ_FOLD_ACT
+#define FP8FQ_FOLD_ACT 0
+#endif
+template <int KMODE>
+__device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
+  if (act == FP8FQ_ACT_RELU || act == FP8FQ_ACT_RELU6) c.lo = max_nan(c.lo, 0.0f);
+  if (act == FP8FQ_ACT_RELU6) c.hi = min_nan(c.hi, 6.0f);
+}
+
 // Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
 // vector when any lane is within the guard band of a rounding tie (probability ~ N * 2^(M-19)).
 // GUARD = false drops the exactness check of the reciprocal multiply (only for consumers that tolerate q off by one
@@ -517,6 +533,15 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   ElemCtx<KMODE> ctx, ctx2;
   load_ctx_direct<KMODE>(ctx, a.table, a.K);
   if (kTail) load_ctx_direct<KMODE>(ctx2, a.table2, a.K2);
+#if FP8FQ_FOLD_ACT
+  // the activation (if any) feeds the LAST quantiser of the launch: ctx2 in the block tail, ctx otherwise
+  constexpr bool kFoldAct = KMODE != 2 && (kBnAct || PRE == PRE_ADD || kTail);
+  if (kFoldAct) fold_act(kTail ? ctx2 : ctx, a.act);
+  const int act_left = kFoldAct ? FP8FQ_ACT_NONE : a.act;
+#define FQ_ACT act_left
+#else
+#define FQ_ACT a.act   // (the default build is token for token the code the round-1 profiles were taken from)
+#endif
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTile;
@@ -605,15 +630,15 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
       }
       if (kBnAct) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = apply_act(v[k], a.act);
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(v[k], FQ_ACT);
       } else if (PRE == PRE_ADD) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(v[k], in2[u].v[k]), a.act);
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(v[k], in2[u].v[k]), FQ_ACT);
       } else if (kTail) {
         float t[VEC];
         quant_vec<KMODE, false, VEC>(v, ctx, t, cd);  // inner quantiser (output of the block's last BN)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(t[k], in2[u].v[k]), a.act);
+        for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(t[k], in2[u].v[k]), FQ_ACT);
       }
       if (kTail) quant_vec<KMODE, CODES, VEC>(v, ctx2, yv, cd);
       else quant_vec<KMODE, CODES, VEC>(v, ctx, yv, cd);
@@ -638,13 +663,15 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
       v = bn_apply<BNM>(v, bn_load<BNM>(a, ch));
     }
     int32_t cd;
-    if (kBnAct) v = apply_act(v, a.act);
-    else if (PRE == PRE_ADD) v = apply_act(add_rn(v, a.x2[i]), a.act);
-    else if (kTail) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), a.act);
+    if (kBnAct) v = apply_act(v, FQ_ACT);
+    else if (PRE == PRE_ADD) v = apply_act(add_rn(v, a.x2[i]), FQ_ACT);
+    else if (kTail) v = apply_act(add_rn(quant_elem<KMODE, false>(v, ctx, &cd), a.x2[i]), FQ_ACT);
     a.y[i] = kTail ? quant_elem<KMODE, CODES>(v, ctx2, &cd) : quant_elem<KMODE, CODES>(v, ctx, &cd);
     if (CODES) a.codes[i] = cd;
   }
 }
+
+#undef FQ_ACT
 
 // ------------------------------------------------------------------------------------------------
 // K1 per-channel: x is [C, inner]; one CTA per (row, chunk) work item, row table staged in smem

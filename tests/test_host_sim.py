@@ -395,6 +395,57 @@ def test_add_act_quant_equals_composition(sim, ref):
                     assert same_bits(y, ref_quant(ref, v.astype(np.float32), mv, M)[0]), (M, n, off, act)
 
 
+def test_fold_act_build_option_is_bit_identical_to_the_default_build(sim):
+    """-DFP8FQ_FOLD_ACT=1 (csrc/fp8fq_kernels.cu: ReLU / ReLU6 folded into the quantiser's clamp bounds; off by default)
+    against the default build, bit for bit, on inputs made of the cases the equivalence has to survive: +-0 (identity
+    batch norm: scale 1, shift -0.0, so that -0.0 reaches the activation), +-inf, NaN, values around 0 / 6 / maxval,
+    ranges below and above 6, zero / inf / NaN ranges, signed and unsigned formats, K <= 3 and K > 3, all three fused
+    entry points in both layouts.  (The whole of this module also passes with FP8FQ_SIM_LIB pointing at that build.)"""
+    from fp8_quantization_b200._lib import SIGNATURES
+
+    fold = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim_foldact.so"))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(fold, name)
+        fn.restype, fn.argtypes = res, args
+    rng = np.random.default_rng(5)
+    C, hw, N = 8, 1024, 2     # (the NCHW block tail needs 2 + 4095 // hw <= C)
+    n = N * C * hw
+    one, negzero = aligned(C), aligned(C)
+    one[:], negzero[:] = 1.0, -0.0
+    compared = 0
+    for mvv in (3.0, 7.5, 6.0, 0.4, 0.0, np.inf, np.nan, 1e-38):
+        mv = np.array([mvv], np.float32)
+        sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, -1e-30, 6.0, np.nextafter(np.float32(6), np.float32(7)),
+                       np.nextafter(np.float32(6), np.float32(0)), -6.0, mvv, -mvv, 1e30, -1e30, 5.9999, 1e-45, -1e-45],
+                      np.float32)
+        for M, sb in ((5, 1), (3, 1), (4, 0), (2, 0), (7, 1)):
+            for act in (ACT_NONE, ACT_RELU, ACT_RELU6):
+                x, r = aligned(n), aligned(n)
+                x[:] = rng.standard_normal(n).astype(np.float32) * 3
+                x[:: 7][:sp.size] = sp
+                x[1::11][:sp.size] = sp[::-1]
+                r[:] = np.where(rng.random(n) < 0.5, np.float32(-0.0), rng.standard_normal(n).astype(np.float32))
+                outs = []
+                for lib in (sim, fold):
+                    tab, tab2 = table_for(lib, mv, M, 8, sb), table_for(lib, np.array([2.5], np.float32), 4, 8, 1)
+                    ys = [aligned(n) for _ in range(5)]
+                    assert lib.fp8fq_bn_act_quant_f32(P(x), P(ys[0]), P(one), P(negzero), N * C, hw, C, act, 0, P(tab), M, 8,
+                                                      sb, None) == 0
+                    assert lib.fp8fq_bn_act_quant_nhwc_f32(P(x), P(ys[1]), P(one), P(negzero), N * hw, C, act, 0, P(tab), M,
+                                                           8, sb, None) == 0
+                    assert lib.fp8fq_add_act_quant_f32(P(x), P(r), P(ys[2]), n, act, P(tab), M, 8, sb, None) == 0
+                    assert lib.fp8fq_bn_quant_add_act_quant_f32(P(x), P(r), P(ys[3]), P(one), P(negzero), N * C, hw, C, act,
+                                                                0, P(tab2), 4, 8, 1, P(tab), M, 8, sb, None) == 0
+                    assert lib.fp8fq_bn_quant_add_act_quant_nhwc_f32(P(x), P(r), P(ys[4]), P(one), P(negzero), N * hw, C,
+                                                                     act, 0, P(tab2), 4, 8, 1, P(tab), M, 8, sb, None) == 0
+                    outs.append(ys)
+                for k, (ya, yb) in enumerate(zip(*outs)):
+                    assert np.array_equal(bits(ya), bits(yb)) or same_bits(ya, yb), (mvv, M, sb, act, k)
+                    assert np.array_equal(np.signbit(ya), np.signbit(yb)) or np.isnan(ya).any(), (mvv, M, sb, act, k)
+                    compared += 1
+    assert compared == 8 * 5 * 3 * 5
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # K2a: min/max + estimator update rules (+ fused set_quant_range / prologue)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -56,7 +56,7 @@ for blk in re.split(r"\n\s*Function : ", sass)[1:]:
     name = blk.split("\n", 1)[0].strip()
     ops = collections.Counter()
     for line in blk.split("\n"):
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m:
             ops[m.group(1)] += 1
     tot = sum(ops.values())
