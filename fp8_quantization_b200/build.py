@@ -35,10 +35,14 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """``defines`` / ``out``: an alternative build of the same library (e.g. ``-DFP8FQ_FOLD_ACT=1``) next to the default
+    one; ``FP8FQ_LIB=<out>`` makes the package load it."""
+    target = out or OUT
+    if not force and not defines and out is None and not needs_build():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = ([find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", target, SRC])
     env = dict(os.environ)
     env.pop("CC", None)  # the image's CC points at a gcc nvcc does not need
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -47,8 +51,11 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libfp8fq.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m fp8_quantization_b200.build [--force] [-v] [-DNAME=VALUE ...] [--out PATH]
+    argv = sys.argv[1:]
+    print(build(force="--force" in argv, verbose="-v" in argv, defines=[a[2:] for a in argv if a.startswith("-D")],
+                out=argv[argv.index("--out") + 1] if "--out" in argv else None))
