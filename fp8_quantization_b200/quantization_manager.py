@@ -30,59 +30,61 @@ class Qstates(BaseEnumOptions):  # quantization_manager.py:131-136
 
 
 class QuantizationManager(nn.Module):
-    """quantization_manager.py:28-128."""
+    """One quantiser + its range estimator + the calibration state machine: the contract of the reference's
+    quantization_manager.py:28-128 (constructor arguments :52-61, states :131-136, forward :114-122).  While the state
+    is an estimating one, ``forward`` updates the range from the data before quantising; with this package's
+    device-resident estimator / quantiser pair that update and the quantiser's prologue are one launch."""
 
-    def __init__(self, qmethod: QuantizerBase = QMethods.symmetric_uniform.cls,  # the reference's defaults (:52-61)
+    def __init__(self, qmethod: QuantizerBase = QMethods.symmetric_uniform.cls,
                  init: RangeEstimatorBase = RangeEstimators.current_minmax.cls, per_channel=False, x_min=None,
                  x_max=None, qparams=None, range_estim_params=None):
         super().__init__()
-        self.state = Qstates.estimate_ranges
-        self.qmethod = qmethod
-        self.init = init
-        self.per_channel = per_channel
-        self.qparams = qparams if qparams else {}
-        self.range_estim_params = range_estim_params if range_estim_params else {}
+        self.qmethod, self.init, self.per_channel = qmethod, init, per_channel
+        self.qparams = dict(qparams or {})
+        self.range_estim_params = dict(range_estim_params or {})
+        self.quantizer = qmethod(per_channel=per_channel, **self.qparams)
         self.range_estimator = None
-
-        self.quantizer = self.qmethod(per_channel=self.per_channel, **self.qparams)
-        self.quantizer.state = self.state
-
-        if x_min is not None and x_max is not None:
+        self._enter(Qstates.estimate_ranges)
+        if x_min is None or x_max is None:      # ranges come from data: build the estimator (:81-83)
+            self.range_estimator = init(per_channel=per_channel, quantizer=self.quantizer, **self.range_estim_params)
+        else:                                   # ranges given: install and freeze them (:76-78)
             self.set_quant_range(x_min, x_max)
             self.fix_ranges()
-        else:
-            self.range_estimator = self.init(per_channel=self.per_channel, quantizer=self.quantizer,
-                                             **self.range_estim_params)
+
+    def _enter(self, state):
+        """The manager and its quantiser always carry the same state (:73, 91, 96, 103, 107)."""
+        self.state = state
+        self.quantizer.state = state
 
     @property
     def n_bits(self):
         return self.quantizer.n_bits
 
+    # -- state transitions (:89-111) ----------------------------------------------------------------------------------
     def estimate_ranges(self):
-        self.state = Qstates.estimate_ranges
-        self.quantizer.state = self.state
+        self._enter(Qstates.estimate_ranges)
+
+    def estimate_ranges_train(self):
+        self._enter(Qstates.estimate_ranges_train)
 
     def fix_ranges(self):
-        if self.quantizer.is_initialized:
-            self.state = Qstates.fix_ranges
-            self.quantizer.state = self.state
-        else:
+        if not self.quantizer.is_initialized:   # a bound method for FPQuantizer, hence always truthy there (:94)
             raise QuantizerNotInitializedError()
+        self._enter(Qstates.fix_ranges)
 
     def learn_ranges(self):
         self.quantizer.make_range_trainable()
-        self.state = Qstates.learn_ranges
-        self.quantizer.state = self.state
-
-    def estimate_ranges_train(self):
-        self.state = Qstates.estimate_ranges_train
-        self.quantizer.state = self.state
+        self._enter(Qstates.learn_ranges)
 
     def reset_ranges(self):
         self.range_estimator.reset()
         self.quantizer.reset()
-        self.estimate_ranges()
+        self._enter(Qstates.estimate_ranges)
 
+    def set_quant_range(self, x_min, x_max):
+        self.quantizer.set_quant_range(x_min, x_max)
+
+    # -- the hot path ---------------------------------------------------------------------------------------------------
     def estimating(self) -> bool:
         return self.state == Qstates.estimate_ranges or (self.state == Qstates.estimate_ranges_train and self.training)
 
@@ -95,17 +97,13 @@ class QuantizationManager(nn.Module):
     def _fusable(self) -> bool:
         return self.device_resident_calibration() and self.range_estimator.fused_supported()
 
-    def forward(self, x):  # quantization_manager.py:114-122
+    def forward(self, x):
         if self.estimating():
-            if self._fusable():
+            if self._fusable():     # statistics + estimator update + set_quant_range + prologue: one launch
                 x = self.range_estimator.fused_estimate_prepare(x, self.quantizer)
-            else:
-                cur_xmin, cur_xmax = self.range_estimator(x)
-                self.set_quant_range(cur_xmin, cur_xmax)
+            else:                   # :116-118
+                self.set_quant_range(*self.range_estimator(x))
         return self.quantizer(x)
 
-    def set_quant_range(self, x_min, x_max):
-        self.quantizer.set_quant_range(x_min, x_max)
-
     def extra_repr(self):
-        return "state={}".format(self.state.name)
+        return f"state={self.state.name}"
