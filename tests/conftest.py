@@ -14,6 +14,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The CPU tests drive the reference's Python loops (thousands of tiny ATen ops): with one OpenMP team per op on a
+    # shared host they spend their time in thread hand-offs (measured: the config-4 case 592 s with 8 threads, 75 s
+    # with 1).  Two threads keep the few large convolutions reasonable.  FP8FQ_TEST_THREADS overrides.
+    torch.set_num_threads(int(os.environ.get("FP8FQ_TEST_THREADS", "2")))
 
 
 def pytest_collection_modifyitems(config, items):
