@@ -66,7 +66,11 @@ def test_reference_arm_line_has_the_contract_keys():
     bench = _bench()
     cfg = bench.base_config(5)
     assert cfg["workload"] == bench.WORKLOAD and cfg["mantissa_bits"] == 5 and cfg["n_bits"] == 8
-    cb = bench.run_cpu_reference(1, 0, 2, 5)
+    threads = torch.get_num_threads()
+    try:
+        cb = bench.run_cpu_reference(1, 0, 2, 5)   # probes thread counts and keeps the fastest for its own process
+    finally:
+        torch.set_num_threads(threads)
     for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "steps", "batch"):
         assert k in cb
     assert cb["kind"] == "port" and cb["unit"] == "Gelem/s" and cb["steps"] == 1 and cb["batch"] == 2 and cb["value"] > 0
