@@ -20,6 +20,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 
 #include "../../include/fp8fq.h"
@@ -286,6 +287,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 #ifndef FP8FQ_FOLD_ACT
 #define FP8FQ_FOLD_ACT 0
 #endif
+// FP8FQ_FULL_TILE (build option, default off; same status): fq_stream_kernel instantiates its tile body a second time
+// without the per-vector bounds predicates for the tiles that are full (all but the last one of a launch), so that the
+// four loads / stores of a thread share one base address and the 64-bit bounds tests disappear from the common path.
+#ifndef FP8FQ_FULL_TILE
+#define FP8FQ_FULL_TILE 0
+#endif
 template <int KMODE>
 __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
   if (act == FP8FQ_ACT_RELU || act == FP8FQ_ACT_RELU6) c.lo = max_nan(c.lo, 0.0f);
@@ -545,6 +552,13 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTile;
+#if FP8FQ_FULL_TILE
+    // the tile body is instantiated twice: every tile but the last one is full and needs no bounds predicates
+    auto tile_body = [&](auto full_tag) {
+    constexpr bool kFullTile = decltype(full_tag)::value;
+#else
+    constexpr bool kFullTile = false;
+#endif
     const int64_t base = tile0 + (int64_t)threadIdx.x * VEC;
     // 1. all of this thread's loads go out before any of them is used
     Pack<VEC> in[kUnroll], in2[kUnroll];
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t i = base + (int64_t)u * nthr * VEC;
-      ok[u] = i < nvec_elems;
+      ok[u] = kFullTile || i < nvec_elems;
       if (ok[u]) {
         in[u].load(a.x + i);
         if (kTwoIn) in2[u].load(a.x2 + i);
@@ -649,6 +663,13 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
       out.store(a.y + i);
       if (CODES) co.store(a.codes + i);
     }
+#if FP8FQ_FULL_TILE
+    };
+    // (not for the channel-innermost variants: with the predicates gone the compiler hoists all their batch-norm
+    // parameter loads and spills -- static SASS, profiles/static_build_options_r01.json)
+    if (!kCL && tile0 + kTile <= nvec_elems) tile_body(std::true_type{});
+    else tile_body(std::false_type{});
+#endif
   }
   // scalar tail (n % VEC elements), VEC == 4 only
   if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {

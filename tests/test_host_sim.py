@@ -395,20 +395,23 @@ def test_add_act_quant_equals_composition(sim, ref):
                     assert same_bits(y, ref_quant(ref, v.astype(np.float32), mv, M)[0]), (M, n, off, act)
 
 
-def test_fold_act_build_option_is_bit_identical_to_the_default_build(sim):
-    """-DFP8FQ_FOLD_ACT=1 (csrc/fp8fq_kernels.cu: ReLU / ReLU6 folded into the quantiser's clamp bounds; off by default)
+@pytest.mark.parametrize("variant", ["foldact", "fulltile"])
+def test_build_options_are_bit_identical_to_the_default_build(sim, variant):
+    """The product's build options (csrc/fp8fq_kernels.cu, both off by default) -- -DFP8FQ_FOLD_ACT=1: ReLU / ReLU6 folded
+    into the quantiser's clamp bounds; -DFP8FQ_FULL_TILE=1: a second, predicate-free instantiation of the stream
+    kernel's tile body for full tiles (the launch below has four full tiles and a partial one) --
     against the default build, bit for bit, on inputs made of the cases the equivalence has to survive: +-0 (identity
     batch norm: scale 1, shift -0.0, so that -0.0 reaches the activation), +-inf, NaN, values around 0 / 6 / maxval,
     ranges below and above 6, zero / inf / NaN ranges, signed and unsigned formats, K <= 3 and K > 3, all three fused
     entry points in both layouts.  (The whole of this module also passes with FP8FQ_SIM_LIB pointing at that build.)"""
     from fp8_quantization_b200._lib import SIGNATURES
 
-    fold = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim_foldact.so"))
+    fold = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", f"libfp8fq_sim_{variant}.so"))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(fold, name)
         fn.restype, fn.argtypes = res, args
     rng = np.random.default_rng(5)
-    C, hw, N = 8, 1024, 2     # (the NCHW block tail needs 2 + 4095 // hw <= C)
+    C, hw, N = 8, 1028, 2     # (the NCHW block tail needs 2 + 4095 // hw <= C)
     n = N * C * hw
     one, negzero = aligned(C), aligned(C)
     one[:], negzero[:] = 1.0, -0.0
