@@ -17,7 +17,9 @@ def pytest_configure(config):
     # The CPU tests drive the reference's Python loops (thousands of tiny ATen ops): with one OpenMP team per op on a
     # shared host they spend their time in thread hand-offs (measured: the config-4 case 592 s with 8 threads, 75 s
     # with 1).  Two threads keep the few large convolutions reasonable.  FP8FQ_TEST_THREADS overrides.
-    torch.set_num_threads(int(os.environ.get("FP8FQ_TEST_THREADS", "2")))
+    # (Not on the GPU box: there the parity tests run the CPU oracle over full-size tensors and keep torch's default.)
+    if "FP8FQ_TEST_THREADS" in os.environ or not torch.cuda.is_available():
+        torch.set_num_threads(int(os.environ.get("FP8FQ_TEST_THREADS", "2")))
 
 
 def pytest_collection_modifyitems(config, items):
