@@ -1,0 +1,139 @@
+"""GPU A/B of the product's build options against the default build (run on the B200 box, one GPU):
+
+    python tools/ab_build_options.py [--batch 128] [--dry-run]
+
+For default / fold_act / full_tile / both (csrc/fp8fq_kernels.cu: FP8FQ_FOLD_ACT, FP8FQ_FULL_TILE) it
+  1. builds the variant next to the default library (gpurun_out/libfp8fq_<variant>.so; nvcc is on the box),
+  2. hashes the outputs of a fixed set of fused calls (both layouts, three activations, K <= 3 and K > 3 formats, special
+     values) in a subprocess with FP8FQ_LIB pointing at the variant -- every variant must give the default's hashes,
+  3. times the kernels (tools/bench_kernels.py) and the bench step in both layouts (bench.py --no-cpu --no-e2e
+     --no-model),
+and writes gpurun_out/ab_build_options.json.  Each leg is its own process, so a failing variant cannot take the others
+down.  CPU-side evidence for the same options: tests/test_host_sim.py (bit equality on the host simulation),
+profiles/static_build_options_r01.json (static SASS)."""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+VARIANTS = {"default": [], "fold_act": ["FP8FQ_FOLD_ACT=1"], "full_tile": ["FP8FQ_FULL_TILE=1"],
+            "both": ["FP8FQ_FOLD_ACT=1", "FP8FQ_FULL_TILE=1"]}
+
+
+def hash_leg():
+    """Runs inside the subprocess of one variant: prints {"case": sha256} as JSON."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import ops
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(10)
+    sp = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-30, -1e-30, 6.0, -6.0, 5.9999995, 1e30])
+    res = {}
+
+    def digest(t):
+        t = t.contiguous()
+        t = torch.where(torch.isnan(t), torch.full_like(t, float("nan")), t)   # NaN payloads are not part of the contract
+        return hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()
+
+    for shape in ((4, 64, 56, 56), (3, 24, 9, 5), (2, 96, 14, 14), (5, 8, 33, 33)):
+        x = torch.randn(shape, generator=gen) * 3
+        x.view(-1)[::97][:sp.numel()] = sp[: x.view(-1)[::97].numel()]
+        r = torch.relu(torch.randn(shape, generator=gen))
+        C = shape[1]
+        mean, var = torch.randn(C, generator=gen).to(dev), (torch.rand(C, generator=gen) + 0.5).to(dev)
+        gamma, beta = torch.randn(C, generator=gen).to(dev), torch.randn(C, generator=gen).to(dev)
+        for layout in ("nchw", "channels_last"):
+            fmt = torch.channels_last if layout == "channels_last" else torch.contiguous_format
+            xd, rd = x.to(dev).contiguous(memory_format=fmt), r.to(dev).contiguous(memory_format=fmt)
+            for M, mv in ((5, 3.0), (3, 7.5), (4, 0.4)):
+                q = fq.FPQuantizer(8, mantissa_bits=M, maxval=mv)
+                qi = fq.FPQuantizer(8, mantissa_bits=4, maxval=2.5)
+                tb, _ = q.table_for(xd)
+                ti, _ = qi.table_for(xd)
+                for mode in (0, 1):
+                    if mode == 1:
+                        p0, p1 = ops.bn_pack(mean, var, gamma, beta, 1e-5), None
+                    else:
+                        p0, p1 = ops.bn_fold(mean, var, gamma, beta, 1e-5)
+                    for act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_RELU6):
+                        key = f"{shape}/{layout}/M{M}/bn{mode}/act{act}"
+                        res[key + "/bn_act_quant"] = digest(ops.bn_act_quant(xd, p0, p1, act, tb, float(M), 8, 1, bn_mode=mode))
+                        try:
+                            y = ops.bn_quant_add_act_quant(xd, rd, p0, p1, act, ti, (4.0, 8, 1), tb, (float(M), 8, 1),
+                                                           bn_mode=mode)
+                            res[key + "/block_tail"] = digest(y) if y is not None else "unsupported"
+                        except fq.Fp8fqError as e:   # shapes the fused tail does not cover
+                            res[key + "/block_tail"] = "error: " + str(e)[:40]
+                for act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_RELU6):
+                    res[f"{shape}/{layout}/M{M}/act{act}/add_act_quant"] = digest(ops.add_act_quant(xd, rd, act, tb, float(M), 8, 1))
+                res[f"{shape}/{layout}/M{M}/plain"] = digest(ops.fake_quant(xd, tb, 1, float(M), 8, 1))
+    print("HASHES " + json.dumps(res))
+
+
+def run(cmd, env, dry, timeout=1200):
+    print("+", " ".join(cmd), flush=True)
+    if dry:
+        return 0, ""
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    return p.returncode, p.stdout + p.stderr
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("--hash-leg", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.hash_leg:
+        return hash_leg()
+    os.makedirs(OUT, exist_ok=True)
+    summary = {}
+    for name, defines in VARIANTS.items():
+        rec = summary[name] = {"defines": defines}
+        env = dict(os.environ)
+        if defines:
+            lib = os.path.join(OUT, f"libfp8fq_{name}.so")
+            code, log = run([sys.executable, "-m", "fp8_quantization_b200.build"] + [f"-D{d}" for d in defines]
+                            + ["--out", lib], env, args.dry_run)
+            if code != 0:
+                rec["build_error"] = log[-500:]
+                continue
+            env["FP8FQ_LIB"] = lib
+        code, log = run([sys.executable, os.path.abspath(__file__), "--hash-leg"], env, args.dry_run)
+        line = next((ln for ln in log.split("\n") if ln.startswith("HASHES ")), None)
+        rec["hashes"] = json.loads(line[7:]) if line else None
+        if line is None and not args.dry_run:
+            rec["hash_error"] = log[-500:]
+        env["KERNELS_JSON"] = f"kernels_{name}.json"
+        code, log = run([sys.executable, "tools/bench_kernels.py", str(args.batch)], env, args.dry_run)
+        rec["bench_kernels"] = "ok" if code == 0 else log[-300:]
+        for layout in ("channels_last", "nchw"):
+            code, log = run([sys.executable, "bench.py", "--steps", "30", "--warmup", "5", "--no-cpu", "--no-e2e",
+                             "--no-model", "--memory-format", layout, "--batch", str(args.batch)], env, args.dry_run)
+            line = next((ln for ln in reversed(log.split("\n")) if ln.startswith("{")), None)
+            try:
+                d = json.loads(line)
+                rec[f"bench_{layout}"] = {"ms_per_step": d["ms_per_step"], "value": d["value"],
+                                          "roofline_frac": d["roofline"]["frac"],
+                                          "largest_launch_frac": d["roofline"]["largest_launch"]["frac"]}
+            except (TypeError, ValueError, KeyError):
+                rec[f"bench_{layout}"] = {"error": log[-300:]}
+    base = summary["default"].get("hashes")
+    for name, rec in summary.items():
+        h = rec.pop("hashes", None)
+        if base and h:
+            bad = sorted(k for k in base if h.get(k) != base[k])
+            rec["parity_vs_default"] = {"cases": len(base), "mismatches": len(bad), "first": bad[:5]}
+    json.dump(summary, open(os.path.join(OUT, "ab_build_options.json"), "w"), indent=1)
+    print(json.dumps(summary, indent=1))
+
+
+if __name__ == "__main__":
+    main()
