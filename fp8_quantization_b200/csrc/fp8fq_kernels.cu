@@ -280,9 +280,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // FP8FQ_FOLD_ACT (build option, default off; candidate for round 2 -- bits proven on the host simulation, not yet run
 // on a device): ReLU / ReLU6 in front of an FP quantiser are folded into the quantiser's clamp,
 //   min(max(act(v), lo), hi) == min(max(v, max(lo, 0)), min(hi, 6 for ReLU6)),
-// which holds for every input including NaN (max.NaN / min.NaN propagate), +-inf and signed zeros (PTX orders
-// -0.0 < +0.0, and lo <= 0 <= hi or NaN): the two bounds are adjusted once per thread and the 1-2 min/max per element
-// of the activation disappear from the issue-bound BN variants.  Not applied to the INT quantisers (KMODE 2), whose
+// which holds for every input including NaN (max.NaN / min.NaN propagate), +-inf and signed zeros: with lo < 0 or
+// lo == +0.0 the folded clamp executes the very instruction the activation did, max.NaN(v, +0.0), on the same operands
+// (so the hardware's ordering of -0.0 / +0.0 does not enter), and min(min(a, 6), hi) == min(a, min(hi, 6)) for
+// a >= 0, hi > 0; a zero range (lo == -0.0) yields NaN outputs either way.  The two bounds are adjusted once per thread
+// and the 1-2 min/max per element of the activation disappear from the issue-bound BN variants.  Not applied to the INT quantisers (KMODE 2), whose
 // clamp comes after the rounding.
 #ifndef FP8FQ_FOLD_ACT
 #define FP8FQ_FOLD_ACT 0
