@@ -74,3 +74,21 @@ def test_reference_arm_line_has_the_contract_keys():
     for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "steps", "batch"):
         assert k in cb
     assert cb["kind"] == "port" and cb["unit"] == "Gelem/s" and cb["steps"] == 1 and cb["batch"] == 2 and cb["value"] > 0
+
+
+def test_ab_build_options_tool_hash_leg_on_the_simulation(simdev):
+    """tools/ab_build_options.py (the GPU A/B of the kernels' build options): its parity leg -- output hashes of 384 fused
+    calls -- runs here on the host simulation, so that the tool is known to work before it is given GPU time."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ab_build_options", os.path.join(ROOT, "tools", "ab_build_options.py"))
+    ab = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ab)
+    h = ab.hash_leg("cpu")
+    assert len(h) == 384 and not any(v.startswith("error") for v in h.values())
+    assert sum(v == "unsupported" for v in h.values()) < 40       # block tails of the two small NCHW shapes
+    assert len({v for v in h.values() if len(v) == 64}) >= 90      # distinct outputs per (shape, format, activation, op)
+    for k, v in h.items():                                          # the two layouts give the same bits
+        if "/nchw/" in k and len(v) == 64 and len(h[k.replace("/nchw/", "/channels_last/")]) == 64:
+            assert h[k.replace("/nchw/", "/channels_last/")] == v, k
+    assert set(ab.VARIANTS) == {"default", "fold_act", "full_tile", "both"}

@@ -24,15 +24,16 @@ VARIANTS = {"default": [], "fold_act": ["FP8FQ_FOLD_ACT=1"], "full_tile": ["FP8F
             "both": ["FP8FQ_FOLD_ACT=1", "FP8FQ_FULL_TILE=1"]}
 
 
-def hash_leg():
-    """Runs inside the subprocess of one variant: prints {"case": sha256} as JSON."""
+def hash_leg(device="cuda:0"):
+    """Runs inside the subprocess of one variant: returns {"case": sha256 of the output}.  (``device`` exists for the CPU
+    test of this tool, which runs it on the host simulation: tests/test_bench_plumbing.py.)"""
     import torch
 
     sys.path.insert(0, ROOT)
     import fp8_quantization_b200 as fq
     from fp8_quantization_b200 import ops
 
-    dev = torch.device("cuda:0")
+    dev = torch.device(device)
     gen = torch.Generator().manual_seed(10)
     sp = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-30, -1e-30, 6.0, -6.0, 5.9999995, 1e30])
     res = {}
@@ -74,7 +75,7 @@ def hash_leg():
                 for act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_RELU6):
                     res[f"{shape}/{layout}/M{M}/act{act}/add_act_quant"] = digest(ops.add_act_quant(xd, rd, act, tb, float(M), 8, 1))
                 res[f"{shape}/{layout}/M{M}/plain"] = digest(ops.fake_quant(xd, tb, 1, float(M), 8, 1))
-    print("HASHES " + json.dumps(res))
+    return res
 
 
 def run(cmd, env, dry, timeout=1200):
@@ -92,7 +93,8 @@ def main():
     ap.add_argument("--hash-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.hash_leg:
-        return hash_leg()
+        print("HASHES " + json.dumps(hash_leg()))
+        return
     os.makedirs(OUT, exist_ok=True)
     summary = {}
     for name, defines in VARIANTS.items():
