@@ -88,6 +88,13 @@ def _like(t, ref):
     return t
 
 
+def _weight_for_quantizer(w):
+    """The tensor a weight quantiser receives: the live (graph-attached) weight while autograd records and the weight
+    wants a gradient -- FPQuantizer then returns its STE node, quantizers._FakeQuantSTE, and the forward-only INT
+    quantisers raise instead of silently freezing the layer -- otherwise a detached view."""
+    return w if (torch.is_grad_enabled() and w.requires_grad) else w.detach()
+
+
 def _act_code(act):
     """Kernel activation code for a fusable activation module, or None if it cannot be fused."""
     if act is None:
@@ -333,7 +340,9 @@ class QuantizationHijacker(QuantizedModule):
         return weight, bias
 
     def quantize_weights(self, weights):
-        return self.weight_quantizer(weights.detach())
+        # hijacker.py:96 hands the live Parameter to the quantiser so that the STE gradient reaches ``self.weight``;
+        # without autograd recording the detached view keeps the forward-only kernels on their fast path
+        return self.weight_quantizer(_weight_for_quantizer(weights))
 
     def get_weight_bias(self):
         bias = self.bias if hasattr(self, "bias") else None
@@ -533,7 +542,7 @@ class QuantConvTransposeBase(QuantizationHijacker):
     def quantize_weights(self, weights):
         if self.per_channel_weights:
             weights = weights.transpose(1, 0).contiguous()
-        weights = self.weight_quantizer(weights.detach())
+        weights = self.weight_quantizer(_weight_for_quantizer(weights))
         if self.per_channel_weights:
             weights = weights.transpose(1, 0).contiguous()
         return weights

@@ -100,7 +100,9 @@ class QuantizationManager(nn.Module):
     def forward(self, x):
         if self.estimating():
             if self._fusable():     # statistics + estimator update + set_quant_range + prologue: one launch
-                x = self.range_estimator.fused_estimate_prepare(x, self.quantizer)
+                # (only the statistics see a detached x -- range_estimators.py:73-74 -- the quantiser below gets the
+                # graph-attached tensor, so estimate_ranges_train keeps the upstream layers' gradients)
+                self.range_estimator.fused_estimate_prepare(x, self.quantizer)
             else:                   # :116-118
                 self.set_quant_range(*self.range_estimator(x))
         return self.quantizer(x)

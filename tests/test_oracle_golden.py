@@ -137,3 +137,60 @@ def test_oracle_equals_live_reference():
             oq.set_quant_range(mn, mx)
             assert torch.equal(oq.maxval, q.maxval)
             assert torch.equal(bits(oq(x)), bits(y_ref))
+
+
+# ---- oracle-composed networks (oracle/fp8_oracle_models.py) against the REAL reference's ranges and logits -------------
+def _check_composed(golden, digits, sites, logits):
+    names = [str(n) for n in golden["names"]]
+    mv = sites.maxvals()
+    assert list(mv.keys()) != [] and set(mv.keys()) == set(names)
+    for i, n in enumerate(names):
+        ref = golden[f"maxval_{i:0{digits}d}"]
+        ours = mv[n].numpy()
+        if STRICT:
+            assert np.array_equal(ours, ref), n
+        else:
+            np.testing.assert_allclose(ours, ref, rtol=1e-5, err_msg=n)
+    if STRICT:
+        assert np.array_equal(logits.numpy(), golden["logits"])
+    else:
+        np.testing.assert_allclose(logits.numpy(), golden["logits"], rtol=1e-3, atol=1e-3)
+
+
+def test_oracle_composed_resnet18_equals_reference_golden():
+    """BASELINE config 2 in miniature: the oracle-composed quantised ResNet-18 (plain F.conv2d / F.batch_norm /
+    oracle quantisers and estimators, no product module) calibrated on the golden batch reproduces all 50 ranges and the
+    logits of the real reference's QuantizedResNet bit for bit.  This pins the checker of tests/test_gpu_model_parity.py."""
+    from torchvision.models import resnet18
+
+    from oracle import fp8_oracle_models as OM
+
+    g = load_golden("resnet18_m5.npz")
+    torch.manual_seed(10)
+    net = resnet18().eval()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(10))
+    S = OM.OracleSites(5)
+    OM.resnet_forward(S, net, x)
+    S.fix_ranges()
+    _check_composed(g, 2, S, OM.resnet_forward(S, net, x))
+    assert len(S.sites) == 50
+
+
+def test_oracle_composed_mobilenetv2_equals_reference_golden():
+    """BASELINE config 3 in miniature: same for QuantizedMobileNetV2 (M=4): 123 quantisers (116 used + 7 that keep
+    their default range), logits bit for bit."""
+    from fp8_quantization_b200 import workloads
+    from oracle import fp8_oracle_models as OM
+
+    g = load_golden("mobilenetv2_m4.npz")
+    torch.manual_seed(10)
+    net = workloads.MobileNetV2().eval()
+    sd = net.state_dict()
+    sums = [int(sd[k].float().contiguous().view(torch.int32).to(torch.int64).sum()) for k in sd.keys()]
+    assert sums == list(g["w_checksums"])   # same fp32 network as the reference built under this seed
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(10))
+    S = OM.OracleSites(4)
+    OM.mobilenetv2_forward(S, net, x)
+    S.fix_ranges()
+    _check_composed(g, 3, S, OM.mobilenetv2_forward(S, net, x))
+    assert len(S.sites) == 123
