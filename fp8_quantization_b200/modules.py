@@ -381,8 +381,12 @@ class BNFusedHijacker(QuantizationHijacker):
         pass; BN re-estimation or a state-dict load bumps their version counters / storage and invalidates it."""
         ts = (self.running_mean, self.running_var, self.gamma, self.beta)
         mode = 1 if BN_EXACT else 0
+        # keyed on the tensor OBJECTS (kept alive in _bn_src, so neither an id nor a storage address can be recycled
+        # by a re-bound tensor, e.g. reestimate_BN_stats' fresh running statistics) and their version counters
+        src = self.__dict__.get("_bn_src")
         key = tuple((t.data_ptr(), t._version) for t in ts) + (float(self.epsilon), mode)
-        if key != self._bn_key:
+        if key != self._bn_key or src is None or any(a is not b for a, b in zip(src, ts)):
+            self.__dict__["_bn_src"] = ts
             if mode == 1:
                 self._bn_folded = (ops.bn_pack(self.running_mean, self.running_var, self.gamma.detach(),
                                                self.beta.detach(), self.epsilon), None, 1)
@@ -391,6 +395,10 @@ class BNFusedHijacker(QuantizationHijacker):
                                               self.beta.detach(), self.epsilon) + (0,)
             self._bn_key = key
         return self._bn_folded
+
+    def _load_from_state_dict(self, state_dict, prefix, *a, **k):
+        super()._load_from_state_dict(state_dict, prefix, *a, **k)
+        self._bn_key = None   # loaded statistics: re-pack on the next forward
 
     def _fused_epilogue_ok(self, res) -> bool:
         return (self._qa and not self.quantize_input and not self.training and ops.on_device(res) and res.dim() >= 2

@@ -200,16 +200,37 @@ class FPQuantizer(QuantizerBase):
             self._mantissa_bits = torch.Tensor([float(value)])
         self._table_key = None
 
+    # -- state dict: the reference registers learnable ranges as ``maxval`` / ``mantissa_bits`` (fp8_quantizer.py:
+    # 248-254); here they live behind properties as ``_maxval`` / ``_mantissa_bits``.  Keys are translated both ways so
+    # that checkpoints travel between the two implementations.
+    _STATE_NAMES = (("_maxval", "maxval"), ("_mantissa_bits", "mantissa_bits"))
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        for ours, ref in self._STATE_NAMES:
+            if prefix + ours in destination:
+                destination[prefix + ref] = destination.pop(prefix + ours)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for ours, ref in self._STATE_NAMES:
+            if prefix + ref in state_dict and ours in self._parameters:
+                state_dict[prefix + ours] = state_dict.pop(prefix + ref)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._table_key = None
+
     # -- table management -------------------------------------------------------------------------
     def _ensure_table(self, device):
         mv = self._maxval
         if mv.device != device or mv.dtype != torch.float32 or not mv.is_contiguous():
             mv = mv.detach().to(device=device, dtype=torch.float32).contiguous()
             self._maxval = mv  # same lazy move as fp8_quantizer.py:195-196
+        # keyed on the maxval tensor OBJECT (kept alive in _table_src: a tensor re-bound behind the setters' back cannot
+        # alias a recycled address) and its version counter
         key = (mv.data_ptr(), mv._version, mv.numel(), self._mbits_host, self.n_bits, self.sign_bits)
-        if key != self._table_key:
+        if key != self._table_key or self.__dict__.get("_table_src") is not mv:
             self._table = ops.prepare(mv.detach(), self._mbits_host, self.n_bits, self.sign_bits)
             self._table_key = key
+            self.__dict__["_table_src"] = mv
         return self._table
 
     def adopt_range(self, maxval: torch.Tensor, table: torch.Tensor):
@@ -220,6 +241,7 @@ class FPQuantizer(QuantizerBase):
         self._table = table
         self._table_key = (maxval.data_ptr(), maxval._version, maxval.numel(), self._mbits_host, self.n_bits,
                            self.sign_bits)
+        self.__dict__["_table_src"] = maxval
 
     @property
     def table(self):

@@ -65,6 +65,25 @@ class RangeEstimatorBase(nn.Module):
         self.current_xmin = None
         self.current_xmax = None
 
+    # The reference keeps per-tensor statistics as 0-dim tensors (x.min() / x.max(), range_estimators.py:73-74); the
+    # kernels here write [C]-shaped state with C == 1.  Checkpoints use the reference's shapes, both ways.
+    _STATE_BUFFERS = ("current_xmin", "current_xmax")
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if not self.per_channel:
+            for k in self._STATE_BUFFERS:
+                t = destination.get(prefix + k)
+                if t is not None and t.dim() == 1 and t.numel() == 1:
+                    destination[prefix + k] = t.reshape(())
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for k in self._STATE_BUFFERS:
+            t, cur = state_dict.get(prefix + k), getattr(self, k)
+            if t is not None and cur is not None and t.dim() == 0 and cur.dim() == 1 and cur.numel() == 1:
+                state_dict[prefix + k] = t.reshape(1)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def __repr__(self):
         lines = self.extra_repr().split("\n")
         extra_str = lines[0] if len(lines) == 1 else "\n  " + "\n  ".join(lines) + "\n"
@@ -245,7 +264,14 @@ class FP_MSE_Estimator(RangeEstimatorBase):
             mbit_list = [float(m) for m in range(1, qz.n_bits - qz.sign_bits)]
         grid, mses = self._define_search_range(x, mbit_list)
         assert mses.shape[1:] == grid.shape, f"{mses.shape}, {grid.shape}"
-        sign_bits = int(torch.any(x < 0)) if qz.allow_unsigned else 1
+        sign_bits = 1
+        if qz.allow_unsigned:
+            # one decision for the GLOBAL batch: ranks whose shards disagree on "any negative value" would otherwise
+            # average MSE tables of different formats
+            neg = torch.any(x < 0).to(torch.float32).reshape(1)
+            if fq_dist.active():
+                fq_dist.all_reduce_max(neg)
+            sign_bits = int(neg.item())
         if qz.allow_unsigned and sign_bits == 0:
             qz.sign_bits = 0  # what set_quant_range(-0.0 * maxval, maxval) does in the reference loop (:341-342)
         if fq_dist.active():
@@ -342,6 +368,10 @@ class LineSearchEstimator(RangeEstimatorBase):
         if self.loss_array is None:
             mm = torch.empty(2, dtype=torch.float32, device=data.device)
             ops.minmax(data, False, mm[:1], mm[1:], ops.EST_CURRENT, False)
+            if fq_dist.active():      # global-batch extremes, so that every rank searches the same candidates
+                mm[:1].neg_()
+                fq_dist.all_reduce_max(mm)
+                mm[:1].neg_()
             dmin, dmax = mm.tolist()  # the reference reads float(data.min()) / float(data.max()) here too
             if self.one_sided_dist is None:
                 self.one_sided_dist = bool(dmin >= 0)

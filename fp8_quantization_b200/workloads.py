@@ -25,6 +25,71 @@ from .range_estimators import AllMinMaxEstimator, CurrentMinMaxEstimator
 
 
 # ---------------------------------------------------------------------------------------------------
+# quant_setup: per-layer deviations from the uniform configuration
+# ---------------------------------------------------------------------------------------------------
+# The reference applies them as if/elif ladders at the end of the model constructors (models/resnet_quantized.py:
+# 94-124, models/mobilenet_v2_quantized.py:45-84).  Here they are data: setup name -> edits, an edit being
+# (module path below the model, field, value) with the fields
+#   "w_bits" / "a_bits"  n_bits of the layer's weight / activation quantiser
+#   "fp32_acts"          replace the layer's activation quantiser by FP32Acts (no quantisation)
+#   "fp32_block_acts"    the same for every QuantizedActivation below the path (block outputs, tied wrappers)
+#   "dw_w_bits"          w_bits of every depthwise BNQConv below the path
+# Negative indices count from the end of a Sequential, as in the reference's ``self.features[-1][-1]``.
+_RESNET_SETUPS = {
+    "all": (),
+    "LSQ": (("features.0", "w_bits", 8), ("features.-1.-1", "a_bits", 8), ("features.-1.-1.features.-1", "a_bits", 8),
+            ("fc", "w_bits", 8), ("fc", "fp32_acts", None)),
+    "LSQ_paper": (("features.0", "fp32_acts", None), ("features.0", "w_bits", 8), ("fc", "a_bits", 8), ("fc", "w_bits", 8),
+                  ("features", "fp32_block_acts", None)),
+    "FP_logits": (("fc", "fp32_acts", None),),
+    "fc4": (("features.0", "w_bits", 8), ("fc", "w_bits", 4)),
+}
+_MOBILENETV2_SETUPS = {
+    "all": (),
+    "FP_logits": (("classifier.1", "fp32_acts", None),),
+    "fc4": (("features.0.0", "w_bits", 8), ("classifier.1", "w_bits", 4)),
+    "fc4_dw8": (("features.0.0", "w_bits", 8), ("classifier.1", "w_bits", 4), ("", "dw_w_bits", 8)),
+    "LSQ": (("features.0.0", "w_bits", 8), ("features.-2.0", "a_bits", 8), ("classifier.1", "w_bits", 8),
+            ("classifier.1", "fp32_acts", None)),
+    "LSQ_paper": (("features.0.0", "fp32_acts", None), ("features.0.0", "w_bits", 8), ("classifier.1", "w_bits", 8),
+                  ("classifier.1", "a_bits", 8), ("features", "fp32_block_acts", None)),
+}
+
+
+def _resolve(root, path):
+    mod = root
+    for part in (path.split(".") if path else ()):
+        mod = mod[int(part)] if part.lstrip("-").isdigit() else getattr(mod, part)
+    return mod
+
+
+def apply_quant_setup(model, family, table, quant_setup):
+    """Applies the edits of ``table[quant_setup]`` to a freshly built quantised model (None = "all")."""
+    if quant_setup is None:
+        return
+    if quant_setup not in table:
+        raise ValueError("Quantization setup '{}' not supported for {}".format(quant_setup, family))
+    for path, field, value in table[quant_setup]:
+        target = _resolve(model, path)
+        if field == "w_bits":
+            target.weight_quantizer.quantizer.n_bits = value
+        elif field == "a_bits":
+            target.activation_quantizer.quantizer.n_bits = value
+        elif field == "fp32_acts":
+            target.activation_quantizer = FP32Acts()
+        elif field == "fp32_block_acts":
+            for layer in target.modules():
+                if isinstance(layer, QuantizedActivation):
+                    layer.activation_quantizer = FP32Acts()
+        elif field == "dw_w_bits":
+            for layer in target.modules():
+                if isinstance(layer, BNQConv) and layer.groups == layer.in_channels:
+                    layer.weight_quantizer.quantizer.n_bits = value
+        else:  # pragma: no cover
+            raise KeyError(field)
+
+
+# ---------------------------------------------------------------------------------------------------
 # ResNet
 # ---------------------------------------------------------------------------------------------------
 class QuantizedBlock(QuantizedActivation):
@@ -74,29 +139,7 @@ class QuantizedResNet(QuantizedModel):
         self.flattener = Flattener()
         self.fc = quantize_model(resnet.fc, **quant_params)
 
-        if quant_setup == "LSQ":
-            print("Set quantization to LSQ (first+last layer in 8 bits)")
-            self.features[0].weight_quantizer.quantizer.n_bits = 8
-            self.features[-1][-1].activation_quantizer.quantizer.n_bits = 8
-            self.features[-1][-1].features[-1].activation_quantizer.quantizer.n_bits = 8
-            self.fc.weight_quantizer.quantizer.n_bits = 8
-            self.fc.activation_quantizer = FP32Acts()
-        elif quant_setup == "LSQ_paper":
-            self.features[0].activation_quantizer = FP32Acts()
-            self.features[0].weight_quantizer.quantizer.n_bits = 8
-            self.fc.activation_quantizer.quantizer.n_bits = 8
-            self.fc.weight_quantizer.quantizer.n_bits = 8
-            for layer in self.features.modules():
-                if isinstance(layer, QuantizedActivation):
-                    layer.activation_quantizer = FP32Acts()
-        elif quant_setup == "FP_logits":
-            print("Do not quantize output of FC layer")
-            self.fc.activation_quantizer = FP32Acts()
-        elif quant_setup == "fc4":
-            self.features[0].weight_quantizer.quantizer.n_bits = 8
-            self.fc.weight_quantizer.quantizer.n_bits = 4
-        elif quant_setup is not None and quant_setup != "all":
-            raise ValueError("Quantization setup '{}' not supported for Resnet".format(quant_setup))
+        apply_quant_setup(self, "Resnet", _RESNET_SETUPS, quant_setup)
 
     def forward(self, x):
         self.prequantize_weights()
@@ -231,33 +274,7 @@ class QuantizedMobileNetV2(QuantizedModel):
         self.flattener = Flattener()
         self.classifier = quantize_model(model_fp.classifier, **quant_params)
 
-        if quant_setup == "FP_logits":
-            print("Do not quantize output of FC layer")
-            self.classifier[1].activation_quantizer = FP32Acts()
-        elif quant_setup == "fc4":
-            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
-            self.classifier[1].weight_quantizer.quantizer.n_bits = 4
-        elif quant_setup == "fc4_dw8":
-            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
-            self.classifier[1].weight_quantizer.quantizer.n_bits = 4
-            for name, module in self.named_modules():
-                if isinstance(module, BNQConv) and module.groups == module.in_channels:
-                    module.weight_quantizer.quantizer.n_bits = 8
-        elif quant_setup == "LSQ":
-            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
-            self.features[-2][0].activation_quantizer.quantizer.n_bits = 8
-            self.classifier[1].weight_quantizer.quantizer.n_bits = 8
-            self.classifier[1].activation_quantizer = FP32Acts()
-        elif quant_setup == "LSQ_paper":
-            self.features[0][0].activation_quantizer = FP32Acts()
-            self.features[0][0].weight_quantizer.quantizer.n_bits = 8
-            self.classifier[1].weight_quantizer.quantizer.n_bits = 8
-            self.classifier[1].activation_quantizer.quantizer.n_bits = 8
-            for layer in self.features.modules():
-                if isinstance(layer, QuantizedActivation):
-                    layer.activation_quantizer = FP32Acts()
-        elif quant_setup is not None and quant_setup != "all":
-            raise ValueError("Quantization setup '{}' not supported for MobilenetV2".format(quant_setup))
+        apply_quant_setup(self, "MobilenetV2", _MOBILENETV2_SETUPS, quant_setup)
 
     def forward(self, x):
         self.prequantize_weights()
@@ -326,52 +343,66 @@ def pass_data_for_range_estimation(loader, model, act_quant, weight_quant, max_n
     return passed
 
 
+class _BatchStatisticsMode:
+    """Context in which every BNFusedHijacker of ``model`` (the layer itself, not its quantiser children) normalises with
+    -- and, momentum being 1, records as its running statistics -- the statistics of the current batch."""
+
+    def __init__(self, model):
+        from .modules import BNFusedHijacker
+
+        self.layers = [m for m in model.modules() if isinstance(m, BNFusedHijacker)]
+        self.saved = None
+
+    def __enter__(self):
+        self.saved = [(m.momentum, m.training) for m in self.layers]
+        for m in self.layers:
+            m.momentum, m.training = 1.0, True
+        return self.layers
+
+    def __exit__(self, *exc):
+        for m, (momentum, training) in zip(self.layers, self.saved):
+            m.momentum, m.training = momentum, training
+
+
+def _keep_ema_statistics(layer):
+    """``store_ema_stats``: the statistics being replaced stay available as buffers (and thus in the state dict)."""
+    for name in ("running_mean", "running_var"):
+        ema = getattr(layer, name).detach().clone()
+        if name + "_ema" in layer._buffers:
+            setattr(layer, name + "_ema", ema)
+        else:
+            layer.register_buffer(name + "_ema", ema)
+
+
 @torch.no_grad()
 def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=False):
-    """utils/qat_utils.py:45-90: re-estimate the batch-norm statistics of the QUANTISED network.  Every
-    BNFusedHijacker runs with momentum 1 in training mode (its children do not), so after each forward its running
-    statistics are the current batch statistics; these are averaged over ``num_batches`` batches and written back.
+    """utils/qat_utils.py:45-90: re-estimate the batch-norm statistics of the QUANTISED network as the mean, over up to
+    ``num_batches`` batches, of the per-batch statistics each fused layer sees (quantisers stay in their current state).
     Under data parallelism (fp8_quantization_b200.dist active) the batch statistics are those of the global batch
-    (per-channel sum / sum-of-squares all-reduce), so every rank ends with the statistics a single process would
-    compute on the concatenated batches."""
-    from .modules import BNFusedHijacker
-
+    (per-channel sum / sum-of-squares all-reduce, modules._sync_batch_norm_train), so every rank ends with the
+    statistics a single process would compute on the concatenated batches.  Returns the number of batches used."""
     model.eval()
-    layers = [(n, m) for n, m in model.named_modules() if isinstance(m, BNFusedHijacker)]
-    org_momentum = {}
-    for name, module in layers:
-        org_momentum[name] = module.momentum
-        module.momentum = 1.0
-        module.running_mean_sum = torch.zeros_like(module.running_mean)
-        module.running_var_sum = torch.zeros_like(module.running_var)
-        module.training = True  # this module only, not its children (quantisers keep their state)
-        if store_ema_stats:
-            import copy
-
-            if not hasattr(module, "running_mean_ema"):
-                module.register_buffer("running_mean_ema", copy.deepcopy(module.running_mean))
-                module.register_buffer("running_var_ema", copy.deepcopy(module.running_var))
-            else:
-                module.running_mean_ema = copy.deepcopy(module.running_mean)
-                module.running_var_ema = copy.deepcopy(module.running_var)
     device = next(model.parameters()).device
-    batch_count = 0
-    for data in data_loader:  # the reference's loaders yield (x, y) (:72); bare input tensors are accepted too
-        x = data[0] if isinstance(data, (tuple, list)) else data
-        model(x.to(device))
-        for _, module in layers:
-            module.running_mean_sum += module.running_mean
-            module.running_var_sum += module.running_var
-        batch_count += 1
-        if batch_count == num_batches:
-            break
-    for name, module in layers:
-        module.running_mean = module.running_mean_sum / batch_count
-        module.running_var = module.running_var_sum / batch_count
-        module.momentum = org_momentum[name]
-        del module.running_mean_sum, module.running_var_sum
+    batches = 0
+    with _BatchStatisticsMode(model) as layers:
+        if store_ema_stats:
+            for layer in layers:
+                _keep_ema_statistics(layer)
+        totals = [(torch.zeros_like(m.running_mean), torch.zeros_like(m.running_var)) for m in layers]
+        for data in data_loader:    # the reference's loaders yield (x, y) (:72); bare input tensors are accepted too
+            model((data[0] if isinstance(data, (tuple, list)) else data).to(device))
+            for layer, (mean_sum, var_sum) in zip(layers, totals):
+                mean_sum += layer.running_mean
+                var_sum += layer.running_var
+            batches += 1
+            if batches == num_batches:
+                break
+        for layer, (mean_sum, var_sum) in zip(layers, totals):
+            layer.running_mean = mean_sum / batches
+            layer.running_var = var_sum / batches
+            layer._bn_key = None   # fresh statistics tensors: the packed batch-norm parameters are stale
     model.eval()
-    return batch_count
+    return batches
 
 
 class ReestimateBNStats:

@@ -132,3 +132,79 @@ def test_learnable_range_parameter_registration():
     q.maxval = torch.tensor([3.0])
     q.mantissa_bits = 3
     assert list(q.parameters()) == [] and float(q.maxval) == 3.0 and q._mbits_host == 3.0
+
+
+def _setup_census(model, quantizer_types, fp32_type):
+    """{module path: n_bits | "fp32"} for every quantiser / FP32Acts of a quantised model."""
+    out = {}
+    for name, m in model.named_modules():
+        if isinstance(m, quantizer_types):
+            out[name] = m.n_bits
+        elif isinstance(m, fp32_type):
+            out[name] = "fp32"
+    return out
+
+
+def test_quant_setup_tables():
+    """workloads._RESNET_SETUPS / _MOBILENETV2_SETUPS: the per-layer deviations of every quant_setup the reference
+    defines (models/resnet_quantized.py:94-124, models/mobilenet_v2_quantized.py:45-84)."""
+    from torchvision.models import resnet18
+
+    qp = workloads.readme_quant_params(5)
+    qp.pop("quant_setup")
+    base = _setup_census(workloads.QuantizedResNet(resnet18(), quant_setup="all", **qp), fq.FPQuantizer, modules.FP32Acts)
+    assert set(base.values()) == {8}
+    m = workloads.QuantizedResNet(resnet18(), quant_setup="fc4", **dict(qp, n_bits=4))
+    c = _setup_census(m, fq.FPQuantizer, modules.FP32Acts)
+    assert c["features.0.weight_quantizer.quantizer"] == 8 and c["fc.weight_quantizer.quantizer"] == 4
+    assert c["fc.activation_quantizer.quantizer"] == 4
+    m = workloads.QuantizedResNet(resnet18(), quant_setup="LSQ_paper", **dict(qp, n_bits=4))
+    c = _setup_census(m, fq.FPQuantizer, modules.FP32Acts)
+    assert isinstance(m.avgpool, nn.AdaptiveAvgPool2d)
+    assert c["features.0.activation_quantizer"] == "fp32" and c["features.2.0.activation_quantizer"] == "fp32"
+    assert c["features.2.0.features.0.activation_quantizer.quantizer"] == 4
+    assert c["fc.activation_quantizer.quantizer"] == 8 and c["fc.weight_quantizer.quantizer"] == 8
+    with pytest.raises(ValueError, match="not supported for Resnet"):
+        workloads.QuantizedResNet(resnet18(), quant_setup="nope", **qp)
+    m = workloads.QuantizedMobileNetV2(workloads.MobileNetV2(), quant_setup="fc4_dw8", **dict(qp, n_bits=4))
+    c = _setup_census(m, fq.FPQuantizer, modules.FP32Acts)
+    assert c["features.0.0.weight_quantizer.quantizer"] == 8 and c["classifier.1.weight_quantizer.quantizer"] == 4
+    assert c["features.2.conv.1.weight_quantizer.quantizer"] == 8      # depthwise 3x3
+    assert c["features.2.conv.0.weight_quantizer.quantizer"] == 4      # 1x1 expansion
+    with pytest.raises(ValueError, match="not supported for MobilenetV2"):
+        workloads.QuantizedMobileNetV2(workloads.MobileNetV2(), quant_setup="nope", **qp)
+
+
+def test_quant_setups_match_the_real_reference():
+    """Every quant_setup of both model families: same quantiser bit widths and FP32Acts placements, module path by
+    module path, as the reference's own constructors produce."""
+    from oracle.reference_loader import load_reference_models, reference_available
+
+    if not reference_available():
+        pytest.skip("reference checkout not present")
+    import contextlib
+    import io
+
+    from torchvision.models import resnet18
+
+    R = load_reference_models()
+    RE = R.range_estimators
+    rqp = dict(method=R.FPQuantizer, act_method=R.FPQuantizer, n_bits=4, n_bits_act=None, per_channel_weights=True,
+               weight_range_method=RE.CurrentMinMaxEstimator, weight_range_options={},
+               act_range_method=RE.AllMinMaxEstimator, act_range_options={}, quantize_input=False,
+               fp8_kwargs=dict(maxval=None, mantissa_bits=2, set_maxval=True, learn_maxval=False,
+                               learn_mantissa_bits=False, mse_include_mantissa_bits=False, allow_unsigned=False))
+    qp = workloads.readme_quant_params(2)
+    qp.pop("quant_setup")
+    qp["n_bits"] = 4
+    with contextlib.redirect_stdout(io.StringIO()):
+        for setup in ("all", "LSQ", "LSQ_paper", "FP_logits", "fc4"):
+            ref = R.resnet_quantized.QuantizedResNet(resnet18(), quant_setup=setup, **rqp)
+            ours = workloads.QuantizedResNet(resnet18(), quant_setup=setup, **qp)
+            assert _setup_census(ours, fq.FPQuantizer, modules.FP32Acts) == \
+                _setup_census(ref, R.FPQuantizer, R.base_quantized_classes.FP32Acts), setup
+        for setup in ("all", "FP_logits", "fc4", "fc4_dw8", "LSQ", "LSQ_paper"):
+            ref = R.mobilenet_v2_quantized.QuantizedMobileNetV2(R.mobilenet_v2.MobileNetV2(), quant_setup=setup, **rqp)
+            ours = workloads.QuantizedMobileNetV2(workloads.MobileNetV2(), quant_setup=setup, **qp)
+            assert _setup_census(ours, fq.FPQuantizer, modules.FP32Acts) == \
+                _setup_census(ref, R.FPQuantizer, R.base_quantized_classes.FP32Acts), setup
