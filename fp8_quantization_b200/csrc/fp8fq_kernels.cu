@@ -295,6 +295,51 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 #ifndef FP8FQ_FULL_TILE
 #define FP8FQ_FULL_TILE 0
 #endif
+// FP8FQ_PIN_SEL (build option): the K <= 3 code select is  s = p3 ? s3 : (p2 ? s2 : s1)  (and the same for 1/s).  ptxas
+// keeps the six table values in UNIFORM registers, and an FSEL takes at most one uniform operand, so every element pays
+// two extra moves (uniform -> vector register) for the inner selects.  The option keeps s2 and 1/s2 in vector registers:
+// they are re-loaded through an address ptxas cannot prove warp-uniform (threadIdx.y is 0 in every launch of this
+// library) -- a value it knows to be uniform goes back to a uniform register whatever the source says.
+#ifndef FP8FQ_PIN_SEL
+#define FP8FQ_PIN_SEL 0
+#endif
+__device__ __forceinline__ void pin_vreg(float& v, const float* src) {
+#if FP8FQ_PIN_SEL && defined(__CUDA_ARCH__) && !defined(FP8FQ_HOST_SIM)
+  v = __ldg(src + threadIdx.y);
+#else
+  (void)v; (void)src;
+#endif
+}
+// FP8FQ_PACK2 (build option): the independent fp32 multiplies / adds / FMAs of neighbouring elements are issued as
+// sm_100's two-wide instructions (FMUL2 / FADD2 / FFMA2: same IEEE round-to-nearest results, half the issue slots).
+#ifndef FP8FQ_PACK2
+#define FP8FQ_PACK2 0
+#endif
+__device__ __forceinline__ void mul2_rn(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+#if FP8FQ_PACK2 && defined(__CUDA_ARCH__)
+  const float2 r = __fmul2_rn(make_float2(a0, a1), make_float2(b0, b1));
+  r0 = r.x; r1 = r.y;
+#else
+  r0 = mul_rn(a0, b0); r1 = mul_rn(a1, b1);
+#endif
+}
+__device__ __forceinline__ void sub2_rn(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+#if FP8FQ_PACK2 && defined(__CUDA_ARCH__)
+  const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(-b0, -b1));
+  r0 = r.x; r1 = r.y;
+#else
+  r0 = sub_rn(a0, b0); r1 = sub_rn(a1, b1);
+#endif
+}
+__device__ __forceinline__ void fma2_rn(float a0, float a1, float b0, float b1, float c0, float c1, float& r0, float& r1) {
+#if FP8FQ_PACK2 && defined(__CUDA_ARCH__)
+  const float2 r = __ffma2_rn(make_float2(a0, a1), make_float2(b0, b1), make_float2(c0, c1));
+  r0 = r.x; r1 = r.y;
+#else
+  r0 = fmaf(a0, b0, c0); r1 = fmaf(a1, b1, c1);
+#endif
+}
+
 template <int KMODE>
 __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
   if (act == FP8FQ_ACT_RELU || act == FP8FQ_ACT_RELU6) c.lo = max_nan(c.lo, 0.0f);
@@ -383,11 +428,25 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       }
     }
   }
+  if (FP8FQ_PACK2 && N % 2 == 0) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const float r = mul_rn(xc[k], rs[k]);
-    q[k] = nearbyintf(r);
-    if (GUARD) slow |= !(fabsf(r - q[k]) < c.guard);
+    for (int k = 0; k + 1 < N; k += 2) {
+      float r0, r1, d0, d1;
+      mul2_rn(xc[k], xc[k + 1], rs[k], rs[k + 1], r0, r1);
+      q[k] = nearbyintf(r0);
+      q[k + 1] = nearbyintf(r1);
+      if (GUARD) {
+        sub2_rn(r0, r1, q[k], q[k + 1], d0, d1);
+        slow |= !(fabsf(d0) < c.guard) | !(fabsf(d1) < c.guard);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float r = mul_rn(xc[k], rs[k]);
+      q[k] = nearbyintf(r);
+      if (GUARD) slow |= !(fabsf(r - q[k]) < c.guard);
+    }
   }
   if (GUARD && slow) {
 #pragma unroll
@@ -396,9 +455,15 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       if (!(fabsf(r - q[k]) < c.guard)) q[k] = nearbyintf(div_rn(xc[k], s[k]));  // near a tie, or rs unusable
     }
   }
+  if (FP8FQ_PACK2 && N % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) mul2_rn(q[k], q[k + 1], s[k], s[k + 1], y[k], y[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) y[k] = mul_rn(q[k], s[k]);
+  }
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    y[k] = mul_rn(q[k], s[k]);
     if (s_out) s_out[k] = s[k];
     if (CODES) {
       if (y[k] != y[k]) code[k] = 0x7fffffff;
@@ -493,6 +558,27 @@ __device__ __forceinline__ float bn_apply(float v, const BnParams& p) {
   return fmaf(mul_rn(p.b, sub_rn(v, p.a)), p.c, p.d);
 }
 
+// batch norm of the VEC lanes of one vector that share a channel (NCHW rows)
+template <int BNM, int VEC>
+__device__ __forceinline__ void bn_apply_vec(const float (&in)[VEC], const BnParams& p, float (&v)[VEC]) {
+  if (FP8FQ_PACK2 && VEC % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k + 1 < VEC; k += 2) {
+      if (BNM == 0) {
+        fma2_rn(in[k], in[k + 1], p.a, p.a, p.b, p.b, v[k], v[k + 1]);
+      } else {
+        float t0, t1;
+        sub2_rn(in[k], in[k + 1], p.a, p.a, t0, t1);
+        mul2_rn(p.b, p.b, t0, t1, t0, t1);
+        fma2_rn(t0, t1, p.c, p.c, p.d, p.d, v[k], v[k + 1]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = bn_apply<BNM>(in[k], p);
+  }
+}
+
 constexpr int kThreads = 256;
 // independent 128-bit loads in flight per thread: 4 vectors, or 2 vectors x 2 inputs for the residual variants
 // (same bytes in flight, 16 fewer live registers -> no spills at 5-6 resident CTAs per SM)
@@ -542,6 +628,10 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   ElemCtx<KMODE> ctx, ctx2;
   load_ctx_direct<KMODE>(ctx, a.table, a.K);
   if (kTail) load_ctx_direct<KMODE>(ctx2, a.table2, a.K2);
+  if (KMODE == 0 && FP8FQ_PIN_SEL) {
+    if (a.K >= 2) { pin_vreg(ctx.rt.s2, a.table + off_sr(a.K) + 4); pin_vreg(ctx.rt.r2, a.table + off_sr(a.K) + 5); }
+    if (kTail && a.K2 >= 2) { pin_vreg(ctx2.rt.s2, a.table2 + off_sr(a.K2) + 4); pin_vreg(ctx2.rt.r2, a.table2 + off_sr(a.K2) + 5); }
+  }
 #if FP8FQ_FOLD_ACT
   // the activation (if any) feeds the LAST quantiser of the launch: ctx2 in the block tail, ctx otherwise
   constexpr bool kFoldAct = KMODE != 2 && (kBnAct || PRE == PRE_ADD || kTail);
@@ -623,8 +713,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
           uint32_t ch = ch0 + __umulhi(p, a.hw_rcp);
           ch = ch >= a.Cbn ? ch - a.Cbn : ch;
           const BnParams bp = bn_load<BNM>(a, ch);
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) v[k] = bn_apply<BNM>(in[u].v[k], bp);
+          bn_apply_vec<BNM, VEC>(in[u].v, bp, v);
         } else {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
