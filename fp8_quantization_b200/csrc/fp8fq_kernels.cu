@@ -277,8 +277,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// FP8FQ_FOLD_ACT (build option, default off; candidate for round 2 -- bits proven on the host simulation, not yet run
-// on a device): ReLU / ReLU6 in front of an FP quantiser are folded into the quantiser's clamp,
+// FP8FQ_FOLD_ACT (build option, default ON since round 2: 384 fused calls hash-identical to the unfolded build on the
+// B200, step 0.573 -> 0.551 ms, profiles/ab_build_options_r02a.json): ReLU / ReLU6 in front of an FP quantiser are
+// folded into the quantiser's clamp,
 //   min(max(act(v), lo), hi) == min(max(v, max(lo, 0)), min(hi, 6 for ReLU6)),
 // which holds for every input including NaN (max.NaN / min.NaN propagate), +-inf and signed zeros: with lo < 0 or
 // lo == +0.0 the folded clamp executes the very instruction the activation did, max.NaN(v, +0.0), on the same operands
@@ -287,13 +288,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // and the 1-2 min/max per element of the activation disappear from the issue-bound BN variants.  Not applied to the INT quantisers (KMODE 2), whose
 // clamp comes after the rounding.
 #ifndef FP8FQ_FOLD_ACT
-#define FP8FQ_FOLD_ACT 0
+#define FP8FQ_FOLD_ACT 1
 #endif
-// FP8FQ_FULL_TILE (build option, default off; same status): fq_stream_kernel instantiates its tile body a second time
+// FP8FQ_FULL_TILE (build option, default ON since round 2, same evidence; with FOLD_ACT: step 0.573 -> 0.546 ms,
+// in-step roofline 0.808 -> 0.849): fq_stream_kernel instantiates its tile body a second time
 // without the per-vector bounds predicates for the tiles that are full (all but the last one of a launch), so that the
 // four loads / stores of a thread share one base address and the 64-bit bounds tests disappear from the common path.
 #ifndef FP8FQ_FULL_TILE
-#define FP8FQ_FULL_TILE 0
+#define FP8FQ_FULL_TILE 1
 #endif
 // FP8FQ_PIN_SEL (build option): the K <= 3 code select is  s = p3 ? s3 : (p2 ? s2 : s1)  (and the same for 1/s).  ptxas
 // keeps the six table values in UNIFORM registers, and an FSEL takes at most one uniform operand, so every element pays
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
   const int act_left = kFoldAct ? FP8FQ_ACT_NONE : a.act;
 #define FQ_ACT act_left
 #else
-#define FQ_ACT a.act   // (the default build is token for token the code the round-1 profiles were taken from)
+#define FQ_ACT a.act   // (-DFP8FQ_FOLD_ACT=0 -DFP8FQ_FULL_TILE=0: token for token the code of the round-1 profiles)
 #endif
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -758,7 +760,10 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) 
     };
     // (not for the channel-innermost variants: with the predicates gone the compiler hoists all their batch-norm
     // parameter loads and spills -- static SASS, profiles/static_build_options_r01.json)
-    if (!kCL && tile0 + kTile <= nvec_elems) tile_body(std::true_type{});
+#ifndef FP8FQ_FULL_TILE_CL
+#define FP8FQ_FULL_TILE_CL 0
+#endif
+    if ((!kCL || FP8FQ_FULL_TILE_CL) && tile0 + kTile <= nvec_elems) tile_body(std::true_type{});
     else tile_body(std::false_type{});
 #endif
   }

@@ -91,4 +91,4 @@ def test_ab_build_options_tool_hash_leg_on_the_simulation(simdev):
     for k, v in h.items():                                          # the two layouts give the same bits
         if "/nchw/" in k and len(v) == 64 and len(h[k.replace("/nchw/", "/channels_last/")]) == 64:
             assert h[k.replace("/nchw/", "/channels_last/")] == v, k
-    assert set(ab.VARIANTS) == {"default", "fold_act", "full_tile", "both"}
+    assert "default" in ab.VARIANTS and ab.VARIANTS["default"] == []

@@ -395,11 +395,13 @@ def test_add_act_quant_equals_composition(sim, ref):
                     assert same_bits(y, ref_quant(ref, v.astype(np.float32), mv, M)[0]), (M, n, off, act)
 
 
-@pytest.mark.parametrize("variant", ["foldact", "fulltile"])
+@pytest.mark.parametrize("variant", ["nofoldact", "nofulltile", "fulltilecl"])
 def test_build_options_are_bit_identical_to_the_default_build(sim, variant):
-    """The product's build options (csrc/fp8fq_kernels.cu, both off by default) -- -DFP8FQ_FOLD_ACT=1: ReLU / ReLU6 folded
-    into the quantiser's clamp bounds; -DFP8FQ_FULL_TILE=1: a second, predicate-free instantiation of the stream
-    kernel's tile body for full tiles (the launch below has four full tiles and a partial one) --
+    """The product's build options (csrc/fp8fq_kernels.cu) -- FP8FQ_FOLD_ACT: ReLU / ReLU6 folded into the quantiser's
+    clamp bounds; FP8FQ_FULL_TILE: a second, predicate-free instantiation of the stream kernel's tile body for full
+    tiles (the launch below has four full tiles and a partial one); both ON by default since round 2, so the first two
+    variants are the round-1 arithmetic; "fulltilecl": the predicate-free body for the channel-innermost variants too
+    (+ the PACK2 / PIN_SEL code paths, which the host build evaluates with scalar arithmetic) --
     against the default build, bit for bit, on inputs made of the cases the equivalence has to survive: +-0 (identity
     batch norm: scale 1, shift -0.0, so that -0.0 reaches the activation), +-inf, NaN, values around 0 / 6 / maxval,
     ranges below and above 6, zero / inf / NaN ranges, signed and unsigned formats, K <= 3 and K > 3, all three fused

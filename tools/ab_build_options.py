@@ -2,7 +2,7 @@
 
     python tools/ab_build_options.py [--batch 128] [--dry-run]
 
-For default / fold_act / full_tile / both (csrc/fp8fq_kernels.cu: FP8FQ_FOLD_ACT, FP8FQ_FULL_TILE) it
+For the default build and each variant in VARIANTS / VARIANTS_R2 (build options of csrc/fp8fq_kernels.cu) it
   1. builds the variant next to the default library (gpurun_out/libfp8fq_<variant>.so; nvcc is on the box),
   2. hashes the outputs of a fixed set of fused calls (both layouts, three activations, K <= 3 and K > 3 formats, special
      values) in a subprocess with FP8FQ_LIB pointing at the variant -- every variant must give the default's hashes,
@@ -20,8 +20,14 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-VARIANTS = {"default": [], "fold_act": ["FP8FQ_FOLD_ACT=1"], "full_tile": ["FP8FQ_FULL_TILE=1"],
-            "both": ["FP8FQ_FOLD_ACT=1", "FP8FQ_FULL_TILE=1"]}
+VARIANTS = {"default": [], "round1": ["FP8FQ_FOLD_ACT=0", "FP8FQ_FULL_TILE=0"]}
+# round 2 (FOLD_ACT and FULL_TILE became the defaults after the first A/B, profiles/ab_build_options_r02a.json): operands
+# of the code select pinned in vector registers, two-wide fp32 arithmetic, the predicate-free tile body for the
+# channel-innermost variants too (at 5 and at 4 resident CTAs per SM)
+VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_pack": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1"],
+               "full_cl": ["FP8FQ_FULL_TILE_CL=1"], "full_cl_minb4": ["FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"],
+               "all": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1", "FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"]}
+FULL_BENCH = {"default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
 def hash_leg(device="cuda:0"):
@@ -90,6 +96,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("--round1-only", action="store_true", help="only the four variants of round 1")
     ap.add_argument("--hash-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.hash_leg:
@@ -97,7 +104,10 @@ def main():
         return
     os.makedirs(OUT, exist_ok=True)
     summary = {}
-    for name, defines in VARIANTS.items():
+    variants = dict(VARIANTS)
+    if not args.round1_only:
+        variants.update(VARIANTS_R2)
+    for name, defines in variants.items():
         rec = summary[name] = {"defines": defines}
         env = dict(os.environ)
         if defines:
@@ -116,7 +126,10 @@ def main():
         env["KERNELS_JSON"] = f"kernels_{name}.json"
         code, log = run([sys.executable, "tools/bench_kernels.py", str(args.batch)], env, args.dry_run)
         rec["bench_kernels"] = "ok" if code == 0 else log[-300:]
-        for layout in ("channels_last", "nchw"):
+        env["CL_JSON"] = f"cl_shapes_{name}.json"
+        code, log = run([sys.executable, "tools/bench_cl_shapes.py", str(args.batch)], env, args.dry_run)
+        rec["bench_cl_shapes"] = "ok" if code == 0 else log[-300:]
+        for layout in (("channels_last", "nchw") if name in FULL_BENCH else ()):
             code, log = run([sys.executable, "bench.py", "--steps", "30", "--warmup", "5", "--no-cpu", "--no-e2e",
                              "--no-model", "--memory-format", layout, "--batch", str(args.batch)], env, args.dry_run)
             line = next((ln for ln in reversed(log.split("\n")) if ln.startswith("{")), None)
