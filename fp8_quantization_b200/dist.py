@@ -16,6 +16,7 @@ import torch
 import torch.distributed as td
 
 _group_enabled = False
+counters = {"all_reduce": 0}   # collectives issued through this module (bench.py reports them per calibration pass)
 
 
 def init_from_env(backend: str = None) -> bool:
@@ -54,17 +55,20 @@ def rank() -> int:
 
 
 def all_reduce_max(t: torch.Tensor):
+    counters["all_reduce"] += 1
     td.all_reduce(t, op=td.ReduceOp.MAX)
     return t
 
 
 def all_reduce_sum(t: torch.Tensor):
+    counters["all_reduce"] += 1
     td.all_reduce(t, op=td.ReduceOp.SUM)
     return t
 
 
 def all_reduce_mean(t: torch.Tensor):
     """Equal-sized shards: mean over ranks of per-shard means == mean over the global batch."""
+    counters["all_reduce"] += 1
     td.all_reduce(t, op=td.ReduceOp.SUM)
     t.div_(td.get_world_size())
     return t

@@ -44,6 +44,10 @@ FUSE_CALIBRATION = True    # estimate_ranges state of a BN-fused layer: statisti
 STEM_SPACE_TO_DEPTH = True  # channels_last network, NCHW image: stride-2 k x k stem conv over <= 4 channels as a stride-1
                             # conv over the 2x2 space-to-depth image (same sum re-indexed; a shape cuDNN handles well)
 NATIVE_MAX_POOL = True     # channels_last nn.MaxPool2d through this library's kernel (same bits as ATen's)
+CACHE_QUANTIZED_WEIGHTS = False  # keep each layer's quantised weight until the weight (storage / version counter) or its
+                                 # range / format changes, instead of re-quantising it on every forward as the reference
+                                 # does (hijacker.py:88-98).  Same bits either way; off by default because a CUDA graph
+                                 # captured with it on replays the cached tensors and does not see later weight updates.
 BN_EXACT = True            # fused epilogues use ATen-CUDA's eval batch-norm arithmetic bit for bit (bn_mode 1);
                            # False: one-FMA affine form (2 fewer instructions per element, ulp-level differences
                            # from F.batch_norm before quantisation)
@@ -315,6 +319,8 @@ class QuantizationHijacker(QuantizedModule):
                                                     per_channel=self.per_channel_weights,
                                                     qparams=self.weight_qparams,
                                                     range_estim_params=self.weight_range_options)
+        if self.weight_quantizer.range_estimator is not None:   # replicated weights: no collective for their ranges
+            self.weight_quantizer.range_estimator.replicated_input = True
 
     def forward(self, x, offsets=None):
         if self.quantize_input and self._qa:
@@ -787,12 +793,22 @@ class QuantizedModel(nn.Module):
                 continue
             w = w.detach()
             table, C = q.table_for(w)
-            groups.setdefault((q._mbits_host, q.n_bits, q.sign_bits), []).append((m, w, table, C))
+            key = ((m.weight.data_ptr(), m.weight._version), q._table_key)
+            if CACHE_QUANTIZED_WEIGHTS:
+                hit = m.__dict__.get("_wq_cache")
+                if hit is not None and hit[0] == key:
+                    m.__dict__["_wq_stash"] = (key[0], hit[1])
+                    continue
+            groups.setdefault((q._mbits_host, q.n_bits, q.sign_bits), []).append((m, w, table, C, key))
         for (mb, nb, sb), items in groups.items():
-            outs = ops.fake_quant_multi([w for _, w, _, _ in items], [t for _, _, t, _ in items],
-                                        [c for _, _, _, c in items], mb, nb, sb)
-            for (m, _, _, _), out in zip(items, outs):
-                m.__dict__["_wq_stash"] = ((m.weight.data_ptr(), m.weight._version), out)
+            outs = ops.fake_quant_multi([it[1] for it in items], [it[2] for it in items], [it[3] for it in items],
+                                        mb, nb, sb)
+            for (m, _, _, _, key), out in zip(items, outs):
+                m.__dict__["_wq_stash"] = (key[0], out)
+                if CACHE_QUANTIZED_WEIGHTS:
+                    m.__dict__["_wq_cache"] = (key, out)
+                else:
+                    m.__dict__.pop("_wq_cache", None)
 
     def load_state_dict(self, state_dict, strict: bool = True):
         flags = {k: v for k, v in state_dict.items() if k.endswith("_quant_a") or k.endswith("_quant_w")}

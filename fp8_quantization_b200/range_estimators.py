@@ -57,6 +57,13 @@ class RangeEstimatorBase(nn.Module):
         self.register_buffer("current_xmax", None)
         self.per_channel = per_channel
         self.quantizer = quantizer
+        # True for estimators whose input is identical on every rank (weights of a replicated model): their statistics
+        # need no collective under data parallelism.  Set by QuantizationHijacker.
+        self.replicated_input = False
+
+    def _dp(self) -> bool:
+        """Exchange this estimator's batch statistics across ranks?"""
+        return fq_dist.active() and not self.replicated_input
 
     def forward(self, x):
         raise NotImplementedError()
@@ -113,7 +120,7 @@ class _MinMaxEstimator(RangeEstimatorBase):
     def forward(self, x):
         x = x.detach()
         x = ops.dense(x)
-        if fq_dist.active():
+        if self._dp():
             return self._forward_dp(x)
         cmin, cmax, init = self._state(x)
         ops.minmax(x, self.per_channel, cmin, cmax, self.EST_MODE, init, self.momentum)
@@ -147,7 +154,7 @@ class _MinMaxEstimator(RangeEstimatorBase):
         return self.current_xmin, self.current_xmax
 
     def fused_supported(self) -> bool:
-        return not fq_dist.active()
+        return not self._dp()
 
     def fused_estimate_prepare(self, x, quantizer):
         """estimator update + set_quant_range + table in ONE launch; installs the result in ``quantizer``."""
@@ -172,7 +179,7 @@ class _MinMaxEstimator(RangeEstimatorBase):
         assert not self.per_channel
         x = ops.dense(x.detach())
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
-        if fq_dist.active():
+        if self._dp():
             packed = torch.empty(2, dtype=torch.float32, device=x.device)
             if not ops.bn_act_estimate_prepare(x, bn_scale, bn_shift, act_code, bn_mode, packed[:1], packed[1:],
                                                ops.EST_CURRENT, False, self.momentum):
@@ -245,7 +252,7 @@ class FP_MSE_Estimator(RangeEstimatorBase):
             packed = torch.empty(2 * C, dtype=torch.float32, device=x.device)
             ops.minmax(x, self.per_channel, packed[:C], packed[C:], ops.EST_CURRENT, False)
             absmax = torch.max(packed[:C].abs(), packed[C:].abs())
-            if fq_dist.active():
+            if self._dp():
                 fq_dist.all_reduce_max(absmax)
             # The reference builds the grid on the host from .item() values with torch.linspace; do the
             # same (one D2H copy of C floats, once per estimator) so the grid is bit-identical.
@@ -269,12 +276,12 @@ class FP_MSE_Estimator(RangeEstimatorBase):
             # one decision for the GLOBAL batch: ranks whose shards disagree on "any negative value" would otherwise
             # average MSE tables of different formats
             neg = torch.any(x < 0).to(torch.float32).reshape(1)
-            if fq_dist.active():
+            if self._dp():
                 fq_dist.all_reduce_max(neg)
             sign_bits = int(neg.item())
         if qz.allow_unsigned and sign_bits == 0:
             qz.sign_bits = 0  # what set_quant_range(-0.0 * maxval, maxval) does in the reference loop (:341-342)
-        if fq_dist.active():
+        if self._dp():
             inc = torch.zeros_like(mses)
             ops.mse_grid(x, self.per_channel, grid, mbit_list, qz.n_bits, qz.sign_bits, inc)
             fq_dist.all_reduce_mean(inc)
@@ -368,7 +375,7 @@ class LineSearchEstimator(RangeEstimatorBase):
         if self.loss_array is None:
             mm = torch.empty(2, dtype=torch.float32, device=data.device)
             ops.minmax(data, False, mm[:1], mm[1:], ops.EST_CURRENT, False)
-            if fq_dist.active():      # global-batch extremes, so that every rank searches the same candidates
+            if self._dp():            # global-batch extremes, so that every rank searches the same candidates
                 mm[:1].neg_()
                 fq_dist.all_reduce_max(mm)
                 mm[:1].neg_()

@@ -92,3 +92,43 @@ def test_ab_build_options_tool_hash_leg_on_the_simulation(simdev):
         if "/nchw/" in k and len(v) == 64 and len(h[k.replace("/nchw/", "/channels_last/")]) == 64:
             assert h[k.replace("/nchw/", "/channels_last/")] == v, k
     assert "default" in ab.VARIANTS and ab.VARIANTS["default"] == []
+
+
+def test_extra_legs_plumbing_on_the_simulation(simdev):
+    """The round-2 legs of bench.py that can run without a GPU: the calibration leg's accounting, the replay of the
+    reference's eager op sequence over a recorded plan (its outputs must be the product's, up to the two libm's), the
+    config-3 recorder on MobileNetV2 (launch / element accounting of SURVEY section 8a)."""
+    from fp8_quantization_b200 import dist as fq_dist
+    from fp8_quantization_b200 import ops, workloads
+
+    bench = _bench()
+    torch.manual_seed(10)
+    model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).eval()
+    x = torch.randn(1, 3, 224, 224)
+    workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+    model.fix_ranges()
+    cal = bench.calibration_leg(model, x, workloads, fq_dist, 1, reps=1)
+    assert cal["allreduces"] == 0 and cal["ms"] > 0 and cal["batches"] == 1
+    assert not any(m.estimating() for m in model.modules() if hasattr(m, "estimating"))   # ranges fixed again
+    plan, st = bench.record_hot_path(model, x, ops)
+    assert st["launches"] == 23
+    step = bench.leg_reference_gpu_eager(plan, st, torch.device("cpu"), steps=0)
+    with torch.no_grad():
+        ref_outs = step()
+        ours = bench.run_plan(plan, ops)
+    checked = 0
+    for (name, _, _), a, b in zip(plan, ref_outs, ours):
+        for u, v in zip(a if isinstance(a, (list, tuple)) else [a], b if isinstance(b, (list, tuple)) else [b]):
+            bad = ((u - v).abs() > 1e-5 * v.abs().clamp_min(1e-3)).float().mean().item()
+            assert bad < 2e-2, (name, bad)     # tie flips from ulp-level batch-norm / scale-table differences only
+            checked += 1
+    assert checked == 21 + 22
+    # config 3 accounting: 53 weight tensors (2 multi-tensor launches), 6,896,776 activation elements per image at 224^2
+    m3 = workloads.mobilenetv2_quantized(**workloads.readme_quant_params(4)).eval()
+    x3 = torch.randn(1, 3, 224, 224)
+    workloads.pass_data_for_range_estimation([x3], m3, True, True, 1)
+    m3.fix_ranges()
+    _, st3 = bench.record_hot_path(m3, x3, ops)
+    assert st3["weight_launches"] == 1 and st3["weight_elems"] == 3_469_760   # one call = 2 kernel launches (48 + 5 tensors)
+    assert st3["elems"] - st3["weight_elems"] == 6_896_776
+    assert st3["launches"] == 1 + 42 + 10 + 2

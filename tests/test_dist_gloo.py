@@ -181,6 +181,16 @@ def _sim_worker(rank, world, port, q):
     report["mse"] = (bool(torch.equal(e_dp.search_grid, e_sp.search_grid))
                      and bool(np.allclose(e_dp.mses.numpy(), e_sp.mses.numpy(), rtol=1e-5, atol=1e-12))
                      and q_dp._mbits_host == q_sp._mbits_host and bool(torch.equal(mx_dp, mx_sp)))
+    # bench.py's data-parallel legs (the only multi-GPU code the driver executes): calibration timing + accounting,
+    # and dp_parity -- all-gathered ranges bit-equal across ranks, rank 0 re-calibrating on the gathered batch
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cal = bench.calibration_leg(dp, local, workloads, fq_dist, world, reps=1)
+    par = bench.dp_parity_leg(dp, local, lambda fmt: build(), "nchw", fq, workloads, fq_dist, world, rank)
+    report["bench_calibration"] = cal
+    report["bench_dp_parity"] = par
     fq_dist.barrier()
     q.put((rank, report))
     td.destroy_process_group()
@@ -204,3 +214,10 @@ def test_world_size_2_gloo_sharded_calibration_through_the_simulated_kernels(bui
         # 21 weight + 29 activation quantisers (the tied one is shared); measured here: all 50 bit-identical
         assert total == 50 and exact + close == total and exact >= 40, r["ranges"]
         assert r["metrics"] and r["ranks_agree"] and r["mse"], r
+        cal, par = r["bench_calibration"], r["bench_dp_parity"]
+        assert cal["allreduces"] == 29 and cal["ms"] > 0 and cal["us_per_allreduce"] is not None, cal
+        assert par["ranges"] == 50 and par["bit_equal_across_ranks"], par
+        if rank == 0:
+            vs = par["vs_single_process_on_gathered_batch"]
+            assert vs["weights_bit_equal"] and vs["first_layer_bit_equal"] and vs["weight_ranges"] == 21, vs
+            assert vs["all_bit_equal"] >= 40 and vs["max_rel_diff"] < 2e-2 and vs["global_batch"] == 4, vs

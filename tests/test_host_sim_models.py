@@ -583,3 +583,39 @@ def test_functional_entry_point_quantize_to_fp8_ste_MM(simdev):
     x2 = x.detach().clone().requires_grad_(True)
     qz(x2).sum().backward()
     assert torch.equal(x.grad, x2.grad) and torch.equal(mv.grad, qz.maxval.grad)
+
+
+def test_quantised_weight_cache_is_keyed_on_weight_and_range(simdev):
+    """modules.CACHE_QUANTIZED_WEIGHTS: the second forward launches no weight quantiser, gives the same bits, and an
+    in-place weight update or a new range invalidates the entry (optional, version-keyed)."""
+    from torchvision.models import resnet18
+
+    from fp8_quantization_b200 import modules, ops, workloads
+
+    torch.manual_seed(3)
+    model = workloads.QuantizedResNet(resnet18(), **_qparams(5)).eval()
+    x = torch.randn(1, 3, 64, 64)
+    workloads.pass_data_for_range_estimation([x], model, True, True, 1)
+    model.fix_ranges()
+    with torch.no_grad():
+        ref = model(x)
+        n0 = ops.launch_count()
+        model(x)
+        uncached = ops.launch_count() - n0
+        modules.CACHE_QUANTIZED_WEIGHTS = True
+        try:
+            y1 = model(x)                      # fills the cache
+            n0 = ops.launch_count()
+            y2 = model(x)
+            cached = ops.launch_count() - n0
+            assert torch.equal(y1, ref) and torch.equal(y2, ref)
+            assert cached == uncached - 1      # the one multi-tensor weight launch is gone
+            model.fc.weight.mul_(0.5)          # in-place update bumps the version counter
+            n0 = ops.launch_count()
+            y3 = model(x)
+            assert ops.launch_count() - n0 == uncached          # one (single-tensor) weight launch is back
+            assert not torch.equal(y3, ref)
+            modules.CACHE_QUANTIZED_WEIGHTS = False
+            assert torch.equal(model(x), y3)   # same bits as re-quantising every forward
+        finally:
+            modules.CACHE_QUANTIZED_WEIGHTS = False

@@ -17,9 +17,13 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
+PREBUILT = os.path.join(ROOT, "build_variants")
+sys.path.insert(0, ROOT)
+from fp8_quantization_b200 import build as _build  # noqa: E402
 VARIANTS = {"default": [], "round1": ["FP8FQ_FOLD_ACT=0", "FP8FQ_FULL_TILE=0"]}
 # round 2 (FOLD_ACT and FULL_TILE became the defaults after the first A/B, profiles/ab_build_options_r02a.json): operands
 # of the code select pinned in vector registers, two-wide fp32 arithmetic, the predicate-free tile body for the
@@ -96,7 +100,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--dry-run", action="store_true")
-    ap.add_argument("--round1-only", action="store_true", help="only the four variants of round 1")
+    ap.add_argument("--round1-only", action="store_true", help="only the default build and the round-1 arithmetic")
+    ap.add_argument("--build-only", action="store_true", help="cross-compile every variant into build_variants/ and stop")
+    ap.add_argument("--only", default="", help="comma-separated variant names to run (default: all)")
     ap.add_argument("--hash-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.hash_leg:
@@ -107,17 +113,29 @@ def main():
     variants = dict(VARIANTS)
     if not args.round1_only:
         variants.update(VARIANTS_R2)
+    if args.only:
+        variants = {k: v for k, v in variants.items() if k in set(args.only.split(",")) | {"default"}}
     for name, defines in variants.items():
         rec = summary[name] = {"defines": defines}
         env = dict(os.environ)
         if defines:
-            lib = os.path.join(OUT, f"libfp8fq_{name}.so")
-            code, log = run([sys.executable, "-m", "fp8_quantization_b200.build"] + [f"-D{d}" for d in defines]
-                            + ["--out", lib], env, args.dry_run)
-            if code != 0:
-                rec["build_error"] = log[-500:]
-                continue
+            # variants cross-compiled beforehand (python tools/ab_build_options.py --build-only, in the build container;
+            # build_variants/*.so travel with the snapshot) are used as they are, if newer than the sources
+            lib = os.path.join(PREBUILT, f"libfp8fq_{name}.so")
+            if not (os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(d) for d in _build.DEPS)):
+                # (not into gpurun_out/: only 64 MiB of it travel back from the GPU box)
+                where = PREBUILT if args.build_only else os.path.join(tempfile.gettempdir(), "fp8fq_variants")
+                os.makedirs(where, exist_ok=True)
+                lib = os.path.join(where, f"libfp8fq_{name}.so")
+                code, log = run([sys.executable, "-m", "fp8_quantization_b200.build"] + [f"-D{d}" for d in defines]
+                                + ["--out", lib], env, args.dry_run)
+                if code != 0:
+                    rec["build_error"] = log[-500:]
+                    continue
+            rec["lib"] = os.path.relpath(lib, ROOT)
             env["FP8FQ_LIB"] = lib
+        if args.build_only:
+            continue
         code, log = run([sys.executable, os.path.abspath(__file__), "--hash-leg"], env, args.dry_run)
         line = next((ln for ln in log.split("\n") if ln.startswith("HASHES ")), None)
         rec["hashes"] = json.loads(line[7:]) if line else None
@@ -131,7 +149,7 @@ def main():
         rec["bench_cl_shapes"] = "ok" if code == 0 else log[-300:]
         for layout in (("channels_last", "nchw") if name in FULL_BENCH else ()):
             code, log = run([sys.executable, "bench.py", "--steps", "30", "--warmup", "5", "--no-cpu", "--no-e2e",
-                             "--no-model", "--memory-format", layout, "--batch", str(args.batch)], env, args.dry_run)
+                             "--no-model", "--no-configs", "--memory-format", layout, "--batch", str(args.batch)], env, args.dry_run)
             line = next((ln for ln in reversed(log.split("\n")) if ln.startswith("{")), None)
             try:
                 d = json.loads(line)
@@ -140,6 +158,9 @@ def main():
                                           "largest_launch_frac": d["roofline"]["largest_launch"]["frac"]}
             except (TypeError, ValueError, KeyError):
                 rec[f"bench_{layout}"] = {"error": log[-300:]}
+    if args.build_only:
+        print(json.dumps(summary, indent=1))
+        return
     base = summary["default"].get("hashes")
     for name, rec in summary.items():
         h = rec.pop("hashes", None)
