@@ -70,6 +70,8 @@ SIGNATURES["fp8fq_space_to_depth2_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_l, _c_l, _
 
 SIGNATURES["fp8fq_max_pool2d_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_l, _c_l, _c_l, _c_l, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p])
 
+SIGNATURES["fp8fq_u8_normalize_nchw_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_p])
+
 _lib = None
 
 

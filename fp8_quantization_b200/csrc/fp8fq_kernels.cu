@@ -1346,6 +1346,39 @@ __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const PoolArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// uint8 image -> normalised fp32 image, NCHW: the ToTensor + Normalize steps of the reference's input pipeline
+// (utils/imagenet_dataloaders.py:66-81: x / 255, then (x - mean[c]) / std[c]) applied on the device, so that the host
+// link carries 1 byte per pixel instead of 4.  The three arithmetic steps are tabulated per (channel, byte value) by
+// the caller with the reference's own fp32 operations (256 entries per channel), which makes the result bit-identical
+// to torchvision's by construction.  One thread per 16 pixels (one 128-bit load, four 128-bit stores); the table is
+// staged in shared memory.  HBM-bound: 5 B / pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kU8MaxC = 8;
+__global__ void __launch_bounds__(256) u8_normalize_kernel(const uint8_t* __restrict__ x, const float* __restrict__ lut,
+                                                           float* __restrict__ y, int64_t n, int C, int64_t hw, int vec_ok) {
+  __shared__ float s_lut[kU8MaxC * 256];
+  for (int i = threadIdx.x; i < C * 256; i += blockDim.x) s_lut[i] = __ldg(lut + i);
+  __syncthreads();
+  if (vec_ok) {   // hw % 16 == 0 and 16-byte aligned pointers: the 16 pixels of a thread share a channel
+    const int64_t ngroups = n >> 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = g << 4;
+      const int c = (int)((i / hw) % C);
+      const float* t = s_lut + c * 256;
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x + i));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float4* o = reinterpret_cast<float4*>(y + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_float4(t[w[j] & 0xffu], t[(w[j] >> 8) & 0xffu], t[(w[j] >> 16) & 0xffu], t[w[j] >> 24]);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      y[i] = s_lut[(int)((i / hw) % C) * 256 + x[i]];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // INT uniform quantisers: set_quant_range (uniform_quantizers.py:224-246, 303-314) + channel tables, one CTA
 // ------------------------------------------------------------------------------------------------
 __global__ void uq_prepare_kernel(const float* __restrict__ xmin, const float* __restrict__ xmax, int64_t C,
@@ -1940,6 +1973,24 @@ int fp8fq_max_pool2d_nhwc_f32(const float* x, float* y, int64_t N, int64_t H, in
   if (grid > 0x7fffffffll) return FP8FQ_ERR_UNSUPPORTED;
   PoolArgs a{x, y, nvec, (int)H, (int)W, (int)(C / 4), (int)Ho, (int)Wo, kh, kw, sh, sw, ph, pw};
   launch_plain(maxpool_nhwc_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, a);
+  return launch_status();
+}
+
+int fp8fq_u8_normalize_nchw_f32(const uint8_t* x, const float* lut, float* y, int64_t N, int64_t C, int64_t HW,
+                                void* stream) {
+  if (N < 0 || C < 1 || HW < 1) return FP8FQ_ERR_BAD_ARG;
+  if (C > kU8MaxC) return FP8FQ_ERR_UNSUPPORTED;
+  const int64_t n = N * C * HW;
+  if (n == 0) return FP8FQ_OK;
+  if (x == nullptr || lut == nullptr || y == nullptr) return FP8FQ_ERR_BAD_ARG;
+  if (!aligned4(lut) || !aligned4(y)) return FP8FQ_ERR_ALIGNMENT;
+  const int vec_ok = (HW % 16 == 0) && aligned16(x) && aligned16(y) ? 1 : 0;
+  const int64_t work = vec_ok ? (n >> 4) : n;
+  int64_t grid = (work + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  launch_plain(u8_normalize_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, x, lut, y, n, (int)C, HW, vec_ok);
   return launch_status();
 }
 

@@ -372,6 +372,37 @@ def space_to_depth2(x: torch.Tensor, pad: int, hs: int, ws: int) -> torch.Tensor
     return y
 
 
+def normalize_lut(mean, std, device) -> torch.Tensor:
+    """[C, 256] table of torchvision's ToTensor + Normalize for every byte value, evaluated with the same fp32 tensor
+    operations (utils/imagenet_dataloaders.py:66-81: ``img.to(float32).div(255)``, then ``sub_(mean).div_(std)``)."""
+    v = torch.arange(256, dtype=torch.float32).div(255).repeat(len(mean), 1)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(-1, 1)
+    sd = torch.as_tensor(std, dtype=torch.float32).view(-1, 1)
+    return v.sub_(m).div_(sd).contiguous().to(device)
+
+
+def normalize_u8(x: torch.Tensor, lut: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """uint8 NCHW image batch -> normalised fp32 NCHW batch through ``lut`` (normalize_lut): one HBM-bound pass,
+    bit-identical to ToTensor + Normalize (fp8fq_u8_normalize_nchw_f32)."""
+    if not isinstance(x, torch.Tensor) or x.dtype != torch.uint8 or x.dim() != 4 or not x.is_contiguous():
+        raise Fp8fqError("normalize_u8: x must be a contiguous uint8 [N, C, H, W] tensor")
+    if not on_device(x):
+        raise Fp8fqError(f"normalize_u8: x must be a CUDA tensor (this engine has no CPU path); got device {x.device}")
+    N, C, H, W = x.shape
+    _require(lut, "lut")
+    if lut.numel() != C * 256:
+        raise Fp8fqError(f"normalize_u8: lut must be [C, 256] = [{C}, 256]")
+    if out is None:
+        out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    else:
+        _require(out, "out")
+        if tuple(out.shape) != (N, C, H, W) or not out.is_contiguous():
+            raise Fp8fqError("normalize_u8: out must be a contiguous fp32 tensor of x's shape")
+    check(lib().fp8fq_u8_normalize_nchw_f32(x.data_ptr(), lut.data_ptr(), out.data_ptr(), N, C, H * W, _stream()),
+          "fp8fq_u8_normalize_nchw_f32")
+    return out
+
+
 def max_pool2d_channels_last(x: torch.Tensor, kernel, stride, padding) -> torch.Tensor:
     """F.max_pool2d (floor mode, dilation 1) of a channels_last [N, C, H, W] tensor, C % 4 == 0, in one HBM-bound
     pass (fp8fq_max_pool2d_nhwc_f32); same bits as ATen, NaN propagation included."""

@@ -199,6 +199,15 @@ int fp8fq_uniform_quant_f32(const float* x, float* y, const float* table, int64_
 int fp8fq_space_to_depth2_nhwc_f32(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t pad,
                                    int64_t Hs, int64_t Ws, void* stream);
 
+/* Data format on the caller's side of the path: the ToTensor + Normalize steps of the reference's input pipeline
+ * (utils/imagenet_dataloaders.py:66-81: x / 255, then (x - mean[c]) / std[c]) for a uint8 NCHW image batch
+ * x [N, C <= 8, HW] -> y fp32 [N, C, HW], so that images cross the host link as 1 byte per pixel.  lut [C, 256] (device)
+ * holds the result for every (channel, byte value), computed by the caller with the reference's own fp32 operations:
+ * y[n, c, p] = lut[c, x[n, c, p]] is then bit-identical to torchvision's output.  128-bit accesses when HW % 16 == 0
+ * and x, y are 16-byte aligned (scalar path otherwise). */
+int fp8fq_u8_normalize_nchw_f32(const uint8_t* x, const float* lut, float* y, int64_t N, int64_t C, int64_t HW,
+                                void* stream);
+
 /* Replaces (for channel-innermost activations): the nn.MaxPool2d that consumes the stem's quantised activation
  * (models/resnet_quantized.py:73-78 keeps torchvision's module; ATen: max_pool_forward_nhwc).  x [N, H, W, C] ->
  * y [N, Ho, Wo, C], Ho = (H + 2 ph - kh) / sh + 1 (floor mode, dilation 1, no indices); C % 4 == 0, 16-byte aligned.

@@ -57,6 +57,9 @@ struct alignas(16) float4 {
 struct alignas(16) int4 {
   int x, y, z, w;
 };
+struct alignas(16) uint4 {
+  unsigned int x, y, z, w;
+};
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
