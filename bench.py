@@ -1074,6 +1074,18 @@ def main():
                     raise RuntimeError("e2e logits differ from the device-resident forward")
                 static_x = gf.static_in
                 del gf
+                # the same loop fed with uint8 images (what an image decoder produces): ToTensor + Normalize of the
+                # reference's input pipeline run on the device inside the graph, 1 byte per pixel crosses the host link
+                x_u8 = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8, device=dev)
+                gfu = workloads.GraphedForward(model, x_u8, preprocess=workloads.U8Normalize(device=dev))
+                h_u8 = x_u8.cpu().pin_memory()
+                gfu.run_pipelined([h_u8] * 2, h_log[:2])
+                barrier()
+                t0 = time.perf_counter()
+                gfu.run_pipelined([h_u8] * iters, h_log)
+                barrier()
+                dt_u8 = time.perf_counter() - t0
+                del gfu, x_u8, h_u8
                 # the same forward with the quantised weights cached (modules.CACHE_QUANTIZED_WEIGHTS)
                 modules.CACHE_QUANTIZED_WEIGHTS = True
                 try:
@@ -1102,10 +1114,10 @@ def main():
                 barrier()
                 mms_other = m0.elapsed_time(m1) / iters
                 del gf2, m2
-            vals = torch.tensor([mms, dt, mms_other, mms_cached], device=dev)
+            vals = torch.tensor([mms, dt, mms_other, mms_cached, dt_u8], device=dev)
             if world > 1:
                 fq_dist.all_reduce_max(vals)
-            mms, dt, mms_other, mms_cached = vals.tolist()
+            mms, dt, mms_other, mms_cached, dt_u8 = vals.tolist()
             by_layout = {args.memory_format: B * world / (mms * 1e-3), other_fmt: B * world / (mms_other * 1e-3)}
             model_info = {"resnet18_quantized_img_per_s": B * world / (mms * 1e-3), "ms_per_forward": mms,
                           "memory_format": args.memory_format,
@@ -1118,6 +1130,12 @@ def main():
                           "other_layout": {"memory_format": other_fmt, "ms_per_forward": mms_other,
                                            "img_per_s": B * world / (mms_other * 1e-3)},
                           "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
+                          "e2e_u8": {"img_per_s": B * world * iters / dt_u8, "h2d_bytes_per_step": B * 3 * 224 * 224,
+                                     "d2h_bytes_per_step": B * 1000 * 4,
+                                     "note": "uint8 NCHW images from pinned host memory; ToTensor + Normalize "
+                                             "(utils/imagenet_dataloaders.py:66-81) on the device inside the graph "
+                                             "(workloads.U8Normalize, bit-identical to torchvision): 4x fewer host-link "
+                                             "bytes than feeding normalised fp32 images"},
                           "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
                           "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
                                       "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "

@@ -39,7 +39,8 @@ constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
 constexpr int kMaxK = (1 << kMaxE) - 1;
 
 enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
-enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, BAND_SHIFT = 8 };  // flags = FLAG_* | (band << BAND_SHIFT)
+// flags = FLAG_* | (band << BAND_SHIFT)
+enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8, BAND_SHIFT = 8 };
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -281,6 +282,18 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
     bool rsnan = false;
     for (int k = 1; k <= K; ++k) rsnan = rsnan || !(sr[2 * k + 1] == sr[2 * k + 1]);
     if (rsnan) flags |= FLAG_RSNAN;
+    // FLAG_SDOUBLE: the scales the reference's powf produced are EXACT doublings of each other, s_k = s_1 * 2^(k-1) bit
+    // for bit (and therefore 1/s_k = (1/s_1) * 2^-(k-1)), all normal -- the usual case (the exponents (k - M) - bias of
+    // neighbouring codes differ by exactly 1 unless the subtraction rounds differently across a binade of |y|: measured
+    // 87 % of random ranges for E3M4, 96 % for E4M3).  The element path then derives (s, 1/s) from the exponent code by
+    // integer arithmetic on the bit patterns instead of loading them (lookup_scale_fast).
+    bool dbl = K >= 2 && !(flags & FLAG_IRREGULAR) && !rsnan;
+    for (int k = 1; k <= K && dbl; ++k) {
+      const uint32_t sh = (uint32_t)(k - 1) << 23;
+      dbl = is_normal_pos(sr[2 * k]) && is_normal_pos(sr[2 * k + 1]) && f2u(sr[2 * k]) == f2u(sr[2]) + sh &&
+            f2u(sr[2 * k + 1]) + sh == f2u(sr[3]);
+    }
+    if (dbl) flags |= FLAG_SDOUBLE;
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);
@@ -314,6 +327,22 @@ FQ_HD int lookup_code_fast(float a, uint32_t ref, uint32_t band, int K, bool* am
   int e = q + 2;
   e = e < 1 ? 1 : e;
   return e > K ? K : e;
+}
+
+// Scale pair of the element's exponent code for FLAG_SDOUBLE tables, by integer arithmetic alone: with
+// i = bits(|xc|) - ref, the code is e = clamp(floor(i / 2^23) + 2, 1, K) (lookup_code_fast), so
+// t = (e - 1) << 23 = clamp((i & ~0x7fffff) + 2^23, 0, (K - 1) << 23), s = s_1 * 2^(e-1) has the bits s1b + t and
+// 1/s the bits r1b - t.  *ambiguous as in lookup_code_fast.  Returns t.
+FQ_HD uint32_t lookup_scale_fast(float a, uint32_t ref, uint32_t band, uint32_t tmax, uint32_t s1b, uint32_t r1b,
+                                 float* s, float* rs, bool* ambiguous) {
+  const int32_t i = (int32_t)(f2u(a) - ref);
+  *ambiguous = (uint32_t)(i & 0x7fffff) <= band;
+  int32_t t = (int32_t)((uint32_t)i & 0xff800000u) + (1 << 23);   // floor(i / 2^23) * 2^23 + 2^23 (two's complement)
+  t = t < 0 ? 0 : t;
+  t = t > (int32_t)tmax ? (int32_t)tmax : t;
+  *s = u2f(s1b + (uint32_t)t);
+  *rs = u2f(r1b - (uint32_t)t);
+  return (uint32_t)t;
 }
 
 // ---- INT uniform quantisers (quantization/quantizers/uniform_quantizers.py:107-164) ------------------------

@@ -268,6 +268,8 @@ struct ElemCtx {
   uint32_t base;
   bool irregular;
   uint32_t ref, band;   // KMODE 1: exponent-arithmetic fast path (lookup_code_fast)
+  bool dbl;             // KMODE 1: FLAG_SDOUBLE table -- (s, 1/s) by integer arithmetic (lookup_scale_fast), no load
+  uint32_t s1b, r1b, tmax;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -399,11 +401,24 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
     // (band + 1) / 2^23 ambiguous band.  c.stab is the global table (stream/row kernels, L1-resident) or a
     // shared-memory copy (MSE kernel), hence generic-address loads.
     bool amb = false;
+    if (c.dbl) {
+      // exact-doubling scale table (the usual case): the scale pair comes out of the same integer arithmetic as the
+      // code -- no per-element load at all (ncu, round 2: the per-element 64-bit gathers put the L1 data pipe of the
+      // K > 3 kernels at 64-69 % next to 74 % issue utilisation)
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      bool ak;
-      e[k] = lookup_code_fast(fabsf(xc[k]), c.ref, c.band, c.K, &ak);
-      amb |= ak;
+      for (int k = 0; k < N; ++k) {
+        bool ak;
+        const uint32_t t = lookup_scale_fast(fabsf(xc[k]), c.ref, c.band, c.tmax, c.s1b, c.r1b, &s[k], &rs[k], &ak);
+        e[k] = (int)(t >> 23) + 1;
+        amb |= ak;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        bool ak;
+        e[k] = lookup_code_fast(fabsf(xc[k]), c.ref, c.band, c.K, &ak);
+        amb |= ak;
+      }
     }
     if (amb) {
 #pragma unroll
@@ -413,6 +428,9 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
       }
     }
     const float2* sr = reinterpret_cast<const float2*>(c.stab + off_sr(c.K));
+    if (c.dbl && !amb) {
+      // (s, 1/s) already in registers
+    } else
 #ifndef FP8FQ_HOST_SIM
     if (STAB_SHARED) {  // the table is a shared-memory copy: ld.shared instead of a generic-address load
       const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sr);
@@ -498,6 +516,7 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.rt.t3 = ld(tab + U_SAT);
     c.rt.s2 = c.rt.s3 = c.rt.r2 = c.rt.r3 = 0.0f;
     c.K = 1; c.stab = tab; c.base = 0; c.irregular = false; c.ref = 0; c.band = 0;
+    c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
     return;
   }
   c.hi = ld(tab + H_HI);
@@ -518,12 +537,17 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.irregular = false;
     c.ref = 0;
     c.band = 0;
+    c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
   } else {
     const uint32_t fl = f2u(ld(tab + H_FLAGS));
     c.base = f2u(ld(tab + H_BASE));
     c.irregular = (fl & FLAG_IRREGULAR) != 0;
     c.ref = f2u(ld(tab + H_REF));
     c.band = fl >> BAND_SHIFT;
+    c.dbl = (fl & FLAG_SDOUBLE) != 0;
+    c.s1b = f2u(ld(tab + off_sr(K) + 2));
+    c.r1b = f2u(ld(tab + off_sr(K) + 3));
+    c.tmax = (uint32_t)(K - 1) << 23;
   }
 }
 template <int KMODE>
@@ -1530,6 +1554,28 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   int tpc = tpc_env ? tpc_env : ((kHasBn && KMODE == 0) ? 4 : 1);
   while (tpc > 1 && !tpc_env && ntiles / tpc < (int64_t)sm_count() * 12) tpc >>= 1;
   int64_t grid = (ntiles + tpc - 1) / tpc;
+  // FP8FQ_WAVE_GRID=1 (experiment): round the grid up to a whole number of waves (SMs x resident CTAs of this
+  // instantiation), so that the last wave is as full as the others; the kernel's tile loop strides by the grid size.
+  static const bool wave_env = [] {
+    const char* e = getenv("FP8FQ_WAVE_GRID");
+    return e && e[0] == '1';
+  }();
+#ifndef FP8FQ_HOST_SIM
+  if (wave_env) {
+    static const int resident = [] {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, kThreads, 0) !=
+          cudaSuccess || nb < 1)
+        nb = StreamMinBlocks<KMODE, PRE>::value;
+      return nb;
+    }();
+    const int64_t wave = (int64_t)sm_count() * resident;
+    if (grid > wave) {
+      const int64_t g2 = ((grid + wave - 1) / wave) * wave;
+      if (g2 <= ntiles) grid = g2;
+    }
+  }
+#endif
   if (grid > 0x7fffffffll) grid = 0x7fffffffll;  // the kernel strides over the remaining tiles
   launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, dim3((unsigned)grid), dim3(threads), 0, st, a);
   return launch_status();

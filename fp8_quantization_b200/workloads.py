@@ -495,6 +495,27 @@ def compute_quant_error_empirical(sample, sample_y=None, n_bits=8, num_candidate
 # ---------------------------------------------------------------------------------------------------
 # validate forward as one CUDA graph
 # ---------------------------------------------------------------------------------------------------
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # utils/imagenet_dataloaders.py:66
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class U8Normalize:
+    """ToTensor + Normalize of the reference's input pipeline (utils/imagenet_dataloaders.py:66-81) for a uint8 NCHW
+    image batch that is already on the device: one HBM-bound launch through a per-(channel, byte value) table built with
+    the reference's own fp32 operations -- bit-identical to torchvision, and the images cross the host link as 1 byte
+    per pixel instead of 4.  Use as ``GraphedForward(model, example_u8, preprocess=U8Normalize(device=...))``."""
+
+    def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None):
+        from . import ops
+
+        self.lut = ops.normalize_lut(mean, std, device if device is not None else ops.default_device())
+
+    def __call__(self, x_u8):
+        from . import ops
+
+        return ops.normalize_u8(x_u8, self.lut)
+
+
 class GraphedForward:
     """``model(x)`` for one input shape captured in a CUDA graph and replayed.
 
@@ -508,12 +529,19 @@ class GraphedForward:
     (storage, not values -- in-place updates are seen).  Call :meth:`capture` again after changing any of that.
     """
 
-    def __init__(self, model, example: torch.Tensor, warmup: int = 3):
+    def __init__(self, model, example: torch.Tensor, warmup: int = 3, preprocess=None):
+        """``preprocess``: an optional device-side callable applied to the input inside the graph (e.g. U8Normalize for
+        uint8 images); ``example`` then has the dtype / shape of what the callable takes."""
         self.model = model
+        self.preprocess = preprocess
         self.graph = None
         self.static_in = None
         self.static_out = None
         self.capture(example, warmup)
+
+    def _forward(self):
+        x = self.static_in if self.preprocess is None else self.preprocess(self.static_in)
+        return self.model(x)
 
     def _check_state(self):
         from .quantization_manager import QuantizationManager
@@ -535,11 +563,11 @@ class GraphedForward:
         side.wait_stream(torch.cuda.current_stream(example.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):  # cuDNN algorithm selection, table builds, batch-norm packing
-                self.model(self.static_in)
+                self._forward()
         torch.cuda.current_stream(example.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_out = self.model(self.static_in)
+            self.static_out = self._forward()
         return self
 
     def replay(self):

@@ -61,3 +61,37 @@ def test_functional_entry_point_quantize_to_fp8_ste_MM(M, sb, pc):
     assert torch.equal(bits(y), bits(qz(x)))
     y_ref = O.fake_quant(x, 8, mv, mb, sb)
     assert bool(((bits(y) == bits(y_ref)) | (torch.isnan(y) & torch.isnan(y_ref))).all())
+
+
+def test_uint8_normalisation_on_the_gpu_and_in_the_graph():
+    """ops.normalize_u8 == torchvision's ToTensor + Normalize bit for bit on the device, and GraphedForward with the
+    uint8 pre-processing inside the graph gives the logits of the fp32-fed forward on the same images."""
+    import torch
+    from fp8_quantization_b200 import workloads
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randint(0, 256, (8, 3, 224, 224), dtype=torch.uint8, device=dev, generator=g)
+    norm = workloads.U8Normalize(device=dev)
+    want = x.to(torch.float32).div(255)
+    want.sub_(torch.tensor(workloads.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)).div_(
+        torch.tensor(workloads.IMAGENET_STD, device=dev).view(1, 3, 1, 1))
+    got = norm(x)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    odd = torch.randint(0, 256, (2, 3, 7, 9), dtype=torch.uint8, device=dev, generator=g)     # scalar path
+    w2 = odd.to(torch.float32).div(255)
+    w2.sub_(torch.tensor(workloads.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)).div_(
+        torch.tensor(workloads.IMAGENET_STD, device=dev).view(1, 3, 1, 1))
+    assert torch.equal(norm(odd).view(torch.int32), w2.view(torch.int32))
+    torch.manual_seed(10)
+    model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(dev).eval().to(memory_format=torch.channels_last)
+    workloads.pass_data_for_range_estimation([want], model, True, True, 1)
+    model.fix_ranges()
+    with torch.no_grad():
+        ref = model(want)
+    gf = workloads.GraphedForward(model, x, preprocess=norm)
+    assert torch.equal(gf(x), ref)
+    host = x.cpu().pin_memory()
+    out = torch.empty(3, 8, 1000).pin_memory()
+    gf.run_pipelined([host] * 3, out)
+    assert torch.equal(out[0], ref.cpu()) and torch.equal(out[2], ref.cpu())

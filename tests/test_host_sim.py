@@ -860,3 +860,46 @@ def test_simulated_kernels_against_the_real_reference_golden_vectors(sim):
         total += int(ok.sum())
         mism += int(diff.sum())
     assert mism / total < 1e-4, (mism, total)
+
+
+@pytest.mark.parametrize("M,sb", [(4, 1), (3, 1), (2, 1), (4, 0), (1, 1)])
+def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(sim, ref, M, sb):
+    """K > 3 formats: when the prologue finds the reference's scales to be exact doublings of each other (FLAG_SDOUBLE,
+    the usual case), the element path derives (s, 1/s) from the exponent code by integer arithmetic instead of loading
+    them (lookup_scale_fast); otherwise it keeps the table look-up.  Both kinds of table must occur over a sweep of
+    ranges and both must reproduce the direct formula bit for bit -- values at every code boundary, rounding ties, +-0,
+    denormals, NaN / inf, per tensor (stream kernel) and per channel (row kernel)."""
+    rng = np.random.default_rng(40 + M)
+    FLAG_SDOUBLE, H_FLAGS = 8, 4
+    kinds = {True: 0, False: 0}
+    mvs = np.exp(rng.uniform(np.log(0.02), np.log(60.0), 48)).astype(np.float32)
+    n = 4096 + 64
+    for mvv in mvs:
+        mv = np.array([mvv], np.float32)
+        tab = table_for(sim, mv, M, 8, sb)
+        dbl = bool(int(tab[H_FLAGS:H_FLAGS + 1].view(np.uint32)[0]) & FLAG_SDOUBLE)
+        kinds[dbl] += 1
+        x = aligned(n)
+        x[:] = rng.standard_normal(n).astype(np.float32) * mvv * 0.6
+        # every binade edge below maxval +- a few ulps, and half-way points: the code boundaries and rounding ties
+        edges = mvv * np.float32(2.0) ** -np.arange(0, 40, dtype=np.float32)
+        pts = np.concatenate([edges, np.nextafter(edges, np.float32(0)), np.nextafter(edges, np.float32(np.inf)), edges * 1.5,
+                              edges * np.float32(0.75)]).astype(np.float32)
+        x[:pts.size] = pts
+        x[pts.size:2 * pts.size] = -pts
+        x[2 * pts.size:2 * pts.size + 8] = [0.0, -0.0, np.nan, np.inf, -np.inf, 1e-38, -1e-45, 3e38]
+        y = aligned(n)
+        assert sim.fp8fq_fake_quant_f32(P(x), P(y), P(tab), n, 1, n, M, 8, sb, None) == 0
+        assert same_bits(y, ref_quant(ref, x, mv, M, 8, sb)[0]), (M, sb, float(mvv), dbl)
+    assert kinds[True] >= 10, kinds                      # the arithmetic path is the common one ...
+    if M == 4 and sb == 1:
+        assert kinds[False] >= 1, kinds                  # ... and the look-up still has its cases
+    # per channel: rows with and without the flag in one launch
+    C, inner = 24, 260
+    mv = mvs[:C].copy()
+    xr = aligned(C * inner)
+    xr[:] = (rng.standard_normal((C, inner)).astype(np.float32) * mv[:, None] * 0.6).reshape(-1)
+    tabs = table_for(sim, mv, M, 8, sb)
+    yr = aligned(C * inner)
+    assert sim.fp8fq_fake_quant_f32(P(xr), P(yr), P(tabs), C * inner, C, inner, M, 8, sb, None) == 0
+    assert same_bits(yr, ref_quant(ref, xr, mv, M, 8, sb, per_channel=True)[0])

@@ -619,3 +619,26 @@ def test_quantised_weight_cache_is_keyed_on_weight_and_range(simdev):
             assert torch.equal(model(x), y3)   # same bits as re-quantising every forward
         finally:
             modules.CACHE_QUANTIZED_WEIGHTS = False
+
+
+def test_uint8_normalisation_is_torchvisions_bit_for_bit(simdev):
+    """ops.normalize_u8 / workloads.U8Normalize against ToTensor + Normalize as torchvision computes them
+    (utils/imagenet_dataloaders.py:66-81): ``img.float().div(255)``, then ``sub_(mean).div_(std)`` per channel -- every
+    byte value in every channel, vector and scalar paths (H*W % 16 != 0), bit for bit."""
+    from fp8_quantization_b200 import ops, workloads
+
+    mean, std = workloads.IMAGENET_MEAN, workloads.IMAGENET_STD
+    norm = workloads.U8Normalize(device=torch.device("cpu"))
+    g = torch.Generator().manual_seed(4)
+    for shape in ((2, 3, 32, 32), (3, 3, 7, 9), (1, 3, 16, 16)):
+        x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+        x.view(-1)[:256] = torch.arange(256, dtype=torch.uint8)[: x.numel()][:256] if x.numel() >= 256 else x.view(-1)[:256]
+        want = x.to(torch.float32).div(255)
+        want.sub_(torch.tensor(mean).view(1, 3, 1, 1)).div_(torch.tensor(std).view(1, 3, 1, 1))
+        got = norm(x)
+        assert got.dtype == torch.float32 and got.shape == x.shape
+        assert torch.equal(bits(got), bits(want)), shape
+    with pytest.raises(ops.Fp8fqError):
+        ops.normalize_u8(torch.zeros(1, 3, 4, 4), norm.lut)               # not uint8
+    with pytest.raises(ops.Fp8fqError):
+        ops.normalize_u8(torch.zeros(1, 4, 4, 4, dtype=torch.uint8), norm.lut)   # table of another channel count
