@@ -706,6 +706,16 @@ def leg_reference_gpu_eager(plan, st, dev, steps=3):
 
 # ---------------------------------------------------------------------------------------------------------
 def main():
+    # model constructors print (as the reference's do); stdout carries the ONE JSON line only
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        line = _main()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def _main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -714,7 +724,7 @@ def main():
 
     if args.impl == "reference":
         if rank != 0:
-            return 0
+            return None
         cpu_steps = max(1, args.steps)
         cb = run_cpu_reference(cpu_steps, max(0, args.warmup), args.cpu_batch, M)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -727,8 +737,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
+        return line
 
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
     import fp8_quantization_b200 as fq
@@ -824,6 +833,35 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = st["elems"] * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- host side of one eager (un-graphed) step: what each binding of the C ABI costs per call ----------------------
+    host_binding = None
+    if rank == 0:
+        def eager_ms():
+            with torch.no_grad():
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    step()
+                torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / 10 * 1e3
+        saved = ops._torch_ops
+        host_binding = {"default": "torch (TORCH_LIBRARY fp8fq, libfp8fq_torch.so)" if ops.torch_binding() is not None else "ctypes",
+                        "calls_per_step": st["launches"], "graph_ms_per_step": ms_per_step}
+        if ops.torch_binding() is not None:
+            host_binding["torch_eager_ms_per_step"] = eager_ms()
+        ops._torch_ops = None
+        try:
+            host_binding["ctypes_eager_ms_per_step"] = eager_ms()
+        finally:
+            ops._torch_ops = saved
+        host_binding["note"] = ("wall clock of the step issued call by call from Python (no CUDA graph), synchronised; minus "
+                                "the graph time it is the host cost: Python wrapper + argument checks + binding + launch")
+        for k in ("torch", "ctypes"):
+            if k + "_eager_ms_per_step" in host_binding:
+                host_binding[k + "_us_per_call_over_graph"] = (host_binding[k + "_eager_ms_per_step"] - ms_per_step) * 1e3 / st["launches"]
 
     # ---- roofline of the dominant kernel (fq_stream_kernel), live: CUDA events around each of its launches ---
     roof = None
@@ -933,6 +971,11 @@ def main():
                 d2h_bytes += sum(h.numel() * 4 for h in h_out[-1])
             s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
             ev_site = [None] * len(plan)
+            ev_read = [None] * len(plan)
+            # every site writes into its own preallocated device buffer (the ops' out= argument): no allocation inside
+            # the timed loop -- outputs handed to another stream would otherwise pin their blocks in the caching
+            # allocator until the D2H copy retires, and a fragmented pool then falls back to (synchronising) cudaMalloc
+            d_out = [None if r is None or h_in[i] is None else r for i, r in enumerate(ref_results)]
 
             def e2e_hook(i, name, args, real, kw):
                 if h_in[i] is None:
@@ -945,7 +988,10 @@ def main():
                         dten.copy_(hten, non_blocking=True)
                 s_k.wait_stream(s_in)
                 with torch.cuda.stream(s_k):
-                    out = getattr(ops, name)(*real, **kw)
+                    if ev_read[i] is not None:
+                        s_k.wait_event(ev_read[i])   # last step's D2H copy of this site's output buffer has retired
+                    okw = dict(kw, outs=d_out[i]) if name == "fake_quant_multi" else dict(kw, out=d_out[i])
+                    out = getattr(ops, name)(*real, **okw)
                     if ev_site[i] is None:
                         ev_site[i] = torch.cuda.Event()
                     ev_site[i].record(s_k)
@@ -953,7 +999,9 @@ def main():
                 with torch.cuda.stream(s_out):
                     for o, h in zip(out if isinstance(out, (list, tuple)) else [out], h_out[i]):
                         h.copy_(o, non_blocking=True)
-                        o.record_stream(s_out)
+                    if ev_read[i] is None:
+                        ev_read[i] = torch.cuda.Event()
+                    ev_read[i].record(s_out)
                 return out
 
             def e2e_step():
@@ -979,7 +1027,7 @@ def main():
                    "note": "every site's externally produced inputs (conv outputs, weights) copied from pinned host "
                            "memory and every site's output copied back to pinned host memory, per step; "
                            "3 streams (H2D / kernels / D2H); wall clock around synchronised region, max over ranks"}
-            del h_in, h_out, ref_results
+            del h_in, h_out, ref_results, d_out
             # what the host link can do on this box: the same copies alone and in both directions at once
             nprobe = 64 << 20  # 256 MB per buffer
             hp_a, hp_b = torch.empty(nprobe).pin_memory(), torch.empty(nprobe).pin_memory()
@@ -1172,7 +1220,7 @@ def main():
         import torch.distributed as td
         td.destroy_process_group()
     if rank != 0:
-        return 0
+        return None
 
     cpu_baseline = None
     if not args.no_cpu and world == 1:
@@ -1191,15 +1239,14 @@ def main():
                          "every buffer is touched once per step, so no tensor survives in L2 between steps"}),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu_baseline,
         "model": model_info, "calibration": calibration, "dp_parity": dp_parity, "weights": weights_info,
-        "configs": configs, "numa": numa,
+        "configs": configs, "numa": numa, "host_binding": host_binding,
         "hbm_gbs_step": (st["stream_bytes"] + 8 * st["weight_elems"]) / (ms_per_step * 1e-3) / 1e9,
         "parity": {"checker": "oracle (reference ATen op sequence) run on this GPU, tests/test_gpu_model_parity.py: all "
                               "ranges and logits bit-equal; vs the reference's CPU run codes differ exactly where "
                               "torch-CUDA itself differs from torch-CPU (tests/test_gpu_parity.py)",
                    "reference_on_gpu_is": "the oracle port (the reference checkout does not exist on the GPU box)"},
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 if __name__ == "__main__":

@@ -54,8 +54,39 @@ def build(force=False, verbose=False, defines=(), out=None):
     return target
 
 
+TORCH_SRC = os.path.join(HERE, "csrc", "fp8fq_torch.cpp")
+TORCH_OUT = os.path.join(HERE, "libfp8fq_torch.so")
+
+
+def build_torch_ext(force=False):
+    """Builds libfp8fq_torch.so: the TORCH_LIBRARY(fp8fq, ...) operator layer over the C ABI (csrc/fp8fq_torch.cpp), a plain
+    g++ compile against torch's headers, linked to libfp8fq.so next to it ($ORIGIN).  In-tree, like libfp8fq.so."""
+    deps = [TORCH_SRC, DEPS[2], OUT]
+    if not force and os.path.exists(TORCH_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_OUT) for d in deps):
+        return TORCH_OUT
+    import torch
+
+    tdir = os.path.dirname(torch.__file__)
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(find_nvcc())), "include")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include", f"-I{cuda_inc}", TORCH_SRC, "-o", TORCH_OUT,
+           f"-L{tdir}/lib", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", f"-L{HERE}", "-l:libfp8fq.so",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tdir}/lib"]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libfp8fq_torch.so")
+    return TORCH_OUT
+
+
 if __name__ == "__main__":
     # python -m fp8_quantization_b200.build [--force] [-v] [-DNAME=VALUE ...] [--out PATH]
     argv = sys.argv[1:]
     print(build(force="--force" in argv, verbose="-v" in argv, defines=[a[2:] for a in argv if a.startswith("-D")],
                 out=argv[argv.index("--out") + 1] if "--out" in argv else None))
+    if "--out" not in argv and not any(a.startswith("-D") for a in argv):
+        print(build_torch_ext(force="--force" in argv))

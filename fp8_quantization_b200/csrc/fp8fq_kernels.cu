@@ -314,6 +314,14 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
   (void)v; (void)src;
 #endif
 }
+// FP8FQ_SDOUBLE (build option, default off): for tables whose scales are exact doublings of each other (FLAG_SDOUBLE,
+// the usual case) the K > 3 element path derives (s, 1/s) from the exponent code by integer arithmetic
+// (lookup_scale_fast) instead of the per-element 64-bit table load.  Bit-identical (host simulation + GPU tests of
+// round 2), but measured SLOWER on the B200: the K > 3 kernels are issue / ALU bound, not L1 bound -- MobileNetV2's
+// channels_last BN+ReLU6+E3M4 sites 0.797 -> 0.764 of the HBM peak at [128,96,112,112] (profiles/kernels_ab_r02c.json).
+#ifndef FP8FQ_SDOUBLE
+#define FP8FQ_SDOUBLE 0
+#endif
 // FP8FQ_PACK2 (build option): the independent fp32 multiplies / adds / FMAs of neighbouring elements are issued as
 // sm_100's two-wide instructions (FMUL2 / FADD2 / FFMA2: same IEEE round-to-nearest results, half the issue slots).
 #ifndef FP8FQ_PACK2
@@ -544,7 +552,7 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.irregular = (fl & FLAG_IRREGULAR) != 0;
     c.ref = f2u(ld(tab + H_REF));
     c.band = fl >> BAND_SHIFT;
-    c.dbl = (fl & FLAG_SDOUBLE) != 0;
+    c.dbl = FP8FQ_SDOUBLE && (fl & FLAG_SDOUBLE) != 0;
     c.s1b = f2u(ld(tab + off_sr(K) + 2));
     c.r1b = f2u(ld(tab + off_sr(K) + 3));
     c.tmax = (uint32_t)(K - 1) << 23;

@@ -26,6 +26,46 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- host binding of the hot path ---------------------------------------------------------------------------------------
+# Two bindings of the SAME C ABI: the torch-registered operators of libfp8fq_torch.so (csrc/fp8fq_torch.cpp:
+# TORCH_LIBRARY(fp8fq, ...) -- argument checks, output allocation and the stream look-up in C++, one dispatcher call per
+# op) for the ops of the validate and calibration forwards, and ctypes (_lib.py) for the whole ABI.  The torch binding
+# is used for CUDA tensors whenever the library has been built; FP8FQ_BINDING=ctypes forces ctypes (so does FP8FQ_LIB,
+# an alternative build of libfp8fq.so the operator library is not linked against).
+_torch_ops = None
+_torch_ops_tried = False
+
+
+def torch_binding():
+    """``torch.ops.fp8fq`` if libfp8fq_torch.so is available and selected, else None."""
+    global _torch_ops, _torch_ops_tried
+    if not _torch_ops_tried:
+        _torch_ops_tried = True
+        import os
+
+        from ._lib import _HERE
+
+        path = os.path.join(_HERE, "libfp8fq_torch.so")
+        if (os.environ.get("FP8FQ_BINDING", "torch") == "torch" and not os.environ.get("FP8FQ_LIB")
+                and os.path.exists(path)):
+            torch.ops.load_library(path)
+            if torch.ops.fp8fq.abi_version() != lib().fp8fq_version():
+                raise Fp8fqError("libfp8fq_torch.so and libfp8fq.so disagree about the ABI version: rebuild both")
+            _torch_ops = torch.ops.fp8fq
+    return _torch_ops
+
+
+def _via_torch(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda and torch_binding() is not None
+
+
+def _torch_call(fn, *args):
+    try:
+        return fn(*args)
+    except RuntimeError as exc:       # TORCH_CHECK -> the package's error type
+        raise Fp8fqError(str(exc).split("\n")[0]) from None
+
+
 def on_device(t) -> bool:
     """The one gate that decides whether a tensor may go to the kernels: it must live on a CUDA device.  Every fused
     path of the module layer asks this (and ``_require`` enforces it), so the package has no CPU path.  (Being the
@@ -167,6 +207,8 @@ def set_range_prepare(xmin: torch.Tensor, xmax: torch.Tensor, mantissa_bits: flo
 def fake_quant(x: torch.Tensor, table: torch.Tensor, C: int, mantissa_bits: float, n_bits: int, sign_bits: int,
                out: torch.Tensor = None):
     """FPQuantizer.forward (fp8_quantizer.py:91-133).  C == 1: per tensor; else channel = dim 0."""
+    if _via_torch(x):
+        return _torch_call(_torch_ops.fake_quant, x, table, int(C), float(mantissa_bits), int(n_bits), int(sign_bits), out)
     _require(x, "x")   # channels_last x: elementwise over the same memory; channel = dim 0 stays the outermost stride
     _require_table(table, C, mantissa_bits, n_bits, sign_bits, "table")
     n = x.numel()
@@ -227,6 +269,9 @@ def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n
     """quantized_folded_bn.py:39-55 in one pass: Q(act(bn(x))), x is [N, C, *spatial] contiguous.
     bn_mode 0: (bn_scale, bn_shift) from bn_fold; bn_mode 1: bn_scale = bn_pack(...) (bit-exact ATen arithmetic).
     Returns None for tensors of MAX_FUSED_ELEMS elements or more (the caller composes the unfused ops)."""
+    if _via_torch(x):
+        return _torch_call(_torch_ops.bn_act_quant, x, bn_scale, bn_shift, int(act), table, float(mantissa_bits), int(n_bits),
+                           int(sign_bits), int(bn_mode), out)
     _require(x, "x")
     if x.numel() >= MAX_FUSED_ELEMS:
         return None
@@ -260,6 +305,10 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
     """Whole residual-block tail (models/resnet_quantized.py:39-46) in one pass:
     Q_outer(act(Q_inner(bn(x)) + residual)).  fmt_* = (mantissa_bits, n_bits, sign_bits).
     Returns None when the fused variant does not cover the shape (caller composes the two kernels)."""
+    if _via_torch(x):
+        return _torch_call(_torch_ops.bn_quant_add_act_quant, x, residual, bn_scale, bn_shift, int(act), table_inner,
+                           float(fmt_inner[0]), int(fmt_inner[1]), int(fmt_inner[2]), table_outer, float(fmt_outer[0]),
+                           int(fmt_outer[1]), int(fmt_outer[2]), int(bn_mode), out)
     _require(x, "x")
     _require(residual, "residual")
     _require_same_layout(x, residual, "bn_quant_add_act_quant")
@@ -290,6 +339,9 @@ def bn_quant_add_act_quant(x, residual, bn_scale, bn_shift, act: int, table_inne
 def fake_quant_multi(xs, tables, Cs, mantissa_bits: float, n_bits: int, sign_bits: int, outs=None):
     """Per-channel fake-quant of several tensors of one format in ONE launch (hijacker.py:88-98 for every
     layer of a forward).  Returns the list of outputs."""
+    if outs is None and len(xs) > 0 and _via_torch(xs[0]):
+        return list(_torch_call(_torch_ops.fake_quant_multi, list(xs), list(tables), [int(c) for c in Cs],
+                                float(mantissa_bits), int(n_bits), int(sign_bits)))
     if outs is None:
         outs = [torch.empty_like(x) for x in xs]
     descs = (TensorDesc * len(xs))()
@@ -305,6 +357,8 @@ def fake_quant_multi(xs, tables, Cs, mantissa_bits: float, n_bits: int, sign_bit
 
 def add_act_quant(a, b, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int, out=None):
     """models/resnet_quantized.py:43-46 in one pass: Q(act(a + b))."""
+    if _via_torch(a):
+        return _torch_call(_torch_ops.add_act_quant, a, b, int(act), table, float(mantissa_bits), int(n_bits), int(sign_bits), out)
     _require(a, "a")
     _require(b, "b")
     _require_same_layout(a, b, "add_act_quant")
@@ -432,6 +486,10 @@ def _workspace(device):
 
 def minmax(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float = 0.9):
     """Estimator min/max + state update in place (range_estimators.py:61-125).  cur_min/cur_max: [C]."""
+    if _via_torch(x):
+        _torch_call(_torch_ops.minmax, x, bool(per_channel), cur_min, cur_max, int(est_mode), bool(initialized),
+                    float(momentum), _workspace(x.device))
+        return cur_min, cur_max
     _require(x, "x")
     n = x.numel()
     C = x.shape[0] if per_channel else 1
@@ -446,6 +504,11 @@ def minmax(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: b
 def estimate_prepare(x, per_channel: bool, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float,
                      maxval_out, mantissa_bits: float, n_bits: int, sign_bits: int, table_out):
     """estimator + set_quant_range + table in one launch (quantization_manager.py:114-122 minus the quantiser)."""
+    if _via_torch(x):
+        _torch_call(_torch_ops.estimate_prepare, x, bool(per_channel), cur_min, cur_max, int(est_mode), bool(initialized),
+                    float(momentum), maxval_out, float(mantissa_bits), int(n_bits), int(sign_bits), table_out,
+                    _workspace(x.device))
+        return maxval_out, table_out
     _require(x, "x")
     n = x.numel()
     C = x.shape[0] if per_channel else 1
@@ -466,6 +529,11 @@ def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_m
     """Per-tensor estimator statistics of act(bn(x)) without materialising it (+ estimator update, and with
     ``table_out``: set_quant_range + table) -- fp8fq_bn_act_estimate_prepare_f32.  Returns False when the shape is
     not covered by the fused kernel (the caller then composes the unfused ops)."""
+    if _via_torch(x):
+        mb, nb, sb = fmt if fmt is not None else (0.0, 0, 0)
+        return bool(_torch_call(_torch_ops.bn_act_estimate_prepare, x, bn_scale, bn_shift, int(act), int(bn_mode), cur_min,
+                                cur_max, int(est_mode), bool(initialized), float(momentum), maxval_out, float(mb), int(nb),
+                                int(sb), table_out, _workspace(x.device)))
     _require(x, "x")
     if x.numel() >= MAX_FUSED_ELEMS:
         return False

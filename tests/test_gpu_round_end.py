@@ -73,16 +73,16 @@ def test_uint8_normalisation_on_the_gpu_and_in_the_graph():
     g = torch.Generator(device=dev).manual_seed(5)
     x = torch.randint(0, 256, (8, 3, 224, 224), dtype=torch.uint8, device=dev, generator=g)
     norm = workloads.U8Normalize(device=dev)
-    want = x.to(torch.float32).div(255)
-    want.sub_(torch.tensor(workloads.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)).div_(
-        torch.tensor(workloads.IMAGENET_STD, device=dev).view(1, 3, 1, 1))
+    def torchvision_cpu(u8):     # ToTensor + Normalize as the reference's loader workers compute them: on the HOST
+        t = u8.cpu().to(torch.float32).div(255)   # (ATen-CUDA would multiply by the fp32 reciprocal of 255 instead)
+        return t.sub_(torch.tensor(workloads.IMAGENET_MEAN).view(1, 3, 1, 1)).div_(
+            torch.tensor(workloads.IMAGENET_STD).view(1, 3, 1, 1)).to(dev)
+
+    want = torchvision_cpu(x)
     got = norm(x)
     assert torch.equal(got.view(torch.int32), want.view(torch.int32))
     odd = torch.randint(0, 256, (2, 3, 7, 9), dtype=torch.uint8, device=dev, generator=g)     # scalar path
-    w2 = odd.to(torch.float32).div(255)
-    w2.sub_(torch.tensor(workloads.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)).div_(
-        torch.tensor(workloads.IMAGENET_STD, device=dev).view(1, 3, 1, 1))
-    assert torch.equal(norm(odd).view(torch.int32), w2.view(torch.int32))
+    assert torch.equal(norm(odd).view(torch.int32), torchvision_cpu(odd).view(torch.int32))
     torch.manual_seed(10)
     model = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(dev).eval().to(memory_format=torch.channels_last)
     workloads.pass_data_for_range_estimation([want], model, True, True, 1)
@@ -95,3 +95,54 @@ def test_uint8_normalisation_on_the_gpu_and_in_the_graph():
     out = torch.empty(3, 8, 1000).pin_memory()
     gf.run_pipelined([host] * 3, out)
     assert torch.equal(out[0], ref.cpu()) and torch.equal(out[2], ref.cpu())
+
+
+def test_torch_registered_ops_are_the_default_binding_and_equal_ctypes():
+    """libfp8fq_torch.so (TORCH_LIBRARY(fp8fq, ...), csrc/fp8fq_torch.cpp) is what the package calls for CUDA tensors;
+    the ctypes binding of the same C ABI gives the same bits; argument errors surface as Fp8fqError from both."""
+    import torch
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import ops
+
+    assert ops.torch_binding() is not None and ops.torch_binding().abi_version() == fq.lib().fp8fq_version()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(6)
+    x = torch.randn(4, 32, 28, 28, device=dev)
+    r = torch.relu(torch.randn_like(x))
+    xc, rc = x.contiguous(memory_format=torch.channels_last), r.contiguous(memory_format=torch.channels_last)
+    q5, q4 = fq.FPQuantizer(8, mantissa_bits=5, maxval=3.0), fq.FPQuantizer(8, mantissa_bits=4, maxval=2.0)
+    t5, _ = q5.table_for(x)
+    t4, _ = q4.table_for(x)
+    pk = ops.bn_pack(torch.randn(32, device=dev), torch.rand(32, device=dev) + 0.5, None, None, 1e-5)
+    w = torch.randn(32, 288, device=dev)
+    qw = fq.FPQuantizer(8, per_channel=True, mantissa_bits=5, set_maxval=True)
+    qw.set_quant_range(w.min(1)[0], w.max(1)[0])
+    tw, _ = qw.table_for(w)
+
+    def run_all():
+        cm, cx = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        ops.minmax(x, False, cm, cx, ops.EST_CURRENT, False)
+        return [ops.fake_quant(x, t5, 1, 5.0, 8, 1), ops.fake_quant(xc, t4, 1, 4.0, 8, 1),
+                ops.bn_act_quant(x, pk, None, 1, t5, 5.0, 8, 1, bn_mode=1), ops.bn_act_quant(xc, pk, None, 2, t4, 4.0, 8, 1, bn_mode=1),
+                ops.add_act_quant(x, r, 1, t5, 5.0, 8, 1),
+                ops.bn_quant_add_act_quant(x, r, pk, None, 1, t4, (4.0, 8, 1), t5, (5.0, 8, 1), bn_mode=1),
+                ops.bn_quant_add_act_quant(xc, rc, pk, None, 0, t5, (5.0, 8, 1), t4, (4.0, 8, 1), bn_mode=1),
+                ops.fake_quant_multi([w, w * 0.5], [tw, tw], [32, 32], 5.0, 8, 1)[1], cm, cx]
+
+    a = run_all()
+    saved = ops._torch_ops
+    ops._torch_ops = None
+    try:
+        b = run_all()
+        with pytest.raises(fq.Fp8fqError):
+            ops.add_act_quant(x, rc, 1, t5, 5.0, 8, 1)          # mixed layouts, ctypes binding
+    finally:
+        ops._torch_ops = saved
+    for u, v in zip(a, b):
+        assert torch.equal(u.contiguous().view(torch.int32), v.contiguous().view(torch.int32))
+    with pytest.raises(fq.Fp8fqError):
+        ops.add_act_quant(x, rc, 1, t5, 5.0, 8, 1)              # mixed layouts, torch binding
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x.double(), t5, 1, 5.0, 8, 1)
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x, t5[:4], 1, 5.0, 8, 1)                  # table too small for the format

@@ -863,12 +863,19 @@ def test_simulated_kernels_against_the_real_reference_golden_vectors(sim):
 
 
 @pytest.mark.parametrize("M,sb", [(4, 1), (3, 1), (2, 1), (4, 0), (1, 1)])
-def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(sim, ref, M, sb):
-    """K > 3 formats: when the prologue finds the reference's scales to be exact doublings of each other (FLAG_SDOUBLE,
+def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(built, ref, M, sb):
+    """(Build option FP8FQ_SDOUBLE, exercised on oracle/_build/libfp8fq_sim_fulltilecl.so, which is built with it.)
+    K > 3 formats: when the prologue finds the reference's scales to be exact doublings of each other (FLAG_SDOUBLE,
     the usual case), the element path derives (s, 1/s) from the exponent code by integer arithmetic instead of loading
     them (lookup_scale_fast); otherwise it keeps the table look-up.  Both kinds of table must occur over a sweep of
     ranges and both must reproduce the direct formula bit for bit -- values at every code boundary, rounding ties, +-0,
     denormals, NaN / inf, per tensor (stream kernel) and per channel (row kernel)."""
+    from fp8_quantization_b200._lib import SIGNATURES
+
+    sim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim_fulltilecl.so"))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(sim, name)
+        fn.restype, fn.argtypes = res, args
     rng = np.random.default_rng(40 + M)
     FLAG_SDOUBLE, H_FLAGS = 8, 4
     kinds = {True: 0, False: 0}

@@ -20,7 +20,12 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        # round 2: per-pipe utilisation (which unit is the busiest one besides DRAM)
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct"]
 
 
 def short(name):
