@@ -69,9 +69,10 @@ def parse_args():
                                                               "reference eager on the GPU)")
     ap.add_argument("--c4-batch", type=int, default=32, help="images per GPU of the config-4 (MSE sweep) leg")
     ap.add_argument("--mantissa-bits", type=int, default=5)
-    ap.add_argument("--memory-format", choices=["nchw", "channels_last"], default="channels_last",
-                    help="activation/weight memory layout inside the network (images always arrive NCHW); "
-                         "channels_last is what cuDNN's tensor-core convolutions produce natively")
+    ap.add_argument("--memory-format", choices=["nchw", "channels_last"], default="nchw",
+                    help="activation/weight memory layout inside the network (images always arrive NCHW): nchw is the "
+                         "reference's own layout (the like-for-like headline); channels_last is what cuDNN's tensor-core "
+                         "convolutions produce natively -- both are measured, see 'model' and 'other_layout_step'")
     return ap.parse_args()
 
 

@@ -2246,8 +2246,9 @@ struct HostPipe {
   int device = -1;
   bool ready = false;
 };
-HostPipe g_pipe;
-std::mutex g_pipe_mu;
+constexpr int kMaxPipeDevices = 64;
+HostPipe g_pipes[kMaxPipeDevices];      // one pipeline (streams + staging buffers) per device, created on first use
+std::mutex g_pipe_mu[kMaxPipeDevices];  // calls for the same device are serialised; different devices run concurrently
 
 struct DeviceGuard {  // the entry point selects `device`; the caller's current device is restored on every exit
   int prev = -1;
@@ -2264,13 +2265,13 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
   if (x_host == nullptr || y_host == nullptr || maxval_host == nullptr) return FP8FQ_ERR_BAD_ARG;
   if (n < 0 || C < 1 || inner < 0 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
   if (n == 0) return FP8FQ_OK;
-  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  if (device < 0 || device >= kMaxPipeDevices) return FP8FQ_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
   cudaError_t ce;
 #define FQ_CK(call) do { ce = (call); if (ce != cudaSuccess) return (int)ce; } while (0)
   DeviceGuard restore_device;
   FQ_CK(cudaSetDevice(device));
-  HostPipe& p = g_pipe;
-  if (p.ready && p.device != device) return FP8FQ_ERR_UNSUPPORTED;
+  HostPipe& p = g_pipes[device];
   if (!p.ready) {
     for (int i = 0; i < HostPipe::kStreams; ++i) {
       FQ_CK(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
@@ -2296,10 +2297,11 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
   r = fp8fq_prepare_f32(p.d_maxval, C, mantissa_bits, n_bits, sign_bits, p.d_table, p.st[0]);
   if (r != FP8FQ_OK) return r;
   FQ_CK(cudaStreamSynchronize(p.st[0]));
-  // chunks are whole rows when per-channel, so each chunk sees a contiguous range of channel tables
+  // chunks are whole rows when per-channel, so each chunk sees a contiguous range of channel tables; rows longer than a
+  // chunk are cut into pieces, each piece a per-tensor call with its row's table
   int64_t rows_per_chunk = 1, chunk_elems = HostPipe::kChunk;
-  if (C > 1) {
-    if (inner > HostPipe::kChunk) return FP8FQ_ERR_UNSUPPORTED;
+  const bool long_rows = C > 1 && inner > HostPipe::kChunk;
+  if (C > 1 && !long_rows) {
     rows_per_chunk = HostPipe::kChunk / inner;
     chunk_elems = rows_per_chunk * inner;
   }
@@ -2317,7 +2319,11 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
   int64_t pend_off[HostPipe::kStreams] = {-1, -1, -1}, pend_len[HostPipe::kStreams] = {0, 0, 0};
   while (done < n) {
     const int s = (int)(k % HostPipe::kStreams);
-    const int64_t len = (n - done) < chunk_elems ? (n - done) : chunk_elems;
+    int64_t len = (n - done) < chunk_elems ? (n - done) : chunk_elems;
+    if (long_rows) {   // stay inside the current row
+      const int64_t row_left = inner - done % inner;
+      len = len < row_left ? len : row_left;
+    }
     if (!pin_x || !pin_y) {  // a staging buffer of this stream is about to be reused
       FQ_CK(cudaStreamSynchronize(p.st[s]));
       if (!pin_y && pend_off[s] >= 0) memcpy(y_host + pend_off[s], p.pin_out[s], pend_len[s] * sizeof(float));
@@ -2330,6 +2336,9 @@ int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* m
     FQ_CK(cudaMemcpyAsync(p.dev[s], src, len * sizeof(float), cudaMemcpyHostToDevice, p.st[s]));
     if (C == 1) {
       r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table, len, 1, len, mantissa_bits, n_bits, sign_bits, p.st[s]);
+    } else if (long_rows) {
+      r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table + (done / inner) * stride, len, 1, len, mantissa_bits, n_bits,
+                               sign_bits, p.st[s]);
     } else {
       const int64_t row0 = done / inner, nrows = len / inner;
       r = fp8fq_fake_quant_f32(p.dev[s], p.dev[s], p.d_table + row0 * stride, len, nrows, inner, mantissa_bits,

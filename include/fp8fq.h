@@ -264,9 +264,10 @@ int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, cons
 
 /* End-to-end entry point with HOST buffers (what a caller without device memory binds):
  * chunked H2D -> fake-quant -> D2H pipeline over internal pinned staging and `nstreams` streams.
- * maxval_host: [C].  Synchronises before returning.  The one entry point with state of its own: staging buffers and
- * streams are created on first use for `device` and kept (calls are serialised by a mutex; a second device answers
- * FP8FQ_ERR_UNSUPPORTED); the caller's current device is restored before returning. */
+ * maxval_host: [C].  Synchronises before returning.  The one entry point with state of its own: per device, staging
+ * buffers and streams are created on first use and kept (calls for the same device are serialised by a mutex, calls
+ * for different devices run concurrently -- a single process may drive several GPUs); the caller's current device is
+ * restored before returning.  Per-channel rows longer than the internal chunk are processed in pieces. */
 int fp8fq_fake_quant_host_f32(const float* x_host, float* y_host, const float* maxval_host, int64_t n,
                               int64_t C, int64_t inner, float mantissa_bits, int n_bits, int sign_bits,
                               int device);

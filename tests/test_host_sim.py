@@ -754,12 +754,14 @@ def test_host_entry_point_chunking(sim, ref, pinned):
     sim.fp8fq_sim_report_pinned(pinned)
     try:
         rng = np.random.default_rng(50 + pinned)
-        for C, inner in ((1, (8 << 20) + 4099), (5, 3 << 20)):
+        # per tensor across chunks; per channel with whole rows per chunk; per channel with rows LONGER than a chunk
+        # (cut into pieces that each use their row's table); device 1: every device has its own pipeline
+        for C, inner, device in ((1, (8 << 20) + 4099, 0), (5, 3 << 20, 0), (2, (8 << 20) + 1029, 1)):
             n = C * inner
             x = rng.standard_normal(n).astype(np.float32)
             mv = np.abs(x.reshape(C, inner)).max(1).astype(np.float32)
             y = np.zeros(n, np.float32)
-            assert sim.fp8fq_fake_quant_host_f32(P(x), P(y), P(mv), n, C, inner, 5, 8, 1, 0) == 0
+            assert sim.fp8fq_fake_quant_host_f32(P(x), P(y), P(mv), n, C, inner, 5, 8, 1, device) == 0
             assert same_bits(y, ref_quant(ref, x, mv, 5, per_channel=True)[0]), (C, inner, pinned)
     finally:
         sim.fp8fq_sim_report_pinned(0)
