@@ -72,6 +72,8 @@ SIGNATURES["fp8fq_max_pool2d_nhwc_f32"] = (_c_i, [_c_p, _c_p, _c_l, _c_l, _c_l, 
 
 SIGNATURES["fp8fq_u8_normalize_nchw_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_l, _c_l, _c_l, _c_p])
 
+SIGNATURES["fp8fq_dp_finish_prepare_f32"] = (_c_i, [_c_p, _c_l, _c_p, _c_p, _c_i, _c_i, _c_d, _c_p, _c_f, _c_i, _c_i, _c_p, _c_p])
+
 _lib = None
 
 

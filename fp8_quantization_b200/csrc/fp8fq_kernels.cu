@@ -1071,6 +1071,11 @@ struct EstArgs {
 
 // estimator update rule for one channel; returns the updated (min, max)
 __device__ __forceinline__ void est_update(const EstArgs& e, int64_t c, float& mn, float& mx) {
+  if (e.est_mode == FP8FQ_EST_DP_STATS) {   // batch statistics for a data-parallel exchange: [-min | max], no state rule
+    e.cur_min[c] = -mn;
+    e.cur_max[c] = mx;
+    return;
+  }
   if (e.initialized && e.est_mode == FP8FQ_EST_ALL) {           // range_estimators.py:96-98
     mn = min_nan(e.cur_min[c], mn);
     mx = max_nan(e.cur_max[c], mx);
@@ -1265,6 +1270,27 @@ __global__ void __launch_bounds__(128) minmax_rows_kernel(const float* __restric
     }
     __syncthreads();
     if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table + row * stride);
+    __syncthreads();
+  }
+}
+
+// Data-parallel calibration, second half: `packed` = [-min (C) | max (C)] of the GLOBAL batch (after the MAX all-reduce
+// of every rank's fp8fq_minmax / bn_act_estimate statistics in mode FP8FQ_EST_DP_STATS).  One CTA per channel: the
+// estimator's update rule on (cur_min, cur_max), set_quant_range and the quantiser table -- what the single-GPU fused
+// calibration launch does after its own reduction.
+__global__ void dp_finish_kernel(const float* __restrict__ packed, int64_t C, const EstArgs est) {
+  __shared__ float s_mv;
+  const int stride = est.table != nullptr ? table_stride(est.K) : 0;
+  for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
+    if (threadIdx.x == 0) {
+      float mn = -packed[c], mx = packed[C + c];
+      est_update(est, c, mn, mx);
+      const float mv = range_to_maxval(mn, mx);
+      if (est.maxval_out != nullptr) est.maxval_out[c] = mv;
+      s_mv = mv;
+    }
+    __syncthreads();
+    if (est.table != nullptr) prepare_channel(s_mv, est.M, est.E, est.K, est.sign_bits, est.table + c * stride);
     __syncthreads();
   }
 }
@@ -2055,7 +2081,7 @@ static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, floa
                        float mantissa_bits, int n_bits, int sign_bits, float* table, void* workspace, void* stream) {
   if (n < 1 || C < 1 || inner < 1 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
   if (x == nullptr || cur_min == nullptr || cur_max == nullptr) return FP8FQ_ERR_BAD_ARG;
-  if (est_mode < 0 || est_mode > 2) return FP8FQ_ERR_BAD_ARG;
+  if (est_mode < 0 || est_mode > FP8FQ_EST_DP_STATS) return FP8FQ_ERR_BAD_ARG;
   if (!aligned4(x)) return FP8FQ_ERR_ALIGNMENT;
   EstArgs e{};
   e.cur_min = cur_min; e.cur_max = cur_max; e.est_mode = est_mode; e.initialized = initialized;
@@ -2110,7 +2136,8 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
                                       float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
                                       float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
                                       void* workspace, void* stream) {
-  if (outer < 1 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1 || est_mode < 0 || est_mode > 2)
+  if (outer < 1 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1 || est_mode < 0 ||
+      est_mode > FP8FQ_EST_DP_STATS)
     return FP8FQ_ERR_BAD_ARG;
   if (x == nullptr || cur_min == nullptr || cur_max == nullptr || bn_scale == nullptr ||
       (bn_mode == 0 && bn_shift == nullptr))
@@ -2160,6 +2187,30 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
     if (bn_mode == 1) launch_plain(minmax_bn_act_kernel<0, 1>, g, b, 0, st, a, partial, counter, e);
     else launch_plain(minmax_bn_act_kernel<0, 0>, g, b, 0, st, a, partial, counter, e);
   }
+  return launch_status();
+}
+
+int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, float* cur_max, int est_mode,
+                                int initialized, double momentum, float* maxval_out, float mantissa_bits, int n_bits,
+                                int sign_bits, float* table, void* stream) {
+  if (packed == nullptr || cur_min == nullptr || cur_max == nullptr || C < 1) return FP8FQ_ERR_BAD_ARG;
+  if (est_mode < 0 || est_mode > 2) return FP8FQ_ERR_BAD_ARG;
+  EstArgs e{};
+  e.cur_min = cur_min; e.cur_max = cur_max; e.est_mode = est_mode; e.initialized = initialized;
+  e.w_new = (float)(1.0 - momentum);
+  e.w_old = (float)momentum;
+  e.maxval_out = maxval_out;
+  e.table = nullptr;
+  int threads = 32;
+  if (table != nullptr) {
+    int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
+    if (r != FP8FQ_OK) return r;
+    e.table = table;
+    e.sign_bits = sign_bits;
+    threads = e.K <= 32 ? 32 : (e.K <= 64 ? 64 : 128);
+  }
+  const int64_t grid = C < 4096 ? C : 4096;
+  launch_plain(dp_finish_kernel, dim3((unsigned)grid), dim3(threads), 0, (cudaStream_t)stream, packed, C, e);
   return launch_status();
 }
 

@@ -154,12 +154,39 @@ class _MinMaxEstimator(RangeEstimatorBase):
         return self.current_xmin, self.current_xmax
 
     def fused_supported(self) -> bool:
-        return not self._dp()
+        return True
+
+    def _dp_packed(self, C, device):
+        """Persistent [-min (C) | max (C)] exchange buffer of this estimator (one per estimator: no allocation and no
+        packing kernels on the calibration path)."""
+        buf = self.__dict__.get("_dp_buf")
+        if buf is None or buf.numel() != 2 * C or buf.device != device:
+            buf = self.__dict__["_dp_buf"] = torch.empty(2 * C, dtype=torch.float32, device=device)
+        return buf
+
+    def _dp_finish(self, packed, x, quantizer):
+        """All-reduce + ONE launch: estimator rule, set_quant_range, table (fp8fq_dp_finish_prepare_f32)."""
+        C = packed.numel() // 2
+        fq_dist.all_reduce_max(packed)            # the one collective: MAX over [-min, max] of every rank's shard
+        cmin, cmax, init = self._state(x)
+        mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
+        maxval = torch.empty(C, dtype=torch.float32, device=x.device)
+        table = ops.new_table(C, mb, nb, sb, x.device)
+        ops.dp_finish_prepare(packed, cmin, cmax, self.EST_MODE, init, self.momentum, maxval, (mb, nb, sb), table)
+        quantizer.adopt_range(maxval, table)
 
     def fused_estimate_prepare(self, x, quantizer):
-        """estimator update + set_quant_range + table in ONE launch; installs the result in ``quantizer``."""
+        """estimator update + set_quant_range + table in ONE launch; installs the result in ``quantizer``.  Under data
+        parallelism: statistics launch (writes [-min | max] straight into the exchange buffer), one MAX all-reduce, one
+        finishing launch -- every rank ends with the range of the concatenated batch."""
         x = x.detach()
         x = ops.dense(x)
+        if self._dp():
+            C = x.shape[0] if self.per_channel else 1
+            packed = self._dp_packed(C, x.device)
+            ops.minmax(x, self.per_channel, packed[:C], packed[C:], ops.EST_DP_STATS, False)
+            self._dp_finish(packed, x, quantizer)
+            return x
         cmin, cmax, init = self._state(x)
         C = cmin.numel()
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
@@ -180,11 +207,11 @@ class _MinMaxEstimator(RangeEstimatorBase):
         x = ops.dense(x.detach())
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
         if self._dp():
-            packed = torch.empty(2, dtype=torch.float32, device=x.device)
+            packed = self._dp_packed(1, x.device)
             if not ops.bn_act_estimate_prepare(x, bn_scale, bn_shift, act_code, bn_mode, packed[:1], packed[1:],
-                                               ops.EST_CURRENT, False, self.momentum):
+                                               ops.EST_DP_STATS, False, self.momentum):
                 return False
-            quantizer.set_quant_range(*self.dp_merge(packed))
+            self._dp_finish(packed, x, quantizer)
             return True
         was_init = self.current_xmin is not None
         cmin, cmax, init = self._state(x)

@@ -912,3 +912,42 @@ def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact
     yr = aligned(C * inner)
     assert sim.fp8fq_fake_quant_f32(P(xr), P(yr), P(tabs), C * inner, C, inner, M, 8, sb, None) == 0
     assert same_bits(yr, ref_quant(ref, xr, mv, M, 8, sb, per_channel=True)[0])
+
+
+@pytest.mark.parametrize("C", [1, 37])
+def test_data_parallel_statistics_mode_and_finish_kernel(sim, host_emul, C):
+    """SURVEY 8e on the kernels themselves: two "ranks" compute their shard's statistics in mode FP8FQ_EST_DP_STATS
+    ([-min | max] written straight into the exchange buffer), the buffers are merged with an element-wise MAX (what the
+    NCCL all-reduce does), and fp8fq_dp_finish_prepare_f32 applies the estimator rule, set_quant_range and builds the
+    table -- equal, bit for bit, to the single-process fused calibration launch on the concatenated batch, for the three
+    estimator rules over three calibration batches."""
+    EST_DP_STATS = 3
+    rng = np.random.default_rng(70 + C)
+    ws = workspace(sim)
+    inner = 1500
+    for mode in (EST_CURRENT, EST_ALL, EST_RUNNING):
+        dmin, dmax = aligned(C), aligned(C)          # data-parallel estimator state
+        smin, smax = aligned(C), aligned(C)          # single-process estimator state
+        for call in range(3):
+            shards = [rand(rng, (C, inner), specials=False) * (call + 1 + r) for r in range(2)]
+            packed = []
+            for xs in shards:
+                xs = np.ascontiguousarray(xs)
+                buf = aligned(2 * C)
+                assert sim.fp8fq_minmax_f32(P(xs), xs.size, C, inner, P(buf[:C]), P(buf[C:]), EST_DP_STATS, 0, 0.9, P(ws),
+                                            None) == 0
+                assert same_bits(buf[:C], -xs.min(1)) and same_bits(buf[C:], xs.max(1))
+                packed.append(buf)
+            merged = aligned(2 * C)
+            merged[:] = np.maximum(packed[0], packed[1])
+            stride = sim.fp8fq_table_stride(5, 8, 1)
+            mv_dp, tab_dp = aligned(C), aligned(stride * C)
+            assert sim.fp8fq_dp_finish_prepare_f32(P(merged), C, P(dmin), P(dmax), mode, int(call > 0), 0.9, P(mv_dp), 5, 8, 1,
+                                                   P(tab_dp), None) == 0
+            # single process: the two shards of every channel side by side = the concatenated batch
+            whole = np.ascontiguousarray(np.concatenate(shards, axis=1))
+            mv_sp, tab_sp = aligned(C), aligned(stride * C)
+            assert sim.fp8fq_estimate_prepare_f32(P(whole), whole.size, C, 2 * inner, P(smin), P(smax), mode, int(call > 0),
+                                                  0.9, P(mv_sp), 5, 8, 1, P(tab_sp), P(ws), None) == 0
+            assert same_bits(dmin, smin) and same_bits(dmax, smax), (mode, call)
+            assert same_bits(mv_dp, mv_sp) and same_bits(tab_dp, tab_sp), (mode, call)

@@ -194,3 +194,55 @@ def test_oracle_composed_mobilenetv2_equals_reference_golden():
     S.fix_ranges()
     _check_composed(g, 3, S, OM.mobilenetv2_forward(S, net, x))
     assert len(S.sites) == 123
+
+
+# ---- golden set at the survey's sizes, digests written by the real reference ------------------
+def _survey_module():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_survey_sizes.py")
+    spec = importlib.util.spec_from_file_location("make_golden_survey_sizes", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not STRICT, reason="digests need ATen's AVX-512 (Sleef) path, as when the fixtures were written")
+def test_oracle_reproduces_the_reference_digests_at_survey_sizes():
+    """252 quantiser cases (M 1..7 x sign x sigma {1e-3, 1, 1e3} x {per tensor 2^20, per channel with inner 1 / 9 / 27 /
+    147 / 576}): the oracle's outputs, exponent codes and mantissa integers hash to what the REAL reference produced."""
+    S = _survey_module()
+    g = load_golden("survey_sizes.npz")
+    n = 0
+    for M in range(1, 8):
+        for sb in (0, 1):
+            for sigma in S.SIGMAS:
+                for inner in (0,) + S.INNERS:
+                    x, pc = S.quantizer_case(M, sb, sigma, inner)
+                    key = f"q_M{M}_s{sb}_sig{S.SIGMAS.index(sigma)}_in{inner}"
+                    assert tuple(g[key + "_shape"]) == tuple(x.shape)
+                    q = O.OracleFPQuantizer(8, per_channel=pc, mantissa_bits=M, set_maxval=True)
+                    q.sign_bits = sb
+                    mn, mx = O.minmax(x, pc)
+                    q.set_quant_range(mn * 0.9, mx * 0.9)
+                    assert S.digest(q.maxval) == str(g[key + "_maxval_digest"])
+                    y, e, qq = O.fake_quant(x, 8, q.maxval, q.mantissa_bits, sb, return_codes=True)
+                    assert [S.digest(y), S.digest(e), S.digest(qq)] == [str(v) for v in g[key]], key
+                    n += 1
+    assert n == 252
+
+
+@pytest.mark.skipif(not STRICT, reason="bit-exact MSE tables need the AVX-512 path")
+def test_oracle_mse_estimator_at_survey_sizes_weight_case():
+    """FP_MSE_Estimator with the mantissa sweep on the per-channel [128,64,3,3] weight (the [8,64,56,56] activation case
+    takes minutes on one CPU thread; it is covered on the GPU, tests/test_gpu_parity.py)."""
+    S = _survey_module()
+    g = load_golden("survey_sizes.npz")
+    x, pc = S.mse_case("weight_128x64x3x3")
+    oq = O.OracleFPQuantizer(8, per_channel=pc, mantissa_bits=4, set_maxval=True, mse_include_mantissa_bits=True)
+    oest = O.OracleFPMSE(per_channel=pc, quantizer=oq)
+    _, omx = oest(x)
+    assert np.array_equal(oest.mses.numpy(), g["mse_weight_128x64x3x3_mses"])
+    assert float(oq.mantissa_bits) == float(g["mse_weight_128x64x3x3_best_m"])
+    assert np.array_equal(omx.float().numpy(), g["mse_weight_128x64x3x3_xmax"])
