@@ -1094,92 +1094,88 @@ def _main():
     model_info = None
     if not args.no_model:
         try:
-            with torch.no_grad():
-                # public API: workloads.GraphedForward = the validate forward as one CUDA graph
-                gf = workloads.GraphedForward(model, x_img)
-                for _ in range(3):
-                    gf.replay()
-                barrier()
-                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                iters = max(5, min(args.steps, 20))
-                m0.record()
-                for _ in range(iters):
-                    gf.replay()
-                m1.record()
-                barrier()
-                mms = m0.elapsed_time(m1) / iters
-                ref_logits = gf.static_out.clone()
-                # e2e: images from pinned host memory, logits back to the host, every step (GraphedForward.run_pipelined:
-                # the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the forward of batch k)
-                h_img = x_img.cpu().pin_memory()
-                h_log = torch.empty((iters,) + tuple(ref_logits.shape)).pin_memory()
-                gf.run_pipelined([h_img] * 2, h_log[:2])
-                barrier()
-                t0 = time.perf_counter()
-                gf.run_pipelined([h_img] * iters, h_log)
-                barrier()
-                dt = time.perf_counter() - t0
-                if not (torch.equal(h_log[0], ref_logits.cpu()) and torch.equal(h_log[iters - 1], ref_logits.cpu())):
-                    raise RuntimeError("e2e logits differ from the device-resident forward")
-                static_x = gf.static_in
-                del gf
-                # the same loop fed with uint8 images (what an image decoder produces): ToTensor + Normalize of the
-                # reference's input pipeline run on the device inside the graph, 1 byte per pixel crosses the host link
-                x_u8 = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8, device=dev)
-                gfu = workloads.GraphedForward(model, x_u8, preprocess=workloads.U8Normalize(device=dev))
-                h_u8 = x_u8.cpu().pin_memory()
-                gfu.run_pipelined([h_u8] * 2, h_log[:2])
-                barrier()
-                t0 = time.perf_counter()
-                gfu.run_pipelined([h_u8] * iters, h_log)
-                barrier()
-                dt_u8 = time.perf_counter() - t0
-                del gfu, x_u8, h_u8
-                # the same forward with the quantised weights cached (modules.CACHE_QUANTIZED_WEIGHTS)
-                modules.CACHE_QUANTIZED_WEIGHTS = True
-                try:
-                    gfc = workloads.GraphedForward(model, static_x)
-                    mms_cached = time_ms(gfc.replay, iters)
-                    if not torch.equal(gfc.static_out, ref_logits):
-                        raise RuntimeError("cached-weight forward differs from the re-quantising forward")
-                    del gfc
-                finally:
-                    modules.CACHE_QUANTIZED_WEIGHTS = False
-                    for mod in model.modules():
-                        mod.__dict__.pop("_wq_cache", None)
-                # the same network in the other memory layout (device-resident forward only), for comparison
-                other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
-                m2 = build_model(other_fmt)
-                workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
-                m2.fix_ranges()
-                gf2 = workloads.GraphedForward(m2, static_x)
-                for _ in range(3):
-                    gf2.replay()
-                barrier()
-                m0.record()
-                for _ in range(iters):
-                    gf2.replay()
-                m1.record()
-                barrier()
-                mms_other = m0.elapsed_time(m1) / iters
-                del gf2, m2
-            vals = torch.tensor([mms, dt, mms_other, mms_cached, dt_u8], device=dev)
-            if world > 1:
-                fq_dist.all_reduce_max(vals)
-            mms, dt, mms_other, mms_cached, dt_u8 = vals.tolist()
-            by_layout = {args.memory_format: B * world / (mms * 1e-3), other_fmt: B * world / (mms_other * 1e-3)}
-            model_info = {"resnet18_quantized_img_per_s": B * world / (mms * 1e-3), "ms_per_forward": mms,
-                          "memory_format": args.memory_format,
-                          "img_per_s_reference_layout_nchw": by_layout["nchw"],
-                          "img_per_s_channels_last": by_layout["channels_last"],
+            iters = max(5, min(args.steps, 20))
+            other_fmt = "nchw" if args.memory_format == "channels_last" else "channels_last"
+
+            def model_leg(mdl, cached_leg):
+                """device-resident forward, fp32-fed and uint8-fed end-to-end loops of one network (all ranks)."""
+                with torch.no_grad():
+                    gf = workloads.GraphedForward(mdl, x_img)     # public API: the validate forward as one CUDA graph
+                    barrier()
+                    ms_dev = time_ms(gf.replay, iters)
+                    barrier()
+                    ref_logits = gf.static_out.clone()
+                    # e2e: images from pinned host memory, logits back to the host, every step (run_pipelined: the H2D
+                    # copy of batch k+1 and the D2H copy of batch k-1 overlap the forward of batch k)
+                    h_img = x_img.cpu().pin_memory()
+                    h_log = torch.empty((iters,) + tuple(ref_logits.shape)).pin_memory()
+                    gf.run_pipelined([h_img] * 2, h_log[:2])
+                    barrier()
+                    t0 = time.perf_counter()
+                    gf.run_pipelined([h_img] * iters, h_log)
+                    barrier()
+                    dt_f32 = time.perf_counter() - t0
+                    if not (torch.equal(h_log[0], ref_logits.cpu()) and torch.equal(h_log[iters - 1], ref_logits.cpu())):
+                        raise RuntimeError("e2e logits differ from the device-resident forward")
+                    del gf, h_img
+                    # the same loop fed with uint8 images (what an image decoder produces): ToTensor + Normalize of the
+                    # reference's input pipeline run on the device inside the graph, 1 byte per pixel crosses the link
+                    x_u8 = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8, device=dev)
+                    gfu = workloads.GraphedForward(mdl, x_u8, preprocess=workloads.U8Normalize(device=dev))
+                    h_u8 = x_u8.cpu().pin_memory()
+                    gfu.run_pipelined([h_u8] * 2, h_log[:2])
+                    barrier()
+                    t0 = time.perf_counter()
+                    gfu.run_pipelined([h_u8] * iters, h_log)
+                    barrier()
+                    dt_u8 = time.perf_counter() - t0
+                    del gfu, x_u8, h_u8, h_log
+                    ms_cached = 0.0
+                    if cached_leg:   # the same forward with the quantised weights cached (modules.CACHE_QUANTIZED_WEIGHTS)
+                        modules.CACHE_QUANTIZED_WEIGHTS = True
+                        try:
+                            gfc = workloads.GraphedForward(mdl, x_img)
+                            ms_cached = time_ms(gfc.replay, iters)
+                            if not torch.equal(gfc.static_out, ref_logits):
+                                raise RuntimeError("cached-weight forward differs from the re-quantising forward")
+                            del gfc
+                        finally:
+                            modules.CACHE_QUANTIZED_WEIGHTS = False
+                            for mod in mdl.modules():
+                                mod.__dict__.pop("_wq_cache", None)
+                vals = torch.tensor([ms_dev, dt_f32, dt_u8, ms_cached], device=dev)
+                if world > 1:
+                    fq_dist.all_reduce_max(vals)
+                ms_dev, dt_f32, dt_u8, ms_cached = vals.tolist()
+                rec = {"ms_per_forward": ms_dev, "img_per_s": B * world / (ms_dev * 1e-3),
+                       "e2e_fp32_fed_img_per_s": B * world * iters / dt_f32,
+                       "e2e_u8_fed_img_per_s": B * world * iters / dt_u8,
+                       "e2e_fp32_fed_frac_of_device": (B * world * iters / dt_f32) / (B * world / (ms_dev * 1e-3)),
+                       "e2e_u8_fed_frac_of_device": (B * world * iters / dt_u8) / (B * world / (ms_dev * 1e-3))}
+                if cached_leg:
+                    rec["weights_cached"] = {"ms_per_forward": ms_cached, "img_per_s": B * world / (ms_cached * 1e-3)}
+                return rec
+
+            main_rec = model_leg(model, True)
+            m2 = build_model(other_fmt)
+            workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
+            m2.fix_ranges()
+            other_rec = model_leg(m2, False)
+            del m2
+            by = {args.memory_format: main_rec, other_fmt: other_rec}
+            model_info = {"resnet18_quantized_img_per_s": main_rec["img_per_s"], "ms_per_forward": main_rec["ms_per_forward"],
+                          "memory_format": args.memory_format, "batch_per_gpu": B,
+                          "img_per_s_reference_layout_nchw": by["nchw"]["img_per_s"],
+                          "img_per_s_channels_last": by["channels_last"]["img_per_s"],
+                          "nchw (reference layout)": by["nchw"], "channels_last": by["channels_last"],
                           "layout_note": "nchw is the reference's own layout (autoquant_utils.py:34-44 forces contiguous "
                                          "operands): the like-for-like number; channels_last additionally uses the "
                                          "space-to-depth stem and this library's max-pool (DESIGN.md section 8)",
-                          "weights_cached": {"ms_per_forward": mms_cached, "img_per_s": B * world / (mms_cached * 1e-3)},
-                          "other_layout": {"memory_format": other_fmt, "ms_per_forward": mms_other,
-                                           "img_per_s": B * world / (mms_other * 1e-3)},
-                          "e2e_img_per_s": B * world * iters / dt, "batch_per_gpu": B,
-                          "e2e_u8": {"img_per_s": B * world * iters / dt_u8, "h2d_bytes_per_step": B * 3 * 224 * 224,
+                          "weights_cached": main_rec.get("weights_cached"),
+                          "other_layout": {"memory_format": other_fmt, "ms_per_forward": other_rec["ms_per_forward"],
+                                           "img_per_s": other_rec["img_per_s"]},
+                          "e2e_img_per_s": main_rec["e2e_fp32_fed_img_per_s"],
+                          "e2e_u8": {"img_per_s": main_rec["e2e_u8_fed_img_per_s"], "h2d_bytes_per_step": B * 3 * 224 * 224,
                                      "d2h_bytes_per_step": B * 1000 * 4,
                                      "note": "uint8 NCHW images from pinned host memory; ToTensor + Normalize "
                                              "(utils/imagenet_dataloaders.py:66-81) on the device inside the graph "
@@ -1188,7 +1184,7 @@ def _main():
                           "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
                           "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
                                       "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "
-                                      "(2 staging buffers, 3 streams)",
+                                      "(2 staging buffers, 3 streams); the e2e numbers of BOTH layouts are under their keys",
                           "note": "full validate forward (cuDNN convs with torch's default TF32 policy, like the "
                                   "reference on the same GPU) captured in one CUDA graph; weights re-quantised every "
                                   "forward as the reference does; random-init weights, synthetic images"}
