@@ -816,10 +816,12 @@ def _main():
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    torch.cuda.profiler.start()   # (no-op unless a profiler runs with --profile-from-start off: then exactly the timed
+    e0.record()                   #  steps are what it lists -- profiles/launches_r02*.csv)
     for _ in range(args.steps):
         run_step()
     e1.record()
+    torch.cuda.profiler.stop()
     barrier()
     ms = e0.elapsed_time(e1)
     # keep the GPU under the same load for ~1 s so that the 100 ms clock sampler sees it (not timed)
@@ -924,16 +926,20 @@ def _main():
                                     "modules.CACHE_QUANTIZED_WEIGHTS keeps the result until a weight or range changes: "
                                     "'cached' = the same step without that launch (and without its elements in the count)"}
         achieved = st["stream_bytes"] / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))["by_memory_format"][
-                args.memory_format]["fq_stream_kernel_dram_bytes_per_launch"]
+            for tag in ("r02", "r01"):   # the newest summary that exists
+                pth = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.json")
+                if os.path.exists(pth):
+                    traffic = json.load(open(pth))["by_memory_format"][args.memory_format]["fq_stream_kernel_dram_bytes_per_launch"]
+                    traffic_src = f"profiles/ncu_summary_{tag}.json"
+                    break
         except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": "fq_stream_kernel (fused BN/add + act + FP8 fake-quant, per-tensor)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_source,
-                "traffic": traffic, "traffic_of": "largest_launch (ncu --set full, profiles/ncu_summary_r01.json)",
+                "traffic": traffic, "traffic_of": f"largest_launch (ncu --set full, {traffic_src})",
                 "launches_per_step": st["stream_launches"],
                 "algorithmic_bytes_per_step": st["stream_bytes"],
                 "avg_launch_us": k_ms * 1e3 / st["stream_launches"], "share_of_step": k_ms / ms_per_step,

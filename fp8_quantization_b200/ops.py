@@ -67,6 +67,30 @@ def _torch_call(fn, *args):
         raise Fp8fqError(str(exc).split("\n")[0]) from None
 
 
+class nvtx_range:
+    """NVTX range around a phase of the flow (calibration, BN re-estimation, validate, one graphed forward) when
+    FP8FQ_NVTX=1: shows up in Nsight Systems / ncu --nvtx; free otherwise.  (The reference has no tracing hooks.)"""
+
+    _on = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range._on is None:
+            import os
+
+            nvtx_range._on = os.environ.get("FP8FQ_NVTX", "0") == "1" and torch.cuda.is_available()
+        if nvtx_range._on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if nvtx_range._on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def on_device(t) -> bool:
     """The one gate that decides whether a tensor may go to the kernels: it must live on a CUDA device.  Every fused
     path of the module layer asks this (and ``_require`` enforces it), so the package has no CPU path.  (Being the

@@ -325,11 +325,13 @@ def pass_data_for_range_estimation(loader, model, act_quant, weight_quant, max_n
     range estimator the reference can install here (:82-94) is not part of the FP8 path."""
     if cross_entropy_layer is not None:
         raise NotImplementedError("the cross-entropy range estimator is outside the FP8 fake-quantisation path")
+    from . import ops
+
     model.set_quant_state(weight_quant, act_quant)
     model.eval()  # BN EMA must not be updated
     device = next(model.parameters()).device
     passed = []
-    with torch.no_grad():
+    with torch.no_grad(), ops.nvtx_range("fp8fq.pass_data_for_range_estimation"):
         for i, data in enumerate(loader):
             if isinstance(data, dict):
                 model(**{k: v.to(device=device) for k, v in data.items()})
@@ -381,10 +383,12 @@ def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=Fals
     Under data parallelism (fp8_quantization_b200.dist active) the batch statistics are those of the global batch
     (per-channel sum / sum-of-squares all-reduce, modules._sync_batch_norm_train), so every rank ends with the
     statistics a single process would compute on the concatenated batches.  Returns the number of batches used."""
+    from . import ops
+
     model.eval()
     device = next(model.parameters()).device
     batches = 0
-    with _BatchStatisticsMode(model) as layers:
+    with ops.nvtx_range("fp8fq.reestimate_BN_stats"), _BatchStatisticsMode(model) as layers:
         if store_ema_stats:
             for layer in layers:
                 _keep_ema_statistics(layer)
@@ -573,7 +577,10 @@ class GraphedForward:
     def replay(self):
         """Runs the forward on whatever ``static_in`` currently holds; returns ``static_out`` (overwritten by the
         next replay)."""
-        self.graph.replay()
+        from . import ops
+
+        with ops.nvtx_range("fp8fq.GraphedForward.replay"):
+            self.graph.replay()
         return self.static_out
 
     def __call__(self, x: torch.Tensor):

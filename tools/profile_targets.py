@@ -1,5 +1,7 @@
 """Launches each kernel family twice on a ResNet-18 stem-sized tensor ([128,64,112,112], NCHW and channels_last), the
-multi-tensor weight launch and one MSE sweep, for `ncu --set full` (second round of launches = warm instruction cache)."""
+multi-tensor weight launch and one MSE sweep, for
+    ncu --set full --clock-control none --profile-from-start off -o gpurun_out/prof_targets python tools/profile_targets.py
+(the second round of launches is the profiled one: warm instruction cache)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -37,6 +39,9 @@ xm = torch.relu(torch.randn(8, 64, 56, 56, device=dev))
 grid = (torch.linspace(0.1, 1.2, 111, device=dev) * xm.max()).reshape(111, 1).contiguous()
 mses = torch.zeros(2, 111, 1, device=dev)
 for i in range(2):
+    if i == 1:   # only the second round is profiled (ncu --profile-from-start off): warm instruction cache, small report
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     x, xc = xs[i], xs_cl[i]
     ops.fake_quant(x, t5, 1, 5.0, 8, 1, out=y)                                   # fq_stream_kernel<0,0,4,0,0>
     ops.fake_quant(x, t4, 1, 4.0, 8, 1, out=y)                                   # <1,0,4,0,0>
@@ -49,4 +54,5 @@ for i in range(2):
     ops.fake_quant_multi(ws, wt, [w.shape[0] for w in ws], 5.0, 8, 1, outs=wo)   # fq_rows_kernel<0,0>
     ops.mse_grid(xm, False, grid, [5.0, 3.0], 8, 1, mses)                        # mse_grid_kernel<0,16>, <1,16>
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
