@@ -257,7 +257,7 @@ def test_survey_size_cases_kernel_vs_oracle_on_gpu_and_cpu(M):
     """SURVEY 8(c) sizes: per tensor n = 2^20 and per channel with inner in {1, 9, 27, 147, 576}, sigma in {1e-3, 1, 1e3},
     both signs.  (P1) every output float equals the oracle's run on this GPU; (P2) against the oracle on the CPU -- whose
     digests at these sizes are pinned to the real reference, tests/test_oracle_golden.py -- the canonical codes differ on
-    fewer than 2e-3 of the elements and the floats by at most 1e-5 relative."""
+    fewer than 2e-3 of the elements and the other floats by at most 1e-5 relative."""
     import fp8_quantization_b200 as fq
 
     S = _survey_module()
@@ -281,14 +281,13 @@ def test_survey_size_cases_kernel_vs_oracle_on_gpu_and_cpu(M):
                 same = (y.view(torch.int32) == y_gpu_oracle.view(torch.int32)) | (torch.isnan(y) & torch.isnan(y_gpu_oracle))
                 assert bool(same.all()), (M, sb, sigma, inner)
                 yc = y.cpu()
-                diff = (yc != y_cpu) & ~(torch.isnan(yc) & torch.isnan(y_cpu))
-                assert diff.float().mean().item() < 2e-3, (M, sb, sigma, inner)
-                rel = ((yc - y_cpu).abs() / y_cpu.abs().clamp_min(1e-30))[diff & (y_cpu != 0)]
-                # a flipped rounding tie moves an element by one quantisation step: those are the "codes differ" cases
-                # counted above; everything else is within the libm noise of the scale tables
-                step_flip = rel > 2.0 ** -(M + 2)
-                assert step_flip.float().sum().item() <= 2e-3 * yc.numel()
-                assert float(rel[~step_flip].max()) < 1e-5 if (~step_flip).any() else True
+                assert torch.equal(torch.isnan(yc), torch.isnan(y_cpu)), (M, sb, sigma, inner)
+                ok = ~torch.isnan(y_cpu)
+                # the two backends' libm round bias / scale tables differently by ulps: floats may
+                # differ within 1e-5 relative anywhere; an element whose CODE flipped (a rounding tie or a binade
+                # switch resolved the other way) moves by a quantisation step -- those must stay below 2e-3 of the tensor
+                flipped = ok & ((yc - y_cpu).abs() > 1e-5 * y_cpu.abs().clamp_min(1e-30))
+                assert flipped.float().mean().item() < 2e-3, (M, sb, sigma, inner, flipped.float().mean().item())
 
 
 def test_survey_size_mse_estimator_vs_reference_golden():
