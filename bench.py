@@ -1187,6 +1187,10 @@ def _main():
                                              "(utils/imagenet_dataloaders.py:66-81) on the device inside the graph "
                                              "(workloads.U8Normalize, bit-identical to torchvision): 4x fewer host-link "
                                              "bytes than feeding normalised fp32 images"},
+                          "e2e_limiter": "fp32-fed: the host link -- every image crosses it as 12 bytes per pixel position (at "
+                                         "N = 8 the channels_last forward would need 330 GB/s of H2D, the box delivers "
+                                         "~180-240 in aggregate); uint8-fed: 3 bytes per pixel position, the loop is "
+                                         "device-bound again (measured 0.94-0.99 of the device-resident rate at N = 8)",
                           "e2e_h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "e2e_d2h_bytes_per_step": B * 1000 * 4,
                           "e2e_note": "workloads.GraphedForward.run_pipelined: images from pinned host memory every step, logits "
                                       "back to pinned host memory; H2D of batch k+1 overlaps the forward of batch k "
