@@ -708,11 +708,18 @@ def leg_reference_gpu_eager(plan, st, dev, steps=3):
 # ---------------------------------------------------------------------------------------------------------
 def main():
     # model constructors print (as the reference's do); stdout carries the ONE JSON line only
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):
+    # (file-descriptor level: NCCL prints its version banner to the C stdout)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
         line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     return 0
 
 
