@@ -63,6 +63,8 @@ def _via_torch(t) -> bool:
 def _torch_call(fn, *args):
     try:
         return fn(*args)
+    except torch.OutOfMemoryError:    # (a RuntimeError subclass: not an argument error, keep its type)
+        raise
     except RuntimeError as exc:       # TORCH_CHECK -> the package's error type
         raise Fp8fqError(str(exc).split("\n")[0]) from None
 

@@ -26,7 +26,8 @@ def functions(so):
     return out
 
 
-def walk(ins, max_steps=20000):
+def walk(ins, max_steps=20000, take=(), trace=None):
+    """``take``: addresses of conditional branches to follow (e.g. the uniform branch that selects the cl_same path)."""
     addr2i = {a: i for i, (a, _) in enumerate(ins)}
     i, n, hist, seen_back = 0, 0, collections.Counter(), False
     while i < len(ins) and n < max_steps:
@@ -35,6 +36,8 @@ def walk(ins, max_steps=20000):
         pred, op, rest = m.group(1), m.group(2), m.group(3)
         n += 1
         hist[op.split(".")[0]] += 1
+        if trace is not None:
+            trace.append((a, text))
         if op.startswith("EXIT") and not pred:
             break
         if op.startswith("BRA"):
@@ -48,7 +51,7 @@ def walk(ins, max_steps=20000):
                 break  # loop back edge: one trip is enough
             region = [x for _, x in ins[i + 1:addr2i[tgt]]]
             slow = any(("MUFU.RCP" in x or re.search(r"\bCALL", x)) for x in region) and not any("STG" in x for x in region)
-            if not cond or slow:
+            if not cond or slow or a in take:
                 i = addr2i[tgt]
                 continue
         i += 1
