@@ -633,8 +633,11 @@ struct StreamMinBlocks {
 #ifndef FQ_MINB_CL
 #define FQ_MINB_CL 5
 #endif
+#ifndef FQ_MINB_CL_K1
+#define FQ_MINB_CL_K1 FQ_MINB_CL   // channel-innermost variants of the K > 3 formats (tuning builds may set it apart)
+#endif
   static constexpr int value =
-      PreTraits<PRE>::kCL ? FQ_MINB_CL
+      PreTraits<PRE>::kCL ? (KMODE == 1 ? FQ_MINB_CL_K1 : FQ_MINB_CL)
       : ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE != 1) ? 6 : 5;
 #endif
 };

@@ -31,7 +31,10 @@ VARIANTS = {"default": [], "round1": ["FP8FQ_FOLD_ACT=0", "FP8FQ_FULL_TILE=0"]}
 VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_pack": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1"],
                "full_cl": ["FP8FQ_FULL_TILE_CL=1"], "full_cl_minb4": ["FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"],
                "all": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1", "FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"]}
-FULL_BENCH = {"default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
+# round 2, third A/B: resident CTAs per SM of the channel-innermost variants (they fit 40 registers since the lane-major
+# batch norm and FOLD_ACT: 6 CTAs/SM instead of 5)
+VARIANTS_R2C = {"cl6": ["FQ_MINB_CL=6"], "cl6_k1": ["FQ_MINB_CL_K1=6"]}
+FULL_BENCH = {"cl6", "cl6_k1", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
 def hash_leg(device="cuda:0"):
@@ -113,6 +116,7 @@ def main():
     variants = dict(VARIANTS)
     if not args.round1_only:
         variants.update(VARIANTS_R2)
+        variants.update(VARIANTS_R2C)
     if args.only:
         variants = {k: v for k, v in variants.items() if k in set(args.only.split(",")) | {"default"}}
     for name, defines in variants.items():
