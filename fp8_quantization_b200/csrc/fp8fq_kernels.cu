@@ -1070,13 +1070,20 @@ struct EstArgs {
   float* maxval_out;
   float* table;  // nullptr -> no fused prologue
   int M, E, K, sign_bits;
+  int64_t C;     // channels (FP8FQ_EST_DP_STATS: cur_max holds 2C entries, the second half the NaN flags)
 };
 
 // estimator update rule for one channel; returns the updated (min, max)
 __device__ __forceinline__ void est_update(const EstArgs& e, int64_t c, float& mn, float& mx) {
-  if (e.est_mode == FP8FQ_EST_DP_STATS) {   // batch statistics for a data-parallel exchange: [-min | max], no state rule
-    e.cur_min[c] = -mn;
-    e.cur_max[c] = mx;
+  if (e.est_mode == FP8FQ_EST_DP_STATS) {
+    // batch statistics for a data-parallel exchange: [-min | max | NaN flag], no state rule.  A MAX all-reduce does not
+    // promise to propagate NaN (torch.min / torch.max do), so a NaN statistic travels as a flag and the value slots
+    // carry the neutral element of MAX; fp8fq_dp_finish_prepare_f32 turns the flag back into NaN.
+    const bool nan = !(mn == mn) || !(mx == mx);
+    const float ninf = __int_as_float(0xff800000);
+    e.cur_min[c] = nan ? ninf : -mn;
+    e.cur_max[c] = nan ? ninf : mx;
+    e.cur_max[e.C + c] = nan ? 1.0f : 0.0f;
     return;
   }
   if (e.initialized && e.est_mode == FP8FQ_EST_ALL) {           // range_estimators.py:96-98
@@ -1277,7 +1284,7 @@ __global__ void __launch_bounds__(128) minmax_rows_kernel(const float* __restric
   }
 }
 
-// Data-parallel calibration, second half: `packed` = [-min (C) | max (C)] of the GLOBAL batch (after the MAX all-reduce
+// Data-parallel calibration, second half: `packed` = [-min (C) | max (C) | NaN flag (C)] of the GLOBAL batch (after the MAX all-reduce
 // of every rank's fp8fq_minmax / bn_act_estimate statistics in mode FP8FQ_EST_DP_STATS).  One CTA per channel: the
 // estimator's update rule on (cur_min, cur_max), set_quant_range and the quantiser table -- what the single-GPU fused
 // calibration launch does after its own reduction.
@@ -1287,6 +1294,7 @@ __global__ void dp_finish_kernel(const float* __restrict__ packed, int64_t C, co
   for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
     if (threadIdx.x == 0) {
       float mn = -packed[c], mx = packed[C + c];
+      if (packed[2 * C + c] > 0.0f) mn = mx = __int_as_float(0x7fc00000);   // some rank saw a NaN
       est_update(est, c, mn, mx);
       const float mv = range_to_maxval(mn, mx);
       if (est.maxval_out != nullptr) est.maxval_out[c] = mv;
@@ -2092,6 +2100,7 @@ static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, floa
   e.w_old = (float)momentum;
   e.maxval_out = maxval_out;
   e.table = nullptr;
+  e.C = C;
   if (fuse) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
     if (r != FP8FQ_OK) return r;
@@ -2157,6 +2166,7 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
   e.w_old = (float)momentum;
   e.maxval_out = maxval_out;
   e.table = nullptr;
+  e.C = 1;
   if (table != nullptr) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
     if (r != FP8FQ_OK) return r;
@@ -2204,6 +2214,7 @@ int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, 
   e.w_old = (float)momentum;
   e.maxval_out = maxval_out;
   e.table = nullptr;
+  e.C = C;
   int threads = 32;
   if (table != nullptr) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);

@@ -12,7 +12,7 @@ from ._lib import Fp8fqError, TensorDesc, check, lib
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 EST_CURRENT, EST_ALL, EST_RUNNING = 0, 1, 2
-EST_DP_STATS = 3   # statistics only, packed as [-min | max] for one MAX all-reduce (fp8fq.h: FP8FQ_EST_DP_STATS)
+EST_DP_STATS = 3   # statistics only, packed as [-min | max | NaN flag] for one MAX all-reduce (fp8fq.h)
 
 
 try:  # raw handle of the current stream without constructing a torch.cuda.Stream (~0.2 us instead of ~2 us)
@@ -588,9 +588,9 @@ def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_m
 def dp_finish_prepare(packed, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float, maxval_out, fmt,
                       table_out):
     """Second half of a data-parallel calibration step (fp8fq_dp_finish_prepare_f32): ``packed`` = the all-reduced
-    [-min (C) | max (C)]; applies the estimator rule to (cur_min, cur_max), set_quant_range and builds the table."""
+    [-min (C) | max (C) | NaN flag (C)]; applies the estimator rule to (cur_min, cur_max), set_quant_range and builds the table."""
     _require(packed, "packed")
-    C = packed.numel() // 2
+    C = packed.numel() // 3
     _require_state(cur_min, C, "cur_min")
     _require_state(cur_max, C, "cur_max")
     mb, nb, sb = fmt

@@ -139,9 +139,14 @@ class _MinMaxEstimator(RangeEstimatorBase):
         C = packed.numel() // 2
         init = self.current_xmin is not None
         bmin, bmax = packed[:C], packed[C:]
-        bmin.neg_()
-        fq_dist.all_reduce_max(packed)  # ONE collective for [-min, max]
-        bmin.neg_()
+        # a MAX all-reduce does not promise to propagate NaN (torch.min / torch.max do): NaN statistics travel as a flag
+        nan = (torch.isnan(bmin) | torch.isnan(bmax)).to(packed.dtype)
+        ninf = torch.full_like(bmin, float("-inf"))
+        wire = torch.cat([torch.where(nan > 0, ninf, -bmin), torch.where(nan > 0, ninf, bmax), nan])
+        fq_dist.all_reduce_max(wire)  # ONE collective for [-min, max, NaN flag]
+        bad = wire[2 * C:] > 0
+        bmin = torch.where(bad, torch.full_like(bmin, float("nan")), -wire[:C])
+        bmax = torch.where(bad, torch.full_like(bmax, float("nan")), wire[C:2 * C])
         if not init or self.EST_MODE == ops.EST_CURRENT:
             self.current_xmin, self.current_xmax = bmin.clone(), bmax.clone()
         elif self.EST_MODE == ops.EST_ALL:
@@ -157,17 +162,17 @@ class _MinMaxEstimator(RangeEstimatorBase):
         return True
 
     def _dp_packed(self, C, device):
-        """Persistent [-min (C) | max (C)] exchange buffer of this estimator (one per estimator: no allocation and no
+        """Persistent [-min (C) | max (C) | NaN flag (C)] exchange buffer of this estimator (one per estimator: no allocation and no
         packing kernels on the calibration path)."""
         buf = self.__dict__.get("_dp_buf")
-        if buf is None or buf.numel() != 2 * C or buf.device != device:
-            buf = self.__dict__["_dp_buf"] = torch.empty(2 * C, dtype=torch.float32, device=device)
+        if buf is None or buf.numel() != 3 * C or buf.device != device:
+            buf = self.__dict__["_dp_buf"] = torch.empty(3 * C, dtype=torch.float32, device=device)
         return buf
 
     def _dp_finish(self, packed, x, quantizer):
         """All-reduce + ONE launch: estimator rule, set_quant_range, table (fp8fq_dp_finish_prepare_f32)."""
-        C = packed.numel() // 2
-        fq_dist.all_reduce_max(packed)            # the one collective: MAX over [-min, max] of every rank's shard
+        C = packed.numel() // 3
+        fq_dist.all_reduce_max(packed)            # the one collective: MAX over [-min, max, NaN flag] of every shard
         cmin, cmax, init = self._state(x)
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
         maxval = torch.empty(C, dtype=torch.float32, device=x.device)

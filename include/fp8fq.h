@@ -57,9 +57,10 @@ extern "C" {
 #define FP8FQ_EST_CURRENT 0 /* CurrentMinMaxEstimator, range_estimators.py:61-76  (overwrite) */
 #define FP8FQ_EST_ALL 1     /* AllMinMaxEstimator,     range_estimators.py:83-100 (running min/max) */
 #define FP8FQ_EST_RUNNING 2 /* RunningMinMaxEstimator, range_estimators.py:108-125 (EMA) */
-#define FP8FQ_EST_DP_STATS 3 /* no update rule: cur_min receives -min and cur_max max of THIS batch -- the packed
-                              * statistics one MAX all-reduce merges across data-parallel ranks; followed
-                              * by fp8fq_dp_finish_prepare_f32 */
+#define FP8FQ_EST_DP_STATS 3 /* no update rule: cur_min [C] receives -min, cur_max [2C] max and, in its second half, a
+                              * NaN flag (1.0 / 0.0; a NaN statistic itself travels as -inf) of THIS batch -- with
+                              * cur_max = cur_min + C that is one packed [3C] buffer which one MAX all-reduce merges
+                              * across data-parallel ranks; followed by fp8fq_dp_finish_prepare_f32 */
 
 /* library / build introspection */
 int fp8fq_version(void);
@@ -256,8 +257,9 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
                                       void* workspace, void* stream);
 
 /* Data-parallel calibration, second half (reference dependency order quantization_manager.py:114-122):
- * packed = [-min (C) | max (C)] of the global batch, i.e. the result of a MAX all-reduce over every rank's statistics
- * (fp8fq_minmax_f32 / fp8fq_bn_act_estimate_prepare_f32 with est_mode FP8FQ_EST_DP_STATS writing into one [2C] buffer).
+ * packed = [-min (C) | max (C) | NaN flag (C)] of the global batch, i.e. the result of a MAX all-reduce over every rank's
+ * statistics (fp8fq_minmax_f32 / fp8fq_bn_act_estimate_prepare_f32 with est_mode FP8FQ_EST_DP_STATS writing into one
+ * [3C] buffer; a set flag makes the range NaN, as torch.min / torch.max of the concatenated batch would be).
  * One launch applies the estimator's update rule to (cur_min, cur_max) -- est_mode CURRENT / ALL / RUNNING as in
  * fp8fq_minmax_f32 --, FPQuantizer.set_quant_range (fp8_quantizer.py:236-237) into maxval_out [C] (may be NULL) and,
  * when table is not NULL, the quantiser table.  Every rank ends with the range a single process would have computed on

@@ -930,16 +930,21 @@ def test_data_parallel_statistics_mode_and_finish_kernel(sim, host_emul, C):
         smin, smax = aligned(C), aligned(C)          # single-process estimator state
         for call in range(3):
             shards = [rand(rng, (C, inner), specials=False) * (call + 1 + r) for r in range(2)]
+            if call == 2:
+                shards[1][C // 2, 7] = np.nan      # one rank sees a NaN in one channel: the global range of it is NaN
             packed = []
             for xs in shards:
                 xs = np.ascontiguousarray(xs)
-                buf = aligned(2 * C)
+                buf = aligned(3 * C)               # [-min | max | NaN flag]
                 assert sim.fp8fq_minmax_f32(P(xs), xs.size, C, inner, P(buf[:C]), P(buf[C:]), EST_DP_STATS, 0, 0.9, P(ws),
                                             None) == 0
-                assert same_bits(buf[:C], -xs.min(1)) and same_bits(buf[C:], xs.max(1))
+                isnan = np.isnan(xs).any(1)
+                assert np.array_equal(buf[2 * C:], isnan.astype(np.float32))
+                assert same_bits(buf[:C][~isnan], -xs.min(1)[~isnan]) and same_bits(buf[C:2 * C][~isnan], xs.max(1)[~isnan])
+                assert np.all(np.isneginf(buf[:C][isnan])) and np.all(np.isneginf(buf[C:2 * C][isnan]))
                 packed.append(buf)
-            merged = aligned(2 * C)
-            merged[:] = np.maximum(packed[0], packed[1])
+            merged = aligned(3 * C)
+            merged[:] = np.fmax(packed[0], packed[1])   # a MAX reduction that DROPS NaN, the worst case NCCL may be
             stride = sim.fp8fq_table_stride(5, 8, 1)
             mv_dp, tab_dp = aligned(C), aligned(stride * C)
             assert sim.fp8fq_dp_finish_prepare_f32(P(merged), C, P(dmin), P(dmax), mode, int(call > 0), 0.9, P(mv_dp), 5, 8, 1,

@@ -31,7 +31,7 @@ ops.estimate_prepare(w, True, cmr, cxr, ops.EST_CURRENT, False, 0.9, mvr, 4.0, 8
 pk = ops.bn_pack(torch.randn(16, device=dev), torch.rand(16, device=dev) + 0.5, None, None, 1e-5)
 for t in (x, xc):
     ops.bn_act_estimate_prepare(t, pk, None, 1, 1, cm, cx, ops.EST_ALL, True, 0.9, mv, (5.0, 8, 1), tb)
-packed = torch.empty(2, device=dev)
+packed = torch.empty(3, device=dev)
 ops.minmax(x, False, packed[:1], packed[1:], ops.EST_DP_STATS, False)
 ops.dp_finish_prepare(packed, cm, cx, ops.EST_ALL, True, 0.9, mv, (5.0, 8, 1), tb)
 for M in (5.0, 3.0):
