@@ -1174,7 +1174,17 @@ def _main():
             workloads.pass_data_for_range_estimation([x_img], m2, True, True, 1)
             m2.fix_ranges()
             other_rec = model_leg(m2, False)
-            del m2
+            # the hot-path step in the other layout too (same sites and element counts, recorded from that network)
+            plan2, st2 = record_hot_path(m2, x_img, ops)
+            g2 = capture_graph(lambda: run_plan(plan2, ops))
+            ms2 = time_ms(g2.replay, args.steps)
+            if world > 1:
+                t2 = torch.tensor([ms2], device=dev)
+                fq_dist.all_reduce_max(t2)
+                ms2 = float(t2.item())
+            other_step = {"memory_format": other_fmt, "ms_per_step": ms2, "value": st2["elems"] * world / (ms2 * 1e-3) / 1e9,
+                          "unit": UNIT, "hbm_gbs_step": (st2["stream_bytes"] + 8 * st2["weight_elems"]) / (ms2 * 1e-3) / 1e9}
+            del m2, plan2, g2
             by = {args.memory_format: main_rec, other_fmt: other_rec}
             model_info = {"resnet18_quantized_img_per_s": main_rec["img_per_s"], "ms_per_forward": main_rec["ms_per_forward"],
                           "memory_format": args.memory_format, "batch_per_gpu": B,
@@ -1187,6 +1197,7 @@ def _main():
                           "weights_cached": main_rec.get("weights_cached"),
                           "other_layout": {"memory_format": other_fmt, "ms_per_forward": other_rec["ms_per_forward"],
                                            "img_per_s": other_rec["img_per_s"]},
+                          "other_layout_step": other_step,
                           "e2e_img_per_s": main_rec["e2e_fp32_fed_img_per_s"],
                           "e2e_u8": {"img_per_s": main_rec["e2e_u8_fed_img_per_s"], "h2d_bytes_per_step": B * 3 * 224 * 224,
                                      "d2h_bytes_per_step": B * 1000 * 4,
@@ -1252,7 +1263,17 @@ def _main():
                    "l2": f"per-step working set {(st['in_bytes'] + st['out_bytes']) / 1e9:.2f} GB >> 126 MB L2; "
                          "every buffer is touched once per step, so no tensor survives in L2 between steps"}),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu_baseline,
-        "model": model_info, "calibration": calibration, "dp_parity": dp_parity, "weights": weights_info,
+        "model": model_info,
+        "img_per_s": None if not model_info or "error" in model_info else {
+            "nchw (reference layout)": model_info["img_per_s_reference_layout_nchw"],
+            "channels_last": model_info["img_per_s_channels_last"],
+            "what": "whole quantised ResNet-18 validate forward, device-resident, all GPUs; host-fed rates under model.*"},
+        "step_by_layout": None if not model_info or "error" in model_info else {
+            args.memory_format + (" (reference layout)" if args.memory_format == "nchw" else ""):
+                {"ms_per_step": ms_per_step, "value": value},
+            model_info["other_layout_step"]["memory_format"] + (" (reference layout)" if model_info["other_layout_step"]["memory_format"] == "nchw" else ""):
+                {"ms_per_step": model_info["other_layout_step"]["ms_per_step"], "value": model_info["other_layout_step"]["value"]}},
+        "calibration": calibration, "dp_parity": dp_parity, "weights": weights_info,
         "configs": configs, "numa": numa, "host_binding": host_binding,
         "hbm_gbs_step": (st["stream_bytes"] + 8 * st["weight_elems"]) / (ms_per_step * 1e-3) / 1e9,
         "parity": {"checker": "oracle (reference ATen op sequence) run on this GPU, tests/test_gpu_model_parity.py: all "
