@@ -623,21 +623,24 @@ struct StreamUnroll {
 
 // Resident CTAs per SM the kernel is compiled for.  Measured (tools/bench_kernels.py, B200, [128,64,112,112]):
 // one-tile CTAs are short lived, so occupancy is what keeps HBM busy -- plain E2M5 5.9 -> 6.5 TB/s going from 4 to
-// 6 CTAs/SM; the two-input variants spill at 6 and are best at 5.  FQ_MINB overrides for tuning builds.
-template <int KMODE, int PRE>
+// 6 CTAs/SM; the two-input variants spill at 6 and are best at 5.  The channel-innermost variants fit 40 registers since
+// the lane-major batch norm and FOLD_ACT: 6 CTAs/SM for the constant-CTA-size instantiations (round 2 A/B,
+// profiles/ab_build_options_r02i.json: BN+ReLU+quant 0.944 -> 0.957, block tail 0.938 -> 0.968 of the HBM peak,
+// channels_last step 0.559 -> 0.552 ms), 5 for the run-time-CTA-size ones (DYN: they spill at 6 and lose 2-4 %).
+// FQ_MINB / FQ_MINB_CL / FQ_MINB_CL_DYN override for tuning builds.
+template <int KMODE, int PRE, bool DYN = false>
 struct StreamMinBlocks {
 #ifdef FQ_MINB
   static constexpr int value = FQ_MINB;
 #else
-  // (the *_CL variants keep the parameters of 4 channels -- up to 16 floats -- live: 5 CTAs/SM = 48 registers)
 #ifndef FQ_MINB_CL
-#define FQ_MINB_CL 5
+#define FQ_MINB_CL 6
 #endif
-#ifndef FQ_MINB_CL_K1
-#define FQ_MINB_CL_K1 FQ_MINB_CL   // channel-innermost variants of the K > 3 formats (tuning builds may set it apart)
+#ifndef FQ_MINB_CL_DYN
+#define FQ_MINB_CL_DYN 5
 #endif
   static constexpr int value =
-      PreTraits<PRE>::kCL ? (KMODE == 1 ? FQ_MINB_CL_K1 : FQ_MINB_CL)
+      PreTraits<PRE>::kCL ? (DYN ? FQ_MINB_CL_DYN : FQ_MINB_CL)
       : ((PRE == PRE_PLAIN || PRE == PRE_AFFINE || PRE == PRE_AFFINE_PL || PRE == PRE_AFFINE_G) && KMODE != 1) ? 6 : 5;
 #endif
 };
@@ -645,7 +648,7 @@ struct StreamMinBlocks {
 // DYN: the CTA size is a launch parameter (channel-innermost variants whose channel count does not divide
 // kThreads * VEC); everywhere else it is the compile-time kThreads, which keeps the index arithmetic constant-folded.
 template <int KMODE, int PRE, int VEC, bool CODES, int BNM, bool DYN = false>
-__global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE>::value) fq_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::value) fq_stream_kernel(const StreamArgs a) {
   constexpr bool kTail = PreTraits<PRE>::kTail;
   constexpr bool kPerLane = PreTraits<PRE>::kPerLane;
   constexpr bool kLocalRows = PreTraits<PRE>::kLocalRows;
@@ -1611,7 +1614,7 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
       int nb = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, kThreads, 0) !=
           cudaSuccess || nb < 1)
-        nb = StreamMinBlocks<KMODE, PRE>::value;
+        nb = StreamMinBlocks<KMODE, PRE, DYN>::value;
       return nb;
     }();
     const int64_t wave = (int64_t)sm_count() * resident;

@@ -31,10 +31,10 @@ VARIANTS = {"default": [], "round1": ["FP8FQ_FOLD_ACT=0", "FP8FQ_FULL_TILE=0"]}
 VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_pack": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1"],
                "full_cl": ["FP8FQ_FULL_TILE_CL=1"], "full_cl_minb4": ["FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"],
                "all": ["FP8FQ_PIN_SEL=1", "FP8FQ_PACK2=1", "FP8FQ_FULL_TILE_CL=1", "FQ_MINB_CL=4"]}
-# round 2, third A/B: resident CTAs per SM of the channel-innermost variants (they fit 40 registers since the lane-major
-# batch norm and FOLD_ACT: 6 CTAs/SM instead of 5)
-VARIANTS_R2C = {"cl6": ["FQ_MINB_CL=6"], "cl6_k1": ["FQ_MINB_CL_K1=6"]}
-FULL_BENCH = {"cl6", "cl6_k1", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
+# round 2, third A/B (profiles/ab_build_options_r02i.json): resident CTAs per SM of the channel-innermost variants -- 6 for
+# the constant-CTA-size instantiations became the default; "cl5" is the previous setting, "cl6_dyn" also the DYN ones at 6
+VARIANTS_R2C = {"cl5": ["FQ_MINB_CL=5"], "cl6_dyn": ["FQ_MINB_CL_DYN=6"]}
+FULL_BENCH = {"cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
 def hash_leg(device="cuda:0"):
