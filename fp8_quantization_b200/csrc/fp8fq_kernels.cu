@@ -1967,6 +1967,16 @@ static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* 
   // wider layers (Cbn / VEC > kThreads) keep kThreads and look the channel up per vector
   const int64_t lanes = Cbn / (v4 ? 4 : 1);
   a.threads = lanes <= kThreads ? (int)((kThreads / lanes) * lanes) : kThreads;
+  // FP8FQ_CL_WARP_THREADS=1 (experiment): prefer a CTA size that is also a whole number of warps when one of at least 128
+  // threads exists (C = 96 -> 192 instead of 240 threads: no half-empty warp)
+  static const bool warp_env = [] {
+    const char* e = getenv("FP8FQ_CL_WARP_THREADS");
+    return e && e[0] == '1';
+  }();
+  if (warp_env && lanes <= kThreads && a.threads % 32 != 0) {
+    for (int64_t t = (kThreads / lanes) * lanes; t >= 128; t -= lanes)
+      if (t % 32 == 0) { a.threads = (int)t; break; }
+  }
   a.cl_same = ((int64_t)a.threads * (v4 ? 4 : 1)) % Cbn == 0 ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (table2 != nullptr) return v4 ? launch_stream<PRE_BNQ_ADD_CL, 4>(a, st) : launch_stream<PRE_BNQ_ADD_CL, 1>(a, st);

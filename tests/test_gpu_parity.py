@@ -287,6 +287,12 @@ def test_survey_size_cases_kernel_vs_oracle_on_gpu_and_cpu(M):
                 # differ within 1e-5 relative anywhere; an element whose CODE flipped (a rounding tie or a binade
                 # switch resolved the other way) moves by a quantisation step -- those must stay below 2e-3 of the tensor
                 flipped = ok & ((yc - y_cpu).abs() > 1e-5 * y_cpu.abs().clamp_min(1e-30))
+                if 8 - sb - M == 0:
+                    # E = 0 formats: the top code is maxval / s = 2^M - 1/2, so every CLIPPED element sits exactly on a
+                    # rounding tie and the two backends' last-bit difference in s decides it (the reference
+                    # run with --cuda differs from its own CPU run on exactly these elements: P1 above is that statement)
+                    mvb = oq.maxval.view([-1] + [1] * (x.dim() - 1)) if pc else oq.maxval
+                    flipped = flipped & (x.abs() < mvb)
                 assert flipped.float().mean().item() < 2e-3, (M, sb, sigma, inner, flipped.float().mean().item())
 
 
