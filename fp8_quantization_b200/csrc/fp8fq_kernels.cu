@@ -1967,11 +1967,12 @@ static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* 
   // wider layers (Cbn / VEC > kThreads) keep kThreads and look the channel up per vector
   const int64_t lanes = Cbn / (v4 ? 4 : 1);
   a.threads = lanes <= kThreads ? (int)((kThreads / lanes) * lanes) : kThreads;
-  // FP8FQ_CL_WARP_THREADS=1 (experiment): prefer a CTA size that is also a whole number of warps when one of at least 128
-  // threads exists (C = 96 -> 192 instead of 240 threads: no half-empty warp)
+  // ... preferring one that is also a whole number of warps when such a size of at least 128 threads exists (C = 96 or
+  // 192 -> 192 threads instead of 240: no half-empty warp; measured +3..5 % at those sites, profiles/cl_shapes_r02.json;
+  // FP8FQ_CL_WARP_THREADS=0 restores the largest fitting size)
   static const bool warp_env = [] {
     const char* e = getenv("FP8FQ_CL_WARP_THREADS");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   if (warp_env && lanes <= kThreads && a.threads % 32 != 0) {
     for (int64_t t = (kThreads / lanes) * lanes; t >= 128; t -= lanes)

@@ -13,6 +13,7 @@ Parity statement (measured on the B200):
        percent of arguments, which moves ~1e-5 of the elements across a rounding tie).  The test asserts
        that our mismatch set is exactly the set on which torch-CUDA-eager itself differs from torch-CPU.
 """
+import numpy as np
 import pytest
 import torch
 
