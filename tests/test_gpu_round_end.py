@@ -1,9 +1,10 @@
-"""GPU: cases written after round 1's GPU budget was spent, so their first run on a device is the driver's round-end
-run.  Kept in their own module, collected after the other GPU modules (whose every test has run green on a B200).
+"""GPU: cases added late in a round (their first run on a device used to be the driver's round-end run; all of them have
+since run green on a B200).  Kept in their own module, collected after the other GPU modules.
   * next row f5 -- the empirical flow of compute_quant_error.py (workloads.compute_quant_error_empirical) against the
     real reference's golden vectors (tests/golden/quant_error.npz, made by tests/golden/make_golden_quant_error.py);
-  * row a1 by name -- quantize_to_fp8_ste_MM(x, n_bits, maxval, num_mantissa_bits, sign_bits), the functional form.
-Both also run on the host simulation in tests/test_host_sim_models.py."""
+  * row a1 by name -- quantize_to_fp8_ste_MM(x, n_bits, maxval, num_mantissa_bits, sign_bits), the functional form;
+  * round 2 -- the uint8 input path (ToTensor + Normalize on the device) and the torch-registered operator binding.
+The first two also run on the host simulation in tests/test_host_sim_models.py."""
 import numpy as np
 import pytest
 import torch

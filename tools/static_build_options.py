@@ -1,7 +1,8 @@
 """Static comparison (no GPU) of the default build with the product's build options (csrc/fp8fq_kernels.cu):
   fold_act  : -DFP8FQ_FOLD_ACT=1   ReLU / ReLU6 folded into the quantiser's clamp bounds
   full_tile : -DFP8FQ_FULL_TILE=1  second, predicate-free instantiation of the stream kernel's tile body for full tiles
-  both      : the two together
+  both      : the two together (the default build since round 2);  neither: the round-1 default
+(executed fast-path instruction counts: tools/sass_fast_path.py)
 Per fq_stream_kernel instantiation: registers, spill bytes, static SASS instruction count, FMNMX count, and the size of
 each TILE BODY (from the first 128-bit data load of a body to its last 128-bit store; a build with full_tile has two
 bodies, the first being the predicate-free one that every tile but the last executes).  Static sizes include the
@@ -73,7 +74,10 @@ def demangle(names):
     return [re.sub(r"\(anonymous namespace\)::|\(.*$", "", n) for n in p.stdout.split("\n")]
 
 
-variants = {"default": [], "fold_act": ["-DFP8FQ_FOLD_ACT=1"], "full_tile": ["-DFP8FQ_FULL_TILE=1"],
+# explicit flags for every variant, so that the table means the same whatever the product's current defaults are
+# (round 1: both off; since round 2: both on)
+variants = {"default": [], "neither": ["-DFP8FQ_FOLD_ACT=0", "-DFP8FQ_FULL_TILE=0"],
+            "fold_act": ["-DFP8FQ_FOLD_ACT=1", "-DFP8FQ_FULL_TILE=0"], "full_tile": ["-DFP8FQ_FOLD_ACT=0", "-DFP8FQ_FULL_TILE=1"],
             "both": ["-DFP8FQ_FOLD_ACT=1", "-DFP8FQ_FULL_TILE=1"]}
 built = {v: build(flags, f"/tmp/libfp8fq_opt_{v}.so") for v, flags in variants.items()}
 names = sorted(built["default"])
