@@ -1557,11 +1557,11 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
         int32_t cd[4];
         if (guarded) quant_vec<KMODE, false, 4, true, true>(vi, ctx, yo, cd);
         else quant_vec<KMODE, false, 4, true, false>(vi, ctx, yo, cd);
+        float d[4];
+        sub2_rn(vi[0], vi[1], yo[0], yo[1], d[0], d[1]);   // (two-wide under FP8FQ_PACK2; same roundings, same order of
+        sub2_rn(vi[2], vi[3], yo[2], yo[3], d[2], d[3]);   //  accumulation either way)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float d = sub_rn(vi[k], yo[k]);
-          err = fmaf(d, d, err);
-        }
+        for (int k = 0; k < 4; ++k) err = fmaf(d[k], d[k], err);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);

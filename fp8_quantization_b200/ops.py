@@ -49,7 +49,13 @@ def torch_binding():
         path = os.path.join(_HERE, "libfp8fq_torch.so")
         if (os.environ.get("FP8FQ_BINDING", "torch") == "torch" and not os.environ.get("FP8FQ_LIB")
                 and os.path.exists(path)):
-            torch.ops.load_library(path)
+            try:
+                torch.ops.load_library(path)
+            except (OSError, RuntimeError) as exc:   # e.g. built against another torch: the ctypes binding of the SAME
+                import warnings                       # kernels takes over (this is a choice of binding, not of path)
+
+                warnings.warn(f"libfp8fq_torch.so could not be loaded ({exc}); using the ctypes binding of libfp8fq.so")
+                return None
             if torch.ops.fp8fq.abi_version() != lib().fp8fq_version():
                 raise Fp8fqError("libfp8fq_torch.so and libfp8fq.so disagree about the ABI version: rebuild both")
             _torch_ops = torch.ops.fp8fq

@@ -76,3 +76,30 @@ def test_cpu_tensors_are_rejected_loudly(built):
     est = fq.CurrentMinMaxEstimator()
     with pytest.raises(fq.Fp8fqError):
         est(torch.randn(16))
+
+
+def test_torch_operator_library_loads_and_refuses_cpu_tensors(built):
+    """libfp8fq_torch.so (csrc/fp8fq_torch.cpp, TORCH_LIBRARY(fp8fq, ...)): builds here without a GPU, registers the
+    hot-path operators with the schemas the Python layer calls, agrees with libfp8fq.so about the ABI version, and --
+    like every other entry into the library -- refuses CPU tensors instead of computing anything."""
+    import pytest
+    import torch
+
+    import fp8_quantization_b200 as fq
+    from fp8_quantization_b200 import ops
+
+    T = ops.torch_binding()
+    assert T is not None and T.abi_version() == fq.lib().fp8fq_version()
+    for name in ("fake_quant", "fake_quant_multi", "bn_act_quant", "add_act_quant", "bn_quant_add_act_quant", "minmax",
+                 "estimate_prepare", "bn_act_estimate_prepare"):
+        assert hasattr(T, name), name
+    x, table = torch.zeros(8), torch.zeros(64)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        T.fake_quant(x, table, 1, 5.0, 8, 1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        T.add_act_quant(x, x, 1, table, 5.0, 8, 1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        T.bn_act_quant(x.view(1, 8), table, None, 1, table, 5.0, 8, 1, 0)
+    # the package's own wrapper takes the ctypes route for CPU tensors and fails there with its own error type
+    with pytest.raises(fq.Fp8fqError):
+        ops.fake_quant(x, table, 1, 5.0, 8, 1)
