@@ -476,14 +476,39 @@ def calibration_leg(model, x_img, workloads, fq_dist, world, reps=3):
     out = {"batches": 1, "batch_per_gpu": int(x_img.shape[0]), "mode": "eager launches (not graph-captured)"}
     if world > 1:
         ms_local, _ = run(False)
-        ms_dp, n_ar = run(True)        # last: the ranges left behind are the data-parallel (global-batch) ones
-        t = torch.tensor([ms_dp, ms_local], device=x_img.device)
+        fq_dist.enable(True)
+        px = fq_dist.peer_exchange(x_img.device) if x_img.is_cuda else None   # (collective: set up on first use)
+        # the NCCL route: statistics launch, one MAX all-reduce of [-min, max, NaN flag], finishing launch, per site
+        saved = fq_dist._peer_exchange
+        fq_dist._peer_exchange = None
+        try:
+            ms_nccl, n_ar = run(True)
+        finally:
+            fq_dist._peer_exchange = saved
+        t = torch.tensor([ms_nccl, ms_local], device=x_img.device)
         fq_dist.all_reduce_max(t)
-        ms_dp, ms_local = t.tolist()
-        out.update({"ms": ms_dp, "ms_without_collectives": ms_local, "allreduces": n_ar,
-                    "us_per_allreduce": (ms_dp - ms_local) * 1e3 / max(n_ar, 1),
-                    "collective": "NCCL MAX all-reduce of packed [-min, max], one per activation quantiser, issued "
-                                  "before set_quant_range of that layer (quantization_manager.py:114-122 dependency order)"})
+        ms_nccl, ms_local = t.tolist()
+        out.update({"ms_without_collectives": ms_local, "sites_exchanging": n_ar,
+                    "nccl_path": {"ms": ms_nccl, "allreduces": n_ar, "us_per_allreduce": (ms_nccl - ms_local) * 1e3 / max(n_ar, 1),
+                                  "what": "statistics launch + NCCL MAX all-reduce of packed [-min, max, NaN flag] + finishing "
+                                          "launch per activation quantiser, issued before set_quant_range of that layer "
+                                          "(quantization_manager.py:114-122 dependency order)"}})
+        if px is not None:
+            # the default route: the exchange happens INSIDE the statistics kernel over NVLink peer memory -- one launch
+            # per site, no collective call (include/fp8fq.h: fp8fq_estimate_prepare_p2p_f32)
+            e0 = px.epoch
+            ms_p2p, n_left = run(True)  # last: the ranges left behind are the data-parallel (global-batch) ones
+            t = torch.tensor([ms_p2p], device=x_img.device)
+            fq_dist.all_reduce_max(t)
+            ms_p2p = float(t.item())
+            n_x = (px.epoch - e0) // reps
+            out.update({"ms": ms_p2p, "path": "peer-memory exchange fused into the statistics kernel (NVLink P2P stores, no NCCL)",
+                        "exchanges": n_x, "allreduces": n_left, "us_per_exchange": (ms_p2p - ms_local) * 1e3 / max(n_x, 1),
+                        "us_per_allreduce": (ms_nccl - ms_local) * 1e3 / max(n_ar, 1)})
+        else:
+            ms_dp, _ = run(True)
+            out.update({"ms": ms_nccl, "path": "NCCL all-reduce (peer-memory exchange unavailable on this box)",
+                        "allreduces": n_ar, "us_per_allreduce": (ms_nccl - ms_local) * 1e3 / max(n_ar, 1)})
     else:
         ms, _ = run(False)
         out.update({"ms": ms, "allreduces": 0, "us_per_allreduce": None})
@@ -506,6 +531,20 @@ def dp_parity_leg(model, x_img, build_model, memory_format, fq, workloads, fq_di
     xs = [torch.empty_like(x_img) for _ in range(world)]
     td.all_gather(xs, x_img.contiguous())
     out = {"ranges": len(names), "range_floats": int(flat.numel()), "bit_equal_across_ranks": bool(across)}
+    if fq_dist.peer_exchange(x_img.device) is not None:
+        # the peer-memory route must give the ranges of the NCCL route, bit for bit: calibrate a fresh model through NCCL
+        saved = fq_dist._peer_exchange
+        fq_dist._peer_exchange = None
+        try:
+            m_nccl = build_model(memory_format)
+            workloads.pass_data_for_range_estimation([x_img], m_nccl, True, True, 1)
+            flat_nccl = torch.cat([r for _, r in model_ranges(m_nccl, fq)]).contiguous()
+            del m_nccl
+        finally:
+            fq_dist._peer_exchange = saved
+        same = torch.tensor([int(torch.equal(flat.view(torch.int32), flat_nccl.view(torch.int32)))], device=x_img.device)
+        td.all_reduce(same, op=td.ReduceOp.MIN)
+        out["peer_memory_route_equals_nccl_route"] = bool(int(same.item()))
     if rank == 0:
         fq_dist.enable(False)
         try:

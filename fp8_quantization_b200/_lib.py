@@ -74,6 +74,14 @@ SIGNATURES["fp8fq_u8_normalize_nchw_f32"] = (_c_i, [_c_p, _c_p, _c_p, _c_l, _c_l
 
 SIGNATURES["fp8fq_dp_finish_prepare_f32"] = (_c_i, [_c_p, _c_l, _c_p, _c_p, _c_i, _c_i, _c_d, _c_p, _c_f, _c_i, _c_i, _c_p, _c_p])
 
+_c_u = ctypes.c_uint
+SIGNATURES["fp8fq_dp_exchange_words"] = (_c_l, [_c_i])
+SIGNATURES["fp8fq_estimate_prepare_p2p_f32"] = (_c_i, [_c_p, _c_l, _c_p, _c_p, _c_i, _c_i, _c_d, _c_p, _c_f, _c_i, _c_i, _c_p, _c_p,
+                                                      _c_p, _c_i, _c_i, _c_u, _c_p])
+SIGNATURES["fp8fq_bn_act_estimate_prepare_p2p_f32"] = (_c_i, [_c_p, _c_l, _c_l, _c_l, _c_i, _c_p, _c_p, _c_i, _c_i, _c_p, _c_p,
+                                                             _c_i, _c_i, _c_d, _c_p, _c_f, _c_i, _c_i, _c_p, _c_p, _c_p, _c_i,
+                                                             _c_i, _c_u, _c_p])
+
 _lib = None
 
 

@@ -1076,7 +1076,84 @@ struct EstArgs {
   float* table;  // nullptr -> no fused prologue
   int M, E, K, sign_bits;
   int64_t C;     // channels (FP8FQ_EST_DP_STATS: cur_max holds 2C entries, the second half the NaN flags)
+  // data-parallel exchange over peer memory (world > 1): every rank's exchange buffer, this rank, the call's epoch
+  unsigned long long* const* peers;
+  int rank, world;
+  unsigned int epoch;
 };
+
+// ---- data-parallel statistics exchange over NVLink peer memory ------------------------------------------------------
+// The calibration step of a batch-sharded run is "local statistics -> MAX over the ranks -> estimator rule ->
+// set_quant_range -> table" (dependency order of quantization_manager.py:114-122).  With NCCL that is
+// statistics kernel + all-reduce + finishing kernel, ~33 us per site of which the reduction of 12 bytes is almost all
+// latency.  Here the LAST CTA of the statistics kernel does the exchange itself: it stores its three values
+// (-min, max, NaN flag) into every peer's exchange buffer with 64-bit system-scope stores -- value in the low word, the
+// call's epoch in the high word, so data and "ready" flag arrive in one single-copy-atomic access, as in NCCL's LL
+// protocol -- polls its own buffer until every peer's words carry this epoch, takes the MAX and goes on to the estimator
+// rule and the table build: ONE launch per site, no collective call.  Buffers: kXchgSlots x world x 3 words per rank,
+// slot = epoch % kXchgSlots (a rank can run at most one call ahead of the slowest peer, so 2 slots would do), allocated
+// as symmetric memory by the host (torch.distributed._symmetric_memory) and zeroed once; epochs start at 1.
+constexpr int kXchgSlots = 4;
+constexpr int kXchgMaxWorld = 16;
+constexpr long long kXchgTimeoutClocks = 6000000000ll;   // ~3 s at 1.9 GHz: a peer that never arrives poisons the range with NaN
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+#ifndef FP8FQ_HOST_SIM
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+#ifndef FP8FQ_HOST_SIM
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+#endif
+}
+
+// All threads of the (last) CTA call it; thread 0 brings this rank's (mn, mx) and leaves with the global ones.
+__device__ __forceinline__ void peer_exchange_minmax(const EstArgs& e, float& mn, float& mx) {
+  __shared__ float s_loc[3];
+  __shared__ float s_all[3 * kXchgMaxWorld];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    const bool nan = !(mn == mn) || !(mx == mx);
+    const float ninf = __int_as_float(0xff800000);
+    s_loc[0] = nan ? ninf : -mn;
+    s_loc[1] = nan ? ninf : mx;
+    s_loc[2] = nan ? 1.0f : 0.0f;
+  }
+  __syncthreads();
+  const int nw = e.world * 3;
+  if (tid < nw) {
+    const int peer = tid / 3, j = tid - peer * 3;
+    const size_t slot = (size_t)(e.epoch % kXchgSlots) * (size_t)e.world * 3;
+    st_sys_u64(e.peers[peer] + slot + (size_t)e.rank * 3 + j,
+               ((unsigned long long)e.epoch << 32) | (unsigned long long)f2u(s_loc[j]));
+    const unsigned long long* src = e.peers[e.rank] + slot + (size_t)peer * 3 + j;
+    unsigned long long got = ld_sys_u64(src);
+#ifndef FP8FQ_HOST_SIM
+    const long long t0 = clock64();
+    while ((unsigned int)(got >> 32) != e.epoch && clock64() - t0 < kXchgTimeoutClocks) got = ld_sys_u64(src);
+#endif
+    s_all[tid] = (unsigned int)(got >> 32) == e.epoch ? u2f((uint32_t)got) : __int_as_float(0x7fc00000);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = s_all[0], b = s_all[1], f = s_all[2];
+    for (int p = 1; p < e.world; ++p) {
+      a = max_nan(a, s_all[3 * p]);
+      b = max_nan(b, s_all[3 * p + 1]);
+      f = max_nan(f, s_all[3 * p + 2]);
+    }
+    if (!(f <= 0.0f)) a = b = __int_as_float(0x7fc00000);   // a NaN somewhere (or a peer that never arrived)
+    mn = -a;
+    mx = b;
+  }
+}
 
 // estimator update rule for one channel; returns the updated (min, max)
 __device__ __forceinline__ void est_update(const EstArgs& e, int64_t c, float& mn, float& mx) {
@@ -1130,6 +1207,7 @@ __device__ __forceinline__ void minmax_tensor_finish(float mn, float mx, float* 
   }
   block_minmax(mn, mx);
   __shared__ float s_mv;
+  if (est.world > 1) peer_exchange_minmax(est, mn, mx);   // data-parallel: MAX over the ranks, inside this launch
   if (threadIdx.x == 0) {
     *counter = 0u;  // leave the workspace ready for the next call
     est_update(est, 0, mn, mx);
@@ -2103,9 +2181,30 @@ int fp8fq_u8_normalize_nchw_f32(const uint8_t* x, const float* lut, float* y, in
 
 int64_t fp8fq_minmax_workspace_bytes(void) { return 16384; }
 
+namespace {
+struct Xchg {   // data-parallel exchange over peer memory (peer_exchange_minmax); world <= 1: none
+  const void* peers = nullptr;
+  int rank = 0, world = 1;
+  unsigned int epoch = 0;
+};
+int check_xchg(const Xchg& xc, int64_t C) {
+  if (xc.world <= 1) return FP8FQ_OK;
+  if (xc.peers == nullptr || xc.rank < 0 || xc.rank >= xc.world || xc.epoch == 0) return FP8FQ_ERR_BAD_ARG;
+  if (xc.world > kXchgMaxWorld || C != 1) return FP8FQ_ERR_UNSUPPORTED;   // per-tensor statistics only
+  return FP8FQ_OK;
+}
+void set_xchg(EstArgs& e, const Xchg& xc) {
+  e.peers = reinterpret_cast<unsigned long long* const*>(xc.peers);
+  e.rank = xc.rank;
+  e.world = xc.world > 1 ? xc.world : 1;
+  e.epoch = xc.epoch;
+}
+}  // namespace
+
 static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, float* cur_min, float* cur_max,
                        int est_mode, int initialized, double momentum, float* maxval_out, bool fuse,
-                       float mantissa_bits, int n_bits, int sign_bits, float* table, void* workspace, void* stream) {
+                       float mantissa_bits, int n_bits, int sign_bits, float* table, void* workspace, void* stream,
+                       const Xchg& xc = Xchg()) {
   if (n < 1 || C < 1 || inner < 1 || n != C * inner) return FP8FQ_ERR_BAD_ARG;
   if (x == nullptr || cur_min == nullptr || cur_max == nullptr) return FP8FQ_ERR_BAD_ARG;
   if (est_mode < 0 || est_mode > FP8FQ_EST_DP_STATS) return FP8FQ_ERR_BAD_ARG;
@@ -2117,6 +2216,12 @@ static int minmax_impl(const float* x, int64_t n, int64_t C, int64_t inner, floa
   e.maxval_out = maxval_out;
   e.table = nullptr;
   e.C = C;
+  {
+    const int r = check_xchg(xc, C);
+    if (r != FP8FQ_OK) return r;
+    if (xc.world > 1 && est_mode == FP8FQ_EST_DP_STATS) return FP8FQ_ERR_BAD_ARG;
+    set_xchg(e, xc);
+  }
   if (fuse) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
     if (r != FP8FQ_OK) return r;
@@ -2159,11 +2264,11 @@ int fp8fq_estimate_prepare_f32(const float* x, int64_t n, int64_t C, int64_t inn
                      mantissa_bits, n_bits, sign_bits, table, workspace, stream);
 }
 
-int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
-                                      const float* bn_scale, const float* bn_shift, int bn_mode, int act,
-                                      float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
-                                      float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
-                                      void* workspace, void* stream) {
+static int bn_act_estimate_impl(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                void* workspace, void* stream, const Xchg& xc) {
   if (outer < 1 || hw < 1 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1 || est_mode < 0 ||
       est_mode > FP8FQ_EST_DP_STATS)
     return FP8FQ_ERR_BAD_ARG;
@@ -2183,6 +2288,12 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
   e.maxval_out = maxval_out;
   e.table = nullptr;
   e.C = 1;
+  {
+    const int r = check_xchg(xc, 1);
+    if (r != FP8FQ_OK) return r;
+    if (xc.world > 1 && est_mode == FP8FQ_EST_DP_STATS) return FP8FQ_ERR_BAD_ARG;
+    set_xchg(e, xc);
+  }
   if (table != nullptr) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);
     if (r != FP8FQ_OK) return r;
@@ -2219,6 +2330,45 @@ int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw,
   return launch_status();
 }
 
+int fp8fq_bn_act_estimate_prepare_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                      const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                      float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                      float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                      void* workspace, void* stream) {
+  return bn_act_estimate_impl(x, outer, hw, Cbn, nhwc, bn_scale, bn_shift, bn_mode, act, cur_min, cur_max, est_mode,
+                              initialized, momentum, maxval_out, mantissa_bits, n_bits, sign_bits, table, workspace, stream,
+                              Xchg());
+}
+
+int64_t fp8fq_dp_exchange_words(int world) {
+  return (world < 1 || world > kXchgMaxWorld) ? FP8FQ_ERR_UNSUPPORTED : (int64_t)kXchgSlots * world * 3;
+}
+
+int fp8fq_estimate_prepare_p2p_f32(const float* x, int64_t n, float* cur_min, float* cur_max, int est_mode, int initialized,
+                                   double momentum, float* maxval_out, float mantissa_bits, int n_bits, int sign_bits,
+                                   float* table, void* workspace, const void* peer_bufs, int rank, int world,
+                                   unsigned int epoch, void* stream) {
+  Xchg xc;
+  xc.peers = peer_bufs; xc.rank = rank; xc.world = world; xc.epoch = epoch;
+  if (world < 2) return FP8FQ_ERR_BAD_ARG;
+  return minmax_impl(x, n, 1, n, cur_min, cur_max, est_mode, initialized, momentum, maxval_out, table != nullptr,
+                     mantissa_bits, n_bits, sign_bits, table, workspace, stream, xc);
+}
+
+int fp8fq_bn_act_estimate_prepare_p2p_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                          const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                          float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                          float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                          void* workspace, const void* peer_bufs, int rank, int world, unsigned int epoch,
+                                          void* stream) {
+  Xchg xc;
+  xc.peers = peer_bufs; xc.rank = rank; xc.world = world; xc.epoch = epoch;
+  if (world < 2) return FP8FQ_ERR_BAD_ARG;
+  return bn_act_estimate_impl(x, outer, hw, Cbn, nhwc, bn_scale, bn_shift, bn_mode, act, cur_min, cur_max, est_mode,
+                              initialized, momentum, maxval_out, mantissa_bits, n_bits, sign_bits, table, workspace, stream,
+                              xc);
+}
+
 int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, float* cur_max, int est_mode,
                                 int initialized, double momentum, float* maxval_out, float mantissa_bits, int n_bits,
                                 int sign_bits, float* table, void* stream) {
@@ -2231,6 +2381,7 @@ int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, 
   e.maxval_out = maxval_out;
   e.table = nullptr;
   e.C = C;
+  set_xchg(e, Xchg());
   int threads = 32;
   if (table != nullptr) {
     int r = check_format(mantissa_bits, n_bits, sign_bits, &e.M, &e.E, &e.K);

@@ -74,6 +74,69 @@ def all_reduce_mean(t: torch.Tensor):
     return t
 
 
+class PeerExchange:
+    """Exchange buffers for the calibration statistics over NVLink peer memory (include/fp8fq.h:
+    fp8fq_estimate_prepare_p2p_f32): one small symmetric-memory buffer per rank, every rank holding a device array of all
+    ranks' buffer addresses.  ``next()`` hands out the (pointers, rank, world, epoch) tuple of the next exchange; every
+    rank must issue the same sequence of exchanges (the calibration forward is SPMD, so it does)."""
+
+    def __init__(self, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import lib
+
+        self.rank, self.world = td.get_rank(), td.get_world_size()
+        words = int(lib().fp8fq_dp_exchange_words(self.world))
+        if words <= 0:
+            raise RuntimeError(f"peer exchange supports at most 16 ranks, got {self.world}")
+        self.buf = symm_mem.empty(words, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, td.group.WORLD)     # collective: exchanges the memory handles
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        td.barrier()                    # nobody writes into a buffer that its owner has not zeroed yet
+        self.epoch = 0
+
+    def next(self):
+        self.epoch += 1
+        return self.ptrs, self.rank, self.world, self.epoch
+
+    def unused(self):
+        """The exchange handed out last did not take place (the same decision on every rank): give its epoch back."""
+        self.epoch -= 1
+
+
+_peer_exchange = None
+_peer_exchange_tried = False
+
+
+def peer_exchange(device=None):
+    """The process-wide PeerExchange when the calibration collectives are active on NCCL / CUDA and symmetric memory
+    could be set up on EVERY rank (the decision is all-reduced, so that no rank waits in a kernel for a peer that took
+    the NCCL route); None otherwise -- the estimators then use the all-reduce path.  FP8FQ_DP_P2P=0 forces NCCL."""
+    global _peer_exchange, _peer_exchange_tried
+    if not active():
+        return None
+    if not _peer_exchange_tried:
+        _peer_exchange_tried = True
+        ok, px = 0, None
+        if (os.environ.get("FP8FQ_DP_P2P", "1") != "0" and torch.cuda.is_available() and td.get_backend() == "nccl"
+                and device is not None and device.type == "cuda" and td.get_world_size() <= 16):
+            try:
+                px = PeerExchange(device)
+                ok = 1
+            except Exception as exc:   # no P2P between the GPUs, symmetric memory unavailable in this build, ...
+                import warnings
+
+                warnings.warn(f"peer-memory exchange unavailable ({exc!r}); calibration statistics go through NCCL")
+        if torch.cuda.is_available() and td.get_backend() == "nccl" and device is not None and device.type == "cuda":
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            td.all_reduce(flag, op=td.ReduceOp.MIN)
+            ok = int(flag.item())
+        _peer_exchange = px if ok else None
+    return _peer_exchange
+
+
 def barrier():
     if td.is_available() and td.is_initialized():
         td.barrier()

@@ -591,6 +591,54 @@ def bn_act_estimate_prepare(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_m
     return True
 
 
+def estimate_prepare_p2p(x, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float, maxval_out, fmt, table_out,
+                         xchg):
+    """Per-tensor calibration step of a data-parallel run in ONE launch: local statistics, MAX over the ranks through
+    NVLink peer memory (no collective call), estimator rule, set_quant_range, table (fp8fq_estimate_prepare_p2p_f32).
+    ``xchg`` = (device tensor of the ranks' exchange-buffer pointers, rank, world, epoch): dist.PeerExchange.next()."""
+    _require(x, "x")
+    ptrs, rank, world, epoch = xchg
+    mb, nb, sb = fmt
+    _require_state(cur_min, 1, "cur_min")
+    _require_state(cur_max, 1, "cur_max")
+    _require_state(maxval_out, 1, "maxval_out")
+    _require_table(table_out, 1, mb, nb, sb, "table_out")
+    check(lib().fp8fq_estimate_prepare_p2p_f32(x.data_ptr(), x.numel(), cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode),
+                                               1 if initialized else 0, float(momentum), maxval_out.data_ptr(), float(mb),
+                                               int(nb), int(sb), table_out.data_ptr(), _workspace(x.device).data_ptr(),
+                                               ptrs.data_ptr(), int(rank), int(world), int(epoch), _stream()),
+          "fp8fq_estimate_prepare_p2p_f32")
+    return maxval_out, table_out
+
+
+def bn_act_estimate_prepare_p2p(x, bn_scale, bn_shift, act: int, bn_mode: int, cur_min, cur_max, est_mode: int,
+                                initialized: bool, momentum: float, maxval_out, fmt, table_out, xchg) -> bool:
+    """The BN-fused twin (fp8fq_bn_act_estimate_prepare_p2p_f32): statistics of act(bn(x)) without materialising it, the
+    exchange over peer memory, range and table -- one launch.  False when the shape is not covered by the fused kernel
+    (decided from the shape alone, hence identically on every rank; the exchange epoch is then not consumed)."""
+    _require(x, "x")
+    if x.numel() >= MAX_FUSED_ELEMS:
+        return False
+    ptrs, rank, world, epoch = xchg
+    Cbn = bn_scale.numel() // (4 if bn_mode == 1 else 1)
+    rows, hw = _rows_hw(x, Cbn)
+    nhwc = hw == 1 or is_channels_last(x)
+    mb, nb, sb = fmt
+    _require_state(cur_min, 1, "cur_min")
+    _require_state(cur_max, 1, "cur_max")
+    _require_state(maxval_out, 1, "maxval_out")
+    _require_table(table_out, 1, mb, nb, sb, "table_out")
+    code = lib().fp8fq_bn_act_estimate_prepare_p2p_f32(
+        x.data_ptr(), x.numel() // Cbn if nhwc else rows, hw, Cbn, 1 if nhwc else 0, bn_scale.data_ptr(), _opt_ptr(bn_shift),
+        int(bn_mode), int(act), cur_min.data_ptr(), cur_max.data_ptr(), int(est_mode), 1 if initialized else 0,
+        float(momentum), maxval_out.data_ptr(), float(mb), int(nb), int(sb), table_out.data_ptr(),
+        _workspace(x.device).data_ptr(), ptrs.data_ptr(), int(rank), int(world), int(epoch), _stream())
+    if code == -2:
+        return False
+    check(code, "fp8fq_bn_act_estimate_prepare_p2p_f32")
+    return True
+
+
 def dp_finish_prepare(packed, cur_min, cur_max, est_mode: int, initialized: bool, momentum: float, maxval_out, fmt,
                       table_out):
     """Second half of a data-parallel calibration step (fp8fq_dp_finish_prepare_f32): ``packed`` = the all-reduced

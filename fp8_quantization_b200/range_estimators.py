@@ -188,6 +188,16 @@ class _MinMaxEstimator(RangeEstimatorBase):
         x = ops.dense(x)
         if self._dp():
             C = x.shape[0] if self.per_channel else 1
+            px = fq_dist.peer_exchange(x.device) if C == 1 else None
+            if px is not None:      # ONE launch: statistics, exchange over NVLink peer memory, rule, range, table
+                cmin, cmax, init = self._state(x)
+                mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
+                maxval = torch.empty(1, dtype=torch.float32, device=x.device)
+                table = ops.new_table(1, mb, nb, sb, x.device)
+                ops.estimate_prepare_p2p(x, cmin, cmax, self.EST_MODE, init, self.momentum, maxval, (mb, nb, sb), table,
+                                         px.next())
+                quantizer.adopt_range(maxval, table)
+                return x
             packed = self._dp_packed(C, x.device)
             ops.minmax(x, self.per_channel, packed[:C], packed[C:], ops.EST_DP_STATS, False)
             self._dp_finish(packed, x, quantizer)
@@ -212,6 +222,20 @@ class _MinMaxEstimator(RangeEstimatorBase):
         x = ops.dense(x.detach())
         mb, nb, sb = quantizer._mbits_host, quantizer.n_bits, quantizer.sign_bits
         if self._dp():
+            px = fq_dist.peer_exchange(x.device)
+            if px is not None:      # ONE launch, the exchange inside it
+                was_init = self.current_xmin is not None
+                cmin, cmax, init = self._state(x)
+                maxval = torch.empty(1, dtype=torch.float32, device=x.device)
+                table = ops.new_table(1, mb, nb, sb, x.device)
+                if not ops.bn_act_estimate_prepare_p2p(x, bn_scale, bn_shift, act_code, bn_mode, cmin, cmax, self.EST_MODE,
+                                                       init, self.momentum, maxval, (mb, nb, sb), table, px.next()):
+                    px.unused()     # shape not covered (same on every rank): the caller composes the unfused ops
+                    if not was_init:
+                        self.current_xmin = self.current_xmax = None
+                    return False
+                quantizer.adopt_range(maxval, table)
+                return True
             packed = self._dp_packed(1, x.device)
             if not ops.bn_act_estimate_prepare(x, bn_scale, bn_shift, act_code, bn_mode, packed[:1], packed[1:],
                                                ops.EST_DP_STATS, False, self.momentum):

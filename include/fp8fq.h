@@ -268,6 +268,29 @@ int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, 
                                 int initialized, double momentum, float* maxval_out, float mantissa_bits, int n_bits,
                                 int sign_bits, float* table, void* stream);
 
+/* Data-parallel calibration step as ONE launch, the exchange done by the kernel over NVLink peer memory (no collective
+ * call): the per-tensor variants of fp8fq_estimate_prepare_f32 / fp8fq_bn_act_estimate_prepare_f32 whose last CTA, after
+ * the local reduction, stores this rank's (-min, max, NaN flag) into every peer's exchange buffer (64-bit system-scope
+ * stores, value + epoch in one word), waits until its own buffer holds every peer's words of this epoch, takes the MAX
+ * and continues with the estimator rule, set_quant_range and the table -- every rank ends with the range of the
+ * concatenated batch, bit for bit, as with fp8fq_dp_finish_prepare_f32 after an all-reduce.
+ *   peer_bufs : DEVICE array [world] of pointers to each rank's exchange buffer (this rank's own included), each of
+ *               fp8fq_dp_exchange_words(world) 64-bit words, peer-accessible (symmetric / IPC memory), zeroed once
+ *               before the first call;  epoch : the same on every rank for the same call, >= 1, increasing by one per
+ *               call (all ranks must issue the same sequence of calls);  world <= 16.
+ * A peer that does not arrive within ~3 s makes the range NaN instead of hanging the device. */
+int64_t fp8fq_dp_exchange_words(int world);
+int fp8fq_estimate_prepare_p2p_f32(const float* x, int64_t n, float* cur_min, float* cur_max, int est_mode, int initialized,
+                                   double momentum, float* maxval_out, float mantissa_bits, int n_bits, int sign_bits,
+                                   float* table, void* workspace, const void* peer_bufs, int rank, int world,
+                                   unsigned int epoch, void* stream);
+int fp8fq_bn_act_estimate_prepare_p2p_f32(const float* x, int64_t outer, int64_t hw, int64_t Cbn, int nhwc,
+                                          const float* bn_scale, const float* bn_shift, int bn_mode, int act,
+                                          float* cur_min, float* cur_max, int est_mode, int initialized, double momentum,
+                                          float* maxval_out, float mantissa_bits, int n_bits, int sign_bits, float* table,
+                                          void* workspace, const void* peer_bufs, int rank, int world, unsigned int epoch,
+                                          void* stream);
+
 /* Replaces: the double Python loop of FP_MSE_Estimator.forward (range_estimators.py:337-347):
  * mses[m, g, c] += mean over the non-channel elements of (x - Q(x; maxval = grid[g, c], M = mbits[m]))^2.
  * grid: [G, C] device; mbits_host: [Mn] HOST floats; mses: [Mn, G, C] device, accumulated.

@@ -331,6 +331,19 @@ gx = torch.randn(4 * world, 3, 224, 224, generator=gen)
 workloads.pass_data_for_range_estimation([fq_dist.shard_batch(gx).to(dev)], model, True, True, 1)
 model.fix_ranges()
 ranges = [m.maxval.reshape(-1).cpu() for m in model.modules() if isinstance(m, FPQuantizer)]
+# the two data-parallel routes -- exchange over NVLink peer memory inside the statistics kernel (default when symmetric
+# memory is available) and NCCL all-reduce + finishing launch -- must give the same ranges bit for bit
+route = "peer-memory" if fq_dist.peer_exchange(dev) is not None else "nccl"
+saved = fq_dist._peer_exchange
+fq_dist._peer_exchange = None
+torch.manual_seed(10)
+model_nccl = workloads.resnet18_quantized(**workloads.readme_quant_params(5)).to(dev).eval()
+workloads.pass_data_for_range_estimation([fq_dist.shard_batch(gx).to(dev)], model_nccl, True, True, 1)
+fq_dist._peer_exchange = saved
+ranges_nccl = [m.maxval.reshape(-1).cpu() for m in model_nccl.modules() if isinstance(m, FPQuantizer)]
+routes_equal = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(ranges, ranges_nccl))
+assert routes_equal, "peer-memory route and NCCL route disagree on rank %d" % rank
+del model_nccl
 fq_dist.enable(False)
 with torch.no_grad():
     logits = model(fq_dist.shard_batch(gx).to(dev))
@@ -348,7 +361,8 @@ if rank == 0:
         ref_logits = ref(gx.to(dev))[: logits.shape[0]]
     cos = torch.nn.functional.cosine_similarity(logits.flatten(), ref_logits.flatten(), dim=0).item()
     print("DPRESULT " + json.dumps({"world": world, "quantizers": len(ranges), "bit_equal_ranges": exact,
-                                    "all_close": bool(close), "logits_cos": cos, "count": stats["count"]}))
+                                    "all_close": bool(close), "logits_cos": cos, "count": stats["count"],
+                                    "route": route, "routes_equal": bool(routes_equal)}))
 fq_dist.barrier()
 """
 
@@ -370,6 +384,7 @@ def test_config5_sharded_calibration_matches_single_process(tmp_path):
     r = json.loads(line[len("DPRESULT "):])
     print(r)
     assert r["quantizers"] == 50 and r["all_close"] and r["count"] == 4 * world
+    assert r["routes_equal"] and r["route"] in ("peer-memory", "nccl")
     assert r["bit_equal_ranges"] >= 22  # 21 weight quantisers + the stem's activation range at least
     assert r["logits_cos"] > 0.98
 

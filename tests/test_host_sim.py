@@ -956,3 +956,65 @@ def test_data_parallel_statistics_mode_and_finish_kernel(sim, host_emul, C):
                                                   0.9, P(mv_sp), 5, 8, 1, P(tab_sp), P(ws), None) == 0
             assert same_bits(dmin, smin) and same_bits(dmax, smax), (mode, call)
             assert same_bits(mv_dp, mv_sp) and same_bits(tab_dp, tab_sp), (mode, call)
+
+
+def test_peer_memory_exchange_of_the_calibration_statistics(sim):
+    """fp8fq_estimate_prepare_p2p_f32 / fp8fq_bn_act_estimate_prepare_p2p_f32: the last CTA exchanges (-min, max, NaN flag)
+    with the peers through their exchange buffers (64-bit words: value | epoch << 32) and finishes the calibration step
+    itself.  Two "ranks" run one after the other here: rank 1's words are put into rank 0's buffer beforehand (what rank 1's
+    kernel does concurrently on a real machine), rank 0's kernel then delivers its own words to both buffers, and rank
+    1's kernel finds everything in place.  Both must end with the single-process result on the concatenated batch, over
+    three calibration batches (slots rotate with the epoch), for the three estimator rules; a missing peer gives NaN."""
+    rng = np.random.default_rng(90)
+    ws = workspace(sim)
+    world = 2
+    words = sim.fp8fq_dp_exchange_words(world)
+    assert words == 4 * world * 3 and sim.fp8fq_dp_exchange_words(17) < 0
+    U64 = ctypes.c_uint64
+
+    def word(v, epoch):
+        return (epoch << 32) | int(np.float32(v).view(np.uint32))
+
+    for mode in (EST_CURRENT, EST_ALL, EST_RUNNING):
+        bufs = [np.zeros(words, np.uint64) for _ in range(world)]
+        ptrs = np.array([b.ctypes.data for b in bufs], np.uint64)
+        state = [(aligned(1), aligned(1)) for _ in range(world)]
+        smin, smax = aligned(1), aligned(1)
+        stride = sim.fp8fq_table_stride(5, 8, 1)
+        for call in range(3):
+            epoch = call + 1
+            shards = [np.ascontiguousarray(rand(rng, 3000 + 40 * r, specials=False) * (call + 1 + r)) for r in range(world)]
+            if call == 2:
+                shards[1][11] = np.nan
+            s1 = shards[1]
+            nan1 = bool(np.isnan(s1).any())
+            slot = (epoch % 4) * world * 3
+            for j, v in enumerate((-np.inf if nan1 else -np.nanmin(s1), -np.inf if nan1 else np.nanmax(s1), 1.0 if nan1 else 0.0)):
+                bufs[0][slot + 1 * 3 + j] = word(v, epoch)
+            outs = []
+            for r in range(world):
+                mv, tab = aligned(1), aligned(stride)
+                cmin, cmax = state[r]
+                assert sim.fp8fq_estimate_prepare_p2p_f32(P(shards[r]), shards[r].size, P(cmin), P(cmax), mode, int(call > 0), 0.9,
+                                                          P(mv), 5, 8, 1, P(tab), P(ws), ptrs.ctypes.data_as(ctypes.c_void_p), r,
+                                                          world, epoch, None) == 0
+                outs.append((mv.copy(), tab.copy(), cmin.copy(), cmax.copy()))
+            whole = np.ascontiguousarray(np.concatenate(shards))
+            mv_sp, tab_sp = aligned(1), aligned(stride)
+            assert sim.fp8fq_estimate_prepare_f32(P(whole), whole.size, 1, whole.size, P(smin), P(smax), mode, int(call > 0), 0.9,
+                                                  P(mv_sp), 5, 8, 1, P(tab_sp), P(ws), None) == 0
+            for r in range(world):
+                assert same_values(outs[r][0], mv_sp) and same_values(outs[r][1], tab_sp), (mode, call, r)
+                assert same_values(outs[r][2], smin) and same_values(outs[r][3], smax), (mode, call, r)
+    # a peer that never delivers: the range is NaN (on the device after a ~3 s timeout; the simulation reads once)
+    bufs = [np.zeros(words, np.uint64) for _ in range(world)]
+    ptrs = np.array([b.ctypes.data for b in bufs], np.uint64)
+    x = np.ascontiguousarray(rand(rng, 1000, specials=False))
+    mv, tab, cmin, cmax = aligned(1), aligned(sim.fp8fq_table_stride(5, 8, 1)), aligned(1), aligned(1)
+    assert sim.fp8fq_estimate_prepare_p2p_f32(P(x), x.size, P(cmin), P(cmax), EST_CURRENT, 0, 0.9, P(mv), 5, 8, 1, P(tab), P(ws),
+                                              ptrs.ctypes.data_as(ctypes.c_void_p), 0, world, 1, None) == 0
+    assert np.isnan(mv[0]) and np.isnan(cmin[0])
+    # argument checks: world < 2, rank out of range, epoch 0, too many ranks
+    for rank, w, ep, want in ((0, 1, 1, -1), (2, 2, 1, -1), (0, 2, 0, -1), (0, 17, 1, -2)):
+        assert sim.fp8fq_estimate_prepare_p2p_f32(P(x), x.size, P(cmin), P(cmax), EST_CURRENT, 0, 0.9, P(mv), 5, 8, 1, P(tab),
+                                                  P(ws), ptrs.ctypes.data_as(ctypes.c_void_p), rank, w, ep, None) == want
