@@ -39,8 +39,13 @@ constexpr int kMaxM = 12;        // fast-path tie guard validated up to here
 constexpr int kMaxK = (1 << kMaxE) - 1;
 
 enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
-// flags = FLAG_* | (band << BAND_SHIFT)
-enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8, BAND_SHIFT = 8 };
+// flags = FLAG_* | (band field << BAND_SHIFT) | (M << M_SHIFT); band field = band (< 2^20 - 1), or kBandMask for
+// "every mantissa is ambiguous" (band = 0x7fffff); M <= kMaxM < 16
+enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8, FLAG_MAGIC = 16, BAND_SHIFT = 8,
+             M_SHIFT = 28 };
+constexpr uint32_t kBandMask = 0xfffffu;
+// FLAG_MAGIC: how far (ulps) a switching point T_k may sit from its ideal position s_k * 2^M (see prep_finish)
+constexpr int kMagicMaxDev = 128;
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -226,7 +231,7 @@ FQ_HD void prep_entry(float* tab, int k, int M, int K, float bias) {
   if (k >= 2) thr[k - 1] = find_threshold(bias, k);
 }
 // step 3 (one thread, after all entries are visible): bucket base + regularity check
-FQ_HD void prep_finish(float* tab, int K, float mv) {
+FQ_HD void prep_finish(float* tab, int M, int K, float mv) {
   const float* thr = tab + kHdr;
   int flags = 0;
   uint32_t base = 0x00800000u;
@@ -259,7 +264,7 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
       dmin = d < dmin ? d : dmin;
       dmax = d > dmax ? d : dmax;
     }
-    if (dmax - dmin < (1 << 20) && t2 + dmin > 0) {
+    if (dmax - dmin < (1 << 20) - 1 && t2 + dmin > 0) {
       ref = (uint32_t)(t2 + dmin);
       band = (uint32_t)(dmax - dmin);
     }
@@ -294,11 +299,37 @@ FQ_HD void prep_finish(float* tab, int K, float mv) {
             f2u(sr[2 * k + 1]) + sh == f2u(sr[3]);
     }
     if (dbl) flags |= FLAG_SDOUBLE;
+    // FLAG_MAGIC: the whole element path can run in the SCALED domain u = |xc| / s_1 (quant_magic below): with exact
+    // doublings the reference's grid is s_1 * {q * 2^(e-1)}, i.e. u rounded to M + 1 significant bits with a fixed
+    // spacing of 1 below 2^(M+1) -- an ordinary floating-point rounding, done by adding and subtracting
+    // 2^(p+23), p = max(exponent(u) - M, 0) (<= K - 1 because |xc| <= maxval).  That places the code boundaries at the powers of two
+    // 2^(M+k-1) of u instead of at the reference's switching points T_k; the two differ by the fp32 noise of the
+    // reference's log2 / pow (a few ulps), and an element between them is within that distance of the boundary value
+    // itself, which BOTH spacings contain -- it rounds to it either way as long as the distance stays far below half
+    // the finer spacing (2^(21-M) ulps).  Checked here per table: every T_k within kMagicMaxDev ulps of s_k * 2^M.
+    // K == 1 formats qualify too (p is always 0).
+    bool magic = (K == 1 ? (!rsnan && is_normal_pos(sr[2]) && is_normal_pos(sr[3])) : dbl) && M >= 1 && M <= kMaxM;
+    for (int k = 2; k <= K && magic; ++k) {
+      const float ideal = ldexpf(sr[2 * k], M);
+      const int64_t dev = (int64_t)f2u(thr[k - 1]) - (int64_t)f2u(ideal);
+      magic = is_normal_pos(ideal) && is_normal_pos(thr[k - 1]) && dev >= -kMagicMaxDev && dev <= kMagicMaxDev;
+    }
+    // no upper clamp of p in the element path: the largest clamped input must lie inside the top binade of the scaled
+    // domain, maxval / s_1 < 2^(M+K) with room for the rounding of the reciprocal multiply; and nothing may overflow
+    magic = magic && is_normal_pos(ldexpf(sr[2], M + K + 1)) && is_normal_pos(mv) &&
+            mul_rn(mul_rn(mv, sr[3]), 1.0f + 1.0f / 1048576.0f) < ldexpf(1.0f, M + K) && M + K + 24 < 127;
+    if (magic) flags |= FLAG_MAGIC;
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);
-  tab[H_FLAGS] = u2f((uint32_t)flags | (band << BAND_SHIFT));
+  tab[H_FLAGS] = u2f((uint32_t)flags | ((band < kBandMask ? band : kBandMask) << BAND_SHIFT) | ((uint32_t)M << M_SHIFT));
 }
+
+FQ_HD uint32_t flags_band(uint32_t fl) {
+  const uint32_t b = (fl >> BAND_SHIFT) & kBandMask;
+  return b == kBandMask ? 0x7fffffu : b;
+}
+FQ_HD int flags_M(uint32_t fl) { return (int)(fl >> M_SHIFT); }
 
 // ---- element path ------------------------------------------------------------------------------
 // Generic lookup of e' (index into the (scale, rcp) pairs) for a = |xc|, from a channel table.
@@ -380,6 +411,37 @@ FQ_HD float uq_quant(float x, float scale, float rs, float zp, float imin, float
 }
 
 // Quantise xc (already clamped) with the selected (s, rs).  Returns y; *q_out = round(xc / s).
+// ---- FLAG_MAGIC tables: the element path in the scaled domain (see prep_finish) ----------------------------------
+// Per-table constants, all derived from (M, tie guard, s_1, 1/s_1).
+struct MagicConsts {
+  float s1, r1;        // scale of code 1 and its reciprocal
+  float kap;           // guard * 2^p == C * kap for the magic constant C = 2^(p+23)
+  uint32_t lo, add;    // bits(C) = max(bits(u) & 0x7f800000, lo) + add
+};
+FQ_HD MagicConsts magic_consts(int M, float guard, float s1, float r1) {
+  MagicConsts m;
+  m.s1 = s1;
+  m.r1 = r1;
+  m.kap = guard * (1.0f / 8388608.0f);                        // 2^-23
+  m.lo = (uint32_t)(127 + M) << 23;                           // exponent field of 2^M: p = 0 up to u < 2^(M+1)
+  m.add = (uint32_t)(23 - M) << 23;                           // -> exponent p + 23 (u >= 0: u + C stays in C's binade)
+  return m;
+}
+// One element.  Returns |y| (the caller restores the sign of xc: a negative value that rounds to zero is -0.0 in the
+// reference); *ok is false when the reciprocal multiply landed within the guard band of a rounding tie (or xc is NaN):
+// the caller must then take the exact path.  Instruction count: FMUL, LOP, integer max, integer add, 3 FADD, FMUL,
+// FSETP, FMUL -- no table access, no FRND.  There is no upper clamp of p: prep_finish sets FLAG_MAGIC only when the
+// largest clamped input, maxval / s_1, lies inside the top binade [2^(M+K-1), 2^(M+K)).
+FQ_HD float quant_magic(float xc, const MagicConsts& m, bool* ok) {
+  const float u = mul_rn(fabsf(xc), m.r1);
+  uint32_t cb = f2u(u) & 0x7f800000u;
+  cb = (cb < m.lo ? m.lo : cb) + m.add;
+  const float C = u2f(cb);
+  const float qu = sub_rn(add_rn(u, C), C);                   // u rounded half-to-even to a multiple of 2^p
+  *ok = fabsf(sub_rn(u, qu)) < mul_rn(C, m.kap);
+  return mul_rn(qu, m.s1);
+}
+
 FQ_HD float quant_core(float xc, float s, float rs, float guard, float* q_out) {
   float r = mul_rn(xc, rs);
   float q = nearbyintf(r);

@@ -176,7 +176,7 @@ __device__ void prepare_channel(float mv, int M, int E, int K, int sign_bits, fl
   const float bias = s_bias;
   for (int k = tid + 1; k <= K; k += blockDim.x) prep_entry(tab, k, M, K, bias);
   __syncthreads();
-  if (tid == 0) prep_finish(tab, K, mv);
+  if (tid == 0) prep_finish(tab, M, K, mv);
   __syncthreads();
 }
 
@@ -252,7 +252,8 @@ struct StreamArgs {
   uint32_t hw_rcp;      // ceil(2^32 / hw): umulhi(p, hw_rcp) == p / hw for p * hw < 2^32
   FastDiv hw_div, c_div;
   int cl_same;          // *_CL: Cbn divides threads * VEC, i.e. a thread sees the same channels in every vector
-  int threads;          // *_CL: threads per CTA (<= kThreads), chosen so that cl_same holds; 0 = kThreads
+  int threads;          // *_CL: threads per CTA (<= kMaxDynThreads), chosen so that cl_same holds; 0 = kThreads
+  int64_t ntiles;       // tiles of the launch (filled by launch_stream_t: the kernel need not divide by its tile size)
 };
 
 struct RegTab {  // K <= 3: everything in registers
@@ -270,6 +271,8 @@ struct ElemCtx {
   uint32_t ref, band;   // KMODE 1: exponent-arithmetic fast path (lookup_code_fast)
   bool dbl;             // KMODE 1: FLAG_SDOUBLE table -- (s, 1/s) by integer arithmetic (lookup_scale_fast), no load
   uint32_t s1b, r1b, tmax;
+  bool magic;           // KMODE 1: FLAG_MAGIC table -- the element path in the scaled domain (quant_magic), no look-up
+  MagicConsts mc;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -323,6 +326,16 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 #ifndef FP8FQ_SDOUBLE
 #define FP8FQ_SDOUBLE 0
 #endif
+// FP8FQ_MAGIC (default ON, round 2): K > 3 formats whose table carries FLAG_MAGIC (exact-doubling scales and switching
+// points within kMagicMaxDev ulps of their ideal positions -- the usual case, see prep_finish in fp8fq_core.h) run the
+// element path in the scaled domain u = |xc| / s_1: y = s_1 * (u rounded to M + 1 significant bits) by adding and
+// subtracting a magic constant built from u's exponent field (quant_magic).  11 instructions per element after the
+// clamp instead of 15+ (no code look-up, no (s, 1/s) gather, no FRND), same bits: the tie guard of the reciprocal
+// multiply is kept, and a vector with a lane inside it (or a NaN) re-runs the look-up path.  The code-plane variant
+// (CODES) keeps the look-up path: its exponent codes follow the reference's switching points exactly.
+#ifndef FP8FQ_MAGIC
+#define FP8FQ_MAGIC 1
+#endif
 // FP8FQ_PACK2 (build option): the independent fp32 multiplies / adds / FMAs of neighbouring elements are issued as
 // sm_100's two-wide instructions (FMUL2 / FADD2 / FFMA2: same IEEE round-to-nearest results, half the issue slots).
 // Measured (round 2 A/B): K <= 3 stream kernels 0 %, K > 3 +1..2 %, MSE-grid kernel -2..4 % -- off.
@@ -365,7 +378,9 @@ __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
 // GUARD = false drops the exactness check of the reciprocal multiply (only for consumers that tolerate q off by one
 // on an exact rounding tie -- the MSE kernel, where either neighbour is equally far from x -- and only for tables
 // without FLAG_RSNAN).
-template <int KMODE, bool CODES, int N, bool STAB_SHARED = false, bool GUARD = true>
+// SIGNED_OUT = false: the caller only needs |y| (the MSE kernel, which forms |x| - |y|); the magic path then skips
+// restoring the sign.
+template <int KMODE, bool CODES, int N, bool STAB_SHARED = false, bool GUARD = true, bool SIGNED_OUT = true>
 __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N],
                                           float* s_out = nullptr) {
   if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
@@ -397,6 +412,22 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
   bool slow = false;
 #pragma unroll
   for (int k = 0; k < N; ++k) xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
+  if (KMODE == 1 && FP8FQ_MAGIC && !CODES && s_out == nullptr && c.magic) {
+    // scaled-domain path (FP8FQ_MAGIC above); one exactness check per vector, like the look-up path
+    bool all_ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float u = mul_rn(fabsf(xc[k]), c.mc.r1);
+      uint32_t cb = f2u(u) & 0x7f800000u;
+      cb = (cb < c.mc.lo ? c.mc.lo : cb) + c.mc.add;
+      const float C = u2f(cb);
+      const float qu = sub_rn(add_rn(u, C), C);
+      if (GUARD) all_ok &= fabsf(sub_rn(u, qu)) < mul_rn(C, c.mc.kap);
+      const float ya = mul_rn(qu, c.mc.s1);
+      y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
+    }
+    if (!GUARD || all_ok) return;
+  }
   if (KMODE == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -527,6 +558,7 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.rt.s2 = c.rt.s3 = c.rt.r2 = c.rt.r3 = 0.0f;
     c.K = 1; c.stab = tab; c.base = 0; c.irregular = false; c.ref = 0; c.band = 0;
     c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
+    c.magic = false;
     return;
   }
   c.hi = ld(tab + H_HI);
@@ -548,16 +580,19 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.ref = 0;
     c.band = 0;
     c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
+    c.magic = false;
   } else {
     const uint32_t fl = f2u(ld(tab + H_FLAGS));
     c.base = f2u(ld(tab + H_BASE));
     c.irregular = (fl & FLAG_IRREGULAR) != 0;
     c.ref = f2u(ld(tab + H_REF));
-    c.band = fl >> BAND_SHIFT;
+    c.band = flags_band(fl);
     c.dbl = FP8FQ_SDOUBLE && (fl & FLAG_SDOUBLE) != 0;
     c.s1b = f2u(ld(tab + off_sr(K) + 2));
     c.r1b = f2u(ld(tab + off_sr(K) + 3));
     c.tmax = (uint32_t)(K - 1) << 23;
+    c.magic = FP8FQ_MAGIC && (fl & FLAG_MAGIC) != 0;
+    c.mc = magic_consts(flags_M(fl), c.guard, u2f(c.s1b), u2f(c.r1b));
   }
 }
 template <int KMODE>
@@ -639,7 +674,7 @@ struct StreamMinBlocks {
 #define FQ_MINB_CL 6
 #endif
 #ifndef FQ_MINB_CL_DYN
-#define FQ_MINB_CL_DYN 5
+#define FQ_MINB_CL_DYN 4   // x kMaxDynThreads = 320 threads: the same 48-register budget as 5 x 256
 #endif
   static constexpr int value =
       PreTraits<PRE>::kCL ? (DYN ? FQ_MINB_CL_DYN : FQ_MINB_CL)
@@ -649,8 +684,12 @@ struct StreamMinBlocks {
 
 // DYN: the CTA size is a launch parameter (channel-innermost variants whose channel count does not divide
 // kThreads * VEC); everywhere else it is the compile-time kThreads, which keeps the index arithmetic constant-folded.
+// (up to kMaxDynThreads = 320 threads, so that MobileNetV2's 1280-channel layer -- 320 four-channel lanes -- gets a
+// fitted CTA as well; the register budget, 65536 / (320 * 4) -> 48, is that of 5 CTAs of 256 threads)
+constexpr int kMaxDynThreads = 320;
 template <int KMODE, int PRE, int VEC, bool CODES, int BNM, bool DYN = false>
-__global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::value) fq_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(DYN ? kMaxDynThreads : kThreads, StreamMinBlocks<KMODE, PRE, DYN>::value)
+fq_stream_kernel(const StreamArgs a) {
   constexpr bool kTail = PreTraits<PRE>::kTail;
   constexpr bool kPerLane = PreTraits<PRE>::kPerLane;
   constexpr bool kLocalRows = PreTraits<PRE>::kLocalRows;
@@ -659,12 +698,16 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::va
   constexpr bool kBnAct = PreTraits<PRE>::kBnAct;
   constexpr int kUnroll = StreamUnroll<PRE>::value;
 
-  // the channel-innermost variants run with the largest CTA size <= kThreads whose pass stride (threads * VEC) is a
-  // multiple of the channel count, so that a thread meets the same channels in every vector (launch_stream_t)
+  // the channel-innermost variants run with the largest CTA size whose pass stride (threads * VEC) is a multiple of the
+  // channel count, so that a thread meets the same channels in every vector (bn_act_quant_nhwc_impl).  Their tensors
+  // have fewer than 2^31 elements (checked by the launcher), so all of their index arithmetic is 32-bit: the run-time
+  // CTA size of the DYN instantiations otherwise costs a 64-bit multiply-add chain and two-instruction bounds tests
+  // per vector (round 2, static SASS: 23 -> 9 address / bounds instructions per vector).
+  using idx_t = typename std::conditional<kCL, uint32_t, int64_t>::type;
   const int nthr = DYN ? (int)blockDim.x : kThreads;
-  const int64_t kTile = (int64_t)nthr * VEC * kUnroll;
-  const int64_t nvec_elems = a.n - (a.n % VEC);
-  const int64_t ntiles = (nvec_elems + kTile - 1) / kTile;
+  const idx_t kTile = (idx_t)nthr * VEC * kUnroll;
+  const idx_t nvec_elems = (idx_t)a.n - (idx_t)(a.n % VEC);
+  const idx_t ntiles = (idx_t)a.ntiles;
   pdl_prologue();
   // per-CTA parameters: uniform loads, no barrier; issued first, consumed only after the data loads went out
   ElemCtx<KMODE> ctx, ctx2;
@@ -684,8 +727,8 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::va
 #define FQ_ACT a.act   // (-DFP8FQ_FOLD_ACT=0 -DFP8FQ_FULL_TILE=0: token for token the code of the round-1 profiles)
 #endif
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t tile0 = tile * kTile;
+  for (idx_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const idx_t tile0 = tile * kTile;
 #if FP8FQ_FULL_TILE
     // the tile body is instantiated twice: every tile but the last one is full and needs no bounds predicates
     auto tile_body = [&](auto full_tag) {
@@ -693,13 +736,13 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::va
 #else
     constexpr bool kFullTile = false;
 #endif
-    const int64_t base = tile0 + (int64_t)threadIdx.x * VEC;
+    const idx_t base = tile0 + (idx_t)threadIdx.x * VEC;
     // 1. all of this thread's loads go out before any of them is used
     Pack<VEC> in[kUnroll], in2[kUnroll];
     bool ok[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = base + (int64_t)u * nthr * VEC;
+      const idx_t i = base + (idx_t)u * nthr * VEC;
       ok[u] = kFullTile || i < nvec_elems;
       if (ok[u]) {
         in[u].load(a.x + i);
@@ -733,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::va
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           if (!ok[u]) continue;
-          const uint32_t i32 = (uint32_t)(base + (int64_t)u * nthr * VEC);
+          const uint32_t i32 = (uint32_t)(base + (idx_t)u * nthr * VEC);
           const uint32_t ch = i32 - fdiv(i32, a.c_div) * a.Cbn;
 #pragma unroll
           for (int k = 0; k < VEC; ++k) in[u].v[k] = bn_apply<BNM>(in[u].v[k], bn_load<BNM>(a, ch + k));
@@ -743,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, StreamMinBlocks<KMODE, PRE, DYN>::va
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
-      const int64_t i = base + (int64_t)u * nthr * VEC;
+      const idx_t i = base + (idx_t)u * nthr * VEC;
       float v[VEC], yv[VEC];
       int32_t cd[VEC];
       if (kCL) {
@@ -1635,11 +1678,13 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
       for (int u = 0; u < EPT; u += 4) {
         float vi[4] = {v[u], v[u + 1], v[u + 2], v[u + 3]}, yo[4];
         int32_t cd[4];
-        if (guarded) quant_vec<KMODE, false, 4, true, true>(vi, ctx, yo, cd);
-        else quant_vec<KMODE, false, 4, true, false>(vi, ctx, yo, cd);
+        if (guarded) quant_vec<KMODE, false, 4, true, true, false>(vi, ctx, yo, cd);
+        else quant_vec<KMODE, false, 4, true, false, false>(vi, ctx, yo, cd);
+        // y has the sign of x or is zero, so |x| - |y| is x - y up to that sign: the same square (and the scaled-domain
+        // path need not restore the sign)
         float d[4];
-        sub2_rn(vi[0], vi[1], yo[0], yo[1], d[0], d[1]);   // (two-wide under FP8FQ_PACK2; same roundings, same order of
-        sub2_rn(vi[2], vi[3], yo[2], yo[3], d[2], d[3]);   //  accumulation either way)
+        sub2_rn(fabsf(vi[0]), fabsf(vi[1]), fabsf(yo[0]), fabsf(yo[1]), d[0], d[1]);   // (two-wide under FP8FQ_PACK2; same
+        sub2_rn(fabsf(vi[2]), fabsf(vi[3]), fabsf(yo[2]), fabsf(yo[3]), d[2], d[3]);   //  roundings and order either way)
 #pragma unroll
         for (int k = 0; k < 4; ++k) err = fmaf(d[k], d[k], err);
       }
@@ -1705,7 +1750,10 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
   }
 #endif
   if (grid > 0x7fffffffll) grid = 0x7fffffffll;  // the kernel strides over the remaining tiles
-  launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, dim3((unsigned)grid), dim3(threads), 0, st, a);
+  StreamArgs b = a;
+  const int64_t nvec = a.n - a.n % VEC;
+  b.ntiles = (nvec + tile - 1) / tile;
+  launch_kernel(fq_stream_kernel<KMODE, PRE, VEC, CODES, BNM, DYN>, dim3((unsigned)grid), dim3(threads), 0, st, b);
   return launch_status();
 }
 
@@ -2029,7 +2077,8 @@ static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* 
     if (r != FP8FQ_OK) return r;
   }
   if (pixels < 0 || Cbn < 1 || act < 0 || act > 2 || bn_mode < 0 || bn_mode > 1) return FP8FQ_ERR_BAD_ARG;
-  if (Cbn >= (1ll << 31) || pixels >= (1ll << 32) || pixels * Cbn >= (1ll << 32)) return FP8FQ_ERR_UNSUPPORTED;
+  // (the channel-innermost kernels index with 32 bits: fewer than 2^31 elements -- an 8 GB tensor)
+  if (Cbn >= (1ll << 31) || pixels >= (1ll << 31) || pixels * Cbn >= (1ll << 31)) return FP8FQ_ERR_UNSUPPORTED;
   const int64_t n = pixels * Cbn;
   if (n == 0) return FP8FQ_OK;
   if (x == nullptr || y == nullptr || table == nullptr || bn_scale == nullptr || (bn_mode == 0 && bn_shift == nullptr))
@@ -2043,10 +2092,11 @@ static int bn_act_quant_nhwc_impl(const float* x, const float* residual, float* 
   a.c_div = make_fastdiv((uint32_t)Cbn);
   const bool v4 = (Cbn % 4 == 0) && aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual));
   // CTA size: the largest multiple of (channels per pass-lane group) = Cbn / VEC that fits in kThreads, so that the
-  // pass stride threads * VEC is a multiple of Cbn (MobileNetV2: C = 96 -> 240 threads, 144 -> 252, 576 -> 144, ...);
-  // wider layers (Cbn / VEC > kThreads) keep kThreads and look the channel up per vector
+  // pass stride threads * VEC is a multiple of Cbn (MobileNetV2: C = 96 -> 240 threads, 144 -> 252, 576 -> 144, ...;
+  // 1280 -> 320, the one size above kThreads the DYN instantiations are compiled for);
+  // wider layers (Cbn / VEC > kMaxDynThreads) keep kThreads and look the channel up per vector
   const int64_t lanes = Cbn / (v4 ? 4 : 1);
-  a.threads = lanes <= kThreads ? (int)((kThreads / lanes) * lanes) : kThreads;
+  a.threads = lanes <= kThreads ? (int)((kThreads / lanes) * lanes) : (lanes <= kMaxDynThreads ? (int)lanes : kThreads);
   // ... preferring one that is also a whole number of warps when such a size of at least 128 threads exists (C = 96 or
   // 192 -> 192 threads instead of 240: no half-empty warp; measured +3..5 % at those sites, profiles/cl_shapes_r02.json;
   // FP8FQ_CL_WARP_THREADS=0 restores the largest fitting size)

@@ -25,7 +25,7 @@ namespace {
 using at::Tensor;
 using OptTensor = c10::optional<Tensor>;
 
-constexpr int64_t kMaxFusedElems = int64_t(1) << 32;  // the fused epilogues index with 32 bits (ops.MAX_FUSED_ELEMS)
+constexpr int64_t kMaxFusedElems = int64_t(1) << 31;  // the fused epilogues index with 32 bits (ops.MAX_FUSED_ELEMS)
 
 void* cur_stream() { return static_cast<void*>(c10::cuda::getCurrentCUDAStream().stream()); }
 

@@ -293,8 +293,9 @@ def bn_pack(mean, var, gamma, beta, eps: float):
 
 # The fused batch-norm epilogues index with 32 bits (their row / channel arithmetic is built on 32-bit multiply-high
 # divisions); the C ABI answers FP8FQ_ERR_UNSUPPORTED from this size on and the callers compose the unfused steps
-# (F.batch_norm, activation, the 64-bit-indexed plain quantiser) instead.
-MAX_FUSED_ELEMS = 1 << 32
+# (F.batch_norm, activation, the 64-bit-indexed plain quantiser) instead.  (2^31: the channel-innermost variants keep
+# tile offsets beyond the last element in 32 bits as well.)
+MAX_FUSED_ELEMS = 1 << 31
 
 
 def bn_act_quant(x, bn_scale, bn_shift, act: int, table, mantissa_bits: float, n_bits: int, sign_bits: int,

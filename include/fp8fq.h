@@ -269,7 +269,8 @@ int fp8fq_dp_finish_prepare_f32(const float* packed, int64_t C, float* cur_min, 
                                 int sign_bits, float* table, void* stream);
 
 /* Data-parallel calibration step as ONE launch, the exchange done by the kernel over NVLink peer memory (no collective
- * call): the per-tensor variants of fp8fq_estimate_prepare_f32 / fp8fq_bn_act_estimate_prepare_f32 whose last CTA, after
+ * call; replaces the estimator -> all-reduce -> set_quant_range sequence of quantization_manager.py:114-122 with
+ * range_estimators.py:73-98 under data parallelism): the per-tensor variants of fp8fq_estimate_prepare_f32 / fp8fq_bn_act_estimate_prepare_f32 whose last CTA, after
  * the local reduction, stores this rank's (-min, max, NaN flag) into every peer's exchange buffer (64-bit system-scope
  * stores, value + epoch in one word), waits until its own buffer holds every peer's words of this epoch, takes the MAX
  * and continues with the estimator rule, set_quant_range and the table -- every rank ends with the range of the

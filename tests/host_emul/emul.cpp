@@ -24,7 +24,7 @@ int emul_prepare(const float* maxval, int64_t C, float mantissa_bits, int n_bits
     float* tab = table + c * stride;
     const float bias = prep_header(tab, maxval[c], M, E, K, sign_bits);
     for (int k = 1; k <= K; ++k) prep_entry(tab, k, M, K, bias);
-    prep_finish(tab, K, maxval[c]);
+    prep_finish(tab, M, K, maxval[c]);
   }
   return 0;
 }
@@ -41,11 +41,24 @@ int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table
     const float* tab = table + c * stride;
     const float hi = tab[H_HI], lo = tab[H_LO], guard = tab[H_GUARD];
     const uint32_t base = f2u(tab[H_BASE]);
-    const bool irregular = force_irregular || (f2u(tab[H_FLAGS]) & FLAG_IRREGULAR);
-    const uint32_t ref = f2u(tab[H_REF]), band = force_irregular ? 0x7fffffu : (f2u(tab[H_FLAGS]) >> BAND_SHIFT);
+    const bool irregular = force_irregular == 1 || (f2u(tab[H_FLAGS]) & FLAG_IRREGULAR);
+    const uint32_t ref = f2u(tab[H_REF]), band = force_irregular == 1 ? 0x7fffffu : flags_band(f2u(tab[H_FLAGS]));
+    // force_irregular: 0 = as the kernels run (FLAG_MAGIC tables take the scaled-domain path, quant_vec<1, false>),
+    // 1 = linear threshold scan, 2 = the table path even for FLAG_MAGIC tables (what the code-plane variant runs)
+    const bool magic = force_irregular == 0 && codes == nullptr && (f2u(tab[H_FLAGS]) & FLAG_MAGIC) != 0;
+    const MagicConsts mc = magic_consts(flags_M(f2u(tab[H_FLAGS])), guard, tab[off_sr(K) + 2], tab[off_sr(K) + 3]);
     for (int64_t i = 0; i < inner; ++i) {
       const float v = x[c * inner + i];
       const float xc = min_nan(max_nan(v, lo), hi);
+      if (magic) {
+        bool ok;
+        const float ya = quant_magic(xc, mc, &ok);
+        if (ok) {
+          y[c * inner + i] = u2f((f2u(ya) & 0x7fffffffu) | (f2u(xc) & 0x80000000u));
+          continue;
+        }
+        ++slow;
+      }
       const float a = fabsf(xc);
       bool amb;
       int e = lookup_code_fast(a, ref, band, K, &amb);  // same two-level lookup as quant_vec<1, ...>
@@ -111,6 +124,6 @@ int emul_table_flags(const float* table, int64_t c, float mantissa_bits, int n_b
 int emul_table_band(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
   int M, E, K;
   if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
-  return (int)(f2u(table[c * table_stride(K) + H_FLAGS]) >> BAND_SHIFT);
+  return (int)flags_band(f2u(table[c * table_stride(K) + H_FLAGS]));
 }
 }

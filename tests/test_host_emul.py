@@ -19,7 +19,9 @@ def P(a):
     return a.ctypes.data_as(FP)
 
 
-def run_pair(oracle_c, emul, x, maxval, mb, nb, sb, force=0):
+def run_pair(oracle_c, emul, x, maxval, mb, nb, sb, force=0, codes=True):
+    """force: 0 = the paths the kernels take (with ``codes=False`` FLAG_MAGIC tables run the scaled-domain path
+    quant_magic; the code-plane variant keeps the look-up), 1 = linear threshold scan, 2 = look-up path."""
     C, inner = x.shape
     y0, e0, q0 = np.empty_like(x), np.empty_like(x), np.empty_like(x)
     oracle_c.oracle_c_fake_quant(P(x), P(y0), P(e0), P(q0), P(maxval), ctypes.c_int64(C), ctypes.c_int64(inner),
@@ -31,8 +33,8 @@ def run_pair(oracle_c, emul, x, maxval, mb, nb, sb, force=0):
     y1 = np.empty_like(x)
     cd = np.empty(x.shape, np.int32)
     slow = ctypes.c_int64(0)
-    assert emul.emul_fake_quant(P(x), P(y1), cd.ctypes.data_as(IP), P(tab), ctypes.c_int64(C), ctypes.c_int64(inner),
-                                ctypes.c_float(mb), nb, sb, force, ctypes.byref(slow)) == 0
+    assert emul.emul_fake_quant(P(x), P(y1), cd.ctypes.data_as(IP) if codes else None, P(tab), ctypes.c_int64(C),
+                                ctypes.c_int64(inner), ctypes.c_float(mb), nb, sb, force, ctypes.byref(slow)) == 0
     return y0, e0, q0, y1, cd, slow.value, tab
 
 
@@ -53,6 +55,10 @@ def test_table_algorithm_equals_direct_formula(oracle_c, host_emul, M, sb):
             e1, q1 = (cd >> 16) & 0x7FFF, cd & 0xFFFF
             ok = ((e1 == e0) & (q1 == np.abs(q0))) | np.isnan(y0)
             assert ok.all(), "codes differ"
+            if force == 0:   # the path the stream / row kernels take: scaled-domain rounding for FLAG_MAGIC tables
+                y2 = run_pair(oracle_c, host_emul, x, mv, float(M), 8, sb, 0, codes=False)[3]
+                same = (y0.view(np.int32) == y2.view(np.int32)) | (np.isnan(y0) & np.isnan(y2))
+                assert same.all(), f"scaled-domain path differs: M={M} sign={sb} scale={scale}"
 
 
 def test_edge_inputs_and_degenerate_ranges(oracle_c, host_emul):
@@ -64,9 +70,10 @@ def test_edge_inputs_and_degenerate_ranges(oracle_c, host_emul):
                 x = np.tile(specials, (1, 4)).astype(np.float32)
                 x = np.concatenate([x, x * np.float32(mvv if np.isfinite(mvv) else 1.0)], axis=1)
                 mv = np.array([mvv], np.float32)
-                y0, e0, q0, y1, cd, _, _ = run_pair(oracle_c, host_emul, x, mv, float(M), 8, sb)
-                same = (y0.view(np.int32) == y1.view(np.int32)) | (np.isnan(y0) & np.isnan(y1))
-                assert same.all(), (M, sb, mvv, x[~same], y0[~same], y1[~same])
+                for codes in (True, False):
+                    y0, e0, q0, y1, cd, _, _ = run_pair(oracle_c, host_emul, x, mv, float(M), 8, sb, codes=codes)
+                    same = (y0.view(np.int32) == y1.view(np.int32)) | (np.isnan(y0) & np.isnan(y1))
+                    assert same.all(), (M, sb, mvv, codes, x[~same], y0[~same], y1[~same])
 
 
 def test_binade_edges_and_ties_exhaustive_neighbourhood(oracle_c, host_emul):
@@ -90,8 +97,51 @@ def test_binade_edges_and_ties_exhaustive_neighbourhood(oracle_c, host_emul):
             xs.append((pi + np.arange(-64, 65)).astype(np.int32).view(np.float32))
         x = np.concatenate(xs)[None, :].astype(np.float32)
         x = np.concatenate([x, -x], axis=1)
-        y0, e0, q0, y1, cd, _, _ = run_pair(oracle_c, host_emul, x, mv, float(M), 8, 1)
-        assert (y0.view(np.int32) == y1.view(np.int32)).all()
+        for codes in (True, False):
+            y0, e0, q0, y1, cd, _, _ = run_pair(oracle_c, host_emul, x, mv, float(M), 8, 1, codes=codes)
+            assert (y0.view(np.int32) == y1.view(np.int32)).all(), (M, mvv, codes)
+
+
+@pytest.mark.parametrize("nb,M", [(8, 1), (8, 2), (8, 3), (8, 4), (8, 5), (8, 6), (8, 7), (6, 2), (12, 6), (16, 10), (16, 12), (10, 3)])
+def test_scaled_domain_path_is_the_common_one_and_bit_exact(oracle_c, host_emul, nb, M):
+    """FLAG_MAGIC (csrc/fp8fq_core.h prep_finish / quant_magic): over a sweep of ranges most tables qualify, and on those
+    the add-and-subtract rounding in the scaled domain returns the reference's bits for random values, for every float
+    within +-200 ulps of every code boundary (where the two classifications of the binade differ) and of rounding ties
+    in every binade, for zeros of both signs, denormals, NaN and infinities -- signed and unsigned."""
+    FLAG_MAGIC = 16
+    rng = np.random.default_rng(1000 * nb + M)
+    mvs = np.exp(rng.uniform(np.log(1e-3), np.log(3e3), 64)).astype(np.float32)
+    magic = 0
+    for sb in (1, 0):
+        for mvv in mvs[: 64 if sb else 16]:
+            mv = np.array([mvv], np.float32)
+            st = host_emul.emul_table_stride(ctypes.c_float(M), nb, sb)
+            tab = np.zeros(st, np.float32)
+            assert host_emul.emul_prepare(P(mv), ctypes.c_int64(1), ctypes.c_float(M), nb, sb, P(tab)) == 0
+            is_magic = bool(host_emul.emul_table_flags(P(tab), ctypes.c_int64(0), ctypes.c_float(M), nb, sb) & FLAG_MAGIC)
+            magic += is_magic and sb == 1
+            K = int(tab[5:6].view(np.int32)[0])
+            kp = (K + 2) & ~1
+            thr = tab[8:8 + K + 1]
+            sr = tab[8 + kp:8 + kp + 2 * (K + 1)].reshape(K + 1, 2)
+            pts = [t for t in thr[1:K] if np.isfinite(t)]
+            for e in sorted(set([1, 2, 3, K // 2, K - 1, K]) & set(range(1, K + 1))):
+                s = sr[e, 0]
+                pts += [np.float32((q + 0.5) * s) for q in (0, 1, 2, 3, 2 ** M - 1, 2 ** M, 2 ** M + 1, 2 ** (M + 1) - 2,
+                                                              2 ** (M + 1) - 1)]
+                pts += [np.float32(q * s) for q in (1, 2 ** M, 2 ** (M + 1))]
+            pts = [p for p in pts if np.isfinite(p) and p > 0]
+            xs = [(np.float32(p).view(np.int32).astype(np.int64) + np.arange(-200, 201)).astype(np.int32).view(np.float32)
+                  for p in pts]
+            xs.append((rng.standard_normal(20000) * mvv * 0.5).astype(np.float32))
+            xs.append(np.exp(rng.uniform(np.log(1e-6), 0.1, 20000)).astype(np.float32) * mvv)
+            xs.append(np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-38, -1e-38, 1e-45, -1e-45, 3e38, -3e38], np.float32))
+            x = np.concatenate(xs)[None, :].astype(np.float32)
+            x = np.ascontiguousarray(np.concatenate([x, -x], axis=1))
+            y0, _, _, y1, _, _, _ = run_pair(oracle_c, host_emul, x, mv, float(M), nb, sb, codes=False)
+            same = (y0.view(np.int32) == y1.view(np.int32)) | (np.isnan(y0) & np.isnan(y1))
+            assert same.all(), (nb, M, sb, float(mvv), is_magic, x[~same][:8], y0[~same][:8], y1[~same][:8])
+    assert magic >= 32, magic   # of 64 signed tables (E3M4: ~74 %, the rest keeps the look-up path)
 
 
 def test_c_restatement_vs_torch_oracle(oracle_c, host_emul):

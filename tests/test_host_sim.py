@@ -865,8 +865,12 @@ def test_simulated_kernels_against_the_real_reference_golden_vectors(sim):
 
 
 @pytest.mark.parametrize("M,sb", [(4, 1), (3, 1), (2, 1), (4, 0), (1, 1)])
-def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(built, ref, M, sb):
-    """(Build option FP8FQ_SDOUBLE, exercised on oracle/_build/libfp8fq_sim_fulltilecl.so, which is built with it.)
+@pytest.mark.parametrize("which", ["sdouble", "magic"])
+def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(built, ref, M, sb, which):
+    """which = "magic": the DEFAULT build -- tables with FLAG_MAGIC run the element path in the scaled domain
+    (quant_magic: add-and-subtract rounding of |xc| / s_1, no look-up at all), the others the look-up; both kinds must
+    occur and both must reproduce the direct formula bit for bit.  which = "sdouble":
+    (Build option FP8FQ_SDOUBLE, exercised on oracle/_build/libfp8fq_sim_fulltilecl.so, which is built with it.)
     K > 3 formats: when the prologue finds the reference's scales to be exact doublings of each other (FLAG_SDOUBLE,
     the usual case), the element path derives (s, 1/s) from the exponent code by integer arithmetic instead of loading
     them (lookup_scale_fast); otherwise it keeps the table look-up.  Both kinds of table must occur over a sweep of
@@ -874,12 +878,13 @@ def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact
     denormals, NaN / inf, per tensor (stream kernel) and per channel (row kernel)."""
     from fp8_quantization_b200._lib import SIGNATURES
 
-    sim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfp8fq_sim_fulltilecl.so"))
+    sim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build",
+                                   "libfp8fq_sim_fulltilecl.so" if which == "sdouble" else "libfp8fq_sim.so"))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(sim, name)
         fn.restype, fn.argtypes = res, args
     rng = np.random.default_rng(40 + M)
-    FLAG_SDOUBLE, H_FLAGS = 8, 4
+    FLAG_SDOUBLE, H_FLAGS = (8 if which == "sdouble" else 16), 4
     kinds = {True: 0, False: 0}
     mvs = np.exp(rng.uniform(np.log(0.02), np.log(60.0), 48)).astype(np.float32)
     n = 4096 + 64

@@ -456,7 +456,7 @@ def test_empirical_quant_error_flow_vs_reference_golden(simdev):
 
 
 def test_fused_epilogues_fall_back_beyond_their_index_range(simdev):
-    """Tensors of ops.MAX_FUSED_ELEMS (2^32) elements or more are outside the fused batch-norm kernels' 32-bit index
+    """Tensors of ops.MAX_FUSED_ELEMS (2^31) elements or more are outside the fused batch-norm kernels' 32-bit index
     arithmetic: the module layer composes F.batch_norm -> activation -> the (64-bit-indexed) plain quantiser instead of
     raising.  Exercised here by lowering the limit."""
     from fp8_quantization_b200 import modules, ops

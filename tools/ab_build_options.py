@@ -34,6 +34,8 @@ VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_
 # round 2, third A/B (profiles/ab_build_options_r02i.json): resident CTAs per SM of the channel-innermost variants -- 6 for
 # the constant-CTA-size instantiations became the default; "cl5" is the previous setting, "cl6_dyn" also the DYN ones at 6
 VARIANTS_R2C = {"cl5": ["FQ_MINB_CL=5"], "cl6_dyn": ["FQ_MINB_CL_DYN=6"]}
+# round 2, fourth A/B: the scaled-domain element path of the K > 3 formats (FP8FQ_MAGIC, default on) against the look-up
+VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"]}
 FULL_BENCH = {"cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
@@ -117,6 +119,7 @@ def main():
     if not args.round1_only:
         variants.update(VARIANTS_R2)
         variants.update(VARIANTS_R2C)
+        variants.update(VARIANTS_R2D)
     if args.only:
         variants = {k: v for k, v in variants.items() if k in set(args.only.split(",")) | {"default"}}
     for name, defines in variants.items():

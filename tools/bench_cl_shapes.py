@@ -12,9 +12,12 @@ try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except (OSError, ValueError, KeyError):
     PEAK = 6650.0
-q4 = fq.FPQuantizer(8, mantissa_bits=4, maxval=4.0)
-q5 = fq.FPQuantizer(8, mantissa_bits=5, maxval=4.0)
-out = {"batch": B, "peak_gbs": PEAK, "sites": []}
+# CL_MAXVAL: the range decides which element path a K > 3 table takes (FLAG_MAGIC, csrc/fp8fq_core.h prep_finish):
+# e.g. 3.0 qualifies for M = 4, 4.0 does not (its scale table is not an exact doubling table)
+MAXVAL = float(os.environ.get("CL_MAXVAL", "4.0"))
+q4 = fq.FPQuantizer(8, mantissa_bits=4, maxval=MAXVAL)
+q5 = fq.FPQuantizer(8, mantissa_bits=5, maxval=MAXVAL)
+out = {"batch": B, "peak_gbs": PEAK, "maxval": MAXVAL, "sites": []}
 for (C, H) in ((32, 112), (96, 112), (96, 56), (144, 56), (144, 28), (192, 28), (384, 14), (576, 14), (960, 7), (1280, 7), (64, 56)):
     n = B * C * H * H
     nbuf = max(2, min(16, int(600e6 // (n * 4)) + 1))
@@ -25,6 +28,7 @@ for (C, H) in ((32, 112), (96, 112), (96, 56), (144, 56), (144, 28), (192, 28), 
     rec = {"shape": [B, C, H, H]}
     for name, q, M, act in (("bn_relu6_quant_M4", q4, 4.0, 2), ("bn_relu_quant_M5", q5, 5.0, 1)):
         tb, _ = q.table_for(xs[0])
+        out.setdefault("table_flags", {})[name] = int(tb.view(torch.int32)[4].item()) & 0xff
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

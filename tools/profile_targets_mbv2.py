@@ -11,7 +11,7 @@ from fp8_quantization_b200 import ops, workloads
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 CL = torch.channels_last
-q4 = fq.FPQuantizer(8, mantissa_bits=4, maxval=4.0)
+q4 = fq.FPQuantizer(8, mantissa_bits=4, maxval=float(os.environ.get("CL_MAXVAL", "4.0")))   # 3.0: a FLAG_MAGIC table
 sites = []
 for (C, H) in ((96, 56), (144, 56), (384, 14), (32, 112)):
     x = torch.randn(B, C, H, H, device=dev)
