@@ -46,6 +46,8 @@ enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8
 constexpr uint32_t kBandMask = 0xfffffu;
 // FLAG_MAGIC: how far (ulps) a switching point T_k may sit from its ideal position s_k * 2^M (see prep_finish)
 constexpr int kMagicMaxDev = 128;
+// ... and how far (ulps) the normalised scales / reciprocals of the two groups of a two-group table may differ
+constexpr int kMagicGroupUlps = 16;   // (11 ulps occur: bias in [8, 16), |y| in [16, 32))
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
@@ -308,17 +310,41 @@ FQ_HD void prep_finish(float* tab, int M, int K, float mv) {
     // itself, which BOTH spacings contain -- it rounds to it either way as long as the distance stays far below half
     // the finer spacing (2^(21-M) ulps).  Checked here per table: every T_k within kMagicMaxDev ulps of s_k * 2^M.
     // K == 1 formats qualify too (p is always 0).
-    bool magic = (K == 1 ? (!rsnan && is_normal_pos(sr[2]) && is_normal_pos(sr[3])) : dbl) && M >= 1 && M <= kMaxM;
+    // Two-group tables: where |(k - M) - bias| crosses into a binade coarser than the one bias was rounded in, the
+    // reference's subtraction rounds and the scales of the codes on either side of that point, each group an exact
+    // doubling sequence in itself, differ by a few ulps after normalisation (s_k * 2^-(k-1)).  E3M4 with maxval in
+    // [2, 8) -- the usual range behind a ReLU6 -- is the typical case: code 1 against codes 2..7.  Such a table
+    // qualifies as well: the rounding runs with group a's reciprocal for every element (a quotient perturbed by the
+    // <= kMagicGroupUlps difference, covered by a wider tie guard, magic_consts), and the final multiply takes the scale
+    // of the element's own group, decided by comparing |xc| with the reference's own switching point T_{kb+1} -- an
+    // exact classification, so the one boundary whose two sides are different floats is resolved as the reference does.
+    int kb = 0;   // last code of group a (0: one group)
+    bool magic = !rsnan && !(flags & FLAG_IRREGULAR) && M >= 1 && M <= kMaxM;
+    for (int k = 1; k <= K && magic; ++k) magic = is_normal_pos(sr[2 * k]) && is_normal_pos(sr[2 * k + 1]);
+    if (magic && K >= 2) {
+      auto sn = [&](int k) { return (int64_t)f2u(sr[2 * k]) - ((int64_t)(k - 1) << 23); };
+      auto rn = [&](int k) { return (int64_t)f2u(sr[2 * k + 1]) + ((int64_t)(k - 1) << 23); };
+      int g = 1;
+      while (g < K && sn(g + 1) == sn(1) && rn(g + 1) == rn(1)) ++g;
+      if (g < K) {
+        kb = g;
+        for (int k = kb + 2; k <= K && magic; ++k) magic = sn(k) == sn(kb + 1) && rn(k) == rn(kb + 1);
+        const int64_t ds = sn(kb + 1) - sn(1), dr = rn(kb + 1) - rn(1);
+        magic = magic && ds >= -kMagicGroupUlps && ds <= kMagicGroupUlps && dr >= -kMagicGroupUlps && dr <= kMagicGroupUlps &&
+                sn(kb + 1) >= 0x00800000 && sn(kb + 1) < 0x7f800000 && M <= 8;   // (M: the wider guard of magic_consts)
+      }
+    }
     for (int k = 2; k <= K && magic; ++k) {
       const float ideal = ldexpf(sr[2 * k], M);
       const int64_t dev = (int64_t)f2u(thr[k - 1]) - (int64_t)f2u(ideal);
       magic = is_normal_pos(ideal) && is_normal_pos(thr[k - 1]) && dev >= -kMagicMaxDev && dev <= kMagicMaxDev;
     }
     // no upper clamp of p in the element path: the largest clamped input must lie inside the top binade of the scaled
-    // domain, maxval / s_1 < 2^(M+K) with room for the rounding of the reciprocal multiply; and nothing may overflow
+    // domain, maxval / s_1 < 2^(M+K) with room for the perturbations above; and nothing may overflow
     magic = magic && is_normal_pos(ldexpf(sr[2], M + K + 1)) && is_normal_pos(mv) &&
-            mul_rn(mul_rn(mv, sr[3]), 1.0f + 1.0f / 1048576.0f) < ldexpf(1.0f, M + K) && M + K + 24 < 127;
+            mul_rn(mul_rn(mv, sr[3]), 1.0f + 1.0f / 65536.0f) < ldexpf(1.0f, M + K) && M + K + 24 < 127;
     if (magic) flags |= FLAG_MAGIC;
+    tab[H_K] = u2f((uint32_t)K | ((uint32_t)(magic ? kb : 0) << 8));
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);
@@ -414,14 +440,27 @@ FQ_HD float uq_quant(float x, float scale, float rs, float zp, float imin, float
 // ---- FLAG_MAGIC tables: the element path in the scaled domain (see prep_finish) ----------------------------------
 // Per-table constants, all derived from (M, tie guard, s_1, 1/s_1).
 struct MagicConsts {
-  float s1, r1;        // scale of code 1 and its reciprocal
+  float s1, r1;        // scale of code 1 and its reciprocal (group a)
+  float sb, tb;        // two-group tables: normalised scale of group b and the switching point |xc| >= tb that selects
+                       // it; one group: sb == s1, tb = NaN (never)
   float kap;           // guard * 2^p == C * kap for the magic constant C = 2^(p+23)
   uint32_t lo, add;    // bits(C) = max(bits(u) & 0x7f800000, lo) + add
+  bool two;
 };
-FQ_HD MagicConsts magic_consts(int M, float guard, float s1, float r1) {
+// tab: the channel table; ld reads one float of it (global or shared memory)
+template <typename Ld>
+FQ_HD MagicConsts magic_consts(const float* tab, int K, uint32_t flags, Ld ld) {
+  const int M = flags_M(flags);
+  const int kb = (int)(f2u(ld(tab + H_K)) >> 8);
   MagicConsts m;
-  m.s1 = s1;
-  m.r1 = r1;
+  m.s1 = ld(tab + off_sr(K) + 2);
+  m.r1 = ld(tab + off_sr(K) + 3);
+  m.two = kb != 0;
+  m.sb = m.two ? u2f(f2u(ld(tab + off_sr(K) + 2 * K)) - ((uint32_t)(K - 1) << 23)) : m.s1;
+  m.tb = m.two ? ld(tab + kHdr + kb) : u2f(0x7fc00000u);
+  // tie guard: 1/2 - 2^(M-20) (tie_guard); two groups: the quotient of a group-b element is taken with group a's
+  // reciprocal, i.e. perturbed by up to kMagicGroupUlps more ulps -- (16 + 1.5) * 2^-23 * 2^(M+1) < 2^(M-17)
+  const float guard = m.two ? 0.5f - ldexpf(1.0f, M - 17) : ld(tab + H_GUARD);
   m.kap = guard * (1.0f / 8388608.0f);                        // 2^-23
   m.lo = (uint32_t)(127 + M) << 23;                           // exponent field of 2^M: p = 0 up to u < 2^(M+1)
   m.add = (uint32_t)(23 - M) << 23;                           // -> exponent p + 23 (u >= 0: u + C stays in C's binade)
@@ -430,7 +469,7 @@ FQ_HD MagicConsts magic_consts(int M, float guard, float s1, float r1) {
 // One element.  Returns |y| (the caller restores the sign of xc: a negative value that rounds to zero is -0.0 in the
 // reference); *ok is false when the reciprocal multiply landed within the guard band of a rounding tie (or xc is NaN):
 // the caller must then take the exact path.  Instruction count: FMUL, LOP, integer max, integer add, 3 FADD, FMUL,
-// FSETP, FMUL -- no table access, no FRND.  There is no upper clamp of p: prep_finish sets FLAG_MAGIC only when the
+// FSETP, FMUL (+ FSETP, FSEL for a two-group table) -- no table access, no FRND.  There is no upper clamp of p: prep_finish sets FLAG_MAGIC only when the
 // largest clamped input, maxval / s_1, lies inside the top binade [2^(M+K-1), 2^(M+K)).
 FQ_HD float quant_magic(float xc, const MagicConsts& m, bool* ok) {
   const float u = mul_rn(fabsf(xc), m.r1);
@@ -439,7 +478,7 @@ FQ_HD float quant_magic(float xc, const MagicConsts& m, bool* ok) {
   const float C = u2f(cb);
   const float qu = sub_rn(add_rn(u, C), C);                   // u rounded half-to-even to a multiple of 2^p
   *ok = fabsf(sub_rn(u, qu)) < mul_rn(C, m.kap);
-  return mul_rn(qu, m.s1);
+  return mul_rn(qu, fabsf(xc) >= m.tb ? m.sb : m.s1);
 }
 
 FQ_HD float quant_core(float xc, float s, float rs, float guard, float* q_out) {

@@ -271,7 +271,7 @@ struct ElemCtx {
   uint32_t ref, band;   // KMODE 1: exponent-arithmetic fast path (lookup_code_fast)
   bool dbl;             // KMODE 1: FLAG_SDOUBLE table -- (s, 1/s) by integer arithmetic (lookup_scale_fast), no load
   uint32_t s1b, r1b, tmax;
-  bool magic;           // KMODE 1: FLAG_MAGIC table -- the element path in the scaled domain (quant_magic), no look-up
+  bool magic;           // KMODE 0 / 1: FLAG_MAGIC table -- the element path in the scaled domain (quant_magic), no look-up
   MagicConsts mc;
 };
 
@@ -333,8 +333,13 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 // clamp instead of 15+ (no code look-up, no (s, 1/s) gather, no FRND), same bits: the tie guard of the reciprocal
 // multiply is kept, and a vector with a lane inside it (or a NaN) re-runs the look-up path.  The code-plane variant
 // (CODES) keeps the look-up path: its exponent codes follow the reference's switching points exactly.
+// Two-group tables (prep_finish) pay one compare and one select more for the scale of the element's group.
+// FP8FQ_MAGIC_K0: also for the formats with <= 3 exponent codes (M >= 5), in place of their register select.
 #ifndef FP8FQ_MAGIC
 #define FP8FQ_MAGIC 1
+#endif
+#ifndef FP8FQ_MAGIC_K0
+#define FP8FQ_MAGIC_K0 1
 #endif
 // FP8FQ_PACK2 (build option): the independent fp32 multiplies / adds / FMAs of neighbouring elements are issued as
 // sm_100's two-wide instructions (FMUL2 / FADD2 / FFMA2: same IEEE round-to-nearest results, half the issue slots).
@@ -412,20 +417,26 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
   bool slow = false;
 #pragma unroll
   for (int k = 0; k < N; ++k) xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
-  if (KMODE == 1 && FP8FQ_MAGIC && !CODES && s_out == nullptr && c.magic) {
+  if ((KMODE == 1 || (KMODE == 0 && FP8FQ_MAGIC_K0)) && FP8FQ_MAGIC && !CODES && s_out == nullptr && c.magic) {
     // scaled-domain path (FP8FQ_MAGIC above); one exactness check per vector, like the look-up path
     bool all_ok = true;
+    auto body = [&](auto two_tag) {
+      constexpr bool kTwo = decltype(two_tag)::value;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const float u = mul_rn(fabsf(xc[k]), c.mc.r1);
-      uint32_t cb = f2u(u) & 0x7f800000u;
-      cb = (cb < c.mc.lo ? c.mc.lo : cb) + c.mc.add;
-      const float C = u2f(cb);
-      const float qu = sub_rn(add_rn(u, C), C);
-      if (GUARD) all_ok &= fabsf(sub_rn(u, qu)) < mul_rn(C, c.mc.kap);
-      const float ya = mul_rn(qu, c.mc.s1);
-      y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
-    }
+      for (int k = 0; k < N; ++k) {
+        const float a = fabsf(xc[k]);
+        const float u = mul_rn(a, c.mc.r1);
+        uint32_t cb = f2u(u) & 0x7f800000u;
+        cb = (cb < c.mc.lo ? c.mc.lo : cb) + c.mc.add;
+        const float C = u2f(cb);
+        const float qu = sub_rn(add_rn(u, C), C);
+        if (GUARD) all_ok &= fabsf(sub_rn(u, qu)) < mul_rn(C, c.mc.kap);
+        const float ya = mul_rn(qu, kTwo ? (a >= c.mc.tb ? c.mc.sb : c.mc.s1) : c.mc.s1);
+        y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
+      }
+    };
+    if (c.mc.two) body(std::true_type{});
+    else body(std::false_type{});
     if (!GUARD || all_ok) return;
   }
   if (KMODE == 0) {
@@ -580,7 +591,9 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.ref = 0;
     c.band = 0;
     c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
-    c.magic = false;
+    const uint32_t fl = f2u(ld(tab + H_FLAGS));
+    c.magic = FP8FQ_MAGIC && FP8FQ_MAGIC_K0 && (fl & FLAG_MAGIC) != 0;
+    c.mc = magic_consts(tab, K, fl, ld);
   } else {
     const uint32_t fl = f2u(ld(tab + H_FLAGS));
     c.base = f2u(ld(tab + H_BASE));
@@ -592,7 +605,7 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.r1b = f2u(ld(tab + off_sr(K) + 3));
     c.tmax = (uint32_t)(K - 1) << 23;
     c.magic = FP8FQ_MAGIC && (fl & FLAG_MAGIC) != 0;
-    c.mc = magic_consts(flags_M(fl), c.guard, u2f(c.s1b), u2f(c.r1b));
+    c.mc = magic_consts(tab, K, fl, ld);
   }
 }
 template <int KMODE>

@@ -46,7 +46,7 @@ int emul_fake_quant(const float* x, float* y, int32_t* codes, const float* table
     // force_irregular: 0 = as the kernels run (FLAG_MAGIC tables take the scaled-domain path, quant_vec<1, false>),
     // 1 = linear threshold scan, 2 = the table path even for FLAG_MAGIC tables (what the code-plane variant runs)
     const bool magic = force_irregular == 0 && codes == nullptr && (f2u(tab[H_FLAGS]) & FLAG_MAGIC) != 0;
-    const MagicConsts mc = magic_consts(flags_M(f2u(tab[H_FLAGS])), guard, tab[off_sr(K) + 2], tab[off_sr(K) + 3]);
+    const MagicConsts mc = magic_consts(tab, K, f2u(tab[H_FLAGS]), [](const float* p) { return *p; });
     for (int64_t i = 0; i < inner; ++i) {
       const float v = x[c * inner + i];
       const float xc = min_nan(max_nan(v, lo), hi);
@@ -121,6 +121,13 @@ int emul_table_flags(const float* table, int64_t c, float mantissa_bits, int n_b
 }
 
 // mantissa band of the exponent-arithmetic fast path (ulps); 0x7fffff = fast path disabled for this channel
+// 0: one scale group (or not a FLAG_MAGIC table); kb >= 1: codes 1..kb / kb+1..K are the two groups
+int emul_table_break(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
+  int M, E, K;
+  if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;
+  return (int)(f2u(table[c * table_stride(K) + H_K]) >> 8);
+}
+
 int emul_table_band(const float* table, int64_t c, float mantissa_bits, int n_bits, int sign_bits) {
   int M, E, K;
   if (format_split(mantissa_bits, n_bits, sign_bits, &M, &E, &K) != 0) return -1;

@@ -35,8 +35,8 @@ VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_
 # the constant-CTA-size instantiations became the default; "cl5" is the previous setting, "cl6_dyn" also the DYN ones at 6
 VARIANTS_R2C = {"cl5": ["FQ_MINB_CL=5"], "cl6_dyn": ["FQ_MINB_CL_DYN=6"]}
 # round 2, fourth A/B: the scaled-domain element path of the K > 3 formats (FP8FQ_MAGIC, default on) against the look-up
-VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"]}
-FULL_BENCH = {"cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
+VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k1": ["FP8FQ_MAGIC_K0=0"]}   # magic_k1: not for the K <= 3 formats
+FULL_BENCH = {"magic_k1", "nomagic", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
 def hash_leg(device="cuda:0"):

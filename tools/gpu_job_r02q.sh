@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 GPU job "q" (two-group scale tables and K <= 3 formats on the scaled-domain path): tests, A/B of the scaled-domain element path (FP8FQ_MAGIC), channel-innermost shapes, MSE, bench, ncu.
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02q_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 1200 python tools/ab_build_options.py --only nomagic,magic_k1 > gpurun_out/r02q_ab.log 2>&1; echo "ab rc=$?"
+cp gpurun_out/ab_build_options.json gpurun_out/ab_build_options_r02q.json
+for mv in 3.0; do
+  CL_MAXVAL=$mv CL_JSON=cl_shapes_r02q_mv3_default.json timeout 300 python tools/bench_cl_shapes.py > gpurun_out/r02q_cl_mv3_default.log 2>&1
+  FP8FQ_LIB=$PWD/build_variants/libfp8fq_nomagic.so CL_MAXVAL=$mv CL_JSON=cl_shapes_r02q_mv3_nomagic.json timeout 300 python tools/bench_cl_shapes.py > gpurun_out/r02q_cl_mv3_nomagic.log 2>&1
+done
+MSE_JSON=mse_r02q_default.json timeout 300 python tools/bench_mse.py > /dev/null 2>&1
+FP8FQ_LIB=$PWD/build_variants/libfp8fq_nomagic.so MSE_JSON=mse_r02q_nomagic.json timeout 300 python tools/bench_mse.py > /dev/null 2>&1
+FP8FQ_LIB=$PWD/build_variants/libfp8fq_magic_k1.so MSE_JSON=mse_r02q_magic_k1.json timeout 300 python tools/bench_mse.py > /dev/null 2>&1
+timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_r02q.json 2> gpurun_out/bench_r02q.err; echo "bench rc=$?"
+CL_MAXVAL=3.0 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:fq_ -o gpurun_out/prof_mbv2_r02q -f python tools/profile_targets_mbv2.py > gpurun_out/ncu_mbv2_r02q.log 2>&1; echo "ncu rc=$?"
+tail -3 gpurun_out/r02q_pytest.log
