@@ -572,6 +572,29 @@ def dp_parity_leg(model, x_img, build_model, memory_format, fq, workloads, fq_di
 # ---------------------------------------------------------------------------------------------------------
 # extra BASELINE configs (N = 1)
 # ---------------------------------------------------------------------------------------------------------
+def table_paths(model):
+    """Which element path the quantiser tables of a calibrated model take (flags word of each channel table, csrc/fp8fq_core.h
+    prep_finish): the scaled-domain path (one or two scale groups) or the look-up path."""
+    from fp8_quantization_b200.quantizers import FPQuantizer
+
+    out = {"per_tensor": {"scaled_one_group": 0, "scaled_two_groups": 0, "look_up": 0},
+           "per_channel_rows": {"scaled_one_group": 0, "scaled_two_groups": 0, "look_up": 0}}
+    for q in model.modules():
+        if not isinstance(q, FPQuantizer) or getattr(q, "_table", None) is None:
+            continue
+        t = q._table
+        C = int(q.maxval.numel()) if hasattr(q, "maxval") and torch.is_tensor(q.maxval) else 1
+        C = max(C, 1)
+        tab = t.reshape(C, -1).view(torch.int32)
+        magic = (tab[:, 4] & 16) != 0
+        two = (tab[:, 5] >> 8) != 0
+        d = out["per_tensor" if C == 1 else "per_channel_rows"]
+        d["scaled_one_group"] += int((magic & ~two).sum())
+        d["scaled_two_groups"] += int((magic & two).sum())
+        d["look_up"] += int((~magic).sum())
+    return out
+
+
 def leg_c3_mobilenetv2(args, dev, ops, workloads, peak, steps):
     """BASELINE config 3: MobileNetV2, FP8 M=4 per-channel + BN-fused modules, synthetic 3x224x224: the hot-path step
     (every library call of one validate forward, replayed as one CUDA graph) and the whole forward, both layouts."""
@@ -589,6 +612,7 @@ def leg_c3_mobilenetv2(args, dev, ops, workloads, peak, steps):
         ms = time_ms(g.replay, steps)
         nbytes = st["stream_bytes"] + 8 * st["weight_elems"]
         rec = {"ms_per_step": ms, "value": st["elems"] / (ms * 1e-3) / 1e9, "unit": UNIT, "launches_per_step": st["launches"],
+               "element_path": table_paths(m),
                "elems_per_step": st["elems"], "algorithmic_bytes_per_step": nbytes,
                "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": nbytes / (ms * 1e-3) / 1e9 / peak,

@@ -339,7 +339,19 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 #define FP8FQ_MAGIC 1
 #endif
 #ifndef FP8FQ_MAGIC_K0
-#define FP8FQ_MAGIC_K0 1
+#define FP8FQ_MAGIC_K0 0
+#endif
+// FP8FQ_MAGIC_ONEPATH: one instantiation of the scaled-domain loop for one- and two-group tables (always the select).
+// FP8FQ_MAGIC_SELFSLOW: lanes inside the tie guard are finished by an IEEE division inside the scaled-domain path
+// instead of re-running the whole vector through the look-up path.
+#ifndef FP8FQ_MAGIC_HOIST
+#define FP8FQ_MAGIC_HOIST 1
+#endif
+#ifndef FP8FQ_MAGIC_ONEPATH
+#define FP8FQ_MAGIC_ONEPATH 0
+#endif
+#ifndef FP8FQ_MAGIC_SELFSLOW
+#define FP8FQ_MAGIC_SELFSLOW 0
 #endif
 // FP8FQ_PACK2 (build option): the independent fp32 multiplies / adds / FMAs of neighbouring elements are issued as
 // sm_100's two-wide instructions (FMUL2 / FADD2 / FFMA2: same IEEE round-to-nearest results, half the issue slots).
@@ -385,7 +397,14 @@ __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
 // without FLAG_RSNAN).
 // SIGNED_OUT = false: the caller only needs |y| (the MSE kernel, which forms |x| - |y|); the magic path then skips
 // restoring the sign.
-template <int KMODE, bool CODES, int N, bool STAB_SHARED = false, bool GUARD = true, bool SIGNED_OUT = true>
+// MM: what the caller already knows about the table (fq_stream_kernel decides once per launch and instantiates its tile
+// loop per case, FP8FQ_MAGIC_HOIST): 0 = nothing, look at c.magic / c.mc.two here; 1 = a one-group FLAG_MAGIC table;
+// 2 = a two-group one; 3 = not a FLAG_MAGIC table.  With MM = 1 / 2 the lanes inside the tie guard are finished inside
+// the scaled-domain path, so those instantiations carry no look-up code at all.
+// NONNEG: the caller passes |x| and the format is signed (clamp bounds -maxval / +maxval): |clamp(x)| = min(|x|, maxval),
+// so the lower clamp is skipped (the MSE kernel, which takes |x| once and sweeps hundreds of candidate tables over it).
+template <int KMODE, bool CODES, int N, bool STAB_SHARED = false, bool GUARD = true, bool SIGNED_OUT = true, int MM = 0,
+          bool NONNEG = false>
 __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMODE>& c, float (&y)[N], int32_t (&code)[N],
                                           float* s_out = nullptr) {
   if (KMODE == 2) {  // INT uniform quantiser: c.rt = {zp, sat, scale, -, -, 1/scale, -, -}, c.lo/hi = int_min/int_max
@@ -416,8 +435,9 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
   int e[N];
   bool slow = false;
 #pragma unroll
-  for (int k = 0; k < N; ++k) xc[k] = min_nan(max_nan(v[k], c.lo), c.hi);
-  if ((KMODE == 1 || (KMODE == 0 && FP8FQ_MAGIC_K0)) && FP8FQ_MAGIC && !CODES && s_out == nullptr && c.magic) {
+  for (int k = 0; k < N; ++k) xc[k] = NONNEG ? min_nan(v[k], c.hi) : min_nan(max_nan(v[k], c.lo), c.hi);
+  constexpr bool kCanMagic = (KMODE == 1 || (KMODE == 0 && FP8FQ_MAGIC_K0)) && FP8FQ_MAGIC && !CODES;
+  if (kCanMagic && s_out == nullptr && MM != 3 && (MM != 0 || c.magic)) {
     // scaled-domain path (FP8FQ_MAGIC above); one exactness check per vector, like the look-up path
     bool all_ok = true;
     auto body = [&](auto two_tag) {
@@ -435,9 +455,29 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
         y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
       }
     };
-    if (c.mc.two) body(std::true_type{});
+    if (MM == 2 || (MM == 0 && (FP8FQ_MAGIC_ONEPATH || c.mc.two))) body(std::true_type{});   // (one group: tb is NaN, the select keeps s1)
     else body(std::false_type{});
     if (!GUARD || all_ok) return;
+    if (FP8FQ_MAGIC_SELFSLOW || MM != 0) {
+    // a lane within the guard band of a rounding tie (or NaN): the reference's own arithmetic for that lane -- IEEE
+    // division by the scale of its code, s' * 2^p (a tie is half a step away from every code boundary, so p is the
+    // reference's code here) -- without leaving the scaled-domain path
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float a = fabsf(xc[k]);
+      const float u = mul_rn(a, c.mc.r1);
+      uint32_t t = f2u(u) & 0x7f800000u;
+      t = t < c.mc.lo ? c.mc.lo : t;
+      const float C = u2f(t + c.mc.add);
+      const float qu = sub_rn(add_rn(u, C), C);
+      if (!(fabsf(sub_rn(u, qu)) < mul_rn(C, c.mc.kap))) {
+        const float se = u2f(f2u(a >= c.mc.tb ? c.mc.sb : c.mc.s1) + (t - c.mc.lo));
+        const float ya = mul_rn(nearbyintf(div_rn(a, se)), se);
+        y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
+      }
+    }
+    return;
+    }
   }
   if (KMODE == 0) {
 #pragma unroll
@@ -591,9 +631,12 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.ref = 0;
     c.band = 0;
     c.dbl = false; c.s1b = c.r1b = c.tmax = 0;
-    const uint32_t fl = f2u(ld(tab + H_FLAGS));
-    c.magic = FP8FQ_MAGIC && FP8FQ_MAGIC_K0 && (fl & FLAG_MAGIC) != 0;
-    c.mc = magic_consts(tab, K, fl, ld);
+    c.magic = false;
+    if (FP8FQ_MAGIC && FP8FQ_MAGIC_K0) {
+      const uint32_t fl = f2u(ld(tab + H_FLAGS));
+      c.magic = (fl & FLAG_MAGIC) != 0;
+      c.mc = magic_consts(tab, K, fl, ld);
+    }
   } else {
     const uint32_t fl = f2u(ld(tab + H_FLAGS));
     c.base = f2u(ld(tab + H_BASE));
@@ -740,6 +783,13 @@ fq_stream_kernel(const StreamArgs a) {
 #define FQ_ACT a.act   // (-DFP8FQ_FOLD_ACT=0 -DFP8FQ_FULL_TILE=0: token for token the code of the round-1 profiles)
 #endif
 
+  // FP8FQ_MAGIC_HOIST: which element path the launch's table takes is decided HERE, once, and the tile loop is
+  // instantiated per case (quant_vec's MM), so that the per-vector code is straight-line: the scaled-domain loop of that
+  // table kind with its own finish for tie-guard lanes, or the look-up path -- not all three behind uniform branches in
+  // every vector.  (The block tails, with two tables per element, keep the run-time form.)
+  constexpr bool kHoist = FP8FQ_MAGIC_HOIST && FP8FQ_MAGIC && !CODES && !kTail && (KMODE == 1 || (KMODE == 0 && FP8FQ_MAGIC_K0));
+  auto run_tiles = [&](auto mm_tag) {
+  constexpr int MM = decltype(mm_tag)::value;
   for (idx_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const idx_t tile0 = tile * kTile;
 #if FP8FQ_FULL_TILE
@@ -844,7 +894,7 @@ fq_stream_kernel(const StreamArgs a) {
         for (int k = 0; k < VEC; ++k) v[k] = apply_act(add_rn(t[k], in2[u].v[k]), FQ_ACT);
       }
       if (kTail) quant_vec<KMODE, CODES, VEC>(v, ctx2, yv, cd);
-      else quant_vec<KMODE, CODES, VEC>(v, ctx, yv, cd);
+      else quant_vec<KMODE, CODES, VEC, false, true, true, MM>(v, ctx, yv, cd);
       Pack<VEC> out;
       IPack<VEC> co;
 #pragma unroll
@@ -862,6 +912,14 @@ fq_stream_kernel(const StreamArgs a) {
     if ((!kCL || FP8FQ_FULL_TILE_CL) && tile0 + kTile <= nvec_elems) tile_body(std::true_type{});
     else tile_body(std::false_type{});
 #endif
+  }
+  };
+  if (kHoist) {
+    if (!ctx.magic) run_tiles(std::integral_constant<int, 3>{});
+    else if (ctx.mc.two) run_tiles(std::integral_constant<int, 2>{});
+    else run_tiles(std::integral_constant<int, 1>{});
+  } else {
+    run_tiles(std::integral_constant<int, 0>{});
   }
   // scalar tail (n % VEC elements), VEC == 4 only
   if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(a.n - nvec_elems)) {
@@ -919,8 +977,13 @@ struct RowsArgs {
 // took 27.0 us.
 constexpr int kRowsWarpChunk = 1024;
 constexpr int kRowsWarps = 4;
+// FQ_ROWS_MINB: resident CTAs per SM the row kernel is compiled for (6 x 128 threads -> at most 80 registers; the K > 3
+// instantiation with both element paths inlined would otherwise take 95)
+#ifndef FQ_ROWS_MINB
+#define FQ_ROWS_MINB 6
+#endif
 template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(kRowsWarps * 32) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__(kRowsWarps * 32, KMODE == 1 ? FQ_ROWS_MINB : 1) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
@@ -1644,7 +1707,9 @@ __global__ void mse_finish_kernel(const double* __restrict__ acc, int64_t GC, do
 // Measured on B200 (tools/bench_mse.py): 1.47 T candidate evaluations/s on [64,64,56,56] x 666 candidates; the first
 // version (table double-buffered per candidate behind a barrier, 8 elements per thread, shared double atomics) 0.75 T.
 constexpr int kMseThreads = 256;
-template <int KMODE, int EPT>
+// ABS (signed formats): the elements are kept as |x| -- the squared error only needs |x| - |y|, and |clamp(x)| is then
+// one min per candidate instead of a max and a min.
+template <int KMODE, int EPT, bool ABS>
 __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __restrict__ x, int64_t inner, int64_t C,
                                                                   const float* __restrict__ tables, int G, int K,
                                                                   int gpb, double* __restrict__ acc) {
@@ -1667,6 +1732,7 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
   for (int u = 0; u < EPT; ++u) {
     const int64_t i = beg + (int64_t)u * kMseThreads + threadIdx.x;
     v[u] = i < inner ? __ldg(xr + i) : 0.0f;
+    if (ABS) v[u] = fabsf(v[u]);
   }
   for (int g0 = 0; g0 < G; g0 += gpb) {
     const int ng = (G - g0 < gpb) ? G - g0 : gpb;
@@ -1691,8 +1757,8 @@ __global__ void __launch_bounds__(kMseThreads) mse_grid_kernel(const float* __re
       for (int u = 0; u < EPT; u += 4) {
         float vi[4] = {v[u], v[u + 1], v[u + 2], v[u + 3]}, yo[4];
         int32_t cd[4];
-        if (guarded) quant_vec<KMODE, false, 4, true, true, false>(vi, ctx, yo, cd);
-        else quant_vec<KMODE, false, 4, true, false, false>(vi, ctx, yo, cd);
+        if (guarded) quant_vec<KMODE, false, 4, true, true, false, 0, ABS>(vi, ctx, yo, cd);
+        else quant_vec<KMODE, false, 4, true, false, false, 0, ABS>(vi, ctx, yo, cd);
         // y has the sign of x or is zero, so |x| - |y| is x - y up to that sign: the same square (and the scaled-domain
         // path need not restore the sign)
         float d[4];
@@ -2508,12 +2574,13 @@ int fp8fq_mse_grid_f32(const float* x, int64_t n, int64_t C, int64_t inner, cons
       const size_t smem = sizeof(float) * (size_t)gpb * strideP + part_bytes;
       const float* tb = tables + gs * C * stride;
       double* ac = acc + gs * C;
-      if (K <= 3) {
-        if (ept == 16) launch_plain(mse_grid_kernel<0, 16>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
-        else launch_plain(mse_grid_kernel<0, 4>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
+      auto go = [&](auto kern) { launch_plain(kern, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac); };
+      if (sign_bits != 0) {
+        if (K <= 3) { if (ept == 16) go(mse_grid_kernel<0, 16, true>); else go(mse_grid_kernel<0, 4, true>); }
+        else { if (ept == 16) go(mse_grid_kernel<1, 16, true>); else go(mse_grid_kernel<1, 4, true>); }
       } else {
-        if (ept == 16) launch_plain(mse_grid_kernel<1, 16>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
-        else launch_plain(mse_grid_kernel<1, 4>, gdim, dim3(kMseThreads), smem, st, x, inner, C, tb, Gs, K, gpb, ac);
+        if (K <= 3) { if (ept == 16) go(mse_grid_kernel<0, 16, false>); else go(mse_grid_kernel<0, 4, false>); }
+        else { if (ept == 16) go(mse_grid_kernel<1, 16, false>); else go(mse_grid_kernel<1, 4, false>); }
       }
       r = launch_status();
       if (r != FP8FQ_OK) return r;

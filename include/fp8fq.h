@@ -27,8 +27,12 @@
  *   floor(log2|x| + bias) steps to e (:128) -- is computed ONCE by fp8fq_prepare_f32 into a
  *   caller-owned device buffer of fp8fq_table_floats(...) floats and then consumed by the
  *   streaming kernels.  Layout (floats, per channel, stride = fp8fq_table_stride(...)):
- *     [0] maxval  [1] minval  [2] bucket base (int bits)  [3] bias  [4] flags (int bits)
- *     [5] K (int bits)  [6..7] reserved
+ *     [0] maxval  [1] minval  [2] bucket base (int bits)  [3] bias
+ *     [4] flags (int bits): bit 0 irregular thresholds, 1 all scales exact powers of two, 2 an unusable reciprocal,
+ *         3 scales exact doublings of each other, 4 qualifies for the scaled-domain element path; bits 8..27 mantissa
+ *         band of the exponent-arithmetic look-up (0xfffff = every mantissa); bits 28..31 M
+ *     [5] K (int bits, low 8) | last code of the first scale group of a two-group table << 8 (0: one group)
+ *     [6] tie guard of the reciprocal multiply  [7] reference point of the exponent-arithmetic look-up (int bits)
  *     [8 .. 8+KP)            thr[j], j = 0..K      (KP = K+1 rounded up to even)
  *     [8+KP .. 8+KP+2(K+1))  (scale, 1/scale)[e'], e' = 0..K
  */

@@ -132,3 +132,9 @@ def test_extra_legs_plumbing_on_the_simulation(simdev):
     assert st3["weight_launches"] == 1 and st3["weight_elems"] == 3_469_760   # one call = 2 kernel launches (48 + 5 tensors)
     assert st3["elems"] - st3["weight_elems"] == 6_896_776
     assert st3["launches"] == 1 + 42 + 10 + 2
+    # which element path the calibrated tables take (the flags word the prologue wrote)
+    paths = bench.table_paths(m3)
+    pt, pc = paths["per_tensor"], paths["per_channel_rows"]
+    assert sum(pt.values()) >= 50 and sum(pc.values()) > 1000
+    assert pt["scaled_one_group"] + pt["scaled_two_groups"] >= 0.9 * sum(pt.values()), paths
+    assert pc["scaled_one_group"] + pc["scaled_two_groups"] >= 0.9 * sum(pc.values()), paths

@@ -35,8 +35,12 @@ VARIANTS_R2 = {"pin_sel": ["FP8FQ_PIN_SEL=1"], "pack2": ["FP8FQ_PACK2=1"], "pin_
 # the constant-CTA-size instantiations became the default; "cl5" is the previous setting, "cl6_dyn" also the DYN ones at 6
 VARIANTS_R2C = {"cl5": ["FQ_MINB_CL=5"], "cl6_dyn": ["FQ_MINB_CL_DYN=6"]}
 # round 2, fourth A/B: the scaled-domain element path of the K > 3 formats (FP8FQ_MAGIC, default on) against the look-up
-VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k1": ["FP8FQ_MAGIC_K0=0"]}   # magic_k1: not for the K <= 3 formats
-FULL_BENCH = {"magic_k1", "nomagic", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
+VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k0": ["FP8FQ_MAGIC_K0=1"],   # magic_k0: the K <= 3 formats too
+                "onepath": ["FP8FQ_MAGIC_ONEPATH=1"], "selfslow": ["FP8FQ_MAGIC_SELFSLOW=1"],
+                "onepath_selfslow": ["FP8FQ_MAGIC_ONEPATH=1", "FP8FQ_MAGIC_SELFSLOW=1"],
+                # the element path decided once per launch (default) vs per vector; the K > 3 row kernel at 95 registers
+                "nohoist": ["FP8FQ_MAGIC_HOIST=0"], "rows_minb1": ["FQ_ROWS_MINB=1"]}
+FULL_BENCH = {"magic_k0", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
 def hash_leg(device="cuda:0"):

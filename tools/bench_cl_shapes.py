@@ -54,5 +54,38 @@ for (C, H) in ((32, 112), (96, 112), (96, 56), (144, 56), (144, 28), (192, 28), 
     print(rec["shape"], " ".join(f"{k}={v['gbs']:.0f}GB/s({v['us']:.1f}us)" for k, v in rec.items() if isinstance(v, dict)), flush=True)
     del xs, y
     torch.cuda.empty_cache()
+# MobileNetV2's 53 per-channel weight tensors (M = 4) in one multi-tensor call of the row kernel, graph-timed
+from fp8_quantization_b200 import workloads
+torch.manual_seed(10)
+ws = [m.weight.detach().to(dev) for m in workloads.MobileNetV2().modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+wt = []
+for w in ws:
+    qq = fq.FPQuantizer(8, per_channel=True, mantissa_bits=4, set_maxval=True)
+    wf = w.reshape(w.shape[0], -1)
+    qq.set_quant_range(wf.min(1)[0], wf.max(1)[0])
+    wt.append(qq.table_for(w)[0])
+wo = [torch.empty_like(w) for w in ws]
+call = lambda: ops.fake_quant_multi(ws, wt, [w.shape[0] for w in ws], 4.0, 8, 1, outs=wo)
+s_ = torch.cuda.Stream()
+s_.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s_):
+    call()
+torch.cuda.current_stream().wait_stream(s_)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for _ in range(10):
+        call()
+g.replay()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    g.replay()
+b.record()
+torch.cuda.synchronize()
+nw = sum(w.numel() for w in ws)
+out["mobilenetv2_weights_M4"] = {"tensors": len(ws), "elements": nw, "us_per_call": a.elapsed_time(b) / 50 * 1e3,
+                                 "note": "L2-resident (14 MB of weights, back to back)"}
+print("weights", out["mobilenetv2_weights_M4"], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("CL_JSON", "cl_shapes.json")), "w"), indent=1)

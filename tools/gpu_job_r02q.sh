@@ -13,5 +13,5 @@ MSE_JSON=mse_r02q_default.json timeout 300 python tools/bench_mse.py > /dev/null
 FP8FQ_LIB=$PWD/build_variants/libfp8fq_nomagic.so MSE_JSON=mse_r02q_nomagic.json timeout 300 python tools/bench_mse.py > /dev/null 2>&1
 FP8FQ_LIB=$PWD/build_variants/libfp8fq_magic_k1.so MSE_JSON=mse_r02q_magic_k1.json timeout 300 python tools/bench_mse.py > /dev/null 2>&1
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_r02q.json 2> gpurun_out/bench_r02q.err; echo "bench rc=$?"
-CL_MAXVAL=3.0 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:fq_ -o gpurun_out/prof_mbv2_r02q -f python tools/profile_targets_mbv2.py > gpurun_out/ncu_mbv2_r02q.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:fq_stream -o gpurun_out/prof_targets_r02q -f python tools/profile_targets.py > gpurun_out/ncu_targets_r02q.log 2>&1; echo "ncu rc=$?"
 tail -3 gpurun_out/r02q_pytest.log
