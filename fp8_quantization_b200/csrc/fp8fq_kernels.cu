@@ -273,6 +273,7 @@ struct ElemCtx {
   uint32_t s1b, r1b, tmax;
   bool magic;           // KMODE 0 / 1: FLAG_MAGIC table -- the element path in the scaled domain (quant_magic), no look-up
   MagicConsts mc;
+  int folded_act;       // activation folded into (lo, hi) by fold_act (quant_vec_cold rebuilds the context from the table)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -345,7 +346,20 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 // FP8FQ_MAGIC_SELFSLOW: lanes inside the tie guard are finished by an IEEE division inside the scaled-domain path
 // instead of re-running the whole vector through the look-up path.
 #ifndef FP8FQ_MAGIC_HOIST
-#define FP8FQ_MAGIC_HOIST 1
+#define FP8FQ_MAGIC_HOIST 0
+#endif
+// FP8FQ_COLD_CALL: in the K > 3 stream / row kernels everything that is not the scaled-domain loop -- the look-up path of
+// the few tables without FLAG_MAGIC, and the vectors with a lane inside the tie guard -- is ONE out-of-line function
+// (quant_vec_cold) instead of being inlined into each of the unrolled vector bodies: the look-up, the IEEE-division
+// fallback and their slow paths are ~4/5 of those kernels' 70-80 KB of SASS, far beyond the instruction caches, and every
+// variant added next to the hot loop had cost it 1-3 % (round 2 calls p -> q -> s).
+#ifndef FP8FQ_COLD_CALL
+#define FP8FQ_COLD_CALL 1
+#endif
+#if defined(FP8FQ_HOST_SIM)
+#define FQ_NOINLINE __attribute__((noinline))
+#else
+#define FQ_NOINLINE __noinline__
 #endif
 #ifndef FP8FQ_MAGIC_ONEPATH
 #define FP8FQ_MAGIC_ONEPATH 0
@@ -388,6 +402,7 @@ template <int KMODE>
 __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
   if (act == FP8FQ_ACT_RELU || act == FP8FQ_ACT_RELU6) c.lo = max_nan(c.lo, 0.0f);
   if (act == FP8FQ_ACT_RELU6) c.hi = min_nan(c.hi, 6.0f);
+  c.folded_act = act;
 }
 
 // Quantises N values.  One exactness check per vector: the IEEE-division fallback is entered by the whole
@@ -397,6 +412,9 @@ __device__ __forceinline__ void fold_act(ElemCtx<KMODE>& c, int act) {
 // without FLAG_RSNAN).
 // SIGNED_OUT = false: the caller only needs |y| (the MSE kernel, which forms |x| - |y|); the magic path then skips
 // restoring the sign.
+template <int KMODE, bool CODES, int N>
+__device__ FQ_NOINLINE void quant_vec_cold(const float* v, float* y, int32_t* code, const float* table, int K, int folded_act);
+
 // MM: what the caller already knows about the table (fq_stream_kernel decides once per launch and instantiates its tile
 // loop per case, FP8FQ_MAGIC_HOIST): 0 = nothing, look at c.magic / c.mc.two here; 1 = a one-group FLAG_MAGIC table;
 // 2 = a two-group one; 3 = not a FLAG_MAGIC table.  With MM = 1 / 2 the lanes inside the tie guard are finished inside
@@ -478,6 +496,10 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
     }
     return;
     }
+  }
+  if (FP8FQ_COLD_CALL && kCanMagic && KMODE == 1 && MM == 0 && !STAB_SHARED && GUARD && SIGNED_OUT && !NONNEG && s_out == nullptr) {
+    quant_vec_cold<KMODE, CODES, N>(v, y, code, c.stab, c.K, c.folded_act);
+    return;
   }
   if (KMODE == 0) {
 #pragma unroll
@@ -598,6 +620,7 @@ __device__ __forceinline__ float quant_elem(float v, const ElemCtx<KMODE>& c, in
 // the MSE kernel passes a shared-memory copy).
 template <int KMODE, typename Ld>
 __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, int K, Ld ld) {
+  c.folded_act = FP8FQ_ACT_NONE;
   if (KMODE == 2) {  // uniform table
     c.hi = ld(tab + U_IMAX);
     c.lo = ld(tab + U_IMIN);
@@ -654,6 +677,25 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
 template <int KMODE>
 __device__ __forceinline__ void load_ctx_direct(ElemCtx<KMODE>& c, const float* __restrict__ gtab, int K) {
   load_ctx<KMODE>(c, gtab, K, [](const float* p) { return __ldg(p); });
+}
+
+// The out-of-line rest of quant_vec (FP8FQ_COLD_CALL): rebuilds the element context from the (global-memory) table and
+// runs the vector through the look-up path (MM = 3) -- the IEEE-division fallback included.
+template <int KMODE, bool CODES, int N>
+__device__ FQ_NOINLINE void quant_vec_cold(const float* v, float* y, int32_t* code, const float* table, int K, int folded_act) {
+  ElemCtx<KMODE> c;
+  load_ctx_direct<KMODE>(c, table, K);
+  if (folded_act != FP8FQ_ACT_NONE) fold_act(c, folded_act);
+  float vv[N], yy[N];
+  int32_t cc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) vv[k] = v[k];
+  quant_vec<KMODE, CODES, N, false, true, true, 3>(vv, c, yy, cc);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    y[k] = yy[k];
+    if (CODES) code[k] = cc[k];
+  }
 }
 
 // Per-channel batch-norm parameters of one vector.

@@ -39,7 +39,9 @@ VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k0": ["FP8FQ_MAGIC_K0=1"], 
                 "onepath": ["FP8FQ_MAGIC_ONEPATH=1"], "selfslow": ["FP8FQ_MAGIC_SELFSLOW=1"],
                 "onepath_selfslow": ["FP8FQ_MAGIC_ONEPATH=1", "FP8FQ_MAGIC_SELFSLOW=1"],
                 # the element path decided once per launch (default) vs per vector; the K > 3 row kernel at 95 registers
-                "nohoist": ["FP8FQ_MAGIC_HOIST=0"], "rows_minb1": ["FQ_ROWS_MINB=1"]}
+                "hoist": ["FP8FQ_MAGIC_HOIST=1"], "rows_minb1": ["FQ_ROWS_MINB=1"],
+                # everything but the scaled-domain loop out of line (default) vs inlined into every vector body
+                "nocold": ["FP8FQ_COLD_CALL=0"]}
 FULL_BENCH = {"magic_k0", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
