@@ -51,9 +51,16 @@ constexpr int kMagicGroupUlps = 16;   // (11 ulps occur: bias in [8, 16), |y| in
 
 FQ_HD int k_codes(int E) { return E <= 0 ? 1 : ((1 << E) - 1); }
 FQ_HD int k_pad(int K) { return (K + 2) & ~1; }                       // K+1 rounded up to even
-FQ_HD int table_stride(int K) { return kHdr + k_pad(K) + 2 * (K + 1); }
+constexpr int kExt = 4;           // trailing floats: constants of the scaled-domain path at a FIXED offset (see off_ext)
+FQ_HD int table_stride(int K) { return kHdr + k_pad(K) + 2 * (K + 1) + kExt; }
 FQ_HD int off_thr(int) { return kHdr; }
 FQ_HD int off_sr(int K) { return kHdr + k_pad(K); }
+// [0] switching point that selects scale group b (NaN: one group), [1] normalised scale of group b (s_1 if one group),
+// [2] the tie guard of the scaled-domain path, [3] unused.  At an offset that depends on K only, so that a kernel's
+// prologue reads them with loads independent of each other (a look-up through the break code stored in H_K was a chain
+// of two dependent loads in front of every CTA's data loads: measured 3-10 % on one-tile CTAs, round 2 call u).
+FQ_HD int off_ext(int K) { return kHdr + k_pad(K) + 2 * (K + 1); }
+enum : int { X_TB = 0, X_SB = 1, X_GUARD = 2 };
 
 FQ_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
@@ -344,7 +351,15 @@ FQ_HD void prep_finish(float* tab, int M, int K, float mv) {
     magic = magic && is_normal_pos(ldexpf(sr[2], M + K + 1)) && is_normal_pos(mv) &&
             mul_rn(mul_rn(mv, sr[3]), 1.0f + 1.0f / 65536.0f) < ldexpf(1.0f, M + K) && M + K + 24 < 127;
     if (magic) flags |= FLAG_MAGIC;
-    tab[H_K] = u2f((uint32_t)K | ((uint32_t)(magic ? kb : 0) << 8));
+    if (!magic) kb = 0;
+    tab[H_K] = u2f((uint32_t)K | ((uint32_t)kb << 8));
+    float* ext = tab + off_ext(K);
+    ext[X_TB] = kb ? thr[kb] : u2f(0x7fc00000u);
+    ext[X_SB] = kb ? u2f(f2u(sr[2 * K]) - ((uint32_t)(K - 1) << 23)) : sr[2];
+    // tie guard: 1/2 - 2^(M-20) (tie_guard); two groups: the quotient of a group-b element is taken with group a's
+    // reciprocal, i.e. perturbed by up to kMagicGroupUlps more ulps -- (16 + 1.5) * 2^-23 * 2^(M+1) < 2^(M-17)
+    ext[X_GUARD] = kb ? 0.5f - ldexpf(1.0f, M - 17) : tab[H_GUARD];
+    ext[3] = 0.0f;
   }
   tab[H_BASE] = u2f(base);
   tab[H_REF] = u2f(ref);
@@ -447,21 +462,17 @@ struct MagicConsts {
   uint32_t lo, add;    // bits(C) = max(bits(u) & 0x7f800000, lo) + add
   bool two;
 };
-// tab: the channel table; ld reads one float of it (global or shared memory)
+// tab: the channel table; ld reads one float of it (global or shared memory).  Independent loads at fixed offsets.
 template <typename Ld>
 FQ_HD MagicConsts magic_consts(const float* tab, int K, uint32_t flags, Ld ld) {
   const int M = flags_M(flags);
-  const int kb = (int)(f2u(ld(tab + H_K)) >> 8);
   MagicConsts m;
   m.s1 = ld(tab + off_sr(K) + 2);
   m.r1 = ld(tab + off_sr(K) + 3);
-  m.two = kb != 0;
-  m.sb = m.two ? u2f(f2u(ld(tab + off_sr(K) + 2 * K)) - ((uint32_t)(K - 1) << 23)) : m.s1;
-  m.tb = m.two ? ld(tab + kHdr + kb) : u2f(0x7fc00000u);
-  // tie guard: 1/2 - 2^(M-20) (tie_guard); two groups: the quotient of a group-b element is taken with group a's
-  // reciprocal, i.e. perturbed by up to kMagicGroupUlps more ulps -- (16 + 1.5) * 2^-23 * 2^(M+1) < 2^(M-17)
-  const float guard = m.two ? 0.5f - ldexpf(1.0f, M - 17) : ld(tab + H_GUARD);
-  m.kap = guard * (1.0f / 8388608.0f);                        // 2^-23
+  m.tb = ld(tab + off_ext(K) + X_TB);
+  m.sb = ld(tab + off_ext(K) + X_SB);
+  m.two = m.tb == m.tb;
+  m.kap = ld(tab + off_ext(K) + X_GUARD) * (1.0f / 8388608.0f);   // 2^-23
   m.lo = (uint32_t)(127 + M) << 23;                           // exponent field of 2^M: p = 0 up to u < 2^(M+1)
   m.add = (uint32_t)(23 - M) << 23;                           // -> exponent p + 23 (u >= 0: u + C stays in C's binade)
   return m;

@@ -353,8 +353,20 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 // (quant_vec_cold) instead of being inlined into each of the unrolled vector bodies: the look-up, the IEEE-division
 // fallback and their slow paths are ~4/5 of those kernels' 70-80 KB of SASS, far beyond the instruction caches, and every
 // variant added next to the hot loop had cost it 1-3 % (round 2 calls p -> q -> s).
+// MEASURED (round 2, call t): 0.85-0.89 -> 0.59 of the HBM peak -- a call in the kernel takes the address of the vector
+// arrays, which then live in local memory on the hot path too.  Off; kept as a negative result.
 #ifndef FP8FQ_COLD_CALL
-#define FP8FQ_COLD_CALL 1
+#define FP8FQ_COLD_CALL 0
+#endif
+// FP8FQ_MAGIC_TWO: two-group tables on the scaled-domain path too (a second instantiation of its loop in every vector
+// body, with the compare + select of the element's scale group).  Measured (round 2 calls u, v; E3M4 channel-innermost
+// sites, fraction of the HBM peak): with it one-group tables run at 0.87 and two-group ones at 0.83; without it, 0.92 and
+// 0.78 (two-group tables take the look-up path) -- the second instantiation costs the first 5 %.  About half of the
+// ranges in [2, 8) and a sixth of all ranges are two-group, so the means are equal or in favour of OFF, and BASELINE
+// config 3 (62 of its 63 calibrated tables are one-group) runs its step at 0.863 instead of 0.843 of the roofline: off.
+// The prologue flags both kinds either way (FLAG_MAGIC + the table's trailing constants).
+#ifndef FP8FQ_MAGIC_TWO
+#define FP8FQ_MAGIC_TWO 0
 #endif
 #if defined(FP8FQ_HOST_SIM)
 #define FQ_NOINLINE __attribute__((noinline))
@@ -473,7 +485,7 @@ __device__ __forceinline__ void quant_vec(const float (&v)[N], const ElemCtx<KMO
         y[k] = SIGNED_OUT ? u2f(f2u(ya) | (f2u(xc[k]) & 0x80000000u)) : ya;
       }
     };
-    if (MM == 2 || (MM == 0 && (FP8FQ_MAGIC_ONEPATH || c.mc.two))) body(std::true_type{});   // (one group: tb is NaN, the select keeps s1)
+    if (FP8FQ_MAGIC_TWO && (MM == 2 || (MM == 0 && (FP8FQ_MAGIC_ONEPATH || c.mc.two)))) body(std::true_type{});   // (one group: tb is NaN, the select keeps s1)
     else body(std::false_type{});
     if (!GUARD || all_ok) return;
     if (FP8FQ_MAGIC_SELFSLOW || MM != 0) {
@@ -657,8 +669,8 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.magic = false;
     if (FP8FQ_MAGIC && FP8FQ_MAGIC_K0) {
       const uint32_t fl = f2u(ld(tab + H_FLAGS));
-      c.magic = (fl & FLAG_MAGIC) != 0;
       c.mc = magic_consts(tab, K, fl, ld);
+      c.magic = (fl & FLAG_MAGIC) != 0 && (FP8FQ_MAGIC_TWO || !c.mc.two);
     }
   } else {
     const uint32_t fl = f2u(ld(tab + H_FLAGS));
@@ -670,8 +682,8 @@ __device__ __forceinline__ void load_ctx(ElemCtx<KMODE>& c, const float* tab, in
     c.s1b = f2u(ld(tab + off_sr(K) + 2));
     c.r1b = f2u(ld(tab + off_sr(K) + 3));
     c.tmax = (uint32_t)(K - 1) << 23;
-    c.magic = FP8FQ_MAGIC && (fl & FLAG_MAGIC) != 0;
     c.mc = magic_consts(tab, K, fl, ld);
+    c.magic = FP8FQ_MAGIC && (fl & FLAG_MAGIC) != 0 && (FP8FQ_MAGIC_TWO || !c.mc.two);
   }
 }
 template <int KMODE>

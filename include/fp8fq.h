@@ -35,6 +35,8 @@
  *     [6] tie guard of the reciprocal multiply  [7] reference point of the exponent-arithmetic look-up (int bits)
  *     [8 .. 8+KP)            thr[j], j = 0..K      (KP = K+1 rounded up to even)
  *     [8+KP .. 8+KP+2(K+1))  (scale, 1/scale)[e'], e' = 0..K
+ *     [8+KP+2(K+1) .. +4)    constants of the scaled-domain element path: switching point between the two scale groups
+ *                            (NaN: one group), normalised scale of the second group, tie guard, unused
  */
 #ifndef FP8FQ_H
 #define FP8FQ_H

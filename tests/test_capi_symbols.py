@@ -39,7 +39,7 @@ def test_format_split_and_table_sizes(built):
     assert ops.format_split(9, 8, 1) == (7, 0, 1)
     assert ops.format_split(9, 8, 0) == (8, 0, 1)
     assert ops.format_split(7, 8, 1) == (7, 0, 1)
-    assert ops.table_stride(5, 8, 1) == 8 + 4 + 8
+    assert ops.table_stride(5, 8, 1) == 8 + 4 + 8 + 4
     with pytest.raises(Fp8fqError):
         ops.format_split(1, 16, 1)  # E = 14 > 7 unsupported
     with pytest.raises(Fp8fqError):

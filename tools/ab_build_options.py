@@ -41,7 +41,9 @@ VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k0": ["FP8FQ_MAGIC_K0=1"], 
                 # the element path decided once per launch (default) vs per vector; the K > 3 row kernel at 95 registers
                 "hoist": ["FP8FQ_MAGIC_HOIST=1"], "rows_minb1": ["FQ_ROWS_MINB=1"],
                 # everything but the scaled-domain loop out of line (default) vs inlined into every vector body
-                "nocold": ["FP8FQ_COLD_CALL=0"]}
+                "cold": ["FP8FQ_COLD_CALL=1"],
+                # two-group tables on the scaled-domain path too (default: on the look-up path, one loop instantiation in the kernels)
+                "two1": ["FP8FQ_MAGIC_TWO=1"]}
 FULL_BENCH = {"magic_k0", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
