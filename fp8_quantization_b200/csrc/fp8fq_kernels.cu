@@ -1031,13 +1031,15 @@ struct RowsArgs {
 // took 27.0 us.
 constexpr int kRowsWarpChunk = 1024;
 constexpr int kRowsWarps = 4;
-// FQ_ROWS_MINB: resident CTAs per SM the row kernel is compiled for (6 x 128 threads -> at most 80 registers; the K > 3
-// instantiation with both element paths inlined would otherwise take 95)
+// FQ_ROWS_MINB: resident CTAs per SM the K > 3 row kernel is compiled for (6 x 128 threads -> at most 80 registers; with
+// both element paths inlined it would otherwise take 95: MobileNetV2's 53-tensor weight call 29.1 -> 23.2 us).  The other
+// instantiations keep the 7 CTAs of their 71 registers (stating a minimum of 1 made ptxas spend 80: 18.7 -> 20.7 us on
+// ResNet-18's weight call)
 #ifndef FQ_ROWS_MINB
 #define FQ_ROWS_MINB 6
 #endif
 template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(kRowsWarps * 32, KMODE == 1 ? FQ_ROWS_MINB : 1) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__(kRowsWarps * 32, KMODE == 1 ? FQ_ROWS_MINB : 7) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
