@@ -998,7 +998,7 @@ def _main():
         achieved = st["stream_bytes"] / (k_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
-            for tag in ("r02", "r01"):   # the newest summary that exists
+            for tag in ("r02w", "r02", "r01"):   # the newest summary that exists
                 pth = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.json")
                 if os.path.exists(pth):
                     traffic = json.load(open(pth))["by_memory_format"][args.memory_format]["fq_stream_kernel_dram_bytes_per_launch"]

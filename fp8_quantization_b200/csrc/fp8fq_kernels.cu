@@ -1032,14 +1032,25 @@ struct RowsArgs {
 constexpr int kRowsWarpChunk = 1024;
 constexpr int kRowsWarps = 4;
 // FQ_ROWS_MINB: resident CTAs per SM the K > 3 row kernel is compiled for (6 x 128 threads -> at most 80 registers; with
-// both element paths inlined it would otherwise take 95: MobileNetV2's 53-tensor weight call 29.1 -> 23.2 us).  The other
-// instantiations keep the 7 CTAs of their 71 registers (stating a minimum of 1 made ptxas spend 80: 18.7 -> 20.7 us on
-// ResNet-18's weight call)
+// both element paths inlined it would otherwise take 95: MobileNetV2's 53-tensor weight call 29.1 -> 23.2 us)
 #ifndef FQ_ROWS_MINB
 #define FQ_ROWS_MINB 6
 #endif
 template <int KMODE, bool CODES>
-__global__ void __launch_bounds__(kRowsWarps * 32, KMODE == 1 ? FQ_ROWS_MINB : 7) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+__device__ __forceinline__ void fq_rows_body(const RowsArgs& a);
+// (two entry points because a launch bound cannot be left out per instantiation: the K <= 3 / INT row kernels keep the
+// unconstrained 71 registers of round 1 -- any stated minimum, even one their 71 registers satisfy, made ResNet-18's
+// weight call 2 us slower)
+template <int KMODE, bool CODES>
+__global__ void __launch_bounds__(kRowsWarps * 32) fq_rows_kernel(const __grid_constant__ RowsArgs a) {
+  fq_rows_body<KMODE, CODES>(a);
+}
+template <int KMODE, bool CODES>
+__global__ void __launch_bounds__(kRowsWarps * 32, FQ_ROWS_MINB) fq_rows_kernel_k1(const __grid_constant__ RowsArgs a) {
+  fq_rows_body<KMODE, CODES>(a);
+}
+template <int KMODE, bool CODES>
+__device__ __forceinline__ void fq_rows_body(const RowsArgs& a) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
@@ -2021,8 +2032,8 @@ static int launch_rows(const fp8fq_tensor_desc* d, int32_t* codes0, int count, i
     if (codes) launch_kernel(fq_rows_kernel<0, true>, g, b, 0, st, a);
     else launch_kernel(fq_rows_kernel<0, false>, g, b, 0, st, a);
   } else {
-    if (codes) launch_kernel(fq_rows_kernel<1, true>, g, b, 0, st, a);
-    else launch_kernel(fq_rows_kernel<1, false>, g, b, 0, st, a);
+    if (codes) launch_kernel(fq_rows_kernel_k1<1, true>, g, b, 0, st, a);
+    else launch_kernel(fq_rows_kernel_k1<1, false>, g, b, 0, st, a);
   }
   return launch_status();
 }
