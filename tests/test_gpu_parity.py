@@ -324,3 +324,60 @@ def test_survey_size_mse_estimator_vs_reference_golden():
             row = ref_mses[bi, :, c]
             assert row[gi] <= row.min() * (1 + 3e-4), (key, c)
         assert (ours == ref_mx.reshape(-1)).mean() >= 0.95
+
+
+@pytest.mark.parametrize("M,sb", [(4, 1), (3, 1), (2, 1), (4, 0), (1, 1)])
+def test_scaled_domain_path_equals_the_reference_on_the_gpu(M, sb):
+    """The K > 3 element path of the default build (|xc| / s_1 rounded by adding and subtracting a
+    power of two; csrc/fp8fq_core.h quant_magic) on the tables the DEVICE prologue builds with libdevice's log2f / powf:
+    over a sweep of 48 ranges -- one-group tables (scaled-domain path), two-group ones and whatever else the prologue
+    finds (look-up path) -- the plain, the per-channel and the fused BN + ReLU6 kernels return the bits of the
+    reference's ATen op sequence run on the same GPU, for random values, every float within +-3 ulps of every binade
+    edge of the range (the code boundaries), rounding ties of both parities, +-0, denormals, NaN and infinities."""
+    from fp8_quantization_b200 import ops
+
+    g = torch.Generator().manual_seed(400 + 10 * M + sb)
+    mvs = torch.exp(torch.empty(48).uniform_(float(np.log(0.02)), float(np.log(60.0)), generator=g))
+    kinds = {"scaled_one_group": 0, "scaled_two_groups": 0, "look_up": 0}
+    mb_d = torch.tensor([float(M)], device=DEV)
+    n = 1 << 15
+    for mvv in mvs.tolist():
+        mv = torch.tensor([mvv])
+        x = torch.randn(n, generator=g) * mvv * 0.6
+        edges = mvv * 2.0 ** -torch.arange(0, 40, dtype=torch.float32)
+        pts = [edges]
+        for d in (1, 2, 3):
+            pts += [(edges.view(torch.int32) + d).view(torch.float32), (edges.view(torch.int32) - d).view(torch.float32)]
+        pts += [edges * 1.5, edges * 0.75, edges * (1 + 2.0 ** -(M + 1)), edges * (1 + 3 * 2.0 ** -(M + 1))]
+        pts = torch.cat(pts)
+        x[:pts.numel()] = pts
+        x[pts.numel():2 * pts.numel()] = -pts
+        x[2 * pts.numel():2 * pts.numel() + 8] = torch.tensor([0.0, -0.0, float("nan"), float("inf"), -float("inf"), 1e-38,
+                                                                  -1e-45, 3e38])
+        xd = x.to(DEV)
+        q = make_quantizer(M, sb, False, mv)
+        tab, _ = q.table_for(xd)
+        ti = tab.view(torch.int32)
+        magic, two = bool(int(ti[4]) & 16), (int(ti[5]) >> 8) != 0
+        kinds["look_up" if not magic else ("scaled_two_groups" if two else "scaled_one_group")] += 1
+        ref = O.fake_quant(xd, 8, mv.to(DEV), mb_d, sb)
+        y = q(xd)
+        assert bool(((bits(y) == bits(ref)) | (torch.isnan(y) & torch.isnan(ref))).all()), (M, sb, mvv, magic, two)
+        # fused BN (identity parameters) + ReLU6 + quantiser, channel-innermost and NCHW, against the same composition
+        C = 8
+        xb = xd[: (n // (C * 16)) * C * 16].reshape(-1, C, 4, 4).contiguous()
+        pk = ops.bn_pack(torch.zeros(C, device=DEV), torch.ones(C, device=DEV) - 1e-5, None, None, 1e-5)
+        refb = O.fake_quant(torch.clamp(torch.nn.functional.batch_norm(xb, torch.zeros(C, device=DEV),
+                                                                       torch.ones(C, device=DEV) - 1e-5, None, None, False,
+                                                                       0.0, 1e-5), 0.0, 6.0), 8, mv.to(DEV), mb_d, sb)
+        for fmt in (torch.contiguous_format, torch.channels_last):
+            yb = ops.bn_act_quant(xb.contiguous(memory_format=fmt), pk, None, ops.ACT_RELU6, tab, float(M), 8, sb, bn_mode=1)
+            assert bool(((bits(yb.contiguous()) == bits(refb)) | (torch.isnan(yb) & torch.isnan(refb))).all()), (M, sb, mvv, fmt)
+    assert kinds["scaled_one_group"] >= 10, kinds
+    # per channel: rows of all kinds in one launch of the row kernel
+    Cw, inner = 48, 520
+    xw = torch.randn(Cw, inner, generator=g) * mvs[:, None] * 0.6
+    qw = make_quantizer(M, sb, True, mvs)
+    refw = O.fake_quant(xw.to(DEV), 8, mvs.to(DEV), mb_d, sb)
+    yw = qw(xw.to(DEV))
+    assert torch.equal(bits(yw), bits(refw))
