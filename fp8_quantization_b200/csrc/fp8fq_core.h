@@ -41,7 +41,7 @@ constexpr int kMaxK = (1 << kMaxE) - 1;
 enum : int { H_HI = 0, H_LO = 1, H_BASE = 2, H_BIAS = 3, H_FLAGS = 4, H_K = 5, H_GUARD = 6, H_REF = 7 };
 // flags = FLAG_* | (band field << BAND_SHIFT) | (M << M_SHIFT); band field = band (< 2^20 - 1), or kBandMask for
 // "every mantissa is ambiguous" (band = 0x7fffff); M <= kMaxM < 16
-enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8, FLAG_MAGIC = 16, BAND_SHIFT = 8,
+enum : int { FLAG_IRREGULAR = 1, FLAG_POW2 = 2, FLAG_RSNAN = 4, FLAG_SDOUBLE = 8, FLAG_MAGIC = 16, FLAG_TWO = 32, BAND_SHIFT = 8,
              M_SHIFT = 28 };
 constexpr uint32_t kBandMask = 0xfffffu;
 // FLAG_MAGIC: how far (ulps) a switching point T_k may sit from its ideal position s_k * 2^M (see prep_finish)
@@ -352,6 +352,7 @@ FQ_HD void prep_finish(float* tab, int M, int K, float mv) {
             mul_rn(mul_rn(mv, sr[3]), 1.0f + 1.0f / 65536.0f) < ldexpf(1.0f, M + K) && M + K + 24 < 127;
     if (magic) flags |= FLAG_MAGIC;
     if (!magic) kb = 0;
+    if (kb) flags |= FLAG_TWO;   // (a bit of the flags word: the kernels branch on it with a uniform predicate)
     tab[H_K] = u2f((uint32_t)K | ((uint32_t)kb << 8));
     float* ext = tab + off_ext(K);
     ext[X_TB] = kb ? thr[kb] : u2f(0x7fc00000u);
@@ -471,7 +472,7 @@ FQ_HD MagicConsts magic_consts(const float* tab, int K, uint32_t flags, Ld ld) {
   m.r1 = ld(tab + off_sr(K) + 3);
   m.tb = ld(tab + off_ext(K) + X_TB);
   m.sb = ld(tab + off_ext(K) + X_SB);
-  m.two = m.tb == m.tb;
+  m.two = (flags & FLAG_TWO) != 0;
   m.kap = ld(tab + off_ext(K) + X_GUARD) * (1.0f / 8388608.0f);   // 2^-23
   m.lo = (uint32_t)(127 + M) << 23;                           // exponent field of 2^M: p = 0 up to u < 2^(M+1)
   m.add = (uint32_t)(23 - M) << 23;                           // -> exponent p + 23 (u >= 0: u + C stays in C's binade)

@@ -358,15 +358,16 @@ __device__ __forceinline__ void pin_vreg(float& v, const float* src) {
 #ifndef FP8FQ_COLD_CALL
 #define FP8FQ_COLD_CALL 0
 #endif
-// FP8FQ_MAGIC_TWO: two-group tables on the scaled-domain path too (a second instantiation of its loop in every vector
-// body, with the compare + select of the element's scale group).  Measured (round 2 calls u, v; E3M4 channel-innermost
-// sites, fraction of the HBM peak): with it one-group tables run at 0.87 and two-group ones at 0.83; without it, 0.92 and
-// 0.78 (two-group tables take the look-up path) -- the second instantiation costs the first 5 %.  About half of the
-// ranges in [2, 8) and a sixth of all ranges are two-group, so the means are equal or in favour of OFF, and BASELINE
-// config 3 (62 of its 63 calibrated tables are one-group) runs its step at 0.863 instead of 0.843 of the roofline: off.
-// The prologue flags both kinds either way (FLAG_MAGIC + the table's trailing constants).
+// FP8FQ_MAGIC_TWO (default ON): two-group tables on the scaled-domain path too -- a second instantiation of its loop in
+// every vector body, with the compare + select of the element's scale group, chosen by a uniform branch on a bit of the
+// table's flags word.  Measured (round 2, E3M4 channel-innermost sites, mean fraction of the HBM peak): one-group tables
+// 0.920 -> 0.904, two-group ones 0.779 (look-up path) -> 0.869; BASELINE config 3 with random-init weights (62 of its 63
+// calibrated tables are one-group) 0.865 -> 0.854.  About half of the ranges in [2, 8) -- a ReLU6 network saturating at
+// maxval = 6 -- and a sixth of all ranges are two-group, so ON is the better or equal choice everywhere but on that
+// synthetic workload.  (The first version branched on a bool derived from a float compare, which ptxas re-evaluated
+// per vector in vector registers: +14 instructions per vector, one-group tables at 0.87 -- calls u, v.)
 #ifndef FP8FQ_MAGIC_TWO
-#define FP8FQ_MAGIC_TWO 0
+#define FP8FQ_MAGIC_TWO 1
 #endif
 #if defined(FP8FQ_HOST_SIM)
 #define FQ_NOINLINE __attribute__((noinline))

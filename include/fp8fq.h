@@ -29,7 +29,8 @@
  *   streaming kernels.  Layout (floats, per channel, stride = fp8fq_table_stride(...)):
  *     [0] maxval  [1] minval  [2] bucket base (int bits)  [3] bias
  *     [4] flags (int bits): bit 0 irregular thresholds, 1 all scales exact powers of two, 2 an unusable reciprocal,
- *         3 scales exact doublings of each other, 4 qualifies for the scaled-domain element path; bits 8..27 mantissa
+ *         3 scales exact doublings of each other, 4 qualifies for the scaled-domain element path, 5 ... with two scale groups;
+ *         bits 8..27 mantissa
  *         band of the exponent-arithmetic look-up (0xfffff = every mantissa); bits 28..31 M
  *     [5] K (int bits, low 8) | last code of the first scale group of a two-group table << 8 (0: one group)
  *     [6] tie guard of the reciprocal multiply  [7] reference point of the exponent-arithmetic look-up (int bits)

@@ -395,7 +395,7 @@ def test_add_act_quant_equals_composition(sim, ref):
                     assert same_bits(y, ref_quant(ref, v.astype(np.float32), mv, M)[0]), (M, n, off, act)
 
 
-@pytest.mark.parametrize("variant", ["nofoldact", "nofulltile", "fulltilecl", "magicopts", "magictwo"])
+@pytest.mark.parametrize("variant", ["nofoldact", "nofulltile", "fulltilecl", "magicopts", "magicone"])
 def test_build_options_are_bit_identical_to_the_default_build(sim, variant):
     """The product's build options (csrc/fp8fq_kernels.cu) -- FP8FQ_FOLD_ACT: ReLU / ReLU6 folded into the quantiser's
     clamp bounds; FP8FQ_FULL_TILE: a second, predicate-free instantiation of the stream kernel's tile body for full
@@ -404,7 +404,7 @@ def test_build_options_are_bit_identical_to_the_default_build(sim, variant):
     (+ the PACK2 / PIN_SEL code paths, which the host build evaluates with scalar arithmetic; this build has the
     scaled-domain element path FP8FQ_MAGIC off); "magicopts": that path with its three options flipped (K <= 3 formats on
     it too, two-group tables on it, one loop for one- and two-group tables, tie-guard lanes finished by a division inside the
-    path); "magictwo": the default build with two-group tables on that path (FP8FQ_MAGIC_TWO) --
+    path); "magicone": the default build with two-group tables on the look-up path (FP8FQ_MAGIC_TWO=0) --
     against the default build, bit for bit, on inputs made of the cases the equivalence has to survive: +-0 (identity
     batch norm: scale 1, shift -0.0, so that -0.0 reaches the activation), +-inf, NaN, values around 0 / 6 / maxval,
     ranges below and above 6, zero / inf / NaN ranges, signed and unsigned formats, K <= 3 and K > 3, all three fused
@@ -868,7 +868,7 @@ def test_simulated_kernels_against_the_real_reference_golden_vectors(sim):
 
 
 @pytest.mark.parametrize("M,sb", [(4, 1), (3, 1), (2, 1), (4, 0), (1, 1)])
-@pytest.mark.parametrize("which", ["sdouble", "magic", "magicopts", "magictwo"])
+@pytest.mark.parametrize("which", ["sdouble", "magic", "magicopts", "magicone"])
 def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact(built, ref, M, sb, which):
     """which = "magic": the DEFAULT build -- tables with FLAG_MAGIC run the element path in the scaled domain
     (quant_magic: add-and-subtract rounding of |xc| / s_1, no look-up at all), the others the look-up; both kinds must
@@ -883,7 +883,7 @@ def test_exact_doubling_scale_tables_take_the_arithmetic_path_and_stay_bit_exact
 
     sim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build",
                                    {"sdouble": "libfp8fq_sim_fulltilecl.so", "magic": "libfp8fq_sim.so",
-                                    "magicopts": "libfp8fq_sim_magicopts.so", "magictwo": "libfp8fq_sim_magictwo.so"}[which]))
+                                    "magicopts": "libfp8fq_sim_magicopts.so", "magicone": "libfp8fq_sim_magicone.so"}[which]))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(sim, name)
         fn.restype, fn.argtypes = res, args

@@ -42,8 +42,8 @@ VARIANTS_R2D = {"nomagic": ["FP8FQ_MAGIC=0"], "magic_k0": ["FP8FQ_MAGIC_K0=1"], 
                 "hoist": ["FP8FQ_MAGIC_HOIST=1"], "rows_minb1": ["FQ_ROWS_MINB=1"],
                 # everything but the scaled-domain loop out of line (default) vs inlined into every vector body
                 "cold": ["FP8FQ_COLD_CALL=1"],
-                # two-group tables on the scaled-domain path too (default: on the look-up path, one loop instantiation in the kernels)
-                "two1": ["FP8FQ_MAGIC_TWO=1"]}
+                # two-group tables on the look-up path (one instantiation of the scaled-domain loop in the kernels; default: both)
+                "two0": ["FP8FQ_MAGIC_TWO=0"]}
 FULL_BENCH = {"magic_k0", "cl5", "cl6_dyn", "default", "pin_pack", "full_cl_minb4", "all"}   # the others: kernel-level timings only
 
 
