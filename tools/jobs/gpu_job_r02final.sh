@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 final verification: GPU tests, smoke(), bench (both layouts + reference arm), launch list, ncu full summaries, site shapes.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02final_pytest.log 2>&1; echo "pytest rc=$?"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02final_smoke.log 2>&1; echo "smoke rc=$?"

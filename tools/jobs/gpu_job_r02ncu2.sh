@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu of the same one-group E3M4 launches in the default build and in the build that also carries the two-group loop
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 for v in default two1; do
   if [ $v = default ]; then unset FP8FQ_LIB; else export FP8FQ_LIB=$PWD/build_variants/libfp8fq_$v.so; fi

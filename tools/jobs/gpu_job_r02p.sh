@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU job "p": tests, A/B of the scaled-domain element path (FP8FQ_MAGIC), channel-innermost shapes, MSE, bench, ncu.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02p_pytest.log 2>&1; echo "pytest rc=$?"
 timeout 900 python tools/ab_build_options.py --only nomagic > gpurun_out/r02p_ab.log 2>&1; echo "ab rc=$?"

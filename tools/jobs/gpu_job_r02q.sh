@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU job "q" (two-group scale tables and K <= 3 formats on the scaled-domain path): tests, A/B of the scaled-domain element path (FP8FQ_MAGIC), channel-innermost shapes, MSE, bench, ncu.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02q_pytest.log 2>&1; echo "pytest rc=$?"
 timeout 1200 python tools/ab_build_options.py --only nomagic,magic_k1 > gpurun_out/r02q_ab.log 2>&1; echo "ab rc=$?"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU job "r": A/B of the options of the scaled-domain path (one loop instantiation, self-contained tie-guard lanes).
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 timeout 1500 python tools/ab_build_options.py --only nomagic,onepath,selfslow,onepath_selfslow > gpurun_out/r02r_ab.log 2>&1; echo "ab rc=$?"
 cp gpurun_out/ab_build_options.json gpurun_out/ab_build_options_r02r.json

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU job "s": element path decided once per launch (FP8FQ_MAGIC_HOIST) vs per vector; row-kernel registers.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02s_pytest.log 2>&1; echo "pytest rc=$?"
 timeout 1500 python tools/ab_build_options.py --only nomagic,nohoist,rows_minb1 > gpurun_out/r02s_ab.log 2>&1; echo "ab rc=$?"

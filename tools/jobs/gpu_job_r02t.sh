@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU job "t": cold paths out of line (FP8FQ_COLD_CALL) vs inlined.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02t_pytest.log 2>&1; echo "pytest rc=$?"
 timeout 1500 python tools/ab_build_options.py --only nomagic,nocold > gpurun_out/r02t_ab.log 2>&1; echo "ab rc=$?"

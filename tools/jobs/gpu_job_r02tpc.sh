@@ -1,6 +1,6 @@
 #!/bin/bash
 # tiles per CTA for the K > 3 batch-norm kernels (default 1): FP8FQ_TILES_PER_CTA = 2 / 4 on the site shapes and on config 3
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 for t in 0 2 4; do
   if [ $t = 0 ]; then unset FP8FQ_TILES_PER_CTA; else export FP8FQ_TILES_PER_CTA=$t; fi

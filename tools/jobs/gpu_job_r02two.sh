@@ -1,6 +1,6 @@
 #!/bin/bash
 # two-group tables on the scaled-domain path with the group test on a flag bit (uniform branch): two1 vs default
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 for v in default two1; do
   if [ $v = default ]; then unset FP8FQ_LIB; else export FP8FQ_LIB=$PWD/build_variants/libfp8fq_$v.so; fi

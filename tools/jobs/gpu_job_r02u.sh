@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job "u": two-group tables on the scaled-domain path (default) vs on the look-up path (two0) vs one loop (onepath),
 # judged on config 3 itself (MobileNetV2 step + forward) and on the channel-innermost site shapes.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 for v in default two0 onepath; do
   if [ $v = default ]; then unset FP8FQ_LIB; else export FP8FQ_LIB=$PWD/build_variants/libfp8fq_$v.so; fi

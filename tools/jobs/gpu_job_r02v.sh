@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job "v": scaled-domain constants at fixed table offsets (independent prologue loads); default vs two0 vs look-up
 # build on config 3 and the channel-innermost site shapes; GPU tests.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02v_pytest.log 2>&1; echo "pytest rc=$?"
 for v in default two0 nomagic; do
