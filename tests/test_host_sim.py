@@ -335,7 +335,8 @@ NHWC_SHAPES = [
     (200, 4), (300, 8), (77, 256), (33, 1024),
     (14 * 14 * 3, 96),    # MobileNetV2 widths: CTA size fitted to C (240 threads)
     (28 * 28, 144), (100, 24), (50, 192), (20, 384), (30, 576), (9, 960),
-    (7 * 7 * 2, 1280),    # C / 4 > 256 lanes: per-vector channel look-up
+    (7 * 7 * 2, 1280),    # C / 4 = 320 lanes: the fitted 320-thread CTA (round 1: per-vector channel look-up)
+    (6, 2048),            # C / 4 > 320 lanes: per-vector channel look-up
     (5, 2048), (3, 4100),
     (40, 30),             # C % 4 != 0: scalar accesses, 240 threads
     (221, 3), (64, 1), (1000, 10),
