@@ -1871,7 +1871,9 @@ int launch_stream_t(const StreamArgs& a, cudaStream_t st) {
     const int v = e ? atoi(e) : 0;
     return v >= 1 && v <= 64 ? v : 0;
   }();
-  int tpc = tpc_env ? tpc_env : ((kHasBn && KMODE == 0) ? 4 : 1);
+  // (K > 3 formats: 2 tiles per CTA for the fitted-CTA instantiations, whose per-CTA prologue is the longest -- measured
+  // +1.5..5 % at [128,96..576,14..56], -1..2 % for the compile-time-CTA ones; profiles/tiles_per_cta_k1_r02.json)
+  int tpc = tpc_env ? tpc_env : ((kHasBn && KMODE == 0) ? 4 : ((kHasBn && KMODE == 1 && DYN) ? 2 : 1));
   while (tpc > 1 && !tpc_env && ntiles / tpc < (int64_t)sm_count() * 12) tpc >>= 1;
   int64_t grid = (ntiles + tpc - 1) / tpc;
   // FP8FQ_WAVE_GRID=1 (experiment): round the grid up to a whole number of waves (SMs x resident CTAs of this
