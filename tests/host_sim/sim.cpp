@@ -258,7 +258,10 @@ int64_t ctas_run() { return g_ctas; }
 
 extern "C" {
 // test hooks of the simulation (not part of include/fp8fq.h)
-void fp8fq_sim_set_sm_count(int n) { fp8fq_sim::g_sm_count = n; }
+void fp8fq_sim_set_sm_count(int n) {
+  fp8fq_sim::g_sm_count = n;
+  for (auto& c : g_sms) c.store(0);   // the library caches the attribute per device: make it read again
+}
 void fp8fq_sim_report_pinned(int yes) { fp8fq_sim::g_report_pinned = yes != 0; }
 int64_t fp8fq_sim_launches(void) { return fp8fq_sim::launches(); }
 int64_t fp8fq_sim_ctas(void) { return fp8fq_sim::ctas_run(); }

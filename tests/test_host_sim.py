@@ -376,6 +376,54 @@ def test_bn_act_quant_and_block_tail_channel_innermost(sim, ref, shape, mode):
         assert same_bits(y, ref_quant(ref, v.astype(np.float32), mvo, Mo)[0]), (shape, mode, Mi, Mo, act, off)
 
 
+def test_several_tiles_per_cta_strided_tile_loop(sim, ref):
+    """The launcher gives the batch-norm kernels several tiles per CTA (4 for K <= 3 formats, 2 for the fitted-CTA K > 3
+    instantiations) as long as >= 12 waves of CTAs remain -- on 148 SMs that needs tens of millions of elements.  With the
+    simulated SM count set to 1 the same rule applies at test sizes: the grid is smaller than the tile count and every
+    CTA strides over its tiles, incl. a partial last tile, in both layouts and for both element paths."""
+    sim.fp8fq_sim_set_sm_count.argtypes = [ctypes.c_int]
+    sim.fp8fq_sim_set_sm_count.restype = None
+    sim.fp8fq_sim_ctas.restype = ctypes.c_int64
+    rng = np.random.default_rng(77)
+    try:
+        sim.fp8fq_sim_set_sm_count(1)
+        # the rule is in force: [1100, 96] with M = 4 is 34 tiles of 192 x 16 elements on 17 CTAs
+        x, y = aligned(1100 * 96), aligned(1100 * 96)
+        x[:] = rand(rng, x.size)
+        p0, p1 = bn_params(sim, rng, 96, 1)
+        c0 = sim.fp8fq_sim_ctas()
+        assert sim.fp8fq_bn_act_quant_nhwc_f32(P(x), P(y), P(p0), P(p1), 1100, 96, ACT_RELU6, 1,
+                                               P(table_for(sim, np.array([3.0], np.float32), 4)), 4, 8, 1, None) == 0
+        assert sim.fp8fq_sim_ctas() - c0 == 1 + 18, sim.fp8fq_sim_ctas() - c0   # (1 CTA of the table prologue)
+        for (pixels, C) in ((1100, 96), (700, 144), (650, 64)):       # 34 / 25 / 10 tiles: fitted CTA (192, 252) and 256
+            n = pixels * C
+            for mode in (0, 1):
+                p0, p1 = bn_params(sim, rng, C, mode)
+                for M, act, mvv in ((4, ACT_RELU6, 3.0), (4, ACT_RELU, 4.0), (5, ACT_RELU, 3.0)):
+                    x, y = aligned(n), aligned(n)
+                    x[:] = rand(rng, n)
+                    mv = np.array([mvv], np.float32)
+                    tab = table_for(sim, mv, M)
+                    assert sim.fp8fq_bn_act_quant_nhwc_f32(P(x), P(y), P(p0), P(p1), pixels, C, act, mode, P(tab), M, 8, 1,
+                                                           None) == 0
+                    v = ref_bn_act(ref, x, 1, C, 1, mode, p0, p1, act)
+                    assert same_bits(y, ref_quant(ref, v, mv, M)[0]), (pixels, C, mode, M, act)
+        # NCHW: [N * C rows, hw], 4 tiles per CTA for M = 5
+        N, C, hw = 6, 16, 2052
+        n = N * C * hw
+        p0, p1 = bn_params(sim, rng, C, 1)
+        for M, act in ((5, ACT_RELU), (4, ACT_RELU6)):
+            x, y = aligned(n), aligned(n)
+            x[:] = rand(rng, n)
+            mv = np.array([3.0], np.float32)
+            tab = table_for(sim, mv, M)
+            assert sim.fp8fq_bn_act_quant_f32(P(x), P(y), P(p0), P(p1), N * C, hw, C, act, 1, P(tab), M, 8, 1, None) == 0
+            v = ref_bn_act(ref, x, hw, C, 0, 1, p0, p1, act)
+            assert same_bits(y, ref_quant(ref, v, mv, M)[0]), (M, act)
+    finally:
+        sim.fp8fq_sim_set_sm_count(148)
+
+
 def test_add_act_quant_equals_composition(sim, ref):
     """fp8fq_add_act_quant_f32 = Q(act(a + b)) (models/resnet_quantized.py:43-46, mobilenet_v2_quantized.py:22-24)."""
     rng = np.random.default_rng(11)
